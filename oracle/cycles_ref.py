@@ -1,0 +1,221 @@
+"""ctypes binding over oracle/_ref/libcycles_ref.so - the REFERENCE's own CPU
+Cycles (BVH2 path) compiled from /root/reference by oracle/Makefile.
+
+TEST INFRASTRUCTURE ONLY.  May be imported by tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs - never by the product
+path (raytracingproject_b200/), which must fail loudly without its CUDA library.
+
+The library is the oracle ("kind": "reference"): scene flattening
+(render/scene.cpp:193-321), BVH2 build (bvh/bvh_build.cpp:370), and the CPU
+kernels (kernel/kernels/cpu/kernel.cpp generic = parity variant,
+kernel_avx2.cpp = speed variant) are the reference's code, unmodified.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libcycles_ref.so")
+
+RAY_DTYPE = np.dtype(
+    [("P", "<f4", 3), ("t", "<f4"), ("D", "<f4", 3), ("visibility", "<u4")], align=False
+)
+HIT_DTYPE = np.dtype(
+    [("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<i4"), ("object", "<i4"), ("type", "<i4")],
+    align=False,
+)
+assert RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 24
+
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError(
+                "%s missing: run `make -C oracle -j8` where /root/reference exists" % LIB_PATH
+            )
+        L = C.CDLL(LIB_PATH, mode=C.RTLD_LOCAL)
+        L.ref_scene_new.restype = C.c_void_p
+        L.ref_scene_new.argtypes = [C.c_char_p, C.c_int, C.c_void_p]
+        L.ref_scene_free.argtypes = [C.c_void_p]
+        L.ref_scene_error.restype = C.c_char_p
+        L.ref_scene_error.argtypes = [C.c_void_p]
+        L.ref_scene_add_mesh.argtypes = [
+            C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+        L.ref_scene_add_object.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_scene_update.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        for f in ("ref_scene_width", "ref_scene_height", "ref_scene_pass_stride"):
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.ref_scene_global.argtypes = [
+            C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+            C.POINTER(C.c_uint32)]
+        L.ref_global_name.restype = C.c_char_p
+        L.ref_global_name.argtypes = [C.c_int]
+        L.ref_scene_data.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.ref_render.argtypes = [
+            C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+        L.ref_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.ref_camera_rays.argtypes = [
+            C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_shadow_rays.argtypes = [
+            C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.ref_init.argtypes = [C.c_int]
+        _lib = L
+    return _lib
+
+
+def global_names():
+    L = lib()
+    out, i = [], 0
+    while True:
+        n = L.ref_global_name(i)
+        if n is None:
+            return out
+        out.append(n.decode())
+        i += 1
+
+
+class RefScene:
+    """One reference Scene bound to the reference CPUDevice (or to an external
+    ccl::Device* - used to drive the B200 device shim through the same Scene)."""
+
+    GENERIC, AVX2 = 0, 1
+
+    def __init__(self, xml_path, kernel=GENERIC, external_device=None, threads=0):
+        L = lib()
+        L.ref_init(int(threads))
+        self._L = L
+        self._h = L.ref_scene_new(os.fsencode(xml_path), int(kernel), external_device)
+        if not self._h:
+            raise RuntimeError("ref_scene_new failed")
+        self.kernel = kernel
+
+    def close(self):
+        if self._h:
+            self._L.ref_scene_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("reference: " + self._L.ref_scene_error(self._h).decode())
+
+    def add_mesh(self, P, tris, shader, smooth=False):
+        P = np.ascontiguousarray(P, dtype=np.float32).reshape(-1, 3)
+        tris = np.ascontiguousarray(tris, dtype=np.int32).reshape(-1, 3)
+        m = self._L.ref_scene_add_mesh(
+            self._h, P.ctypes.data, len(P), tris.ctypes.data, len(tris), shader.encode(),
+            int(smooth))
+        if m < 0:
+            self._check(1)
+        return m
+
+    def add_object(self, mesh, tfm=None):
+        if tfm is None:
+            tfm = np.eye(4, dtype=np.float32)[:3]
+        tfm = np.ascontiguousarray(tfm, dtype=np.float32).reshape(3, 4)
+        o = self._L.ref_scene_add_object(self._h, int(mesh), tfm.ctypes.data)
+        if o < 0:
+            raise RuntimeError("bad mesh handle")
+        return o
+
+    def update(self, width=0, height=0):
+        self._check(self._L.ref_scene_update(self._h, int(width), int(height)))
+
+    @property
+    def width(self):
+        return self._L.ref_scene_width(self._h)
+
+    @property
+    def height(self):
+        return self._L.ref_scene_height(self._h)
+
+    @property
+    def pass_stride(self):
+        return self._L.ref_scene_pass_stride(self._h)
+
+    def kernel_data(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._L.ref_scene_data(self._h, C.byref(p), C.byref(n))
+        return np.ctypeslib.as_array((C.c_uint8 * n.value).from_address(p.value)).copy()
+
+    def global_array(self, name):
+        """Raw bytes of one kernel_textures.h array + its element size."""
+        p, n, es = C.c_void_p(), C.c_uint64(), C.c_uint32()
+        rc = self._L.ref_scene_global(self._h, name.encode(), C.byref(p), C.byref(n), C.byref(es))
+        if rc != 0:
+            raise KeyError(name)
+        nbytes = n.value * es.value
+        if nbytes == 0 or not p.value:
+            return np.zeros(0, dtype=np.uint8), es.value
+        return (
+            np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(p.value)).copy(),
+            es.value,
+        )
+
+    def device_arrays(self):
+        """{name: (bytes, elem_size)} for every non-empty kernel array + '__data'."""
+        out = {}
+        for name in global_names():
+            a, es = self.global_array(name)
+            if a.size:
+                out[name] = (a, es)
+        out["__data"] = (self.kernel_data(), 1)
+        return out
+
+    def render(self, start_sample, num_samples, tile_size=64, accumulate=False):
+        """Film sums, shape (h, w, pass_stride) float32, and the wall seconds."""
+        w, h, ps = self.width, self.height, self.pass_stride
+        out = np.empty((h, w, ps), dtype=np.float32)
+        sec = C.c_double()
+        self._check(self._L.ref_render(
+            self._h, int(start_sample), int(num_samples), int(tile_size), int(accumulate),
+            out.ctypes.data, C.byref(sec)))
+        return out, sec.value
+
+    def intersect(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.empty(len(rays), dtype=HIT_DTYPE)
+        self._check(self._L.ref_intersect(self._h, rays.ctypes.data, hits.ctypes.data, len(rays)))
+        return hits
+
+    def camera_rays(self, sample, x0, y0, w, h):
+        rays = np.empty(w * h, dtype=RAY_DTYPE)
+        hashes = np.empty(w * h, dtype=np.uint32)
+        self._check(self._L.ref_camera_rays(
+            self._h, sample, x0, y0, w, h, rays.ctypes.data, hashes.ctypes.data))
+        return rays, hashes
+
+    def shadow_rays(self, sample, x0, y0, w, h):
+        rays = np.empty(w * h, dtype=RAY_DTYPE)
+        self._check(self._L.ref_shadow_rays(self._h, sample, x0, y0, w, h, rays.ctypes.data))
+        return rays
+
+
+def build_scene(desc, kernel=RefScene.GENERIC, external_device=None, threads=0, tmpdir=None):
+    """Flatten a raytracingproject_b200.scenes.SceneDesc through the reference's
+    own host code; returns the updated RefScene."""
+    import tempfile
+
+    d = tmpdir or tempfile.mkdtemp(prefix="cyref_")
+    path = os.path.join(d, desc.name + ".xml")
+    with open(path, "w") as f:
+        f.write(desc.xml)
+    rs = RefScene(path, kernel=kernel, external_device=external_device, threads=threads)
+    handles = [rs.add_mesh(m.P, m.tris, m.shader, m.smooth) for m in desc.meshes]
+    for mi, tfm in desc.objects:
+        rs.add_object(handles[mi], tfm)
+    rs.update(desc.width, desc.height)
+    return rs

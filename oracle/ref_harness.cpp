@@ -1,0 +1,435 @@
+/* Host-side harness over the REFERENCE's own Scene / Device / DeviceTask API
+ * (intern/cycles/render/scene.h, device/device.h, device/device_task.h),
+ * exported as a small C API for ctypes.  It plays the part Session does in the
+ * reference (render/session.cpp:381-486 acquire_tile, :1053-1121 render) without
+ * the display / tile-manager machinery, so the very same Scene can be driven
+ * either by the reference CPUDevice (the oracle and the CPU baseline) or by an
+ * externally created Device* (the B200 device shim, see
+ * raytracingproject_b200/csrc/device_b200.cpp).
+ *
+ * TEST INFRASTRUCTURE ONLY - part of oracle/_ref/libcycles_ref.so; compiled
+ * from the reference sources where they lie (see oracle/Makefile). */
+
+/* CPUDevice is defined in a .cpp, not a header; include it here (in place, not
+ * copied) so the probe can reach CPUDevice::kernel_globals. */
+#include "device/device_cpu.cpp"
+
+#include "app/cycles_xml.h"
+#include "render/background.h"
+#include "render/buffers.h"
+#include "render/camera.h"
+#include "render/film.h"
+#include "render/integrator.h"
+#include "render/light.h"
+#include "render/mesh.h"
+#include "render/object.h"
+#include "render/scene.h"
+#include "render/shader.h"
+#include "util/util_progress.h"
+#include "util/util_task.h"
+#include "util/util_time.h"
+
+#include <atomic>
+#include <execinfo.h>
+#include <signal.h>
+#include <xmmintrin.h>
+#include <unistd.h>
+#include <cstdio>
+#include <cstring>
+
+#include "ref_probe.h"
+
+using namespace ccl;
+
+/* Only widens access to the per-thread KernelGlobals helpers; every virtual is
+ * CPUDevice's own, so renders through it ARE the unmodified reference device. */
+class ProbeCPUDevice : public CPUDevice {
+ public:
+  ProbeCPUDevice(DeviceInfo &info, Stats &stats, Profiler &profiler, bool background)
+      : CPUDevice(info, stats, profiler, background)
+  {
+  }
+  KernelGlobals kg_init()
+  {
+    return thread_kernel_globals_init();
+  }
+  void kg_free(KernelGlobals *kg)
+  {
+    thread_kernel_globals_free(kg);
+  }
+};
+
+struct ref_scene {
+  Stats stats;
+  Profiler profiler;
+  DeviceInfo info;
+  Device *device;
+  bool own_device;
+  ProbeCPUDevice *cpu; /* NULL for an external device */
+  Scene *scene;
+  Progress progress;
+  RenderBuffers *buffers;
+  vector<Mesh *> meshes;
+  std::string error;
+};
+
+static bool g_sched_init = false;
+
+/* REF_BACKTRACE=1: print a symbolised backtrace on SIGSEGV (no gdb in the image). */
+static void segv_handler(int sig)
+{
+  void *frames[64];
+  int n = backtrace(frames, 64);
+  backtrace_symbols_fd(frames, n, 2);
+  signal(sig, SIG_DFL);
+  raise(sig);
+}
+
+extern "C" {
+
+int ref_version(void)
+{
+  return 2;
+}
+
+/* threads = 0 -> all cores (TaskScheduler::num_threads, util_task.cpp). */
+void ref_init(int threads)
+{
+  if (getenv("REF_BACKTRACE"))
+    signal(SIGSEGV, segv_handler);
+  if (g_sched_init)
+    TaskScheduler::exit();
+  TaskScheduler::init(threads);
+  g_sched_init = true;
+}
+
+int ref_num_threads(void)
+{
+  return TaskScheduler::num_threads();
+}
+
+/* kernel: 0 = generic scalar kernel (parity variant, -ffp-contract=off),
+ *         1 = AVX2 kernel (speed variant).  Selected exactly as the reference
+ *         does, through DebugFlags().cpu (device_cpu.cpp:89-131). */
+ref_scene *ref_scene_new(const char *xml_path, int kernel, void *external_device)
+{
+  if (!g_sched_init)
+    ref_init(0);
+
+  ref_scene *rs = new ref_scene();
+  rs->buffers = NULL;
+  rs->cpu = NULL;
+
+  if (external_device) {
+    rs->device = (Device *)external_device;
+    rs->own_device = false;
+  }
+  else {
+    DebugFlags().cpu.reset();
+    if (kernel == 0) {
+      DebugFlags().cpu.avx2 = false;
+      DebugFlags().cpu.avx = false;
+      DebugFlags().cpu.sse41 = false;
+      DebugFlags().cpu.sse3 = false;
+      DebugFlags().cpu.sse2 = false;
+    }
+    DebugFlags().cpu.bvh_layout = BVH_LAYOUT_BVH2;
+    DebugFlags().cpu.split_kernel = false;
+    vector<DeviceInfo> infos;
+    device_cpu_info(infos);
+    rs->info = infos[0];
+    rs->cpu = new ProbeCPUDevice(rs->info, rs->stats, rs->profiler, true);
+    rs->device = rs->cpu;
+    rs->own_device = true;
+  }
+
+  SceneParams params;
+  params.shadingsystem = SHADINGSYSTEM_SVM;
+  params.bvh_layout = BVH_LAYOUT_BVH2;
+  params.bvh_type = SceneParams::BVH_STATIC;
+  params.use_bvh_spatial_split = false;
+  params.background = true;
+  rs->scene = new Scene(params, rs->device);
+
+  if (xml_path && xml_path[0]) {
+    xml_read_file(rs->scene, xml_path);
+  }
+  return rs;
+}
+
+void ref_scene_free(ref_scene *rs)
+{
+  if (!rs)
+    return;
+  delete rs->buffers;
+  delete rs->scene;
+  if (rs->own_device)
+    delete rs->device;
+  delete rs;
+}
+
+const char *ref_scene_error(ref_scene *rs)
+{
+  return rs->error.c_str();
+}
+
+static Shader *find_shader(Scene *scene, const char *name)
+{
+  foreach (Shader *shader, scene->shaders) {
+    if (shader->name == name)
+      return shader;
+  }
+  return NULL;
+}
+
+/* Adds a triangle mesh (no object yet).  Returns the mesh handle or -1. */
+int ref_scene_add_mesh(ref_scene *rs,
+                       const float *P,
+                       int num_verts,
+                       const int *tris,
+                       int num_tris,
+                       const char *shader_name,
+                       int smooth)
+{
+  Shader *shader = find_shader(rs->scene, shader_name);
+  if (!shader) {
+    rs->error = std::string("unknown shader ") + shader_name;
+    return -1;
+  }
+  Mesh *mesh = new Mesh();
+  rs->scene->geometry.push_back(mesh);
+  mesh->used_shaders.push_back(shader);
+  mesh->reserve_mesh(num_verts, num_tris);
+  for (int i = 0; i < num_verts; i++)
+    mesh->add_vertex(make_float3(P[3 * i], P[3 * i + 1], P[3 * i + 2]));
+  for (int i = 0; i < num_tris; i++)
+    mesh->add_triangle(tris[3 * i], tris[3 * i + 1], tris[3 * i + 2], 0, smooth != 0);
+  rs->meshes.push_back(mesh);
+  return (int)rs->meshes.size() - 1;
+}
+
+/* tfm: 12 floats, row-major 3x4 (ccl::Transform x,y,z rows). */
+int ref_scene_add_object(ref_scene *rs, int mesh, const float *tfm)
+{
+  if (mesh < 0 || mesh >= (int)rs->meshes.size())
+    return -1;
+  Object *object = new Object();
+  object->geometry = rs->meshes[mesh];
+  Transform t;
+  t.x = make_float4(tfm[0], tfm[1], tfm[2], tfm[3]);
+  t.y = make_float4(tfm[4], tfm[5], tfm[6], tfm[7]);
+  t.z = make_float4(tfm[8], tfm[9], tfm[10], tfm[11]);
+  object->tfm = t;
+  rs->scene->objects.push_back(object);
+  return (int)rs->scene->objects.size() - 1;
+}
+
+/* Equivalent of Session::update_scene (session.cpp:909-950). */
+int ref_scene_update(ref_scene *rs, int width, int height)
+{
+  Scene *scene = rs->scene;
+  Camera *cam = scene->camera;
+  if (width > 0 && height > 0 && (width != cam->width || height != cam->height)) {
+    cam->width = width;
+    cam->height = height;
+    cam->full_width = width;
+    cam->full_height = height;
+    cam->compute_auto_viewplane();
+    cam->tag_update();
+  }
+  bool kernel_switch_needed = false;
+  scene->update(rs->progress, kernel_switch_needed);
+  /* session.cpp:282,702 - size the profiler's per-shader / per-object counters. */
+  rs->profiler.reset(scene->shaders.size(), scene->objects.size());
+  if (rs->device->have_error()) {
+    rs->error = rs->device->error_message();
+    return 1;
+  }
+  if (rs->progress.get_error()) {
+    rs->error = rs->progress.get_error_message();
+    return 1;
+  }
+  return 0;
+}
+
+int ref_scene_width(ref_scene *rs)
+{
+  return rs->scene->camera->width;
+}
+int ref_scene_height(ref_scene *rs)
+{
+  return rs->scene->camera->height;
+}
+int ref_scene_pass_stride(ref_scene *rs)
+{
+  return rs->scene->dscene.data.film.pass_stride;
+}
+
+/* The flat device arrays exactly as handed to Device::mem_copy_to, looked up by
+ * their kernel_textures.h name; read from the CPU device's KernelGlobals. */
+int ref_scene_global(
+    ref_scene *rs, const char *name, const void **ptr, uint64_t *count, uint32_t *elem_size)
+{
+  if (!rs->cpu)
+    return 1;
+  KernelGlobals *kg = &rs->cpu->kernel_globals;
+#define KERNEL_TEX(type, tname) \
+  if (strcmp(name, #tname) == 0) { \
+    *ptr = kg->tname.data; \
+    *count = kg->tname.width; \
+    *elem_size = sizeof(type); \
+    return 0; \
+  }
+#include "kernel/kernel_textures.h"
+  return 1;
+}
+
+/* Name of the i-th kernel_textures.h entry, NULL past the end. */
+const char *ref_global_name(int index)
+{
+  static const char *names[] = {
+#define KERNEL_TEX(type, tname) #tname,
+#include "kernel/kernel_textures.h"
+      NULL};
+  int n = (int)(sizeof(names) / sizeof(names[0])) - 1;
+  return (index >= 0 && index < n) ? names[index] : NULL;
+}
+
+int ref_scene_data(ref_scene *rs, const void **ptr, uint64_t *size)
+{
+  *ptr = &rs->scene->dscene.data;
+  *size = sizeof(KernelData);
+  return 0;
+}
+
+/* Render samples [start_sample, start_sample+num_samples) of the full frame
+ * through Device::task_add(RENDER) with tile_size x tile_size tiles handed out
+ * from one permanent full-frame RenderBuffers (the `buffers != NULL` branch of
+ * Session::acquire_tile, session.cpp:427-446).  `out` receives
+ * height*width*pass_stride floats (unnormalised sums, as in the film buffer).
+ * accumulate != 0 keeps the current film contents. */
+int ref_render(ref_scene *rs,
+               int start_sample,
+               int num_samples,
+               int tile_size,
+               int accumulate,
+               float *out,
+               double *seconds)
+{
+  Scene *scene = rs->scene;
+  Device *device = rs->device;
+  const int width = scene->camera->width;
+  const int height = scene->camera->height;
+
+  BufferParams bp;
+  bp.width = width;
+  bp.height = height;
+  bp.full_width = width;
+  bp.full_height = height;
+  bp.passes = scene->passes;
+
+  if (!rs->buffers || rs->buffers->params.modified(bp)) {
+    delete rs->buffers;
+    rs->buffers = new RenderBuffers(device);
+    rs->buffers->reset(bp);
+  }
+  else if (!accumulate) {
+    rs->buffers->zero();
+  }
+  RenderBuffers *buffers = rs->buffers;
+
+  if (tile_size <= 0)
+    tile_size = max(width, height);
+  const int tiles_x = (width + tile_size - 1) / tile_size;
+  const int tiles_y = (height + tile_size - 1) / tile_size;
+  const int num_tiles = tiles_x * tiles_y;
+  std::atomic<int> next_tile(0);
+
+  DeviceTask task(DeviceTask::RENDER);
+  task.acquire_tile = [&](Device *, RenderTile &rtile, uint) -> bool {
+    int t = next_tile.fetch_add(1);
+    if (t >= num_tiles)
+      return false;
+    int tx = t % tiles_x, ty = t / tiles_x;
+    rtile.x = tx * tile_size;
+    rtile.y = ty * tile_size;
+    rtile.w = min(tile_size, width - rtile.x);
+    rtile.h = min(tile_size, height - rtile.y);
+    rtile.start_sample = start_sample;
+    rtile.num_samples = num_samples;
+    rtile.sample = start_sample;
+    rtile.resolution = 1;
+    rtile.tile_index = t;
+    rtile.task = RenderTile::PATH_TRACE;
+    buffers->params.get_offset_stride(rtile.offset, rtile.stride);
+    rtile.buffer = buffers->buffer.device_pointer;
+    rtile.buffers = buffers;
+    return true;
+  };
+  task.release_tile = [](RenderTile &) {};
+  task.get_cancel = []() -> bool { return false; };
+  task.update_tile_sample = [](RenderTile &) {};
+  task.update_progress_sample = [](long, int) {};
+  task.need_finish_queue = false;
+  task.integrator_branched = false;
+  task.adaptive_sampling.use = false;
+  task.tile_types = RenderTile::PATH_TRACE;
+
+  /* CPUDevice::render sets FTZ/DAZ (SIMD_SET_FLUSH_TO_ZERO) on whichever thread
+   * runs a tile, including this one; do not leak it into the caller. */
+  const unsigned int mxcsr = _mm_getcsr();
+  double t0 = time_dt();
+  device->task_add(task);
+  device->task_wait();
+  buffers->copy_from_device();
+  double t1 = time_dt();
+  _mm_setcsr(mxcsr);
+  if (seconds)
+    *seconds = t1 - t0;
+
+  if (device->have_error()) {
+    rs->error = device->error_message();
+    return 1;
+  }
+  if (out) {
+    memcpy(out,
+           buffers->buffer.data(),
+           sizeof(float) * (size_t)width * height * bp.get_passes_size());
+  }
+  return 0;
+}
+
+/* ---- kernel probes (CPU device only) ---- */
+
+int ref_intersect(ref_scene *rs, const RefProbeRay *rays, RefProbeHit *hits, uint64_t n)
+{
+  if (!rs->cpu)
+    return 1;
+  KernelGlobals kg = rs->cpu->kg_init();
+  ref_probe_intersect(&kg, rays, hits, n);
+  rs->cpu->kg_free(&kg);
+  return 0;
+}
+
+int ref_camera_rays(
+    ref_scene *rs, int sample, int x0, int y0, int w, int h, RefProbeRay *rays, uint32_t *rng_hash)
+{
+  if (!rs->cpu)
+    return 1;
+  KernelGlobals kg = rs->cpu->kg_init();
+  ref_probe_camera_rays(&kg, sample, x0, y0, w, h, rays, rng_hash);
+  rs->cpu->kg_free(&kg);
+  return 0;
+}
+
+int ref_shadow_rays(ref_scene *rs, int sample, int x0, int y0, int w, int h, RefProbeRay *rays)
+{
+  if (!rs->cpu)
+    return 1;
+  KernelGlobals kg = rs->cpu->kg_init();
+  ref_probe_shadow_rays(&kg, sample, x0, y0, w, h, rays);
+  rs->cpu->kg_free(&kg);
+  return 0;
+}
+
+} /* extern "C" */

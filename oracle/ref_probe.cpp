@@ -1,0 +1,183 @@
+/* Kernel-side probe: instantiates the REFERENCE kernel headers (generic scalar
+ * variant, same flags as kernels/cpu/kernel.cpp in oracle/Makefile) and exposes
+ * the individual hot-path functions on batches, so tests can compare the CUDA
+ * path stage by stage:
+ *   - scene_intersect            (kernel/bvh/bvh.h:154-237)      closest hit
+ *   - scene_intersect any-hit    (PATH_RAY_SHADOW_OPAQUE, bvh_traversal.h:144-147)
+ *   - kernel_path_trace_setup    (kernel/kernel_path_common.h:21-46) camera rays
+ *   - the first-bounce light connection (kernel_path_surface.h:214-268) to dump
+ *     the shadow rays the reference would trace.
+ * TEST INFRASTRUCTURE ONLY - part of oracle/_ref/libcycles_ref.so. */
+
+#if defined(__x86_64__) || defined(_M_X64)
+#  define __KERNEL_SSE2__
+#endif
+
+#include "kernel/kernel.h"
+#define KERNEL_ARCH cpu_probe
+
+// clang-format off
+#include "kernel/kernel_compat_cpu.h"
+#include "kernel/kernel_math.h"
+#include "kernel/kernel_types.h"
+#include "kernel/split/kernel_split_data.h"
+#include "kernel/kernel_globals.h"
+#include "kernel/kernel_color.h"
+#include "kernel/kernels/cpu/kernel_cpu_image.h"
+#include "kernel/kernel_film.h"
+#include "kernel/kernel_path.h"
+// clang-format on
+
+#include "ref_probe.h"
+
+CCL_NAMESPACE_BEGIN
+
+static inline void ray_from_probe(const RefProbeRay &in, Ray *ray)
+{
+  ray->P = make_float3(in.P[0], in.P[1], in.P[2]);
+  ray->D = make_float3(in.D[0], in.D[1], in.D[2]);
+  ray->t = in.t;
+  ray->time = 0.0f;
+  ray->dP = differential3_zero();
+  ray->dD = differential3_zero();
+}
+
+void ref_probe_intersect(KernelGlobals *kg, const RefProbeRay *rays, RefProbeHit *hits, size_t n)
+{
+  for (size_t i = 0; i < n; i++) {
+    Ray ray;
+    ray_from_probe(rays[i], &ray);
+    Intersection isect;
+    isect.t = 0.0f;
+    isect.u = isect.v = 0.0f;
+    isect.prim = PRIM_NONE;
+    isect.object = OBJECT_NONE;
+    isect.type = PRIMITIVE_NONE;
+    bool hit = (ray.t != 0.0f) && scene_intersect(kg, &ray, rays[i].visibility, &isect);
+    RefProbeHit &h = hits[i];
+    if (hit) {
+      h.t = isect.t;
+      h.u = isect.u;
+      h.v = isect.v;
+      h.prim = isect.prim;
+      h.object = isect.object;
+      h.type = isect.type;
+    }
+    else {
+      h.t = rays[i].t;
+      h.u = h.v = 0.0f;
+      h.prim = -1;
+      h.object = -1;
+      h.type = 0;
+    }
+  }
+}
+
+void ref_probe_camera_rays(
+    KernelGlobals *kg, int sample, int x0, int y0, int w, int h, RefProbeRay *rays, uint *rng_hash)
+{
+  for (int y = 0; y < h; y++) {
+    for (int x = 0; x < w; x++) {
+      Ray ray;
+      uint hash;
+      kernel_path_trace_setup(kg, sample, x0 + x, y0 + y, &hash, &ray);
+      RefProbeRay &r = rays[(size_t)y * w + x];
+      r.P[0] = ray.P.x;
+      r.P[1] = ray.P.y;
+      r.P[2] = ray.P.z;
+      r.t = ray.t;
+      r.D[0] = ray.D.x;
+      r.D[1] = ray.D.y;
+      r.D[2] = ray.D.z;
+      r.visibility = PATH_RAY_CAMERA | PATH_RAY_ALL_VISIBILITY; /* refined below */
+      if (rng_hash)
+        rng_hash[(size_t)y * w + x] = hash;
+    }
+  }
+  /* visibility exactly as path_state_ray_visibility() would compute for the
+   * first segment (kernel_path_state.h:190-203). */
+  {
+    Ray ray;
+    uint hash;
+    kernel_path_trace_setup(kg, sample, x0, y0, &hash, &ray);
+    ShaderDataTinyStorage sd_storage;
+    PathState state;
+    path_state_init(kg, AS_SHADER_DATA(&sd_storage), &state, hash, sample, &ray);
+    uint vis = path_state_ray_visibility(kg, &state);
+    for (size_t i = 0; i < (size_t)w * h; i++)
+      rays[i].visibility = vis;
+  }
+}
+
+/* First-bounce shadow rays: run the reference path up to the light connection
+ * (kernel_path_integrate, kernel_path.h:509-641, first iteration only) and
+ * record the light ray that shadow_blocked() would be given
+ * (kernel_path_surface.h:236-262).  Rays that the reference would not trace
+ * (miss, no light sample, zero contribution) get t = 0. */
+void ref_probe_shadow_rays(
+    KernelGlobals *kg, int sample, int x0, int y0, int w, int h, RefProbeRay *rays)
+{
+  for (int y = 0; y < h; y++) {
+    for (int x = 0; x < w; x++) {
+      RefProbeRay &out = rays[(size_t)y * w + x];
+      memset(&out, 0, sizeof(out));
+      out.visibility = PATH_RAY_SHADOW_OPAQUE;
+
+      Ray ray;
+      uint rng_hash;
+      kernel_path_trace_setup(kg, sample, x0 + x, y0 + y, &rng_hash, &ray);
+      if (ray.t == 0.0f)
+        continue;
+
+      PathRadiance L;
+      path_radiance_init(kg, &L);
+      ShaderDataTinyStorage emission_sd_storage;
+      ShaderData *emission_sd = AS_SHADER_DATA(&emission_sd_storage);
+      PathState state;
+      path_state_init(kg, emission_sd, &state, rng_hash, sample, &ray);
+
+      Intersection isect;
+      if (!kernel_path_scene_intersect(kg, &state, &ray, &isect, &L))
+        continue;
+
+      ShaderData sd;
+      shader_setup_from_ray(kg, &sd, &isect, &ray);
+      shader_eval_surface(kg, &sd, &state, NULL, state.flag);
+      shader_prepare_closures(&sd, &state);
+
+      if (!(kernel_data.integrator.use_direct_light && (sd.flag & SD_BSDF_HAS_EVAL)))
+        continue;
+
+      float light_u, light_v;
+      path_state_rng_2D(kg, &state, PRNG_LIGHT_U, &light_u, &light_v);
+
+      Ray light_ray;
+      BsdfEval L_light;
+      bool is_lamp;
+      light_ray.time = sd.time;
+
+      LightSample ls;
+      if (light_sample(kg, -1, light_u, light_v, sd.time, sd.P, state.bounce, &ls)) {
+        float terminate = path_state_rng_light_termination(kg, &state);
+        if (direct_emission(
+                kg, &sd, emission_sd, &ls, &state, &light_ray, &L_light, &is_lamp, terminate)) {
+          out.P[0] = light_ray.P.x;
+          out.P[1] = light_ray.P.y;
+          out.P[2] = light_ray.P.z;
+          out.t = light_ray.t;
+          out.D[0] = light_ray.D.x;
+          out.D[1] = light_ray.D.y;
+          out.D[2] = light_ray.D.z;
+        }
+      }
+    }
+  }
+}
+
+void ref_probe_path_trace(
+    KernelGlobals *kg, float *buffer, int sample, int x, int y, int offset, int stride)
+{
+  kernel_path_trace(kg, buffer, sample, x, y, offset, stride);
+}
+
+CCL_NAMESPACE_END

@@ -1,0 +1,36 @@
+/* Shared between ref_probe.cpp (kernel side) and ref_harness.cpp (host side).
+ * Plain-data batch records; the same layouts are used by include/b200_cycles.h
+ * (b200_ray / b200_hit) so a dumped batch feeds both sides unchanged.
+ * TEST INFRASTRUCTURE ONLY. */
+#ifndef REF_PROBE_H
+#define REF_PROBE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+struct RefProbeRay {
+  float P[3];
+  float t;
+  float D[3];
+  uint32_t visibility;
+};
+
+struct RefProbeHit {
+  float t, u, v;
+  int32_t prim;
+  int32_t object;
+  int32_t type;
+};
+
+namespace ccl {
+struct KernelGlobals;
+void ref_probe_intersect(KernelGlobals *kg, const RefProbeRay *rays, RefProbeHit *hits, size_t n);
+void ref_probe_camera_rays(KernelGlobals *kg, int sample, int x0, int y0, int w, int h,
+                           RefProbeRay *rays, unsigned int *rng_hash);
+void ref_probe_shadow_rays(KernelGlobals *kg, int sample, int x0, int y0, int w, int h,
+                           RefProbeRay *rays);
+void ref_probe_path_trace(KernelGlobals *kg, float *buffer, int sample, int x, int y, int offset,
+                          int stride);
+}  // namespace ccl
+
+#endif

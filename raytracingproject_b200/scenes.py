@@ -1,0 +1,420 @@
+"""Procedural scene descriptions for the BASELINE.json configs.
+
+A SceneDesc is neutral data: a Cycles-XML header (camera, integrator, film,
+background, shaders, lights and small meshes - the syntax read by the
+reference's intern/cycles/app/cycles_xml.cpp:614-660) plus numpy triangle
+meshes and object instances that are too big for XML.  It contains no
+renderer code; the reference's own host code (Scene / BVHBuild / SVM compiler)
+flattens it into the device arrays that both the CPU oracle and the B200 device
+consume.  All generators are seeded and deterministic.
+"""
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+
+@dataclass
+class MeshDesc:
+    P: np.ndarray  # (nv, 3) float32
+    tris: np.ndarray  # (nt, 3) int32
+    shader: str
+    smooth: bool = False
+
+
+@dataclass
+class SceneDesc:
+    name: str
+    xml: str
+    width: int
+    height: int
+    meshes: List[MeshDesc] = field(default_factory=list)
+    # (mesh index, 3x4 row-major object-to-world transform)
+    objects: List[Tuple[int, np.ndarray]] = field(default_factory=list)
+    spp: int = 64
+    notes: str = ""
+
+    @property
+    def num_triangles(self):
+        return int(sum(len(m.tris) for m in self.meshes))
+
+    @property
+    def num_instanced_triangles(self):
+        return int(sum(len(self.meshes[m].tris) for m, _ in self.objects))
+
+
+def _f(v):
+    return " ".join("%.9g" % float(x) for x in np.asarray(v, dtype=np.float64).ravel())
+
+
+def _matrix_attr(m34):
+    """cycles_xml.cpp:550-559 reads 16 floats and transposes: column-major."""
+    m = np.eye(4)
+    m[:3, :] = np.asarray(m34, dtype=np.float64).reshape(3, 4)
+    return _f(m.T)
+
+
+def look_at(eye, target, up=(0.0, 0.0, 1.0)):
+    """Cycles camera space: +Z forward, +X right, +Y up (camera.cpp / Blender's
+    -Z camera flipped by scale(1,1,-1) in blender_camera.cpp)."""
+    eye = np.asarray(eye, dtype=np.float64)
+    fwd = np.asarray(target, dtype=np.float64) - eye
+    fwd /= np.linalg.norm(fwd)
+    right = np.cross(fwd, np.asarray(up, dtype=np.float64))
+    right /= np.linalg.norm(right)
+    upv = np.cross(right, fwd)
+    m = np.zeros((3, 4))
+    m[:, 0], m[:, 1], m[:, 2], m[:, 3] = right, upv, fwd, eye
+    return m
+
+
+def euler_xyz_camera(loc, rot):
+    """Blender camera object (XYZ euler, looks down -Z) -> Cycles matrix."""
+    rx, ry, rz = rot
+    cx, sx, cy, sy, cz, sz = np.cos(rx), np.sin(rx), np.cos(ry), np.sin(ry), np.cos(rz), np.sin(rz)
+    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    R = Rz @ Ry @ Rx
+    m = np.zeros((3, 4))
+    m[:, :3] = R @ np.diag([1.0, 1.0, -1.0])
+    m[:, 3] = loc
+    return m
+
+
+def _header(width, height, cam_m34, fov, integrator, film="", nearclip=0.1, farclip=1000.0):
+    return (
+        '<camera width="%d" height="%d"/>\n'
+        '<transform matrix="%s">\n'
+        '  <camera type="perspective" fov="%s" nearclip="%s" farclip="%s" shuttertime="-1"/>\n'
+        "</transform>\n"
+        "<integrator %s/>\n"
+        '<film filter_type="blackman_harris" filter_width="1.5" exposure="1" %s/>\n'
+        % (width, height, _matrix_attr(cam_m34), _f(fov), _f(nearclip), _f(farclip), integrator, film)
+    )
+
+
+def _background(color, strength=1.0):
+    return (
+        "<background>\n"
+        '  <background name="bg" color="%s" strength="%s"/>\n'
+        '  <connect from="bg background" to="output surface"/>\n'
+        "</background>\n" % (_f(color), _f(strength))
+    )
+
+
+def _diffuse_shader(name, color):
+    return (
+        '<shader name="%s">\n'
+        '  <diffuse_bsdf name="d" color="%s"/>\n'
+        '  <connect from="d bsdf" to="output surface"/>\n'
+        "</shader>\n" % (name, _f(color))
+    )
+
+
+def _emission_shader(name, color=(1, 1, 1), strength=1.0):
+    return (
+        '<shader name="%s">\n'
+        '  <emission name="e" color="%s" strength="%s"/>\n'
+        '  <connect from="e emission" to="output surface"/>\n'
+        "</shader>\n" % (name, _f(color), _f(strength))
+    )
+
+
+def _principled_shader(name, base_color, metallic=0.0, roughness=0.5, specular=0.5,
+                       transmission=0.0, ior=1.45, distribution="GGX"):
+    return (
+        '<shader name="%s">\n'
+        '  <principled_bsdf name="p" distribution="%s" base_color="%s" metallic="%s" '
+        'roughness="%s" specular="%s" transmission="%s" ior="%s"/>\n'
+        '  <connect from="p bsdf" to="output surface"/>\n'
+        "</shader>\n"
+        % (name, distribution, _f(base_color), _f(metallic), _f(roughness), _f(specular),
+           _f(transmission), _f(ior))
+    )
+
+
+def _integrator(max_bounce, diffuse=None, glossy=None, transmission=None, transparent=8,
+                clamp_indirect=0.0, seed=0, light_threshold=0.01, caustics=True):
+    diffuse = max_bounce if diffuse is None else diffuse
+    glossy = max_bounce if glossy is None else glossy
+    transmission = max_bounce if transmission is None else transmission
+    return (
+        'method="path" sampling_pattern="sobol" seed="%d" min_bounce="0" max_bounce="%d" '
+        'max_diffuse_bounce="%d" max_glossy_bounce="%d" max_transmission_bounce="%d" '
+        'transparent_min_bounce="0" transparent_max_bounce="%d" sample_clamp_direct="0" '
+        'sample_clamp_indirect="%s" light_sampling_threshold="%s" caustics_reflective="%s" '
+        'caustics_refractive="%s" filter_glossy="0"'
+        % (seed, max_bounce, diffuse, glossy, transmission, transparent, _f(clamp_indirect),
+           _f(light_threshold), "true" if caustics else "false", "true" if caustics else "false")
+    )
+
+
+def _state(shader, body):
+    return '<state shader="%s">\n%s</state>\n' % (shader, body)
+
+
+CUBE_VERTS = np.array(
+    [[-1, -1, -1], [1, -1, -1], [1, 1, -1], [-1, 1, -1],
+     [-1, -1, 1], [1, -1, 1], [1, 1, 1], [-1, 1, 1]], dtype=np.float32)
+# outward-facing quads (counter-clockwise seen from outside)
+CUBE_QUADS = np.array(
+    [[0, 3, 2, 1], [4, 5, 6, 7], [0, 1, 5, 4], [1, 2, 6, 5], [2, 3, 7, 6], [3, 0, 4, 7]],
+    dtype=np.int32)
+
+
+def quads_to_tris(quads):
+    q = np.asarray(quads, dtype=np.int32)
+    return np.concatenate([q[:, [0, 1, 2]], q[:, [0, 2, 3]]], axis=1).reshape(-1, 3)
+
+
+def box_mesh(lo, hi):
+    lo, hi = np.asarray(lo, np.float32), np.asarray(hi, np.float32)
+    P = lo + (CUBE_VERTS * 0.5 + 0.5) * (hi - lo)
+    return P.astype(np.float32), quads_to_tris(CUBE_QUADS)
+
+
+# ---------------------------------------------------------------- config 1
+def default_cube(width=1920, height=1080, spp=64, material="principled", max_bounce=12):
+    """BASELINE config 1 - Blender's startup scene, values extracted from
+    release/datafiles/startup.blend."""
+    cam = euler_xyz_camera((7.358891, -6.925791, 4.958309), (1.109319, 0.0, 0.814928))
+    fov = 2.0 * np.arctan(0.5 * 36.0 / 50.0 / (width / height))
+    xml = "<cycles>\n"
+    xml += _header(
+        width, height, cam, fov,
+        _integrator(max_bounce, diffuse=min(4, max_bounce), glossy=min(4, max_bounce),
+                    transmission=max_bounce, clamp_indirect=10.0),
+        nearclip=0.1, farclip=100.0)
+    xml += _background((0.05087609, 0.05087609, 0.05087609))
+    if material == "principled":
+        xml += _principled_shader("cube", (0.8, 0.8, 0.8), 0.0, 0.5, 0.5)
+    else:
+        xml += _diffuse_shader("cube", (0.8, 0.8, 0.8))
+    xml += _emission_shader("lamp", (1, 1, 1), 1.0)
+    xml += _state(
+        "lamp",
+        '<light type="point" co="4.076245 1.005454 5.903862" size="0.1" '
+        'strength="1000 1000 1000" use_mis="true"/>\n')
+    xml += "</cycles>\n"
+    P, tris = box_mesh((-1, -1, -1), (1, 1, 1))
+    return SceneDesc(
+        "default_cube_" + material, xml, width, height,
+        meshes=[MeshDesc(P, tris, "cube")], objects=[(0, np.eye(4, dtype=np.float32)[:3])],
+        spp=spp, notes="config 1")
+
+
+# ---------------------------------------------------------------- config 2
+def value_noise_height(n, seed=1234, octaves=5, amplitude=1.5, base_cells=4):
+    """Sum of `octaves` octaves of bilinear-smoothstep value noise on an
+    (n+1)x(n+1) lattice over [0,1]^2."""
+    rng = np.random.default_rng(seed)
+    u = np.linspace(0.0, 1.0, n + 1)
+    X, Y = np.meshgrid(u, u, indexing="xy")
+    H = np.zeros_like(X)
+    amp, cells, total = 1.0, base_cells, 0.0
+    for _ in range(octaves):
+        g = rng.random((cells + 2, cells + 2))
+        fx, fy = X * cells, Y * cells
+        ix, iy = np.minimum(fx.astype(np.int64), cells), np.minimum(fy.astype(np.int64), cells)
+        tx, ty = fx - ix, fy - iy
+        tx, ty = tx * tx * (3 - 2 * tx), ty * ty * (3 - 2 * ty)
+        v = (g[iy, ix] * (1 - tx) + g[iy, ix + 1] * tx) * (1 - ty) + (
+            g[iy + 1, ix] * (1 - tx) + g[iy + 1, ix + 1] * tx) * ty
+        H += amp * (v - 0.5)
+        total += amp
+        amp *= 0.5
+        cells *= 2
+    return (H / total) * 2.0 * amplitude
+
+
+def grid_mesh(n, extent=10.0, height=None):
+    u = np.linspace(-extent, extent, n + 1, dtype=np.float64)
+    X, Y = np.meshgrid(u, u, indexing="xy")
+    Z = np.zeros_like(X) if height is None else height
+    P = np.stack([X, Y, Z], axis=-1).reshape(-1, 3).astype(np.float32)
+    i = np.arange(n, dtype=np.int64)
+    I, J = np.meshgrid(i, i, indexing="xy")
+    v00 = (J * (n + 1) + I).ravel()
+    v10, v01, v11 = v00 + 1, v00 + (n + 1), v00 + (n + 2)
+    tris = np.stack(
+        [np.stack([v00, v10, v11], -1), np.stack([v00, v11, v01], -1)], axis=1).reshape(-1, 3)
+    return P, tris.astype(np.int32)
+
+
+def terrain(width=1920, height=1080, spp=256, n=708, max_bounce=0):
+    """BASELINE config 2 - 708x708 grid (1 002 528 tris) displaced by 5 octaves of
+    value noise; diffuse only; one sun; max_bounce 0 (traversal-bound)."""
+    H = value_noise_height(n)
+    P, tris = grid_mesh(n, 10.0, H)
+    elev = np.deg2rad(35.0)
+    dist = 24.0
+    cam = look_at((0.0, -dist * np.cos(elev), dist * np.sin(elev)), (0.0, 0.0, 0.0))
+    xml = "<cycles>\n"
+    xml += _header(width, height, cam, 0.62, _integrator(max_bounce), nearclip=0.1, farclip=1000.0)
+    xml += _background((0.3, 0.4, 0.6), 0.25)
+    xml += _diffuse_shader("ground", (0.8, 0.8, 0.8))
+    xml += _emission_shader("sun", (1.0, 0.95, 0.9), 1.0)
+    sun_dir = np.array([0.35, 0.45, -0.82])
+    sun_dir /= np.linalg.norm(sun_dir)
+    xml += _state(
+        "sun",
+        '<light type="distant" dir="%s" angle="%s" strength="3 3 3" use_mis="true"/>\n'
+        % (_f(sun_dir), _f(np.deg2rad(0.5))))
+    xml += "</cycles>\n"
+    return SceneDesc(
+        "terrain_%dk" % (len(tris) // 1000), xml, width, height,
+        meshes=[MeshDesc(P, tris, "ground")], objects=[(0, np.eye(4, dtype=np.float32)[:3])],
+        spp=spp, notes="config 2")
+
+
+# ---------------------------------------------------------------- config 3
+def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
+            materials="principled"):
+    """BASELINE config 3 - Cornell box, ceiling area light, one metallic and one
+    glass Principled box (materials="diffuse" gives the all-diffuse variant)."""
+    xml = "<cycles>\n"
+    cam = look_at((0.0, -3.6, 1.0), (0.0, 0.0, 1.0))
+    fov = 2.0 * np.arctan(0.5 * 36.0 / 50.0 / (width / height)) * 1.6
+    xml += _header(width, height, cam, fov,
+                   _integrator(max_bounce, clamp_indirect=10.0), nearclip=0.01, farclip=100.0)
+    xml += _background((0, 0, 0), 0.0)
+    xml += _diffuse_shader("white", (0.73, 0.73, 0.73))
+    xml += _diffuse_shader("red", (0.65, 0.05, 0.05))
+    xml += _diffuse_shader("green", (0.12, 0.45, 0.15))
+    if materials == "principled":
+        xml += _principled_shader("metal", (0.9, 0.85, 0.7), 1.0, 0.2, 0.5, 0.0, 1.45, distribution)
+        xml += _principled_shader("glass", (1, 1, 1), 0.0, 0.0, 0.5, 1.0, 1.45, distribution)
+    else:
+        xml += _diffuse_shader("metal", (0.9, 0.85, 0.7))
+        xml += _diffuse_shader("glass", (0.6, 0.7, 0.9))
+    xml += _emission_shader("lamp", (1.0, 0.9, 0.7), 1.0)
+    xml += _state(
+        "lamp",
+        '<light type="area" co="0 0 1.98" dir="0 0 -1" axisu="1 0 0" axisv="0 1 0" '
+        'sizeu="0.5" sizev="0.5" size="1" strength="12 12 12" use_mis="true"/>\n')
+    xml += "</cycles>\n"
+
+    def quad(a, b, c, d):
+        return np.array([a, b, c, d], np.float32), np.array([[0, 1, 2], [0, 2, 3]], np.int32)
+
+    meshes, objects = [], []
+
+    def add(P, tris, shader, tfm=None):
+        meshes.append(MeshDesc(np.asarray(P, np.float32), np.asarray(tris, np.int32), shader))
+        objects.append((len(meshes) - 1, np.eye(4, dtype=np.float32)[:3] if tfm is None else tfm))
+
+    add(*quad((-1, -1, 0), (1, -1, 0), (1, 1, 0), (-1, 1, 0)), "white")  # floor
+    add(*quad((-1, -1, 2), (-1, 1, 2), (1, 1, 2), (1, -1, 2)), "white")  # ceiling
+    add(*quad((-1, 1, 0), (1, 1, 0), (1, 1, 2), (-1, 1, 2)), "white")  # back
+    add(*quad((-1, -1, 0), (-1, 1, 0), (-1, 1, 2), (-1, -1, 2)), "red")  # left
+    add(*quad((1, -1, 0), (1, -1, 2), (1, 1, 2), (1, 1, 0)), "green")  # right
+
+    def rot_z(deg, t):
+        a = np.deg2rad(deg)
+        m = np.eye(4, dtype=np.float32)[:3].copy()
+        m[:2, :2] = [[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]
+        m[:, 3] = t
+        return m
+
+    Pb, Tb = box_mesh((-0.3, -0.3, 0.0), (0.3, 0.3, 1.2))
+    add(Pb, Tb, "metal", rot_z(20.0, (-0.35, 0.3, 0.0)))
+    Ps, Ts = box_mesh((-0.3, -0.3, 0.0), (0.3, 0.3, 0.6))
+    add(Ps, Ts, "glass", rot_z(-18.0, (0.35, -0.3, 0.0)))
+    return SceneDesc("cornell_" + materials, xml, width, height, meshes=meshes, objects=objects,
+                     spp=spp, notes="config 3")
+
+
+# ---------------------------------------------------------------- config 4
+def icosphere(subdiv):
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    V = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t),
+         (0, -1, -t), (0, 1, -t), (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    F = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4),
+         (11, 10, 2), (10, 7, 6), (7, 1, 8), (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8),
+         (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    V = np.array(V, dtype=np.float64)
+    V /= np.linalg.norm(V, axis=1, keepdims=True)
+    F = np.array(F, dtype=np.int64)
+    for _ in range(subdiv):
+        e = np.concatenate([F[:, [0, 1]], F[:, [1, 2]], F[:, [2, 0]]], axis=0)
+        es = np.sort(e, axis=1)
+        uniq, inv = np.unique(es, axis=0, return_inverse=True)
+        mid = V[uniq[:, 0]] + V[uniq[:, 1]]
+        mid /= np.linalg.norm(mid, axis=1, keepdims=True)
+        base = len(V)
+        V = np.concatenate([V, mid], axis=0)
+        nF = len(F)
+        inv = inv.reshape(-1)
+        m01, m12, m20 = base + inv[:nF], base + inv[nF:2 * nF], base + inv[2 * nF:]
+        F = np.concatenate([
+            np.stack([F[:, 0], m01, m20], 1), np.stack([F[:, 1], m12, m01], 1),
+            np.stack([F[:, 2], m20, m12], 1), np.stack([m01, m12, m20], 1)], axis=0)
+    return V, F
+
+
+def rock_mesh(subdiv=6, seed=42, amplitude=0.18):
+    """Icosphere (20*4^subdiv tris; subdiv 6 -> 81 920) with lumpy radial noise."""
+    V, F = icosphere(subdiv)
+    rng = np.random.default_rng(seed)
+    r = np.ones(len(V))
+    for k in range(1, 5):
+        for _ in range(6):
+            d = rng.normal(size=3)
+            d /= np.linalg.norm(d)
+            ph = rng.uniform(0, 2 * np.pi)
+            r += (amplitude / (k * 6)) * np.sin(k * 3.0 * (V @ d) + ph)
+    return (V * r[:, None]).astype(np.float32), F.astype(np.int32)
+
+
+def instanced(width=3840, height=2160, spp=256, grid=100, subdiv=6, max_bounce=2, seed=7):
+    """BASELINE config 4 - grid x grid instances of one lumpy icosphere BLAS
+    (two-level BVH, transform_applied=false) over a ground plane."""
+    P, T = rock_mesh(subdiv)
+    rng = np.random.default_rng(seed)
+    meshes = [MeshDesc(P, T, "rock")]
+    objects = []
+    spacing = 3.0
+    half = 0.5 * spacing * (grid - 1)
+    for j in range(grid):
+        for i in range(grid):
+            s = rng.uniform(0.6, 1.2)
+            ax = rng.normal(size=3)
+            ax /= np.linalg.norm(ax)
+            ang = rng.uniform(0, 2 * np.pi)
+            K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+            R = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * (K @ K)
+            m = np.zeros((3, 4), dtype=np.float32)
+            m[:, :3] = (R * s).astype(np.float32)
+            m[:, 3] = (i * spacing - half + rng.uniform(-0.6, 0.6),
+                       j * spacing - half + rng.uniform(-0.6, 0.6), 1.25 * s)
+            objects.append((0, m))
+    g = half + 10.0
+    Pg = np.array([(-g, -g, 0), (g, -g, 0), (g, g, 0), (-g, g, 0)], np.float32)
+    meshes.append(MeshDesc(Pg, np.array([[0, 1, 2], [0, 2, 3]], np.int32), "ground"))
+    objects.append((1, np.eye(4, dtype=np.float32)[:3]))
+
+    cam = look_at((0.0, -half * 0.55, half * 0.22), (0.0, half * 0.1, 0.0))
+    xml = "<cycles>\n"
+    xml += _header(width, height, cam, 0.55, _integrator(max_bounce), nearclip=0.1, farclip=5000.0)
+    xml += _background((0.35, 0.45, 0.65), 0.3)
+    xml += _diffuse_shader("rock", (0.7, 0.6, 0.5))
+    xml += _diffuse_shader("ground", (0.5, 0.5, 0.5))
+    xml += _emission_shader("sun", (1.0, 0.95, 0.9), 1.0)
+    sun_dir = np.array([0.4, 0.3, -0.85])
+    sun_dir /= np.linalg.norm(sun_dir)
+    xml += _state(
+        "sun",
+        '<light type="distant" dir="%s" angle="%s" strength="3 3 3" use_mis="true"/>\n'
+        % (_f(sun_dir), _f(np.deg2rad(0.5))))
+    xml += "</cycles>\n"
+    return SceneDesc("instanced_%dx%d" % (grid, grid), xml, width, height, meshes=meshes,
+                     objects=objects, spp=spp, notes="config 4")
+
+
+CONFIGS = {
+    "cube": default_cube,
+    "terrain": terrain,
+    "cornell": cornell,
+    "instanced": instanced,
+}
