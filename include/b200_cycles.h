@@ -1,0 +1,165 @@
+/* b200_cycles.h - C ABI of the B200-native Cycles path-tracing device.
+ *
+ * This is the drop-in boundary: everything CUDA-specific lives behind these
+ * entry points (libb200cycles.so); the host side is either the C++ Device
+ * subclass (raytracingproject_b200/csrc/device_b200.cpp, a ccl::Device exactly
+ * like the reference's CUDADevice) or the Python mirror
+ * (raytracingproject_b200/device.py).  Plain pointers and sizes only; no
+ * exceptions cross the boundary; every function returns 0 on success and a
+ * non-zero B200_ERR_* code on failure, with the text in b200_last_error().
+ *
+ * Each entry point cites the reference interface it stands in for.  Reference
+ * paths are relative to /root/reference/blender/intern/cycles/.
+ */
+#ifndef B200_CYCLES_H
+#define B200_CYCLES_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+
+enum {
+  B200_OK = 0,
+  B200_ERR_CUDA = 1,        /* a CUDA runtime call failed */
+  B200_ERR_INVALID = 2,     /* bad argument / unknown name / size mismatch */
+  B200_ERR_UNSUPPORTED = 3, /* scene uses a feature outside the hot-path scope */
+  B200_ERR_NOT_READY = 4,   /* render before the scene was bound */
+  B200_ERR_OOM = 5,
+  B200_ERR_CANCELLED = 6
+};
+
+typedef struct b200_ctx b200_ctx;
+
+/* Ray / hit records of the batch-trace hook.  Same layout as the oracle's
+ * RefProbeRay / RefProbeHit so one dumped batch feeds both sides.
+ * b200_hit mirrors struct Intersection (kernel/kernel_types.h:672-686). */
+typedef struct b200_ray {
+  float P[3];
+  float t; /* max distance; 0 = inactive ray */
+  float D[3];
+  uint32_t visibility; /* PATH_RAY_* mask tested against __prim_visibility */
+} b200_ray;
+
+typedef struct b200_hit {
+  float t, u, v;
+  int32_t prim;   /* index into the reference's packed prim arrays; -1 = miss */
+  int32_t object; /* instance object id, -1 (OBJECT_NONE) for static geometry */
+  int32_t type;   /* PRIMITIVE_* */
+} b200_hit;
+
+/* Fields of WorkTile (kernel/kernel_types.h:1690-1700) / RenderTile
+ * (render/buffers.h:135-160) that RENDER needs. */
+typedef struct b200_work_tile {
+  int32_t x, y, w, h;
+  int32_t start_sample, num_samples;
+  int32_t offset, stride;
+  uint64_t buffer; /* device pointer of the float film (RenderBuffers::buffer) */
+} b200_work_tile;
+
+/* Counters of the last b200_render / b200_trace_batch (device-side counts, not
+ * estimates): rays actually traversed and the BVH work they did. */
+typedef struct b200_stats {
+  uint64_t primary_rays;  /* scene_intersect calls for camera rays */
+  uint64_t bounce_rays;   /* scene_intersect calls for bounce rays */
+  uint64_t shadow_rays;   /* shadow_blocked traversals */
+  uint64_t nodes_visited; /* BVH8 nodes fetched (counter build only, else 0) */
+  uint64_t tris_tested;   /* triangles tested   (counter build only, else 0) */
+  uint64_t instances_entered;
+  uint64_t kernel_launches; /* our kernels launched inside the call */
+  double device_ms;         /* CUDA-event time of the call's device work */
+  double traverse_ms;       /* CUDA-event time spent in the traversal kernels */
+} b200_stats;
+
+/* BVH8 build report (host builder). */
+typedef struct b200_bvh_info {
+  uint64_t num_nodes, num_tri_records, num_triangles, num_instances;
+  uint64_t node_bytes, tri_bytes;
+  double build_ms;
+  float sah_cost;
+  uint32_t max_depth;
+} b200_bvh_info;
+
+int b200_abi_version(void);
+
+/* Device enumeration - device_cuda_info() / device_cuda_init()
+ * (device/device_intern.h:34-35,47; device/device_cuda.cpp:100-190). */
+int b200_device_count(void);
+int b200_device_name(int ordinal, char *name, size_t len, int *sm_major, int *sm_minor,
+                     uint64_t *total_mem, int *num_sms);
+
+/* Context - CUDADevice ctor/dtor (device/cuda/device_cuda_impl.cpp:199-262).
+ * Fails (returns NULL, message in err) unless the device is sm_100. */
+b200_ctx *b200_create(int cuda_ordinal, char *err, size_t errlen);
+void b200_destroy(b200_ctx *ctx);
+const char *b200_last_error(b200_ctx *ctx);
+
+/* Memory - Device::mem_alloc / mem_copy_to / mem_copy_from / mem_zero / mem_free
+ * (device/device.h:484-488; CUDADevice::generic_alloc .. mem_free,
+ * device_cuda_impl.cpp:806-1086). */
+int b200_alloc(b200_ctx *ctx, size_t bytes, uint64_t *dptr);
+int b200_free(b200_ctx *ctx, uint64_t dptr);
+int b200_h2d(b200_ctx *ctx, uint64_t dptr, const void *host, size_t offset, size_t bytes);
+int b200_d2h(b200_ctx *ctx, uint64_t dptr, void *host, size_t offset, size_t bytes);
+int b200_zero(b200_ctx *ctx, uint64_t dptr, size_t offset, size_t bytes);
+size_t b200_mem_used(b200_ctx *ctx);
+
+/* MEM_GLOBAL binding by kernel_textures.h name ("__bvh_nodes", "__svm_nodes"..) -
+ * the const_copy_to(mem.name, &device_pointer) self-call of CUDADevice::mem_copy_to
+ * (device_cuda_impl.cpp:1088-1096) / kernel_global_memory_copy
+ * (kernel/kernels/cpu/kernel.cpp:77-92).  `host` may be NULL; when given, the
+ * host copy is kept for the BVH8 build (the BVH arrays) and validation
+ * (__svm_nodes is scanned for opcodes outside the supported subset ->
+ * B200_ERR_UNSUPPORTED). */
+int b200_bind_global(b200_ctx *ctx, const char *name, uint64_t dptr, const void *host,
+                     size_t bytes);
+
+/* Device::const_copy_to("__data", &KernelData, sizeof) (render/scene.cpp:307). */
+int b200_set_kernel_data(b200_ctx *ctx, const void *kernel_data, size_t bytes);
+
+/* Builds the compressed BVH8 from the bound BVH2 arrays and uploads it.  Called
+ * implicitly by the first render/trace after a (re)bind; exposed so the build
+ * time can be reported - stands where BVH::build + pack_nodes + copy_to_device
+ * stand (bvh/bvh.cpp:128-178, render/geometry.cpp:1093-1098). */
+int b200_build_bvh(b200_ctx *ctx, b200_bvh_info *info);
+
+/* DeviceTask::RENDER for one tile - CUDADevice::render
+ * (device_cuda_impl.cpp:1853-1952): runs the whole wavefront (init_from_camera,
+ * intersect_closest, shade_*, intersect_shadow, film write) for samples
+ * [start_sample, start_sample+num_samples) of the tile and accumulates into the
+ * film at tile.buffer.  `cancel` (may be NULL) is polled between batches
+ * (task.get_cancel(), device_cuda_impl.cpp:1908). */
+int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *cancel);
+
+/* Parity / benchmark hook: scene_intersect (kernel/bvh/bvh.h:154-237) on a batch
+ * of rays resident in device memory.  any_hit != 0 gives the shadow-ray
+ * early-out (bvh_traversal.h:144-147): only `prim >= 0` is meaningful then. */
+int b200_trace_batch(b200_ctx *ctx, uint64_t rays, uint64_t hits, uint64_t n, int any_hit);
+
+/* DeviceTask::FILM_CONVERT - kernel_film_convert_to_byte / _half_float
+ * (kernel/kernel_film.h:90-130; CUDADevice::film_convert
+ * device_cuda_impl.cpp:1954-2017). */
+int b200_film_convert(b200_ctx *ctx, uint64_t film, uint64_t rgba, int half_float,
+                      float sample_scale, int x, int y, int w, int h, int offset, int stride);
+
+/* Multi-GPU film reduction inside ONE process (device/device_multi.cpp:374-393
+ * replaced by a device-side sum): films[i] lives on ctxs[i]; after the call
+ * films[0] holds the element-wise sum.  Peer copies over NVLink + one add
+ * kernel per peer.  The one-process-per-GPU path uses NCCL all-reduce through
+ * torch.distributed on the same device pointer instead (bench.py). */
+int b200_film_reduce(b200_ctx **ctxs, int n, const uint64_t *films, size_t n_floats);
+
+int b200_get_stats(b200_ctx *ctx, b200_stats *out);
+int b200_synchronize(b200_ctx *ctx);
+
+/* Tunables (0 keeps the default): paths per wavefront batch. */
+int b200_set_option(b200_ctx *ctx, const char *name, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_CYCLES_H */

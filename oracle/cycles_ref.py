@@ -169,7 +169,10 @@ class RefScene:
         """{name: (bytes, elem_size)} for every non-empty kernel array + '__data'."""
         out = {}
         for name in global_names():
-            a, es = self.global_array(name)
+            try:
+                a, es = self.global_array(name)
+            except KeyError:  # device-owned arrays (__texture_info) are not in DeviceScene
+                continue
             if a.size:
                 out[name] = (a, es)
         out["__data"] = (self.kernel_data(), 1)

@@ -266,21 +266,33 @@ int ref_scene_pass_stride(ref_scene *rs)
 }
 
 /* The flat device arrays exactly as handed to Device::mem_copy_to, looked up by
- * their kernel_textures.h name; read from the CPU device's KernelGlobals. */
+ * their kernel_textures.h name among the Scene's DeviceScene vectors
+ * (render/scene.h:65-132).  Works for any device (host copies). */
 int ref_scene_global(
     ref_scene *rs, const char *name, const void **ptr, uint64_t *count, uint32_t *elem_size)
 {
-  if (!rs->cpu)
-    return 1;
-  KernelGlobals *kg = &rs->cpu->kernel_globals;
-#define KERNEL_TEX(type, tname) \
-  if (strcmp(name, #tname) == 0) { \
-    *ptr = kg->tname.data; \
-    *count = kg->tname.width; \
-    *elem_size = sizeof(type); \
-    return 0; \
+  DeviceScene &d = rs->scene->dscene;
+  device_memory *all[] = {
+      &d.bvh_nodes, &d.bvh_leaf_nodes, &d.object_node, &d.prim_tri_index, &d.prim_tri_verts,
+      &d.prim_type, &d.prim_visibility, &d.prim_index, &d.prim_object, &d.prim_time,
+      &d.tri_shader, &d.tri_vnormal, &d.tri_vindex, &d.tri_patch, &d.tri_patch_uv, &d.curves,
+      &d.curve_keys, &d.patches, &d.objects, &d.object_motion_pass, &d.object_motion,
+      &d.object_flag, &d.object_volume_step, &d.camera_motion, &d.attributes_map,
+      &d.attributes_float, &d.attributes_float2, &d.attributes_float3, &d.attributes_uchar4,
+      &d.light_distribution, &d.lights, &d.light_background_marginal_cdf,
+      &d.light_background_conditional_cdf, &d.particles, &d.svm_nodes, &d.shaders,
+      &d.lookup_table, &d.sample_pattern_lut, &d.ies_lights};
+  for (size_t i = 0; i < sizeof(all) / sizeof(all[0]); i++) {
+    device_memory *m = all[i];
+    if (strcmp(m->name, name) == 0) {
+      *ptr = m->host_pointer;
+      *elem_size = (uint32_t)(m->data_elements * datatype_size(m->data_type));
+      *count = (*elem_size) ? m->memory_size() / (*elem_size) : 0;
+      if (!m->host_pointer)
+        *count = 0;
+      return 0;
+    }
   }
-#include "kernel/kernel_textures.h"
   return 1;
 }
 

@@ -1,0 +1,643 @@
+/* b200_cycles.cu - libb200cycles.so: the C ABI of include/b200_cycles.h and every
+ * CUDA kernel behind it (one translation unit; compiled for sm_100a only with
+ * -fmad=false, see Makefile).  Host code here is the thin runtime a Device
+ * needs: context, memory, by-name array binding, the BVH8 build + upload and
+ * the wavefront launch loop.  No CPU fallback: without a B200 b200_create fails.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+
+#include "b200_internal.h"
+#include "device_scene.cuh"
+#include "traverse.cuh"
+
+/* ------------------------------------------------------------------ utils */
+
+#define CUDA_TRY(ctx, call) \
+  do { \
+    cudaError_t err__ = (call); \
+    if (err__ != cudaSuccess) { \
+      set_error(ctx, std::string(#call) + ": " + cudaGetErrorString(err__)); \
+      return B200_ERR_CUDA; \
+    } \
+  } while (0)
+
+static void set_error(b200_ctx *ctx, const std::string &msg)
+{
+  if (ctx)
+    ctx->error = msg;
+}
+
+static int fail(b200_ctx *ctx, int code, const std::string &msg)
+{
+  set_error(ctx, msg);
+  return code;
+}
+
+struct DeviceGuard {
+  int prev = 0;
+  explicit DeviceGuard(int ordinal)
+  {
+    cudaGetDevice(&prev);
+    if (prev != ordinal)
+      cudaSetDevice(ordinal);
+  }
+  ~DeviceGuard()
+  {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != prev)
+      cudaSetDevice(prev);
+  }
+};
+
+/* device counter slots (ctx->d_counters) */
+enum {
+  CNT_WORK = 0,     /* persistent-kernel work cursor */
+  CNT_NODES = 1,    /* traversal statistics (counter build) */
+  CNT_TRIS = 2,
+  CNT_INSTANCES = 3,
+  CNT_ACTIVE = 4,   /* wavefront queue sizes */
+  CNT_NEXT = 5,
+  CNT_SHADOW = 6,
+  CNT_PRIMARY = 7,
+  CNT_BOUNCE = 8,
+  CNT_SHADOW_TOTAL = 9,
+  CNT_WORK2 = 10,
+  CNT_NODES_HI = 11,
+  CNT_TRIS_HI = 12,
+  CNT_NUM = 64
+};
+
+/* ------------------------------------------------------------ trace batch */
+
+/* Persistent warps: each warp claims 32 rays at a time from a global cursor
+ * (one atomic per warp), so the grid is sized to the machine (a multiple of the
+ * SM count), not to the batch. */
+template<bool ANY_HIT, bool COUNT>
+__global__ void __launch_bounds__(128)
+    k_trace_batch(const b200_ray *__restrict__ rays, b200_hit *__restrict__ hits, uint64_t n,
+                  unsigned int *counters)
+{
+  const unsigned lane = threadIdx.x & 31u;
+  TraceCounters cnt;
+  cnt.nodes = cnt.tris = cnt.instances = 0;
+  while (true) {
+    unsigned int base = 0;
+    if (lane == 0)
+      base = atomicAdd(&counters[CNT_WORK], 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n)
+      break;
+    const uint64_t i = (uint64_t)base + lane;
+    if (i < n) {
+      /* 32-byte ray record = two 128-bit loads */
+      const float4 r0 = __ldg((const float4 *)(rays + i) + 0);
+      const float4 r1 = __ldg((const float4 *)(rays + i) + 1);
+      TraceHit h;
+      h.t = r0.w;
+      h.u = h.v = 0.0f;
+      h.prim = -1;
+      h.object = -1;
+      if (r0.w != 0.0f) {
+        bvh8_intersect<ANY_HIT, COUNT>(mk3(r0), mk3(r1), r0.w, __float_as_uint(r1.w), h, cnt);
+      }
+      b200_hit out;
+      out.t = h.t;
+      out.u = h.u;
+      out.v = h.v;
+      out.prim = h.prim;
+      out.object = h.object;
+      out.type = (h.prim >= 0) ? (int)CY_PRIMITIVE_TRIANGLE : 0;
+      hits[i] = out;
+    }
+  }
+  if (COUNT) {
+    for (int o = 16; o > 0; o >>= 1) {
+      cnt.nodes += __shfl_xor_sync(0xffffffffu, cnt.nodes, o);
+      cnt.tris += __shfl_xor_sync(0xffffffffu, cnt.tris, o);
+      cnt.instances += __shfl_xor_sync(0xffffffffu, cnt.instances, o);
+    }
+    if (lane == 0) {
+      atomicAdd((unsigned long long *)&counters[16], (unsigned long long)cnt.nodes);
+      atomicAdd((unsigned long long *)&counters[18], (unsigned long long)cnt.tris);
+      atomicAdd((unsigned long long *)&counters[20], (unsigned long long)cnt.instances);
+    }
+  }
+}
+
+/* --------------------------------------------------------------- C ABI */
+
+extern "C" {
+
+int b200_abi_version(void)
+{
+  return B200_ABI_VERSION;
+}
+
+int b200_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess)
+    return 0;
+  return n;
+}
+
+int b200_device_name(int ordinal, char *name, size_t len, int *sm_major, int *sm_minor,
+                     uint64_t *total_mem, int *num_sms)
+{
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, ordinal) != cudaSuccess)
+    return B200_ERR_CUDA;
+  if (name && len) {
+    strncpy(name, prop.name, len - 1);
+    name[len - 1] = 0;
+  }
+  if (sm_major)
+    *sm_major = prop.major;
+  if (sm_minor)
+    *sm_minor = prop.minor;
+  if (total_mem)
+    *total_mem = prop.totalGlobalMem;
+  if (num_sms)
+    *num_sms = prop.multiProcessorCount;
+  return B200_OK;
+}
+
+b200_ctx *b200_create(int cuda_ordinal, char *err, size_t errlen)
+{
+  auto report = [&](const std::string &m) {
+    if (err && errlen) {
+      strncpy(err, m.c_str(), errlen - 1);
+      err[errlen - 1] = 0;
+    }
+  };
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    report(std::string("no CUDA device: ") + cudaGetErrorString(e));
+    return nullptr;
+  }
+  if (cuda_ordinal < 0 || cuda_ordinal >= n) {
+    report("CUDA ordinal out of range");
+    return nullptr;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cuda_ordinal) != cudaSuccess) {
+    report("cudaGetDeviceProperties failed");
+    return nullptr;
+  }
+  if (prop.major != 10) {
+    report(std::string("device ") + prop.name +
+           " is not sm_100: this library carries sm_100a code only");
+    return nullptr;
+  }
+  b200_ctx *ctx = new b200_ctx();
+  ctx->ordinal = cuda_ordinal;
+  ctx->num_sms = prop.multiProcessorCount;
+  DeviceGuard guard(cuda_ordinal);
+  bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess;
+  ok = ok && cudaEventCreate(&ctx->ev2) == cudaSuccess && cudaEventCreate(&ctx->ev3) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->d_counters, CNT_NUM * sizeof(unsigned int)) == cudaSuccess;
+  ok = ok && cudaMallocHost(&ctx->h_counters, CNT_NUM * sizeof(unsigned int)) == cudaSuccess;
+  if (!ok) {
+    report(std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError()));
+    delete ctx;
+    return nullptr;
+  }
+  cudaMemset(ctx->d_counters, 0, CNT_NUM * sizeof(unsigned int));
+  return ctx;
+}
+
+static void free_pool(b200_ctx *ctx);
+
+void b200_destroy(b200_ctx *ctx)
+{
+  if (!ctx)
+    return;
+  DeviceGuard guard(ctx->ordinal);
+  cudaStreamSynchronize(ctx->stream);
+  free_pool(ctx);
+  for (auto &a : ctx->allocs)
+    cudaFree((void *)a.first);
+  if (ctx->d_nodes)
+    cudaFree(ctx->d_nodes);
+  if (ctx->d_records)
+    cudaFree(ctx->d_records);
+  if (ctx->d_counters)
+    cudaFree(ctx->d_counters);
+  if (ctx->h_counters)
+    cudaFreeHost(ctx->h_counters);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaEventDestroy(ctx->ev2);
+  cudaEventDestroy(ctx->ev3);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *b200_last_error(b200_ctx *ctx)
+{
+  return ctx ? ctx->error.c_str() : "null context";
+}
+
+int b200_alloc(b200_ctx *ctx, size_t bytes, uint64_t *dptr)
+{
+  if (!ctx || !dptr)
+    return B200_ERR_INVALID;
+  DeviceGuard guard(ctx->ordinal);
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    return fail(ctx, B200_ERR_OOM, "out of device memory");
+  }
+  if (e != cudaSuccess)
+    return fail(ctx, B200_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  std::lock_guard<std::mutex> lock(ctx->mutex);
+  ctx->allocs[(uint64_t)p] = bytes;
+  ctx->mem_used += bytes;
+  *dptr = (uint64_t)p;
+  return B200_OK;
+}
+
+int b200_free(b200_ctx *ctx, uint64_t dptr)
+{
+  if (!ctx)
+    return B200_ERR_INVALID;
+  if (!dptr)
+    return B200_OK;
+  DeviceGuard guard(ctx->ordinal);
+  {
+    std::lock_guard<std::mutex> lock(ctx->mutex);
+    auto it = ctx->allocs.find(dptr);
+    if (it == ctx->allocs.end())
+      return fail(ctx, B200_ERR_INVALID, "b200_free: unknown pointer");
+    ctx->mem_used -= it->second;
+    ctx->allocs.erase(it);
+    /* drop any by-name binding of this buffer */
+    for (auto g = ctx->globals.begin(); g != ctx->globals.end();) {
+      if (g->second.dptr == dptr) {
+        g = ctx->globals.erase(g);
+        ctx->scene_dirty = true;
+      }
+      else
+        ++g;
+    }
+  }
+  cudaStreamSynchronize(ctx->stream);
+  CUDA_TRY(ctx, cudaFree((void *)dptr));
+  return B200_OK;
+}
+
+int b200_h2d(b200_ctx *ctx, uint64_t dptr, const void *host, size_t offset, size_t bytes)
+{
+  if (!ctx || !dptr || (!host && bytes))
+    return B200_ERR_INVALID;
+  DeviceGuard guard(ctx->ordinal);
+  CUDA_TRY(ctx, cudaMemcpyAsync((char *)dptr + offset, host, bytes, cudaMemcpyHostToDevice,
+                                ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+int b200_d2h(b200_ctx *ctx, uint64_t dptr, void *host, size_t offset, size_t bytes)
+{
+  if (!ctx || !dptr || (!host && bytes))
+    return B200_ERR_INVALID;
+  DeviceGuard guard(ctx->ordinal);
+  CUDA_TRY(ctx, cudaMemcpyAsync(host, (const char *)dptr + offset, bytes, cudaMemcpyDeviceToHost,
+                                ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+int b200_zero(b200_ctx *ctx, uint64_t dptr, size_t offset, size_t bytes)
+{
+  if (!ctx || !dptr)
+    return B200_ERR_INVALID;
+  DeviceGuard guard(ctx->ordinal);
+  CUDA_TRY(ctx, cudaMemsetAsync((char *)dptr + offset, 0, bytes, ctx->stream));
+  return B200_OK;
+}
+
+size_t b200_mem_used(b200_ctx *ctx)
+{
+  return ctx ? ctx->mem_used : 0;
+}
+
+int b200_synchronize(b200_ctx *ctx)
+{
+  if (!ctx)
+    return B200_ERR_INVALID;
+  DeviceGuard guard(ctx->ordinal);
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+/* SVM opcodes / closures the shading kernels implement; anything else in a
+ * bound __svm_nodes stream is refused up front instead of rendering wrongly. */
+static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why);
+
+int b200_bind_global(b200_ctx *ctx, const char *name, uint64_t dptr, const void *host,
+                     size_t bytes)
+{
+  if (!ctx || !name)
+    return B200_ERR_INVALID;
+  static const char *known[] = {
+#define KNOWN(n) #n,
+      KNOWN(__bvh_nodes) KNOWN(__bvh_leaf_nodes) KNOWN(__prim_tri_verts) KNOWN(__prim_tri_index)
+          KNOWN(__prim_type) KNOWN(__prim_visibility) KNOWN(__prim_index) KNOWN(__prim_object)
+              KNOWN(__object_node) KNOWN(__prim_time) KNOWN(__objects) KNOWN(__object_motion_pass)
+                  KNOWN(__object_motion) KNOWN(__object_flag) KNOWN(__object_volume_step)
+                      KNOWN(__camera_motion) KNOWN(__tri_shader) KNOWN(__tri_vnormal)
+                          KNOWN(__tri_vindex) KNOWN(__tri_patch) KNOWN(__tri_patch_uv)
+                              KNOWN(__curves) KNOWN(__curve_keys) KNOWN(__patches)
+                                  KNOWN(__attributes_map) KNOWN(__attributes_float)
+                                      KNOWN(__attributes_float2) KNOWN(__attributes_float3)
+                                          KNOWN(__attributes_uchar4) KNOWN(__light_distribution)
+                                              KNOWN(__lights)
+                                                  KNOWN(__light_background_marginal_cdf)
+                                                      KNOWN(__light_background_conditional_cdf)
+                                                          KNOWN(__particles) KNOWN(__svm_nodes)
+                                                              KNOWN(__shaders)
+                                                                  KNOWN(__lookup_table)
+                                                                      KNOWN(__sample_pattern_lut)
+                                                                          KNOWN(__texture_info)
+                                                                              KNOWN(__ies)
+#undef KNOWN
+  };
+  bool found = false;
+  for (const char *k : known)
+    if (strcmp(k, name) == 0)
+      found = true;
+  if (!found)
+    return fail(ctx, B200_ERR_INVALID, std::string("unknown kernel array ") + name);
+
+  static const char *keep_host[] = {"__bvh_nodes",     "__bvh_leaf_nodes", "__prim_tri_verts",
+                                    "__prim_tri_index", "__prim_type",      "__prim_visibility",
+                                    "__prim_object",    "__object_node",    "__objects",
+                                    "__svm_nodes",      "__lights",         "__curves"};
+  HostArray ha;
+  ha.dptr = dptr;
+  ha.bytes = bytes;
+  bool keep = false;
+  for (const char *k : keep_host)
+    if (strcmp(k, name) == 0)
+      keep = true;
+  if (keep && bytes) {
+    ha.host.resize(bytes);
+    if (host) {
+      memcpy(ha.host.data(), host, bytes);
+    }
+    else {
+      int rc = b200_d2h(ctx, dptr, ha.host.data(), 0, bytes);
+      if (rc)
+        return rc;
+    }
+  }
+  if (strcmp(name, "__svm_nodes") == 0 && bytes) {
+    std::string why;
+    if (!svm_validate((const uint32_t *)ha.host.data(), bytes / 16, why))
+      return fail(ctx, B200_ERR_UNSUPPORTED, why);
+  }
+  if ((strcmp(name, "__curves") == 0 || strcmp(name, "__curve_keys") == 0) && bytes)
+    return fail(ctx, B200_ERR_UNSUPPORTED, "hair curves are outside the hot-path scope");
+  std::lock_guard<std::mutex> lock(ctx->mutex);
+  ctx->globals[name] = std::move(ha);
+  ctx->scene_dirty = true;
+  return B200_OK;
+}
+
+int b200_set_kernel_data(b200_ctx *ctx, const void *kernel_data, size_t bytes)
+{
+  if (!ctx || !kernel_data)
+    return B200_ERR_INVALID;
+  if (bytes != SIZEOF_KERNEL_DATA)
+    return fail(ctx, B200_ERR_INVALID, "KernelData size mismatch (ABI)");
+  ctx->kernel_data.assign((const uint8_t *)kernel_data, (const uint8_t *)kernel_data + bytes);
+  ctx->have_data = true;
+  ctx->scene_dirty = true;
+  return B200_OK;
+}
+
+} /* extern "C" */
+
+/* -------------------------------------------------- scene (re)build + upload */
+
+template<typename T> static T kd_host(const b200_ctx *ctx, int off)
+{
+  T v;
+  memcpy(&v, ctx->kernel_data.data() + off, sizeof(T));
+  return v;
+}
+
+static const HostArray *find_global(b200_ctx *ctx, const char *name)
+{
+  auto it = ctx->globals.find(name);
+  return (it == ctx->globals.end()) ? nullptr : &it->second;
+}
+
+static int check_scope(b200_ctx *ctx);
+
+static int prepare_scene(b200_ctx *ctx)
+{
+  if (!ctx->scene_dirty)
+    return B200_OK;
+  if (!ctx->have_data)
+    return fail(ctx, B200_ERR_NOT_READY, "KernelData (\"__data\") was never uploaded");
+  const HostArray *nodes = find_global(ctx, "__bvh_nodes");
+  const HostArray *leaves = find_global(ctx, "__bvh_leaf_nodes");
+  const HostArray *verts = find_global(ctx, "__prim_tri_verts");
+  const HostArray *tri_index = find_global(ctx, "__prim_tri_index");
+  const HostArray *vis = find_global(ctx, "__prim_visibility");
+  const HostArray *pobj = find_global(ctx, "__prim_object");
+  const HostArray *onode = find_global(ctx, "__object_node");
+  const HostArray *objects = find_global(ctx, "__objects");
+  if (!leaves || !verts || !tri_index || !vis || !pobj || !objects)
+    return fail(ctx, B200_ERR_NOT_READY, "BVH arrays are not bound (scene without geometry?)");
+  int rc = check_scope(ctx);
+  if (rc)
+    return rc;
+
+  b200::BVH2Input in;
+  memset(&in, 0, sizeof(in));
+  in.nodes = nodes ? (const float *)nodes->host.data() : nullptr;
+  in.num_nodes_f4 = nodes ? nodes->bytes / 16 : 0;
+  in.leaf_nodes = (const float *)leaves->host.data();
+  in.num_leaf_nodes_f4 = leaves->bytes / 16;
+  in.prim_tri_verts = (const float *)verts->host.data();
+  in.prim_tri_index = (const uint32_t *)tri_index->host.data();
+  in.prim_visibility = (const uint32_t *)vis->host.data();
+  in.prim_object = (const uint32_t *)pobj->host.data();
+  in.num_prims = tri_index->bytes / 4;
+  in.object_node = onode ? (const int32_t *)onode->host.data() : nullptr;
+  in.objects = objects->host.data();
+  in.object_stride = SIZEOF_KERNEL_OBJECT;
+  in.object_tfm_offset = KO_TFM;
+  in.num_objects = objects->bytes / SIZEOF_KERNEL_OBJECT;
+  in.root = kd_host<int>(ctx, KD_BVH_ROOT);
+  in.node_unaligned_flag = CY_PATH_RAY_NODE_UNALIGNED;
+  in.primitive_all = CY_PRIMITIVE_ALL;
+  in.primitive_triangle = CY_PRIMITIVE_TRIANGLE;
+
+  b200::BVH8Output out;
+  std::string err;
+  if (!b200::build_bvh8(in, out, err))
+    return fail(ctx, B200_ERR_UNSUPPORTED, "BVH8 build: " + err);
+
+  DeviceGuard guard(ctx->ordinal);
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_nodes)
+    cudaFree(ctx->d_nodes);
+  if (ctx->d_records)
+    cudaFree(ctx->d_records);
+  ctx->d_nodes = ctx->d_records = nullptr;
+  const size_t node_bytes = out.nodes.size() * sizeof(BVH8Node);
+  const size_t rec_bytes = out.records.size() * sizeof(float);
+  CUDA_TRY(ctx, cudaMalloc(&ctx->d_nodes, std::max<size_t>(node_bytes, 16)));
+  CUDA_TRY(ctx, cudaMalloc(&ctx->d_records, std::max<size_t>(rec_bytes, 16)));
+  CUDA_TRY(ctx, cudaMemcpy(ctx->d_nodes, out.nodes.data(), node_bytes, cudaMemcpyHostToDevice));
+  CUDA_TRY(ctx,
+           cudaMemcpy(ctx->d_records, out.records.data(), rec_bytes, cudaMemcpyHostToDevice));
+
+  ctx->bvh_info.num_nodes = out.nodes.size();
+  ctx->bvh_info.num_tri_records = out.records.size() / 12;
+  ctx->bvh_info.num_triangles = out.num_triangles;
+  ctx->bvh_info.num_instances = out.num_instances;
+  ctx->bvh_info.node_bytes = node_bytes;
+  ctx->bvh_info.tri_bytes = rec_bytes;
+  ctx->bvh_info.build_ms = out.build_ms;
+  ctx->bvh_info.sah_cost = out.sah_cost;
+  ctx->bvh_info.max_depth = out.max_depth;
+
+  DeviceScene ds;
+  memset(&ds, 0, sizeof(ds));
+  ds.nodes = (const uint4 *)ctx->d_nodes;
+  ds.records = (const float4 *)ctx->d_records;
+  ds.bvh_root = out.root;
+  auto ptr = [&](const char *name) -> uint64_t {
+    const HostArray *h = find_global(ctx, name);
+    return h ? h->dptr : 0;
+  };
+  ds.prim_tri_verts = (const float4 *)ptr("__prim_tri_verts");
+  ds.prim_tri_index = (const uint32_t *)ptr("__prim_tri_index");
+  ds.prim_index = (const uint32_t *)ptr("__prim_index");
+  ds.prim_object = (const uint32_t *)ptr("__prim_object");
+  ds.objects = (const uint8_t *)ptr("__objects");
+  ds.object_flag = (const uint32_t *)ptr("__object_flag");
+  ds.tri_shader = (const uint32_t *)ptr("__tri_shader");
+  ds.tri_vnormal = (const float4 *)ptr("__tri_vnormal");
+  ds.tri_vindex = (const uint4 *)ptr("__tri_vindex");
+  ds.lights = (const uint8_t *)ptr("__lights");
+  ds.light_distribution = (const uint8_t *)ptr("__light_distribution");
+  ds.shaders = (const uint8_t *)ptr("__shaders");
+  ds.svm_nodes = (const uint4 *)ptr("__svm_nodes");
+  ds.lookup_table = (const float *)ptr("__lookup_table");
+  ds.sample_pattern_lut = (const uint32_t *)ptr("__sample_pattern_lut");
+  memcpy(ds.kdata, ctx->kernel_data.data(), SIZEOF_KERNEL_DATA);
+  CUDA_TRY(ctx, cudaMemcpyToSymbol(g_scene, &ds, sizeof(ds)));
+  ctx->scene_dirty = false;
+  return B200_OK;
+}
+
+static int launch_grid(const b200_ctx *ctx, int blocks_per_sm)
+{
+  return ctx->num_sms * blocks_per_sm;
+}
+
+#include "wavefront.cuh"
+
+extern "C" {
+
+int b200_build_bvh(b200_ctx *ctx, b200_bvh_info *info)
+{
+  if (!ctx)
+    return B200_ERR_INVALID;
+  ctx->scene_dirty = true;
+  int rc = prepare_scene(ctx);
+  if (rc)
+    return rc;
+  if (info)
+    *info = ctx->bvh_info;
+  return B200_OK;
+}
+
+int b200_trace_batch(b200_ctx *ctx, uint64_t rays, uint64_t hits, uint64_t n, int any_hit)
+{
+  if (!ctx || !rays || !hits)
+    return B200_ERR_INVALID;
+  if (n >= 0xffffffe0ull)
+    return fail(ctx, B200_ERR_INVALID, "batch too large (max 2^32-32 rays)");
+  int rc = prepare_scene(ctx);
+  if (rc)
+    return rc;
+  DeviceGuard guard(ctx->ordinal);
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, CNT_NUM * sizeof(unsigned int), ctx->stream));
+  const int grid = launch_grid(ctx, 8);
+  const bool count = ctx->opt_count_traversal != 0;
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  const b200_ray *r = (const b200_ray *)rays;
+  b200_hit *h = (b200_hit *)hits;
+  if (any_hit) {
+    if (count)
+      k_trace_batch<true, true><<<grid, 128, 0, ctx->stream>>>(r, h, n, ctx->d_counters);
+    else
+      k_trace_batch<true, false><<<grid, 128, 0, ctx->stream>>>(r, h, n, ctx->d_counters);
+  }
+  else {
+    if (count)
+      k_trace_batch<false, true><<<grid, 128, 0, ctx->stream>>>(r, h, n, ctx->d_counters);
+    else
+      k_trace_batch<false, false><<<grid, 128, 0, ctx->stream>>>(r, h, n, ctx->d_counters);
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, CNT_NUM * sizeof(unsigned int),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0.0f;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  memset(&ctx->stats, 0, sizeof(ctx->stats));
+  if (any_hit)
+    ctx->stats.shadow_rays = n;
+  else
+    ctx->stats.primary_rays = n;
+  memcpy(&ctx->stats.nodes_visited, &ctx->h_counters[16], 8);
+  memcpy(&ctx->stats.tris_tested, &ctx->h_counters[18], 8);
+  memcpy(&ctx->stats.instances_entered, &ctx->h_counters[20], 8);
+  ctx->stats.kernel_launches = 1;
+  ctx->stats.device_ms = ms;
+  ctx->stats.traverse_ms = ms;
+  return B200_OK;
+}
+
+int b200_get_stats(b200_ctx *ctx, b200_stats *out)
+{
+  if (!ctx || !out)
+    return B200_ERR_INVALID;
+  *out = ctx->stats;
+  return B200_OK;
+}
+
+int b200_set_option(b200_ctx *ctx, const char *name, int64_t value)
+{
+  if (!ctx || !name)
+    return B200_ERR_INVALID;
+  if (strcmp(name, "batch_paths") == 0) {
+    ctx->opt_batch_paths = value;
+    free_pool(ctx);
+  }
+  else if (strcmp(name, "count_traversal") == 0)
+    ctx->opt_count_traversal = value;
+  else
+    return fail(ctx, B200_ERR_INVALID, std::string("unknown option ") + name);
+  return B200_OK;
+}
+
+} /* extern "C" */

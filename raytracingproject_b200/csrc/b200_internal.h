@@ -1,0 +1,56 @@
+/* b200_internal.h - host-side context behind the C ABI (include/b200_cycles.h). */
+#ifndef B200_INTERNAL_H
+#define B200_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200_cycles.h"
+#include "../../include/cycles_abi.h"
+#include "bvh8_build.h"
+
+struct HostArray {
+  uint64_t dptr = 0;
+  size_t bytes = 0;
+  std::vector<uint8_t> host; /* kept only for the arrays the BVH8 build / validation needs */
+};
+
+struct PathPool; /* wavefront state, defined in b200_cycles.cu */
+
+struct b200_ctx {
+  int ordinal = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  std::string error;
+  std::mutex mutex;
+
+  std::map<uint64_t, size_t> allocs; /* dptr -> bytes */
+  size_t mem_used = 0;
+
+  std::map<std::string, HostArray> globals; /* kernel_textures.h name -> binding */
+  std::vector<uint8_t> kernel_data;
+  bool scene_dirty = true; /* BVH8 / constant block must be (re)built */
+  bool have_data = false;
+
+  /* BVH8 on the device */
+  void *d_nodes = nullptr;
+  void *d_records = nullptr;
+  b200_bvh_info bvh_info = {};
+
+  PathPool *pool = nullptr;
+  int64_t opt_batch_paths = 0;
+  int64_t opt_count_traversal = 0;
+
+  /* trace_batch work counter + stats */
+  unsigned int *d_counters = nullptr; /* small block of device counters */
+  unsigned int *h_counters = nullptr; /* pinned mirror */
+  b200_stats stats = {};
+};
+
+#endif

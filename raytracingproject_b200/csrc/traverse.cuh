@@ -1,0 +1,332 @@
+/* traverse.cuh - stack traversal of the compressed BVH8 (bvh8.h) for one ray.
+ *
+ * Semantics follow the reference's BVH2 walker, so that hit records mean the
+ * same thing:
+ *   - scene_intersect / bvh_intersect       kernel/bvh/bvh.h:154-237,
+ *                                            kernel/bvh/bvh_traversal.h:34-227
+ *   - triangle test (generic scalar branch)  util/util_math_intersect.h:88-195,
+ *                                            geom/geom_triangle_intersect.h:25-72
+ *   - instance push / pop                    geom/geom_object.h:412-460
+ *   - shadow early-out (PATH_RAY_SHADOW_OPAQUE) bvh_traversal.h:144-147
+ * What is new is the structure walked: an 8-wide quantised node fetched with
+ * five 128-bit loads, octant-ordered child visiting with a hit bit-mask, and
+ * (node group, triangle group) stack entries after Ylitie et al. 2017.
+ *
+ * The triangle test is written without FMA contraction (the file is compiled
+ * with -fmad=false) in the reference's operation order: u, v, t and the
+ * accept/reject decision are bit-identical to the oracle's for the same ray in
+ * the same space.  The box test uses explicit fmaf and is only conservative.
+ */
+#ifndef B200_TRAVERSE_CUH
+#define B200_TRAVERSE_CUH
+
+#include "device_scene.cuh"
+
+#define BVH8_STACK_SIZE 64
+#define BVH8_SENTINEL 0xffffffffu
+
+struct TraceHit {
+  float t, u, v;
+  int prim;   /* -1 = miss */
+  int object; /* -1 = OBJECT_NONE */
+};
+
+struct TraceCounters {
+  uint32_t nodes, tris, instances;
+};
+
+/* geom_object.h:414-420 */
+CY_DEV f3 bvh_clamp_direction(f3 dir)
+{
+  const float ooeps = 8.271806E-25f;
+  return mk3((fabsf(dir.x) > ooeps) ? dir.x : copysignf(ooeps, dir.x),
+             (fabsf(dir.y) > ooeps) ? dir.y : copysignf(ooeps, dir.y),
+             (fabsf(dir.z) > ooeps) ? dir.z : copysignf(ooeps, dir.z));
+}
+
+CY_DEV uint32_t sign_extend_s8x4(uint32_t x)
+{
+  uint32_t r;
+  asm("prmt.b32 %0, %1, 0x0, 0x0000BA98;" : "=r"(r) : "r"(x));
+  return r;
+}
+
+CY_DEV float byte_to_float(uint32_t x, int j)
+{
+  return __uint2float_rn((x >> (8 * j)) & 0xffu);
+}
+
+/* util_math_intersect.h:88-195, scalar branch.  Returns true and u,v,t on a hit
+ * closer than ray_t. */
+CY_DEV bool ray_triangle_intersect(
+    f3 P, f3 dir, float ray_t, f3 tri_a, f3 tri_b, f3 tri_c, float *isect_u, float *isect_v,
+    float *isect_t)
+{
+  const f3 v0 = tri_c - P;
+  const f3 v1 = tri_a - P;
+  const f3 v2 = tri_b - P;
+
+  const f3 e0 = v2 - v0;
+  const f3 e1 = v0 - v1;
+  const f3 e2 = v1 - v2;
+
+  const float U = dot(cross(v2 + v0, e0), dir);
+  const float V = dot(cross(v0 + v1, e1), dir);
+  const float W = dot(cross(v1 + v2, e2), dir);
+
+  const float minUVW = fminf(U, fminf(V, W));
+  const float maxUVW = fmaxf(U, fmaxf(V, W));
+  if (minUVW < 0.0f && maxUVW > 0.0f)
+    return false;
+
+  const f3 Ng1 = cross(e1, e0);
+  const f3 Ng = Ng1 + Ng1;
+  const float den = dot(Ng, dir);
+  if (den == 0.0f)
+    return false;
+
+  const float T = dot(v0, Ng);
+  const int sign_den = (__float_as_int(den) & 0x80000000);
+  const float sign_T = xor_signmask(T, sign_den);
+  if ((sign_T < 0.0f) || (sign_T > ray_t * xor_signmask(den, sign_den)))
+    return false;
+
+  const float inv_den = 1.0f / den;
+  *isect_u = U * inv_den;
+  *isect_v = V * inv_den;
+  *isect_t = T * inv_den;
+  return true;
+}
+
+struct RaySpace {
+  f3 P, dir, idir;
+  uint32_t oct_inv4;
+};
+
+CY_DEV void ray_space_setup(RaySpace &rs, f3 P, f3 D)
+{
+  rs.P = P;
+  rs.dir = bvh_clamp_direction(D);
+  rs.idir = mk3(1.0f / rs.dir.x, 1.0f / rs.dir.y, 1.0f / rs.dir.z);
+  rs.oct_inv4 = ((rs.dir.x < 0.0f) ? 0u : 0x04040404u) | ((rs.dir.y < 0.0f) ? 0u : 0x02020202u) |
+                ((rs.dir.z < 0.0f) ? 0u : 0x01010101u);
+}
+
+/* Intersects the 8 quantised child boxes of node `node_index`; returns the hit
+ * mask: bits 24..31 inner children (ordered front to back for this octant),
+ * bits 0..23 leaf records relative to prim_base. */
+CY_DEV uint32_t bvh8_node_intersect(const RaySpace &rs,
+                                    float tmax,
+                                    uint32_t node_index,
+                                    uint32_t &child_base,
+                                    uint32_t &prim_base,
+                                    uint32_t &imask)
+{
+  const uint4 *np = g_scene.nodes + (size_t)node_index * 5;
+  const uint4 n0 = __ldg(np + 0);
+  const uint4 n1 = __ldg(np + 1);
+  const uint4 n2 = __ldg(np + 2);
+  const uint4 n3 = __ldg(np + 3);
+  const uint4 n4 = __ldg(np + 4);
+
+  const uint32_t e_imask = n0.w;
+  imask = e_imask >> 24;
+  child_base = n1.x;
+  prim_base = n1.y;
+
+  const float adjx = __uint_as_float((e_imask & 0xffu) << 23) * rs.idir.x;
+  const float adjy = __uint_as_float(((e_imask >> 8) & 0xffu) << 23) * rs.idir.y;
+  const float adjz = __uint_as_float(((e_imask >> 16) & 0xffu) << 23) * rs.idir.z;
+  const float orgx = (__uint_as_float(n0.x) - rs.P.x) * rs.idir.x;
+  const float orgy = (__uint_as_float(n0.y) - rs.P.y) * rs.idir.y;
+  const float orgz = (__uint_as_float(n0.z) - rs.P.z) * rs.idir.z;
+
+  const bool negx = rs.dir.x < 0.0f, negy = rs.dir.y < 0.0f, negz = rs.dir.z < 0.0f;
+  uint32_t hitmask = 0;
+
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const uint32_t meta4 = h ? n1.w : n1.z;
+    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+    const uint32_t bit_index4 = (meta4 ^ (rs.oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+
+    const uint32_t qlox = h ? n2.y : n2.x, qloy = h ? n2.w : n2.z;
+    const uint32_t qloz = h ? n3.y : n3.x, qhix = h ? n3.w : n3.z;
+    const uint32_t qhiy = h ? n4.y : n4.x, qhiz = h ? n4.w : n4.z;
+
+    const uint32_t xn = negx ? qhix : qlox, xf = negx ? qlox : qhix;
+    const uint32_t yn = negy ? qhiy : qloy, yf = negy ? qloy : qhiy;
+    const uint32_t zn = negz ? qhiz : qloz, zf = negz ? qloz : qhiz;
+
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float tnx = fmaf(byte_to_float(xn, j), adjx, orgx);
+      const float tny = fmaf(byte_to_float(yn, j), adjy, orgy);
+      const float tnz = fmaf(byte_to_float(zn, j), adjz, orgz);
+      const float tfx = fmaf(byte_to_float(xf, j), adjx, orgx);
+      const float tfy = fmaf(byte_to_float(yf, j), adjy, orgy);
+      const float tfz = fmaf(byte_to_float(zf, j), adjz, orgz);
+      /* a few ulps of slack in both directions: the planes are reconstructed in
+       * a per-node frame, keep the test conservative against rounding */
+      const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f)) * 0.9999995f;
+      const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax)) * 1.0000005f;
+      if (cmin <= cmax) {
+        const uint32_t bits = (child_bits4 >> (8 * j)) & 0xffu;
+        const uint32_t index = (bit_index4 >> (8 * j)) & 0xffu;
+        hitmask |= bits << index;
+      }
+    }
+  }
+  return hitmask;
+}
+
+/* Closest hit (ANY_HIT = false) or occlusion (ANY_HIT = true) for one ray.
+ * P, D, tmax are Ray::P, Ray::D, Ray::t; visibility is the PATH_RAY_* mask.
+ * Returns true on a hit; for closest hits `hit` is the Intersection. */
+template<bool ANY_HIT, bool COUNT>
+__device__ __forceinline__ bool bvh8_intersect(
+    f3 P, f3 D, float tmax, uint32_t visibility, TraceHit &hit, TraceCounters &cnt)
+{
+  uint2 stack[BVH8_STACK_SIZE];
+  int sp = 0;
+
+  RaySpace rs;
+  ray_space_setup(rs, P, D);
+
+  hit.t = tmax;
+  hit.u = 0.0f;
+  hit.v = 0.0f;
+  hit.prim = -1;
+  hit.object = -1;
+
+  int cur_object = -1;     /* OBJECT_NONE while in world space */
+  float world_tmax = tmax; /* world-space limit saved while inside an instance */
+  float inst_len = 1.0f;
+  bool inst_hit = false;
+
+  uint2 G = make_uint2(g_scene.bvh_root, 0x80000000u); /* node group */
+  uint2 Gt = make_uint2(0u, 0u);                       /* leaf-record group */
+
+  while (true) {
+    if (G.y & 0xff000000u) {
+      const uint32_t hits_imask = G.y;
+      const uint32_t child_bit_index = 31u - (uint32_t)__clz((int)hits_imask);
+      G.y &= ~(1u << child_bit_index);
+      if (G.y & 0xff000000u) {
+        if (sp < BVH8_STACK_SIZE)
+          stack[sp++] = G;
+      }
+      const uint32_t slot_index = (child_bit_index - 24u) ^ (rs.oct_inv4 & 0xffu);
+      const uint32_t relative_index = __popc(hits_imask & ~(0xffffffffu << slot_index) & 0xffu);
+      const uint32_t node_index = G.x + relative_index;
+
+      uint32_t child_base, prim_base, imask;
+      const uint32_t hitmask = bvh8_node_intersect(rs, tmax, node_index, child_base, prim_base,
+                                                   imask);
+      if (COUNT)
+        cnt.nodes++;
+      G = make_uint2(child_base, (hitmask & 0xff000000u) | imask);
+      Gt = make_uint2(prim_base, hitmask & 0x00ffffffu);
+    }
+    else {
+      Gt = G;
+      G = make_uint2(0u, 0u);
+    }
+
+    /* leaf records */
+    while (Gt.y != 0u) {
+      const uint32_t bit = (uint32_t)__ffs((int)Gt.y) - 1u;
+      Gt.y &= ~(1u << bit);
+      const float4 *rp = g_scene.records + (size_t)(Gt.x + bit) * 3;
+      const float4 ra = __ldg(rp + 0);
+      const int tag = __float_as_int(ra.w);
+      if (tag >= 0) {
+        const float4 rb = __ldg(rp + 1);
+        const float4 rc = __ldg(rp + 2);
+        if (COUNT)
+          cnt.tris++;
+        float t, u, v;
+        if (ray_triangle_intersect(rs.P, rs.dir, tmax, mk3(ra), mk3(rb), mk3(rc), &u, &v, &t)) {
+          if (__float_as_uint(rb.w) & visibility) {
+            hit.prim = tag;
+            hit.object = cur_object;
+            hit.u = u;
+            hit.v = v;
+            hit.t = t;
+            tmax = t;
+            if (ANY_HIT)
+              return true;
+            if (cur_object >= 0)
+              inst_hit = true;
+          }
+        }
+      }
+      else if (__float_as_uint(ra.y) & visibility) {
+        /* instance push - geom_object.h:427-443 */
+        const int object = ~tag;
+        if (COUNT)
+          cnt.instances++;
+        if (G.y & 0xff000000u) {
+          if (sp < BVH8_STACK_SIZE)
+            stack[sp++] = G;
+        }
+        if (Gt.y != 0u) {
+          if (sp < BVH8_STACK_SIZE)
+            stack[sp++] = Gt;
+        }
+        if (sp < BVH8_STACK_SIZE)
+          stack[sp++] = make_uint2(BVH8_SENTINEL, 0u);
+
+        const tfm34 itfm = object_itfm(object);
+        float len;
+        const f3 oP = transform_point(itfm, P);
+        const f3 oD = normalize_len(transform_direction(itfm, D), &len);
+        ray_space_setup(rs, oP, oD);
+        world_tmax = tmax;
+        inst_len = len;
+        inst_hit = false;
+        if (tmax != FLT_MAX)
+          tmax *= len;
+        cur_object = object;
+
+        G = make_uint2(__float_as_uint(ra.x), 0x80000000u);
+        Gt = make_uint2(0u, 0u);
+      }
+    }
+
+    /* pop */
+    if ((G.y & 0xff000000u) == 0u) {
+      bool done = false;
+      while (true) {
+        if (sp == 0) {
+          done = true;
+          break;
+        }
+        G = stack[--sp];
+        if (G.x == BVH8_SENTINEL) {
+          /* instance pop - geom_object.h:447-460 */
+          if (inst_hit) {
+            tmax = tmax / inst_len;
+            hit.t = tmax;
+          }
+          else {
+            tmax = world_tmax;
+          }
+          ray_space_setup(rs, P, D);
+          cur_object = -1;
+          inst_hit = false;
+          continue;
+        }
+        break;
+      }
+      if (done)
+        break;
+    }
+  }
+
+  return hit.prim >= 0;
+}
+
+#endif /* B200_TRAVERSE_CUH */

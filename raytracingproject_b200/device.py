@@ -1,0 +1,300 @@
+"""Python host-side mirror of the reference Device interface for the B200
+path-tracing device (intern/cycles/device/device.h:288-500), over the C ABI of
+include/b200_cycles.h (raytracingproject_b200/libb200cycles.so).
+
+Method names and argument meaning follow the reference: mem_alloc / mem_copy_to /
+mem_copy_from / mem_zero / mem_free act on a `DeviceMemory` handle the way
+Device::mem_* act on a ccl::device_memory (device/device_memory.h:198-320);
+const_copy_to("__data", ...) is Device::const_copy_to; task RENDER is
+`render_tile`.  Errors are latched like Device::set_error (device.h:341-348)
+AND raised, because Python callers do not poll have_error().
+
+There is no CPU fallback: constructing a device without the CUDA library or
+without a B200 raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200cycles.so")
+
+RAY_DTYPE = np.dtype(
+    [("P", "<f4", 3), ("t", "<f4"), ("D", "<f4", 3), ("visibility", "<u4")], align=False)
+HIT_DTYPE = np.dtype(
+    [("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("prim", "<i4"), ("object", "<i4"), ("type", "<i4")],
+    align=False)
+
+# device_memory.h:35-42
+MEM_READ_ONLY, MEM_READ_WRITE, MEM_DEVICE_ONLY, MEM_GLOBAL, MEM_TEXTURE, MEM_PIXELS = range(6)
+
+EXPORTS = [
+    "b200_abi_version", "b200_device_count", "b200_device_name", "b200_create", "b200_destroy",
+    "b200_last_error", "b200_alloc", "b200_free", "b200_h2d", "b200_d2h", "b200_zero",
+    "b200_mem_used", "b200_bind_global", "b200_set_kernel_data", "b200_build_bvh", "b200_render",
+    "b200_trace_batch", "b200_film_convert", "b200_film_reduce", "b200_get_stats",
+    "b200_synchronize", "b200_set_option",
+]
+
+
+class WorkTile(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("w", C.c_int32), ("h", C.c_int32),
+                ("start_sample", C.c_int32), ("num_samples", C.c_int32),
+                ("offset", C.c_int32), ("stride", C.c_int32), ("buffer", C.c_uint64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("primary_rays", C.c_uint64), ("bounce_rays", C.c_uint64),
+                ("shadow_rays", C.c_uint64), ("nodes_visited", C.c_uint64),
+                ("tris_tested", C.c_uint64), ("instances_entered", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("device_ms", C.c_double),
+                ("traverse_ms", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class BVHInfo(C.Structure):
+    _fields_ = [("num_nodes", C.c_uint64), ("num_tri_records", C.c_uint64),
+                ("num_triangles", C.c_uint64), ("num_instances", C.c_uint64),
+                ("node_bytes", C.c_uint64), ("tri_bytes", C.c_uint64),
+                ("build_ms", C.c_double), ("sah_cost", C.c_float), ("max_depth", C.c_uint32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the C-ABI library and declare the prototypes.  Raises if missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "%s is missing - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C raytracingproject_b200/csrc).  There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, u64, sz = C.c_void_p, C.c_uint64, C.c_size_t
+    L.b200_create.restype = vp
+    L.b200_create.argtypes = [C.c_int, C.c_char_p, sz]
+    L.b200_destroy.argtypes = [vp]
+    L.b200_last_error.restype = C.c_char_p
+    L.b200_last_error.argtypes = [vp]
+    L.b200_device_name.argtypes = [C.c_int, C.c_char_p, sz, C.POINTER(C.c_int),
+                                   C.POINTER(C.c_int), C.POINTER(u64), C.POINTER(C.c_int)]
+    L.b200_alloc.argtypes = [vp, sz, C.POINTER(u64)]
+    L.b200_free.argtypes = [vp, u64]
+    L.b200_h2d.argtypes = [vp, u64, vp, sz, sz]
+    L.b200_d2h.argtypes = [vp, u64, vp, sz, sz]
+    L.b200_zero.argtypes = [vp, u64, sz, sz]
+    L.b200_mem_used.restype = sz
+    L.b200_mem_used.argtypes = [vp]
+    L.b200_bind_global.argtypes = [vp, C.c_char_p, u64, vp, sz]
+    L.b200_set_kernel_data.argtypes = [vp, vp, sz]
+    L.b200_build_bvh.argtypes = [vp, C.POINTER(BVHInfo)]
+    L.b200_render.argtypes = [vp, C.POINTER(WorkTile), vp]
+    L.b200_trace_batch.argtypes = [vp, u64, u64, u64, C.c_int]
+    L.b200_film_convert.argtypes = [vp, u64, u64, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.c_int]
+    L.b200_film_reduce.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(u64), sz]
+    L.b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.b200_synchronize.argtypes = [vp]
+    L.b200_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    _lib = L
+    return L
+
+
+class DeviceError(RuntimeError):
+    pass
+
+
+class DeviceMemory:
+    """Counterpart of ccl::device_memory: a host array + its device allocation."""
+
+    def __init__(self, name, host=None, mem_type=MEM_READ_WRITE):
+        self.name = name
+        self.type = mem_type
+        self.host = host  # numpy array or None
+        self.device_pointer = 0
+        self.device_size = 0
+
+    @property
+    def memory_size(self):
+        return 0 if self.host is None else self.host.nbytes
+
+
+class B200Device:
+    """Device subclass equivalent (device.h:288).  One instance = one GPU context."""
+
+    def __init__(self, ordinal=0):
+        self._L = load_library()
+        err = C.create_string_buffer(512)
+        self._ctx = self._L.b200_create(int(ordinal), err, len(err))
+        self._error = ""
+        if not self._ctx:
+            raise DeviceError("b200_create: " + err.value.decode())
+        self.ordinal = ordinal
+        self._globals = {}
+
+    # -- error latch (Device::set_error / have_error / error_message) --
+    def have_error(self):
+        return bool(self._error)
+
+    def error_message(self):
+        return self._error
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = "%s: %s (code %d)" % (what, self._L.b200_last_error(self._ctx).decode(), rc)
+            if not self._error:
+                self._error = msg
+            raise DeviceError(msg)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._L.b200_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- memory (device.h:484-488) --
+    def mem_alloc(self, mem):
+        if mem.device_pointer:
+            return
+        p = C.c_uint64()
+        self._check(self._L.b200_alloc(self._ctx, max(mem.memory_size, 16), C.byref(p)),
+                    "mem_alloc(%s)" % mem.name)
+        mem.device_pointer = p.value
+        mem.device_size = mem.memory_size
+
+    def mem_copy_to(self, mem):
+        """(Re)allocate, upload and - for MEM_GLOBAL - bind by name, as
+        CUDADevice::mem_copy_to does (device_cuda_impl.cpp:1020-1096)."""
+        if mem.device_pointer and mem.device_size != mem.memory_size:
+            self.mem_free(mem)
+        self.mem_alloc(mem)
+        host = np.ascontiguousarray(mem.host)
+        if host.nbytes:
+            self._check(self._L.b200_h2d(self._ctx, mem.device_pointer, host.ctypes.data, 0,
+                                         host.nbytes), "mem_copy_to(%s)" % mem.name)
+        if mem.type == MEM_GLOBAL:
+            self._check(self._L.b200_bind_global(self._ctx, mem.name.encode(), mem.device_pointer,
+                                                 host.ctypes.data if host.nbytes else None,
+                                                 host.nbytes), "bind(%s)" % mem.name)
+            self._globals[mem.name] = mem
+
+    def mem_copy_from(self, mem, y=0, w=None, h=None, elem=None):
+        """Rows [y, y+h) of width w elements of `elem` bytes (device.h:485)."""
+        host = mem.host
+        if w is None:
+            offset, size = 0, host.nbytes
+        else:
+            offset, size = elem * y * w, elem * w * h
+        flat = host.reshape(-1).view(np.uint8)
+        self._check(self._L.b200_d2h(self._ctx, mem.device_pointer,
+                                     flat[offset:].ctypes.data, offset, size),
+                    "mem_copy_from(%s)" % mem.name)
+
+    def mem_zero(self, mem):
+        self.mem_alloc(mem)
+        self._check(self._L.b200_zero(self._ctx, mem.device_pointer, 0, mem.memory_size),
+                    "mem_zero(%s)" % mem.name)
+        if mem.host is not None:
+            mem.host[...] = 0
+
+    def mem_free(self, mem):
+        if mem.device_pointer:
+            self._check(self._L.b200_free(self._ctx, mem.device_pointer), "mem_free")
+            mem.device_pointer = 0
+            mem.device_size = 0
+            self._globals.pop(mem.name, None)
+
+    def mem_used(self):
+        return self._L.b200_mem_used(self._ctx)
+
+    def const_copy_to(self, name, host_bytes):
+        """Device::const_copy_to - only ever "__data" (render/scene.cpp:307)."""
+        if name != "__data":
+            raise DeviceError("const_copy_to: unknown constant " + name)
+        buf = np.ascontiguousarray(host_bytes).view(np.uint8)
+        self._check(self._L.b200_set_kernel_data(self._ctx, buf.ctypes.data, buf.nbytes),
+                    "const_copy_to(__data)")
+
+    # -- convenience: upload everything Scene::device_update would --
+    def upload_scene(self, arrays):
+        """arrays: {kernel_textures name: (uint8 bytes, elem_size)} + "__data"."""
+        for name, (data, _es) in arrays.items():
+            if name == "__data":
+                continue
+            mem = DeviceMemory(name, np.ascontiguousarray(data), MEM_GLOBAL)
+            self.mem_copy_to(mem)
+        self.const_copy_to("__data", arrays["__data"][0])
+
+    def build_bvh(self):
+        info = BVHInfo()
+        self._check(self._L.b200_build_bvh(self._ctx, C.byref(info)), "build_bvh")
+        return info.as_dict()
+
+    def set_option(self, name, value):
+        self._check(self._L.b200_set_option(self._ctx, name.encode(), int(value)), "set_option")
+
+    def synchronize(self):
+        self._check(self._L.b200_synchronize(self._ctx), "synchronize")
+
+    def stats(self):
+        s = Stats()
+        self._check(self._L.b200_get_stats(self._ctx, C.byref(s)), "get_stats")
+        return s.as_dict()
+
+    # -- parity / bench hook --
+    def trace_batch(self, rays, any_hit=False):
+        """scene_intersect on a host ray batch; returns the HIT_DTYPE array."""
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        rmem = DeviceMemory("rays", rays.view(np.uint8), MEM_READ_ONLY)
+        hits = np.zeros(len(rays), dtype=HIT_DTYPE)
+        hmem = DeviceMemory("hits", hits.view(np.uint8), MEM_READ_WRITE)
+        self.mem_copy_to(rmem)
+        self.mem_alloc(hmem)
+        try:
+            self.trace_device(rmem.device_pointer, hmem.device_pointer, len(rays), any_hit)
+            self.mem_copy_from(hmem)
+        finally:
+            self.mem_free(rmem)
+            self.mem_free(hmem)
+        return hits
+
+    def trace_device(self, rays_dptr, hits_dptr, n, any_hit=False):
+        self._check(self._L.b200_trace_batch(self._ctx, rays_dptr, hits_dptr, int(n),
+                                             int(bool(any_hit))), "trace_batch")
+
+    # -- DeviceTask::RENDER for one tile --
+    def render_tile(self, film_dptr, x, y, w, h, start_sample, num_samples, offset, stride):
+        wt = WorkTile(x, y, w, h, start_sample, num_samples, offset, stride, film_dptr)
+        self._check(self._L.b200_render(self._ctx, C.byref(wt), None), "render")
+
+    def render(self, width, height, pass_stride, start_sample, num_samples, film=None):
+        """Full-frame RENDER into a fresh (or given) RenderBuffers-like film and
+        read it back: returns (h, w, pass_stride) float32 sums."""
+        if film is None:
+            film = DeviceMemory("RenderBuffers",
+                                np.zeros((height, width, pass_stride), np.float32))
+            self.mem_zero(film)
+            own = True
+        else:
+            own = False
+        try:
+            self.render_tile(film.device_pointer, 0, 0, width, height, start_sample, num_samples,
+                             0, width)
+            self.mem_copy_from(film)
+        finally:
+            if own:
+                self.mem_free(film)
+        return film.host

@@ -1,0 +1,47 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _has_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The reference oracle (oracle/_ref/libcycles_ref.so); skip when not built."""
+    from oracle import cycles_ref
+    if not cycles_ref.available():
+        pytest.skip("oracle/_ref/libcycles_ref.so not built (needs /root/reference)")
+    return cycles_ref
+
+
+@pytest.fixture(scope="session")
+def device():
+    from raytracingproject_b200.device import B200Device
+    dev = B200Device(0)
+    yield dev
+    dev.close()

@@ -1,0 +1,13 @@
+"""Small, seconds-sized scene cases shared by the parity tests."""
+from raytracingproject_b200 import scenes
+
+W, H = 256, 144
+
+
+def small_cases():
+    return {
+        "cube": scenes.default_cube(W, H, material="diffuse"),
+        "cornell": scenes.cornell(W, H, materials="diffuse"),
+        "terrain": scenes.terrain(W, H, n=96),
+        "instanced": scenes.instanced(W, H, grid=8, subdiv=3),
+    }
