@@ -203,6 +203,8 @@ b200_ctx *b200_create(int cuda_ordinal, char *err, size_t errlen)
   bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess;
   ok = ok && cudaEventCreate(&ctx->ev2) == cudaSuccess && cudaEventCreate(&ctx->ev3) == cudaSuccess;
+  ok = ok && cudaEventCreate(&ctx->ev4) == cudaSuccess && cudaEventCreate(&ctx->ev5) == cudaSuccess;
+  ok = ok && cudaEventCreate(&ctx->ev6) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->d_counters, CNT_NUM * sizeof(unsigned int)) == cudaSuccess;
   ok = ok && cudaMallocHost(&ctx->h_counters, CNT_NUM * sizeof(unsigned int)) == cudaSuccess;
   if (!ok) {
@@ -237,6 +239,9 @@ void b200_destroy(b200_ctx *ctx)
   cudaEventDestroy(ctx->ev1);
   cudaEventDestroy(ctx->ev2);
   cudaEventDestroy(ctx->ev3);
+  cudaEventDestroy(ctx->ev4);
+  cudaEventDestroy(ctx->ev5);
+  cudaEventDestroy(ctx->ev6);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

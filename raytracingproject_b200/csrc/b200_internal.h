@@ -27,6 +27,7 @@ struct b200_ctx {
   int num_sms = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  cudaEvent_t ev4 = nullptr, ev5 = nullptr, ev6 = nullptr;
   std::string error;
   std::mutex mutex;
 

@@ -1,0 +1,1135 @@
+/* shade.cuh - device-side shading for the wavefront stages: random numbers,
+ * camera rays, ShaderData setup, the SVM subset, closures (BSDF eval/sample),
+ * light sampling and emission.  Each function restates the reference function
+ * cited above it with the same operation order (the file is compiled with
+ * -fmad=false), so sample sequences, pdfs and weights agree with the CPU oracle
+ * to rounding of the transcendental functions.
+ *
+ * Scope (b200_cycles.cu:check_scope / svm_validate refuse anything else):
+ * perspective camera without DOF / motion, static triangles and instances,
+ * point / spot / area / distant lamps, background colour, SVM nodes of
+ * SVM_SUPPORTED_NODES and the Diffuse + Principled(GGX) + Glass(GGX) closures,
+ * opaque shadows, combined pass only.
+ */
+#ifndef B200_SHADE_CUH
+#define B200_SHADE_CUH
+
+#include "device_scene.cuh"
+#include "traverse.cuh"
+
+#define CLOSURE_WEIGHT_CUTOFF 1e-5f
+#define MAX_CLOSURES_GPU 8
+#define SVM_STACK_GPU 64 /* offsets used by the supported graphs stay far below 255 */
+
+/* ------------------------------------------------------------- path state */
+
+struct PathStateG {
+  uint32_t flag;
+  uint32_t rng_hash;
+  int rng_offset;
+  int sample;
+  int bounce, diffuse_bounce, glossy_bounce, transmission_bounce, transparent_bounce;
+  float min_ray_pdf, ray_pdf, ray_t;
+};
+
+/* ---------------------------------------------------------------- hashing */
+
+/* util/util_hash.h:28-93 (Jenkins lookup3 final) */
+CY_DEV uint32_t rot32(uint32_t x, int k)
+{
+  return (x << k) | (x >> (32 - k));
+}
+CY_DEV uint32_t hash_uint2(uint32_t kx, uint32_t ky)
+{
+  uint32_t a, b, c;
+  a = b = c = 0xdeadbeefu + (2u << 2) + 13u;
+  b += ky;
+  a += kx;
+  c ^= b;
+  c -= rot32(b, 14);
+  a ^= c;
+  a -= rot32(c, 11);
+  b ^= a;
+  b -= rot32(a, 25);
+  c ^= b;
+  c -= rot32(b, 16);
+  a ^= c;
+  a -= rot32(c, 4);
+  b ^= a;
+  b -= rot32(a, 14);
+  c ^= b;
+  c -= rot32(b, 24);
+  return c;
+}
+
+/* kernel/kernel_jitter.h:122-129 */
+CY_DEV uint32_t cmj_hash_simple(uint32_t i, uint32_t p)
+{
+  i = (i ^ 61u) ^ p;
+  i += i << 3;
+  i ^= i >> 4;
+  i *= 0x27d4eb2du;
+  return i;
+}
+
+/* kernel/kernel_random.h:40-50 - Sobol via the uploaded direction vectors */
+CY_DEV uint32_t sobol_dimension(int index, int dimension)
+{
+  uint32_t result = 0;
+  uint32_t i = (uint32_t)index + 64u; /* SOBOL_SKIP */
+  for (int j = 0, x; (x = __ffs((int)i)); i >>= x) {
+    j += x;
+    result ^= __ldg(&g_scene.sample_pattern_lut[32 * dimension + j - 1]);
+  }
+  return result;
+}
+
+/* kernel/kernel_random.h:53-89 (SAMPLING_PATTERN_SOBOL branch) */
+CY_DEV float path_rng_1D(uint32_t rng_hash, int sample, int dimension)
+{
+  uint32_t result = sobol_dimension(sample, dimension);
+  float r = (float)result * (1.0f / (float)0xFFFFFFFF);
+  uint32_t tmp_rng = cmj_hash_simple((uint32_t)dimension, rng_hash);
+  float shift = (float)tmp_rng * (1.0f / (float)0xFFFFFFFF);
+  return r + shift - floorf(r + shift);
+}
+CY_DEV void path_rng_2D(uint32_t rng_hash, int sample, int dimension, float *fx, float *fy)
+{
+  *fx = path_rng_1D(rng_hash, sample, dimension);
+  *fy = path_rng_1D(rng_hash, sample, dimension + 1);
+}
+CY_DEV float path_state_rng_1D(const PathStateG &s, int dimension)
+{
+  return path_rng_1D(s.rng_hash, s.sample, s.rng_offset + dimension);
+}
+CY_DEV void path_state_rng_2D(const PathStateG &s, int dimension, float *fx, float *fy)
+{
+  path_rng_2D(s.rng_hash, s.sample, s.rng_offset + dimension, fx, fy);
+}
+
+/* kernel/kernel_globals.h:213-227 */
+CY_DEV float lookup_table_read(float x, int offset, int size)
+{
+  x = saturate(x) * (size - 1);
+  int index = min((int)x, size - 1);
+  int nindex = min(index + 1, size - 1);
+  float t = x - index;
+  float data0 = __ldg(&g_scene.lookup_table[index + offset]);
+  if (t == 0.0f)
+    return data0;
+  float data1 = __ldg(&g_scene.lookup_table[nindex + offset]);
+  return (1.0f - t) * data0 + t * data1;
+}
+
+/* ------------------------------------------------------------- camera ray */
+
+/* util/util_projection.h:48-55 */
+CY_DEV f3 transform_perspective(const float4 tx, const float4 ty, const float4 tz,
+                                const float4 tw, f3 a)
+{
+  float4 b = make_float4(a.x, a.y, a.z, 1.0f);
+  f3 c = mk3(dot4(tx, b), dot4(ty, b), dot4(tz, b));
+  float w = dot4(tw, b);
+  return (w != 0.0f) ? c / w : zero3();
+}
+
+/* kernel_path_common.h:21-46 + kernel_random.h:129-153 + kernel_camera.h:355-427,
+ * 42-170 (perspective, no DOF, no motion).  Returns Ray::t (0 = no ray). */
+CY_DEV float camera_ray(int x, int y, int sample, uint32_t *rng_hash, f3 *P, f3 *D)
+{
+  *rng_hash = hash_uint2((uint32_t)x, (uint32_t)y);
+  *rng_hash ^= (uint32_t)kd_int(KD_INT_SEED);
+
+  float filter_u, filter_v;
+  if (sample == 0) {
+    filter_u = 0.5f;
+    filter_v = 0.5f;
+  }
+  else {
+    path_rng_2D(*rng_hash, sample, CY_PRNG_FILTER_U, &filter_u, &filter_v);
+  }
+
+  const int filter_table_offset = kd_int(KD_FILM_FILTER_TABLE_OFFSET);
+  float raster_x = x + lookup_table_read(filter_u, filter_table_offset, CY_FILTER_TABLE_SIZE);
+  float raster_y = y + lookup_table_read(filter_v, filter_table_offset, CY_FILTER_TABLE_SIZE);
+
+  const int r2c = KD_CAM_RASTERTOCAMERA;
+  f3 raster = mk3(raster_x, raster_y, 0.0f);
+  f3 Pcamera = transform_perspective(kd_float4(r2c), kd_float4(r2c + 16), kd_float4(r2c + 32),
+                                     kd_float4(r2c + 48), raster);
+
+  tfm34 c2w;
+  c2w.x = kd_float4(KD_CAM_CAMERATOWORLD);
+  c2w.y = kd_float4(KD_CAM_CAMERATOWORLD + 16);
+  c2w.z = kd_float4(KD_CAM_CAMERATOWORLD + 32);
+
+  f3 Pw = transform_point(c2w, zero3());
+  f3 Dw = normalize(transform_direction(c2w, Pcamera));
+
+  /* clipping - kernel_camera.h:158-167 */
+  float z_inv = 1.0f / normalize(Pcamera).z;
+  float nearclip = kd_float(KD_CAM_NEARCLIP) * z_inv;
+  Pw += nearclip * Dw;
+  *P = Pw;
+  *D = Dw;
+  return kd_float(KD_CAM_CLIPLENGTH) * z_inv;
+}
+
+/* ----------------------------------------------------------- ShaderData */
+
+struct Closure {
+  int type;
+  f3 weight;
+  float sample_weight;
+  f3 N;
+  /* microfacet / principled parameters (closure/bsdf_microfacet.h:38-56) */
+  float alpha_x, alpha_y, ior;
+  f3 T;
+  f3 color, cspec0, fresnel_color; /* MicrofacetExtra */
+  float clearcoat;
+  float roughness; /* PrincipledDiffuseBsdf */
+};
+
+struct ShaderDataG {
+  f3 P, N, Ng, I;
+  f3 dPdu;
+  int shader;
+  uint32_t flag, object_flag;
+  int prim, type, object;
+  float u, v, ray_length;
+  f3 svm_closure_weight;
+  f3 closure_emission_background;
+  int num_closure, num_closure_left;
+  Closure closure[MAX_CLOSURES_GPU];
+};
+
+CY_DEV uint32_t shader_flags(int shader)
+{
+  return __ldg((const uint32_t *)(g_scene.shaders +
+                                  (size_t)(shader & CY_SHADER_MASK) * SIZEOF_KERNEL_SHADER +
+                                  KS_FLAGS));
+}
+
+/* geom/geom_object.h:166-186 */
+CY_DEV f3 object_normal_transform(int object, f3 N)
+{
+  tfm34 itfm = object_itfm(object);
+  return normalize(transform_direction_transposed(itfm, N));
+}
+CY_DEV f3 object_dir_transform(int object, f3 D)
+{
+  tfm34 tfm = object_tfm(object);
+  return transform_direction(tfm, D);
+}
+
+/* bvh/bvh.h:541-587 (__INTERSECTION_REFINE__ branch) */
+CY_DEV float ray_offset_1(float p, float ng)
+{
+  const float epsilon_f = 1e-5f;
+  const float epsilon_test = 1.0f;
+  const int epsilon_i = 32;
+  if (fabsf(p) < epsilon_test) {
+    return p + ng * epsilon_f;
+  }
+  uint32_t ix = __float_as_uint(p);
+  ix += ((ix ^ __float_as_uint(ng)) >> 31) ? (uint32_t)(-epsilon_i) : (uint32_t)epsilon_i;
+  return __uint_as_float(ix);
+}
+CY_DEV f3 ray_offset(f3 P, f3 Ng)
+{
+  return mk3(ray_offset_1(P.x, Ng.x), ray_offset_1(P.y, Ng.y), ray_offset_1(P.z, Ng.z));
+}
+
+/* geom/geom_triangle_intersect.h:195-256 */
+CY_DEV f3 triangle_refine(int isect_prim, int isect_object, float isect_t, f3 P, f3 D)
+{
+  float t = isect_t;
+  if (isect_object != -1) {
+    if (t == 0.0f)
+      return P;
+    tfm34 itfm = object_itfm(isect_object);
+    P = transform_point(itfm, P);
+    D = transform_direction(itfm, D * t);
+    D = normalize_len(D, &t);
+  }
+  P = P + D * t;
+
+  const uint32_t tri_vindex = __ldg(&g_scene.prim_tri_index[isect_prim]);
+  const float4 tri_a = __ldg(&g_scene.prim_tri_verts[tri_vindex + 0]);
+  const float4 tri_b = __ldg(&g_scene.prim_tri_verts[tri_vindex + 1]);
+  const float4 tri_c = __ldg(&g_scene.prim_tri_verts[tri_vindex + 2]);
+  f3 edge1 = mk3(tri_a.x - tri_c.x, tri_a.y - tri_c.y, tri_a.z - tri_c.z);
+  f3 edge2 = mk3(tri_b.x - tri_c.x, tri_b.y - tri_c.y, tri_b.z - tri_c.z);
+  f3 tvec = mk3(P.x - tri_c.x, P.y - tri_c.y, P.z - tri_c.z);
+  f3 qvec = cross(tvec, edge1);
+  f3 pvec = cross(D, edge2);
+  float det = dot(edge1, pvec);
+  if (det != 0.0f) {
+    float rt = dot(edge2, qvec) / det;
+    P = P + D * rt;
+  }
+  if (isect_object != -1) {
+    tfm34 tfm = object_tfm(isect_object);
+    P = transform_point(tfm, P);
+  }
+  return P;
+}
+
+/* kernel_shader.h:59-153 (static triangles) */
+CY_DEV void shader_setup_from_ray(
+    ShaderDataG &sd, int isect_prim, int isect_object, float t, float u, float v, f3 rayP, f3 rayD)
+{
+  sd.object = (isect_object == -1) ? (int)__ldg(&g_scene.prim_object[isect_prim]) : isect_object;
+  sd.type = CY_PRIMITIVE_TRIANGLE;
+  sd.flag = 0;
+  sd.object_flag = __ldg(&g_scene.object_flag[sd.object]);
+  sd.prim = (int)__ldg(&g_scene.prim_index[isect_prim]);
+  sd.ray_length = t;
+  sd.u = u;
+  sd.v = v;
+
+  /* triangle_normal - geom/geom_triangle.h:26-41 */
+  const uint4 tri_vindex = __ldg(&g_scene.tri_vindex[sd.prim]);
+  const f3 v0 = mk3(__ldg(&g_scene.prim_tri_verts[tri_vindex.w + 0]));
+  const f3 v1 = mk3(__ldg(&g_scene.prim_tri_verts[tri_vindex.w + 1]));
+  const f3 v2 = mk3(__ldg(&g_scene.prim_tri_verts[tri_vindex.w + 2]));
+  f3 Ng;
+  if (sd.object_flag & CY_SD_OBJECT_NEGATIVE_SCALE_APPLIED)
+    Ng = normalize(cross(v2 - v0, v1 - v0));
+  else
+    Ng = normalize(cross(v1 - v0, v2 - v0));
+
+  sd.shader = (int)__ldg(&g_scene.tri_shader[sd.prim]);
+  sd.P = triangle_refine(isect_prim, isect_object, t, rayP, rayD);
+  sd.Ng = Ng;
+  sd.N = Ng;
+
+  if (sd.shader & CY_SHADER_SMOOTH_NORMAL) {
+    /* triangle_smooth_normal - geom/geom_triangle.h:80-92 */
+    f3 n0 = mk3(__ldg(&g_scene.tri_vnormal[tri_vindex.x]));
+    f3 n1 = mk3(__ldg(&g_scene.tri_vnormal[tri_vindex.y]));
+    f3 n2 = mk3(__ldg(&g_scene.tri_vnormal[tri_vindex.z]));
+    f3 N = safe_normalize((1.0f - u - v) * n2 + u * n0 + v * n1);
+    sd.N = is_zero(N) ? Ng : N;
+  }
+
+  /* triangle_dPdudv - geom/geom_triangle.h:96-110 */
+  sd.dPdu = (v0 - v2);
+
+  sd.I = -rayD;
+  sd.flag |= shader_flags(sd.shader);
+
+  if (isect_object != -1) {
+    sd.N = object_normal_transform(sd.object, sd.N);
+    sd.Ng = object_normal_transform(sd.object, sd.Ng);
+    sd.dPdu = object_dir_transform(sd.object, sd.dPdu);
+  }
+
+  bool backfacing = (dot(sd.Ng, sd.I) < 0.0f);
+  if (backfacing) {
+    sd.flag |= CY_SD_BACKFACING;
+    sd.Ng = -sd.Ng;
+    sd.N = -sd.N;
+    sd.dPdu = -sd.dPdu;
+  }
+}
+
+/* ------------------------------------------------------------------ BSDFs */
+
+#include "bsdf.cuh"
+
+/* --------------------------------------------------------------------- SVM */
+
+#define CY_NODE_GEOM_P 0
+#define CY_NODE_GEOM_N 1
+#define CY_NODE_GEOM_T 2
+#define CY_NODE_GEOM_I 3
+#define CY_NODE_GEOM_Ng 4
+#define CY_NODE_GEOM_uv 5
+
+/* closure/alloc.h:19-68 */
+CY_DEV Closure *closure_alloc(ShaderDataG &sd, f3 weight)
+{
+  if (sd.num_closure_left == 0)
+    return NULL;
+  Closure *sc = &sd.closure[sd.num_closure];
+  sc->type = CY_CLOSURE_NONE_ID;
+  sc->weight = weight;
+  sd.num_closure++;
+  sd.num_closure_left--;
+  return sc;
+}
+CY_DEV bool closure_alloc_extra(ShaderDataG &sd)
+{
+  if (1 > sd.num_closure_left) {
+    sd.num_closure--;
+    sd.num_closure_left++;
+    return false;
+  }
+  sd.num_closure_left -= 1;
+  return true;
+}
+CY_DEV Closure *bsdf_alloc(ShaderDataG &sd, f3 weight)
+{
+  Closure *sc = closure_alloc(sd, weight);
+  if (sc == NULL)
+    return NULL;
+  float sample_weight = fabsf(average(weight));
+  sc->sample_weight = sample_weight;
+  return (sample_weight >= CLOSURE_WEIGHT_CUTOFF) ? sc : NULL;
+}
+
+CY_DEV void emission_setup(ShaderDataG &sd, f3 weight)
+{
+  if (sd.flag & CY_SD_EMISSION) {
+    sd.closure_emission_background += weight;
+  }
+  else {
+    sd.flag |= CY_SD_EMISSION;
+    sd.closure_emission_background = weight;
+  }
+}
+
+CY_DEV f3 stack_load_float3(const float *stack, uint32_t a)
+{
+  return mk3(stack[a + 0], stack[a + 1], stack[a + 2]);
+}
+CY_DEV void stack_store_float3(float *stack, uint32_t a, f3 f)
+{
+  stack[a + 0] = f.x;
+  stack[a + 1] = f.y;
+  stack[a + 2] = f.z;
+}
+CY_DEV bool stack_valid(uint32_t a)
+{
+  return a != (uint32_t)CY_SVM_STACK_INVALID;
+}
+
+#include "svm_closure.cuh"
+
+/* svm/svm.h:220-300 for the supported opcodes.  max_closures = 0 evaluates only
+ * emission / background weights (PATH_RAY_EMISSION / TERMINATE evaluation,
+ * kernel_shader.h:1063-1075). */
+__device__ __noinline__ void svm_eval_nodes(ShaderDataG &sd, uint32_t path_flag, int max_closures)
+{
+  float stack[SVM_STACK_GPU];
+  sd.num_closure = 0;
+  sd.num_closure_left = max_closures;
+  sd.svm_closure_weight = zero3();
+  int offset = sd.shader & CY_SHADER_MASK;
+
+  while (true) {
+    const uint4 node = __ldg(&g_scene.svm_nodes[offset]);
+    offset++;
+    switch (node.x) {
+      case CY_NODE_END:
+        return;
+      case CY_NODE_SHADER_JUMP:
+        offset = (int)node.y; /* SHADER_TYPE_SURFACE */
+        break;
+      case CY_NODE_CLOSURE_BSDF:
+        svm_node_closure_bsdf(sd, stack, node, path_flag, &offset);
+        break;
+      case CY_NODE_CLOSURE_EMISSION:
+      case CY_NODE_CLOSURE_BACKGROUND: {
+        /* svm_closure.h:1068-1100 */
+        f3 weight = sd.svm_closure_weight;
+        if (stack_valid(node.y)) {
+          float mix_weight = stack[node.y];
+          if (mix_weight == 0.0f)
+            break;
+          weight *= mix_weight;
+        }
+        emission_setup(sd, weight);
+        break;
+      }
+      case CY_NODE_CLOSURE_SET_WEIGHT:
+        sd.svm_closure_weight = mk3(__uint_as_float(node.y), __uint_as_float(node.z),
+                                    __uint_as_float(node.w));
+        break;
+      case CY_NODE_CLOSURE_WEIGHT:
+        sd.svm_closure_weight = stack_load_float3(stack, node.y);
+        break;
+      case CY_NODE_EMISSION_WEIGHT: {
+        float strength = stack[node.z];
+        sd.svm_closure_weight = stack_load_float3(stack, node.y) * strength;
+        break;
+      }
+      case CY_NODE_MIX_CLOSURE: {
+        uint32_t weight_offset = node.y & 0xff, in_weight_offset = (node.y >> 8) & 0xff;
+        uint32_t weight1_offset = (node.y >> 16) & 0xff, weight2_offset = (node.y >> 24) & 0xff;
+        float weight = saturate(stack[weight_offset]);
+        float in_weight = stack_valid(in_weight_offset) ? stack[in_weight_offset] : 1.0f;
+        if (stack_valid(weight1_offset))
+          stack[weight1_offset] = in_weight * (1.0f - weight);
+        if (stack_valid(weight2_offset))
+          stack[weight2_offset] = in_weight * weight;
+        break;
+      }
+      case CY_NODE_JUMP_IF_ZERO:
+        if (stack[node.z] == 0.0f)
+          offset += (int)node.y;
+        break;
+      case CY_NODE_JUMP_IF_ONE:
+        if (stack[node.z] == 1.0f)
+          offset += (int)node.y;
+        break;
+      case CY_NODE_GEOMETRY: {
+        f3 data;
+        switch (node.y) {
+          case CY_NODE_GEOM_P:
+            data = sd.P;
+            break;
+          case CY_NODE_GEOM_N:
+            data = sd.N;
+            break;
+          case CY_NODE_GEOM_T:
+            /* primitive_tangent without the generated-coordinates branch
+             * (geom_primitive.h:292-320); only read by anisotropic closures */
+            data = normalize(sd.dPdu);
+            break;
+          case CY_NODE_GEOM_I:
+            data = sd.I;
+            break;
+          case CY_NODE_GEOM_Ng:
+            data = sd.Ng;
+            break;
+          case CY_NODE_GEOM_uv:
+            data = mk3(sd.u, sd.v, 0.0f);
+            break;
+          default:
+            data = zero3();
+        }
+        stack_store_float3(stack, node.z, data);
+        break;
+      }
+      case CY_NODE_VALUE_F:
+        stack[node.z] = __uint_as_float(node.y);
+        break;
+      case CY_NODE_VALUE_V: {
+        const uint4 node1 = __ldg(&g_scene.svm_nodes[offset]);
+        offset++;
+        stack_store_float3(stack, node.y,
+                           mk3(__uint_as_float(node1.y), __uint_as_float(node1.z),
+                               __uint_as_float(node1.w)));
+        break;
+      }
+      default:
+        /* refused at bind time by svm_validate(); unreachable */
+        return;
+    }
+  }
+}
+
+/* kernel_shader.h:1057-1110 */
+CY_DEV void shader_eval_surface(ShaderDataG &sd, uint32_t path_flag)
+{
+  int max_closures;
+  if (path_flag & (CY_PATH_RAY_TERMINATE | CY_PATH_RAY_SHADOW | CY_PATH_RAY_EMISSION))
+    max_closures = 0;
+  else
+    max_closures = min(kd_int(KD_INT_MAX_CLOSURES), MAX_CLOSURES_GPU);
+  svm_eval_nodes(sd, path_flag, max_closures);
+}
+
+/* kernel_shader.h:530-555 */
+CY_DEV void shader_prepare_closures(ShaderDataG &sd, const PathStateG &state)
+{
+  if (state.bounce + state.transparent_bounce == 0 && sd.num_closure > 1) {
+    float sum = 0.0f;
+    for (int i = 0; i < sd.num_closure; i++) {
+      if (sd.closure[i].type <= CY_CLOSURE_BSSRDF_PRINCIPLED_RANDOM_WALK_ID)
+        sum += sd.closure[i].sample_weight;
+    }
+    for (int i = 0; i < sd.num_closure; i++) {
+      if (sd.closure[i].type <= CY_CLOSURE_BSSRDF_PRINCIPLED_RANDOM_WALK_ID)
+        sd.closure[i].sample_weight = fmaxf(sd.closure[i].sample_weight, 0.125f * sum);
+    }
+  }
+}
+
+/* kernel_shader.h:556-582 (_shader_bsdf_multi_eval), use_light_pass = 0 */
+CY_DEV void shader_bsdf_multi_eval(const ShaderDataG &sd, f3 omega_in, float *pdf, int skip,
+                                   f3 *result_eval, float sum_pdf, float sum_sample_weight)
+{
+  for (int i = 0; i < sd.num_closure; i++) {
+    const Closure &sc = sd.closure[i];
+    if (i != skip && sc.type <= CY_CLOSURE_BSDF_TRANSPARENT_ID) {
+      float bsdf_pdf = 0.0f;
+      f3 eval = bsdf_eval(sd, sc, omega_in, &bsdf_pdf);
+      if (bsdf_pdf != 0.0f) {
+        *result_eval += eval * sc.weight;
+        sum_pdf += bsdf_pdf * sc.sample_weight;
+      }
+      sum_sample_weight += sc.sample_weight;
+    }
+  }
+  *pdf = (sum_sample_weight > 0.0f) ? sum_pdf / sum_sample_weight : 0.0f;
+}
+
+/* kernel_montecarlo.h:133-136 */
+CY_DEV float power_heuristic(float a, float b)
+{
+  return (a * a) / (a * a + b * b);
+}
+
+/* kernel_shader.h:612-636 (non-branched) */
+CY_DEV f3 shader_bsdf_eval(const ShaderDataG &sd, f3 omega_in, float light_pdf, bool use_mis)
+{
+  f3 eval = zero3();
+  float pdf;
+  shader_bsdf_multi_eval(sd, omega_in, &pdf, -1, &eval, 0.0f, 0.0f);
+  if (use_mis) {
+    float weight = power_heuristic(light_pdf, pdf);
+    eval *= weight;
+  }
+  return eval;
+}
+
+/* kernel_shader.h:638-680 + 739-775 */
+CY_DEV int shader_bsdf_sample(ShaderDataG &sd, float randu, float randv, f3 *bsdf_eval_out,
+                              f3 *omega_in, float *pdf)
+{
+  int sampled = 0;
+  if (sd.num_closure > 1) {
+    float sum = 0.0f;
+    for (int i = 0; i < sd.num_closure; i++) {
+      if (sd.closure[i].type <= CY_CLOSURE_BSSRDF_PRINCIPLED_RANDOM_WALK_ID)
+        sum += sd.closure[i].sample_weight;
+    }
+    float r = randu * sum;
+    float partial_sum = 0.0f;
+    for (int i = 0; i < sd.num_closure; i++) {
+      const Closure &sc = sd.closure[i];
+      if (sc.type <= CY_CLOSURE_BSSRDF_PRINCIPLED_RANDOM_WALK_ID) {
+        float next_sum = partial_sum + sc.sample_weight;
+        if (r < next_sum) {
+          sampled = i;
+          randu = (r - partial_sum) / sc.sample_weight;
+          break;
+        }
+        partial_sum = next_sum;
+      }
+    }
+  }
+  const Closure &sc = sd.closure[sampled];
+  if (!(sc.type <= CY_CLOSURE_BSDF_TRANSPARENT_ID)) {
+    *pdf = 0.0f;
+    return CY_LABEL_NONE;
+  }
+  f3 eval = zero3();
+  *pdf = 0.0f;
+  int label = bsdf_sample(sd, sc, randu, randv, &eval, omega_in, pdf);
+  if (*pdf != 0.0f) {
+    *bsdf_eval_out = eval * sc.weight;
+    if (sd.num_closure > 1) {
+      float sweight = sc.sample_weight;
+      shader_bsdf_multi_eval(sd, *omega_in, pdf, sampled, bsdf_eval_out, *pdf * sweight, sweight);
+    }
+  }
+  return label;
+}
+
+/* --------------------------------------------------------------- lights */
+
+struct LightSampleG {
+  f3 P, Ng, D;
+  float t, u, v, pdf, eval_fac;
+  int object, prim, shader, lamp, type;
+};
+
+CY_DEV const uint8_t *light_ptr(int lamp)
+{
+  return g_scene.lights + (size_t)lamp * SIZEOF_KERNEL_LIGHT;
+}
+CY_DEV float kl_float(const uint8_t *kl, int off)
+{
+  return __ldg((const float *)(kl + off));
+}
+CY_DEV int kl_int(const uint8_t *kl, int off)
+{
+  return __ldg((const int *)(kl + off));
+}
+CY_DEV f3 kl_float3(const uint8_t *kl, int off)
+{
+  return mk3(kl_float(kl, off), kl_float(kl, off + 4), kl_float(kl, off + 8));
+}
+
+/* kernel_montecarlo.h:39-46 */
+CY_DEV void to_unit_disk(float *x, float *y)
+{
+  float phi = CY_2PI_F * (*x);
+  float r = sqrtf(*y);
+  *x = r * cosf(phi);
+  *y = r * sinf(phi);
+}
+
+/* kernel_light_common.h:117-150 */
+CY_DEV f3 ellipse_sample(f3 ru, f3 rv, float randu, float randv)
+{
+  to_unit_disk(&randu, &randv);
+  return ru * randu + rv * randv;
+}
+CY_DEV f3 disk_light_sample(f3 v, float randu, float randv)
+{
+  f3 ru, rv;
+  make_orthonormals(v, &ru, &rv);
+  return ellipse_sample(ru, rv, randu, randv);
+}
+CY_DEV f3 distant_light_sample(f3 D, float radius, float randu, float randv)
+{
+  return normalize(D + disk_light_sample(D, randu, randv) * radius);
+}
+CY_DEV f3 sphere_light_sample(f3 P, f3 center, float radius, float randu, float randv)
+{
+  return disk_light_sample(normalize(P - center), randu, randv) * radius;
+}
+CY_DEV float smoothstepf(float f)
+{
+  float ff = f * f;
+  return (3.0f * ff - 2.0f * ff * f);
+}
+CY_DEV float spot_light_attenuation(f3 dir, float spot_angle, float spot_smooth, f3 N)
+{
+  float attenuation = dot(dir, N);
+  if (attenuation <= spot_angle) {
+    attenuation = 0.0f;
+  }
+  else {
+    float t = attenuation - spot_angle;
+    if (t < spot_smooth && spot_smooth != 0.0f)
+      attenuation *= smoothstepf(t / spot_smooth);
+  }
+  return attenuation;
+}
+CY_DEV float lamp_light_pdf(f3 Ng, f3 I, float t)
+{
+  float cos_pi = dot(Ng, I);
+  if (cos_pi <= 0.0f)
+    return 0.0f;
+  return t * t / cos_pi;
+}
+
+/* kernel_light_common.h:31-115 (Urena et al. spherical rectangle) */
+CY_DEV float rect_light_sample(f3 P, f3 *light_p, f3 axisu, f3 axisv, float randu, float randv,
+                               bool sample_coord)
+{
+  f3 corner = *light_p - axisu * 0.5f - axisv * 0.5f;
+  float axisu_len, axisv_len;
+  f3 x = normalize_len(axisu, &axisu_len);
+  f3 y = normalize_len(axisv, &axisv_len);
+  f3 z = cross(x, y);
+  f3 dir = corner - P;
+  float z0 = dot(dir, z);
+  if (z0 > 0.0f) {
+    z *= -1.0f;
+    z0 *= -1.0f;
+  }
+  float x0 = dot(dir, x);
+  float y0 = dot(dir, y);
+  float x1 = x0 + axisu_len;
+  float y1 = y0 + axisv_len;
+  /* float4 arithmetic component-wise, util_math_float4.h */
+  float dfx = x0 - x1, dfy = y1 - y0, dfz = x1 - x0, dfw = y0 - y1;
+  float nzx = y0 * dfx, nzy = x1 * dfy, nzz = y1 * dfz, nzw = x0 * dfw;
+  nzx = nzx / sqrtf(z0 * z0 * dfx * dfx + nzx * nzx);
+  nzy = nzy / sqrtf(z0 * z0 * dfy * dfy + nzy * nzy);
+  nzz = nzz / sqrtf(z0 * z0 * dfz * dfz + nzz * nzz);
+  nzw = nzw / sqrtf(z0 * z0 * dfw * dfw + nzw * nzw);
+  float g0 = safe_acosf(-nzx * nzy);
+  float g1 = safe_acosf(-nzy * nzz);
+  float g2 = safe_acosf(-nzz * nzw);
+  float g3 = safe_acosf(-nzw * nzx);
+  float b0 = nzx;
+  float b1 = nzz;
+  float b0sq = b0 * b0;
+  float k = CY_2PI_F - g2 - g3;
+  float S = g0 + g1 - k;
+
+  if (sample_coord) {
+    float au = randu * S + k;
+    float fu = (cosf(au) * b0 - b1) / sinf(au);
+    float cu = 1.0f / sqrtf(fu * fu + b0sq) * (fu > 0.0f ? 1.0f : -1.0f);
+    cu = clampf(cu, -1.0f, 1.0f);
+    float xu = -(cu * z0) / fmaxf(sqrtf(1.0f - cu * cu), 1e-7f);
+    xu = clampf(xu, x0, x1);
+    float z0sq = z0 * z0;
+    float y0sq = y0 * y0;
+    float y1sq = y1 * y1;
+    float d = sqrtf(xu * xu + z0sq);
+    float h0 = y0 / sqrtf(d * d + y0sq);
+    float h1 = y1 / sqrtf(d * d + y1sq);
+    float hv = h0 + randv * (h1 - h0), hv2 = hv * hv;
+    float yv = (hv2 < 1.0f - 1e-6f) ? (hv * d) / sqrtf(1.0f - hv2) : y1;
+    *light_p = P + xu * x + yv * y + z0 * z;
+  }
+  if (S != 0.0f)
+    return 1.0f / S;
+  else
+    return 0.0f;
+}
+
+/* kernel_light.h:40-168 (no background light, no triangle lights) */
+CY_DEV bool lamp_light_sample(int lamp, float randu, float randv, f3 P, LightSampleG *ls)
+{
+  const uint8_t *kl = light_ptr(lamp);
+  const int type = kl_int(kl, KL_TYPE);
+  ls->type = type;
+  ls->shader = kl_int(kl, KL_SHADER_ID);
+  ls->object = CY_PRIM_NONE;
+  ls->prim = CY_PRIM_NONE;
+  ls->lamp = lamp;
+  ls->u = randu;
+  ls->v = randv;
+
+  if (type == CY_LIGHT_DISTANT) {
+    f3 lightD = kl_float3(kl, KL_CO);
+    f3 D = lightD;
+    float radius = kl_float(kl, KL_DISTANT_RADIUS);
+    float invarea = kl_float(kl, KL_DISTANT_INVAREA);
+    if (radius > 0.0f)
+      D = distant_light_sample(D, radius, randu, randv);
+    ls->P = D;
+    ls->Ng = D;
+    ls->D = -D;
+    ls->t = FLT_MAX;
+    float costheta = dot(lightD, D);
+    ls->pdf = invarea / (costheta * costheta * costheta);
+    ls->eval_fac = ls->pdf;
+  }
+  else if (type == CY_LIGHT_BACKGROUND) {
+    return false; /* refused by check_scope */
+  }
+  else {
+    ls->P = kl_float3(kl, KL_CO);
+    if (type == CY_LIGHT_POINT || type == CY_LIGHT_SPOT) {
+      float radius = kl_float(kl, KL_SPOT_RADIUS);
+      if (radius > 0.0f)
+        ls->P += sphere_light_sample(P, ls->P, radius, randu, randv);
+      ls->D = normalize_len(ls->P - P, &ls->t);
+      ls->Ng = -ls->D;
+      float invarea = kl_float(kl, KL_SPOT_INVAREA);
+      ls->eval_fac = (0.25f * CY_1_PI_F) * invarea;
+      ls->pdf = invarea;
+      if (type == CY_LIGHT_SPOT) {
+        f3 dir = kl_float3(kl, KL_SPOT_DIR);
+        ls->eval_fac *= spot_light_attenuation(dir, kl_float(kl, KL_SPOT_SPOT_ANGLE),
+                                               kl_float(kl, KL_SPOT_SPOT_SMOOTH), ls->Ng);
+        if (ls->eval_fac == 0.0f)
+          return false;
+      }
+      ls->pdf *= lamp_light_pdf(ls->Ng, -ls->D, ls->t);
+    }
+    else {
+      f3 axisu = kl_float3(kl, KL_AREA_AXISU);
+      f3 axisv = kl_float3(kl, KL_AREA_AXISV);
+      f3 D = kl_float3(kl, KL_AREA_DIR);
+      float invarea_raw = kl_float(kl, KL_AREA_INVAREA);
+      float invarea = fabsf(invarea_raw);
+      bool is_round = (invarea_raw < 0.0f);
+      if (dot(ls->P - P, D) > 0.0f)
+        return false;
+      f3 inplane;
+      if (is_round) {
+        inplane = ellipse_sample(axisu * 0.5f, axisv * 0.5f, randu, randv);
+        ls->P += inplane;
+        ls->pdf = invarea;
+      }
+      else {
+        inplane = ls->P;
+        ls->pdf = rect_light_sample(P, &ls->P, axisu, axisv, randu, randv, true);
+        inplane = ls->P - inplane;
+      }
+      ls->u = dot(inplane, axisu) * (1.0f / dot(axisu, axisu)) + 0.5f;
+      ls->v = dot(inplane, axisv) * (1.0f / dot(axisv, axisv)) + 0.5f;
+      ls->Ng = D;
+      ls->D = normalize_len(ls->P - P, &ls->t);
+      ls->eval_fac = 0.25f * invarea;
+      if (is_round)
+        ls->pdf *= lamp_light_pdf(D, -ls->D, ls->t);
+    }
+  }
+  ls->pdf *= kd_float(KD_INT_PDF_LIGHTS);
+  return (ls->pdf > 0.0f);
+}
+
+/* util_math_intersect.h:58-86 */
+CY_DEV bool ray_aligned_disk_intersect(f3 ray_P, f3 ray_D, float ray_t, f3 disk_P,
+                                       float disk_radius, f3 *isect_P, float *isect_t)
+{
+  float disk_t;
+  const f3 disk_N = normalize_len(ray_P - disk_P, &disk_t);
+  const float div = dot(ray_D, disk_N);
+  if (div == 0.0f)
+    return false;
+  const float t = -disk_t / div;
+  if (t < 0.0f || t > ray_t)
+    return false;
+  f3 P = ray_P + ray_D * t;
+  if (len_squared(P - disk_P) > disk_radius * disk_radius)
+    return false;
+  *isect_P = P;
+  *isect_t = t;
+  return true;
+}
+
+/* util_math_intersect.h:202-245 */
+CY_DEV bool ray_quad_intersect(f3 ray_P, f3 ray_D, float ray_mint, float ray_maxt, f3 quad_P,
+                               f3 quad_u, f3 quad_v, f3 quad_n, f3 *isect_P, float *isect_t,
+                               float *isect_u, float *isect_v, bool ellipse)
+{
+  float t = -(dot(ray_P, quad_n) - dot(quad_P, quad_n)) / dot(ray_D, quad_n);
+  if (t < ray_mint || t > ray_maxt)
+    return false;
+  const f3 hit = ray_P + t * ray_D;
+  const f3 inplane = hit - quad_P;
+  const float u = dot(inplane, quad_u) / dot(quad_u, quad_u);
+  if (u < -0.5f || u > 0.5f)
+    return false;
+  const float v = dot(inplane, quad_v) / dot(quad_v, quad_v);
+  if (v < -0.5f || v > 0.5f)
+    return false;
+  if (ellipse && (u * u + v * v > 0.25f))
+    return false;
+  *isect_P = hit;
+  *isect_t = t;
+  *isect_u = u + 0.5f;
+  *isect_v = v + 0.5f;
+  return true;
+}
+
+/* kernel_light.h:170-300 */
+CY_DEV bool lamp_light_eval(int lamp, f3 P, f3 D, float t, LightSampleG *ls)
+{
+  const uint8_t *kl = light_ptr(lamp);
+  const int type = kl_int(kl, KL_TYPE);
+  ls->type = type;
+  ls->shader = kl_int(kl, KL_SHADER_ID);
+  ls->object = CY_PRIM_NONE;
+  ls->prim = CY_PRIM_NONE;
+  ls->lamp = lamp;
+  ls->u = 0.0f;
+  ls->v = 0.0f;
+
+  if (!(ls->shader & CY_SHADER_USE_MIS))
+    return false;
+
+  if (type == CY_LIGHT_DISTANT) {
+    float radius = kl_float(kl, KL_DISTANT_RADIUS);
+    if (radius == 0.0f)
+      return false;
+    if (t != FLT_MAX)
+      return false;
+    f3 lightD = kl_float3(kl, KL_CO);
+    float costheta = dot(-lightD, D);
+    float cosangle = kl_float(kl, KL_DISTANT_COSANGLE);
+    if (costheta < cosangle)
+      return false;
+    ls->P = -D;
+    ls->Ng = -D;
+    ls->D = D;
+    ls->t = FLT_MAX;
+    float invarea = kl_float(kl, KL_DISTANT_INVAREA);
+    ls->pdf = invarea / (costheta * costheta * costheta);
+    ls->eval_fac = ls->pdf;
+  }
+  else if (type == CY_LIGHT_POINT || type == CY_LIGHT_SPOT) {
+    f3 lightP = kl_float3(kl, KL_CO);
+    float radius = kl_float(kl, KL_SPOT_RADIUS);
+    if (radius == 0.0f)
+      return false;
+    if (!ray_aligned_disk_intersect(P, D, t, lightP, radius, &ls->P, &ls->t))
+      return false;
+    ls->Ng = -D;
+    ls->D = D;
+    float invarea = kl_float(kl, KL_SPOT_INVAREA);
+    ls->eval_fac = (0.25f * CY_1_PI_F) * invarea;
+    ls->pdf = invarea;
+    if (type == CY_LIGHT_SPOT) {
+      f3 dir = kl_float3(kl, KL_SPOT_DIR);
+      ls->eval_fac *= spot_light_attenuation(dir, kl_float(kl, KL_SPOT_SPOT_ANGLE),
+                                             kl_float(kl, KL_SPOT_SPOT_SMOOTH), ls->Ng);
+      if (ls->eval_fac == 0.0f)
+        return false;
+    }
+    if (ls->t != FLT_MAX)
+      ls->pdf *= lamp_light_pdf(ls->Ng, -ls->D, ls->t);
+  }
+  else if (type == CY_LIGHT_AREA) {
+    float invarea_raw = kl_float(kl, KL_AREA_INVAREA);
+    float invarea = fabsf(invarea_raw);
+    bool is_round = (invarea_raw < 0.0f);
+    if (invarea == 0.0f)
+      return false;
+    f3 axisu = kl_float3(kl, KL_AREA_AXISU);
+    f3 axisv = kl_float3(kl, KL_AREA_AXISV);
+    f3 Ng = kl_float3(kl, KL_AREA_DIR);
+    if (dot(D, Ng) >= 0.0f)
+      return false;
+    f3 light_P = kl_float3(kl, KL_CO);
+    if (!ray_quad_intersect(P, D, 0.0f, t, light_P, axisu, axisv, Ng, &ls->P, &ls->t, &ls->u,
+                            &ls->v, is_round))
+      return false;
+    ls->D = D;
+    ls->Ng = Ng;
+    if (is_round)
+      ls->pdf = invarea * lamp_light_pdf(Ng, -D, ls->t);
+    else
+      ls->pdf = rect_light_sample(P, &light_P, axisu, axisv, 0, 0, false);
+    ls->eval_fac = 0.25f * invarea;
+  }
+  else {
+    return false;
+  }
+  ls->pdf *= kd_float(KD_INT_PDF_LIGHTS);
+  return true;
+}
+
+/* kernel_light.h:582-614 */
+CY_DEV int light_distribution_sample(float *randu)
+{
+  int first = 0;
+  const int num_distribution = kd_int(KD_INT_NUM_DISTRIBUTION);
+  int len = num_distribution + 1;
+  float r = *randu;
+  do {
+    int half_len = len >> 1;
+    int middle = first + half_len;
+    float totarea = __ldg((const float *)(g_scene.light_distribution +
+                                          (size_t)middle * SIZEOF_KERNEL_LIGHT_DISTRIBUTION +
+                                          KLD_TOTAREA));
+    if (r < totarea) {
+      len = half_len;
+    }
+    else {
+      first = middle + 1;
+      len = len - half_len - 1;
+    }
+  } while (len > 0);
+  int index = min(max(first - 1, 0), num_distribution - 1);
+  float distr_min = __ldg((const float *)(g_scene.light_distribution +
+                                          (size_t)index * SIZEOF_KERNEL_LIGHT_DISTRIBUTION));
+  float distr_max = __ldg((const float *)(g_scene.light_distribution +
+                                          (size_t)(index + 1) * SIZEOF_KERNEL_LIGHT_DISTRIBUTION));
+  *randu = (r - distr_min) / (distr_max - distr_min);
+  return index;
+}
+
+/* kernel_light.h:624-660 (lamp < 0: pick from the distribution) */
+CY_DEV bool light_sample(float randu, float randv, f3 P, int bounce, LightSampleG *ls)
+{
+  int index = light_distribution_sample(&randu);
+  int prim = __ldg((const int *)(g_scene.light_distribution +
+                                 (size_t)index * SIZEOF_KERNEL_LIGHT_DISTRIBUTION + KLD_PRIM));
+  if (prim >= 0)
+    return false; /* mesh lights: refused by check_scope (pdf_triangles != 0) */
+  int lamp = -prim - 1;
+  if ((float)bounce > kl_float(light_ptr(lamp), KL_MAX_BOUNCES))
+    return false;
+  return lamp_light_sample(lamp, randu, randv, P, ls);
+}
+
+/* ------------------------------------------------------------- emission */
+
+/* kernel_shader.h:978-992 */
+CY_DEV bool shader_constant_emission_eval(int shader, f3 *eval)
+{
+  const uint8_t *ks = g_scene.shaders + (size_t)(shader & CY_SHADER_MASK) * SIZEOF_KERNEL_SHADER;
+  uint32_t flags = __ldg((const uint32_t *)(ks + KS_FLAGS));
+  if (flags & CY_SD_HAS_CONSTANT_EMISSION) {
+    *eval = mk3(__ldg((const float *)(ks + KS_CONSTANT_EMISSION)),
+                __ldg((const float *)(ks + KS_CONSTANT_EMISSION + 4)),
+                __ldg((const float *)(ks + KS_CONSTANT_EMISSION + 8)));
+    return true;
+  }
+  return false;
+}
+
+/* kernel_emission.h:20-98 (lamps only).  `emission_sd` is scratch. */
+CY_DEV f3 direct_emissive_eval(ShaderDataG &emission_sd, LightSampleG *ls, f3 I, float t)
+{
+  f3 eval = zero3();
+  if (shader_constant_emission_eval(ls->shader, &eval)) {
+    if ((ls->prim != CY_PRIM_NONE) && dot(ls->Ng, I) < 0.0f)
+      ls->Ng = -ls->Ng;
+  }
+  else {
+    /* shader_setup_from_sample for a lamp (kernel_shader.h:244-345) */
+    emission_sd.P = ls->P;
+    emission_sd.N = ls->Ng;
+    emission_sd.Ng = ls->Ng;
+    emission_sd.I = I;
+    emission_sd.shader = ls->shader;
+    emission_sd.type = 0;
+    emission_sd.object = -1;
+    emission_sd.prim = CY_PRIM_NONE;
+    emission_sd.u = ls->u;
+    emission_sd.v = ls->v;
+    emission_sd.ray_length = t;
+    emission_sd.flag = shader_flags(ls->shader);
+    emission_sd.object_flag = 0;
+    emission_sd.dPdu = zero3();
+    ls->Ng = emission_sd.Ng;
+    shader_eval_surface(emission_sd, CY_PATH_RAY_EMISSION);
+    /* shader_emissive_eval: emissive_simple_eval(Ng, I) * weight */
+    if (emission_sd.flag & CY_SD_EMISSION) {
+      float cosNO = fabsf(dot(emission_sd.Ng, emission_sd.I));
+      float res = (cosNO > 0.0f) ? 1.0f : 0.0f;
+      eval = mk3(res, res, res) * emission_sd.closure_emission_background;
+    }
+  }
+  eval *= ls->eval_fac;
+  if (ls->lamp != CY_LAMP_NONE) {
+    eval *= kl_float3(light_ptr(ls->lamp), KL_STRENGTH);
+  }
+  return eval;
+}
+
+/* kernel_emission.h:288-340 without background MIS (refused by check_scope) */
+CY_DEV f3 indirect_background(ShaderDataG &emission_sd, const PathStateG &state, f3 rayD)
+{
+  int shader = kd_int(KD_BG_SURFACE_SHADER);
+  if (shader & CY_SHADER_EXCLUDE_ANY) {
+    if (((shader & CY_SHADER_EXCLUDE_DIFFUSE) && (state.flag & CY_PATH_RAY_DIFFUSE)) ||
+        ((shader & CY_SHADER_EXCLUDE_GLOSSY) &&
+         ((state.flag & (CY_PATH_RAY_GLOSSY | CY_PATH_RAY_REFLECT)) ==
+          (CY_PATH_RAY_GLOSSY | CY_PATH_RAY_REFLECT))) ||
+        ((shader & CY_SHADER_EXCLUDE_TRANSMIT) && (state.flag & CY_PATH_RAY_TRANSMIT)) ||
+        ((shader & CY_SHADER_EXCLUDE_CAMERA) && (state.flag & CY_PATH_RAY_CAMERA)) ||
+        ((shader & CY_SHADER_EXCLUDE_SCATTER) && (state.flag & CY_PATH_RAY_VOLUME_SCATTER)))
+      return zero3();
+  }
+  f3 L = zero3();
+  if (!shader_constant_emission_eval(shader, &L)) {
+    /* shader_setup_from_background (kernel_shader.h:395-430) */
+    emission_sd.P = rayD;
+    emission_sd.N = -rayD;
+    emission_sd.Ng = -rayD;
+    emission_sd.I = -rayD;
+    emission_sd.shader = shader;
+    emission_sd.flag = shader_flags(shader);
+    emission_sd.object_flag = 0;
+    emission_sd.ray_length = 0.0f;
+    emission_sd.object = -1;
+    emission_sd.prim = CY_PRIM_NONE;
+    emission_sd.type = 0;
+    emission_sd.u = emission_sd.v = 0.0f;
+    emission_sd.dPdu = zero3();
+    shader_eval_surface(emission_sd, state.flag | CY_PATH_RAY_EMISSION);
+    if (emission_sd.flag & CY_SD_EMISSION)
+      L = emission_sd.closure_emission_background;
+  }
+  return L;
+}
+
+/* kernel_accumulate.h:279-290 */
+CY_DEV void path_radiance_clamp(f3 *L, int bounce)
+{
+  float limit = (bounce > 0) ? kd_float(KD_INT_SAMPLE_CLAMP_INDIRECT) :
+                               kd_float(KD_INT_SAMPLE_CLAMP_DIRECT);
+  float sum = reduce_add(fabs3(*L));
+  if (sum > limit)
+    *L *= limit / sum;
+}
+
+#endif /* B200_SHADE_CUH */

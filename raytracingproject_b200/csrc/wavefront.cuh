@@ -1,9 +1,1172 @@
-/* wavefront.cuh - STAGE 1 placeholder (replaced by the real wavefront). */
-static void free_pool(b200_ctx *) {}
-static bool svm_validate(const uint32_t *, size_t, std::string &) { return true; }
-static int check_scope(b200_ctx *) { return B200_OK; }
-extern "C" {
-int b200_render(b200_ctx *ctx, const b200_work_tile *, volatile const int *) { return fail(ctx, B200_ERR_NOT_READY, "render not built yet"); }
-int b200_film_convert(b200_ctx *ctx, uint64_t, uint64_t, int, float, int, int, int, int, int, int) { return fail(ctx, B200_ERR_NOT_READY, "nyi"); }
-int b200_film_reduce(b200_ctx **, int, const uint64_t *, size_t) { return B200_ERR_NOT_READY; }
+/* wavefront.cuh - the path-tracing wavefront: SoA path pool, stage kernels and
+ * the host launch loop behind b200_render.  Included by b200_cycles.cu.
+ *
+ * Stage contract (names of the north star; reference semantics in brackets):
+ *   init_from_camera   [split/kernel_path_init.h:24, kernel_path.h:643-680]
+ *   intersect_closest  [split/kernel_scene_intersect.h:26, kernel_path.h:57-84]
+ *   sort / compaction  [split/kernel_queue_enqueue.h:38, kernel_shader_sort.h:19-95]
+ *   shade_background   [split/kernel_indirect_background.h:19, kernel_path.h:115-144]
+ *   shade_surface      [split/kernel_shader_setup.h .. kernel_next_iteration_setup.h,
+ *                       kernel_path.h:254-321,540-640, kernel_path_surface.h:22-358]
+ *   intersect_shadow + shade_shadow [split/kernel_shadow_blocked_dl.h:20-94]
+ *   film write         [split/kernel_buffer_update.h:41-171, kernel_passes.h:338-350]
+ *
+ * Differences from the reference's split kernel, by design: paths live in SoA
+ * arrays (one 128-bit record per field group) instead of AoS structs; queues
+ * are dense index arrays appended with one warp-aggregated atomic per warp;
+ * every stage runs over its queue only (not over the whole pool); hits are
+ * really sorted by shader before shading; the film is written once per batch by
+ * a float4 read-modify-write with one owner thread per pixel (no atomics); the
+ * host reads back one counter per bounce instead of the whole ray_state array.
+ */
+#ifndef B200_WAVEFRONT_CUH
+#define B200_WAVEFRONT_CUH
+
+#include <cuda_fp16.h>
+
+#include "shade.cuh"
+
+#define WF_MAX_KEYS 4096
+#define WF_BLOCK 256
+
+struct WFCounters {
+  unsigned int n_active; /* paths in q_active (input of intersect_closest) */
+  unsigned int n_next;   /* paths appended to q_next by shade_surface */
+  unsigned int n_shadow; /* shadow rays appended by shade_surface */
+  unsigned int work_closest, work_shadow;
+  unsigned int pad[3];
+  unsigned long long primary_rays, bounce_rays, shadow_rays;
+  unsigned long long nodes, tris, instances;
+  unsigned int hist[WF_MAX_KEYS + 1];
+  unsigned int offsets[WF_MAX_KEYS + 2];
+  unsigned int cursor[WF_MAX_KEYS + 1];
+};
+
+struct PathSoA {
+  float4 *ray_P_t;    /* Ray::P, Ray::t */
+  float4 *ray_D;      /* Ray::D, PathState::ray_pdf */
+  float4 *hit;        /* Intersection t,u,v, prim */
+  int *hit_object;    /* Intersection::object */
+  float4 *throughput; /* throughput, PathState::ray_t */
+  float4 *L;          /* PathRadiance::emission, transparent */
+  uint4 *stateA;      /* flag, rng_hash, rng_offset, sample */
+  uint4 *stateB;      /* bounce|diffuse<<16, glossy|transmission<<16, transparent, min_ray_pdf */
+  float4 *sh_P_t;     /* shadow ray */
+  float4 *sh_D;
+  float4 *sh_contrib; /* throughput * L_light (already clamped) */
+  unsigned int *key;  /* sort key: 0 miss, 1 + shader */
+  int *q_active, *q_next, *q_sorted, *q_shadow;
+  WFCounters *counters;
+};
+
+struct PathPool {
+  size_t capacity = 0;
+  PathSoA soa;
+  void *block = nullptr;
+  WFCounters *h_counters = nullptr; /* pinned */
+};
+
+struct BatchParams {
+  int x, y, w, h;      /* pixel rectangle of this batch */
+  int sample0, nsamples;
+  int offset, stride;  /* film addressing (buffers.cpp:50-54) */
+  int num_keys;
+  int count_stats;
+};
+
+/* ------------------------------------------------------------ helpers */
+
+/* one atomic per warp: lanes with `pred` get consecutive slots */
+CY_DEV unsigned int warp_append(unsigned int *counter, bool pred)
+{
+  const unsigned int mask = __ballot_sync(__activemask(), pred);
+  if (!pred)
+    return 0;
+  const unsigned int lane = threadIdx.x & 31u;
+  const unsigned int leader = __ffs(mask) - 1u;
+  unsigned int base = 0;
+  if (lane == leader)
+    base = atomicAdd(counter, __popc(mask));
+  base = __shfl_sync(mask, base, leader);
+  return base + __popc(mask & ((1u << lane) - 1u));
 }
+
+CY_DEV void state_load(const PathSoA &p, int i, PathStateG &s)
+{
+  const uint4 a = p.stateA[i];
+  const uint4 b = p.stateB[i];
+  s.flag = a.x;
+  s.rng_hash = a.y;
+  s.rng_offset = (int)a.z;
+  s.sample = (int)a.w;
+  s.bounce = (int)(b.x & 0xffffu);
+  s.diffuse_bounce = (int)(b.x >> 16);
+  s.glossy_bounce = (int)(b.y & 0xffffu);
+  s.transmission_bounce = (int)(b.y >> 16);
+  s.transparent_bounce = (int)b.z;
+  s.min_ray_pdf = __uint_as_float(b.w);
+}
+CY_DEV void state_store(const PathSoA &p, int i, const PathStateG &s)
+{
+  p.stateA[i] = make_uint4(s.flag, s.rng_hash, (unsigned)s.rng_offset, (unsigned)s.sample);
+  p.stateB[i] = make_uint4((unsigned)s.bounce | ((unsigned)s.diffuse_bounce << 16),
+                           (unsigned)s.glossy_bounce | ((unsigned)s.transmission_bounce << 16),
+                           (unsigned)s.transparent_bounce, __float_as_uint(s.min_ray_pdf));
+}
+
+/* kernel_path_state.h:190-203 */
+CY_DEV uint32_t path_state_ray_visibility(uint32_t state_flag)
+{
+  uint32_t flag = state_flag & CY_PATH_RAY_ALL_VISIBILITY;
+  if (flag & CY_PATH_RAY_TRANSMIT)
+    flag &= ~(CY_PATH_RAY_DIFFUSE | CY_PATH_RAY_GLOSSY);
+  if (state_flag & CY_PATH_RAY_VOLUME_SCATTER)
+    flag |= CY_PATH_RAY_DIFFUSE;
+  return flag;
+}
+
+/* kernel_path_state.h:251-260 */
+CY_DEV bool path_state_ao_bounce(const PathStateG &s)
+{
+  const int ao_bounces = kd_int(KD_INT_AO_BOUNCES);
+  if (s.bounce <= ao_bounces)
+    return false;
+  int bounce = s.bounce - s.transmission_bounce - (s.glossy_bounce > 0);
+  return (bounce > ao_bounces);
+}
+
+/* kernel_path_state.h:205-241 (no shadow catcher) */
+CY_DEV float path_state_continuation_probability(const PathStateG &s, f3 throughput)
+{
+  if (s.flag & CY_PATH_RAY_TERMINATE_IMMEDIATE) {
+    return 0.0f;
+  }
+  else if (s.flag & CY_PATH_RAY_TRANSPARENT) {
+    if (s.transparent_bounce <= kd_int(KD_INT_TRANSPARENT_MIN_BOUNCE))
+      return 1.0f;
+  }
+  else {
+    if (s.bounce <= kd_int(KD_INT_MIN_BOUNCE))
+      return 1.0f;
+  }
+  /* branch_factor is 1 for the non-branched integrator */
+  return fminf(sqrtf(max3(fabs3(throughput)) * 1.0f), 1.0f);
+}
+
+/* kernel_path_state.h:72-169 (surface labels) */
+CY_DEV void path_state_next(PathStateG &s, int label)
+{
+  if (label & CY_LABEL_TRANSPARENT) {
+    s.flag |= CY_PATH_RAY_TRANSPARENT;
+    s.transparent_bounce++;
+    if (s.transparent_bounce >= kd_int(KD_INT_TRANSPARENT_MAX_BOUNCE))
+      s.flag |= CY_PATH_RAY_TERMINATE_IMMEDIATE;
+    if (!kd_int(KD_INT_TRANSPARENT_SHADOWS))
+      s.flag |= CY_PATH_RAY_MIS_SKIP;
+    s.rng_offset += CY_PRNG_BOUNCE_NUM;
+    return;
+  }
+  s.bounce++;
+  if (s.bounce >= kd_int(KD_INT_MAX_BOUNCE))
+    s.flag |= CY_PATH_RAY_TERMINATE_AFTER_TRANSPARENT;
+  s.flag &= ~(CY_PATH_RAY_ALL_VISIBILITY | CY_PATH_RAY_MIS_SKIP);
+
+  if (label & CY_LABEL_REFLECT) {
+    s.flag |= CY_PATH_RAY_REFLECT;
+    s.flag &= ~CY_PATH_RAY_TRANSPARENT_BACKGROUND;
+    if (label & CY_LABEL_DIFFUSE) {
+      s.diffuse_bounce++;
+      if (s.diffuse_bounce >= kd_int(KD_INT_MAX_DIFFUSE_BOUNCE))
+        s.flag |= CY_PATH_RAY_TERMINATE_AFTER_TRANSPARENT;
+    }
+    else {
+      s.glossy_bounce++;
+      if (s.glossy_bounce >= kd_int(KD_INT_MAX_GLOSSY_BOUNCE))
+        s.flag |= CY_PATH_RAY_TERMINATE_AFTER_TRANSPARENT;
+    }
+  }
+  else {
+    s.flag |= CY_PATH_RAY_TRANSMIT;
+    if (!(label & CY_LABEL_TRANSMIT_TRANSPARENT))
+      s.flag &= ~CY_PATH_RAY_TRANSPARENT_BACKGROUND;
+    s.transmission_bounce++;
+    if (s.transmission_bounce >= kd_int(KD_INT_MAX_TRANSMISSION_BOUNCE))
+      s.flag |= CY_PATH_RAY_TERMINATE_AFTER_TRANSPARENT;
+  }
+  if (label & CY_LABEL_DIFFUSE) {
+    s.flag |= CY_PATH_RAY_DIFFUSE | CY_PATH_RAY_DIFFUSE_ANCESTOR;
+  }
+  else if (label & CY_LABEL_GLOSSY) {
+    s.flag |= CY_PATH_RAY_GLOSSY;
+  }
+  else {
+    s.flag |= CY_PATH_RAY_GLOSSY | CY_PATH_RAY_SINGULAR | CY_PATH_RAY_MIS_SKIP;
+  }
+  s.rng_offset += CY_PRNG_BOUNCE_NUM;
+}
+
+/* ------------------------------------------------------ init_from_camera */
+
+__global__ void __launch_bounds__(WF_BLOCK)
+    k_init_from_camera(PathSoA p, BatchParams bp)
+{
+  const unsigned int npix = (unsigned)bp.w * (unsigned)bp.h;
+  const unsigned int n = npix * (unsigned)bp.nsamples;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned int pix = i % npix;
+    const int s = (int)(i / npix);
+    const int x = bp.x + (int)(pix % (unsigned)bp.w);
+    const int y = bp.y + (int)(pix / (unsigned)bp.w);
+    const int sample = bp.sample0 + s;
+
+    uint32_t rng_hash;
+    f3 P, D;
+    const float t = camera_ray(x, y, sample, &rng_hash, &P, &D);
+
+    /* path_state_init - kernel_path_state.h:19-70 */
+    PathStateG st;
+    st.flag = CY_PATH_RAY_CAMERA | CY_PATH_RAY_MIS_SKIP | CY_PATH_RAY_TRANSPARENT_BACKGROUND;
+    st.rng_hash = rng_hash;
+    st.rng_offset = CY_PRNG_BASE_NUM;
+    st.sample = sample;
+    st.bounce = st.diffuse_bounce = st.glossy_bounce = st.transmission_bounce = 0;
+    st.transparent_bounce = 0;
+    st.min_ray_pdf = FLT_MAX;
+    state_store(p, i, st);
+
+    p.ray_P_t[i] = make_float4(P.x, P.y, P.z, t);
+    p.ray_D[i] = make_float4(D.x, D.y, D.z, 0.0f);            /* ray_pdf = 0 */
+    p.throughput[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);    /* ray_t = 0 */
+    /* kernel_path_trace returns before kernel_write_result when ray.t == 0
+     * (kernel_path.h:668-670): transparent = 1 makes the film add (0,0,0,0). */
+    p.L[i] = make_float4(0.0f, 0.0f, 0.0f, (t == 0.0f) ? 1.0f : 0.0f);
+    const unsigned int slot = warp_append(&p.counters->n_active, t != 0.0f);
+    if (t != 0.0f)
+      p.q_active[slot] = (int)i;
+  }
+}
+
+/* ----------------------------------------------------- intersect_closest */
+
+template<bool COUNT>
+__global__ void __launch_bounds__(128) k_intersect_closest(PathSoA p)
+{
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned int n = p.counters->n_active;
+  TraceCounters cnt;
+  cnt.nodes = cnt.tris = cnt.instances = 0;
+  unsigned int n_primary = 0, n_bounce = 0;
+  while (true) {
+    unsigned int base = 0;
+    if (lane == 0)
+      base = atomicAdd(&p.counters->work_closest, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n)
+      break;
+    const unsigned int qi = base + lane;
+    if (qi < n) {
+      const int i = p.q_active[qi];
+      float4 r0 = p.ray_P_t[i];
+      const float4 r1 = p.ray_D[i];
+      PathStateG st;
+      state_load(p, i, st);
+      /* kernel_path_scene_intersect - kernel_path.h:57-84 */
+      uint32_t visibility = path_state_ray_visibility(st.flag);
+      if (path_state_ao_bounce(st)) {
+        visibility = CY_PATH_RAY_SHADOW;
+        r0.w = kd_float(KD_BG_AO_DISTANCE);
+      }
+      if (st.flag & CY_PATH_RAY_CAMERA)
+        n_primary++;
+      else
+        n_bounce++;
+      TraceHit h;
+      h.t = r0.w;
+      h.u = h.v = 0.0f;
+      h.prim = -1;
+      h.object = -1;
+      /* scene_intersect_valid - bvh/bvh.h:146-152 */
+      const f3 D = mk3(r1);
+      if (isfinite_safe(r0.x) && isfinite_safe(r1.x) && len_squared(D) != 0.0f)
+        bvh8_intersect<false, COUNT>(mk3(r0), D, r0.w, visibility, h, cnt);
+      p.hit[i] = make_float4(h.t, h.u, h.v, __int_as_float(h.prim));
+      p.hit_object[i] = h.object;
+      unsigned int key = 0;
+      if (h.prim >= 0) {
+        const unsigned int tri = __ldg(&g_scene.prim_index[h.prim]);
+        key = 1u + (__ldg(&g_scene.tri_shader[tri]) & CY_SHADER_MASK);
+        if (key > WF_MAX_KEYS)
+          key = WF_MAX_KEYS;
+      }
+      p.key[i] = key;
+      /* histogram for the shader sort: one atomic per distinct key per warp */
+      const unsigned int peers = __match_any_sync(__activemask(), key);
+      if (lane == (unsigned)(__ffs(peers) - 1))
+        atomicAdd(&p.counters->hist[key], __popc(peers));
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    n_primary += __shfl_xor_sync(0xffffffffu, n_primary, o);
+    n_bounce += __shfl_xor_sync(0xffffffffu, n_bounce, o);
+    if (COUNT) {
+      cnt.nodes += __shfl_xor_sync(0xffffffffu, cnt.nodes, o);
+      cnt.tris += __shfl_xor_sync(0xffffffffu, cnt.tris, o);
+      cnt.instances += __shfl_xor_sync(0xffffffffu, cnt.instances, o);
+    }
+  }
+  if (lane == 0) {
+    if (n_primary)
+      atomicAdd(&p.counters->primary_rays, (unsigned long long)n_primary);
+    if (n_bounce)
+      atomicAdd(&p.counters->bounce_rays, (unsigned long long)n_bounce);
+    if (COUNT) {
+      atomicAdd(&p.counters->nodes, (unsigned long long)cnt.nodes);
+      atomicAdd(&p.counters->tris, (unsigned long long)cnt.tris);
+      atomicAdd(&p.counters->instances, (unsigned long long)cnt.instances);
+    }
+  }
+}
+
+/* ----------------------------------------------- sort by shader (counting) */
+
+__global__ void k_sort_scan(PathSoA p, int num_keys)
+{
+  /* single block: exclusive scan of the key histogram */
+  __shared__ unsigned int sh[WF_MAX_KEYS + 1];
+  WFCounters *c = p.counters;
+  for (int k = threadIdx.x; k <= num_keys; k += blockDim.x)
+    sh[k] = c->hist[k];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int run = 0;
+    for (int k = 0; k <= num_keys; k++) {
+      const unsigned int v = sh[k];
+      c->offsets[k] = run;
+      c->cursor[k] = 0;
+      run += v;
+    }
+    c->offsets[num_keys + 1] = run;
+  }
+}
+
+__global__ void __launch_bounds__(WF_BLOCK) k_sort_scatter(PathSoA p)
+{
+  WFCounters *c = p.counters;
+  const unsigned int n = c->n_active;
+  for (unsigned int qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n;
+       qi += gridDim.x * blockDim.x) {
+    const int i = p.q_active[qi];
+    const unsigned int key = p.key[i];
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int peers = __match_any_sync(__activemask(), key);
+    const unsigned int leader = __ffs(peers) - 1u;
+    unsigned int base = 0;
+    if (lane == leader)
+      base = atomicAdd(&c->cursor[key], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const unsigned int pos = c->offsets[key] + base + __popc(peers & ((1u << lane) - 1u));
+    p.q_sorted[pos] = i;
+  }
+}
+
+/* --------------------------------------------------- lamp emission (MIS) */
+
+/* kernel_path.h:86-113 + kernel_emission.h:235-286: emission of lamps hit by the
+ * ray segment, weighted against light sampling.  Returns the updated ray_t. */
+CY_DEV void path_lamp_emission(PathStateG &st, f3 rayP, f3 rayD, float isect_t, f3 throughput,
+                               ShaderDataG &emission_sd, f3 &L_emission)
+{
+  if (kd_int(KD_INT_USE_LAMP_MIS) && !(st.flag & CY_PATH_RAY_CAMERA)) {
+    const f3 lP = rayP - st.ray_t * rayD;
+    st.ray_t += isect_t;
+    const float lt = st.ray_t;
+    const int num_lights = kd_int(KD_INT_NUM_ALL_LIGHTS);
+    for (int lamp = 0; lamp < num_lights; lamp++) {
+      LightSampleG ls;
+      if (!lamp_light_eval(lamp, lP, rayD, lt, &ls))
+        continue;
+      if (ls.shader & CY_SHADER_EXCLUDE_ANY) {
+        if (((ls.shader & CY_SHADER_EXCLUDE_DIFFUSE) && (st.flag & CY_PATH_RAY_DIFFUSE)) ||
+            ((ls.shader & CY_SHADER_EXCLUDE_GLOSSY) &&
+             ((st.flag & (CY_PATH_RAY_GLOSSY | CY_PATH_RAY_REFLECT)) ==
+              (CY_PATH_RAY_GLOSSY | CY_PATH_RAY_REFLECT))) ||
+            ((ls.shader & CY_SHADER_EXCLUDE_TRANSMIT) && (st.flag & CY_PATH_RAY_TRANSMIT)) ||
+            ((ls.shader & CY_SHADER_EXCLUDE_SCATTER) && (st.flag & CY_PATH_RAY_VOLUME_SCATTER)))
+          continue;
+      }
+      f3 lamp_L = direct_emissive_eval(emission_sd, &ls, -rayD, ls.t);
+      if (!(st.flag & CY_PATH_RAY_MIS_SKIP)) {
+        float mis_weight = power_heuristic(st.ray_pdf, ls.pdf);
+        lamp_L *= mis_weight;
+      }
+      /* path_radiance_accum_emission - kernel_accumulate.h:310-340 */
+      f3 contribution = throughput * lamp_L;
+      path_radiance_clamp(&contribution, st.bounce - 1);
+      L_emission += contribution;
+    }
+  }
+}
+
+/* ----------------------------------------------------- shade_background */
+
+__global__ void __launch_bounds__(WF_BLOCK) k_shade_background(PathSoA p)
+{
+  WFCounters *c = p.counters;
+  const unsigned int n = c->offsets[1]; /* key 0 segment */
+  for (unsigned int qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n;
+       qi += gridDim.x * blockDim.x) {
+    const int i = p.q_sorted[qi];
+    const float4 r0 = p.ray_P_t[i];
+    const float4 r1 = p.ray_D[i];
+    const float4 tp = p.throughput[i];
+    float4 Lr = p.L[i];
+    PathStateG st;
+    state_load(p, i, st);
+    st.ray_pdf = r1.w;
+    st.ray_t = tp.w;
+    f3 throughput = mk3(tp);
+    f3 L = mk3(Lr);
+    const f3 rayP = mk3(r0), rayD = mk3(r1);
+    const float isect_t = p.hit[i].x; /* = ray t on a miss (bvh_traversal.h:62) */
+
+    ShaderDataG esd;
+    path_lamp_emission(st, rayP, rayD, isect_t, throughput, esd, L);
+
+    /* kernel_path_background - kernel_path.h:115-144 */
+    bool eval_bg = true;
+    if (kd_int(KD_BG_TRANSPARENT) && (st.flag & CY_PATH_RAY_TRANSPARENT_BACKGROUND)) {
+      Lr.w += average(throughput);
+      eval_bg = false; /* no light passes: return */
+    }
+    if (eval_bg) {
+      if (path_state_ao_bounce(st))
+        throughput *= kd_float(KD_BG_AO_BOUNCES_FACTOR);
+      f3 L_background = indirect_background(esd, st, rayD);
+      /* path_radiance_accum_background - kernel_accumulate.h:478-515 */
+      f3 contribution = throughput * L_background;
+      path_radiance_clamp(&contribution, st.bounce - 1);
+      L += contribution;
+    }
+    p.L[i] = make_float4(L.x, L.y, L.z, Lr.w);
+  }
+}
+
+/* -------------------------------------------------------- shade_surface */
+
+__global__ void __launch_bounds__(WF_BLOCK) k_shade_surface(PathSoA p, int num_keys)
+{
+  WFCounters *c = p.counters;
+  const unsigned int begin = c->offsets[1];
+  const unsigned int end = c->offsets[num_keys + 1];
+  const unsigned int total = end - begin;
+  /* the grid-stride loop is uniform per warp so that warp_append's ballots see
+   * every lane of the warp that is still looping */
+  const unsigned int rounds = (total + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+  for (unsigned int r = 0; r < rounds; r++) {
+    const unsigned int k = r * gridDim.x * blockDim.x + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = k < total;
+    bool want_next = false, want_shadow = false;
+    int i = -1;
+    if (valid) {
+      i = p.q_sorted[begin + k];
+      const float4 r0 = p.ray_P_t[i];
+      const float4 r1 = p.ray_D[i];
+      const float4 tp = p.throughput[i];
+      const float4 hit = p.hit[i];
+      const int hit_object = p.hit_object[i];
+      const float4 Lr = p.L[i];
+      PathStateG st;
+      state_load(p, i, st);
+      st.ray_pdf = r1.w;
+      st.ray_t = tp.w;
+      f3 throughput = mk3(tp);
+      f3 L = mk3(Lr);
+      f3 rayP = mk3(r0), rayD = mk3(r1);
+      float ray_t = r0.w;
+      const int hit_prim = __float_as_int(hit.w);
+
+      ShaderDataG sd;
+      {
+        /* lamps crossed before the hit (kernel_path.h:537) - uses `sd` as scratch */
+        path_lamp_emission(st, rayP, rayD, hit.x, throughput, sd, L);
+      }
+
+      bool alive = !path_state_ao_bounce(st); /* kernel_path.h:560-562 */
+      if (alive) {
+        shader_setup_from_ray(sd, hit_prim, hit_object, hit.x, hit.y, hit.z, rayP, rayD);
+        shader_eval_surface(sd, st.flag);
+        shader_prepare_closures(sd, st);
+
+        /* kernel_path_shader_apply - kernel_path.h:254-321 (no holdout / shadow catcher;
+         * filter_glossy handled below) */
+        if (kd_float(KD_INT_FILTER_GLOSSY) != FLT_MAX) {
+          float blur_pdf = kd_float(KD_INT_FILTER_GLOSSY) * st.min_ray_pdf;
+          if (blur_pdf < 1.0f) {
+            float blur_roughness = sqrtf(1.0f - blur_pdf) * 0.5f;
+            for (int ci = 0; ci < sd.num_closure; ci++) {
+              Closure &sc = sd.closure[ci];
+              if (sc.type >= CY_CLOSURE_BSDF_MICROFACET_GGX_ID &&
+                  sc.type <= CY_CLOSURE_BSDF_MICROFACET_GGX_REFRACTION_ID &&
+                  sc.type != CY_CLOSURE_BSDF_MICROFACET_BECKMANN_ID) {
+                sc.alpha_x = fmaxf(blur_roughness, sc.alpha_x);
+                sc.alpha_y = fmaxf(blur_roughness, sc.alpha_y);
+              }
+            }
+          }
+        }
+        if (sd.flag & CY_SD_EMISSION) {
+          /* indirect_primitive_emission without mesh-light MIS (pdf_triangles == 0) */
+          float cosNO = fabsf(dot(sd.Ng, sd.I));
+          float res = (cosNO > 0.0f) ? 1.0f : 0.0f;
+          f3 emission = mk3(res, res, res) * sd.closure_emission_background;
+          f3 contribution = throughput * emission;
+          path_radiance_clamp(&contribution, st.bounce - 1);
+          L += contribution;
+        }
+
+        /* russian roulette - kernel_path.h:578-589 */
+        float probability = path_state_continuation_probability(st, throughput);
+        if (probability == 0.0f) {
+          alive = false;
+        }
+        else if (probability != 1.0f) {
+          float terminate = path_state_rng_1D(st, CY_PRNG_TERMINATE);
+          if (terminate >= probability)
+            alive = false;
+          else
+            throughput /= probability;
+        }
+      }
+
+      if (alive) {
+        /* direct light - kernel_path_surface.h:22-125 with one light sample */
+        if (kd_int(KD_INT_USE_DIRECT_LIGHT) && (sd.flag & CY_SD_BSDF_HAS_EVAL)) {
+          float light_u, light_v;
+          path_state_rng_2D(st, CY_PRNG_LIGHT_U, &light_u, &light_v);
+          float terminate = 0.0f;
+          if (kd_float(KD_INT_LIGHT_INV_RR_THRESHOLD) > 0.0f)
+            terminate = path_state_rng_1D(st, CY_PRNG_LIGHT_TERMINATE);
+          LightSampleG ls;
+          if (light_sample(light_u, light_v, sd.P, st.bounce, &ls) && ls.pdf != 0.0f) {
+            /* direct_emission - kernel_emission.h:101-212 */
+            f3 light_eval;
+            {
+              /* the emission ShaderData must not clobber sd: evaluate constant
+               * emission directly, fall back to a scratch copy otherwise */
+              f3 ce;
+              if (shader_constant_emission_eval(ls.shader, &ce)) {
+                light_eval = ce * ls.eval_fac;
+                if (ls.lamp != CY_LAMP_NONE)
+                  light_eval *= kl_float3(light_ptr(ls.lamp), KL_STRENGTH);
+              }
+              else {
+                ShaderDataG scratch;
+                light_eval = direct_emissive_eval(scratch, &ls, -ls.D, ls.t);
+              }
+            }
+            if (!is_zero(light_eval)) {
+              f3 eval = shader_bsdf_eval(sd, ls.D, ls.pdf, (ls.shader & CY_SHADER_USE_MIS) != 0);
+              eval *= light_eval / ls.pdf;
+              bool ok = !is_zero(eval);
+              if (ok && kd_float(KD_INT_LIGHT_INV_RR_THRESHOLD) > 0.0f) {
+                float probability = max3(fabs3(eval)) * kd_float(KD_INT_LIGHT_INV_RR_THRESHOLD);
+                if (probability < 1.0f) {
+                  if (terminate >= probability)
+                    ok = false;
+                  else
+                    eval *= 1.0f / probability;
+                }
+              }
+              if (ok) {
+                /* path_radiance_accum_light (no light passes): contribution =
+                 * throughput * shadow(=1) * eval, clamped by bounce */
+                f3 contribution = throughput * eval;
+                path_radiance_clamp(&contribution, st.bounce);
+                if (ls.shader & CY_SHADER_CAST_SHADOW) {
+                  bool transmit = (dot(sd.Ng, ls.D) < 0.0f);
+                  f3 sP = ray_offset(sd.P, transmit ? -sd.Ng : sd.Ng);
+                  f3 sD;
+                  float st_t;
+                  if (ls.t == FLT_MAX) {
+                    sD = ls.D;
+                    st_t = ls.t;
+                  }
+                  else {
+                    sD = ray_offset(ls.P, ls.Ng) - sP;
+                    sD = normalize_len(sD, &st_t);
+                  }
+                  p.sh_P_t[i] = make_float4(sP.x, sP.y, sP.z, st_t);
+                  p.sh_D[i] = make_float4(sD.x, sD.y, sD.z, 0.0f);
+                  p.sh_contrib[i] = make_float4(contribution.x, contribution.y, contribution.z,
+                                                0.0f);
+                  want_shadow = true;
+                }
+                else {
+                  /* ray.t = 0: shadow_blocked returns false immediately */
+                  L += contribution;
+                }
+              }
+            }
+          }
+        }
+
+        /* kernel_path_surface_bounce - kernel_path_surface.h:270-358 */
+        if (sd.flag & CY_SD_BSDF) {
+          float bsdf_u, bsdf_v;
+          path_state_rng_2D(st, CY_PRNG_BSDF_U, &bsdf_u, &bsdf_v);
+          f3 bsdf_eval = zero3(), omega_in = zero3();
+          float bsdf_pdf;
+          int label = shader_bsdf_sample(sd, bsdf_u, bsdf_v, &bsdf_eval, &omega_in, &bsdf_pdf);
+          if (!(bsdf_pdf == 0.0f || is_zero(bsdf_eval))) {
+            /* LABEL_TRANSMIT_TRANSPARENT (closure/bsdf.h:466-475) needs transparent glass,
+             * which check_scope refuses (threshold < 0 here) */
+            /* path_radiance_bsdf_bounce, no light passes */
+            float inverse_pdf = 1.0f / bsdf_pdf;
+            throughput *= bsdf_eval * inverse_pdf;
+            if (!(label & CY_LABEL_TRANSPARENT)) {
+              st.ray_pdf = bsdf_pdf;
+              st.ray_t = 0.0f;
+              st.min_ray_pdf = fminf(bsdf_pdf, st.min_ray_pdf);
+            }
+            path_state_next(st, label);
+            rayP = ray_offset(sd.P, (label & CY_LABEL_TRANSMIT) ? -sd.Ng : sd.Ng);
+            rayD = normalize(omega_in);
+            if (st.bounce == 0)
+              ray_t -= sd.ray_length;
+            else
+              ray_t = FLT_MAX;
+            want_next = true;
+          }
+        }
+      }
+
+      /* write back */
+      p.L[i] = make_float4(L.x, L.y, L.z, Lr.w);
+      if (want_next) {
+        p.ray_P_t[i] = make_float4(rayP.x, rayP.y, rayP.z, ray_t);
+        p.ray_D[i] = make_float4(rayD.x, rayD.y, rayD.z, st.ray_pdf);
+        p.throughput[i] = make_float4(throughput.x, throughput.y, throughput.z, st.ray_t);
+        state_store(p, i, st);
+      }
+    }
+    const unsigned int s_next = warp_append(&c->n_next, want_next);
+    if (want_next)
+      p.q_next[s_next] = i;
+    const unsigned int s_sh = warp_append(&c->n_shadow, want_shadow);
+    if (want_shadow)
+      p.q_shadow[s_sh] = i;
+  }
+}
+
+/* -------------------------------------- intersect_shadow + shade_shadow */
+
+template<bool COUNT>
+__global__ void __launch_bounds__(128) k_intersect_shadow(PathSoA p)
+{
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned int n = p.counters->n_shadow;
+  TraceCounters cnt;
+  cnt.nodes = cnt.tris = cnt.instances = 0;
+  while (true) {
+    unsigned int base = 0;
+    if (lane == 0)
+      base = atomicAdd(&p.counters->work_shadow, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n)
+      break;
+    const unsigned int qi = base + lane;
+    if (qi < n) {
+      const int i = p.q_shadow[qi];
+      const float4 r0 = p.sh_P_t[i];
+      const float4 r1 = p.sh_D[i];
+      TraceHit h;
+      bool blocked = false;
+      /* shadow_blocked_opaque - kernel_shadow.h:90-106: visibility & SHADOW_OPAQUE */
+      const f3 D = mk3(r1);
+      if (isfinite_safe(r0.x) && isfinite_safe(r1.x) && len_squared(D) != 0.0f)
+        blocked = bvh8_intersect<true, COUNT>(mk3(r0), D, r0.w, CY_PATH_RAY_SHADOW_OPAQUE, h, cnt);
+      if (!blocked) {
+        /* shade_shadow - path_radiance_accum_light, kernel_accumulate.h:402-459 */
+        const float4 cn = p.sh_contrib[i];
+        float4 L = p.L[i];
+        L.x += cn.x;
+        L.y += cn.y;
+        L.z += cn.z;
+        p.L[i] = L;
+      }
+    }
+  }
+  if (COUNT) {
+    for (int o = 16; o > 0; o >>= 1) {
+      cnt.nodes += __shfl_xor_sync(0xffffffffu, cnt.nodes, o);
+      cnt.tris += __shfl_xor_sync(0xffffffffu, cnt.tris, o);
+      cnt.instances += __shfl_xor_sync(0xffffffffu, cnt.instances, o);
+    }
+    if (lane == 0) {
+      atomicAdd(&p.counters->nodes, (unsigned long long)cnt.nodes);
+      atomicAdd(&p.counters->tris, (unsigned long long)cnt.tris);
+      atomicAdd(&p.counters->instances, (unsigned long long)cnt.instances);
+    }
+  }
+}
+
+/* per-iteration bookkeeping: q_next becomes q_active (pointers are swapped on
+ * the host), counters roll over */
+__global__ void k_iteration_end(PathSoA p, int num_keys)
+{
+  WFCounters *c = p.counters;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    c->shadow_rays += c->n_shadow;
+    c->n_active = c->n_next;
+    c->n_next = 0;
+    c->n_shadow = 0;
+    c->work_closest = 0;
+    c->work_shadow = 0;
+  }
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= num_keys; k += gridDim.x * blockDim.x)
+    c->hist[k] = 0;
+}
+
+/* ---------------------------------------------------------- film write */
+
+/* kernel_write_result / kernel_write_pass_float4 (kernel_passes.h:338-350,
+ * kernel_write_passes.h:49-65) for the whole batch: one thread owns a pixel,
+ * sums its samples in sample order (the order the CPU adds them) and does one
+ * float4 read-modify-write - no atomics. */
+__global__ void __launch_bounds__(WF_BLOCK)
+    k_film_accumulate(PathSoA p, BatchParams bp, float *film, int pass_stride, int pass_combined)
+{
+  const unsigned int npix = (unsigned)bp.w * (unsigned)bp.h;
+  for (unsigned int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
+       pix += gridDim.x * blockDim.x) {
+    const int x = bp.x + (int)(pix % (unsigned)bp.w);
+    const int y = bp.y + (int)(pix / (unsigned)bp.w);
+    const long long index = (long long)bp.offset + x + (long long)y * bp.stride;
+    float4 *dst = (float4 *)(film + index * pass_stride + pass_combined);
+    float4 acc = *dst;
+    for (int s = 0; s < bp.nsamples; s++) {
+      const float4 L = p.L[(size_t)s * npix + pix];
+      /* path_radiance_clamp_and_sum - kernel_accumulate.h:622-688 */
+      float3 Ls = make_float3(L.x, L.y, L.z);
+      const float sum = fabsf(Ls.x) + fabsf(Ls.y) + fabsf(Ls.z);
+      if (!isfinite_safe(sum))
+        Ls = make_float3(0.0f, 0.0f, 0.0f);
+      const float alpha = 1.0f - L.w;
+      acc.x += Ls.x;
+      acc.y += Ls.y;
+      acc.z += Ls.z;
+      acc.w += alpha;
+    }
+    *dst = acc;
+  }
+}
+
+/* kernel_film.h:90-130 - float film -> display bytes / halfs */
+CY_DEV float color_linear_to_srgb(float c)
+{
+  if (c < 0.0031308f)
+    return (c < 0.0f) ? 0.0f : c * 12.92f;
+  else
+    return 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
+}
+__global__ void k_film_convert(const float *film, void *rgba, int half_float, float sample_scale,
+                               int x0, int y0, int w, int h, int offset, int stride,
+                               int pass_stride, float exposure)
+{
+  const int x = x0 + blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= x0 + w || y >= y0 + h)
+    return;
+  const long long index = (long long)offset + x + (long long)y * stride;
+  const float4 in = *(const float4 *)(film + index * pass_stride);
+  /* film_get_pass_result with the combined pass: scale, exposure on rgb */
+  float4 r = make_float4(in.x * sample_scale * exposure, in.y * sample_scale * exposure,
+                         in.z * sample_scale * exposure, in.w * sample_scale);
+  if (half_float) {
+    __half *out = (__half *)rgba + index * 4;
+    out[0] = __float2half(r.x);
+    out[1] = __float2half(r.y);
+    out[2] = __float2half(r.z);
+    out[3] = __float2half(r.w);
+  }
+  else {
+    uchar4 *out = (uchar4 *)rgba + index;
+    uchar4 v;
+    v.x = (unsigned char)(saturate(color_linear_to_srgb(r.x)) * 255.0f);
+    v.y = (unsigned char)(saturate(color_linear_to_srgb(r.y)) * 255.0f);
+    v.z = (unsigned char)(saturate(color_linear_to_srgb(r.z)) * 255.0f);
+    v.w = (unsigned char)(saturate(r.w) * 255.0f);
+    *out = v;
+  }
+}
+
+__global__ void k_film_add(float4 *dst, const float4 *src, size_t n4)
+{
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float4 a = dst[i];
+    const float4 b = src[i];
+    a.x += b.x;
+    a.y += b.y;
+    a.z += b.z;
+    a.w += b.w;
+    dst[i] = a;
+  }
+}
+
+/* ============================================================ host side */
+
+static void free_pool(b200_ctx *ctx)
+{
+  if (!ctx->pool)
+    return;
+  DeviceGuard guard(ctx->ordinal);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->pool->block)
+    cudaFree(ctx->pool->block);
+  if (ctx->pool->h_counters)
+    cudaFreeHost(ctx->pool->h_counters);
+  delete ctx->pool;
+  ctx->pool = nullptr;
+}
+
+static int ensure_pool(b200_ctx *ctx, size_t capacity)
+{
+  if (ctx->pool && ctx->pool->capacity >= capacity)
+    return B200_OK;
+  free_pool(ctx);
+  PathPool *pool = new PathPool();
+  pool->capacity = capacity;
+  /* carve one allocation; every array 256-byte aligned */
+  size_t off = 0;
+  auto carve = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t n = capacity;
+  size_t o_rayP = carve(n * 16), o_rayD = carve(n * 16), o_hit = carve(n * 16),
+         o_hobj = carve(n * 4), o_thr = carve(n * 16), o_L = carve(n * 16), o_sA = carve(n * 16),
+         o_sB = carve(n * 16), o_shP = carve(n * 16), o_shD = carve(n * 16), o_shC = carve(n * 16),
+         o_key = carve(n * 4), o_qa = carve(n * 4), o_qn = carve(n * 4), o_qs = carve(n * 4),
+         o_qsh = carve(n * 4), o_cnt = carve(sizeof(WFCounters));
+  cudaError_t e = cudaMalloc(&pool->block, off);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    delete pool;
+    return fail(ctx, e == cudaErrorMemoryAllocation ? B200_ERR_OOM : B200_ERR_CUDA,
+                std::string("path pool allocation: ") + cudaGetErrorString(e));
+  }
+  char *b = (char *)pool->block;
+  PathSoA &s = pool->soa;
+  s.ray_P_t = (float4 *)(b + o_rayP);
+  s.ray_D = (float4 *)(b + o_rayD);
+  s.hit = (float4 *)(b + o_hit);
+  s.hit_object = (int *)(b + o_hobj);
+  s.throughput = (float4 *)(b + o_thr);
+  s.L = (float4 *)(b + o_L);
+  s.stateA = (uint4 *)(b + o_sA);
+  s.stateB = (uint4 *)(b + o_sB);
+  s.sh_P_t = (float4 *)(b + o_shP);
+  s.sh_D = (float4 *)(b + o_shD);
+  s.sh_contrib = (float4 *)(b + o_shC);
+  s.key = (unsigned int *)(b + o_key);
+  s.q_active = (int *)(b + o_qa);
+  s.q_next = (int *)(b + o_qn);
+  s.q_sorted = (int *)(b + o_qs);
+  s.q_shadow = (int *)(b + o_qsh);
+  s.counters = (WFCounters *)(b + o_cnt);
+  if (cudaMallocHost(&pool->h_counters, sizeof(WFCounters)) != cudaSuccess) {
+    cudaFree(pool->block);
+    delete pool;
+    return fail(ctx, B200_ERR_CUDA, "pinned counter allocation failed");
+  }
+  ctx->pool = pool;
+  return B200_OK;
+}
+
+/* Opcodes and closure ids the kernels implement (svm.h switch subset). */
+static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why)
+{
+  /* Walk the stream linearly; NODE_CLOSURE_BSDF and NODE_VALUE_V carry data nodes
+   * that must be skipped exactly as the interpreter does. */
+  size_t i = 0;
+  while (i < n_nodes) {
+    const uint32_t op = nodes[4 * i];
+    switch (op) {
+      case CY_NODE_END:
+      case CY_NODE_SHADER_JUMP:
+      case CY_NODE_CLOSURE_EMISSION:
+      case CY_NODE_CLOSURE_BACKGROUND:
+      case CY_NODE_CLOSURE_SET_WEIGHT:
+      case CY_NODE_CLOSURE_WEIGHT:
+      case CY_NODE_EMISSION_WEIGHT:
+      case CY_NODE_MIX_CLOSURE:
+      case CY_NODE_JUMP_IF_ZERO:
+      case CY_NODE_JUMP_IF_ONE:
+      case CY_NODE_GEOMETRY:
+      case CY_NODE_VALUE_F:
+        i += 1;
+        break;
+      case CY_NODE_VALUE_V:
+        i += 2;
+        break;
+      case CY_NODE_CLOSURE_BSDF: {
+        const uint32_t type = nodes[4 * i + 1] & 0xff;
+        if (type == CY_CLOSURE_BSDF_PRINCIPLED_ID) {
+          if (i + 2 >= n_nodes) {
+            why = "truncated Principled BSDF node";
+            return false;
+          }
+          const uint32_t distribution = nodes[4 * (i + 2) + 1];
+          const uint32_t subsurface_method = nodes[4 * (i + 2) + 2];
+          (void)subsurface_method;
+          if (distribution != CY_CLOSURE_BSDF_MICROFACET_GGX_GLASS_ID) {
+            why = "Principled BSDF with the Multiscatter GGX distribution is outside the "
+                  "hot-path scope (random-walk closure); set distribution to GGX";
+            return false;
+          }
+          i += 6;
+        }
+        else if (type == CY_CLOSURE_BSDF_DIFFUSE_ID || type == CY_CLOSURE_BSDF_MICROFACET_GGX_ID) {
+          i += 2;
+        }
+        else {
+          why = "SVM closure type " + std::to_string(type) + " is outside the hot-path scope";
+          return false;
+        }
+        break;
+      }
+      default:
+        why = "SVM node opcode " + std::to_string(op) + " at " + std::to_string(i) +
+              " is outside the hot-path scope (supported: closures diffuse/principled-GGX/"
+              "glossy-GGX/emission/background, mix, value, geometry)";
+        return false;
+    }
+  }
+  return true;
+}
+
+/* Features of KernelData the kernels do not implement are refused, never
+ * silently approximated. */
+static int check_scope(b200_ctx *ctx)
+{
+  auto I = [&](int off) { return kd_host<int>(ctx, off); };
+  auto F = [&](int off) { return kd_host<float>(ctx, off); };
+  std::string why;
+  if (I(KD_CAM_TYPE) != CY_CAMERA_PERSPECTIVE)
+    why = "only the perspective camera is in scope";
+  else if (F(KD_CAM_APERTURESIZE) > 0.0f)
+    why = "depth of field is outside the hot-path scope";
+  else if (F(KD_CAM_SHUTTERTIME) != -1.0f || I(KD_CAM_NUM_MOTION_STEPS) != 0 ||
+           I(KD_BVH_HAVE_MOTION))
+    why = "motion blur is outside the hot-path scope";
+  else if (I(KD_BVH_HAVE_CURVES))
+    why = "hair curves are outside the hot-path scope";
+  else if (I(KD_INT_SAMPLING_PATTERN) != CY_SAMPLING_PATTERN_SOBOL)
+    why = "only the Sobol sampling pattern is in scope";
+  else if (I(KD_INT_BRANCHED))
+    why = "branched path tracing is outside the hot-path scope";
+  else if (I(KD_INT_TRANSPARENT_SHADOWS))
+    why = "transparent shadows are outside the hot-path scope";
+  else if (I(KD_INT_USE_VOLUMES))
+    why = "volumes are outside the hot-path scope";
+  else if (I(KD_INT_USE_AMBIENT_OCCLUSION))
+    why = "ambient occlusion is outside the hot-path scope";
+  else if (F(KD_INT_PDF_TRIANGLES) != 0.0f)
+    why = "mesh lights are outside the hot-path scope (use lamps)";
+  else if (I(KD_BG_USE_MIS))
+    why = "background importance sampling is outside the hot-path scope";
+  else if (I(KD_FILM_USE_LIGHT_PASS) || I(KD_FILM_PASS_DENOISING_DATA) ||
+           I(KD_FILM_PASS_ADAPTIVE_AUX_BUFFER) || I(KD_FILM_PASS_SAMPLE_COUNT) ||
+           I(KD_FILM_CRYPTOMATTE_PASSES))
+    why = "only the combined pass is in scope";
+  else if (!(I(KD_FILM_PASS_FLAG) & (1u << CY_PASS_COMBINED)))
+    why = "the combined pass must be enabled";
+  else if (I(KD_FILM_PASS_STRIDE) % 4 != 0)
+    why = "pass_stride must be a multiple of 4";
+  else if (F(KD_BG_TRANSPARENT_ROUGHNESS_SQ_THRESHOLD) >= 0.0f)
+    why = "transparent glass is outside the hot-path scope";
+  else if (I(KD_INT_MAX_CLOSURES) > MAX_CLOSURES_GPU)
+    why = "more than 8 closures per shader";
+  const HostArray *sh = find_global(ctx, "__shaders");
+  if (why.empty() && sh && sh->bytes / SIZEOF_KERNEL_SHADER > WF_MAX_KEYS - 1)
+    why = "more than 4095 shaders";
+  if (!why.empty())
+    return fail(ctx, B200_ERR_UNSUPPORTED, why);
+  return B200_OK;
+}
+
+extern "C" {
+
+int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *cancel)
+{
+  if (!ctx || !tile || !tile->buffer)
+    return B200_ERR_INVALID;
+  if (tile->w <= 0 || tile->h <= 0 || tile->num_samples <= 0)
+    return B200_OK;
+  int rc = prepare_scene(ctx);
+  if (rc)
+    return rc;
+  DeviceGuard guard(ctx->ordinal);
+
+  const size_t capacity = ctx->opt_batch_paths > 0 ? (size_t)ctx->opt_batch_paths :
+                                                     ((size_t)1 << 22);
+  rc = ensure_pool(ctx, std::max<size_t>(capacity, (size_t)tile->w));
+  if (rc)
+    return rc;
+  PathPool *pool = ctx->pool;
+  const HostArray *sh = find_global(ctx, "__shaders");
+  const int num_keys = sh ? (int)(sh->bytes / SIZEOF_KERNEL_SHADER) : 1;
+  const int pass_stride = kd_host<int>(ctx, KD_FILM_PASS_STRIDE);
+  const int pass_combined = kd_host<int>(ctx, KD_FILM_PASS_COMBINED);
+  const bool count = ctx->opt_count_traversal != 0;
+  const int grid_wide = launch_grid(ctx, 8);
+  const int grid_trace = launch_grid(ctx, 8);
+  cudaStream_t st = ctx->stream;
+
+  b200_stats stats;
+  memset(&stats, 0, sizeof(stats));
+  float traverse_ms = 0.0f;
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev5, st));
+
+  /* bands of rows so that one sample of a band fits the pool */
+  const int band_h = (int)std::max<size_t>(1, std::min<size_t>((size_t)tile->h,
+                                                               pool->capacity / (size_t)tile->w));
+  for (int by = 0; by < tile->h; by += band_h) {
+    const int bh = std::min(band_h, tile->h - by);
+    const size_t npix = (size_t)tile->w * bh;
+    const int spb = (int)std::max<size_t>(1, pool->capacity / npix);
+    for (int s0 = 0; s0 < tile->num_samples; s0 += spb) {
+      if (cancel && *cancel)
+        return fail(ctx, B200_ERR_CANCELLED, "cancelled");
+      BatchParams bp;
+      bp.x = tile->x;
+      bp.y = tile->y + by;
+      bp.w = tile->w;
+      bp.h = bh;
+      bp.sample0 = tile->start_sample + s0;
+      bp.nsamples = std::min(spb, tile->num_samples - s0);
+      bp.offset = tile->offset;
+      bp.stride = tile->stride;
+      bp.num_keys = num_keys;
+      bp.count_stats = count;
+
+      PathSoA soa = pool->soa;
+      CUDA_TRY(ctx, cudaMemsetAsync(soa.counters, 0, sizeof(WFCounters), st));
+      k_init_from_camera<<<grid_wide, WF_BLOCK, 0, st>>>(soa, bp);
+      stats.kernel_launches += 1;
+
+      const int max_iterations = 4096;
+      for (int it = 0; it < max_iterations; it++) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+        if (count)
+          k_intersect_closest<true><<<grid_trace, 128, 0, st>>>(soa);
+        else
+          k_intersect_closest<false><<<grid_trace, 128, 0, st>>>(soa);
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+        k_sort_scan<<<1, 256, 0, st>>>(soa, num_keys);
+        k_sort_scatter<<<grid_wide, WF_BLOCK, 0, st>>>(soa);
+        k_shade_background<<<grid_wide, WF_BLOCK, 0, st>>>(soa);
+        k_shade_surface<<<grid_wide, WF_BLOCK, 0, st>>>(soa, num_keys);
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev3, st));
+        if (count)
+          k_intersect_shadow<true><<<grid_trace, 128, 0, st>>>(soa);
+        else
+          k_intersect_shadow<false><<<grid_trace, 128, 0, st>>>(soa);
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev4, st));
+        k_iteration_end<<<8, 256, 0, st>>>(soa, num_keys);
+        stats.kernel_launches += 7;
+        /* one counter back per bounce (the reference copies the whole ray_state
+         * array every 16 iterations, device_split_kernel.cpp:302-318) */
+        CUDA_TRY(ctx, cudaMemcpyAsync(pool->h_counters, soa.counters, 64,
+                                      cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        CUDA_TRY(ctx, cudaGetLastError());
+        {
+          float a = 0.0f, b = 0.0f;
+          cudaEventElapsedTime(&a, ctx->ev0, ctx->ev1);
+          cudaEventElapsedTime(&b, ctx->ev3, ctx->ev4);
+          traverse_ms += a + b;
+        }
+        std::swap(soa.q_active, soa.q_next);
+        if (pool->h_counters->n_active == 0)
+          break;
+      }
+      k_film_accumulate<<<grid_wide, WF_BLOCK, 0, st>>>(soa, bp, (float *)tile->buffer,
+                                                        pass_stride, pass_combined);
+      stats.kernel_launches += 1;
+      CUDA_TRY(ctx, cudaMemcpyAsync(pool->h_counters, soa.counters, 128, cudaMemcpyDeviceToHost,
+                                    st));
+      CUDA_TRY(ctx, cudaStreamSynchronize(st));
+      CUDA_TRY(ctx, cudaGetLastError());
+      stats.primary_rays += pool->h_counters->primary_rays;
+      stats.bounce_rays += pool->h_counters->bounce_rays;
+      stats.shadow_rays += pool->h_counters->shadow_rays;
+      stats.nodes_visited += pool->h_counters->nodes;
+      stats.tris_tested += pool->h_counters->tris;
+      stats.instances_entered += pool->h_counters->instances;
+    }
+  }
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev6, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  {
+    float total = 0.0f;
+    cudaEventElapsedTime(&total, ctx->ev5, ctx->ev6);
+    stats.device_ms = total;
+    stats.traverse_ms = traverse_ms;
+  }
+  ctx->stats = stats;
+  return B200_OK;
+}
+
+int b200_film_convert(b200_ctx *ctx, uint64_t film, uint64_t rgba, int half_float,
+                      float sample_scale, int x, int y, int w, int h, int offset, int stride)
+{
+  if (!ctx || !film || !rgba)
+    return B200_ERR_INVALID;
+  if (!ctx->have_data)
+    return fail(ctx, B200_ERR_NOT_READY, "KernelData not uploaded");
+  DeviceGuard guard(ctx->ordinal);
+  dim3 block(16, 16), grid((w + 15) / 16, (h + 15) / 16);
+  k_film_convert<<<grid, block, 0, ctx->stream>>>(
+      (const float *)film, (void *)rgba, half_float, sample_scale, x, y, w, h, offset, stride,
+      kd_host<int>(ctx, KD_FILM_PASS_STRIDE), kd_host<float>(ctx, KD_FILM_EXPOSURE));
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+int b200_film_reduce(b200_ctx **ctxs, int n, const uint64_t *films, size_t n_floats)
+{
+  if (!ctxs || n <= 0 || !films)
+    return B200_ERR_INVALID;
+  if (n == 1)
+    return B200_OK;
+  if (n_floats % 4)
+    return fail(ctxs[0], B200_ERR_INVALID, "film size must be a multiple of 4 floats");
+  b200_ctx *root = ctxs[0];
+  DeviceGuard guard(root->ordinal);
+  void *tmp = nullptr;
+  CUDA_TRY(root, cudaMalloc(&tmp, n_floats * sizeof(float)));
+  for (int i = 1; i < n; i++) {
+    /* peer copy over NVLink, then one vectorised add on the root */
+    cudaError_t e = cudaMemcpyPeerAsync(tmp, root->ordinal, (const void *)films[i],
+                                        ctxs[i]->ordinal, n_floats * sizeof(float), root->stream);
+    if (e != cudaSuccess) {
+      cudaFree(tmp);
+      return fail(root, B200_ERR_CUDA, std::string("peer copy: ") + cudaGetErrorString(e));
+    }
+    k_film_add<<<launch_grid(root, 4), 256, 0, root->stream>>>((float4 *)films[0],
+                                                               (const float4 *)tmp, n_floats / 4);
+  }
+  cudaError_t e = cudaStreamSynchronize(root->stream);
+  cudaFree(tmp);
+  if (e != cudaSuccess)
+    return fail(root, B200_ERR_CUDA, std::string("film reduce: ") + cudaGetErrorString(e));
+  return B200_OK;
+}
+
+} /* extern "C" */
+
+#endif /* B200_WAVEFRONT_CUH */
