@@ -67,12 +67,16 @@ typedef struct b200_stats {
   uint64_t primary_rays;  /* scene_intersect calls for camera rays */
   uint64_t bounce_rays;   /* scene_intersect calls for bounce rays */
   uint64_t shadow_rays;   /* shadow_blocked traversals */
-  uint64_t nodes_visited; /* BVH8 nodes fetched (counter build only, else 0) */
-  uint64_t tris_tested;   /* triangles tested   (counter build only, else 0) */
-  uint64_t instances_entered;
-  uint64_t kernel_launches; /* our kernels launched inside the call */
-  double device_ms;         /* CUDA-event time of the call's device work */
-  double traverse_ms;       /* CUDA-event time spent in the traversal kernels */
+  /* BVH work, counted only when option "count_traversal" is on (else 0): the
+   * equivalent of the reference's __KERNEL_DEBUG__ passes (bvh_types.h:46-70) */
+  uint64_t closest_nodes, closest_tris, closest_instances; /* intersect_closest */
+  uint64_t shadow_nodes, shadow_tris, shadow_instances;    /* intersect_shadow */
+  uint64_t kernel_launches;  /* our kernels launched inside the call */
+  uint64_t closest_launches; /* intersect_closest launches among them */
+  uint64_t shadow_launches;  /* intersect_shadow launches among them */
+  double device_ms;          /* CUDA-event time of the call's device work */
+  double closest_ms;         /* CUDA-event time inside intersect_closest launches */
+  double shadow_ms;          /* CUDA-event time inside intersect_shadow launches */
 } b200_stats;
 
 /* BVH8 build report (host builder). */
@@ -156,7 +160,13 @@ int b200_film_reduce(b200_ctx **ctxs, int n, const uint64_t *films, size_t n_flo
 int b200_get_stats(b200_ctx *ctx, b200_stats *out);
 int b200_synchronize(b200_ctx *ctx);
 
-/* Tunables (0 keeps the default): paths per wavefront batch. */
+/* Run all work of this context on an existing CUDA stream (cudaStream_t handle,
+ * e.g. torch.cuda.Stream.cuda_stream) so callers can bracket it with their own
+ * events; 0 restores the context's private stream. */
+int b200_set_stream(b200_ctx *ctx, uint64_t cuda_stream);
+
+/* Tunables (0 keeps the default): "batch_paths" paths per wavefront batch,
+ * "count_traversal" 1 = count BVH nodes / triangles per ray (slower). */
 int b200_set_option(b200_ctx *ctx, const char *name, int64_t value);
 
 #ifdef __cplusplus

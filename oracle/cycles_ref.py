@@ -67,6 +67,8 @@ def lib():
         L.ref_shadow_rays.argtypes = [
             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.ref_init.argtypes = [C.c_int]
+        L.ref_count_rays.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ref_num_threads.restype = C.c_int
         _lib = L
     return _lib
 
@@ -187,6 +189,16 @@ class RefScene:
             self._h, int(start_sample), int(num_samples), int(tile_size), int(accumulate),
             out.ctypes.data, C.byref(sec)))
         return out, sec.value
+
+    def count_rays(self, start_sample, num_samples):
+        """(camera, bounce, shadow) rays the reference traces for these samples."""
+        counts = np.zeros(3, dtype=np.uint64)
+        self._check(self._L.ref_count_rays(self._h, int(start_sample), int(num_samples),
+                                           counts.ctypes.data))
+        return tuple(int(c) for c in counts)
+
+    def num_threads(self):
+        return int(self._L.ref_num_threads())
 
     def intersect(self, rays):
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)

@@ -30,6 +30,8 @@
 #include "util/util_time.h"
 
 #include <atomic>
+#include <thread>
+#include <vector>
 #include <execinfo.h>
 #include <signal.h>
 #include <xmmintrin.h>
@@ -431,6 +433,44 @@ int ref_camera_rays(
   KernelGlobals kg = rs->cpu->kg_init();
   ref_probe_camera_rays(&kg, sample, x0, y0, w, h, rays, rng_hash);
   rs->cpu->kg_free(&kg);
+  return 0;
+}
+
+/* Census of the rays the reference traces for samples [start, start+num) of the
+ * full frame: counts[0] camera, counts[1] bounce, counts[2] shadow.  Row bands
+ * on std::threads (the census is per pixel, order-free). */
+int ref_count_rays(ref_scene *rs, int start_sample, int num_samples, unsigned long long *counts)
+{
+  if (!rs->cpu)
+    return 1;
+  const int width = rs->scene->camera->width, height = rs->scene->camera->height;
+  const int nthreads = std::max(1, TaskScheduler::num_threads());
+  std::vector<std::thread> threads;
+  std::vector<unsigned long long> partial(3 * (size_t)nthreads, 0ull);
+  std::atomic<int> next_row(0);
+  for (int t = 0; t < nthreads; t++) {
+    threads.emplace_back([&, t]() {
+      KernelGlobals kg = rs->cpu->kg_init();
+      const unsigned int mxcsr = _mm_getcsr();
+      _mm_setcsr(mxcsr | 0x8040); /* FTZ + DAZ as CPUDevice::render */
+      for (;;) {
+        int y = next_row.fetch_add(4);
+        if (y >= height)
+          break;
+        int rows = std::min(4, height - y);
+        for (int s = start_sample; s < start_sample + num_samples; s++)
+          ref_probe_count_rays(&kg, s, 0, y, width, rows, &partial[3 * (size_t)t]);
+      }
+      _mm_setcsr(mxcsr);
+      rs->cpu->kg_free(&kg);
+    });
+  }
+  for (auto &th : threads)
+    th.join();
+  counts[0] = counts[1] = counts[2] = 0;
+  for (int t = 0; t < nthreads; t++)
+    for (int k = 0; k < 3; k++)
+      counts[k] += partial[3 * (size_t)t + k];
   return 0;
 }
 

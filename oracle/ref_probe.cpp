@@ -174,6 +174,82 @@ void ref_probe_shadow_rays(
   }
 }
 
+/* Ray census of the reference path loop: follows kernel_path_integrate
+ * (kernel_path.h:509-641, surface-only branches) with the reference's own inline
+ * functions and counts scene_intersect calls for camera rays, bounce rays and
+ * shadow rays (light rays with t != 0, kernel_shadow.h:398-400).  Used to turn a
+ * timed CPU render into Mrays/s without a __KERNEL_DEBUG__ rebuild. */
+void ref_probe_count_rays(KernelGlobals *kg, int sample, int x0, int y0, int w, int h,
+                          unsigned long long counts[3])
+{
+  for (int y = 0; y < h; y++) {
+    for (int x = 0; x < w; x++) {
+      Ray ray;
+      uint rng_hash;
+      kernel_path_trace_setup(kg, sample, x0 + x, y0 + y, &rng_hash, &ray);
+      if (ray.t == 0.0f)
+        continue;
+      float3 throughput = make_float3(1.0f, 1.0f, 1.0f);
+      PathRadiance L;
+      path_radiance_init(kg, &L);
+      ShaderDataTinyStorage emission_sd_storage;
+      ShaderData *emission_sd = AS_SHADER_DATA(&emission_sd_storage);
+      PathState state;
+      path_state_init(kg, emission_sd, &state, rng_hash, sample, &ray);
+      ShaderData sd;
+      for (;;) {
+        Intersection isect;
+        counts[(state.flag & PATH_RAY_CAMERA) ? 0 : 1]++;
+        bool hit = kernel_path_scene_intersect(kg, &state, &ray, &isect, &L);
+        kernel_path_lamp_emission(kg, &state, &ray, throughput, &isect, &sd, &L);
+        if (!hit) {
+          kernel_path_background(kg, &state, &ray, throughput, &sd, NULL, &L);
+          break;
+        }
+        else if (path_state_ao_bounce(kg, &state)) {
+          break;
+        }
+        shader_setup_from_ray(kg, &sd, &isect, &ray);
+        shader_eval_surface(kg, &sd, &state, NULL, state.flag);
+        shader_prepare_closures(&sd, &state);
+        if (!kernel_path_shader_apply(kg, &sd, &state, &ray, throughput, emission_sd, &L, NULL))
+          break;
+        float probability = path_state_continuation_probability(kg, &state, throughput);
+        if (probability == 0.0f) {
+          break;
+        }
+        else if (probability != 1.0f) {
+          float terminate = path_state_rng_1D(kg, &state, PRNG_TERMINATE);
+          if (terminate >= probability)
+            break;
+          throughput /= probability;
+        }
+        /* kernel_branched_path_surface_connect_light with one light (kernel_path_surface.h:22-125) */
+        if (kernel_data.integrator.use_direct_light && (sd.flag & SD_BSDF_HAS_EVAL)) {
+          float light_u, light_v;
+          path_state_rng_2D(kg, &state, PRNG_LIGHT_U, &light_u, &light_v);
+          float terminate = path_state_rng_light_termination(kg, &state);
+          Ray light_ray;
+          light_ray.t = 0.0f;
+          light_ray.time = sd.time;
+          BsdfEval L_light;
+          bool is_lamp = false;
+          LightSample ls;
+          if (light_sample(kg, -1, light_u, light_v, sd.time, sd.P, state.bounce, &ls)) {
+            if (direct_emission(
+                    kg, &sd, emission_sd, &ls, &state, &light_ray, &L_light, &is_lamp, terminate)) {
+              if (light_ray.t != 0.0f)
+                counts[2]++;
+            }
+          }
+        }
+        if (!kernel_path_surface_bounce(kg, &sd, &throughput, &state, &L.state, &ray))
+          break;
+      }
+    }
+  }
+}
+
 void ref_probe_path_trace(
     KernelGlobals *kg, float *buffer, int sample, int x, int y, int offset, int stride)
 {

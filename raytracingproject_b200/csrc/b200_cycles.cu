@@ -200,7 +200,8 @@ b200_ctx *b200_create(int cuda_ordinal, char *err, size_t errlen)
   ctx->ordinal = cuda_ordinal;
   ctx->num_sms = prop.multiProcessorCount;
   DeviceGuard guard(cuda_ordinal);
-  bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+  bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ctx->stream = ctx->own_stream;
   ok = ok && cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess;
   ok = ok && cudaEventCreate(&ctx->ev2) == cudaSuccess && cudaEventCreate(&ctx->ev3) == cudaSuccess;
   ok = ok && cudaEventCreate(&ctx->ev4) == cudaSuccess && cudaEventCreate(&ctx->ev5) == cudaSuccess;
@@ -242,7 +243,7 @@ void b200_destroy(b200_ctx *ctx)
   cudaEventDestroy(ctx->ev4);
   cudaEventDestroy(ctx->ev5);
   cudaEventDestroy(ctx->ev6);
-  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
 
@@ -609,16 +610,28 @@ int b200_trace_batch(b200_ctx *ctx, uint64_t rays, uint64_t hits, uint64_t n, in
   float ms = 0.0f;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   memset(&ctx->stats, 0, sizeof(ctx->stats));
-  if (any_hit)
+  uint64_t cn = 0, ct = 0, ci = 0;
+  memcpy(&cn, &ctx->h_counters[16], 8);
+  memcpy(&ct, &ctx->h_counters[18], 8);
+  memcpy(&ci, &ctx->h_counters[20], 8);
+  if (any_hit) {
     ctx->stats.shadow_rays = n;
-  else
+    ctx->stats.shadow_nodes = cn;
+    ctx->stats.shadow_tris = ct;
+    ctx->stats.shadow_instances = ci;
+    ctx->stats.shadow_launches = 1;
+    ctx->stats.shadow_ms = ms;
+  }
+  else {
     ctx->stats.primary_rays = n;
-  memcpy(&ctx->stats.nodes_visited, &ctx->h_counters[16], 8);
-  memcpy(&ctx->stats.tris_tested, &ctx->h_counters[18], 8);
-  memcpy(&ctx->stats.instances_entered, &ctx->h_counters[20], 8);
+    ctx->stats.closest_nodes = cn;
+    ctx->stats.closest_tris = ct;
+    ctx->stats.closest_instances = ci;
+    ctx->stats.closest_launches = 1;
+    ctx->stats.closest_ms = ms;
+  }
   ctx->stats.kernel_launches = 1;
   ctx->stats.device_ms = ms;
-  ctx->stats.traverse_ms = ms;
   return B200_OK;
 }
 
@@ -627,6 +640,16 @@ int b200_get_stats(b200_ctx *ctx, b200_stats *out)
   if (!ctx || !out)
     return B200_ERR_INVALID;
   *out = ctx->stats;
+  return B200_OK;
+}
+
+int b200_set_stream(b200_ctx *ctx, uint64_t cuda_stream)
+{
+  if (!ctx)
+    return B200_ERR_INVALID;
+  DeviceGuard guard(ctx->ordinal);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
   return B200_OK;
 }
 

@@ -25,7 +25,8 @@ struct PathPool; /* wavefront state, defined in b200_cycles.cu */
 struct b200_ctx {
   int ordinal = 0;
   int num_sms = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;     /* stream all work is issued on */
+  cudaStream_t own_stream = nullptr; /* the private stream created with the context */
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   cudaEvent_t ev4 = nullptr, ev5 = nullptr, ev6 = nullptr;
   std::string error;

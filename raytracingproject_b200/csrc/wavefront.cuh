@@ -36,7 +36,8 @@ struct WFCounters {
   unsigned int work_closest, work_shadow;
   unsigned int pad[3];
   unsigned long long primary_rays, bounce_rays, shadow_rays;
-  unsigned long long nodes, tris, instances;
+  unsigned long long nodes, tris, instances;          /* intersect_closest */
+  unsigned long long sh_nodes, sh_tris, sh_instances; /* intersect_shadow */
   unsigned int hist[WF_MAX_KEYS + 1];
   unsigned int offsets[WF_MAX_KEYS + 2];
   unsigned int cursor[WF_MAX_KEYS + 1];
@@ -703,9 +704,9 @@ __global__ void __launch_bounds__(128) k_intersect_shadow(PathSoA p)
       cnt.instances += __shfl_xor_sync(0xffffffffu, cnt.instances, o);
     }
     if (lane == 0) {
-      atomicAdd(&p.counters->nodes, (unsigned long long)cnt.nodes);
-      atomicAdd(&p.counters->tris, (unsigned long long)cnt.tris);
-      atomicAdd(&p.counters->instances, (unsigned long long)cnt.instances);
+      atomicAdd(&p.counters->sh_nodes, (unsigned long long)cnt.nodes);
+      atomicAdd(&p.counters->sh_tris, (unsigned long long)cnt.tris);
+      atomicAdd(&p.counters->sh_instances, (unsigned long long)cnt.instances);
     }
   }
 }
@@ -1027,7 +1028,7 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
 
   b200_stats stats;
   memset(&stats, 0, sizeof(stats));
-  float traverse_ms = 0.0f;
+  float closest_ms = 0.0f, shadow_ms = 0.0f;
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev5, st));
 
   /* bands of rows so that one sample of a band fits the pool */
@@ -1077,6 +1078,8 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev4, st));
         k_iteration_end<<<8, 256, 0, st>>>(soa, num_keys);
         stats.kernel_launches += 7;
+        stats.closest_launches += 1;
+        stats.shadow_launches += 1;
         /* one counter back per bounce (the reference copies the whole ray_state
          * array every 16 iterations, device_split_kernel.cpp:302-318) */
         CUDA_TRY(ctx, cudaMemcpyAsync(pool->h_counters, soa.counters, 64,
@@ -1087,7 +1090,8 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
           float a = 0.0f, b = 0.0f;
           cudaEventElapsedTime(&a, ctx->ev0, ctx->ev1);
           cudaEventElapsedTime(&b, ctx->ev3, ctx->ev4);
-          traverse_ms += a + b;
+          closest_ms += a;
+          shadow_ms += b;
         }
         std::swap(soa.q_active, soa.q_next);
         if (pool->h_counters->n_active == 0)
@@ -1096,16 +1100,19 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
       k_film_accumulate<<<grid_wide, WF_BLOCK, 0, st>>>(soa, bp, (float *)tile->buffer,
                                                         pass_stride, pass_combined);
       stats.kernel_launches += 1;
-      CUDA_TRY(ctx, cudaMemcpyAsync(pool->h_counters, soa.counters, 128, cudaMemcpyDeviceToHost,
+      CUDA_TRY(ctx, cudaMemcpyAsync(pool->h_counters, soa.counters, 256, cudaMemcpyDeviceToHost,
                                     st));
       CUDA_TRY(ctx, cudaStreamSynchronize(st));
       CUDA_TRY(ctx, cudaGetLastError());
       stats.primary_rays += pool->h_counters->primary_rays;
       stats.bounce_rays += pool->h_counters->bounce_rays;
       stats.shadow_rays += pool->h_counters->shadow_rays;
-      stats.nodes_visited += pool->h_counters->nodes;
-      stats.tris_tested += pool->h_counters->tris;
-      stats.instances_entered += pool->h_counters->instances;
+      stats.closest_nodes += pool->h_counters->nodes;
+      stats.closest_tris += pool->h_counters->tris;
+      stats.closest_instances += pool->h_counters->instances;
+      stats.shadow_nodes += pool->h_counters->sh_nodes;
+      stats.shadow_tris += pool->h_counters->sh_tris;
+      stats.shadow_instances += pool->h_counters->sh_instances;
     }
   }
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev6, st));
@@ -1114,7 +1121,8 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
     float total = 0.0f;
     cudaEventElapsedTime(&total, ctx->ev5, ctx->ev6);
     stats.device_ms = total;
-    stats.traverse_ms = traverse_ms;
+    stats.closest_ms = closest_ms;
+    stats.shadow_ms = shadow_ms;
   }
   ctx->stats = stats;
   return B200_OK;

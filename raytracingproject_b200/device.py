@@ -34,7 +34,7 @@ EXPORTS = [
     "b200_last_error", "b200_alloc", "b200_free", "b200_h2d", "b200_d2h", "b200_zero",
     "b200_mem_used", "b200_bind_global", "b200_set_kernel_data", "b200_build_bvh", "b200_render",
     "b200_trace_batch", "b200_film_convert", "b200_film_reduce", "b200_get_stats",
-    "b200_synchronize", "b200_set_option",
+    "b200_synchronize", "b200_set_option", "b200_set_stream",
 ]
 
 
@@ -46,10 +46,14 @@ class WorkTile(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("primary_rays", C.c_uint64), ("bounce_rays", C.c_uint64),
-                ("shadow_rays", C.c_uint64), ("nodes_visited", C.c_uint64),
-                ("tris_tested", C.c_uint64), ("instances_entered", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("device_ms", C.c_double),
-                ("traverse_ms", C.c_double)]
+                ("shadow_rays", C.c_uint64),
+                ("closest_nodes", C.c_uint64), ("closest_tris", C.c_uint64),
+                ("closest_instances", C.c_uint64),
+                ("shadow_nodes", C.c_uint64), ("shadow_tris", C.c_uint64),
+                ("shadow_instances", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("closest_launches", C.c_uint64),
+                ("shadow_launches", C.c_uint64),
+                ("device_ms", C.c_double), ("closest_ms", C.c_double), ("shadow_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -104,6 +108,7 @@ def load_library():
     L.b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.b200_synchronize.argtypes = [vp]
     L.b200_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.b200_set_stream.argtypes = [vp, u64]
     _lib = L
     return L
 
@@ -245,6 +250,10 @@ class B200Device:
 
     def set_option(self, name, value):
         self._check(self._L.b200_set_option(self._ctx, name.encode(), int(value)), "set_option")
+
+    def set_stream(self, cuda_stream):
+        """Issue all work on an existing CUDA stream (0 = the private stream)."""
+        self._check(self._L.b200_set_stream(self._ctx, int(cuda_stream)), "set_stream")
 
     def synchronize(self):
         self._check(self._L.b200_synchronize(self._ctx), "synchronize")
