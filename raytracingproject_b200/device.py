@@ -307,3 +307,50 @@ class B200Device:
             if own:
                 self.mem_free(film)
         return film.host
+
+
+SHIM_PATH = os.path.join(_HERE, "libcycles_device_b200.so")
+
+
+class B200HostDevice:
+    """The C++ `B200Device : ccl::Device` (csrc/device_b200.cpp) as a handle whose
+    `.ptr` is a ccl::Device* that a reference Scene / DeviceTask can drive - the real
+    drop-in path.  Needs libcycles_device_b200.so (built where the reference headers
+    are available) and the host application library it links to."""
+
+    def __init__(self, ordinal=0):
+        load_library()
+        if not os.path.exists(SHIM_PATH):
+            raise DeviceError("%s is missing (make -C raytracingproject_b200/csrc -f "
+                              "Makefile.device, needs /root/reference)" % SHIM_PATH)
+        S = C.CDLL(SHIM_PATH, mode=C.RTLD_GLOBAL)
+        S.b200_host_device_create.restype = C.c_void_p
+        S.b200_host_device_create.argtypes = [C.c_int, C.c_char_p, C.c_size_t]
+        S.b200_host_device_ptr.restype = C.c_void_p
+        S.b200_host_device_ptr.argtypes = [C.c_void_p]
+        S.b200_host_device_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        S.b200_host_device_error.restype = C.c_char_p
+        S.b200_host_device_error.argtypes = [C.c_void_p]
+        S.b200_host_device_destroy.argtypes = [C.c_void_p]
+        self._S = S
+        err = C.create_string_buffer(512)
+        self._h = S.b200_host_device_create(int(ordinal), err, len(err))
+        if not self._h:
+            raise DeviceError("B200Device: " + err.value.decode())
+
+    @property
+    def ptr(self):
+        return self._S.b200_host_device_ptr(self._h)
+
+    def stats(self):
+        s = Stats()
+        self._S.b200_host_device_stats(self._h, C.byref(s))
+        return s.as_dict()
+
+    def error_message(self):
+        return self._S.b200_host_device_error(self._h).decode()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._S.b200_host_device_destroy(self._h)
+            self._h = None
