@@ -210,6 +210,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from oracle import cycles_ref  # scene front-end (reference host code) + cpu_baseline leg
+    from raytracingproject_b200 import multigpu
     from raytracingproject_b200.device import B200Device, DeviceMemory
 
     rank, world, local = dist_env()
@@ -241,13 +242,12 @@ def run_b200(args):
     t_upload = time.perf_counter() - t0
 
     film = torch.zeros(h * w * ps, dtype=torch.float32, device="cuda")
-    start_sample = rank * spp
+    start_sample, _ = multigpu.weak_range(rank, spp)
 
     def step():
         film.zero_()
         dev.render_tile(film.data_ptr(), 0, 0, w, h, start_sample, spp, 0, w)
-        if world > 1:
-            dist.all_reduce(film)
+        multigpu.reduce_film(film)  # NCCL all-reduce over NVLink when world > 1
         return dev.stats()
 
     for _ in range(max(args.warmup, 0)):
@@ -365,6 +365,30 @@ def run_b200(args):
                    "ms_per_step": 1e3 * e_sec / e2e_steps,
                    "api": "B200Device.mem_copy_to / render_tile (DeviceTask::RENDER) / "
                           "mem_copy_from over the C ABI"}
+            # the same step through the C++ `B200Device : ccl::Device`, driven by the
+            # reference's own Scene::device_update + DeviceTask::RENDER + RenderBuffers
+            # readback (mem_zero on the device, D2H of the film)
+            try:
+                from raytracingproject_b200.device import B200HostDevice
+                host = B200HostDevice(local)
+                rs_gpu = cycles_ref.build_scene(desc, external_device=host.ptr)
+                rs_gpu.render(0, spp, tile_size=0)
+                t0 = time.perf_counter()
+                p_rays = 0
+                for _ in range(e2e_steps):
+                    rs_gpu.render(0, spp, tile_size=0)
+                    s = host.stats()
+                    p_rays += s["primary_rays"] + s["bounce_rays"] + s["shadow_rays"]
+                p_sec = time.perf_counter() - t0
+                e2e["reference_flow"] = {
+                    "value": p_rays / p_sec / 1e6, "unit": "Mrays/s",
+                    "ms_per_step": 1e3 * p_sec / e2e_steps, "h2d_bytes_per_step": 64,
+                    "d2h_bytes_per_step": int(host_film.numel() * 4),
+                    "api": "reference Scene + DeviceTask::RENDER -> C++ B200Device -> C ABI"}
+                rs_gpu.close()
+                host.close()
+            except Exception as exc:  # the shim needs the reference headers to be built
+                e2e["reference_flow"] = {"unavailable": str(exc)[:200]}
         elif world > 1:
             e2e = {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0,
                    "d2h_bytes_per_step": 0, "note": "measured at N=1 only"}
