@@ -50,6 +50,8 @@ def parse_args():
                     help="samples of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--opt", action="append", default=[],
+                    help="device tunable name=value (b200_set_option), repeatable")
     return ap.parse_args()
 
 
@@ -236,6 +238,9 @@ def run_b200(args):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     dev.set_stream(stream.cuda_stream)
+    for o in args.opt:
+        k, v = o.split("=")
+        dev.set_option(k, int(v))
     t0 = time.perf_counter()
     dev.upload_scene(arrays)
     bvh = dev.build_bvh()

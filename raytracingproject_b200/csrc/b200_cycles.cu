@@ -75,47 +75,47 @@ enum {
 
 /* ------------------------------------------------------------ trace batch */
 
-/* Persistent warps: each warp claims 32 rays at a time from a global cursor
- * (one atomic per warp), so the grid is sized to the machine (a multiple of the
- * SM count), not to the batch. */
+/* Job of the batch hook: 32-byte ray records in (two 16-byte halves), 24-byte hit
+ * records out. */
+struct BatchJob {
+  const b200_ray *rays;
+  b200_hit *hits;
+  __device__ __forceinline__ const float4 *ray_P(unsigned int qi) const
+  {
+    return (const float4 *)(rays + qi);
+  }
+  __device__ __forceinline__ const float4 *ray_D(unsigned int qi) const
+  {
+    return (const float4 *)(rays + qi) + 1;
+  }
+  __device__ __forceinline__ void store(unsigned int qi, const TraceHit &h, bool found)
+  {
+    b200_hit out;
+    out.t = h.t;
+    out.u = h.u;
+    out.v = h.v;
+    out.prim = h.prim;
+    out.object = h.object;
+    out.type = found ? (int)CY_PRIMITIVE_TRIANGLE : 0;
+    hits[qi] = out;
+  }
+};
+
+/* Persistent warps with dynamic lane refill (trace_persistent, traverse.cuh): the
+ * grid is sized to the machine (a multiple of the SM count), not to the batch. */
 template<bool ANY_HIT, bool COUNT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(TRACE_BLOCK)
     k_trace_batch(const b200_ray *__restrict__ rays, b200_hit *__restrict__ hits, uint64_t n,
-                  unsigned int *counters)
+                  unsigned int *counters, int refill_threshold)
 {
   const unsigned lane = threadIdx.x & 31u;
   TraceCounters cnt;
   cnt.nodes = cnt.tris = cnt.instances = 0;
-  while (true) {
-    unsigned int base = 0;
-    if (lane == 0)
-      base = atomicAdd(&counters[CNT_WORK], 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= n)
-      break;
-    const uint64_t i = (uint64_t)base + lane;
-    if (i < n) {
-      /* 32-byte ray record = two 128-bit loads */
-      const float4 r0 = __ldg((const float4 *)(rays + i) + 0);
-      const float4 r1 = __ldg((const float4 *)(rays + i) + 1);
-      TraceHit h;
-      h.t = r0.w;
-      h.u = h.v = 0.0f;
-      h.prim = -1;
-      h.object = -1;
-      if (r0.w != 0.0f) {
-        bvh8_intersect<ANY_HIT, COUNT>(mk3(r0), mk3(r1), r0.w, __float_as_uint(r1.w), h, cnt);
-      }
-      b200_hit out;
-      out.t = h.t;
-      out.u = h.u;
-      out.v = h.v;
-      out.prim = h.prim;
-      out.object = h.object;
-      out.type = (h.prim >= 0) ? (int)CY_PRIMITIVE_TRIANGLE : 0;
-      hits[i] = out;
-    }
-  }
+  BatchJob job;
+  job.rays = rays;
+  job.hits = hits;
+  trace_persistent<ANY_HIT, COUNT>(job, (unsigned int)n, &counters[CNT_WORK], refill_threshold,
+                                   cnt);
   if (COUNT) {
     for (int o = 16; o > 0; o >>= 1) {
       cnt.nodes += __shfl_xor_sync(0xffffffffu, cnt.nodes, o);
@@ -557,6 +557,12 @@ static int launch_grid(const b200_ctx *ctx, int blocks_per_sm)
   return ctx->num_sms * blocks_per_sm;
 }
 
+/* lanes still busy below which a warp goes back to its queue for more rays */
+static int refill_threshold(const b200_ctx *ctx)
+{
+  return ctx->opt_refill_threshold > 0 ? (int)ctx->opt_refill_threshold : 24;
+}
+
 #include "wavefront.cuh"
 
 extern "C" {
@@ -585,22 +591,23 @@ int b200_trace_batch(b200_ctx *ctx, uint64_t rays, uint64_t hits, uint64_t n, in
     return rc;
   DeviceGuard guard(ctx->ordinal);
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters, 0, CNT_NUM * sizeof(unsigned int), ctx->stream));
-  const int grid = launch_grid(ctx, 8);
+  const int grid = launch_grid(ctx, ctx->opt_trace_blocks_per_sm > 0 ? (int)ctx->opt_trace_blocks_per_sm : 8);
   const bool count = ctx->opt_count_traversal != 0;
+  const int refill = refill_threshold(ctx);
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
   const b200_ray *r = (const b200_ray *)rays;
   b200_hit *h = (b200_hit *)hits;
   if (any_hit) {
     if (count)
-      k_trace_batch<true, true><<<grid, 128, 0, ctx->stream>>>(r, h, n, ctx->d_counters);
+      k_trace_batch<true, true><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(r, h, n, ctx->d_counters, refill);
     else
-      k_trace_batch<true, false><<<grid, 128, 0, ctx->stream>>>(r, h, n, ctx->d_counters);
+      k_trace_batch<true, false><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(r, h, n, ctx->d_counters, refill);
   }
   else {
     if (count)
-      k_trace_batch<false, true><<<grid, 128, 0, ctx->stream>>>(r, h, n, ctx->d_counters);
+      k_trace_batch<false, true><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(r, h, n, ctx->d_counters, refill);
     else
-      k_trace_batch<false, false><<<grid, 128, 0, ctx->stream>>>(r, h, n, ctx->d_counters);
+      k_trace_batch<false, false><<<grid, TRACE_BLOCK, 0, ctx->stream>>>(r, h, n, ctx->d_counters, refill);
   }
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
@@ -663,6 +670,10 @@ int b200_set_option(b200_ctx *ctx, const char *name, int64_t value)
   }
   else if (strcmp(name, "count_traversal") == 0)
     ctx->opt_count_traversal = value;
+  else if (strcmp(name, "refill_threshold") == 0)
+    ctx->opt_refill_threshold = value;
+  else if (strcmp(name, "trace_blocks_per_sm") == 0)
+    ctx->opt_trace_blocks_per_sm = value;
   else
     return fail(ctx, B200_ERR_INVALID, std::string("unknown option ") + name);
   return B200_OK;

@@ -48,6 +48,8 @@ struct b200_ctx {
   PathPool *pool = nullptr;
   int64_t opt_batch_paths = 0;
   int64_t opt_count_traversal = 0;
+  int64_t opt_refill_threshold = 0;
+  int64_t opt_trace_blocks_per_sm = 0;
 
   /* trace_batch work counter + stats */
   unsigned int *d_counters = nullptr; /* small block of device counters */

@@ -182,42 +182,65 @@ CY_DEV uint32_t bvh8_node_intersect(const RaySpace &rs,
   return hitmask;
 }
 
-/* Closest hit (ANY_HIT = false) or occlusion (ANY_HIT = true) for one ray.
- * P, D, tmax are Ray::P, Ray::D, Ray::t; visibility is the PATH_RAY_* mask.
- * Returns true on a hit; for closest hits `hit` is the Intersection. */
-template<bool ANY_HIT, bool COUNT>
-__device__ __forceinline__ bool bvh8_intersect(
-    f3 P, f3 D, float tmax, uint32_t visibility, TraceHit &hit, TraceCounters &cnt)
-{
-  uint2 stack[BVH8_STACK_SIZE];
-  int sp = 0;
-
+/* Resumable traversal of one ray: start() arms it, step() does one unit of work
+ * (one BVH8 node, then the leaf records that node - or a popped leaf group -
+ * exposed) and returns true when the ray is finished.  Kernels keep one of these
+ * per lane and refill finished lanes from their queue (persistent threads with
+ * dynamic fetch), instead of parking a lane until the slowest ray of its warp ends.
+ *
+ * ANY_HIT = false: closest hit, `hit` is the Intersection.  ANY_HIT = true:
+ * occlusion (shadow early-out), only hit.prim >= 0 is meaningful. */
+template<bool ANY_HIT, bool COUNT> struct Traversal {
+  /* the (node group, leaf group) stack is a separate local array handed to step():
+   * keeping it out of the struct lets every scalar member live in a register */
+  int sp;
   RaySpace rs;
-  ray_space_setup(rs, P, D);
+  f3 P, D; /* the world-space ray, kept for the instance pop */
+  float tmax;
+  uint32_t visibility;
+  TraceHit hit;
+  int cur_object;   /* OBJECT_NONE (-1) while in world space */
+  float world_tmax; /* world-space limit saved while inside an instance */
+  float inst_len;
+  bool inst_hit;
+  uint2 G; /* node group: (child base, hits << 24 | imask) */
 
-  hit.t = tmax;
-  hit.u = 0.0f;
-  hit.v = 0.0f;
-  hit.prim = -1;
-  hit.object = -1;
+  __device__ __forceinline__ void start(f3 P_, f3 D_, float tmax_, uint32_t visibility_)
+  {
+    sp = 0;
+    P = P_;
+    D = D_;
+    tmax = tmax_;
+    visibility = visibility_;
+    ray_space_setup(rs, P, D);
+    hit.t = tmax;
+    hit.u = 0.0f;
+    hit.v = 0.0f;
+    hit.prim = -1;
+    hit.object = -1;
+    cur_object = -1;
+    world_tmax = tmax;
+    inst_len = 1.0f;
+    inst_hit = false;
+    G = make_uint2(g_scene.bvh_root, 0x80000000u);
+  }
 
-  int cur_object = -1;     /* OBJECT_NONE while in world space */
-  float world_tmax = tmax; /* world-space limit saved while inside an instance */
-  float inst_len = 1.0f;
-  bool inst_hit = false;
+  __device__ __forceinline__ void push(uint2 *stack, uint2 e)
+  {
+    if (sp < BVH8_STACK_SIZE)
+      stack[sp++] = e;
+  }
 
-  uint2 G = make_uint2(g_scene.bvh_root, 0x80000000u); /* node group */
-  uint2 Gt = make_uint2(0u, 0u);                       /* leaf-record group */
-
-  while (true) {
+  /* returns true when the traversal is complete */
+  __device__ __forceinline__ bool step(uint2 *stack, TraceCounters &cnt)
+  {
+    uint2 Gt;
     if (G.y & 0xff000000u) {
       const uint32_t hits_imask = G.y;
       const uint32_t child_bit_index = 31u - (uint32_t)__clz((int)hits_imask);
       G.y &= ~(1u << child_bit_index);
-      if (G.y & 0xff000000u) {
-        if (sp < BVH8_STACK_SIZE)
-          stack[sp++] = G;
-      }
+      if (G.y & 0xff000000u)
+        push(stack, G);
       const uint32_t slot_index = (child_bit_index - 24u) ^ (rs.oct_inv4 & 0xffu);
       const uint32_t relative_index = __popc(hits_imask & ~(0xffffffffu << slot_index) & 0xffu);
       const uint32_t node_index = G.x + relative_index;
@@ -268,16 +291,11 @@ __device__ __forceinline__ bool bvh8_intersect(
         const int object = ~tag;
         if (COUNT)
           cnt.instances++;
-        if (G.y & 0xff000000u) {
-          if (sp < BVH8_STACK_SIZE)
-            stack[sp++] = G;
-        }
-        if (Gt.y != 0u) {
-          if (sp < BVH8_STACK_SIZE)
-            stack[sp++] = Gt;
-        }
-        if (sp < BVH8_STACK_SIZE)
-          stack[sp++] = make_uint2(BVH8_SENTINEL, 0u);
+        if (G.y & 0xff000000u)
+          push(stack, G);
+        if (Gt.y != 0u)
+          push(stack, Gt);
+        push(stack, make_uint2(BVH8_SENTINEL, 0u));
 
         const tfm34 itfm = object_itfm(object);
         float len;
@@ -298,12 +316,9 @@ __device__ __forceinline__ bool bvh8_intersect(
 
     /* pop */
     if ((G.y & 0xff000000u) == 0u) {
-      bool done = false;
       while (true) {
-        if (sp == 0) {
-          done = true;
-          break;
-        }
+        if (sp == 0)
+          return true;
         G = stack[--sp];
         if (G.x == BVH8_SENTINEL) {
           /* instance pop - geom_object.h:447-460 */
@@ -321,12 +336,168 @@ __device__ __forceinline__ bool bvh8_intersect(
         }
         break;
       }
-      if (done)
+    }
+    return false;
+  }
+};
+
+/* One ray to completion (used where no refill is wanted). */
+template<bool ANY_HIT, bool COUNT>
+__device__ __forceinline__ bool bvh8_intersect(
+    f3 P, f3 D, float tmax, uint32_t visibility, TraceHit &hit, TraceCounters &cnt)
+{
+  uint2 stack[BVH8_STACK_SIZE];
+  Traversal<ANY_HIT, COUNT> tr;
+  tr.start(P, D, tmax, visibility);
+  while (!tr.step(stack, cnt)) {
+  }
+  hit = tr.hit;
+  return hit.prim >= 0;
+}
+
+#define TRACE_BLOCK 128
+#define TRACE_WARPS (TRACE_BLOCK / 32)
+
+CY_DEV void cp_async16(void *smem_dst, const void *gmem_src)
+{
+  const unsigned int dst = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+CY_DEV void cp_async_commit()
+{
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template<int N> CY_DEV void cp_async_wait()
+{
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+/* Persistent-thread driver shared by every traversal kernel.
+ *
+ * Rays arrive in QUEUE ORDER as two 16-byte records (P.xyz,t | D.xyz,visibility) -
+ * the 32 B "ray in" of the roofline model.  Each warp stages them through shared
+ * memory: it claims 32 queue entries with one atomic, pulls them in with cp.async
+ * (LDGSTS, fully coalesced) into one half of a double buffer while the lanes
+ * traverse, and finished lanes refill from the staged rays at shared-memory latency
+ * instead of stalling the warp on a dependent global load.  Each lane owns a
+ * Traversal; a refill round is taken when fewer than `refill_threshold` lanes are
+ * still busy.  `Job` supplies
+ *   const float4 *ray_P(unsigned qi), *ray_D(unsigned qi)   addresses of the records
+ *   void store(unsigned qi, const TraceHit &hit, bool found)
+ */
+template<bool ANY_HIT, bool COUNT, class Job>
+__device__ __forceinline__ void trace_persistent(Job &job, unsigned int n, unsigned int *cursor,
+                                                 int refill_threshold, TraceCounters &cnt)
+{
+  __shared__ float4 s_ray[TRACE_WARPS][2][2][32]; /* [warp][buffer][P|D][entry] : 8 KB */
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  uint2 stack[BVH8_STACK_SIZE];
+  Traversal<ANY_HIT, COUNT> tr;
+  bool active = false;
+  unsigned int my_qi = 0;
+
+  /* warp-uniform staging state */
+  unsigned int base0 = 0, base1 = 0, avail0 = 0, avail1 = 0;
+  unsigned int cur = 0, consumed = 0;
+  bool drained = false;
+
+  auto fill = [&](unsigned int b) {
+    unsigned int bs = 0;
+    if (lane == 0)
+      bs = atomicAdd(cursor, 32u);
+    bs = __shfl_sync(0xffffffffu, bs, 0);
+    const unsigned int av = (bs < n) ? min(32u, n - bs) : 0u;
+    if (lane < av) {
+      cp_async16(&s_ray[warp][b][0][lane], job.ray_P(bs + lane));
+      cp_async16(&s_ray[warp][b][1][lane], job.ray_D(bs + lane));
+    }
+    cp_async_commit();
+    if (b == 0) {
+      base0 = bs;
+      avail0 = av;
+    }
+    else {
+      base1 = bs;
+      avail1 = av;
+    }
+  };
+
+  fill(0);
+  fill(1);
+  cp_async_wait<1>(); /* buffer 0 has landed */
+  __syncwarp();
+  if (avail0 == 0)
+    drained = true;
+
+  while (true) {
+    /* ---- refill idle lanes from the staged rays ---- */
+    while (!drained) {
+      const unsigned int need = __ballot_sync(0xffffffffu, !active);
+      if (need == 0u)
+        break;
+      const unsigned int cur_base = cur ? base1 : base0;
+      const unsigned int cur_avail = cur ? avail1 : avail0;
+      const unsigned int left = cur_avail - consumed;
+      const unsigned int take = min((unsigned int)__popc(need), left);
+      const unsigned int rank = __popc(need & lt_mask);
+      if (!active && rank < take) {
+        const unsigned int e = consumed + rank;
+        const float4 r0 = s_ray[warp][cur][0][e];
+        const float4 r1 = s_ray[warp][cur][1][e];
+        const unsigned int qi = cur_base + e;
+        const f3 D = mk3(r1);
+        /* inactive (t = 0) or invalid rays (scene_intersect_valid, bvh/bvh.h:146-152) */
+        if (r0.w != 0.0f && isfinite_safe(r0.x) && isfinite_safe(r1.x) &&
+            len_squared(D) != 0.0f) {
+          tr.start(mk3(r0), D, r0.w, __float_as_uint(r1.w));
+          my_qi = qi;
+          active = true;
+        }
+        else {
+          TraceHit miss;
+          miss.t = r0.w;
+          miss.u = miss.v = 0.0f;
+          miss.prim = -1;
+          miss.object = -1;
+          job.store(qi, miss, false);
+        }
+      }
+      consumed += take;
+      if (consumed == cur_avail) {
+        /* current half is used up: restage it, switch to the other half */
+        __syncwarp();
+        fill(cur);
+        cp_async_wait<1>();
+        __syncwarp();
+        cur ^= 1u;
+        consumed = 0;
+        if ((cur ? avail1 : avail0) == 0u)
+          drained = true;
+      }
+    }
+
+    if (!__any_sync(0xffffffffu, active))
+      break;
+
+    /* ---- traverse until too few lanes are busy ---- */
+    while (true) {
+      if (active) {
+        if (tr.step(stack, cnt)) {
+          job.store(my_qi, tr.hit, tr.hit.prim >= 0);
+          active = false;
+        }
+      }
+      const unsigned int busy = __ballot_sync(0xffffffffu, active);
+      if (busy == 0u)
+        break;
+      if (!drained && __popc(busy) < refill_threshold)
         break;
     }
   }
-
-  return hit.prim >= 0;
+  cp_async_wait<0>();
 }
 
 #endif /* B200_TRAVERSE_CUH */

@@ -44,19 +44,27 @@ struct WFCounters {
 };
 
 struct PathSoA {
+  /* ray queue, in QUEUE order (entry qi belongs to path q_active[qi]): the 32-byte
+   * "ray in" record the traversal kernel streams through shared memory */
   float4 *ray_P_t;    /* Ray::P, Ray::t */
-  float4 *ray_D;      /* Ray::D, PathState::ray_pdf */
-  float4 *hit;        /* Intersection t,u,v, prim */
-  int *hit_object;    /* Intersection::object */
+  float4 *ray_D;      /* Ray::D, visibility mask of this segment */
+  float4 *nray_P_t;   /* next bounce's queue, written by shade_surface */
+  float4 *nray_D;
+  float4 *hit;        /* [qi] Intersection t,u,v, prim */
+  int *hit_object;    /* [qi] Intersection::object */
+  float *ray_pdf;     /* [path] PathState::ray_pdf */
   float4 *throughput; /* throughput, PathState::ray_t */
   float4 *L;          /* PathRadiance::emission, transparent */
   uint4 *stateA;      /* flag, rng_hash, rng_offset, sample */
   uint4 *stateB;      /* bounce|diffuse<<16, glossy|transmission<<16, transparent, min_ray_pdf */
-  float4 *sh_P_t;     /* shadow ray */
-  float4 *sh_D;
-  float4 *sh_contrib; /* throughput * L_light (already clamped) */
-  unsigned int *key;  /* sort key: 0 miss, 1 + shader */
-  int *q_active, *q_next, *q_sorted, *q_shadow;
+  float4 *sh_P_t;     /* [shadow queue] shadow ray P, t */
+  float4 *sh_D;       /* [shadow queue] D, PATH_RAY_SHADOW_OPAQUE */
+  float4 *sh_contrib; /* [shadow queue] throughput * L_light (already clamped) */
+  unsigned int *key;  /* [qi] sort key: 0 miss, 1 + shader */
+  int *q_active; /* [qi] -> path */
+  int *q_next;   /* next bounce's q_active */
+  int *q_sorted; /* queue positions qi ordered by key */
+  int *q_shadow; /* [shadow queue] -> path */
   WFCounters *counters;
 };
 
@@ -206,6 +214,23 @@ CY_DEV void path_state_next(PathStateG &s, int label)
   s.rng_offset += CY_PRNG_BOUNCE_NUM;
 }
 
+/* Pixel order inside a batch: 8x4 tiles, so the 32 lanes of a warp start with a
+ * compact bundle of camera rays (coherent traversal, 128-byte film rows); plain
+ * rows when the rectangle is not a multiple of the tile. */
+CY_DEV void batch_pixel(const BatchParams &bp, unsigned int pix, int *x, int *y)
+{
+  if (((bp.w & 7) | (bp.h & 3)) == 0) {
+    const unsigned int t = pix >> 5, l = pix & 31u;
+    const unsigned int tiles_x = (unsigned)bp.w >> 3;
+    *x = bp.x + (int)((t % tiles_x) * 8u + (l & 7u));
+    *y = bp.y + (int)((t / tiles_x) * 4u + (l >> 3));
+  }
+  else {
+    *x = bp.x + (int)(pix % (unsigned)bp.w);
+    *y = bp.y + (int)(pix / (unsigned)bp.w);
+  }
+}
+
 /* ------------------------------------------------------ init_from_camera */
 
 __global__ void __launch_bounds__(WF_BLOCK)
@@ -216,8 +241,8 @@ __global__ void __launch_bounds__(WF_BLOCK)
   for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const unsigned int pix = i % npix;
     const int s = (int)(i / npix);
-    const int x = bp.x + (int)(pix % (unsigned)bp.w);
-    const int y = bp.y + (int)(pix / (unsigned)bp.w);
+    int x, y;
+    batch_pixel(bp, pix, &x, &y);
     const int sample = bp.sample0 + s;
 
     uint32_t rng_hash;
@@ -235,92 +260,65 @@ __global__ void __launch_bounds__(WF_BLOCK)
     st.min_ray_pdf = FLT_MAX;
     state_store(p, i, st);
 
-    p.ray_P_t[i] = make_float4(P.x, P.y, P.z, t);
-    p.ray_D[i] = make_float4(D.x, D.y, D.z, 0.0f);            /* ray_pdf = 0 */
+    p.ray_pdf[i] = 0.0f;
     p.throughput[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);    /* ray_t = 0 */
     /* kernel_path_trace returns before kernel_write_result when ray.t == 0
      * (kernel_path.h:668-670): transparent = 1 makes the film add (0,0,0,0). */
     p.L[i] = make_float4(0.0f, 0.0f, 0.0f, (t == 0.0f) ? 1.0f : 0.0f);
     const unsigned int slot = warp_append(&p.counters->n_active, t != 0.0f);
-    if (t != 0.0f)
+    if (t != 0.0f) {
       p.q_active[slot] = (int)i;
+      p.ray_P_t[slot] = make_float4(P.x, P.y, P.z, t);
+      p.ray_D[slot] = make_float4(D.x, D.y, D.z,
+                                  __uint_as_float(path_state_ray_visibility(st.flag)));
+    }
   }
 }
 
 /* ----------------------------------------------------- intersect_closest */
 
+struct ClosestJob {
+  PathSoA p;
+  __device__ __forceinline__ const float4 *ray_P(unsigned int qi) const
+  {
+    return p.ray_P_t + qi;
+  }
+  __device__ __forceinline__ const float4 *ray_D(unsigned int qi) const
+  {
+    return p.ray_D + qi;
+  }
+  __device__ __forceinline__ void store(unsigned int qi, const TraceHit &h, bool found)
+  {
+    p.hit[qi] = make_float4(h.t, h.u, h.v, __int_as_float(h.prim));
+    p.hit_object[qi] = h.object;
+    unsigned int key = 0;
+    if (found) {
+      const unsigned int tri = __ldg(&g_scene.prim_index[h.prim]);
+      key = 1u + (__ldg(&g_scene.tri_shader[tri]) & CY_SHADER_MASK);
+      if (key > WF_MAX_KEYS)
+        key = WF_MAX_KEYS;
+    }
+    p.key[qi] = key;
+  }
+};
+
 template<bool COUNT>
-__global__ void __launch_bounds__(128) k_intersect_closest(PathSoA p)
+__global__ void __launch_bounds__(TRACE_BLOCK) k_intersect_closest(PathSoA p, int refill_threshold)
 {
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned int n = p.counters->n_active;
   TraceCounters cnt;
   cnt.nodes = cnt.tris = cnt.instances = 0;
-  unsigned int n_primary = 0, n_bounce = 0;
-  while (true) {
-    unsigned int base = 0;
-    if (lane == 0)
-      base = atomicAdd(&p.counters->work_closest, 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= n)
-      break;
-    const unsigned int qi = base + lane;
-    if (qi < n) {
-      const int i = p.q_active[qi];
-      float4 r0 = p.ray_P_t[i];
-      const float4 r1 = p.ray_D[i];
-      PathStateG st;
-      state_load(p, i, st);
-      /* kernel_path_scene_intersect - kernel_path.h:57-84 */
-      uint32_t visibility = path_state_ray_visibility(st.flag);
-      if (path_state_ao_bounce(st)) {
-        visibility = CY_PATH_RAY_SHADOW;
-        r0.w = kd_float(KD_BG_AO_DISTANCE);
-      }
-      if (st.flag & CY_PATH_RAY_CAMERA)
-        n_primary++;
-      else
-        n_bounce++;
-      TraceHit h;
-      h.t = r0.w;
-      h.u = h.v = 0.0f;
-      h.prim = -1;
-      h.object = -1;
-      /* scene_intersect_valid - bvh/bvh.h:146-152 */
-      const f3 D = mk3(r1);
-      if (isfinite_safe(r0.x) && isfinite_safe(r1.x) && len_squared(D) != 0.0f)
-        bvh8_intersect<false, COUNT>(mk3(r0), D, r0.w, visibility, h, cnt);
-      p.hit[i] = make_float4(h.t, h.u, h.v, __int_as_float(h.prim));
-      p.hit_object[i] = h.object;
-      unsigned int key = 0;
-      if (h.prim >= 0) {
-        const unsigned int tri = __ldg(&g_scene.prim_index[h.prim]);
-        key = 1u + (__ldg(&g_scene.tri_shader[tri]) & CY_SHADER_MASK);
-        if (key > WF_MAX_KEYS)
-          key = WF_MAX_KEYS;
-      }
-      p.key[i] = key;
-      /* histogram for the shader sort: one atomic per distinct key per warp */
-      const unsigned int peers = __match_any_sync(__activemask(), key);
-      if (lane == (unsigned)(__ffs(peers) - 1))
-        atomicAdd(&p.counters->hist[key], __popc(peers));
-    }
-  }
-  for (int o = 16; o > 0; o >>= 1) {
-    n_primary += __shfl_xor_sync(0xffffffffu, n_primary, o);
-    n_bounce += __shfl_xor_sync(0xffffffffu, n_bounce, o);
-    if (COUNT) {
+  ClosestJob job;
+  job.p = p;
+  trace_persistent<false, COUNT>(job, p.counters->n_active, &p.counters->work_closest,
+                                 refill_threshold, cnt);
+  if (COUNT) {
+    for (int o = 16; o > 0; o >>= 1) {
       cnt.nodes += __shfl_xor_sync(0xffffffffu, cnt.nodes, o);
       cnt.tris += __shfl_xor_sync(0xffffffffu, cnt.tris, o);
       cnt.instances += __shfl_xor_sync(0xffffffffu, cnt.instances, o);
     }
-  }
-  if (lane == 0) {
-    if (n_primary)
-      atomicAdd(&p.counters->primary_rays, (unsigned long long)n_primary);
-    if (n_bounce)
-      atomicAdd(&p.counters->bounce_rays, (unsigned long long)n_bounce);
-    if (COUNT) {
+    if (lane == 0) {
       atomicAdd(&p.counters->nodes, (unsigned long long)cnt.nodes);
       atomicAdd(&p.counters->tris, (unsigned long long)cnt.tris);
       atomicAdd(&p.counters->instances, (unsigned long long)cnt.instances);
@@ -329,6 +327,22 @@ __global__ void __launch_bounds__(128) k_intersect_closest(PathSoA p)
 }
 
 /* ----------------------------------------------- sort by shader (counting) */
+
+/* histogram of the sort keys: converged grid-stride pass, one atomic per distinct
+ * key per warp (__match_any_sync) */
+__global__ void __launch_bounds__(WF_BLOCK) k_sort_count(PathSoA p)
+{
+  WFCounters *c = p.counters;
+  const unsigned int n = c->n_active;
+  for (unsigned int qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n;
+       qi += gridDim.x * blockDim.x) {
+    const unsigned int key = p.key[qi];
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int peers = __match_any_sync(__activemask(), key);
+    if (lane == (unsigned)(__ffs(peers) - 1))
+      atomicAdd(&c->hist[key], __popc(peers));
+  }
+}
 
 __global__ void k_sort_scan(PathSoA p, int num_keys)
 {
@@ -356,8 +370,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_sort_scatter(PathSoA p)
   const unsigned int n = c->n_active;
   for (unsigned int qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n;
        qi += gridDim.x * blockDim.x) {
-    const int i = p.q_active[qi];
-    const unsigned int key = p.key[i];
+    const unsigned int key = p.key[qi];
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int peers = __match_any_sync(__activemask(), key);
     const unsigned int leader = __ffs(peers) - 1u;
@@ -366,7 +379,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_sort_scatter(PathSoA p)
       base = atomicAdd(&c->cursor[key], __popc(peers));
     base = __shfl_sync(peers, base, leader);
     const unsigned int pos = c->offsets[key] + base + __popc(peers & ((1u << lane) - 1u));
-    p.q_sorted[pos] = i;
+    p.q_sorted[pos] = (int)qi;
   }
 }
 
@@ -416,19 +429,20 @@ __global__ void __launch_bounds__(WF_BLOCK) k_shade_background(PathSoA p)
   const unsigned int n = c->offsets[1]; /* key 0 segment */
   for (unsigned int qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n;
        qi += gridDim.x * blockDim.x) {
-    const int i = p.q_sorted[qi];
-    const float4 r0 = p.ray_P_t[i];
-    const float4 r1 = p.ray_D[i];
+    const int qpos = p.q_sorted[qi];
+    const int i = p.q_active[qpos];
+    const float4 r0 = p.ray_P_t[qpos];
+    const float4 r1 = p.ray_D[qpos];
     const float4 tp = p.throughput[i];
     float4 Lr = p.L[i];
     PathStateG st;
     state_load(p, i, st);
-    st.ray_pdf = r1.w;
+    st.ray_pdf = p.ray_pdf[i];
     st.ray_t = tp.w;
     f3 throughput = mk3(tp);
     f3 L = mk3(Lr);
     const f3 rayP = mk3(r0), rayD = mk3(r1);
-    const float isect_t = p.hit[i].x; /* = ray t on a miss (bvh_traversal.h:62) */
+    const float isect_t = p.hit[qpos].x; /* = ray t on a miss (bvh_traversal.h:62) */
 
     ShaderDataG esd;
     path_lamp_emission(st, rayP, rayD, isect_t, throughput, esd, L);
@@ -468,17 +482,20 @@ __global__ void __launch_bounds__(WF_BLOCK) k_shade_surface(PathSoA p, int num_k
     const bool valid = k < total;
     bool want_next = false, want_shadow = false;
     int i = -1;
+    float4 out_ray_P = make_float4(0.0f, 0.0f, 0.0f, 0.0f), out_ray_D = out_ray_P;
+    float4 out_sh_P = out_ray_P, out_sh_D = out_ray_P, out_sh_C = out_ray_P;
     if (valid) {
-      i = p.q_sorted[begin + k];
-      const float4 r0 = p.ray_P_t[i];
-      const float4 r1 = p.ray_D[i];
+      const int qpos = p.q_sorted[begin + k];
+      i = p.q_active[qpos];
+      const float4 r0 = p.ray_P_t[qpos];
+      const float4 r1 = p.ray_D[qpos];
       const float4 tp = p.throughput[i];
-      const float4 hit = p.hit[i];
-      const int hit_object = p.hit_object[i];
+      const float4 hit = p.hit[qpos];
+      const int hit_object = p.hit_object[qpos];
       const float4 Lr = p.L[i];
       PathStateG st;
       state_load(p, i, st);
-      st.ray_pdf = r1.w;
+      st.ray_pdf = p.ray_pdf[i];
       st.ray_t = tp.w;
       f3 throughput = mk3(tp);
       f3 L = mk3(Lr);
@@ -596,10 +613,10 @@ __global__ void __launch_bounds__(WF_BLOCK) k_shade_surface(PathSoA p, int num_k
                     sD = ray_offset(ls.P, ls.Ng) - sP;
                     sD = normalize_len(sD, &st_t);
                   }
-                  p.sh_P_t[i] = make_float4(sP.x, sP.y, sP.z, st_t);
-                  p.sh_D[i] = make_float4(sD.x, sD.y, sD.z, 0.0f);
-                  p.sh_contrib[i] = make_float4(contribution.x, contribution.y, contribution.z,
-                                                0.0f);
+                  out_sh_P = make_float4(sP.x, sP.y, sP.z, st_t);
+                  out_sh_D = make_float4(sD.x, sD.y, sD.z,
+                                         __uint_as_float(CY_PATH_RAY_SHADOW_OPAQUE));
+                  out_sh_C = make_float4(contribution.x, contribution.y, contribution.z, 0.0f);
                   want_shadow = true;
                 }
                 else {
@@ -644,59 +661,73 @@ __global__ void __launch_bounds__(WF_BLOCK) k_shade_surface(PathSoA p, int num_k
       /* write back */
       p.L[i] = make_float4(L.x, L.y, L.z, Lr.w);
       if (want_next) {
-        p.ray_P_t[i] = make_float4(rayP.x, rayP.y, rayP.z, ray_t);
-        p.ray_D[i] = make_float4(rayD.x, rayD.y, rayD.z, st.ray_pdf);
+        /* visibility and AO-bounce clipping of the NEXT segment, decided here so the
+         * traversal kernel needs nothing but the 32-byte ray (kernel_path.h:66-71) */
+        uint32_t vis = path_state_ray_visibility(st.flag);
+        if (path_state_ao_bounce(st)) {
+          vis = CY_PATH_RAY_SHADOW;
+          ray_t = kd_float(KD_BG_AO_DISTANCE);
+        }
+        out_ray_P = make_float4(rayP.x, rayP.y, rayP.z, ray_t);
+        out_ray_D = make_float4(rayD.x, rayD.y, rayD.z, __uint_as_float(vis));
+        p.ray_pdf[i] = st.ray_pdf;
         p.throughput[i] = make_float4(throughput.x, throughput.y, throughput.z, st.ray_t);
         state_store(p, i, st);
       }
     }
     const unsigned int s_next = warp_append(&c->n_next, want_next);
-    if (want_next)
+    if (want_next) {
       p.q_next[s_next] = i;
+      p.nray_P_t[s_next] = out_ray_P;
+      p.nray_D[s_next] = out_ray_D;
+    }
     const unsigned int s_sh = warp_append(&c->n_shadow, want_shadow);
-    if (want_shadow)
+    if (want_shadow) {
       p.q_shadow[s_sh] = i;
+      p.sh_P_t[s_sh] = out_sh_P;
+      p.sh_D[s_sh] = out_sh_D;
+      p.sh_contrib[s_sh] = out_sh_C;
+    }
   }
 }
 
 /* -------------------------------------- intersect_shadow + shade_shadow */
 
-template<bool COUNT>
-__global__ void __launch_bounds__(128) k_intersect_shadow(PathSoA p)
-{
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned int n = p.counters->n_shadow;
-  TraceCounters cnt;
-  cnt.nodes = cnt.tris = cnt.instances = 0;
-  while (true) {
-    unsigned int base = 0;
-    if (lane == 0)
-      base = atomicAdd(&p.counters->work_shadow, 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= n)
-      break;
-    const unsigned int qi = base + lane;
-    if (qi < n) {
+struct ShadowJob {
+  PathSoA p;
+  __device__ __forceinline__ const float4 *ray_P(unsigned int qi) const
+  {
+    return p.sh_P_t + qi;
+  }
+  __device__ __forceinline__ const float4 *ray_D(unsigned int qi) const
+  {
+    return p.sh_D + qi; /* .w = PATH_RAY_SHADOW_OPAQUE: shadow_blocked_opaque, kernel_shadow.h:90 */
+  }
+  __device__ __forceinline__ void store(unsigned int qi, const TraceHit &, bool blocked)
+  {
+    if (!blocked) {
+      /* shade_shadow - path_radiance_accum_light, kernel_accumulate.h:402-459 */
       const int i = p.q_shadow[qi];
-      const float4 r0 = p.sh_P_t[i];
-      const float4 r1 = p.sh_D[i];
-      TraceHit h;
-      bool blocked = false;
-      /* shadow_blocked_opaque - kernel_shadow.h:90-106: visibility & SHADOW_OPAQUE */
-      const f3 D = mk3(r1);
-      if (isfinite_safe(r0.x) && isfinite_safe(r1.x) && len_squared(D) != 0.0f)
-        blocked = bvh8_intersect<true, COUNT>(mk3(r0), D, r0.w, CY_PATH_RAY_SHADOW_OPAQUE, h, cnt);
-      if (!blocked) {
-        /* shade_shadow - path_radiance_accum_light, kernel_accumulate.h:402-459 */
-        const float4 cn = p.sh_contrib[i];
-        float4 L = p.L[i];
-        L.x += cn.x;
-        L.y += cn.y;
-        L.z += cn.z;
-        p.L[i] = L;
-      }
+      const float4 cn = p.sh_contrib[qi];
+      float4 L = p.L[i];
+      L.x += cn.x;
+      L.y += cn.y;
+      L.z += cn.z;
+      p.L[i] = L;
     }
   }
+};
+
+template<bool COUNT>
+__global__ void __launch_bounds__(TRACE_BLOCK) k_intersect_shadow(PathSoA p, int refill_threshold)
+{
+  const unsigned lane = threadIdx.x & 31u;
+  TraceCounters cnt;
+  cnt.nodes = cnt.tris = cnt.instances = 0;
+  ShadowJob job;
+  job.p = p;
+  trace_persistent<true, COUNT>(job, p.counters->n_shadow, &p.counters->work_shadow,
+                                refill_threshold, cnt);
   if (COUNT) {
     for (int o = 16; o > 0; o >>= 1) {
       cnt.nodes += __shfl_xor_sync(0xffffffffu, cnt.nodes, o);
@@ -713,10 +744,15 @@ __global__ void __launch_bounds__(128) k_intersect_shadow(PathSoA p)
 
 /* per-iteration bookkeeping: q_next becomes q_active (pointers are swapped on
  * the host), counters roll over */
-__global__ void k_iteration_end(PathSoA p, int num_keys)
+__global__ void k_iteration_end(PathSoA p, int num_keys, int iteration)
 {
   WFCounters *c = p.counters;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
+    /* the first segment of every path is the camera ray (PATH_RAY_CAMERA) */
+    if (iteration == 0)
+      c->primary_rays += c->n_active;
+    else
+      c->bounce_rays += c->n_active;
     c->shadow_rays += c->n_shadow;
     c->n_active = c->n_next;
     c->n_next = 0;
@@ -740,8 +776,8 @@ __global__ void __launch_bounds__(WF_BLOCK)
   const unsigned int npix = (unsigned)bp.w * (unsigned)bp.h;
   for (unsigned int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
        pix += gridDim.x * blockDim.x) {
-    const int x = bp.x + (int)(pix % (unsigned)bp.w);
-    const int y = bp.y + (int)(pix / (unsigned)bp.w);
+    int x, y;
+    batch_pixel(bp, pix, &x, &y);
     const long long index = (long long)bp.offset + x + (long long)y * bp.stride;
     float4 *dst = (float4 *)(film + index * pass_stride + pass_combined);
     float4 acc = *dst;
@@ -846,6 +882,7 @@ static int ensure_pool(b200_ctx *ctx, size_t capacity)
     return o;
   };
   const size_t n = capacity;
+  size_t o_nrayP = carve(n * 16), o_nrayD = carve(n * 16), o_rpdf = carve(n * 4);
   size_t o_rayP = carve(n * 16), o_rayD = carve(n * 16), o_hit = carve(n * 16),
          o_hobj = carve(n * 4), o_thr = carve(n * 16), o_L = carve(n * 16), o_sA = carve(n * 16),
          o_sB = carve(n * 16), o_shP = carve(n * 16), o_shD = carve(n * 16), o_shC = carve(n * 16),
@@ -862,6 +899,9 @@ static int ensure_pool(b200_ctx *ctx, size_t capacity)
   PathSoA &s = pool->soa;
   s.ray_P_t = (float4 *)(b + o_rayP);
   s.ray_D = (float4 *)(b + o_rayD);
+  s.nray_P_t = (float4 *)(b + o_nrayP);
+  s.nray_D = (float4 *)(b + o_nrayD);
+  s.ray_pdf = (float *)(b + o_rpdf);
   s.hit = (float4 *)(b + o_hit);
   s.hit_object = (int *)(b + o_hobj);
   s.throughput = (float4 *)(b + o_thr);
@@ -1023,7 +1063,9 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
   const int pass_combined = kd_host<int>(ctx, KD_FILM_PASS_COMBINED);
   const bool count = ctx->opt_count_traversal != 0;
   const int grid_wide = launch_grid(ctx, 8);
-  const int grid_trace = launch_grid(ctx, 8);
+  const int grid_trace = launch_grid(
+      ctx, ctx->opt_trace_blocks_per_sm > 0 ? (int)ctx->opt_trace_blocks_per_sm : 8);
+  const int refill = refill_threshold(ctx);
   cudaStream_t st = ctx->stream;
 
   b200_stats stats;
@@ -1062,22 +1104,23 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
       for (int it = 0; it < max_iterations; it++) {
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
         if (count)
-          k_intersect_closest<true><<<grid_trace, 128, 0, st>>>(soa);
+          k_intersect_closest<true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
         else
-          k_intersect_closest<false><<<grid_trace, 128, 0, st>>>(soa);
+          k_intersect_closest<false><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+        k_sort_count<<<grid_wide, WF_BLOCK, 0, st>>>(soa);
         k_sort_scan<<<1, 256, 0, st>>>(soa, num_keys);
         k_sort_scatter<<<grid_wide, WF_BLOCK, 0, st>>>(soa);
         k_shade_background<<<grid_wide, WF_BLOCK, 0, st>>>(soa);
         k_shade_surface<<<grid_wide, WF_BLOCK, 0, st>>>(soa, num_keys);
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev3, st));
         if (count)
-          k_intersect_shadow<true><<<grid_trace, 128, 0, st>>>(soa);
+          k_intersect_shadow<true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
         else
-          k_intersect_shadow<false><<<grid_trace, 128, 0, st>>>(soa);
+          k_intersect_shadow<false><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev4, st));
-        k_iteration_end<<<8, 256, 0, st>>>(soa, num_keys);
-        stats.kernel_launches += 7;
+        k_iteration_end<<<8, 256, 0, st>>>(soa, num_keys, it);
+        stats.kernel_launches += 8;
         stats.closest_launches += 1;
         stats.shadow_launches += 1;
         /* one counter back per bounce (the reference copies the whole ray_state
@@ -1094,6 +1137,8 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
           shadow_ms += b;
         }
         std::swap(soa.q_active, soa.q_next);
+        std::swap(soa.ray_P_t, soa.nray_P_t);
+        std::swap(soa.ray_D, soa.nray_D);
         if (pool->h_counters->n_active == 0)
           break;
       }
