@@ -318,6 +318,138 @@ struct Builder {
     return root_idx;
   }
 
+  /* ---- SAH-optimal 2 -> 8 collapse (dynamic programme of Ylitie et al. 2017, sec. 3) ----
+   * cost[n][i-1] = cheapest way to present binary subtree n to its BVH8 parent in at
+   * most i child slots; a slot is a leaf (<= 3 triangles, possibly a merged small
+   * subtree) or an inner BVH8 node (which itself distributes 8 slots).  */
+  struct DP {
+    float cost[7];
+    uint8_t split[7]; /* i > 1: slots given to the left subtree, 0 = same as i-1 */
+    uint8_t split8;   /* distribution of the 8 slots when n becomes an inner node */
+    bool leaf1;       /* the single-slot form is a (merged) leaf */
+    int prims;        /* triangles below, big when an instance is below */
+  };
+  std::vector<DP> dp;
+
+  void run_dp(int root)
+  {
+    const float c_node = 1.0f, c_prim = 0.3f;
+    /* post-order without recursion */
+    std::vector<int> order, st;
+    st.push_back(root);
+    while (!st.empty()) {
+      int n = st.back();
+      st.pop_back();
+      order.push_back(n);
+      if (bn[n].left >= 0) {
+        st.push_back(bn[n].left);
+        st.push_back(bn[n].right);
+      }
+    }
+    if (dp.size() < bn.size())
+      dp.resize(bn.size());
+    for (size_t oi = order.size(); oi-- > 0;) {
+      const int n = order[oi];
+      const BNode &b = bn[n];
+      DP &d = dp[n];
+      const float area = b.box.half_area();
+      if (b.left < 0) {
+        d.prims = (b.object >= 0) ? 1000000 : b.count;
+        const float c = area * c_prim * (b.object >= 0 ? 4.0f : (float)std::max(b.count, 1));
+        for (int i = 0; i < 7; i++) {
+          d.cost[i] = c;
+          d.split[i] = 0;
+        }
+        d.leaf1 = true;
+        d.split8 = 0;
+        continue;
+      }
+      const DP &l = dp[b.left], &r = dp[b.right];
+      d.prims = std::min(1000000, l.prims + r.prims);
+      /* as an inner BVH8 node: distribute 8 slots over the two subtrees */
+      float best8 = INFINITY;
+      int k8 = 1;
+      for (int k = 1; k <= 7; k++) {
+        const float c = l.cost[k - 1] + r.cost[8 - k - 1];
+        if (c < best8) {
+          best8 = c;
+          k8 = k;
+        }
+      }
+      d.split8 = (uint8_t)k8;
+      const float c_internal = best8 + area * c_node;
+      const float c_leaf = (d.prims <= BVH8_MAX_LEAF_RECORDS) ? area * c_prim * (float)d.prims :
+                                                                INFINITY;
+      d.leaf1 = c_leaf <= c_internal;
+      d.cost[0] = std::min(c_leaf, c_internal);
+      d.split[0] = 0;
+      for (int i = 2; i <= 7; i++) {
+        float best = d.cost[i - 2];
+        int bk = 0;
+        for (int k = 1; k < i; k++) {
+          const float c = l.cost[k - 1] + r.cost[i - k - 1];
+          if (c < best) {
+            best = c;
+            bk = k;
+          }
+        }
+        d.cost[i - 1] = best;
+        d.split[i - 1] = (uint8_t)bk;
+      }
+    }
+  }
+
+  struct Slot {
+    int bnode;
+    bool leaf; /* whole subtree becomes one leaf slot */
+  };
+
+  /* children of subtree n when it may use at most i slots */
+  void gather(int n, int i, std::vector<Slot> &out)
+  {
+    struct Item {
+      int n, i;
+    };
+    std::vector<Item> st;
+    st.push_back({n, i});
+    while (!st.empty()) {
+      Item it = st.back();
+      st.pop_back();
+      const BNode &b = bn[it.n];
+      const DP &d = dp[it.n];
+      int ii = it.i;
+      while (ii > 1 && d.split[ii - 1] == 0)
+        ii--;
+      if (b.left < 0 || ii == 1) {
+        out.push_back({it.n, b.left < 0 ? true : d.leaf1});
+        continue;
+      }
+      const int k = d.split[ii - 1];
+      st.push_back({b.right, ii - k});
+      st.push_back({b.left, k});
+    }
+  }
+
+  /* triangles below a (merged) leaf slot */
+  void collect_refs(int n, std::vector<int> &out_refs)
+  {
+    std::vector<int> st;
+    st.push_back(n);
+    while (!st.empty()) {
+      int m = st.back();
+      st.pop_back();
+      const BNode &b = bn[m];
+      if (b.left < 0) {
+        for (int t = 0; t < b.count; t++)
+          out_refs.push_back(refs[b.first + t]);
+      }
+      else {
+        st.push_back(b.right);
+        st.push_back(b.left);
+      }
+    }
+  }
+
   struct Child {
     int bnode;
     Box box;
@@ -341,41 +473,26 @@ struct Builder {
       max_depth = std::max(max_depth, w.depth);
       const BNode &rootb = bn[w.bnode];
 
-      /* gather up to 8 children */
-      std::vector<int> ch;
+      /* children chosen by the dynamic programme */
+      std::vector<Slot> slots;
       if (rootb.left < 0) {
-        ch.push_back(w.bnode); /* leaf-only root */
+        slots.push_back({w.bnode, true}); /* leaf-only root */
       }
       else {
-        ch.push_back(rootb.left);
-        ch.push_back(rootb.right);
-        while ((int)ch.size() < 8) {
-          int best = -1;
-          float best_area = -1.0f;
-          for (int i = 0; i < (int)ch.size(); i++) {
-            const BNode &c = bn[ch[i]];
-            if (c.left < 0)
-              continue;
-            float a = c.box.half_area();
-            if (a > best_area) {
-              best_area = a;
-              best = i;
-            }
-          }
-          if (best < 0)
-            break;
-          int c = ch[best];
-          ch[best] = bn[c].left;
-          ch.push_back(bn[c].right);
-        }
+        const int k8 = dp[w.bnode].split8;
+        gather(rootb.left, k8, slots);
+        gather(rootb.right, 8 - k8, slots);
       }
       /* drop empty leaves */
-      ch.erase(std::remove_if(ch.begin(), ch.end(),
-                              [&](int c) {
-                                const BNode &b = bn[c];
-                                return b.left < 0 && b.object < 0 && b.count == 0;
-                              }),
-               ch.end());
+      slots.erase(std::remove_if(slots.begin(), slots.end(),
+                                 [&](const Slot &sl) {
+                                   const BNode &b = bn[sl.bnode];
+                                   return b.left < 0 && b.object < 0 && b.count == 0;
+                                 }),
+                  slots.end());
+      std::vector<int> ch;
+      for (const Slot &sl : slots)
+        ch.push_back(sl.bnode);
 
       Box nb;
       nb.reset();
@@ -463,7 +580,7 @@ struct Builder {
 
       uint32_t num_inner = 0;
       for (size_t i = 0; i < ch.size(); i++)
-        if (bn[ch[i]].left >= 0)
+        if (!slots[i].leaf)
           num_inner++;
       node.child_base = (uint32_t)out.nodes.size();
       node.prim_base = (uint32_t)(out.records.size() / 12);
@@ -488,7 +605,7 @@ struct Builder {
           node.qlo[k][s] = (uint8_t)lo;
           node.qhi[k][s] = (uint8_t)hi;
         }
-        if (c.left >= 0) {
+        if (!slots[i].leaf) {
           node.imask |= (uint8_t)(1u << s);
           node.meta[s] = (uint8_t)((1u << 5) | (24 + s));
           queue.push_back({ch[i], node.child_base + inner_i, w.depth + 1});
@@ -511,10 +628,13 @@ struct Builder {
           out.num_instances++;
         }
         else {
-          uint32_t unary = (c.count == 1) ? 1u : (c.count == 2) ? 3u : 7u;
+          std::vector<int> leaf_refs;
+          collect_refs(ch[i], leaf_refs);
+          const int count = (int)leaf_refs.size();
+          uint32_t unary = (count == 1) ? 1u : (count == 2) ? 3u : 7u;
           node.meta[s] = (uint8_t)((unary << 5) | rec_off);
-          for (int t = 0; t < c.count; t++) {
-            int pa = refs[c.first + t];
+          for (int t = 0; t < count; t++) {
+            int pa = leaf_refs[t];
             uint32_t vi = in.prim_tri_index[pa];
             float rec[12];
             for (int k = 0; k < 3; k++) {
@@ -529,9 +649,9 @@ struct Builder {
             out.records.insert(out.records.end(), rec, rec + 12);
             out.num_triangles++;
           }
-          rec_off += (uint32_t)c.count;
+          rec_off += (uint32_t)count;
           if (area > 0.0)
-            sah += (double)c.count * c.box.half_area() / area;
+            sah += (double)count * c.box.half_area() / area;
         }
       }
       out.nodes[w.node_index] = node;
@@ -544,6 +664,7 @@ struct Builder {
     int root = decode(root_addr);
     if (root < 0)
       return 0xffffffffu;
+    run_dp(root);
     uint32_t root_index = (uint32_t)out.nodes.size();
     out.nodes.resize(out.nodes.size() + 1);
     collapse(root, root_index);

@@ -357,6 +357,9 @@ __device__ __forceinline__ bool bvh8_intersect(
 
 #define TRACE_BLOCK 128
 #define TRACE_WARPS (TRACE_BLOCK / 32)
+#ifndef TRACE_MIN_BLOCKS
+#  define TRACE_MIN_BLOCKS 8 /* <= 64 registers: 32 resident warps per SM */
+#endif
 
 CY_DEV void cp_async16(void *smem_dst, const void *gmem_src)
 {

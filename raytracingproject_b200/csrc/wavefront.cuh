@@ -303,7 +303,7 @@ struct ClosestJob {
 };
 
 template<bool COUNT>
-__global__ void __launch_bounds__(TRACE_BLOCK) k_intersect_closest(PathSoA p, int refill_threshold)
+__global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_intersect_closest(PathSoA p, int refill_threshold)
 {
   const unsigned lane = threadIdx.x & 31u;
   TraceCounters cnt;
@@ -719,7 +719,7 @@ struct ShadowJob {
 };
 
 template<bool COUNT>
-__global__ void __launch_bounds__(TRACE_BLOCK) k_intersect_shadow(PathSoA p, int refill_threshold)
+__global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_intersect_shadow(PathSoA p, int refill_threshold)
 {
   const unsigned lane = threadIdx.x & 31u;
   TraceCounters cnt;
