@@ -160,6 +160,10 @@ int b200_film_reduce(b200_ctx **ctxs, int n, const uint64_t *films, size_t n_flo
 int b200_get_stats(b200_ctx *ctx, b200_stats *out);
 int b200_synchronize(b200_ctx *ctx);
 
+/* Debugging aid: with option "debug_slot" = s (>= 0) the path in pool slot s records
+ * 32 floats per bounce in shade_surface; this reads up to 16 bounces back. */
+int b200_debug_read(b200_ctx *ctx, float *out, size_t n_floats);
+
 /* Run all work of this context on an existing CUDA stream (cudaStream_t handle,
  * e.g. torch.cuda.Stream.cuda_stream) so callers can bracket it with their own
  * events; 0 restores the context's private stream. */

@@ -67,6 +67,7 @@ def lib():
         L.ref_shadow_rays.argtypes = [
             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.ref_init.argtypes = [C.c_int]
+        L.ref_path_dump.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.ref_count_rays.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.ref_num_threads.restype = C.c_int
         _lib = L
@@ -189,6 +190,12 @@ class RefScene:
             self._h, int(start_sample), int(num_samples), int(tile_size), int(accumulate),
             out.ctypes.data, C.byref(sec)))
         return out, sec.value
+
+    def path_dump(self, sample, x, y):
+        """(16, 32) per-bounce debug records of one reference path (ref_probe_path_dump)."""
+        out = np.zeros((16, 32), np.float32)
+        self._check(self._L.ref_path_dump(self._h, sample, x, y, out.ctypes.data))
+        return out
 
     def count_rays(self, start_sample, num_samples):
         """(camera, bounce, shadow) rays the reference traces for these samples."""

@@ -474,6 +474,16 @@ int ref_count_rays(ref_scene *rs, int start_sample, int num_samples, unsigned lo
   return 0;
 }
 
+int ref_path_dump(ref_scene *rs, int sample, int x, int y, float *out)
+{
+  if (!rs->cpu)
+    return 1;
+  KernelGlobals kg = rs->cpu->kg_init();
+  ref_probe_path_dump(&kg, sample, x, y, out);
+  rs->cpu->kg_free(&kg);
+  return 0;
+}
+
 int ref_shadow_rays(ref_scene *rs, int sample, int x0, int y0, int w, int h, RefProbeRay *rays)
 {
   if (!rs->cpu)

@@ -250,6 +250,95 @@ void ref_probe_count_rays(KernelGlobals *kg, int sample, int x0, int y0, int w, 
   }
 }
 
+/* Debugging aid: the same 32 floats per bounce the B200 device records with option
+ * "debug_slot" (wavefront.cuh), taken from the reference path loop. */
+void ref_probe_path_dump(KernelGlobals *kg, int sample, int x, int y, float *out)
+{
+  Ray ray;
+  uint rng_hash;
+  kernel_path_trace_setup(kg, sample, x, y, &rng_hash, &ray);
+  if (ray.t == 0.0f)
+    return;
+  float3 throughput = make_float3(1.0f, 1.0f, 1.0f);
+  PathRadiance L;
+  path_radiance_init(kg, &L);
+  ShaderDataTinyStorage emission_sd_storage;
+  ShaderData *emission_sd = AS_SHADER_DATA(&emission_sd_storage);
+  PathState state;
+  path_state_init(kg, emission_sd, &state, rng_hash, sample, &ray);
+  ShaderData sd;
+  for (;;) {
+    Intersection isect;
+    bool hit = kernel_path_scene_intersect(kg, &state, &ray, &isect, &L);
+    kernel_path_lamp_emission(kg, &state, &ray, throughput, &isect, &sd, &L);
+    if (!hit) {
+      kernel_path_background(kg, &state, &ray, throughput, &sd, NULL, &L);
+      break;
+    }
+    else if (path_state_ao_bounce(kg, &state)) {
+      break;
+    }
+    shader_setup_from_ray(kg, &sd, &isect, &ray);
+    shader_eval_surface(kg, &sd, &state, NULL, state.flag);
+    shader_prepare_closures(&sd, &state);
+    if (!kernel_path_shader_apply(kg, &sd, &state, &ray, throughput, emission_sd, &L, NULL))
+      break;
+    float probability = path_state_continuation_probability(kg, &state, throughput);
+    if (probability == 0.0f) {
+      break;
+    }
+    else if (probability != 1.0f) {
+      float terminate = path_state_rng_1D(kg, &state, PRNG_TERMINATE);
+      if (terminate >= probability)
+        break;
+      throughput /= probability;
+    }
+    kernel_path_surface_connect_light(kg, &sd, emission_sd, throughput, &state, &L);
+    /* kernel_path_surface_bounce, opened up to record the sample */
+    if (!(sd.flag & SD_BSDF))
+      break;
+    float bsdf_pdf;
+    BsdfEval bsdf_eval;
+    float3 bsdf_omega_in;
+    differential3 bsdf_domega_in;
+    float bsdf_u, bsdf_v;
+    path_state_rng_2D(kg, &state, PRNG_BSDF_U, &bsdf_u, &bsdf_v);
+    Ray in_ray = ray;
+    int label = shader_bsdf_sample(
+        kg, &sd, bsdf_u, bsdf_v, &bsdf_eval, &bsdf_omega_in, &bsdf_domega_in, &bsdf_pdf);
+    if (bsdf_pdf == 0.0f || bsdf_eval_is_zero(&bsdf_eval))
+      break;
+    path_radiance_bsdf_bounce(kg, &L.state, &throughput, &bsdf_eval, bsdf_pdf, state.bounce, label);
+    if (!(label & LABEL_TRANSPARENT)) {
+      state.ray_pdf = bsdf_pdf;
+      state.ray_t = 0.0f;
+      state.min_ray_pdf = fminf(bsdf_pdf, state.min_ray_pdf);
+    }
+    path_state_next(kg, &state, label);
+    ray.P = ray_offset(sd.P, (label & LABEL_TRANSMIT) ? -sd.Ng : sd.Ng);
+    ray.D = normalize(bsdf_omega_in);
+    if (state.bounce == 0)
+      ray.t -= sd.ray_length;
+    else
+      ray.t = FLT_MAX;
+    ray.dP = sd.dP;
+    ray.dD = bsdf_domega_in;
+    if (state.bounce < 16) {
+      float *dbg = out + 32 * (state.bounce + state.transparent_bounce - 1);
+      dbg[0] = in_ray.P.x, dbg[1] = in_ray.P.y, dbg[2] = in_ray.P.z, dbg[3] = in_ray.t;
+      dbg[4] = in_ray.D.x, dbg[5] = in_ray.D.y, dbg[6] = in_ray.D.z, dbg[7] = isect.t;
+      dbg[8] = (float)isect.prim, dbg[9] = (float)isect.object, dbg[10] = sd.P.x;
+      dbg[11] = sd.P.y, dbg[12] = sd.P.z, dbg[13] = sd.N.x, dbg[14] = sd.N.y;
+      dbg[15] = sd.N.z, dbg[16] = (float)(sd.flag & 0xffff), dbg[17] = (float)sd.num_closure;
+      dbg[18] = (float)sd.closure[0].type, dbg[19] = sd.closure[0].sample_weight;
+      dbg[20] = (float)sd.closure[1].type, dbg[21] = sd.closure[1].sample_weight;
+      dbg[22] = (float)label, dbg[23] = bsdf_pdf, dbg[24] = bsdf_omega_in.x;
+      dbg[25] = bsdf_omega_in.y, dbg[26] = bsdf_omega_in.z, dbg[27] = throughput.x;
+      dbg[28] = throughput.y, dbg[29] = throughput.z, dbg[30] = bsdf_u, dbg[31] = bsdf_v;
+    }
+  }
+}
+
 void ref_probe_path_trace(
     KernelGlobals *kg, float *buffer, int sample, int x, int y, int offset, int stride)
 {

@@ -31,6 +31,7 @@ void ref_probe_shadow_rays(KernelGlobals *kg, int sample, int x0, int y0, int w,
                            RefProbeRay *rays);
 void ref_probe_count_rays(KernelGlobals *kg, int sample, int x0, int y0, int w, int h,
                           unsigned long long counts[3]);
+void ref_probe_path_dump(KernelGlobals *kg, int sample, int x, int y, float *out);
 void ref_probe_path_trace(KernelGlobals *kg, float *buffer, int sample, int x, int y, int offset,
                           int stride);
 }  // namespace ccl

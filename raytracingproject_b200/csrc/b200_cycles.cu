@@ -234,6 +234,8 @@ void b200_destroy(b200_ctx *ctx)
     cudaFree(ctx->d_records);
   if (ctx->d_counters)
     cudaFree(ctx->d_counters);
+  if (ctx->d_debug)
+    cudaFree(ctx->d_debug);
   if (ctx->h_counters)
     cudaFreeHost(ctx->h_counters);
   cudaEventDestroy(ctx->ev0);
@@ -650,6 +652,15 @@ int b200_get_stats(b200_ctx *ctx, b200_stats *out)
   return B200_OK;
 }
 
+int b200_debug_read(b200_ctx *ctx, float *out, size_t n_floats)
+{
+  if (!ctx || !out || !ctx->d_debug || n_floats > 16 * 32)
+    return B200_ERR_INVALID;
+  DeviceGuard guard(ctx->ordinal);
+  CUDA_TRY(ctx, cudaMemcpy(out, ctx->d_debug, n_floats * sizeof(float), cudaMemcpyDeviceToHost));
+  return B200_OK;
+}
+
 int b200_set_stream(b200_ctx *ctx, uint64_t cuda_stream)
 {
   if (!ctx)
@@ -670,6 +681,18 @@ int b200_set_option(b200_ctx *ctx, const char *name, int64_t value)
   }
   else if (strcmp(name, "count_traversal") == 0)
     ctx->opt_count_traversal = value;
+  else if (strcmp(name, "debug_slot") == 0) {
+    /* debugging aid: record the shading of one path slot, read back with b200_d2h from
+     * the pointer returned through option "debug_ptr" semantics (see tools/) */
+    DeviceGuard guard(ctx->ordinal);
+    ctx->opt_debug_slot = value;
+    if (value >= 0 && !ctx->d_debug) {
+      if (cudaMalloc(&ctx->d_debug, 16 * 32 * sizeof(float)) != cudaSuccess)
+        return fail(ctx, B200_ERR_CUDA, "debug buffer allocation failed");
+    }
+    if (ctx->d_debug)
+      cudaMemset(ctx->d_debug, 0, 16 * 32 * sizeof(float));
+  }
   else if (strcmp(name, "refill_threshold") == 0)
     ctx->opt_refill_threshold = value;
   else if (strcmp(name, "trace_blocks_per_sm") == 0)

@@ -48,6 +48,8 @@ struct b200_ctx {
   PathPool *pool = nullptr;
   int64_t opt_batch_paths = 0;
   int64_t opt_count_traversal = 0;
+  int64_t opt_debug_slot = -1;
+  float *d_debug = nullptr; /* 16 bounces x 32 floats when "debug_slot" >= 0 */
   int64_t opt_refill_threshold = 0;
   int64_t opt_trace_blocks_per_sm = 0;
 

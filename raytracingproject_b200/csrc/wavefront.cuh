@@ -66,6 +66,10 @@ struct PathSoA {
   int *q_sorted; /* queue positions qi ordered by key */
   int *q_shadow; /* [shadow queue] -> path */
   WFCounters *counters;
+  /* debugging aid: when debug != NULL the path in slot debug_slot records 32 floats
+   * per bounce (ray, hit, shading point, closures, sampled direction) */
+  float *debug;
+  int debug_slot;
 };
 
 struct PathPool {
@@ -654,6 +658,19 @@ __global__ void __launch_bounds__(WF_BLOCK) k_shade_surface(PathSoA p, int num_k
             else
               ray_t = FLT_MAX;
             want_next = true;
+            if (p.debug && i == p.debug_slot && st.bounce < 16) {
+              float *dbg = p.debug + 32 * (st.bounce + st.transparent_bounce - 1);
+              dbg[0] = r0.x, dbg[1] = r0.y, dbg[2] = r0.z, dbg[3] = r0.w;
+              dbg[4] = r1.x, dbg[5] = r1.y, dbg[6] = r1.z, dbg[7] = hit.x;
+              dbg[8] = (float)hit_prim, dbg[9] = (float)hit_object, dbg[10] = sd.P.x;
+              dbg[11] = sd.P.y, dbg[12] = sd.P.z, dbg[13] = sd.N.x, dbg[14] = sd.N.y;
+              dbg[15] = sd.N.z, dbg[16] = (float)(sd.flag & 0xffff), dbg[17] = (float)sd.num_closure;
+              dbg[18] = (float)sd.closure[0].type, dbg[19] = sd.closure[0].sample_weight;
+              dbg[20] = (float)sd.closure[1].type, dbg[21] = sd.closure[1].sample_weight;
+              dbg[22] = (float)label, dbg[23] = bsdf_pdf, dbg[24] = omega_in.x;
+              dbg[25] = omega_in.y, dbg[26] = omega_in.z, dbg[27] = throughput.x;
+              dbg[28] = throughput.y, dbg[29] = throughput.z, dbg[30] = bsdf_u, dbg[31] = bsdf_v;
+            }
           }
         }
       }
@@ -1096,6 +1113,8 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
       bp.count_stats = count;
 
       PathSoA soa = pool->soa;
+      soa.debug = ctx->d_debug;
+      soa.debug_slot = (int)ctx->opt_debug_slot;
       CUDA_TRY(ctx, cudaMemsetAsync(soa.counters, 0, sizeof(WFCounters), st));
       k_init_from_camera<<<grid_wide, WF_BLOCK, 0, st>>>(soa, bp);
       stats.kernel_launches += 1;

@@ -34,7 +34,7 @@ EXPORTS = [
     "b200_last_error", "b200_alloc", "b200_free", "b200_h2d", "b200_d2h", "b200_zero",
     "b200_mem_used", "b200_bind_global", "b200_set_kernel_data", "b200_build_bvh", "b200_render",
     "b200_trace_batch", "b200_film_convert", "b200_film_reduce", "b200_get_stats",
-    "b200_synchronize", "b200_set_option", "b200_set_stream",
+    "b200_synchronize", "b200_set_option", "b200_set_stream", "b200_debug_read",
 ]
 
 
@@ -109,6 +109,7 @@ def load_library():
     L.b200_synchronize.argtypes = [vp]
     L.b200_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.b200_set_stream.argtypes = [vp, u64]
+    L.b200_debug_read.argtypes = [vp, vp, sz]
     _lib = L
     return L
 
@@ -250,6 +251,12 @@ class B200Device:
 
     def set_option(self, name, value):
         self._check(self._L.b200_set_option(self._ctx, name.encode(), int(value)), "set_option")
+
+    def debug_read(self):
+        """(16, 32) float32 records of the path selected with option debug_slot."""
+        out = np.zeros((16, 32), np.float32)
+        self._check(self._L.b200_debug_read(self._ctx, out.ctypes.data, out.size), "debug_read")
+        return out
 
     def set_stream(self, cuda_stream):
         """Issue all work on an existing CUDA stream (0 = the private stream)."""

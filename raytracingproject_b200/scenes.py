@@ -282,11 +282,13 @@ def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
     xml += _diffuse_shader("white", (0.73, 0.73, 0.73))
     xml += _diffuse_shader("red", (0.65, 0.05, 0.05))
     xml += _diffuse_shader("green", (0.12, 0.45, 0.15))
-    if materials == "principled":
+    if materials in ("principled", "metal"):
         xml += _principled_shader("metal", (0.9, 0.85, 0.7), 1.0, 0.2, 0.5, 0.0, 1.45, distribution)
-        xml += _principled_shader("glass", (1, 1, 1), 0.0, 0.0, 0.5, 1.0, 1.45, distribution)
     else:
         xml += _diffuse_shader("metal", (0.9, 0.85, 0.7))
+    if materials in ("principled", "glass"):
+        xml += _principled_shader("glass", (1, 1, 1), 0.0, 0.0, 0.5, 1.0, 1.45, distribution)
+    else:
         xml += _diffuse_shader("glass", (0.6, 0.7, 0.9))
     xml += _emission_shader("lamp", (1.0, 0.9, 0.7), 1.0)
     xml += _state(
@@ -317,9 +319,11 @@ def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
         m[:, 3] = t
         return m
 
-    Pb, Tb = box_mesh((-0.3, -0.3, 0.0), (0.3, 0.3, 1.2))
+    # the boxes float 2 mm above the floor: coplanar overlapping faces would make the
+    # closest hit an exact tie whose winner depends on the BVH traversal order
+    Pb, Tb = box_mesh((-0.3, -0.3, 0.002), (0.3, 0.3, 1.2))
     add(Pb, Tb, "metal", rot_z(20.0, (-0.35, 0.3, 0.0)))
-    Ps, Ts = box_mesh((-0.3, -0.3, 0.0), (0.3, 0.3, 0.6))
+    Ps, Ts = box_mesh((-0.3, -0.3, 0.002), (0.3, 0.3, 0.6))
     add(Ps, Ts, "glass", rot_z(-18.0, (0.35, -0.3, 0.0)))
     return SceneDesc("cornell_" + materials, xml, width, height, meshes=meshes, objects=objects,
                      spp=spp, notes="config 3")

@@ -11,3 +11,12 @@ def small_cases():
         "terrain": scenes.terrain(W, H, n=96),
         "instanced": scenes.instanced(W, H, grid=8, subdiv=3),
     }
+
+
+def principled_cases():
+    """Config 1 / config 3 materials: Principled BSDF (GGX distribution), metallic and
+    glass variants, 12 / 8 bounces."""
+    return {
+        "cube_principled": scenes.default_cube(W, H, material="principled"),
+        "cornell_principled": scenes.cornell(W, H, materials="principled"),
+    }

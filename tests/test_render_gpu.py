@@ -6,7 +6,7 @@ gates hold at any spp, not only at 1024."""
 import numpy as np
 import pytest
 
-from scene_cases import small_cases
+from scene_cases import principled_cases, small_cases
 
 pytestmark = pytest.mark.gpu
 
@@ -36,6 +36,20 @@ def image_gates(ref_img, got, spp, label):
 @pytest.mark.parametrize("name", ["cube", "cornell", "terrain", "instanced"])
 def test_image_matches_reference(ref, device, name):
     desc = small_cases()[name]
+    rs = ref.build_scene(desc)
+    try:
+        device.upload_scene(rs.device_arrays())
+        ref_img, _ = rs.render(0, SPP, tile_size=64)
+        got = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP)
+        print(name, device.stats())
+        image_gates(ref_img, got, SPP, name)
+    finally:
+        rs.close()
+
+
+@pytest.mark.parametrize("name", ["cube_principled", "cornell_principled"])
+def test_principled_image_matches_reference(ref, device, name):
+    desc = principled_cases()[name]
     rs = ref.build_scene(desc)
     try:
         device.upload_scene(rs.device_arrays())
