@@ -415,12 +415,30 @@ int ref_render(ref_scene *rs,
 
 /* ---- kernel probes (CPU device only) ---- */
 
+/* The reference renders with FTZ + DAZ on every worker thread
+ * (SIMD_SET_FLUSH_TO_ZERO, device_cpu.cpp:905); the probes run on the caller's
+ * thread, so they adopt the same mode for the duration of the call. */
+struct ScopedFlushToZero {
+  unsigned int saved;
+  ScopedFlushToZero() : saved(_mm_getcsr())
+  {
+    _mm_setcsr(saved | 0x8040);
+  }
+  ~ScopedFlushToZero()
+  {
+    _mm_setcsr(saved);
+  }
+};
+
 int ref_intersect(ref_scene *rs, const RefProbeRay *rays, RefProbeHit *hits, uint64_t n)
 {
   if (!rs->cpu)
     return 1;
   KernelGlobals kg = rs->cpu->kg_init();
-  ref_probe_intersect(&kg, rays, hits, n);
+  {
+    ScopedFlushToZero ftz;
+    ref_probe_intersect(&kg, rays, hits, n);
+  }
   rs->cpu->kg_free(&kg);
   return 0;
 }
@@ -431,7 +449,10 @@ int ref_camera_rays(
   if (!rs->cpu)
     return 1;
   KernelGlobals kg = rs->cpu->kg_init();
-  ref_probe_camera_rays(&kg, sample, x0, y0, w, h, rays, rng_hash);
+  {
+    ScopedFlushToZero ftz;
+    ref_probe_camera_rays(&kg, sample, x0, y0, w, h, rays, rng_hash);
+  }
   rs->cpu->kg_free(&kg);
   return 0;
 }
@@ -479,7 +500,10 @@ int ref_path_dump(ref_scene *rs, int sample, int x, int y, float *out)
   if (!rs->cpu)
     return 1;
   KernelGlobals kg = rs->cpu->kg_init();
-  ref_probe_path_dump(&kg, sample, x, y, out);
+  {
+    ScopedFlushToZero ftz;
+    ref_probe_path_dump(&kg, sample, x, y, out);
+  }
   rs->cpu->kg_free(&kg);
   return 0;
 }
@@ -489,7 +513,10 @@ int ref_shadow_rays(ref_scene *rs, int sample, int x0, int y0, int w, int h, Ref
   if (!rs->cpu)
     return 1;
   KernelGlobals kg = rs->cpu->kg_init();
-  ref_probe_shadow_rays(&kg, sample, x0, y0, w, h, rays);
+  {
+    ScopedFlushToZero ftz;
+    ref_probe_shadow_rays(&kg, sample, x0, y0, w, h, rays);
+  }
   rs->cpu->kg_free(&kg);
   return 0;
 }
