@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--spp", type=int, default=0, help="samples per step (0 = the config's)")
     ap.add_argument("--cpu-spp", type=int, default=0,
                     help="samples of the bounded CPU sample (0 = auto)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank renders the config's spp; strong: the spp are split")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--opt", action="append", default=[],
@@ -247,11 +249,15 @@ def run_b200(args):
     t_upload = time.perf_counter() - t0
 
     film = torch.zeros(h * w * ps, dtype=torch.float32, device="cuda")
-    start_sample, _ = multigpu.weak_range(rank, spp)
+    if args.scaling == "strong":
+        start_sample, my_spp = multigpu.strong_range(rank, world, spp)
+    else:
+        start_sample, my_spp = multigpu.weak_range(rank, spp)
+    total_spp = spp if args.scaling == "strong" else spp * world
 
     def step():
         film.zero_()
-        dev.render_tile(film.data_ptr(), 0, 0, w, h, start_sample, spp, 0, w)
+        dev.render_tile(film.data_ptr(), 0, 0, w, h, start_sample, my_spp, 0, w)
         multigpu.reduce_film(film)  # NCCL all-reduce over NVLink when world > 1
         return dev.stats()
 
@@ -292,7 +298,50 @@ def run_b200(args):
         ms_max, rays_total, launches_total = ms, float(rays_rank), agg["kernel_launches"]
 
     value = rays_total / (ms_max * 1e-3) / 1e6
-    spp_per_s = world * spp * args.steps / (ms_max * 1e-3)
+    spp_per_s = total_spp * args.steps / (ms_max * 1e-3)
+
+    # ---- e2e: the Device call a host makes, host buffers, copies inside the timing.
+    # Every rank uploads its RenderBuffers from pinned host memory, renders its share of the
+    # samples, joins the film reduction and reads the film back; wall clock between
+    # barriers, max over ranks. ----
+    e2e_all = None
+    if not args.no_e2e:
+        host_film = torch.zeros(h * w * ps, dtype=torch.float32).pin_memory()
+        mem = DeviceMemory("RenderBuffers", host_film.numpy())
+        dev.mem_alloc(mem)
+        e2e_steps = max(1, min(args.steps, 3))
+        dev.mem_copy_to(mem)
+        dev.render_tile(mem.device_pointer, 0, 0, w, h, start_sample, my_spp, 0, w)  # warm
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        e_rays = 0
+        for _ in range(e2e_steps):
+            host_film.zero_()
+            dev.mem_copy_to(mem)          # H2D of the step's film (RenderBuffers)
+            dev.render_tile(mem.device_pointer, 0, 0, w, h, start_sample, my_spp, 0, w)
+            s_ = dev.stats()
+            e_rays += s_["primary_rays"] + s_["bounce_rays"] + s_["shadow_rays"]
+            if world > 1:
+                multigpu.reduce_film(mem_as_tensor(mem, film))
+            dev.mem_copy_from(mem)        # D2H of the result
+        torch.cuda.synchronize()
+        e_sec = time.perf_counter() - t0
+        dev.mem_free(mem)
+        if world > 1:
+            t = torch.tensor([e_sec], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_sec = float(t.item())
+            r = torch.tensor([e_rays], dtype=torch.float64, device="cuda")
+            dist.all_reduce(r)
+            e_rays = float(r.item())
+        e2e_all = {"value": e_rays / e_sec / 1e6, "unit": "Mrays/s",
+                   "h2d_bytes_per_step": int(host_film.numel() * 4) * world,
+                   "d2h_bytes_per_step": int(host_film.numel() * 4) * world,
+                   "ms_per_step": 1e3 * e_sec / e2e_steps, "steps": e2e_steps,
+                   "api": "B200Device.mem_copy_to / render_tile (DeviceTask::RENDER) / "
+                          "mem_copy_from over the C ABI, every rank"}
 
     out = None
     if rank == 0:
@@ -342,34 +391,10 @@ def run_b200(args):
                        "share_of_step": agg["shadow_ms"] / max(agg["device_ms"], 1e-9)},
         }
 
-        # ---- e2e: the Device call a host makes, host buffers, copies inside the timing ----
-        e2e = None
-        if not args.no_e2e and world == 1:
-            host_film = torch.zeros(h * w * ps, dtype=torch.float32).pin_memory()
-            mem = DeviceMemory("RenderBuffers", host_film.numpy())
-            dev.mem_alloc(mem)
-            e2e_steps = max(1, min(args.steps, 3))
-            dev.mem_copy_to(mem)
-            dev.render_tile(mem.device_pointer, 0, 0, w, h, 0, spp, 0, w)  # warm
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            e_rays = 0
-            for _ in range(e2e_steps):
-                host_film.zero_()
-                dev.mem_copy_to(mem)          # H2D of the step's film (RenderBuffers)
-                dev.render_tile(mem.device_pointer, 0, 0, w, h, 0, spp, 0, w)
-                s = dev.stats()
-                e_rays += s["primary_rays"] + s["bounce_rays"] + s["shadow_rays"]
-                dev.mem_copy_from(mem)        # D2H of the result
-            torch.cuda.synchronize()
-            e_sec = time.perf_counter() - t0
-            dev.mem_free(mem)
-            e2e = {"value": e_rays / e_sec / 1e6, "unit": "Mrays/s",
-                   "h2d_bytes_per_step": int(host_film.numel() * 4),
-                   "d2h_bytes_per_step": int(host_film.numel() * 4),
-                   "ms_per_step": 1e3 * e_sec / e2e_steps,
-                   "api": "B200Device.mem_copy_to / render_tile (DeviceTask::RENDER) / "
-                          "mem_copy_from over the C ABI"}
+        # ---- e2e (measured on every rank above); rank 0 adds the reference-driven flow ----
+        e2e = e2e_all
+        if e2e is not None and world == 1:
+            e2e_steps = e2e["steps"]
             # the same step through the C++ `B200Device : ccl::Device`, driven by the
             # reference's own Scene::device_update + DeviceTask::RENDER + RenderBuffers
             # readback (mem_zero on the device, D2H of the film)
@@ -394,9 +419,6 @@ def run_b200(args):
                 host.close()
             except Exception as exc:  # the shim needs the reference headers to be built
                 e2e["reference_flow"] = {"unavailable": str(exc)[:200]}
-        elif world > 1:
-            e2e = {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0,
-                   "d2h_bytes_per_step": 0, "note": "measured at N=1 only"}
 
         # ---- CPU baseline on the box's host cores (bounded sample) ----
         cpu = None
@@ -407,11 +429,11 @@ def run_b200(args):
         out = {
             "metric": "Mrays/s (primary+bounce+shadow)", "value": value, "unit": "Mrays/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": workload_name(desc), "width": w, "height": h, "spp_per_step": spp,
-                "triangles": desc.num_triangles, "parallelism": "sample-split x%d" % world,
+                "workload": workload_name(desc), "width": w, "height": h, "spp_per_step": total_spp,
+                "spp_per_rank": my_spp, "triangles": desc.num_triangles, "parallelism": "sample-split x%d" % world,
                 "l2": "inputs larger than L2: %.0f MB of BVH8 + %.0f MB of path state per batch"
                       % ((bvh["node_bytes"] + bvh["tri_bytes"]) / 1e6, 4194304 * 180 / 1e6),
                 "bvh8": bvh, "scene_build_s": t_scene, "upload_and_bvh8_s": t_upload,
@@ -435,6 +457,17 @@ def run_b200(args):
 
 
 _REAL_STDOUT = None
+
+
+class _RawCuda:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False),
+                                         "version": 2}
+
+
+def mem_as_tensor(mem, like):
+    """View a C-ABI device allocation as a torch tensor (for the NCCL film reduce)."""
+    return torch.as_tensor(_RawCuda(mem.device_pointer, like.numel()), device=like.device)
 
 
 def emit(obj):

@@ -182,47 +182,50 @@ CY_DEV uint32_t bvh8_node_intersect(const RaySpace &rs,
   return hitmask;
 }
 
-/* Resumable traversal of one ray: start() arms it, step() does one unit of work
- * (one BVH8 node, then the leaf records that node - or a popped leaf group -
- * exposed) and returns true when the ray is finished.  Kernels keep one of these
- * per lane and refill finished lanes from their queue (persistent threads with
- * dynamic fetch), instead of parking a lane until the slowest ray of its warp ends.
+/* Resumable traversal of one ray, cut into the three phases the persistent warp
+ * driver below interleaves:
+ *   node_phase()   one BVH8 node (or a leaf group popped earlier) -> pending leaf
+ *                  records in Gt
+ *   leaf phase     WARP-COOPERATIVE (trace_persistent): the pending records of all
+ *                  lanes are pooled and spread over the 32 lanes, so the triangle
+ *                  test runs once per step with many lanes on instead of once per
+ *                  record with the two or three lanes that happen to own one
+ *   finish_step()  instance push for records the leaf phase flagged, stack pop
+ * Kernels keep one Traversal per lane and refill finished lanes from their queue
+ * (persistent threads with dynamic fetch).
  *
  * ANY_HIT = false: closest hit, `hit` is the Intersection.  ANY_HIT = true:
  * occlusion (shadow early-out), only hit.prim >= 0 is meaningful. */
 template<bool ANY_HIT, bool COUNT> struct Traversal {
-  /* the (node group, leaf group) stack is a separate local array handed to step():
-   * keeping it out of the struct lets every scalar member live in a register */
+  /* the (node group, leaf group) stack is a separate local array handed to the
+   * phases: keeping it out of the struct lets every scalar member live in a register */
   int sp;
   RaySpace rs;
-  f3 P, D; /* the world-space ray, kept for the instance pop */
-  float tmax;
+  float tmax; /* current limit = distance of the closest hit so far (hit.t is filled at the end) */
   uint32_t visibility;
   TraceHit hit;
-  int cur_object;   /* OBJECT_NONE (-1) while in world space */
-  float world_tmax; /* world-space limit saved while inside an instance */
-  float inst_len;
+  int cur_object; /* OBJECT_NONE (-1) while in world space */
   bool inst_hit;
-  uint2 G; /* node group: (child base, hits << 24 | imask) */
+  /* The world-space ray is NOT kept in registers: the instance push / pop re-read it
+   * from the ray queue; the world-space limit and the direction scale saved at an
+   * instance push live in the stack entry under the sentinel. */
+  uint2 G;  /* node group: (child base, hits << 24 | imask) */
+  uint2 Gt; /* pending leaf group: (record base, record hit bits) */
 
-  __device__ __forceinline__ void start(f3 P_, f3 D_, float tmax_, uint32_t visibility_)
+  __device__ __forceinline__ void start(f3 P, f3 D, float tmax_, uint32_t visibility_)
   {
     sp = 0;
-    P = P_;
-    D = D_;
     tmax = tmax_;
     visibility = visibility_;
     ray_space_setup(rs, P, D);
-    hit.t = tmax;
     hit.u = 0.0f;
     hit.v = 0.0f;
     hit.prim = -1;
     hit.object = -1;
     cur_object = -1;
-    world_tmax = tmax;
-    inst_len = 1.0f;
     inst_hit = false;
     G = make_uint2(g_scene.bvh_root, 0x80000000u);
+    Gt = make_uint2(0u, 0u);
   }
 
   __device__ __forceinline__ void push(uint2 *stack, uint2 e)
@@ -231,10 +234,8 @@ template<bool ANY_HIT, bool COUNT> struct Traversal {
       stack[sp++] = e;
   }
 
-  /* returns true when the traversal is complete */
-  __device__ __forceinline__ bool step(uint2 *stack, TraceCounters &cnt)
+  __device__ __forceinline__ void node_phase(uint2 *stack, TraceCounters &cnt)
   {
-    uint2 Gt;
     if (G.y & 0xff000000u) {
       const uint32_t hits_imask = G.y;
       const uint32_t child_bit_index = 31u - (uint32_t)__clz((int)hits_imask);
@@ -257,61 +258,53 @@ template<bool ANY_HIT, bool COUNT> struct Traversal {
       Gt = G;
       G = make_uint2(0u, 0u);
     }
+  }
 
-    /* leaf records */
-    while (Gt.y != 0u) {
-      const uint32_t bit = (uint32_t)__ffs((int)Gt.y) - 1u;
-      Gt.y &= ~(1u << bit);
-      const float4 *rp = g_scene.records + (size_t)(Gt.x + bit) * 3;
-      const float4 ra = __ldg(rp + 0);
-      const int tag = __float_as_int(ra.w);
-      if (tag >= 0) {
-        const float4 rb = __ldg(rp + 1);
-        const float4 rc = __ldg(rp + 2);
-        if (COUNT)
-          cnt.tris++;
-        float t, u, v;
-        if (ray_triangle_intersect(rs.P, rs.dir, tmax, mk3(ra), mk3(rb), mk3(rc), &u, &v, &t)) {
-          if (__float_as_uint(rb.w) & visibility) {
-            hit.prim = tag;
-            hit.object = cur_object;
-            hit.u = u;
-            hit.v = v;
-            hit.t = t;
-            tmax = t;
-            if (ANY_HIT)
-              return true;
-            if (cur_object >= 0)
-              inst_hit = true;
-          }
-        }
-      }
-      else if (__float_as_uint(ra.y) & visibility) {
-        /* instance push - geom_object.h:427-443 */
-        const int object = ~tag;
-        if (COUNT)
-          cnt.instances++;
-        if (G.y & 0xff000000u)
-          push(stack, G);
-        if (Gt.y != 0u)
-          push(stack, Gt);
-        push(stack, make_uint2(BVH8_SENTINEL, 0u));
+  /* a triangle of this ray's pending group was hit (found by whichever lane ran the test) */
+  __device__ __forceinline__ void accept(float t, float u, float v, int prim)
+  {
+    hit.prim = prim;
+    hit.object = cur_object;
+    hit.u = u;
+    hit.v = v;
+    tmax = t;
+    if (cur_object >= 0)
+      inst_hit = true;
+  }
 
-        const tfm34 itfm = object_itfm(object);
-        float len;
-        const f3 oP = transform_point(itfm, P);
-        const f3 oD = normalize_len(transform_direction(itfm, D), &len);
-        ray_space_setup(rs, oP, oD);
-        world_tmax = tmax;
-        inst_len = len;
-        inst_hit = false;
-        if (tmax != FLT_MAX)
-          tmax *= len;
-        cur_object = object;
+  /* `inst_bits`: records of the group at Gt.x the leaf phase found to be visible
+   * instances.  Returns true when the traversal is complete. */
+  template<class Job>
+  __device__ __forceinline__ bool finish_step(
+      uint2 *stack, uint32_t inst_bits, TraceCounters &cnt, const Job &job, unsigned int qi)
+  {
+    if (inst_bits != 0u) {
+      /* instance push - geom_object.h:427-443 */
+      const uint32_t bit = (uint32_t)__ffs((int)inst_bits) - 1u;
+      inst_bits &= inst_bits - 1u;
+      const float4 ra = __ldg(g_scene.records + (size_t)(Gt.x + bit) * 3);
+      const int object = ~__float_as_int(ra.w);
+      if (COUNT)
+        cnt.instances++;
+      if (G.y & 0xff000000u)
+        push(stack, G);
+      if (inst_bits != 0u)
+        push(stack, make_uint2(Gt.x, inst_bits));
 
-        G = make_uint2(__float_as_uint(ra.x), 0x80000000u);
-        Gt = make_uint2(0u, 0u);
-      }
+      const tfm34 itfm = object_itfm(object);
+      float len;
+      const f3 oP = transform_point(itfm, mk3(__ldg(job.ray_P(qi))));
+      const f3 oD = normalize_len(transform_direction(itfm, mk3(__ldg(job.ray_D(qi)))), &len);
+      ray_space_setup(rs, oP, oD);
+      push(stack, make_uint2(__float_as_uint(tmax), __float_as_uint(len)));
+      push(stack, make_uint2(BVH8_SENTINEL, 0u));
+      inst_hit = false;
+      if (tmax != FLT_MAX)
+        tmax *= len;
+      cur_object = object;
+
+      G = make_uint2(__float_as_uint(ra.x), 0x80000000u);
+      return false;
     }
 
     /* pop */
@@ -322,14 +315,12 @@ template<bool ANY_HIT, bool COUNT> struct Traversal {
         G = stack[--sp];
         if (G.x == BVH8_SENTINEL) {
           /* instance pop - geom_object.h:447-460 */
-          if (inst_hit) {
-            tmax = tmax / inst_len;
-            hit.t = tmax;
-          }
-          else {
-            tmax = world_tmax;
-          }
-          ray_space_setup(rs, P, D);
+          const uint2 saved = stack[--sp]; /* (world-space limit, direction scale) */
+          if (inst_hit)
+            tmax = tmax / __uint_as_float(saved.y);
+          else
+            tmax = __uint_as_float(saved.x);
+          ray_space_setup(rs, mk3(__ldg(job.ray_P(qi))), mk3(__ldg(job.ray_D(qi))));
           cur_object = -1;
           inst_hit = false;
           continue;
@@ -340,20 +331,6 @@ template<bool ANY_HIT, bool COUNT> struct Traversal {
     return false;
   }
 };
-
-/* One ray to completion (used where no refill is wanted). */
-template<bool ANY_HIT, bool COUNT>
-__device__ __forceinline__ bool bvh8_intersect(
-    f3 P, f3 D, float tmax, uint32_t visibility, TraceHit &hit, TraceCounters &cnt)
-{
-  uint2 stack[BVH8_STACK_SIZE];
-  Traversal<ANY_HIT, COUNT> tr;
-  tr.start(P, D, tmax, visibility);
-  while (!tr.step(stack, cnt)) {
-  }
-  hit = tr.hit;
-  return hit.prim >= 0;
-}
 
 #define TRACE_BLOCK 128
 #define TRACE_WARPS (TRACE_BLOCK / 32)
@@ -393,6 +370,8 @@ __device__ __forceinline__ void trace_persistent(Job &job, unsigned int n, unsig
                                                  int refill_threshold, TraceCounters &cnt)
 {
   __shared__ float4 s_ray[TRACE_WARPS][2][2][32]; /* [warp][buffer][P|D][entry] : 8 KB */
+  /* cooperative leaf phase: pooled (record, owner lane | bit << 8) work list */
+  __shared__ uint2 s_list[TRACE_WARPS][96];
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -487,8 +466,112 @@ __device__ __forceinline__ void trace_persistent(Job &job, unsigned int n, unsig
 
     /* ---- traverse until too few lanes are busy ---- */
     while (true) {
+      if (active)
+        tr.node_phase(stack, cnt);
+
+      /* ---- cooperative leaf phase (warp-convergent) ---- */
+      uint32_t inst_bits = 0u;
+      bool finished = false;
+      while (true) {
+        const uint32_t pend = active ? tr.Gt.y : 0u;
+        /* up to three records per lane and round (a leaf holds at most three), pooled
+         * in lane order: offsets from two ballots, no scan, no atomics */
+        const unsigned int npend = min((unsigned int)__popc(pend), 3u);
+        const unsigned int b0 = __ballot_sync(0xffffffffu, (npend & 1u) != 0u);
+        const unsigned int b1 = __ballot_sync(0xffffffffu, (npend & 2u) != 0u);
+        if ((b0 | b1) == 0u)
+          break;
+        const unsigned int total = __popc(b0) + 2u * __popc(b1);
+        if (npend != 0u) {
+          uint2 *dst = s_list[warp] + (__popc(b0 & lt_mask) + 2u * __popc(b1 & lt_mask));
+          uint32_t bits = pend;
+          const uint32_t bit0 = (uint32_t)__ffs((int)bits) - 1u;
+          dst[0] = make_uint2(tr.Gt.x + bit0, lane | (bit0 << 8));
+          bits &= bits - 1u;
+          if (npend > 1u) {
+            const uint32_t bit1 = (uint32_t)__ffs((int)bits) - 1u;
+            dst[1] = make_uint2(tr.Gt.x + bit1, lane | (bit1 << 8));
+            bits &= bits - 1u;
+            if (npend > 2u) {
+              const uint32_t bit2 = (uint32_t)__ffs((int)bits) - 1u;
+              dst[2] = make_uint2(tr.Gt.x + bit2, lane | (bit2 << 8));
+              bits &= bits - 1u;
+            }
+          }
+          tr.Gt.y = bits;
+        }
+        __syncwarp();
+
+        for (unsigned int base = 0; base < total; base += 32u) {
+          const bool has = base + lane < total;
+          const uint2 ent = has ? s_list[warp][base + lane] : make_uint2(0u, lane);
+          const unsigned int owner = ent.y & 31u;
+          /* the owner's ray, in the space it is traversing in */
+          const float opx = __shfl_sync(0xffffffffu, tr.rs.P.x, owner);
+          const float opy = __shfl_sync(0xffffffffu, tr.rs.P.y, owner);
+          const float opz = __shfl_sync(0xffffffffu, tr.rs.P.z, owner);
+          const float odx = __shfl_sync(0xffffffffu, tr.rs.dir.x, owner);
+          const float ody = __shfl_sync(0xffffffffu, tr.rs.dir.y, owner);
+          const float odz = __shfl_sync(0xffffffffu, tr.rs.dir.z, owner);
+          const float otmax = __shfl_sync(0xffffffffu, tr.tmax, owner);
+          const uint32_t ovis = __shfl_sync(0xffffffffu, tr.visibility, owner);
+          bool cand = false, inst = false;
+          float t = 0.0f, u = 0.0f, v = 0.0f;
+          int tag = 0;
+          if (has) {
+            /* all three quarters of the record at once: triangles dominate, an
+             * instance record just ignores the last two */
+            const float4 *rp = g_scene.records + (size_t)ent.x * 3;
+            const float4 ra = __ldg(rp + 0);
+            const float4 rb = __ldg(rp + 1);
+            const float4 rc = __ldg(rp + 2);
+            tag = __float_as_int(ra.w);
+            if (tag >= 0) {
+              if (COUNT)
+                cnt.tris++;
+              cand = ray_triangle_intersect(mk3(opx, opy, opz), mk3(odx, ody, odz), otmax,
+                                            mk3(ra), mk3(rb), mk3(rc), &u, &v, &t) &&
+                     (__float_as_uint(rb.w) & ovis) != 0u;
+            }
+            else {
+              inst = (__float_as_uint(ra.y) & ovis) != 0u;
+            }
+          }
+          /* results go back to the owners by shuffle, candidates in list order - the
+           * order a single lane would have tested them in (a later record with the
+           * same t replaces an earlier one, like the serial loop) */
+          unsigned int hm = __ballot_sync(0xffffffffu, cand);
+          while (hm != 0u) {
+            const int src = __ffs((int)hm) - 1;
+            hm &= hm - 1u;
+            const unsigned int o = __shfl_sync(0xffffffffu, owner, src);
+            const float ht = __shfl_sync(0xffffffffu, t, src);
+            const float hu = __shfl_sync(0xffffffffu, u, src);
+            const float hv = __shfl_sync(0xffffffffu, v, src);
+            const int hp = __shfl_sync(0xffffffffu, tag, src);
+            if (lane == o && ht <= tr.tmax) {
+              tr.accept(ht, hu, hv, hp);
+              if (ANY_HIT)
+                finished = true;
+            }
+          }
+          unsigned int im = __ballot_sync(0xffffffffu, inst);
+          while (im != 0u) {
+            const int src = __ffs((int)im) - 1;
+            im &= im - 1u;
+            const unsigned int ob = __shfl_sync(0xffffffffu, ent.y, src);
+            if (lane == (ob & 31u))
+              inst_bits |= 1u << (ob >> 8);
+          }
+        }
+        if (ANY_HIT && finished)
+          tr.Gt.y = 0u;
+        __syncwarp();
+      }
+
       if (active) {
-        if (tr.step(stack, cnt)) {
+        if (finished || tr.finish_step(stack, inst_bits, cnt, job, my_qi)) {
+          tr.hit.t = tr.tmax;
           job.store(my_qi, tr.hit, tr.hit.prim >= 0);
           active = false;
         }
