@@ -261,8 +261,10 @@ def run_b200(args):
         multigpu.reduce_film(film)  # NCCL all-reduce over NVLink when world > 1
         return dev.stats()
 
+    mem0 = dev.mem_used()
     for _ in range(max(args.warmup, 0)):
         step()
+    pool_bytes = dev.mem_used() - mem0   # the path pool is allocated by the first render
 
     torch.cuda.synchronize()
     if world > 1:
@@ -435,7 +437,7 @@ def run_b200(args):
                 "workload": workload_name(desc), "width": w, "height": h, "spp_per_step": total_spp,
                 "spp_per_rank": my_spp, "triangles": desc.num_triangles, "parallelism": "sample-split x%d" % world,
                 "l2": "inputs larger than L2: %.0f MB of BVH8 + %.0f MB of path state per batch"
-                      % ((bvh["node_bytes"] + bvh["tri_bytes"]) / 1e6, 4194304 * 180 / 1e6),
+                      % ((bvh["node_bytes"] + bvh["tri_bytes"]) / 1e6, pool_bytes / 1e6),
                 "bvh8": bvh, "scene_build_s": t_scene, "upload_and_bvh8_s": t_upload,
             },
             "spp_per_s": spp_per_s,

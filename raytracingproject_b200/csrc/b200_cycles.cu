@@ -336,7 +336,7 @@ int b200_zero(b200_ctx *ctx, uint64_t dptr, size_t offset, size_t bytes)
 
 size_t b200_mem_used(b200_ctx *ctx)
 {
-  return ctx ? ctx->mem_used : 0;
+  return ctx ? ctx->mem_used + ctx->pool_bytes : 0;
 }
 
 int b200_synchronize(b200_ctx *ctx)

@@ -46,6 +46,7 @@ struct b200_ctx {
   b200_bvh_info bvh_info = {};
 
   PathPool *pool = nullptr;
+  size_t pool_bytes = 0; /* wavefront path pool (device-only memory) */
   int64_t opt_batch_paths = 0;
   int64_t opt_count_traversal = 0;
   int64_t opt_debug_slot = -1;

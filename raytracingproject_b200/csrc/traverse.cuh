@@ -20,10 +20,21 @@
 #ifndef B200_TRAVERSE_CUH
 #define B200_TRAVERSE_CUH
 
+#include <cuda_fp16.h>
+
 #include "device_scene.cuh"
 
 #define BVH8_STACK_SIZE 64
 #define BVH8_SENTINEL 0xffffffffu
+#ifndef PREFETCH
+#  define PREFETCH 0
+#endif
+#ifndef CHUNK_DIV
+#  define CHUNK_DIV 4u
+#endif
+#ifndef CHUNK_MAX
+#  define CHUNK_MAX 512u
+#endif
 
 struct TraceHit {
   float t, u, v;
@@ -51,9 +62,11 @@ CY_DEV uint32_t sign_extend_s8x4(uint32_t x)
   return r;
 }
 
-CY_DEV float byte_to_float(uint32_t x, int j)
+/* bytes 2*jj and 2*jj+1 of x as the floats (1024 + b0, 1024 + b1) */
+CY_DEV float2 bytes_to_float2(uint32_t x, int jj)
 {
-  return __uint2float_rn((x >> (8 * j)) & 0xffu);
+  const uint32_t pair = __byte_perm(x, 0x64646464u, jj ? 0x4342u : 0x4140u);
+  return __half22float2(*reinterpret_cast<const __half2 *>(&pair));
 }
 
 /* util_math_intersect.h:88-195, scalar branch.  Returns true and u,v,t on a hit
@@ -134,12 +147,24 @@ CY_DEV uint32_t bvh8_node_intersect(const RaySpace &rs,
   child_base = n1.x;
   prim_base = n1.y;
 
+  /* Plane distances  t = q * adj + org  for the quantised byte q, without integer ->
+   * float conversions (I2F runs on the XU pipe at a quarter of the FP32 rate and was
+   * the busiest pipe of this kernel): two bytes at a time are dropped under the
+   * exponent byte 0x64 by one byte-permute, which makes the fp16 pair (1024 + q0,
+   * 1024 + q1) exactly; fp16 -> fp32 is an FMA-pipe op, and the 1024 is folded into
+   * the constant term.  The test is kept conservative by an ABSOLUTE pad of ~4 ulp of
+   * the largest intermediate (covers the rounding of org, adj, 1/dir and the fma). */
   const float adjx = __uint_as_float((e_imask & 0xffu) << 23) * rs.idir.x;
   const float adjy = __uint_as_float(((e_imask >> 8) & 0xffu) << 23) * rs.idir.y;
   const float adjz = __uint_as_float(((e_imask >> 16) & 0xffu) << 23) * rs.idir.z;
-  const float orgx = (__uint_as_float(n0.x) - rs.P.x) * rs.idir.x;
-  const float orgy = (__uint_as_float(n0.y) - rs.P.y) * rs.idir.y;
-  const float orgz = (__uint_as_float(n0.z) - rs.P.z) * rs.idir.z;
+  const float orgx = fmaf(-1024.0f, adjx, (__uint_as_float(n0.x) - rs.P.x) * rs.idir.x);
+  const float orgy = fmaf(-1024.0f, adjy, (__uint_as_float(n0.y) - rs.P.y) * rs.idir.y);
+  const float orgz = fmaf(-1024.0f, adjz, (__uint_as_float(n0.z) - rs.P.z) * rs.idir.z);
+  const float padx = fmaf(1280.0f, fabsf(adjx), fabsf(orgx)) * 2.4e-7f;
+  const float pady = fmaf(1280.0f, fabsf(adjy), fabsf(orgy)) * 2.4e-7f;
+  const float padz = fmaf(1280.0f, fabsf(adjz), fabsf(orgz)) * 2.4e-7f;
+  const float onx = orgx - padx, ony = orgy - pady, onz = orgz - padz; /* near: earlier */
+  const float ofx = orgx + padx, ofy = orgy + pady, ofz = orgz + padz; /* far: later */
 
   const bool negx = rs.dir.x < 0.0f, negy = rs.dir.y < 0.0f, negz = rs.dir.z < 0.0f;
   uint32_t hitmask = 0;
@@ -161,21 +186,26 @@ CY_DEV uint32_t bvh8_node_intersect(const RaySpace &rs,
     const uint32_t zn = negz ? qhiz : qloz, zf = negz ? qloz : qhiz;
 
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const float tnx = fmaf(byte_to_float(xn, j), adjx, orgx);
-      const float tny = fmaf(byte_to_float(yn, j), adjy, orgy);
-      const float tnz = fmaf(byte_to_float(zn, j), adjz, orgz);
-      const float tfx = fmaf(byte_to_float(xf, j), adjx, orgx);
-      const float tfy = fmaf(byte_to_float(yf, j), adjy, orgy);
-      const float tfz = fmaf(byte_to_float(zf, j), adjz, orgz);
-      /* a few ulps of slack in both directions: the planes are reconstructed in
-       * a per-node frame, keep the test conservative against rounding */
-      const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f)) * 0.9999995f;
-      const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax)) * 1.0000005f;
-      if (cmin <= cmax) {
-        const uint32_t bits = (child_bits4 >> (8 * j)) & 0xffu;
-        const uint32_t index = (bit_index4 >> (8 * j)) & 0xffu;
-        hitmask |= bits << index;
+    for (int jj = 0; jj < 2; jj++) {
+      const float2 fxn = bytes_to_float2(xn, jj), fyn = bytes_to_float2(yn, jj);
+      const float2 fzn = bytes_to_float2(zn, jj), fxf = bytes_to_float2(xf, jj);
+      const float2 fyf = bytes_to_float2(yf, jj), fzf = bytes_to_float2(zf, jj);
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const int j = 2 * jj + k;
+        const float tnx = fmaf(k ? fxn.y : fxn.x, adjx, onx);
+        const float tny = fmaf(k ? fyn.y : fyn.x, adjy, ony);
+        const float tnz = fmaf(k ? fzn.y : fzn.x, adjz, onz);
+        const float tfx = fmaf(k ? fxf.y : fxf.x, adjx, ofx);
+        const float tfy = fmaf(k ? fyf.y : fyf.x, adjy, ofy);
+        const float tfz = fmaf(k ? fzf.y : fzf.x, adjz, ofz);
+        const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+        const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+        if (cmin <= cmax) {
+          const uint32_t bits = (child_bits4 >> (8 * j)) & 0xffu;
+          const uint32_t index = (bit_index4 >> (8 * j)) & 0xffu;
+          hitmask |= bits << index;
+        }
       }
     }
   }
@@ -253,6 +283,16 @@ template<bool ANY_HIT, bool COUNT> struct Traversal {
         cnt.nodes++;
       G = make_uint2(child_base, (hitmask & 0xff000000u) | imask);
       Gt = make_uint2(prim_base, hitmask & 0x00ffffffu);
+      /* the child this ray visits next is known now: pull its 80 bytes towards L1
+       * while the leaf phase runs */
+      if (PREFETCH && (G.y & 0xff000000u)) {
+        const uint32_t cbi = 31u - (uint32_t)__clz((int)G.y);
+        const uint32_t slot = (cbi - 24u) ^ (rs.oct_inv4 & 0xffu);
+        const uint32_t rel = __popc(G.y & ~(0xffffffffu << slot) & 0xffu);
+        const char *np = (const char *)(g_scene.nodes + (size_t)(G.x + rel) * 5);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(np));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(np + 64));
+      }
     }
     else {
       Gt = G;
@@ -386,11 +426,26 @@ __device__ __forceinline__ void trace_persistent(Job &job, unsigned int n, unsig
   unsigned int cur = 0, consumed = 0;
   bool drained = false;
 
+  /* Each warp claims a CHUNK of consecutive queue entries (neighbouring pixel tiles /
+   * neighbouring paths) and takes its 32-ray refills from it, so the rays a warp holds
+   * stay close together in the scene and its lanes keep fetching the same BVH nodes.
+   * The chunk shrinks with the work that is left (guided self-scheduling) so that the
+   * queue still drains evenly over the warps. */
+  const unsigned int n_warps = gridDim.x * TRACE_WARPS;
+  unsigned int chunk_next = 0, chunk_end = 0;
   auto fill = [&](unsigned int b) {
-    unsigned int bs = 0;
-    if (lane == 0)
-      bs = atomicAdd(cursor, 32u);
-    bs = __shfl_sync(0xffffffffu, bs, 0);
+    if (chunk_next >= chunk_end) {
+      unsigned int bs0 = 0, want = 0;
+      if (lane == 0) {
+        const unsigned int left = (chunk_end < n) ? n - chunk_end : 0u;
+        want = min(max((left / (CHUNK_DIV * n_warps)) & ~31u, 32u), CHUNK_MAX);
+        bs0 = atomicAdd(cursor, want);
+      }
+      chunk_next = __shfl_sync(0xffffffffu, bs0, 0);
+      chunk_end = chunk_next + __shfl_sync(0xffffffffu, want, 0);
+    }
+    const unsigned int bs = chunk_next;
+    chunk_next += 32u;
     const unsigned int av = (bs < n) ? min(32u, n - bs) : 0u;
     if (lane < av) {
       cp_async16(&s_ray[warp][b][0][lane], job.ray_P(bs + lane));

@@ -76,6 +76,7 @@ struct PathPool {
   size_t capacity = 0;
   PathSoA soa;
   void *block = nullptr;
+  size_t bytes = 0;
   WFCounters *h_counters = nullptr; /* pinned */
 };
 
@@ -882,7 +883,10 @@ static void free_pool(b200_ctx *ctx)
     cudaFreeHost(ctx->pool->h_counters);
   delete ctx->pool;
   ctx->pool = nullptr;
+  ctx->pool_bytes = 0;
 }
+
+#define PATH_POOL_BYTES_PER_PATH 224 /* 12 float4 + 7 words per path, see the carve list */
 
 static int ensure_pool(b200_ctx *ctx, size_t capacity)
 {
@@ -912,6 +916,8 @@ static int ensure_pool(b200_ctx *ctx, size_t capacity)
     return fail(ctx, e == cudaErrorMemoryAllocation ? B200_ERR_OOM : B200_ERR_CUDA,
                 std::string("path pool allocation: ") + cudaGetErrorString(e));
   }
+  pool->bytes = off;
+  ctx->pool_bytes = off;
   char *b = (char *)pool->block;
   PathSoA &s = pool->soa;
   s.ray_P_t = (float4 *)(b + o_rayP);
@@ -1068,8 +1074,23 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
     return rc;
   DeviceGuard guard(ctx->ordinal);
 
-  const size_t capacity = ctx->opt_batch_paths > 0 ? (size_t)ctx->opt_batch_paths :
-                                                     ((size_t)1 << 22);
+  /* Paths per wavefront batch.  Every kernel of a bounce is one launch over the whole
+   * batch and the persistent traversal kernels pay a drain phase per launch (warps
+   * running out of rays), so the batch is made as large as the work and the memory
+   * allow: up to 32 Mi paths (7 GB of the 180 GB), never more than a quarter of what
+   * is free, never more than the task has. */
+  size_t capacity = (size_t)ctx->opt_batch_paths;
+  if (capacity == 0) {
+    const size_t task_paths = (size_t)tile->w * tile->h * (size_t)tile->num_samples;
+    capacity = std::min<size_t>(std::max<size_t>(task_paths, (size_t)1 << 20), (size_t)1 << 25);
+    size_t free_b = 0, total_b = 0;
+    if (!(ctx->pool && ctx->pool->capacity >= capacity) &&
+        cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      const size_t held = ctx->pool ? ctx->pool->capacity * PATH_POOL_BYTES_PER_PATH : 0;
+      const size_t fit = (free_b + held) / 4 / PATH_POOL_BYTES_PER_PATH;
+      capacity = std::max<size_t>(std::min(capacity, fit), (size_t)1 << 16);
+    }
+  }
   rc = ensure_pool(ctx, std::max<size_t>(capacity, (size_t)tile->w));
   if (rc)
     return rc;

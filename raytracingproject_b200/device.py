@@ -18,7 +18,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200cycles.so")
+# B200_CYCLES_LIB: developer override to A/B-test differently compiled builds (tools/variants.sh)
+LIB_PATH = os.environ.get("B200_CYCLES_LIB") or os.path.join(_HERE, "libb200cycles.so")
 
 RAY_DTYPE = np.dtype(
     [("P", "<f4", 3), ("t", "<f4"), ("D", "<f4", 3), ("visibility", "<u4")], align=False)
