@@ -28,6 +28,9 @@
 
 #define WF_MAX_KEYS 4096
 #define WF_BLOCK 256
+/* sort keys below this are histogrammed / ranked in shared memory, the (rare) rest by
+ * global atomics */
+#define WF_SMALL_KEYS 64
 
 struct WFCounters {
   unsigned int n_active; /* paths in q_active (input of intersect_closest) */
@@ -333,20 +336,32 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_intersect_clo
 
 /* ----------------------------------------------- sort by shader (counting) */
 
-/* histogram of the sort keys: converged grid-stride pass, one atomic per distinct
- * key per warp (__match_any_sync) */
+/* histogram of the sort keys: per-block shared histogram (one shared atomic per
+ * distinct key per warp), one global atomic per key and block */
 __global__ void __launch_bounds__(WF_BLOCK) k_sort_count(PathSoA p)
 {
+  __shared__ unsigned int s_cnt[WF_SMALL_KEYS];
   WFCounters *c = p.counters;
   const unsigned int n = c->n_active;
-  for (unsigned int qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n;
+  const unsigned int lane = threadIdx.x & 31u;
+  if (threadIdx.x < WF_SMALL_KEYS)
+    s_cnt[threadIdx.x] = 0u;
+  __syncthreads();
+  const unsigned int n_round = (n + 31u) & ~31u; /* whole warps stay converged */
+  for (unsigned int qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n_round;
        qi += gridDim.x * blockDim.x) {
-    const unsigned int key = p.key[qi];
-    const unsigned int lane = threadIdx.x & 31u;
-    const unsigned int peers = __match_any_sync(__activemask(), key);
-    if (lane == (unsigned)(__ffs(peers) - 1))
-      atomicAdd(&c->hist[key], __popc(peers));
+    const unsigned int key = (qi < n) ? p.key[qi] : 0xffffffffu;
+    const unsigned int peers = __match_any_sync(0xffffffffu, key);
+    if (lane == (unsigned)(__ffs(peers) - 1) && qi < n) {
+      if (key < WF_SMALL_KEYS)
+        atomicAdd(&s_cnt[key], __popc(peers));
+      else
+        atomicAdd(&c->hist[key], __popc(peers));
+    }
   }
+  __syncthreads();
+  if (threadIdx.x < WF_SMALL_KEYS && s_cnt[threadIdx.x] != 0u)
+    atomicAdd(&c->hist[threadIdx.x], s_cnt[threadIdx.x]);
 }
 
 __global__ void k_sort_scan(PathSoA p, int num_keys)
@@ -369,22 +384,56 @@ __global__ void k_sort_scan(PathSoA p, int num_keys)
   }
 }
 
+/* Counting-sort scatter.  A block ranks a tile of SORT_ITEMS * WF_BLOCK queue entries
+ * in shared memory (one shared atomic per distinct key per warp, __match_any_sync) and
+ * reserves its share of every key's output range with ONE global atomic per key and
+ * tile, so the few hot counters (one shader, "miss") are not hammered by every warp.
+ * The order inside a key is arbitrary - nothing downstream depends on it (the film is
+ * summed per pixel in sample order). */
+#define SORT_ITEMS 8
 __global__ void __launch_bounds__(WF_BLOCK) k_sort_scatter(PathSoA p)
 {
+  __shared__ unsigned int s_cnt[WF_SMALL_KEYS], s_base[WF_SMALL_KEYS];
   WFCounters *c = p.counters;
   const unsigned int n = c->n_active;
-  for (unsigned int qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n;
-       qi += gridDim.x * blockDim.x) {
-    const unsigned int key = p.key[qi];
-    const unsigned int lane = threadIdx.x & 31u;
-    const unsigned int peers = __match_any_sync(__activemask(), key);
-    const unsigned int leader = __ffs(peers) - 1u;
-    unsigned int base = 0;
-    if (lane == leader)
-      base = atomicAdd(&c->cursor[key], __popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    const unsigned int pos = c->offsets[key] + base + __popc(peers & ((1u << lane) - 1u));
-    p.q_sorted[pos] = (int)qi;
+  const unsigned int lane = threadIdx.x & 31u;
+  const unsigned int lt_mask = (1u << lane) - 1u;
+  const unsigned int tile_size = SORT_ITEMS * WF_BLOCK;
+  for (unsigned int tile = blockIdx.x * tile_size; tile < n; tile += gridDim.x * tile_size) {
+    if (threadIdx.x < WF_SMALL_KEYS)
+      s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    unsigned int key[SORT_ITEMS], rank[SORT_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; k++) {
+      const unsigned int qi = tile + k * WF_BLOCK + threadIdx.x;
+      key[k] = (qi < n) ? p.key[qi] : 0xffffffffu;
+      const unsigned int peers = __match_any_sync(0xffffffffu, key[k]);
+      const unsigned int leader = __ffs(peers) - 1u;
+      unsigned int base = 0;
+      if (lane == leader && qi < n) {
+        if (key[k] < WF_SMALL_KEYS)
+          base = atomicAdd(&s_cnt[key[k]], __popc(peers));
+        else /* many-shader scenes: straight to the global cursor, final position */
+          base = atomicAdd(&c->cursor[key[k]], __popc(peers));
+      }
+      base = __shfl_sync(0xffffffffu, base, leader);
+      rank[k] = base + __popc(peers & lt_mask);
+    }
+    __syncthreads();
+    if (threadIdx.x < WF_SMALL_KEYS && s_cnt[threadIdx.x] != 0u)
+      s_base[threadIdx.x] = atomicAdd(&c->cursor[threadIdx.x], s_cnt[threadIdx.x]);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; k++) {
+      const unsigned int qi = tile + k * WF_BLOCK + threadIdx.x;
+      if (qi < n) {
+        const unsigned int kk = key[k];
+        const unsigned int pos = c->offsets[kk] + rank[k] + (kk < WF_SMALL_KEYS ? s_base[kk] : 0u);
+        p.q_sorted[pos] = (int)qi;
+      }
+    }
+    __syncthreads();
   }
 }
 
