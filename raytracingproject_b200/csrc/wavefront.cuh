@@ -108,6 +108,53 @@ CY_DEV unsigned int warp_append(unsigned int *counter, bool pred)
   return base + __popc(mask & ((1u << lane) - 1u));
 }
 
+/* One atomic per BLOCK for up to two queues at once: the queue counters are single
+ * addresses, and same-address atomics with a return value serialise in L2 at about
+ * 2 ns each - per warp that was the whole cost of init_from_camera and a third of
+ * shade_surface.  Must be reached by every thread of the block (WF_BLOCK threads). */
+CY_DEV void block_append2(unsigned int *counter_a, bool pred_a, unsigned int *counter_b,
+                          bool pred_b, unsigned int *slot_a, unsigned int *slot_b)
+{
+  __shared__ unsigned int s_a[WF_BLOCK / 32], s_b[WF_BLOCK / 32];
+  const unsigned int lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  const unsigned int lt_mask = (1u << lane) - 1u;
+  const unsigned int ma = __ballot_sync(0xffffffffu, pred_a);
+  const unsigned int mb = __ballot_sync(0xffffffffu, pred_b);
+  if (lane == 0) {
+    s_a[w] = __popc(ma);
+    s_b[w] = __popc(mb);
+  }
+  __syncthreads();
+  if (w == 0) {
+    /* lanes 0..7 scan queue a, lanes 16..23 queue b */
+    const unsigned int j = lane & 15u;
+    const bool second = lane >= 16u;
+    const unsigned int v = (j < WF_BLOCK / 32) ? (second ? s_b[j] : s_a[j]) : 0u;
+    unsigned int incl = v;
+#pragma unroll
+    for (int o = 1; o < WF_BLOCK / 32; o <<= 1) {
+      const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o, 16);
+      if (j >= (unsigned)o)
+        incl += up;
+    }
+    const unsigned int total = __shfl_sync(0xffffffffu, incl, WF_BLOCK / 32 - 1, 16);
+    unsigned int base = 0;
+    if (j == 0 && total != 0u)
+      base = atomicAdd(second ? counter_b : counter_a, total);
+    base = __shfl_sync(0xffffffffu, base, 0, 16);
+    if (j < WF_BLOCK / 32) {
+      if (second)
+        s_b[j] = base + incl - v;
+      else
+        s_a[j] = base + incl - v;
+    }
+  }
+  __syncthreads();
+  *slot_a = s_a[w] + __popc(ma & lt_mask);
+  *slot_b = s_b[w] + __popc(mb & lt_mask);
+  __syncthreads(); /* the arrays are reused by the next call */
+}
+
 CY_DEV void state_load(const PathSoA &p, int i, PathStateG &s)
 {
   const uint4 a = p.stateA[i];
@@ -246,39 +293,46 @@ __global__ void __launch_bounds__(WF_BLOCK)
 {
   const unsigned int npix = (unsigned)bp.w * (unsigned)bp.h;
   const unsigned int n = npix * (unsigned)bp.nsamples;
-  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const unsigned int pix = i % npix;
-    const int s = (int)(i / npix);
-    int x, y;
-    batch_pixel(bp, pix, &x, &y);
-    const int sample = bp.sample0 + s;
+  /* block-uniform loop: block_append2 has barriers */
+  for (unsigned int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
+    const unsigned int i = i0 + threadIdx.x;
+    float t = 0.0f;
+    f3 P = zero3(), D = zero3();
+    uint32_t vis = 0;
+    if (i < n) {
+      const unsigned int pix = i % npix;
+      const int s = (int)(i / npix);
+      int x, y;
+      batch_pixel(bp, pix, &x, &y);
+      const int sample = bp.sample0 + s;
 
-    uint32_t rng_hash;
-    f3 P, D;
-    const float t = camera_ray(x, y, sample, &rng_hash, &P, &D);
+      uint32_t rng_hash;
+      t = camera_ray(x, y, sample, &rng_hash, &P, &D);
 
-    /* path_state_init - kernel_path_state.h:19-70 */
-    PathStateG st;
-    st.flag = CY_PATH_RAY_CAMERA | CY_PATH_RAY_MIS_SKIP | CY_PATH_RAY_TRANSPARENT_BACKGROUND;
-    st.rng_hash = rng_hash;
-    st.rng_offset = CY_PRNG_BASE_NUM;
-    st.sample = sample;
-    st.bounce = st.diffuse_bounce = st.glossy_bounce = st.transmission_bounce = 0;
-    st.transparent_bounce = 0;
-    st.min_ray_pdf = FLT_MAX;
-    state_store(p, i, st);
+      /* path_state_init - kernel_path_state.h:19-70 */
+      PathStateG st;
+      st.flag = CY_PATH_RAY_CAMERA | CY_PATH_RAY_MIS_SKIP | CY_PATH_RAY_TRANSPARENT_BACKGROUND;
+      st.rng_hash = rng_hash;
+      st.rng_offset = CY_PRNG_BASE_NUM;
+      st.sample = sample;
+      st.bounce = st.diffuse_bounce = st.glossy_bounce = st.transmission_bounce = 0;
+      st.transparent_bounce = 0;
+      st.min_ray_pdf = FLT_MAX;
+      state_store(p, i, st);
+      vis = path_state_ray_visibility(st.flag);
 
-    p.ray_pdf[i] = 0.0f;
-    p.throughput[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);    /* ray_t = 0 */
-    /* kernel_path_trace returns before kernel_write_result when ray.t == 0
-     * (kernel_path.h:668-670): transparent = 1 makes the film add (0,0,0,0). */
-    p.L[i] = make_float4(0.0f, 0.0f, 0.0f, (t == 0.0f) ? 1.0f : 0.0f);
-    const unsigned int slot = warp_append(&p.counters->n_active, t != 0.0f);
+      p.ray_pdf[i] = 0.0f;
+      p.throughput[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);    /* ray_t = 0 */
+      /* kernel_path_trace returns before kernel_write_result when ray.t == 0
+       * (kernel_path.h:668-670): transparent = 1 makes the film add (0,0,0,0). */
+      p.L[i] = make_float4(0.0f, 0.0f, 0.0f, (t == 0.0f) ? 1.0f : 0.0f);
+    }
+    unsigned int slot, unused;
+    block_append2(&p.counters->n_active, t != 0.0f, &p.counters->n_active, false, &slot, &unused);
     if (t != 0.0f) {
       p.q_active[slot] = (int)i;
       p.ray_P_t[slot] = make_float4(P.x, P.y, P.z, t);
-      p.ray_D[slot] = make_float4(D.x, D.y, D.z,
-                                  __uint_as_float(path_state_ray_visibility(st.flag)));
+      p.ray_D[slot] = make_float4(D.x, D.y, D.z, __uint_as_float(vis));
     }
   }
 }
@@ -742,13 +796,13 @@ __global__ void __launch_bounds__(WF_BLOCK) k_shade_surface(PathSoA p, int num_k
         state_store(p, i, st);
       }
     }
-    const unsigned int s_next = warp_append(&c->n_next, want_next);
+    unsigned int s_next, s_sh;
+    block_append2(&c->n_next, want_next, &c->n_shadow, want_shadow, &s_next, &s_sh);
     if (want_next) {
       p.q_next[s_next] = i;
       p.nray_P_t[s_next] = out_ray_P;
       p.nray_D[s_next] = out_ray_D;
     }
-    const unsigned int s_sh = warp_append(&c->n_shadow, want_shadow);
     if (want_shadow) {
       p.q_shadow[s_sh] = i;
       p.sh_P_t[s_sh] = out_sh_P;
