@@ -28,6 +28,10 @@ WANT = [
     "sm__inst_executed.sum", "smsp__inst_executed.sum",
     "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum",
     "local_load_bytes", "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
 ]
 
 
@@ -74,6 +78,23 @@ def report(tag, rep):
                 f.write("%-78s %s\n" % (w, [r[i] for r in rows[1:]]))
         if ki is not None:
             f.write("kernels: %s\n" % [r[ki][:60] for r in rows[2:]])
+    if name == "prof_closest":
+        # bench.py reports this as roofline.traffic (DRAM bytes per launch of the dominant kernel)
+        import json
+
+        def col(metric):
+            i = hdr.index(metric)
+            unit = rows[1][i]
+            mul = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+            return [float(r[i].replace(",", "")) * mul for r in rows[2:]]
+        rd, wr = col("dram__bytes_read.sum"), col("dram__bytes_write.sum")
+        per = [a + b for a, b in zip(rd, wr)]
+        json.dump({"kernel": "k_intersect_closest", "launches_captured": len(per),
+                   "dram_bytes_per_launch": sum(per) / len(per), "per_launch": per,
+                   "workload": "terrain_1002k 1920x1080, 16 spp batch (33.2 M camera rays, then the "
+                               "bounce rays), ncu --set full --clock-control none",
+                   "source": "profiles/%s_prof_closest.txt" % tag},
+                  open(os.path.join(ROOT, "profiles", "traffic_intersect_closest.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":
