@@ -111,6 +111,13 @@ CY_DEV bool ray_triangle_intersect(
   return true;
 }
 
+CY_DEV float rcp_approx(float x)
+{
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 struct RaySpace {
   f3 P, dir, idir;
   uint32_t oct_inv4;
@@ -120,7 +127,9 @@ CY_DEV void ray_space_setup(RaySpace &rs, f3 P, f3 D)
 {
   rs.P = P;
   rs.dir = bvh_clamp_direction(D);
-  rs.idir = mk3(1.0f / rs.dir.x, 1.0f / rs.dir.y, 1.0f / rs.dir.z);
+  /* 1/dir only feeds the (conservative, padded) box test, never the triangle test: the
+   * one-instruction approximate reciprocal (about 1 ulp) instead of three IEEE divisions */
+  rs.idir = mk3(rcp_approx(rs.dir.x), rcp_approx(rs.dir.y), rcp_approx(rs.dir.z));
   rs.oct_inv4 = ((rs.dir.x < 0.0f) ? 0u : 0x04040404u) | ((rs.dir.y < 0.0f) ? 0u : 0x02020202u) |
                 ((rs.dir.z < 0.0f) ? 0u : 0x01010101u);
 }
@@ -152,17 +161,18 @@ CY_DEV uint32_t bvh8_node_intersect(const RaySpace &rs,
    * the busiest pipe of this kernel): two bytes at a time are dropped under the
    * exponent byte 0x64 by one byte-permute, which makes the fp16 pair (1024 + q0,
    * 1024 + q1) exactly; fp16 -> fp32 is an FMA-pipe op, and the 1024 is folded into
-   * the constant term.  The test is kept conservative by an ABSOLUTE pad of ~4 ulp of
-   * the largest intermediate (covers the rounding of org, adj, 1/dir and the fma). */
+   * the constant term.  The test is kept conservative by an ABSOLUTE pad of ~8 ulp of
+   * the largest intermediate (covers the rounding of org, adj, the approximate 1/dir and
+   * the fma). */
   const float adjx = __uint_as_float((e_imask & 0xffu) << 23) * rs.idir.x;
   const float adjy = __uint_as_float(((e_imask >> 8) & 0xffu) << 23) * rs.idir.y;
   const float adjz = __uint_as_float(((e_imask >> 16) & 0xffu) << 23) * rs.idir.z;
   const float orgx = fmaf(-1024.0f, adjx, (__uint_as_float(n0.x) - rs.P.x) * rs.idir.x);
   const float orgy = fmaf(-1024.0f, adjy, (__uint_as_float(n0.y) - rs.P.y) * rs.idir.y);
   const float orgz = fmaf(-1024.0f, adjz, (__uint_as_float(n0.z) - rs.P.z) * rs.idir.z);
-  const float padx = fmaf(1280.0f, fabsf(adjx), fabsf(orgx)) * 2.4e-7f;
-  const float pady = fmaf(1280.0f, fabsf(adjy), fabsf(orgy)) * 2.4e-7f;
-  const float padz = fmaf(1280.0f, fabsf(adjz), fabsf(orgz)) * 2.4e-7f;
+  const float padx = fmaf(1280.0f, fabsf(adjx), fabsf(orgx)) * 4.8e-7f;
+  const float pady = fmaf(1280.0f, fabsf(adjy), fabsf(orgy)) * 4.8e-7f;
+  const float padz = fmaf(1280.0f, fabsf(adjz), fabsf(orgz)) * 4.8e-7f;
   const float onx = orgx - padx, ony = orgy - pady, onz = orgz - padz; /* near: earlier */
   const float ofx = orgx + padx, ofy = orgy + pady, ofz = orgz + padz; /* far: later */
 
@@ -537,8 +547,9 @@ __device__ __forceinline__ void trace_persistent(Job &job, unsigned int n, unsig
         if ((b0 | b1) == 0u)
           break;
         const unsigned int total = __popc(b0) + 2u * __popc(b1);
+        const unsigned int off = __popc(b0 & lt_mask) + 2u * __popc(b1 & lt_mask);
         if (npend != 0u) {
-          uint2 *dst = s_list[warp] + (__popc(b0 & lt_mask) + 2u * __popc(b1 & lt_mask));
+          uint2 *dst = s_list[warp] + off;
           uint32_t bits = pend;
           const uint32_t bit0 = (uint32_t)__ffs((int)bits) - 1u;
           dst[0] = make_uint2(tr.Gt.x + bit0, lane | (bit0 << 8));
@@ -610,13 +621,23 @@ __device__ __forceinline__ void trace_persistent(Job &job, unsigned int n, unsig
                 finished = true;
             }
           }
-          unsigned int im = __ballot_sync(0xffffffffu, inst);
-          while (im != 0u) {
-            const int src = __ffs((int)im) - 1;
-            im &= im - 1u;
-            const unsigned int ob = __shfl_sync(0xffffffffu, ent.y, src);
-            if (lane == (ob & 31u))
-              inst_bits |= 1u << (ob >> 8);
+          /* visible instance records: every owner picks the flags of its own list
+           * entries out of one ballot (entry off + k was tested by lane off + k - base) */
+          const unsigned int im = __ballot_sync(0xffffffffu, inst);
+          if (im != 0u && npend != 0u) {
+            const int rel = (int)off - (int)base;
+            uint32_t mine = (rel >= 0) ? (rel < 32 ? im >> rel : 0u) : (rel > -32 ? im << (-rel) : 0u);
+            mine &= (1u << npend) - 1u;
+            if (mine != 0u) {
+              uint32_t pb = pend;
+              const uint32_t k0 = pb & (0u - pb);
+              pb &= pb - 1u;
+              const uint32_t k1 = pb & (0u - pb);
+              pb &= pb - 1u;
+              const uint32_t k2 = pb & (0u - pb);
+              inst_bits |= ((mine & 1u) ? k0 : 0u) | ((mine & 2u) ? k1 : 0u) |
+                           ((mine & 4u) ? k2 : 0u);
+            }
           }
         }
         if (ANY_HIT && finished)

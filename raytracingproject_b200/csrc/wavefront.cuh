@@ -28,6 +28,9 @@
 
 #define WF_MAX_KEYS 4096
 #define WF_BLOCK 256
+#ifndef WF_OCTANT_SORT
+#  define WF_OCTANT_SORT 1
+#endif
 /* sort keys below this are histogrammed / ranked in shared memory, the (rare) rest by
  * global atomics */
 #define WF_SMALL_KEYS 64
@@ -111,48 +114,73 @@ CY_DEV unsigned int warp_append(unsigned int *counter, bool pred)
 /* One atomic per BLOCK for up to two queues at once: the queue counters are single
  * addresses, and same-address atomics with a return value serialise in L2 at about
  * 2 ns each - per warp that was the whole cost of init_from_camera and a third of
- * shade_surface.  Must be reached by every thread of the block (WF_BLOCK threads). */
-CY_DEV void block_append2(unsigned int *counter_a, bool pred_a, unsigned int *counter_b,
-                          bool pred_b, unsigned int *slot_a, unsigned int *slot_b)
+ * shade_surface.  Must be reached by every thread of the block (WF_BLOCK threads).
+ *
+ * Queue a is additionally ordered by `bin_a` (0..7) inside the block's slot range:
+ * shade_surface passes the direction octant of the new ray, so that the 32 consecutive
+ * rays a traversal warp stages share origin neighbourhood AND child visiting order. */
+CY_DEV void block_append2(unsigned int *counter_a, bool pred_a, unsigned int bin_a,
+                          unsigned int *counter_b, bool pred_b, unsigned int *slot_a,
+                          unsigned int *slot_b)
 {
-  __shared__ unsigned int s_a[WF_BLOCK / 32], s_b[WF_BLOCK / 32];
+  constexpr int NW = WF_BLOCK / 32;
+  static_assert(NW == 8, "the scan below covers an 8 x 8 table with two entries per lane");
+  __shared__ unsigned int s_tab[9][NW]; /* rows 0..7: queue a by bin, row 8: queue b */
   const unsigned int lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
   const unsigned int lt_mask = (1u << lane) - 1u;
-  const unsigned int ma = __ballot_sync(0xffffffffu, pred_a);
+  if (threadIdx.x < 9 * NW)
+    (&s_tab[0][0])[threadIdx.x] = 0u;
+  __syncthreads();
+  const unsigned int key_a = pred_a ? (bin_a & 7u) : 8u;
+  const unsigned int peers = __match_any_sync(0xffffffffu, key_a);
   const unsigned int mb = __ballot_sync(0xffffffffu, pred_b);
-  if (lane == 0) {
-    s_a[w] = __popc(ma);
-    s_b[w] = __popc(mb);
-  }
+  if (pred_a && lane == (unsigned)(__ffs(peers) - 1))
+    s_tab[key_a][w] = __popc(peers);
+  if (lane == 0)
+    s_tab[8][w] = __popc(mb);
   __syncthreads();
   if (w == 0) {
-    /* lanes 0..7 scan queue a, lanes 16..23 queue b */
-    const unsigned int j = lane & 15u;
-    const bool second = lane >= 16u;
-    const unsigned int v = (j < WF_BLOCK / 32) ? (second ? s_b[j] : s_a[j]) : 0u;
-    unsigned int incl = v;
+    /* queue a: exclusive scan of the 8 x NW table in (bin, warp) order, two entries a lane */
+    unsigned int *tab = &s_tab[0][0];
+    const unsigned int v0 = tab[lane], v1 = tab[lane + 32];
+    unsigned int i0 = v0, i1 = v1;
 #pragma unroll
-    for (int o = 1; o < WF_BLOCK / 32; o <<= 1) {
-      const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o, 16);
-      if (j >= (unsigned)o)
-        incl += up;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int u0 = __shfl_up_sync(0xffffffffu, i0, o);
+      const unsigned int u1 = __shfl_up_sync(0xffffffffu, i1, o);
+      if (lane >= (unsigned)o) {
+        i0 += u0;
+        i1 += u1;
+      }
     }
-    const unsigned int total = __shfl_sync(0xffffffffu, incl, WF_BLOCK / 32 - 1, 16);
-    unsigned int base = 0;
-    if (j == 0 && total != 0u)
-      base = atomicAdd(second ? counter_b : counter_a, total);
-    base = __shfl_sync(0xffffffffu, base, 0, 16);
-    if (j < WF_BLOCK / 32) {
-      if (second)
-        s_b[j] = base + incl - v;
-      else
-        s_a[j] = base + incl - v;
+    const unsigned int t0 = __shfl_sync(0xffffffffu, i0, 31);
+    const unsigned int ta = t0 + __shfl_sync(0xffffffffu, i1, 31);
+    /* queue b: lanes 0..NW-1 */
+    const unsigned int vb = (lane < NW) ? s_tab[8][lane] : 0u;
+    unsigned int ib = vb;
+#pragma unroll
+    for (int o = 1; o < NW; o <<= 1) {
+      const unsigned int ub = __shfl_up_sync(0xffffffffu, ib, o);
+      if (lane >= (unsigned)o)
+        ib += ub;
     }
+    const unsigned int tb = __shfl_sync(0xffffffffu, ib, NW - 1);
+    unsigned int base_a = 0, base_b = 0;
+    if (lane == 0 && ta != 0u)
+      base_a = atomicAdd(counter_a, ta);
+    if (lane == 1 && tb != 0u)
+      base_b = atomicAdd(counter_b, tb);
+    base_a = __shfl_sync(0xffffffffu, base_a, 0);
+    base_b = __shfl_sync(0xffffffffu, base_b, 1);
+    tab[lane] = base_a + i0 - v0;
+    tab[lane + 32] = base_a + t0 + i1 - v1;
+    if (lane < NW)
+      s_tab[8][lane] = base_b + ib - vb;
   }
   __syncthreads();
-  *slot_a = s_a[w] + __popc(ma & lt_mask);
-  *slot_b = s_b[w] + __popc(mb & lt_mask);
-  __syncthreads(); /* the arrays are reused by the next call */
+  *slot_a = pred_a ? s_tab[key_a][w] + __popc(peers & lt_mask) : 0u;
+  *slot_b = s_tab[8][w] + __popc(mb & lt_mask);
+  __syncthreads(); /* the table is reused by the next call */
 }
 
 CY_DEV void state_load(const PathSoA &p, int i, PathStateG &s)
@@ -328,7 +356,8 @@ __global__ void __launch_bounds__(WF_BLOCK)
       p.L[i] = make_float4(0.0f, 0.0f, 0.0f, (t == 0.0f) ? 1.0f : 0.0f);
     }
     unsigned int slot, unused;
-    block_append2(&p.counters->n_active, t != 0.0f, &p.counters->n_active, false, &slot, &unused);
+    block_append2(&p.counters->n_active, t != 0.0f, 0u, &p.counters->n_active, false, &slot,
+                  &unused);
     if (t != 0.0f) {
       p.q_active[slot] = (int)i;
       p.ray_P_t[slot] = make_float4(P.x, P.y, P.z, t);
@@ -797,7 +826,9 @@ __global__ void __launch_bounds__(WF_BLOCK) k_shade_surface(PathSoA p, int num_k
       }
     }
     unsigned int s_next, s_sh;
-    block_append2(&c->n_next, want_next, &c->n_shadow, want_shadow, &s_next, &s_sh);
+    const unsigned int octant = (out_ray_D.x < 0.0f ? 1u : 0u) | (out_ray_D.y < 0.0f ? 2u : 0u) |
+                                (out_ray_D.z < 0.0f ? 4u : 0u);
+    block_append2(&c->n_next, want_next, WF_OCTANT_SORT ? octant : 0u, &c->n_shadow, want_shadow, &s_next, &s_sh);
     if (want_next) {
       p.q_next[s_next] = i;
       p.nray_P_t[s_next] = out_ray_P;
