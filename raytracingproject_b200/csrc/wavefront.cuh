@@ -69,7 +69,7 @@ struct PathSoA {
   unsigned int *key;  /* [qi] sort key: 0 miss, 1 + shader */
   int *q_active; /* [qi] -> path */
   int *q_next;   /* next bounce's q_active */
-  int *q_sorted; /* queue positions qi ordered by key */
+  int2 *q_sorted; /* (queue position qi, path index) ordered by key */
   int *q_shadow; /* [shadow queue] -> path */
   WFCounters *counters;
   /* debugging aid: when debug != NULL the path in slot debug_slot records 32 floats
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_sort_scatter(PathSoA p)
       if (qi < n) {
         const unsigned int kk = key[k];
         const unsigned int pos = c->offsets[kk] + rank[k] + (kk < WF_SMALL_KEYS ? s_base[kk] : 0u);
-        p.q_sorted[pos] = (int)qi;
+        p.q_sorted[pos] = make_int2((int)qi, p.q_active[qi]);
       }
     }
     __syncthreads();
@@ -566,8 +566,8 @@ __global__ void __launch_bounds__(WF_BLOCK) k_shade_background(PathSoA p)
   const unsigned int n = c->offsets[1]; /* key 0 segment */
   for (unsigned int qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n;
        qi += gridDim.x * blockDim.x) {
-    const int qpos = p.q_sorted[qi];
-    const int i = p.q_active[qpos];
+    const int2 qs = p.q_sorted[qi];
+    const int qpos = qs.x, i = qs.y;
     const float4 r0 = p.ray_P_t[qpos];
     const float4 r1 = p.ray_D[qpos];
     const float4 tp = p.throughput[i];
@@ -605,7 +605,10 @@ __global__ void __launch_bounds__(WF_BLOCK) k_shade_background(PathSoA p)
 
 /* -------------------------------------------------------- shade_surface */
 
-__global__ void __launch_bounds__(WF_BLOCK) k_shade_surface(PathSoA p, int num_keys)
+#ifndef SHADE_MIN_BLOCKS
+#  define SHADE_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS) k_shade_surface(PathSoA p, int num_keys)
 {
   WFCounters *c = p.counters;
   const unsigned int begin = c->offsets[1];
@@ -622,8 +625,9 @@ __global__ void __launch_bounds__(WF_BLOCK) k_shade_surface(PathSoA p, int num_k
     float4 out_ray_P = make_float4(0.0f, 0.0f, 0.0f, 0.0f), out_ray_D = out_ray_P;
     float4 out_sh_P = out_ray_P, out_sh_D = out_ray_P, out_sh_C = out_ray_P;
     if (valid) {
-      const int qpos = p.q_sorted[begin + k];
-      i = p.q_active[qpos];
+      const int2 qs = p.q_sorted[begin + k];
+      const int qpos = qs.x;
+      i = qs.y;
       const float4 r0 = p.ray_P_t[qpos];
       const float4 r1 = p.ray_D[qpos];
       const float4 tp = p.throughput[i];
@@ -1020,7 +1024,7 @@ static void free_pool(b200_ctx *ctx)
   ctx->pool_bytes = 0;
 }
 
-#define PATH_POOL_BYTES_PER_PATH 224 /* 12 float4 + 7 words per path, see the carve list */
+#define PATH_POOL_BYTES_PER_PATH 228 /* 12 float4 + 8 words per path, see the carve list */
 
 static int ensure_pool(b200_ctx *ctx, size_t capacity)
 {
@@ -1041,7 +1045,7 @@ static int ensure_pool(b200_ctx *ctx, size_t capacity)
   size_t o_rayP = carve(n * 16), o_rayD = carve(n * 16), o_hit = carve(n * 16),
          o_hobj = carve(n * 4), o_thr = carve(n * 16), o_L = carve(n * 16), o_sA = carve(n * 16),
          o_sB = carve(n * 16), o_shP = carve(n * 16), o_shD = carve(n * 16), o_shC = carve(n * 16),
-         o_key = carve(n * 4), o_qa = carve(n * 4), o_qn = carve(n * 4), o_qs = carve(n * 4),
+         o_key = carve(n * 4), o_qa = carve(n * 4), o_qn = carve(n * 4), o_qs = carve(n * 8),
          o_qsh = carve(n * 4), o_cnt = carve(sizeof(WFCounters));
   cudaError_t e = cudaMalloc(&pool->block, off);
   if (e != cudaSuccess) {
@@ -1071,7 +1075,7 @@ static int ensure_pool(b200_ctx *ctx, size_t capacity)
   s.key = (unsigned int *)(b + o_key);
   s.q_active = (int *)(b + o_qa);
   s.q_next = (int *)(b + o_qn);
-  s.q_sorted = (int *)(b + o_qs);
+  s.q_sorted = (int2 *)(b + o_qs);
   s.q_shadow = (int *)(b + o_qsh);
   s.counters = (WFCounters *)(b + o_cnt);
   if (cudaMallocHost(&pool->h_counters, sizeof(WFCounters)) != cudaSuccess) {
