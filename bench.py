@@ -469,6 +469,7 @@ class _RawCuda:
 
 def mem_as_tensor(mem, like):
     """View a C-ABI device allocation as a torch tensor (for the NCCL film reduce)."""
+    import torch
     return torch.as_tensor(_RawCuda(mem.device_pointer, like.numel()), device=like.device)
 
 
