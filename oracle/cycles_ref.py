@@ -61,6 +61,7 @@ def lib():
         L.ref_scene_data.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.ref_render.argtypes = [
             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+        L.ref_film_convert.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.ref_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.ref_camera_rays.argtypes = [
             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -190,6 +191,15 @@ class RefScene:
             self._h, int(start_sample), int(num_samples), int(tile_size), int(accumulate),
             out.ctypes.data, C.byref(sec)))
         return out, sec.value
+
+    def film_convert(self, num_samples, half_float=False):
+        """DeviceTask::FILM_CONVERT of the last rendered film on this scene's device:
+        (h, w, 4) uint8 display bytes, or (h, w, 4) uint16 half bit patterns."""
+        w, h = self.width, self.height
+        out = np.empty((h, w, 4), dtype=np.uint16 if half_float else np.uint8)
+        self._check(self._L.ref_film_convert(self._h, int(num_samples), int(bool(half_float)),
+                                             out.ctypes.data))
+        return out
 
     def path_dump(self, sample, x, y):
         """(16, 32) per-bounce debug records of one reference path (ref_probe_path_dump)."""

@@ -413,6 +413,63 @@ int ref_render(ref_scene *rs,
   return 0;
 }
 
+/* DeviceTask::FILM_CONVERT over the film of the last ref_render (what
+ * DisplayBuffer::draw_set / Session::tonemap issue, render/buffers.cpp, session.cpp):
+ * `out` receives w*h uchar4 (half_float = 0) or w*h half4 (half_float = 1).  Works on
+ * whichever Device the scene was created on - the reference CPUDevice or an external
+ * one - so the same call produces the oracle bytes and drives the device under test. */
+int ref_film_convert(ref_scene *rs, int num_samples, int half_float, void *out)
+{
+  if (!rs->buffers) {
+    rs->error = "film_convert: render first";
+    return 1;
+  }
+  Device *device = rs->device;
+  RenderBuffers *buffers = rs->buffers;
+  const int width = buffers->params.width, height = buffers->params.height;
+  buffers->buffer.copy_to_device();
+
+  device_vector<uchar4> rgba_byte(device, "display_rgba_byte", MEM_READ_WRITE);
+  device_vector<half4> rgba_half(device, "display_rgba_half", MEM_READ_WRITE);
+  DeviceTask task(DeviceTask::FILM_CONVERT);
+  task.x = 0;
+  task.y = 0;
+  task.w = width;
+  task.h = height;
+  task.sample = num_samples - 1; /* sample_scale = 1 / (task.sample + 1) */
+  buffers->params.get_offset_stride(task.offset, task.stride);
+  task.buffer = buffers->buffer.device_pointer;
+  if (half_float) {
+    rgba_half.alloc(width, height);
+    rgba_half.zero_to_device();
+    task.rgba_half = rgba_half.device_pointer;
+  }
+  else {
+    rgba_byte.alloc(width, height);
+    rgba_byte.zero_to_device();
+    task.rgba_byte = rgba_byte.device_pointer;
+  }
+  const unsigned int mxcsr = _mm_getcsr();
+  device->task_add(task);
+  device->task_wait();
+  _mm_setcsr(mxcsr);
+  if (device->have_error()) {
+    rs->error = device->error_message();
+    return 1;
+  }
+  if (half_float) {
+    rgba_half.copy_from_device(0, width, height);
+    memcpy(out, rgba_half.data(), sizeof(half4) * (size_t)width * height);
+    rgba_half.free();
+  }
+  else {
+    rgba_byte.copy_from_device(0, width, height);
+    memcpy(out, rgba_byte.data(), sizeof(uchar4) * (size_t)width * height);
+    rgba_byte.free();
+  }
+  return 0;
+}
+
 /* ---- kernel probes (CPU device only) ---- */
 
 /* The reference renders with FTZ + DAZ on every worker thread

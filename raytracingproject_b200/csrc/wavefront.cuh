@@ -962,34 +962,62 @@ CY_DEV float color_linear_to_srgb(float c)
   else
     return 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
 }
+struct FilmDisplay {
+  int pass_stride;
+  int display_pass_stride;   /* float offset of the displayed pass inside a pixel */
+  int use_pass_alpha;        /* KernelFilm::use_display_pass_alpha */
+  int use_exposure;          /* KernelFilm::use_display_exposure */
+  float exposure;
+};
+
+/* float -> half the way the reference CPU kernels store display pixels
+ * (util/util_half.h:80-100, scalar branch): clamp to [0, 65504], flush what would be a
+ * half denormal to 0, TRUNCATE the mantissa - bit-exact with the oracle, unlike
+ * __float2half which rounds to nearest. */
+CY_DEV unsigned short float_to_half_display(float f)
+{
+  const float c = (f > 0.0f) ? ((f < 65504.0f) ? f : 65504.0f) : 0.0f;
+  const int absolute = __float_as_int(c) & 0x7FFFFFFF;
+  const int Z = absolute + (int)0xC8000000u;
+  const int result = (absolute < 0x38800000) ? 0 : Z;
+  return (unsigned short)((result >> 13) & 0x7FFF);
+}
+
+/* kernel_film_convert_to_byte / _to_half_float (kernel_film.h:19-130) for the combined
+ * display pass (display_pass_components == 4, no divide pass) */
 __global__ void k_film_convert(const float *film, void *rgba, int half_float, float sample_scale,
                                int x0, int y0, int w, int h, int offset, int stride,
-                               int pass_stride, float exposure)
+                               FilmDisplay fd)
 {
   const int x = x0 + blockIdx.x * blockDim.x + threadIdx.x;
   const int y = y0 + blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= x0 + w || y >= y0 + h)
     return;
   const long long index = (long long)offset + x + (long long)y * stride;
-  const float4 in = *(const float4 *)(film + index * pass_stride);
-  /* film_get_pass_result with the combined pass: scale, exposure on rgb */
-  float4 r = make_float4(in.x * sample_scale * exposure, in.y * sample_scale * exposure,
-                         in.z * sample_scale * exposure, in.w * sample_scale);
+  const float4 in = *(const float4 *)(film + fd.display_pass_stride + index * fd.pass_stride);
+  /* film_get_pass_result */
+  float4 r = make_float4(in.x, in.y, in.z, fd.use_pass_alpha ? in.w : 1.0f / sample_scale);
+  if (fd.use_exposure) {
+    r.x *= fd.exposure;
+    r.y *= fd.exposure;
+    r.z *= fd.exposure;
+  }
   if (half_float) {
-    __half *out = (__half *)rgba + index * 4;
-    out[0] = __float2half(r.x);
-    out[1] = __float2half(r.y);
-    out[2] = __float2half(r.z);
-    out[3] = __float2half(r.w);
+    ushort4 v;
+    v.x = float_to_half_display(r.x * sample_scale);
+    v.y = float_to_half_display(r.y * sample_scale);
+    v.z = float_to_half_display(r.z * sample_scale);
+    v.w = float_to_half_display(r.w * sample_scale);
+    *((ushort4 *)rgba + index) = v;
   }
   else {
-    uchar4 *out = (uchar4 *)rgba + index;
+    /* film_map + film_float_to_byte */
     uchar4 v;
-    v.x = (unsigned char)(saturate(color_linear_to_srgb(r.x)) * 255.0f);
-    v.y = (unsigned char)(saturate(color_linear_to_srgb(r.y)) * 255.0f);
-    v.z = (unsigned char)(saturate(color_linear_to_srgb(r.z)) * 255.0f);
-    v.w = (unsigned char)(saturate(r.w) * 255.0f);
-    *out = v;
+    v.x = (unsigned char)(saturate(color_linear_to_srgb(r.x * sample_scale)) * 255.0f);
+    v.y = (unsigned char)(saturate(color_linear_to_srgb(r.y * sample_scale)) * 255.0f);
+    v.z = (unsigned char)(saturate(color_linear_to_srgb(r.z * sample_scale)) * 255.0f);
+    v.w = (unsigned char)(saturate(r.w * sample_scale) * 255.0f);
+    *((uchar4 *)rgba + index) = v;
   }
 }
 
@@ -1359,10 +1387,21 @@ int b200_film_convert(b200_ctx *ctx, uint64_t film, uint64_t rgba, int half_floa
   if (!ctx->have_data)
     return fail(ctx, B200_ERR_NOT_READY, "KernelData not uploaded");
   DeviceGuard guard(ctx->ordinal);
+  if (w <= 0 || h <= 0)
+    return B200_OK;
+  if (kd_host<int>(ctx, KD_FILM_DISPLAY_PASS_COMPONENTS) != 4 ||
+      kd_host<int>(ctx, KD_FILM_DISPLAY_DIVIDE_PASS_STRIDE) != -1)
+    return fail(ctx, B200_ERR_UNSUPPORTED,
+                "film_convert: only the 4-component combined display pass is implemented");
+  FilmDisplay fd;
+  fd.pass_stride = kd_host<int>(ctx, KD_FILM_PASS_STRIDE);
+  fd.display_pass_stride = kd_host<int>(ctx, KD_FILM_DISPLAY_PASS_STRIDE);
+  fd.use_pass_alpha = kd_host<int>(ctx, KD_FILM_USE_DISPLAY_PASS_ALPHA);
+  fd.use_exposure = kd_host<int>(ctx, KD_FILM_USE_DISPLAY_EXPOSURE);
+  fd.exposure = kd_host<float>(ctx, KD_FILM_EXPOSURE);
   dim3 block(16, 16), grid((w + 15) / 16, (h + 15) / 16);
-  k_film_convert<<<grid, block, 0, ctx->stream>>>(
-      (const float *)film, (void *)rgba, half_float, sample_scale, x, y, w, h, offset, stride,
-      kd_host<int>(ctx, KD_FILM_PASS_STRIDE), kd_host<float>(ctx, KD_FILM_EXPOSURE));
+  k_film_convert<<<grid, block, 0, ctx->stream>>>((const float *)film, (void *)rgba, half_float,
+                                                  sample_scale, x, y, w, h, offset, stride, fd);
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return B200_OK;

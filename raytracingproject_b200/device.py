@@ -297,6 +297,35 @@ class B200Device:
         wt = WorkTile(x, y, w, h, start_sample, num_samples, offset, stride, film_dptr)
         self._check(self._L.b200_render(self._ctx, C.byref(wt), None), "render")
 
+    # -- DeviceTask::FILM_CONVERT --
+    def film_convert(self, film, width, height, num_samples, half_float=False):
+        """kernel_film_convert_to_byte / _to_half_float over a full frame: `film` is a
+        DeviceMemory holding (h, w, pass_stride) float sums on the device; returns
+        (h, w, 4) uint8 display bytes or (h, w, 4) uint16 half bit patterns.
+        sample_scale = 1 / num_samples (device_cpu.cpp:1324)."""
+        out = DeviceMemory("display_rgba",
+                           np.zeros((height, width, 4), np.uint16 if half_float else np.uint8))
+        self.mem_zero(out)
+        try:
+            self._check(self._L.b200_film_convert(
+                self._ctx, film.device_pointer, out.device_pointer, int(bool(half_float)),
+                C.c_float(1.0 / float(num_samples)), 0, 0, width, height, 0, width),
+                "film_convert")
+            self.mem_copy_from(out)
+        finally:
+            self.mem_free(out)
+        return out.host
+
+    @staticmethod
+    def film_reduce(devices, films, n_floats):
+        """In-process multi-GPU film sum into films[0] (b200_film_reduce): devices[i] owns
+        the DeviceMemory films[i]."""
+        n = len(devices)
+        ctxs = (C.c_void_p * n)(*[d._ctx for d in devices])
+        ptrs = (C.c_uint64 * n)(*[f.device_pointer for f in films])
+        rc = devices[0]._L.b200_film_reduce(ctxs, n, ptrs, int(n_floats))
+        devices[0]._check(rc, "film_reduce")
+
     def render(self, width, height, pass_stride, start_sample, num_samples, film=None):
         """Full-frame RENDER into a fresh (or given) RenderBuffers-like film and
         read it back: returns (h, w, pass_stride) float32 sums."""
