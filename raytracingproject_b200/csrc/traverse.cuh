@@ -421,7 +421,7 @@ __device__ __forceinline__ void trace_persistent(Job &job, unsigned int n, unsig
 {
   __shared__ float4 s_ray[TRACE_WARPS][2][2][32]; /* [warp][buffer][P|D][entry] : 8 KB */
   /* cooperative leaf phase: pooled (record, owner lane | bit << 8) work list */
-  __shared__ uint2 s_list[TRACE_WARPS][96];
+  __shared__ uint2 s_list[TRACE_WARPS][224];
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -539,30 +539,25 @@ __device__ __forceinline__ void trace_persistent(Job &job, unsigned int n, unsig
       bool finished = false;
       while (true) {
         const uint32_t pend = active ? tr.Gt.y : 0u;
-        /* up to three records per lane and round (a leaf holds at most three), pooled
-         * in lane order: offsets from two ballots, no scan, no atomics */
-        const unsigned int npend = min((unsigned int)__popc(pend), 3u);
+        /* up to seven records per lane and pass (a leaf holds at most three, a node can
+         * expose several leaves), pooled in lane order: offsets from three ballots, no
+         * scan, no atomics */
+        const unsigned int npend = min((unsigned int)__popc(pend), 7u);
         const unsigned int b0 = __ballot_sync(0xffffffffu, (npend & 1u) != 0u);
         const unsigned int b1 = __ballot_sync(0xffffffffu, (npend & 2u) != 0u);
-        if ((b0 | b1) == 0u)
+        const unsigned int b2 = __ballot_sync(0xffffffffu, (npend & 4u) != 0u);
+        if ((b0 | b1 | b2) == 0u)
           break;
-        const unsigned int total = __popc(b0) + 2u * __popc(b1);
-        const unsigned int off = __popc(b0 & lt_mask) + 2u * __popc(b1 & lt_mask);
+        const unsigned int total = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
+        const unsigned int off = __popc(b0 & lt_mask) + 2u * __popc(b1 & lt_mask) +
+                                 4u * __popc(b2 & lt_mask);
         if (npend != 0u) {
           uint2 *dst = s_list[warp] + off;
           uint32_t bits = pend;
-          const uint32_t bit0 = (uint32_t)__ffs((int)bits) - 1u;
-          dst[0] = make_uint2(tr.Gt.x + bit0, lane | (bit0 << 8));
-          bits &= bits - 1u;
-          if (npend > 1u) {
-            const uint32_t bit1 = (uint32_t)__ffs((int)bits) - 1u;
-            dst[1] = make_uint2(tr.Gt.x + bit1, lane | (bit1 << 8));
+          for (unsigned int k = 0; k < npend; k++) {
+            const uint32_t bit = (uint32_t)__ffs((int)bits) - 1u;
+            dst[k] = make_uint2(tr.Gt.x + bit, lane | (bit << 8));
             bits &= bits - 1u;
-            if (npend > 2u) {
-              const uint32_t bit2 = (uint32_t)__ffs((int)bits) - 1u;
-              dst[2] = make_uint2(tr.Gt.x + bit2, lane | (bit2 << 8));
-              bits &= bits - 1u;
-            }
           }
           tr.Gt.y = bits;
         }
@@ -628,15 +623,12 @@ __device__ __forceinline__ void trace_persistent(Job &job, unsigned int n, unsig
             const int rel = (int)off - (int)base;
             uint32_t mine = (rel >= 0) ? (rel < 32 ? im >> rel : 0u) : (rel > -32 ? im << (-rel) : 0u);
             mine &= (1u << npend) - 1u;
-            if (mine != 0u) {
-              uint32_t pb = pend;
-              const uint32_t k0 = pb & (0u - pb);
+            uint32_t pb = pend;
+            while (mine != 0u) { /* k-th flag <-> k-th lowest set bit of pend */
+              if (mine & 1u)
+                inst_bits |= pb & (0u - pb);
               pb &= pb - 1u;
-              const uint32_t k1 = pb & (0u - pb);
-              pb &= pb - 1u;
-              const uint32_t k2 = pb & (0u - pb);
-              inst_bits |= ((mine & 1u) ? k0 : 0u) | ((mine & 2u) ? k1 : 0u) |
-                           ((mine & 4u) ? k2 : 0u);
+              mine >>= 1;
             }
           }
         }
