@@ -602,16 +602,26 @@ __device__ __forceinline__ void trace_persistent(Job &job, unsigned int n, unsig
            * order a single lane would have tested them in (a later record with the
            * same t replaces an earlier one, like the serial loop) */
           unsigned int hm = __ballot_sync(0xffffffffu, cand);
-          while (hm != 0u) {
-            const int src = __ffs((int)hm) - 1;
-            hm &= hm - 1u;
-            const unsigned int o = __shfl_sync(0xffffffffu, owner, src);
-            const float ht = __shfl_sync(0xffffffffu, t, src);
-            const float hu = __shfl_sync(0xffffffffu, u, src);
-            const float hv = __shfl_sync(0xffffffffu, v, src);
-            const int hp = __shfl_sync(0xffffffffu, tag, src);
-            if (lane == o && ht <= tr.tmax) {
-              tr.accept(ht, hu, hv, hp);
+          if (hm != 0u) {
+            /* first only (owner, t) of every candidate travels; an owner remembers the
+             * lane of the hit it keeps and fetches u, v, prim from it once */
+            int win = -1;
+            do {
+              const int src = __ffs((int)hm) - 1;
+              hm &= hm - 1u;
+              const unsigned int o = __shfl_sync(0xffffffffu, owner, src);
+              const float ht = __shfl_sync(0xffffffffu, t, src);
+              if (lane == o && ht <= tr.tmax) {
+                tr.tmax = ht;
+                win = src;
+              }
+            } while (hm != 0u);
+            const int from = (win >= 0) ? win : (int)lane;
+            const float hu = __shfl_sync(0xffffffffu, u, from);
+            const float hv = __shfl_sync(0xffffffffu, v, from);
+            const int hp = __shfl_sync(0xffffffffu, tag, from);
+            if (win >= 0) {
+              tr.accept(tr.tmax, hu, hv, hp);
               if (ANY_HIT)
                 finished = true;
             }
@@ -634,6 +644,9 @@ __device__ __forceinline__ void trace_persistent(Job &job, unsigned int n, unsig
         }
         if (ANY_HIT && finished)
           tr.Gt.y = 0u;
+        /* usually everything fitted into this pass */
+        if (!__any_sync(0xffffffffu, active && tr.Gt.y != 0u))
+          break;
         __syncwarp();
       }
 
