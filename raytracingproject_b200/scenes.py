@@ -175,9 +175,13 @@ def box_mesh(lo, hi):
 
 
 # ---------------------------------------------------------------- config 1
-def default_cube(width=1920, height=1080, spp=64, material="principled", max_bounce=12):
+def default_cube(width=1920, height=1080, spp=64, material="principled", max_bounce=12,
+                 lights="point"):
     """BASELINE config 1 - Blender's startup scene, values extracted from
-    release/datafiles/startup.blend."""
+    release/datafiles/startup.blend.  `lights`: "point" (the
+    startup scene), "spot" (the same lamp as a 50 degree spot aimed at the cube, soft
+    edge) or "mixed" (point + round area + sun: three entries in the light
+    distribution) - variants used by the parity tests only."""
     cam = euler_xyz_camera((7.358891, -6.925791, 4.958309), (1.109319, 0.0, 0.814928))
     fov = 2.0 * np.arctan(0.5 * 36.0 / 50.0 / (width / height))
     xml = "<cycles>\n"
@@ -192,14 +196,32 @@ def default_cube(width=1920, height=1080, spp=64, material="principled", max_bou
     else:
         xml += _diffuse_shader("cube", (0.8, 0.8, 0.8))
     xml += _emission_shader("lamp", (1, 1, 1), 1.0)
-    xml += _state(
-        "lamp",
-        '<light type="point" co="4.076245 1.005454 5.903862" size="0.1" '
-        'strength="1000 1000 1000" use_mis="true"/>\n')
+    co = np.array([4.076245, 1.005454, 5.903862])
+    aim = -co / np.linalg.norm(co)
+    point = ('<light type="point" co="%s" size="0.1" strength="1000 1000 1000" '
+             'use_mis="true"/>\n' % " ".join(_f(c) for c in co))
+    if lights == "point":
+        body = point
+    elif lights == "spot":
+        body = ('<light type="spot" co="%s" dir="%s" spot_angle="%s" spot_smooth="0.25" size="0.1" '
+                'strength="3000 3000 3000" use_mis="true"/>\n'
+                % (" ".join(_f(c) for c in co), " ".join(_f(c) for c in aim),
+                   _f(np.radians(50.0))))
+    elif lights == "mixed":
+        body = point
+        body += ('<light type="area" co="-3 -2 4" dir="0.5570860 0.3713907 -0.7427814" '
+                 'axisu="0.5547002 -0.8320503 0" axisv="0.6180207 0.4120138 0.6695225" '
+                 'sizeu="1.5" sizev="1" size="1" strength="400 380 350" use_mis="true"/>\n')
+        body += ('<light type="distant" dir="0.3 0.2 -0.9327379" angle="0.02" '
+                 'strength="1.5 1.5 1.6" use_mis="true"/>\n')
+    else:
+        raise ValueError(lights)
+    xml += _state("lamp", body)
     xml += "</cycles>\n"
     P, tris = box_mesh((-1, -1, -1), (1, 1, 1))
     return SceneDesc(
-        "default_cube_" + material, xml, width, height,
+        "default_cube_" + material + ("" if lights == "point" else "_" + lights), xml, width,
+        height,
         meshes=[MeshDesc(P, tris, "cube")], objects=[(0, np.eye(4, dtype=np.float32)[:3])],
         spp=spp, notes="config 1")
 

@@ -20,3 +20,12 @@ def principled_cases():
         "cube_principled": scenes.default_cube(W, H, material="principled"),
         "cornell_principled": scenes.cornell(W, H, materials="principled"),
     }
+
+
+def light_cases():
+    """Lamp types of kernel_light.h beyond the configs' point / sun / area: a spot with
+    a smooth edge, and three lamps of different types in one light distribution."""
+    return {
+        "cube_spot": scenes.default_cube(W, H, material="principled", lights="spot"),
+        "cube_mixed_lights": scenes.default_cube(W, H, material="diffuse", lights="mixed"),
+    }
