@@ -7,7 +7,8 @@
  *
  * Scope (b200_cycles.cu:check_scope / svm_validate refuse anything else):
  * perspective camera without DOF / motion, static triangles and instances,
- * point / spot / area / distant lamps, background colour, SVM nodes of
+ * point / spot / area / distant lamps, emissive triangles (light_tri.cuh), background
+ * colour, SVM nodes of
  * SVM_SUPPORTED_NODES and the Diffuse + Principled(GGX) + Glass(GGX) closures,
  * opaque shadows, combined pass only.
  */
@@ -19,7 +20,7 @@
 
 #define CLOSURE_WEIGHT_CUTOFF 1e-5f
 #define MAX_CLOSURES_GPU 8
-#define SVM_STACK_GPU 64 /* offsets used by the supported graphs stay far below 255 */
+#define SVM_STACK_GPU 256 /* SVM_STACK_SIZE 255 (svm_types.h): any offset the compiler can emit is in range */
 
 /* ------------------------------------------------------------- path state */
 
@@ -769,7 +770,7 @@ CY_DEV float rect_light_sample(f3 P, f3 *light_p, f3 axisu, f3 axisv, float rand
     return 0.0f;
 }
 
-/* kernel_light.h:40-168 (no background light, no triangle lights) */
+/* kernel_light.h:40-168 (no background light; triangle lights: light_tri.cuh) */
 CY_DEV bool lamp_light_sample(int lamp, float randu, float randv, f3 P, LightSampleG *ls)
 {
   const uint8_t *kl = light_ptr(lamp);
@@ -1015,14 +1016,22 @@ CY_DEV int light_distribution_sample(float *randu)
   return index;
 }
 
+#include "light_tri.cuh"
+
 /* kernel_light.h:624-660 (lamp < 0: pick from the distribution) */
 CY_DEV bool light_sample(float randu, float randv, f3 P, int bounce, LightSampleG *ls)
 {
   int index = light_distribution_sample(&randu);
-  int prim = __ldg((const int *)(g_scene.light_distribution +
-                                 (size_t)index * SIZEOF_KERNEL_LIGHT_DISTRIBUTION + KLD_PRIM));
-  if (prim >= 0)
-    return false; /* mesh lights: refused by check_scope (pdf_triangles != 0) */
+  const uint8_t *kd = g_scene.light_distribution + (size_t)index * SIZEOF_KERNEL_LIGHT_DISTRIBUTION;
+  int prim = __ldg((const int *)(kd + KLD_PRIM));
+  if (prim >= 0) {
+    /* an emissive triangle */
+    const int object = __ldg((const int *)(kd + KLD_MESH_OBJECT_ID));
+    const int shader_flag = __ldg((const int *)(kd + KLD_MESH_SHADER_FLAG));
+    triangle_light_sample(prim, object, randu, randv, ls, P);
+    ls->shader |= shader_flag;
+    return ls->pdf > 0.0f;
+  }
   int lamp = -prim - 1;
   if ((float)bounce > kl_float(light_ptr(lamp), KL_MAX_BOUNCES))
     return false;
@@ -1045,7 +1054,7 @@ CY_DEV bool shader_constant_emission_eval(int shader, f3 *eval)
   return false;
 }
 
-/* kernel_emission.h:20-98 (lamps only).  `emission_sd` is scratch. */
+/* kernel_emission.h:20-98.  `emission_sd` is scratch. */
 CY_DEV f3 direct_emissive_eval(ShaderDataG &emission_sd, LightSampleG *ls, f3 I, float t)
 {
   f3 eval = zero3();
@@ -1054,21 +1063,47 @@ CY_DEV f3 direct_emissive_eval(ShaderDataG &emission_sd, LightSampleG *ls, f3 I,
       ls->Ng = -ls->Ng;
   }
   else {
-    /* shader_setup_from_sample for a lamp (kernel_shader.h:244-345) */
+    /* shader_setup_from_sample (kernel_shader.h:244-345): a lamp, or a point on an
+     * emissive triangle */
     emission_sd.P = ls->P;
     emission_sd.N = ls->Ng;
     emission_sd.Ng = ls->Ng;
     emission_sd.I = I;
     emission_sd.shader = ls->shader;
-    emission_sd.type = 0;
-    emission_sd.object = -1;
-    emission_sd.prim = CY_PRIM_NONE;
+    emission_sd.type = (ls->prim != CY_PRIM_NONE) ? (int)CY_PRIMITIVE_TRIANGLE : 0;
+    emission_sd.object = ls->object;
+    emission_sd.prim = ls->prim;
     emission_sd.u = ls->u;
     emission_sd.v = ls->v;
     emission_sd.ray_length = t;
     emission_sd.flag = shader_flags(ls->shader);
     emission_sd.object_flag = 0;
     emission_sd.dPdu = zero3();
+    if (ls->prim != CY_PRIM_NONE) {
+      emission_sd.object_flag = __ldg(&g_scene.object_flag[ls->object]);
+      const bool applied = (emission_sd.object_flag & CY_SD_OBJECT_TRANSFORM_APPLIED) != 0;
+      const uint4 tri_vindex = __ldg(&g_scene.tri_vindex[ls->prim]);
+      if (ls->shader & CY_SHADER_SMOOTH_NORMAL) {
+        /* triangle_smooth_normal - geom/geom_triangle.h:80-92 */
+        f3 n0 = mk3(__ldg(&g_scene.tri_vnormal[tri_vindex.x]));
+        f3 n1 = mk3(__ldg(&g_scene.tri_vnormal[tri_vindex.y]));
+        f3 n2 = mk3(__ldg(&g_scene.tri_vnormal[tri_vindex.z]));
+        f3 N = safe_normalize((1.0f - ls->u - ls->v) * n2 + ls->u * n0 + ls->v * n1);
+        emission_sd.N = is_zero(N) ? ls->Ng : N;
+        if (!applied)
+          emission_sd.N = object_normal_transform(ls->object, emission_sd.N);
+      }
+      emission_sd.dPdu = mk3(__ldg(&g_scene.prim_tri_verts[tri_vindex.w + 0])) -
+                         mk3(__ldg(&g_scene.prim_tri_verts[tri_vindex.w + 2]));
+      if (!applied)
+        emission_sd.dPdu = object_dir_transform(ls->object, emission_sd.dPdu);
+      if (dot(emission_sd.Ng, emission_sd.I) < 0.0f) {
+        emission_sd.flag |= CY_SD_BACKFACING;
+        emission_sd.Ng = -emission_sd.Ng;
+        emission_sd.N = -emission_sd.N;
+        emission_sd.dPdu = -emission_sd.dPdu;
+      }
+    }
     ls->Ng = emission_sd.Ng;
     shader_eval_surface(emission_sd, CY_PATH_RAY_EMISSION);
     /* shader_emissive_eval: emissive_simple_eval(Ng, I) * weight */

@@ -674,10 +674,17 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS) k_shade_surface(Pa
           }
         }
         if (sd.flag & CY_SD_EMISSION) {
-          /* indirect_primitive_emission without mesh-light MIS (pdf_triangles == 0) */
+          /* indirect_primitive_emission - kernel_emission.h:214-233 */
           float cosNO = fabsf(dot(sd.Ng, sd.I));
           float res = (cosNO > 0.0f) ? 1.0f : 0.0f;
           f3 emission = mk3(res, res, res) * sd.closure_emission_background;
+          if (!(st.flag & CY_PATH_RAY_MIS_SKIP) && (sd.flag & CY_SD_USE_MIS)) {
+            /* this triangle is also in the light distribution: weight the BSDF-sampled
+             * hit against the pdf light sampling would have had for it */
+            const float pdf = triangle_light_pdf(sd.object, sd.prim, sd.P, sd.Ng, sd.I,
+                                                 sd.ray_length);
+            emission *= power_heuristic(st.ray_pdf, pdf);
+          }
           f3 contribution = throughput * emission;
           path_radiance_clamp(&contribution, st.bounce - 1);
           L += contribution;
@@ -714,6 +721,8 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS) k_shade_surface(Pa
                * emission directly, fall back to a scratch copy otherwise */
               f3 ce;
               if (shader_constant_emission_eval(ls.shader, &ce)) {
+                if ((ls.prim != CY_PRIM_NONE) && dot(ls.Ng, -ls.D) < 0.0f)
+                  ls.Ng = -ls.Ng;
                 light_eval = ce * ls.eval_fac;
                 if (ls.lamp != CY_LAMP_NONE)
                   light_eval *= kl_float3(light_ptr(ls.lamp), KL_STRENGTH);
@@ -1203,8 +1212,6 @@ static int check_scope(b200_ctx *ctx)
     why = "volumes are outside the hot-path scope";
   else if (I(KD_INT_USE_AMBIENT_OCCLUSION))
     why = "ambient occlusion is outside the hot-path scope";
-  else if (F(KD_INT_PDF_TRIANGLES) != 0.0f)
-    why = "mesh lights are outside the hot-path scope (use lamps)";
   else if (I(KD_BG_USE_MIS))
     why = "background importance sampling is outside the hot-path scope";
   else if (I(KD_FILM_USE_LIGHT_PASS) || I(KD_FILM_PASS_DENOISING_DATA) ||

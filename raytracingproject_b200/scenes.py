@@ -292,9 +292,13 @@ def terrain(width=1920, height=1080, spp=256, n=708, max_bounce=0):
 
 # ---------------------------------------------------------------- config 3
 def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
-            materials="principled"):
+            materials="principled", light="area"):
     """BASELINE config 3 - Cornell box, ceiling area light, one metallic and one
-    glass Principled box (materials="diffuse" gives the all-diffuse variant)."""
+    glass Principled box (materials="diffuse" gives the all-diffuse variant).
+    light="mesh" replaces the lamp by an emissive quad (a mesh light: its two triangles
+    enter the light distribution), light="mesh_instanced" by two instances of one small
+    emissive quad with different rotations and non-uniform scales (mesh lights whose
+    object transform is not applied) - parity-test variants."""
     xml = "<cycles>\n"
     cam = look_at((0.0, -3.6, 1.0), (0.0, 0.0, 1.0))
     fov = 2.0 * np.arctan(0.5 * 36.0 / 50.0 / (width / height)) * 1.6
@@ -312,11 +316,14 @@ def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
         xml += _principled_shader("glass", (1, 1, 1), 0.0, 0.0, 0.5, 1.0, 1.45, distribution)
     else:
         xml += _diffuse_shader("glass", (0.6, 0.7, 0.9))
-    xml += _emission_shader("lamp", (1.0, 0.9, 0.7), 1.0)
-    xml += _state(
-        "lamp",
-        '<light type="area" co="0 0 1.98" dir="0 0 -1" axisu="1 0 0" axisv="0 1 0" '
-        'sizeu="0.5" sizev="0.5" size="1" strength="12 12 12" use_mis="true"/>\n')
+    if light == "area":
+        xml += _emission_shader("lamp", (1.0, 0.9, 0.7), 1.0)
+        xml += _state(
+            "lamp",
+            '<light type="area" co="0 0 1.98" dir="0 0 -1" axisu="1 0 0" axisv="0 1 0" '
+            'sizeu="0.5" sizev="0.5" size="1" strength="12 12 12" use_mis="true"/>\n')
+    else:
+        xml += _emission_shader("lamp", (1.0, 0.9, 0.7), 18.0)
     xml += "</cycles>\n"
 
     def quad(a, b, c, d):
@@ -347,8 +354,23 @@ def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
     add(Pb, Tb, "metal", rot_z(20.0, (-0.35, 0.3, 0.0)))
     Ps, Ts = box_mesh((-0.3, -0.3, 0.002), (0.3, 0.3, 0.6))
     add(Ps, Ts, "glass", rot_z(-18.0, (0.35, -0.3, 0.0)))
-    return SceneDesc("cornell_" + materials, xml, width, height, meshes=meshes, objects=objects,
-                     spp=spp, notes="config 3")
+    if light == "mesh":
+        add(*quad((-0.25, -0.25, 1.98), (-0.25, 0.25, 1.98), (0.25, 0.25, 1.98),
+                  (0.25, -0.25, 1.98)), "lamp")
+    elif light == "mesh_instanced":
+        Pq, Tq = quad((-0.5, -0.5, 0), (-0.5, 0.5, 0), (0.5, 0.5, 0), (0.5, -0.5, 0))
+        meshes.append(MeshDesc(Pq, Tq, "lamp"))
+        mi = len(meshes) - 1
+        for deg, sx, sy, t in ((25.0, 0.45, 0.25, (-0.4, 0.2, 1.97)),
+                               (-40.0, 0.2, 0.5, (0.45, -0.1, 1.95))):
+            m = rot_z(deg, t)
+            m[:, 0] *= sx
+            m[:, 1] *= sy
+            objects.append((mi, m))
+    elif light != "area":
+        raise ValueError(light)
+    return SceneDesc("cornell_" + materials + ("" if light == "area" else "_" + light), xml, width,
+                     height, meshes=meshes, objects=objects, spp=spp, notes="config 3")
 
 
 # ---------------------------------------------------------------- config 4

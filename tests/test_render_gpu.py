@@ -61,7 +61,8 @@ def test_principled_image_matches_reference(ref, device, name):
         rs.close()
 
 
-@pytest.mark.parametrize("name", ["cube_spot", "cube_mixed_lights"])
+@pytest.mark.parametrize("name", ["cube_spot", "cube_mixed_lights", "cornell_mesh_light",
+                                  "cornell_mesh_light_instanced"])
 def test_lamp_types_match_reference(ref, device, name):
     desc = light_cases()[name]
     rs = ref.build_scene(desc)
