@@ -20,10 +20,6 @@
 #ifndef B200_LIGHT_TRI_CUH
 #define B200_LIGHT_TRI_CUH
 
-#define CY_M_PI_F 3.1415926535897932f
-#define CY_M_PI_2_F 1.5707963267948966f
-#define CY_M_1_PI_F 0.3183098861837067f
-
 /* round to nearest by adding +-0.5 and truncating (util_math_fast.h:83-93, non-SSE4) */
 CY_DEV int fast_rint(float x)
 {

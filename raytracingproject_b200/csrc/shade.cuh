@@ -407,6 +407,7 @@ CY_DEV bool stack_valid(uint32_t a)
 }
 
 #include "svm_closure.cuh"
+#include "svm_nodes.cuh"
 
 /* svm/svm.h:220-300 for the supported opcodes.  max_closures = 0 evaluates only
  * emission / background weights (PATH_RAY_EMISSION / TERMINATE evaluation,
@@ -515,6 +516,47 @@ __device__ __noinline__ void svm_eval_nodes(ShaderDataG &sd, uint32_t path_flag,
                                __uint_as_float(node1.w)));
         break;
       }
+      case CY_NODE_CONVERT:
+        svm_node_convert(stack, node.y, node.z, node.w);
+        break;
+      case CY_NODE_FRESNEL:
+        svm_node_fresnel(sd, stack, node);
+        break;
+      case CY_NODE_LAYER_WEIGHT:
+        svm_node_layer_weight(sd, stack, node);
+        break;
+      case CY_NODE_MATH:
+        svm_node_math(stack, node);
+        break;
+      case CY_NODE_VECTOR_MATH:
+        svm_node_vector_math(stack, node, &offset);
+        break;
+      case CY_NODE_MIX:
+        svm_node_mix(stack, node, &offset);
+        break;
+      case CY_NODE_INVERT:
+        svm_node_invert(stack, node);
+        break;
+      case CY_NODE_GAMMA:
+        svm_node_gamma(stack, node);
+        break;
+      case CY_NODE_BRIGHTCONTRAST:
+        svm_node_brightness(stack, node);
+        break;
+      case CY_NODE_SEPARATE_VECTOR: {
+        /* svm_sepcomb_vector.h: (vector offset, component index, out offset) */
+        const f3 vec = stack_load_float3(stack, node.y);
+        if (stack_valid(node.w))
+          stack[node.w] = (node.z == 0) ? vec.x : ((node.z == 1) ? vec.y : vec.z);
+        break;
+      }
+      case CY_NODE_COMBINE_VECTOR:
+        if (stack_valid(node.w))
+          stack[node.w + node.z] = stack[node.y];
+        break;
+      case CY_NODE_CLAMP:
+        svm_node_clamp(stack, node, &offset);
+        break;
       default:
         /* refused at bind time by svm_validate(); unreachable */
         return;

@@ -1,0 +1,510 @@
+/* svm_nodes.cuh - value nodes of the SVM interpreter (the nodes that compute numbers
+ * on the stack, as opposed to the closure nodes of svm_closure.cuh).
+ *
+ * Restated from blender/intern/cycles/kernel/svm (same stack encodings, same float
+ * operation order - the file is compiled without FMA contraction):
+ *   convert                         svm_convert.h:22-74
+ *   fresnel, layer weight           svm_fresnel.h:21-74
+ *   math, vector math               svm_math.h:19-77, svm_math_util.h:19-196
+ *   mix (colour blend modes)        svm_mix.h:21-38, svm_color_util.h:19-300
+ *   invert, gamma, bright/contrast  svm_invert.h, svm_gamma.h, svm_brightness.h
+ *   separate / combine vector       svm_sepcomb_vector.h
+ *   clamp                           svm_clamp.h
+ * Helper semantics (safe_divide, wrapf, pingpongf, smoothminf ...) follow
+ * util/util_math.h:345-660.
+ *
+ * The big switches are __noinline__: scenes that do not use them must not pay for
+ * them in registers of k_shade_surface.  Blend modes that need RGB<->HSV (hue,
+ * saturation, value, colour) and dodge / burn are refused by svm_validate.
+ */
+#ifndef B200_SVM_NODES_CUH
+#define B200_SVM_NODES_CUH
+
+CY_DEV void unpack_uchar2(uint32_t i, uint32_t *x, uint32_t *y)
+{
+  *x = i & 0xffu;
+  *y = (i >> 8) & 0xffu;
+}
+CY_DEV void unpack_uchar3(uint32_t i, uint32_t *x, uint32_t *y, uint32_t *z)
+{
+  *x = i & 0xffu;
+  *y = (i >> 8) & 0xffu;
+  *z = (i >> 16) & 0xffu;
+}
+CY_DEV float stack_load_float_default(const float *stack, uint32_t a, uint32_t value)
+{
+  return (a == (uint32_t)CY_SVM_STACK_INVALID) ? __uint_as_float(value) : stack[a];
+}
+
+/* ---- scalar helpers ---- */
+
+CY_DEV float nodes_safe_divide(float a, float b)
+{
+  return (b != 0.0f) ? a / b : 0.0f;
+}
+CY_DEV float nodes_safe_modulo(float a, float b)
+{
+  return (b != 0.0f) ? fmodf(a, b) : 0.0f;
+}
+CY_DEV float nodes_wrapf(float value, float max, float min)
+{
+  const float range = max - min;
+  return (range != 0.0f) ? value - (range * floorf((value - min) / range)) : min;
+}
+CY_DEV float nodes_fractf(float x)
+{
+  return x - floorf(x);
+}
+CY_DEV float nodes_pingpongf(float a, float b)
+{
+  return (b != 0.0f) ? fabsf(nodes_fractf((a - b) / (b * 2.0f)) * b * 2.0f - b) : 0.0f;
+}
+CY_DEV float nodes_smoothminf(float a, float b, float k)
+{
+  if (k != 0.0f) {
+    const float h = fmaxf(k - fabsf(a - b), 0.0f) / k;
+    return fminf(a, b) - h * h * h * k * (1.0f / 6.0f);
+  }
+  return fminf(a, b);
+}
+/* the CPU flavour of compatible_powf is plain powf */
+CY_DEV float nodes_safe_powf(float a, float b)
+{
+  if (a < 0.0f && b != (float)(int)b)
+    return 0.0f;
+  return powf(a, b);
+}
+CY_DEV float nodes_safe_logf(float a, float b)
+{
+  if (a <= 0.0f || b <= 0.0f)
+    return 0.0f;
+  return nodes_safe_divide(logf(a), logf(b));
+}
+CY_DEV float nodes_clamp(float v, float lo, float hi)
+{
+  return fminf(fmaxf(v, lo), hi);
+}
+
+__device__ __noinline__ float svm_math(uint32_t type, float a, float b, float c)
+{
+  switch (type) {
+    case CY_NODE_MATH_ADD:
+      return a + b;
+    case CY_NODE_MATH_SUBTRACT:
+      return a - b;
+    case CY_NODE_MATH_MULTIPLY:
+      return a * b;
+    case CY_NODE_MATH_DIVIDE:
+      return nodes_safe_divide(a, b);
+    case CY_NODE_MATH_POWER:
+      return nodes_safe_powf(a, b);
+    case CY_NODE_MATH_LOGARITHM:
+      return nodes_safe_logf(a, b);
+    case CY_NODE_MATH_SQRT:
+      return sqrtf(fmaxf(a, 0.0f));
+    case CY_NODE_MATH_INV_SQRT:
+      return (a > 0.0f) ? 1.0f / sqrtf(a) : 0.0f;
+    case CY_NODE_MATH_ABSOLUTE:
+      return fabsf(a);
+    case CY_NODE_MATH_RADIANS:
+      return a * (CY_M_PI_F / 180.0f);
+    case CY_NODE_MATH_DEGREES:
+      return a * (180.0f / CY_M_PI_F);
+    case CY_NODE_MATH_MINIMUM:
+      return fminf(a, b);
+    case CY_NODE_MATH_MAXIMUM:
+      return fmaxf(a, b);
+    case CY_NODE_MATH_LESS_THAN:
+      return (a < b) ? 1.0f : 0.0f;
+    case CY_NODE_MATH_GREATER_THAN:
+      return (a > b) ? 1.0f : 0.0f;
+    case CY_NODE_MATH_ROUND:
+      return floorf(a + 0.5f);
+    case CY_NODE_MATH_FLOOR:
+      return floorf(a);
+    case CY_NODE_MATH_CEIL:
+      return ceilf(a);
+    case CY_NODE_MATH_FRACTION:
+      return a - floorf(a);
+    case CY_NODE_MATH_MODULO:
+      return nodes_safe_modulo(a, b);
+    case CY_NODE_MATH_TRUNC:
+      return a >= 0.0f ? floorf(a) : ceilf(a);
+    case CY_NODE_MATH_SNAP:
+      return floorf(nodes_safe_divide(a, b)) * b;
+    case CY_NODE_MATH_WRAP:
+      return nodes_wrapf(a, b, c);
+    case CY_NODE_MATH_PINGPONG:
+      return nodes_pingpongf(a, b);
+    case CY_NODE_MATH_SINE:
+      return sinf(a);
+    case CY_NODE_MATH_COSINE:
+      return cosf(a);
+    case CY_NODE_MATH_TANGENT:
+      return tanf(a);
+    case CY_NODE_MATH_SINH:
+      return sinhf(a);
+    case CY_NODE_MATH_COSH:
+      return coshf(a);
+    case CY_NODE_MATH_TANH:
+      return tanhf(a);
+    case CY_NODE_MATH_ARCSINE:
+      return asinf(nodes_clamp(a, -1.0f, 1.0f));
+    case CY_NODE_MATH_ARCCOSINE:
+      return acosf(nodes_clamp(a, -1.0f, 1.0f));
+    case CY_NODE_MATH_ARCTANGENT:
+      return atanf(a);
+    case CY_NODE_MATH_ARCTAN2:
+      return atan2f(a, b);
+    case CY_NODE_MATH_SIGN:
+      return (a == 0.0f) ? 0.0f : ((a < 0.0f) ? -1.0f : 1.0f);
+    case CY_NODE_MATH_EXPONENT:
+      return expf(a);
+    case CY_NODE_MATH_COMPARE:
+      return ((a == b) || (fabsf(a - b) <= fmaxf(c, FLT_EPSILON))) ? 1.0f : 0.0f;
+    case CY_NODE_MATH_MULTIPLY_ADD:
+      return a * b + c;
+    case CY_NODE_MATH_SMOOTH_MIN:
+      return nodes_smoothminf(a, b, c);
+    case CY_NODE_MATH_SMOOTH_MAX:
+      return -nodes_smoothminf(-a, -b, c);
+    default:
+      return 0.0f;
+  }
+}
+
+CY_DEV f3 nodes_safe_divide3(f3 a, f3 b)
+{
+  return mk3((b.x != 0.0f) ? a.x / b.x : 0.0f, (b.y != 0.0f) ? a.y / b.y : 0.0f,
+             (b.z != 0.0f) ? a.z / b.z : 0.0f);
+}
+CY_DEV f3 nodes_floor3(f3 a)
+{
+  return mk3(floorf(a.x), floorf(a.y), floorf(a.z));
+}
+
+__device__ __noinline__ void svm_vector_math(
+    float *value, f3 *vector, uint32_t type, f3 a, f3 b, f3 c, float scale)
+{
+  switch (type) {
+    case CY_NODE_VECTOR_MATH_ADD:
+      *vector = a + b;
+      break;
+    case CY_NODE_VECTOR_MATH_SUBTRACT:
+      *vector = a - b;
+      break;
+    case CY_NODE_VECTOR_MATH_MULTIPLY:
+      *vector = a * b;
+      break;
+    case CY_NODE_VECTOR_MATH_DIVIDE:
+      *vector = nodes_safe_divide3(a, b);
+      break;
+    case CY_NODE_VECTOR_MATH_CROSS_PRODUCT:
+      *vector = cross(a, b);
+      break;
+    case CY_NODE_VECTOR_MATH_PROJECT: {
+      const float l2 = dot(b, b);
+      *vector = (l2 != 0.0f) ? (dot(a, b) / l2) * b : zero3();
+      break;
+    }
+    case CY_NODE_VECTOR_MATH_REFLECT: {
+      const f3 n = normalize(b);
+      *vector = a - 2.0f * n * dot(a, n);
+      break;
+    }
+    case CY_NODE_VECTOR_MATH_DOT_PRODUCT:
+      *value = dot(a, b);
+      break;
+    case CY_NODE_VECTOR_MATH_DISTANCE:
+      *value = len(a - b);
+      break;
+    case CY_NODE_VECTOR_MATH_LENGTH:
+      *value = len(a);
+      break;
+    case CY_NODE_VECTOR_MATH_SCALE:
+      *vector = a * scale;
+      break;
+    case CY_NODE_VECTOR_MATH_NORMALIZE:
+      *vector = safe_normalize(a);
+      break;
+    case CY_NODE_VECTOR_MATH_SNAP:
+      *vector = nodes_floor3(nodes_safe_divide3(a, b)) * b;
+      break;
+    case CY_NODE_VECTOR_MATH_FLOOR:
+      *vector = nodes_floor3(a);
+      break;
+    case CY_NODE_VECTOR_MATH_CEIL:
+      *vector = mk3(ceilf(a.x), ceilf(a.y), ceilf(a.z));
+      break;
+    case CY_NODE_VECTOR_MATH_MODULO:
+      *vector = mk3(nodes_safe_modulo(a.x, b.x), nodes_safe_modulo(a.y, b.y),
+                    nodes_safe_modulo(a.z, b.z));
+      break;
+    case CY_NODE_VECTOR_MATH_WRAP:
+      *vector = mk3(nodes_wrapf(a.x, b.x, c.x), nodes_wrapf(a.y, b.y, c.y),
+                    nodes_wrapf(a.z, b.z, c.z));
+      break;
+    case CY_NODE_VECTOR_MATH_FRACTION:
+      *vector = a - nodes_floor3(a);
+      break;
+    case CY_NODE_VECTOR_MATH_ABSOLUTE:
+      *vector = fabs3(a);
+      break;
+    case CY_NODE_VECTOR_MATH_MINIMUM:
+      *vector = mk3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z));
+      break;
+    case CY_NODE_VECTOR_MATH_MAXIMUM:
+      *vector = mk3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z));
+      break;
+    case CY_NODE_VECTOR_MATH_SINE:
+      *vector = mk3(sinf(a.x), sinf(a.y), sinf(a.z));
+      break;
+    case CY_NODE_VECTOR_MATH_COSINE:
+      *vector = mk3(cosf(a.x), cosf(a.y), cosf(a.z));
+      break;
+    case CY_NODE_VECTOR_MATH_TANGENT:
+      *vector = mk3(tanf(a.x), tanf(a.y), tanf(a.z));
+      break;
+    default:
+      *vector = zero3();
+      *value = 0.0f;
+  }
+}
+
+/* ---- colour mixing ---- */
+
+CY_DEV f3 nodes_interp(f3 a, f3 b, float t)
+{
+  return a + t * (b - a);
+}
+CY_DEV float mix_overlay_1(float c1, float c2, float t, float tm)
+{
+  if (c1 < 0.5f)
+    return c1 * (tm + 2.0f * t * c2);
+  return 1.0f - (tm + 2.0f * t * (1.0f - c2)) * (1.0f - c1);
+}
+
+__device__ __noinline__ f3 svm_mix(uint32_t type, float fac, f3 c1, f3 c2)
+{
+  const float t = saturate(fac);
+  const float tm = 1.0f - t;
+  const f3 one = one3();
+  switch (type) {
+    case CY_NODE_MIX_BLEND:
+      return nodes_interp(c1, c2, t);
+    case CY_NODE_MIX_ADD:
+      return nodes_interp(c1, c1 + c2, t);
+    case CY_NODE_MIX_MUL:
+      return nodes_interp(c1, c1 * c2, t);
+    case CY_NODE_MIX_SCREEN:
+      return one - (mk3(tm, tm, tm) + t * (one - c2)) * (one - c1);
+    case CY_NODE_MIX_OVERLAY:
+      return mk3(mix_overlay_1(c1.x, c2.x, t, tm), mix_overlay_1(c1.y, c2.y, t, tm),
+                 mix_overlay_1(c1.z, c2.z, t, tm));
+    case CY_NODE_MIX_SUB:
+      return nodes_interp(c1, c1 - c2, t);
+    case CY_NODE_MIX_DIV: {
+      f3 out = c1;
+      if (c2.x != 0.0f)
+        out.x = tm * out.x + t * out.x / c2.x;
+      if (c2.y != 0.0f)
+        out.y = tm * out.y + t * out.y / c2.y;
+      if (c2.z != 0.0f)
+        out.z = tm * out.z + t * out.z / c2.z;
+      return out;
+    }
+    case CY_NODE_MIX_DIFF:
+      return nodes_interp(c1, fabs3(c1 - c2), t);
+    case CY_NODE_MIX_DARK:
+      return nodes_interp(c1, mk3(fminf(c1.x, c2.x), fminf(c1.y, c2.y), fminf(c1.z, c2.z)), t);
+    case CY_NODE_MIX_LIGHT:
+      return nodes_interp(c1, mk3(fmaxf(c1.x, c2.x), fmaxf(c1.y, c2.y), fmaxf(c1.z, c2.z)), t);
+    case CY_NODE_MIX_SOFT: {
+      const f3 scr = one - (one - c2) * (one - c1);
+      return tm * c1 + t * ((one - c1) * c2 * c1 + c1 * scr);
+    }
+    case CY_NODE_MIX_LINEAR:
+      return c1 + t * (2.0f * c2 + mk3(-1.0f, -1.0f, -1.0f));
+    case CY_NODE_MIX_CLAMP:
+      return mk3(saturate(c1.x), saturate(c1.y), saturate(c1.z));
+    default:
+      return zero3();
+  }
+}
+
+/* ---- node bodies; `node` is the instruction, `offset` the program counter ---- */
+
+CY_DEV void svm_node_convert(float *stack, uint32_t type, uint32_t from, uint32_t to)
+{
+  switch (type) {
+    case CY_NODE_CONVERT_FI:
+      stack[to] = __int_as_float((int)stack[from]);
+      break;
+    case CY_NODE_CONVERT_FV: {
+      const float f = stack[from];
+      stack_store_float3(stack, to, mk3(f, f, f));
+      break;
+    }
+    case CY_NODE_CONVERT_CF:
+    case CY_NODE_CONVERT_CI: {
+      /* linear_rgb_to_gray - kernel_color.h:31-34 */
+      const f3 c = stack_load_float3(stack, from);
+      const float g = dot(c, mk3(kd_float(KD_FILM_RGB_TO_Y), kd_float(KD_FILM_RGB_TO_Y + 4),
+                                 kd_float(KD_FILM_RGB_TO_Y + 8)));
+      stack[to] = (type == CY_NODE_CONVERT_CF) ? g : __int_as_float((int)g);
+      break;
+    }
+    case CY_NODE_CONVERT_VF:
+    case CY_NODE_CONVERT_VI: {
+      const float g = average(stack_load_float3(stack, from));
+      stack[to] = (type == CY_NODE_CONVERT_VF) ? g : __int_as_float((int)g);
+      break;
+    }
+    case CY_NODE_CONVERT_IF:
+      stack[to] = (float)__float_as_int(stack[from]);
+      break;
+    case CY_NODE_CONVERT_IV: {
+      const float f = (float)__float_as_int(stack[from]);
+      stack_store_float3(stack, to, mk3(f, f, f));
+      break;
+    }
+  }
+}
+
+CY_DEV void svm_node_fresnel(const ShaderDataG &sd, float *stack, uint4 node)
+{
+  uint32_t normal_offset, out_offset;
+  unpack_uchar2(node.w, &normal_offset, &out_offset);
+  float eta = stack_valid(node.y) ? stack[node.y] : __uint_as_float(node.z);
+  const f3 normal_in = stack_valid(normal_offset) ? stack_load_float3(stack, normal_offset) : sd.N;
+  eta = fmaxf(eta, 1e-5f);
+  eta = (sd.flag & CY_SD_BACKFACING) ? 1.0f / eta : eta;
+  stack[out_offset] = fresnel_dielectric_cos(dot(sd.I, normal_in), eta);
+}
+
+CY_DEV void svm_node_layer_weight(const ShaderDataG &sd, float *stack, uint4 node)
+{
+  uint32_t type, normal_offset, out_offset;
+  unpack_uchar3(node.w, &type, &normal_offset, &out_offset);
+  float blend = stack_valid(node.y) ? stack[node.y] : __uint_as_float(node.z);
+  const f3 normal_in = stack_valid(normal_offset) ? stack_load_float3(stack, normal_offset) : sd.N;
+  float f;
+  if (type == CY_NODE_LAYER_WEIGHT_FRESNEL) {
+    float eta = fmaxf(1.0f - blend, 1e-5f);
+    eta = (sd.flag & CY_SD_BACKFACING) ? eta : 1.0f / eta;
+    f = fresnel_dielectric_cos(dot(sd.I, normal_in), eta);
+  }
+  else {
+    f = fabsf(dot(sd.I, normal_in));
+    if (blend != 0.5f) {
+      blend = nodes_clamp(blend, 0.0f, 1.0f - 1e-5f);
+      blend = (blend < 0.5f) ? 2.0f * blend : 0.5f / (1.0f - blend);
+      f = powf(f, blend);
+    }
+    f = 1.0f - f;
+  }
+  stack[out_offset] = f;
+}
+
+CY_DEV void svm_node_math(float *stack, uint4 node)
+{
+  uint32_t a, b, c;
+  unpack_uchar3(node.z, &a, &b, &c);
+  stack[node.w] = svm_math(node.y, stack[a], stack[b], stack[c]);
+}
+
+CY_DEV void svm_node_vector_math(float *stack, uint4 node, int *offset)
+{
+  uint32_t a_off, b_off, scale_off, value_off, vector_off;
+  unpack_uchar3(node.z, &a_off, &b_off, &scale_off);
+  unpack_uchar2(node.w, &value_off, &vector_off);
+  const f3 a = stack_load_float3(stack, a_off);
+  const f3 b = stack_load_float3(stack, b_off);
+  f3 c = zero3();
+  const float scale = stack[scale_off];
+  if (node.y == CY_NODE_VECTOR_MATH_WRAP) {
+    const uint4 extra = __ldg(&g_scene.svm_nodes[*offset]);
+    (*offset)++;
+    c = stack_load_float3(stack, extra.x);
+  }
+  float value = 0.0f;
+  f3 vector = zero3();
+  svm_vector_math(&value, &vector, node.y, a, b, c, scale);
+  if (stack_valid(value_off))
+    stack[value_off] = value;
+  if (stack_valid(vector_off))
+    stack_store_float3(stack, vector_off, vector);
+}
+
+CY_DEV void svm_node_mix(float *stack, uint4 node, int *offset)
+{
+  const uint4 node1 = __ldg(&g_scene.svm_nodes[*offset]);
+  (*offset)++;
+  const float fac = stack[node.y];
+  const f3 c1 = stack_load_float3(stack, node.z);
+  const f3 c2 = stack_load_float3(stack, node.w);
+  stack_store_float3(stack, node1.z, svm_mix(node1.y, fac, c1, c2));
+}
+
+CY_DEV void svm_node_invert(float *stack, uint4 node)
+{
+  const float factor = stack[node.y];
+  f3 color = stack_load_float3(stack, node.z);
+  color.x = factor * (1.0f - color.x) + (1.0f - factor) * color.x;
+  color.y = factor * (1.0f - color.y) + (1.0f - factor) * color.y;
+  color.z = factor * (1.0f - color.z) + (1.0f - factor) * color.z;
+  if (stack_valid(node.w))
+    stack_store_float3(stack, node.w, color);
+}
+
+CY_DEV void svm_node_gamma(float *stack, uint4 node)
+{
+  f3 color = stack_load_float3(stack, node.z);
+  const float gamma = stack[node.y];
+  if (gamma == 0.0f) {
+    color = one3();
+  }
+  else {
+    if (color.x > 0.0f)
+      color.x = powf(color.x, gamma);
+    if (color.y > 0.0f)
+      color.y = powf(color.y, gamma);
+    if (color.z > 0.0f)
+      color.z = powf(color.z, gamma);
+  }
+  if (stack_valid(node.w))
+    stack_store_float3(stack, node.w, color);
+}
+
+CY_DEV void svm_node_brightness(float *stack, uint4 node)
+{
+  uint32_t bright_offset, contrast_offset;
+  unpack_uchar2(node.w, &bright_offset, &contrast_offset);
+  f3 color = stack_load_float3(stack, node.y);
+  const float brightness = stack[bright_offset];
+  const float contrast = stack[contrast_offset];
+  const float a = 1.0f + contrast;
+  const float b = brightness - contrast * 0.5f;
+  color.x = fmaxf(a * color.x + b, 0.0f);
+  color.y = fmaxf(a * color.y + b, 0.0f);
+  color.z = fmaxf(a * color.z + b, 0.0f);
+  if (stack_valid(node.z))
+    stack_store_float3(stack, node.z, color);
+}
+
+CY_DEV void svm_node_clamp(float *stack, uint4 node, int *offset)
+{
+  uint32_t min_off, max_off, type;
+  unpack_uchar3(node.z, &min_off, &max_off, &type);
+  const uint4 defaults = __ldg(&g_scene.svm_nodes[*offset]);
+  (*offset)++;
+  const float value = stack[node.y];
+  const float lo = stack_load_float_default(stack, min_off, defaults.x);
+  const float hi = stack_load_float_default(stack, max_off, defaults.y);
+  if (type == CY_NODE_CLAMP_RANGE && (lo > hi))
+    stack[node.w] = nodes_clamp(value, hi, lo);
+  else
+    stack[node.w] = nodes_clamp(value, lo, hi);
+}
+
+#endif /* B200_SVM_NODES_CUH */

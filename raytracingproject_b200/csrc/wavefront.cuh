@@ -1124,6 +1124,28 @@ static int ensure_pool(b200_ctx *ctx, size_t capacity)
   return B200_OK;
 }
 
+static bool svm_mix_supported_host(uint32_t type)
+{
+  switch (type) {
+    case CY_NODE_MIX_BLEND:
+    case CY_NODE_MIX_ADD:
+    case CY_NODE_MIX_MUL:
+    case CY_NODE_MIX_SCREEN:
+    case CY_NODE_MIX_OVERLAY:
+    case CY_NODE_MIX_SUB:
+    case CY_NODE_MIX_DIV:
+    case CY_NODE_MIX_DIFF:
+    case CY_NODE_MIX_DARK:
+    case CY_NODE_MIX_LIGHT:
+    case CY_NODE_MIX_SOFT:
+    case CY_NODE_MIX_LINEAR:
+    case CY_NODE_MIX_CLAMP:
+      return true;
+    default:
+      return false;
+  }
+}
+
 /* Opcodes and closure ids the kernels implement (svm.h switch subset). */
 static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why)
 {
@@ -1145,11 +1167,38 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
       case CY_NODE_JUMP_IF_ONE:
       case CY_NODE_GEOMETRY:
       case CY_NODE_VALUE_F:
+      case CY_NODE_CONVERT:
+      case CY_NODE_FRESNEL:
+      case CY_NODE_LAYER_WEIGHT:
+      case CY_NODE_MATH:
+      case CY_NODE_INVERT:
+      case CY_NODE_GAMMA:
+      case CY_NODE_BRIGHTCONTRAST:
+      case CY_NODE_SEPARATE_VECTOR:
+      case CY_NODE_COMBINE_VECTOR:
         i += 1;
         break;
       case CY_NODE_VALUE_V:
+      case CY_NODE_CLAMP: /* + one node of default values */
         i += 2;
         break;
+      case CY_NODE_VECTOR_MATH: /* the three-input operator carries an extra node */
+        i += (nodes[4 * i + 1] == CY_NODE_VECTOR_MATH_WRAP) ? 2 : 1;
+        break;
+      case CY_NODE_MIX: {
+        if (i + 1 >= n_nodes) {
+          why = "truncated Mix node";
+          return false;
+        }
+        const uint32_t blend = nodes[4 * (i + 1) + 1];
+        if (!svm_mix_supported_host(blend)) {
+          why = "MixRGB blend mode " + std::to_string(blend) +
+                " (hue/saturation/value/colour/dodge/burn) is outside the hot-path scope";
+          return false;
+        }
+        i += 2;
+        break;
+      }
       case CY_NODE_CLOSURE_BSDF: {
         const uint32_t type = nodes[4 * i + 1] & 0xff;
         if (type == CY_CLOSURE_BSDF_PRINCIPLED_ID) {
@@ -1179,7 +1228,9 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
       default:
         why = "SVM node opcode " + std::to_string(op) + " at " + std::to_string(i) +
               " is outside the hot-path scope (supported: closures diffuse/principled-GGX/"
-              "glossy-GGX/emission/background, mix, value, geometry)";
+              "glossy-GGX/emission/background, mix closure, value, geometry, convert, fresnel, "
+              "layer weight, math, vector math, mix, invert, gamma, bright/contrast, "
+              "separate/combine, clamp)";
         return false;
     }
   }

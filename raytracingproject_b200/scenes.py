@@ -134,6 +134,72 @@ def _principled_shader(name, base_color, metallic=0.0, roughness=0.5, specular=0
     )
 
 
+def _procedural_shader(name, variant=0):
+    """A material built from value nodes only (no textures): position stripes through
+    separate / math, facing and fresnel weights, colour mix / brightness / gamma / invert,
+    vector math + clamp, a diffuse + glossy-GGX mix.  `variant` changes the blend modes
+    and math operators so that two shaders cover most of svm_nodes.cuh."""
+    blend_a, blend_b, op_a, op_b, vop = [
+        ("mix", "multiply", "sine", "multiply_add", "cross_product"),
+        ("screen", "overlay", "pingpong", "smoothmin", "reflect"),
+    ][variant]
+    return (
+        '<shader name="%s">\n'
+        '  <geometry name="g"/>\n'
+        '  <separate_xyz name="sep"/>\n'
+        '  <connect from="g position" to="sep vector"/>\n'
+        '  <math name="m1" type="multiply" value2="5.5"/>\n'
+        '  <connect from="sep x" to="m1 value1"/>\n'
+        '  <math name="m2" type="%s" value2="0.7"/>\n'
+        '  <connect from="m1 value" to="m2 value1"/>\n'
+        '  <math name="m3" type="%s" value2="0.45" value3="0.5"/>\n'
+        '  <connect from="m2 value" to="m3 value1"/>\n'
+        '  <vector_math name="vd" type="dot_product" vector2="0.3 0.5 0.8"/>\n'
+        '  <connect from="g normal" to="vd vector1"/>\n'
+        '  <vector_math name="vm" type="%s" vector2="0.3 0.5 0.8"/>\n'
+        '  <connect from="g normal" to="vm vector1"/>\n'
+        '  <vector_math name="vl" type="length"/>\n'
+        '  <connect from="vm vector" to="vl vector1"/>\n'
+        '  <math name="m4" type="add"/>\n'
+        '  <connect from="vd value" to="m4 value1"/>\n'
+        '  <connect from="vl value" to="m4 value2"/>\n'
+        '  <clamp name="cl" type="minmax" min="0.1" max="0.9"/>\n'
+        '  <connect from="m4 value" to="cl value"/>\n'
+        '  <combine_xyz name="cmb" z="0.25"/>\n'
+        '  <connect from="cl result" to="cmb x"/>\n'
+        '  <connect from="m3 value" to="cmb y"/>\n'
+        '  <mix name="mx" type="%s" color1="0.8 0.25 0.1" color2="0.1 0.35 0.8"/>\n'
+        '  <connect from="m3 value" to="mx fac"/>\n'
+        '  <layer_weight name="lw" blend="0.3"/>\n'
+        '  <mix name="mx2" type="%s" fac="0.6"/>\n'
+        '  <connect from="mx color" to="mx2 color1"/>\n'
+        '  <connect from="cmb vector" to="mx2 color2"/>\n'
+        '  <mix name="mx3" type="lighten" color2="0.3 0.3 0.3"/>\n'
+        '  <connect from="lw facing" to="mx3 fac"/>\n'
+        '  <connect from="mx2 color" to="mx3 color1"/>\n'
+        '  <brightness_contrast name="bc" bright="0.04" contrast="0.15"/>\n'
+        '  <connect from="mx3 color" to="bc color"/>\n'
+        '  <gamma name="gm" gamma="1.3"/>\n'
+        '  <connect from="bc color" to="gm color"/>\n'
+        '  <invert name="inv" fac="0.1"/>\n'
+        '  <connect from="gm color" to="inv color"/>\n'
+        '  <diffuse_bsdf name="d"/>\n'
+        '  <connect from="inv color" to="d color"/>\n'
+        '  <glossy_bsdf name="gl" distribution="GGX" roughness="0.3" color="0.9 0.9 0.9"/>\n'
+        '  <connect from="cl result" to="gl color"/>\n'
+        '  <math name="m5" type="multiply_add" value2="0.3" value3="0.15"/>\n'
+        '  <connect from="inv color" to="m5 value1"/>\n'
+        '  <connect from="m5 value" to="gl roughness"/>\n'
+        '  <fresnel name="fr" IOR="1.6"/>\n'
+        '  <mix_closure name="mc"/>\n'
+        '  <connect from="fr fac" to="mc fac"/>\n'
+        '  <connect from="d bsdf" to="mc closure1"/>\n'
+        '  <connect from="gl bsdf" to="mc closure2"/>\n'
+        '  <connect from="mc closure" to="output surface"/>\n'
+        "</shader>\n" % (name, op_a, op_b, vop, blend_a, blend_b)
+    )
+
+
 def _integrator(max_bounce, diffuse=None, glossy=None, transmission=None, transparent=8,
                 clamp_indirect=0.0, seed=0, light_threshold=0.01, caustics=True):
     diffuse = max_bounce if diffuse is None else diffuse
@@ -308,11 +374,15 @@ def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
     xml += _diffuse_shader("white", (0.73, 0.73, 0.73))
     xml += _diffuse_shader("red", (0.65, 0.05, 0.05))
     xml += _diffuse_shader("green", (0.12, 0.45, 0.15))
-    if materials in ("principled", "metal"):
+    if materials == "procedural":
+        xml += _procedural_shader("metal", 0)
+    elif materials in ("principled", "metal"):
         xml += _principled_shader("metal", (0.9, 0.85, 0.7), 1.0, 0.2, 0.5, 0.0, 1.45, distribution)
     else:
         xml += _diffuse_shader("metal", (0.9, 0.85, 0.7))
-    if materials in ("principled", "glass"):
+    if materials == "procedural":
+        xml += _procedural_shader("glass", 1)
+    elif materials in ("principled", "glass"):
         xml += _principled_shader("glass", (1, 1, 1), 0.0, 0.0, 0.5, 1.0, 1.45, distribution)
     else:
         xml += _diffuse_shader("glass", (0.6, 0.7, 0.9))
@@ -466,3 +536,139 @@ CONFIGS = {
     "cornell": cornell,
     "instanced": instanced,
 }
+
+
+# ------------------------------------------------- value-node chart (tests)
+MATH_OPS = ["add", "subtract", "multiply", "divide", "multiply_add", "sine", "cosine", "tangent",
+            "sinh", "cosh", "tanh", "arcsine", "arccosine", "arctangent", "power", "logarithm",
+            "minimum", "maximum", "round", "less_than", "greater_than", "modulo", "absolute",
+            "arctan2", "floor", "ceil", "fraction", "trunc", "snap", "wrap", "pingpong", "sqrt",
+            "inversesqrt", "sign", "exponent", "radians", "degrees", "smoothmin", "smoothmax",
+            "compare"]
+VECTOR_OPS = ["add", "subtract", "multiply", "divide", "cross_product", "project", "reflect",
+              "dot_product", "distance", "length", "scale", "normalize", "snap", "floor", "ceil",
+              "modulo", "wrap", "fraction", "absolute", "minimum", "maximum", "sine", "cosine",
+              "tangent"]
+MIX_OPS = ["mix", "add", "multiply", "screen", "overlay", "subtract", "divide", "difference",
+           "darken", "lighten", "soft_light", "linear_light"]
+
+
+def node_chart(width=256, height=144, spp=1):
+    """One emissive quad per group of value nodes; the emitted colour IS the node output,
+    evaluated at the hit position, so one frame compares every operator of svm_nodes.cuh
+    with the reference (camera rays only: the inputs are bit-identical on both sides)."""
+    head = ('  <geometry name="g"/>\n  <separate_xyz name="sep"/>\n'
+            '  <connect from="g position" to="sep vector"/>\n'
+            '  <math name="a" type="multiply_add" value2="1.7" value3="0.13"/>\n'
+            '  <connect from="sep x" to="a value1"/>\n'
+            '  <math name="b" type="multiply_add" value2="-0.9" value3="0.41"/>\n'
+            '  <connect from="sep y" to="b value1"/>\n')
+    tail = ('  <emission name="e" strength="1"/>\n  <connect from="out vector" to="e color"/>\n'
+            '  <connect from="e emission" to="output surface"/>\n')
+    shaders = []
+
+    def scalar_group(kind_ops):
+        body = head + '  <combine_xyz name="out"/>\n'
+        for ch, op in zip("xyz", kind_ops):
+            body += ('  <math name="op_%s" type="%s" value3="0.35"/>\n'
+                     '  <connect from="a value" to="op_%s value1"/>\n'
+                     '  <connect from="b value" to="op_%s value2"/>\n'
+                     '  <connect from="op_%s value" to="out %s"/>\n' % (ch, op, ch, ch, ch, ch))
+        return body + tail
+
+    for i in range(0, len(MATH_OPS), 3):
+        shaders.append(scalar_group(MATH_OPS[i:i + 3]))
+
+    for op in VECTOR_OPS:
+        body = head + ('  <combine_xyz name="va" z="0.6"/>\n'
+                       '  <connect from="a value" to="va x"/>\n'
+                       '  <connect from="b value" to="va y"/>\n'
+                       '  <vector_math name="vop" type="%s" vector2="0.45 -0.8 0.3" '
+                       'vector3="-0.2 0.1 0.05" scale="1.5"/>\n'
+                       '  <connect from="va vector" to="vop vector1"/>\n' % op)
+        if op in ("dot_product", "distance", "length"):
+            body += ('  <combine_xyz name="out" y="0.2" z="0.1"/>\n'
+                     '  <connect from="vop value" to="out x"/>\n')
+        else:
+            body += ('  <vector_math name="out" type="add" vector2="0 0 0"/>\n'
+                     '  <connect from="vop vector" to="out vector1"/>\n')
+        shaders.append(body + tail)
+
+    for op in MIX_OPS:
+        body = head + ('  <combine_xyz name="c1" z="0.3"/>\n'
+                       '  <connect from="a value" to="c1 x"/>\n'
+                       '  <connect from="b value" to="c1 y"/>\n'
+                       '  <math name="f" type="fraction"/>\n'
+                       '  <connect from="a value" to="f value1"/>\n'
+                       '  <mix name="mop" type="%s" color2="0.25 0.6 0.9"/>\n'
+                       '  <connect from="f value" to="mop fac"/>\n'
+                       '  <connect from="c1 vector" to="mop color1"/>\n'
+                       '  <vector_math name="out" type="add" vector2="0 0 0"/>\n'
+                       '  <connect from="mop color" to="out vector1"/>\n' % op)
+        shaders.append(body + tail)
+
+    # a few single-purpose ones: clamp (both types), gamma, brightness, invert, fresnel,
+    # layer weight (both outputs), float -> colour and colour -> float conversion
+    extra = head + (
+        '  <clamp name="cl1" type="minmax" min="0.2" max="0.7"/>\n'
+        '  <connect from="a value" to="cl1 value"/>\n'
+        '  <clamp name="cl2" type="range" min="0.8" max="0.1"/>\n'
+        '  <connect from="b value" to="cl2 value"/>\n'
+        '  <fresnel name="fr" IOR="1.3"/>\n'
+        '  <combine_xyz name="out"/>\n'
+        '  <connect from="cl1 result" to="out x"/>\n'
+        '  <connect from="cl2 result" to="out y"/>\n'
+        '  <connect from="fr fac" to="out z"/>\n')
+    shaders.append(extra + tail)
+    extra2 = head + (
+        '  <combine_xyz name="c1" z="0.3"/>\n'
+        '  <connect from="a value" to="c1 x"/>\n'
+        '  <connect from="b value" to="c1 y"/>\n'
+        '  <gamma name="gm" gamma="2.2"/>\n'
+        '  <connect from="c1 vector" to="gm color"/>\n'
+        '  <brightness_contrast name="bc" bright="0.1" contrast="0.3"/>\n'
+        '  <connect from="gm color" to="bc color"/>\n'
+        '  <invert name="out2" fac="0.7"/>\n'
+        '  <connect from="bc color" to="out2 color"/>\n'
+        '  <vector_math name="out" type="add" vector2="0 0 0"/>\n'
+        '  <connect from="out2 color" to="out vector1"/>\n')
+    shaders.append(extra2 + tail)
+    extra3 = head + (
+        '  <layer_weight name="lw" blend="0.35"/>\n'
+        '  <combine_xyz name="c1" z="0.3"/>\n'
+        '  <connect from="a value" to="c1 x"/>\n'
+        '  <connect from="b value" to="c1 y"/>\n'
+        '  <math name="gray" type="multiply" value2="1.0"/>\n'
+        '  <connect from="c1 vector" to="gray value1"/>\n'     # colour -> float
+        '  <combine_xyz name="out"/>\n'
+        '  <connect from="lw fresnel" to="out x"/>\n'
+        '  <connect from="lw facing" to="out y"/>\n'
+        '  <connect from="gray value" to="out z"/>\n')
+    shaders.append(extra3 + tail)
+    extra4 = head + (
+        '  <emission name="e" strength="1"/>\n'
+        '  <connect from="a value" to="e color"/>\n'           # float -> colour
+        '  <connect from="e emission" to="output surface"/>\n')
+    shaders.append(extra4)
+
+    n = len(shaders)
+    cols = 12
+    rows = (n + cols - 1) // cols
+    cam = look_at((0.0, 0.0, 10.0), (0.0, 0.0, 0.0), up=(0.0, 1.0, 0.0))
+    fov = 2.0 * np.arctan((rows * 0.5 + 0.2) / 10.0)
+    xml = "<cycles>\n"
+    xml += _header(width, height, cam, fov, _integrator(0), nearclip=0.1, farclip=100.0)
+    xml += _background((0, 0, 0), 0.0)
+    for i, body in enumerate(shaders):
+        xml += '<shader name="s%d">\n%s</shader>\n' % (i, body)
+    xml += "</cycles>\n"
+    meshes, objects = [], []
+    for i in range(n):
+        cx = (i % cols) - (cols - 1) / 2.0
+        cy = (rows - 1) / 2.0 - (i // cols)
+        P = np.array([(cx - 0.46, cy - 0.46, 0), (cx + 0.46, cy - 0.46, 0),
+                      (cx + 0.46, cy + 0.46, 0), (cx - 0.46, cy + 0.46, 0)], np.float32)
+        meshes.append(MeshDesc(P, np.array([[0, 1, 2], [0, 2, 3]], np.int32), "s%d" % i))
+        objects.append((i, np.eye(4, dtype=np.float32)[:3]))
+    return SceneDesc("node_chart", xml, width, height, meshes=meshes, objects=objects, spp=spp,
+                     notes="svm value nodes")
