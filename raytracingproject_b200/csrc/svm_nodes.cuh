@@ -13,12 +13,22 @@
  * Helper semantics (safe_divide, wrapf, pingpongf, smoothminf ...) follow
  * util/util_math.h:345-660.
  *
- * The big switches are __noinline__: scenes that do not use them must not pay for
- * them in registers of k_shade_surface.  Blend modes that need RGB<->HSV (hue,
+ * Blend modes that need RGB<->HSV (hue,
  * saturation, value, colour) and dodge / burn are refused by svm_validate.
  */
 #ifndef B200_SVM_NODES_CUH
 #define B200_SVM_NODES_CUH
+
+/* measured on the shading-bound Cornell workload: inlined -0.4 %, out of line -1.3 %
+ * against a build without these nodes */
+#ifndef SVM_NODES_INLINE
+#  define SVM_NODES_INLINE 1
+#endif
+#if SVM_NODES_INLINE
+#  define SVM_NODES_FN __device__ __forceinline__
+#else
+#  define SVM_NODES_FN __device__ __noinline__
+#endif
 
 CY_DEV void unpack_uchar2(uint32_t i, uint32_t *x, uint32_t *y)
 {
@@ -85,7 +95,7 @@ CY_DEV float nodes_clamp(float v, float lo, float hi)
   return fminf(fmaxf(v, lo), hi);
 }
 
-__device__ __noinline__ float svm_math(uint32_t type, float a, float b, float c)
+SVM_NODES_FN float svm_math(uint32_t type, float a, float b, float c)
 {
   switch (type) {
     case CY_NODE_MATH_ADD:
@@ -183,7 +193,7 @@ CY_DEV f3 nodes_floor3(f3 a)
   return mk3(floorf(a.x), floorf(a.y), floorf(a.z));
 }
 
-__device__ __noinline__ void svm_vector_math(
+SVM_NODES_FN void svm_vector_math(
     float *value, f3 *vector, uint32_t type, f3 a, f3 b, f3 c, float scale)
 {
   switch (type) {
@@ -284,7 +294,7 @@ CY_DEV float mix_overlay_1(float c1, float c2, float t, float tm)
   return 1.0f - (tm + 2.0f * t * (1.0f - c2)) * (1.0f - c1);
 }
 
-__device__ __noinline__ f3 svm_mix(uint32_t type, float fac, f3 c1, f3 c2)
+SVM_NODES_FN f3 svm_mix(uint32_t type, float fac, f3 c1, f3 c2)
 {
   const float t = saturate(fac);
   const float tm = 1.0f - t;
