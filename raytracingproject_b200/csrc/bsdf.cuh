@@ -36,7 +36,113 @@ CY_DEV int bsdf_diffuse_sample(const Closure &sc, f3 Ng, float randu, float rand
   return CY_LABEL_REFLECT | CY_LABEL_DIFFUSE;
 }
 
+/* kernel_montecarlo.h:69-82 */
+CY_DEV void sample_uniform_hemisphere(f3 N, float randu, float randv, f3 *omega_in, float *pdf)
+{
+  float z = randu;
+  float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+  float phi = CY_2PI_F * randv;
+  float x = r * cosf(phi);
+  float y = r * sinf(phi);
+  f3 T, B;
+  make_orthonormals(N, &T, &B);
+  *omega_in = x * T + y * B + z * N;
+  *pdf = 0.5f * CY_1_PI_F;
+}
+
+/* closure/bsdf_oren_nayar.h: Diffuse BSDF with roughness > 0.  The two precomputed
+ * coefficients a, b live in alpha_x, alpha_y of the closure record. */
+CY_DEV uint32_t bsdf_oren_nayar_setup(Closure *bsdf, float roughness)
+{
+  bsdf->type = CY_CLOSURE_BSDF_OREN_NAYAR_ID;
+  const float sigma = saturate(roughness);
+  const float div = 1.0f / (CY_M_PI_F + ((3.0f * CY_M_PI_F - 4.0f) / 6.0f) * sigma);
+  bsdf->roughness = roughness;
+  bsdf->alpha_x = 1.0f * div;
+  bsdf->alpha_y = sigma * div;
+  return CY_SD_BSDF | CY_SD_BSDF_HAS_EVAL;
+}
+CY_DEV f3 bsdf_oren_nayar_get_intensity(const Closure &sc, f3 n, f3 v, f3 l)
+{
+  float nl = fmaxf(dot(n, l), 0.0f);
+  float nv = fmaxf(dot(n, v), 0.0f);
+  float t = dot(l, v) - nl * nv;
+  if (t > 0.0f)
+    t /= fmaxf(nl, nv) + FLT_MIN;
+  float is = nl * (sc.alpha_x + sc.alpha_y * t);
+  return mk3(is, is, is);
+}
+CY_DEV f3 bsdf_oren_nayar_eval_reflect(const Closure &sc, f3 I, f3 omega_in, float *pdf)
+{
+  if (dot(sc.N, omega_in) > 0.0f) {
+    *pdf = 0.5f * CY_1_PI_F;
+    return bsdf_oren_nayar_get_intensity(sc, sc.N, I, omega_in);
+  }
+  *pdf = 0.0f;
+  return zero3();
+}
+CY_DEV int bsdf_oren_nayar_sample(const Closure &sc, f3 Ng, f3 I, float randu, float randv,
+                                  f3 *eval, f3 *omega_in, float *pdf)
+{
+  sample_uniform_hemisphere(sc.N, randu, randv, omega_in, pdf);
+  if (dot(Ng, *omega_in) > 0.0f) {
+    *eval = bsdf_oren_nayar_get_intensity(sc, sc.N, I, *omega_in);
+  }
+  else {
+    *pdf = 0.0f;
+    *eval = zero3();
+  }
+  return CY_LABEL_REFLECT | CY_LABEL_DIFFUSE;
+}
+
+/* closure/bsdf_diffuse.h:112-170: Translucent BSDF (Lambert on the far side) */
+CY_DEV f3 bsdf_translucent_eval_transmit(const Closure &sc, f3 omega_in, float *pdf)
+{
+  float cos_pi = fmaxf(-dot(sc.N, omega_in), 0.0f) * CY_1_PI_F;
+  *pdf = cos_pi;
+  return mk3(cos_pi, cos_pi, cos_pi);
+}
+CY_DEV int bsdf_translucent_sample(const Closure &sc, f3 Ng, float randu, float randv, f3 *eval,
+                                   f3 *omega_in, float *pdf)
+{
+  sample_cos_hemisphere(-sc.N, randu, randv, omega_in, pdf);
+  if (dot(Ng, *omega_in) < 0)
+    *eval = mk3(*pdf, *pdf, *pdf);
+  else
+    *pdf = 0;
+  return CY_LABEL_TRANSMIT | CY_LABEL_DIFFUSE;
+}
+
 #include "bsdf_principled.cuh"
+
+/* closure/bsdf_reflection.h, bsdf_refraction.h: the singular (sharp) closures - one
+ * possible direction, evaluation is zero, the sample carries "some high number" */
+CY_DEV int bsdf_reflection_sample(const Closure &sc, f3 Ng, f3 I, f3 *eval, f3 *omega_in,
+                                  float *pdf)
+{
+  const f3 N = sc.N;
+  float cosNO = dot(N, I);
+  if (cosNO > 0) {
+    *omega_in = (2 * cosNO) * N - I;
+    if (dot(Ng, *omega_in) > 0) {
+      *pdf = 1e6f;
+      *eval = mk3(1e6f, 1e6f, 1e6f);
+    }
+  }
+  return CY_LABEL_REFLECT | CY_LABEL_SINGULAR;
+}
+CY_DEV int bsdf_refraction_sample(const Closure &sc, f3 I, f3 *eval, f3 *omega_in, float *pdf)
+{
+  f3 R, T;
+  bool inside;
+  float fresnel = fresnel_dielectric(sc.ior, sc.N, I, &R, &T, &inside);
+  if (!inside && fresnel != 1.0f) {
+    *pdf = 1e6f;
+    *eval = mk3(1e6f, 1e6f, 1e6f);
+    *omega_in = T;
+  }
+  return CY_LABEL_TRANSMIT | CY_LABEL_SINGULAR;
+}
 
 /* closure/bsdf.h bsdf_eval: reflect side when dot(Ng, omega_in) >= 0 */
 CY_DEV f3 bsdf_eval(const ShaderDataG &sd, const Closure &sc, f3 omega_in, float *pdf)
@@ -50,6 +156,9 @@ CY_DEV f3 bsdf_eval(const ShaderDataG &sd, const Closure &sc, f3 omega_in, float
       case CY_CLOSURE_BSDF_PRINCIPLED_DIFFUSE_ID:
         eval = bsdf_principled_diffuse_eval_reflect(sc, sd.I, omega_in, pdf);
         break;
+      case CY_CLOSURE_BSDF_OREN_NAYAR_ID:
+        eval = bsdf_oren_nayar_eval_reflect(sc, sd.I, omega_in, pdf);
+        break;
       case CY_CLOSURE_BSDF_MICROFACET_GGX_ID:
       case CY_CLOSURE_BSDF_MICROFACET_GGX_FRESNEL_ID:
       case CY_CLOSURE_BSDF_MICROFACET_GGX_CLEARCOAT_ID:
@@ -62,6 +171,9 @@ CY_DEV f3 bsdf_eval(const ShaderDataG &sd, const Closure &sc, f3 omega_in, float
   }
   else {
     switch (sc.type) {
+      case CY_CLOSURE_BSDF_TRANSLUCENT_ID:
+        eval = bsdf_translucent_eval_transmit(sc, omega_in, pdf);
+        break;
       case CY_CLOSURE_BSDF_MICROFACET_GGX_ID:
       case CY_CLOSURE_BSDF_MICROFACET_GGX_FRESNEL_ID:
       case CY_CLOSURE_BSDF_MICROFACET_GGX_CLEARCOAT_ID:
@@ -84,6 +196,14 @@ CY_DEV int bsdf_sample(const ShaderDataG &sd, const Closure &sc, float randu, fl
       return bsdf_diffuse_sample(sc, sd.Ng, randu, randv, eval, omega_in, pdf);
     case CY_CLOSURE_BSDF_PRINCIPLED_DIFFUSE_ID:
       return bsdf_principled_diffuse_sample(sc, sd.Ng, sd.I, randu, randv, eval, omega_in, pdf);
+    case CY_CLOSURE_BSDF_OREN_NAYAR_ID:
+      return bsdf_oren_nayar_sample(sc, sd.Ng, sd.I, randu, randv, eval, omega_in, pdf);
+    case CY_CLOSURE_BSDF_TRANSLUCENT_ID:
+      return bsdf_translucent_sample(sc, sd.Ng, randu, randv, eval, omega_in, pdf);
+    case CY_CLOSURE_BSDF_REFLECTION_ID:
+      return bsdf_reflection_sample(sc, sd.Ng, sd.I, eval, omega_in, pdf);
+    case CY_CLOSURE_BSDF_REFRACTION_ID:
+      return bsdf_refraction_sample(sc, sd.I, eval, omega_in, pdf);
     case CY_CLOSURE_BSDF_MICROFACET_GGX_ID:
     case CY_CLOSURE_BSDF_MICROFACET_GGX_FRESNEL_ID:
     case CY_CLOSURE_BSDF_MICROFACET_GGX_CLEARCOAT_ID:

@@ -9,7 +9,8 @@
  * perspective camera without DOF / motion, static triangles and instances,
  * point / spot / area / distant lamps, emissive triangles (light_tri.cuh), background
  * colour, SVM nodes of
- * SVM_SUPPORTED_NODES and the Diffuse + Principled(GGX) + Glass(GGX) closures,
+ * svm_nodes.cuh / svm_validate and the Diffuse / Oren-Nayar, Translucent, Principled(GGX),
+ * Glossy, Glass and Refraction (GGX or sharp) closures,
  * opaque shadows, combined pass only.
  */
 #ifndef B200_SHADE_CUH

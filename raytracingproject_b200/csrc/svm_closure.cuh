@@ -1,6 +1,7 @@
 /* svm_closure.cuh - NODE_CLOSURE_BSDF (kernel/svm/svm_closure.h:60-1000) for the
- * closures in scope: Diffuse, Principled (single-scatter GGX distribution, no
- * subsurface), Glossy/Glass GGX.  Included by shade.cuh. */
+ * closures in scope: Diffuse / Oren-Nayar, Translucent, Principled (single-scatter GGX
+ * distribution, no subsurface), Glossy, Glass and Refraction (GGX or sharp).
+ * Included by shade.cuh. */
 #ifndef B200_SVM_CLOSURE_CUH
 #define B200_SVM_CLOSURE_CUH
 
@@ -250,19 +251,117 @@ CY_DEV void svm_node_closure_bsdf(ShaderDataG &sd, float *stack, uint4 node, uin
       break;
     }
     case CY_CLOSURE_BSDF_DIFFUSE_ID: {
-      /* svm_closure.h:465-483 (roughness 0: Lambert) */
+      /* svm_closure.h:465-483: Lambert, or Oren-Nayar when the node has roughness */
       f3 weight = sd.svm_closure_weight * mix_weight;
       Closure *bsdf = bsdf_alloc(sd, weight);
       if (bsdf) {
         bsdf->N = N;
-        bsdf->type = CY_CLOSURE_BSDF_DIFFUSE_ID;
-        sd.flag |= CY_SD_BSDF | CY_SD_BSDF_HAS_EVAL;
+        if (param1 == 0.0f) {
+          bsdf->type = CY_CLOSURE_BSDF_DIFFUSE_ID;
+          sd.flag |= CY_SD_BSDF | CY_SD_BSDF_HAS_EVAL;
+        }
+        else {
+          sd.flag |= bsdf_oren_nayar_setup(bsdf, param1);
+        }
       }
-      (void)param1;
       break;
     }
+    case CY_CLOSURE_BSDF_TRANSLUCENT_ID: {
+      /* svm_closure.h:484-493 */
+      f3 weight = sd.svm_closure_weight * mix_weight;
+      Closure *bsdf = bsdf_alloc(sd, weight);
+      if (bsdf) {
+        bsdf->N = N;
+        bsdf->type = CY_CLOSURE_BSDF_TRANSLUCENT_ID;
+        sd.flag |= CY_SD_BSDF | CY_SD_BSDF_HAS_EVAL;
+      }
+      break;
+    }
+    case CY_CLOSURE_BSDF_REFRACTION_ID:
+    case CY_CLOSURE_BSDF_MICROFACET_GGX_REFRACTION_ID: {
+      /* svm_closure.h:571-608: Refraction BSDF node, sharp or GGX */
+      if (!kd_int(KD_INT_CAUSTICS_REFRACTIVE) && (path_flag & CY_PATH_RAY_DIFFUSE))
+        break;
+      f3 weight = sd.svm_closure_weight * mix_weight;
+      Closure *bsdf = bsdf_alloc(sd, weight);
+      if (bsdf) {
+        bsdf->N = N;
+        bsdf->T = zero3();
+        float eta = fmaxf(param2, 1e-5f);
+        eta = (sd.flag & CY_SD_BACKFACING) ? 1.0f / eta : eta;
+        if (type == CY_CLOSURE_BSDF_REFRACTION_ID) {
+          bsdf->alpha_x = 0.0f;
+          bsdf->alpha_y = 0.0f;
+          bsdf->ior = eta;
+          bsdf->type = CY_CLOSURE_BSDF_REFRACTION_ID;
+          sd.flag |= CY_SD_BSDF;
+        }
+        else {
+          float roughness = sqr(param1);
+          bsdf->alpha_x = roughness;
+          bsdf->alpha_y = roughness;
+          bsdf->ior = eta;
+          sd.flag |= bsdf_microfacet_ggx_refraction_setup(bsdf);
+        }
+      }
+      break;
+    }
+    case CY_CLOSURE_BSDF_SHARP_GLASS_ID:
+    case CY_CLOSURE_BSDF_MICROFACET_GGX_GLASS_ID: {
+      /* svm_closure.h:609-660 + svm_node_glass_setup :25-58: Glass BSDF node = a
+       * reflection and a refraction closure weighted by the dielectric Fresnel term */
+      const bool refl_ok = kd_int(KD_INT_CAUSTICS_REFLECTIVE) != 0;
+      const bool refr_ok = kd_int(KD_INT_CAUSTICS_REFRACTIVE) != 0;
+      if (!refl_ok && !refr_ok && (path_flag & CY_PATH_RAY_DIFFUSE))
+        break;
+      f3 weight = sd.svm_closure_weight * mix_weight;
+      float eta = fmaxf(param2, 1e-5f);
+      eta = (sd.flag & CY_SD_BACKFACING) ? 1.0f / eta : eta;
+      float cosNO = dot(N, sd.I);
+      float fresnel = fresnel_dielectric_cos(cosNO, eta);
+      float roughness = sqr(param1);
+      const bool sharp = (type == CY_CLOSURE_BSDF_SHARP_GLASS_ID);
+      if (refl_ok || (path_flag & CY_PATH_RAY_DIFFUSE) == 0) {
+        Closure *bsdf = bsdf_alloc(sd, weight * fresnel);
+        if (bsdf) {
+          bsdf->N = N;
+          bsdf->T = zero3();
+          if (sharp) {
+            bsdf->alpha_x = bsdf->alpha_y = 0.0f;
+            bsdf->ior = 0.0f;
+            bsdf->type = CY_CLOSURE_BSDF_REFLECTION_ID;
+            sd.flag |= CY_SD_BSDF;
+          }
+          else {
+            bsdf->alpha_x = bsdf->alpha_y = roughness;
+            bsdf->ior = eta;
+            sd.flag |= bsdf_microfacet_ggx_setup(bsdf);
+          }
+        }
+      }
+      if (refr_ok || (path_flag & CY_PATH_RAY_DIFFUSE) == 0) {
+        Closure *bsdf = bsdf_alloc(sd, weight * (1.0f - fresnel));
+        if (bsdf) {
+          bsdf->N = N;
+          bsdf->T = zero3();
+          if (sharp) {
+            bsdf->alpha_x = bsdf->alpha_y = 0.0f;
+            bsdf->ior = eta;
+            bsdf->type = CY_CLOSURE_BSDF_REFRACTION_ID;
+            sd.flag |= CY_SD_BSDF;
+          }
+          else {
+            bsdf->alpha_x = bsdf->alpha_y = roughness;
+            bsdf->ior = eta;
+            sd.flag |= bsdf_microfacet_ggx_refraction_setup(bsdf);
+          }
+        }
+      }
+      break;
+    }
+    case CY_CLOSURE_BSDF_REFLECTION_ID:
     case CY_CLOSURE_BSDF_MICROFACET_GGX_ID: {
-      /* svm_closure.h:500-560, GGX glossy */
+      /* svm_closure.h:500-560: Glossy BSDF node, sharp or GGX (isotropic) */
       if (!kd_int(KD_INT_CAUSTICS_REFLECTIVE) && (path_flag & CY_PATH_RAY_DIFFUSE))
         break;
       f3 weight = sd.svm_closure_weight * mix_weight;
@@ -274,7 +373,13 @@ CY_DEV void svm_node_closure_bsdf(ShaderDataG &sd, float *stack, uint4 node, uin
         bsdf->alpha_x = roughness;
         bsdf->alpha_y = roughness;
         bsdf->T = zero3();
-        sd.flag |= bsdf_microfacet_ggx_setup(bsdf);
+        if (type == CY_CLOSURE_BSDF_REFLECTION_ID) {
+          bsdf->type = CY_CLOSURE_BSDF_REFLECTION_ID;
+          sd.flag |= CY_SD_BSDF;
+        }
+        else {
+          sd.flag |= bsdf_microfacet_ggx_setup(bsdf);
+        }
       }
       break;
     }

@@ -1216,7 +1216,20 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
           }
           i += 6;
         }
-        else if (type == CY_CLOSURE_BSDF_DIFFUSE_ID || type == CY_CLOSURE_BSDF_MICROFACET_GGX_ID) {
+        else if (type == CY_CLOSURE_BSDF_REFLECTION_ID ||
+                 type == CY_CLOSURE_BSDF_MICROFACET_GGX_ID) {
+          /* the tangent input of the Anisotropic BSDF node is not implemented */
+          if (i + 1 >= n_nodes || nodes[4 * (i + 1) + 1] != (uint32_t)CY_SVM_STACK_INVALID) {
+            why = "anisotropic glossy closures (tangent input) are outside the hot-path scope";
+            return false;
+          }
+          i += 2;
+        }
+        else if (type == CY_CLOSURE_BSDF_DIFFUSE_ID || type == CY_CLOSURE_BSDF_TRANSLUCENT_ID ||
+                 type == CY_CLOSURE_BSDF_REFRACTION_ID ||
+                 type == CY_CLOSURE_BSDF_MICROFACET_GGX_REFRACTION_ID ||
+                 type == CY_CLOSURE_BSDF_SHARP_GLASS_ID ||
+                 type == CY_CLOSURE_BSDF_MICROFACET_GGX_GLASS_ID) {
           i += 2;
         }
         else {

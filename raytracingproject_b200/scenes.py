@@ -200,6 +200,41 @@ def _procedural_shader(name, variant=0):
     )
 
 
+def _node_shader(name, body, out):
+    return ('<shader name="%s">\n%s  <connect from="%s" to="output surface"/>\n</shader>\n'
+            % (name, body, out))
+
+
+def _closure_shaders(variant):
+    """Materials made of the BSDF nodes beyond Diffuse / Principled / Glossy-GGX: Glass
+    (GGX and sharp), Refraction (GGX and sharp), sharp Glossy, Translucent, Oren-Nayar."""
+    white = _node_shader("white", '  <diffuse_bsdf name="d" color="0.73 0.73 0.73" '
+                         'roughness="0.6"/>\n', "d bsdf")
+    red = _node_shader(
+        "red", '  <diffuse_bsdf name="d" color="0.65 0.05 0.05" roughness="0.3"/>\n'
+        '  <glossy_bsdf name="g" distribution="sharp" color="0.9 0.9 0.9"/>\n'
+        '  <mix_closure name="m" fac="0.15"/>\n'
+        '  <connect from="d bsdf" to="m closure1"/>\n  <connect from="g bsdf" to="m closure2"/>\n',
+        "m closure")
+    green = _node_shader(
+        "green", '  <diffuse_bsdf name="d" color="0.12 0.45 0.15"/>\n'
+        '  <translucent_bsdf name="t" color="0.3 0.6 0.3"/>\n'
+        '  <mix_closure name="m" fac="0.4"/>\n'
+        '  <connect from="d bsdf" to="m closure1"/>\n  <connect from="t bsdf" to="m closure2"/>\n',
+        "m closure")
+    if variant == 0:
+        metal = _node_shader("metal", '  <glass_bsdf name="g" distribution="GGX" roughness="0.15" '
+                             'IOR="1.45" color="0.95 0.97 1"/>\n', "g bsdf")
+        glass = _node_shader("glass", '  <glass_bsdf name="g" distribution="sharp" IOR="1.5" '
+                             'color="1 0.95 0.9"/>\n', "g bsdf")
+    else:
+        metal = _node_shader("metal", '  <refraction_bsdf name="g" distribution="GGX" '
+                             'roughness="0.2" IOR="1.33" color="0.9 0.95 1"/>\n', "g bsdf")
+        glass = _node_shader("glass", '  <refraction_bsdf name="g" distribution="sharp" IOR="1.2" '
+                             'color="1 1 1"/>\n', "g bsdf")
+    return white + red + green + metal + glass
+
+
 def _integrator(max_bounce, diffuse=None, glossy=None, transmission=None, transparent=8,
                 clamp_indirect=0.0, seed=0, light_threshold=0.01, caustics=True):
     diffuse = max_bounce if diffuse is None else diffuse
@@ -371,16 +406,23 @@ def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
     xml += _header(width, height, cam, fov,
                    _integrator(max_bounce, clamp_indirect=10.0), nearclip=0.01, farclip=100.0)
     xml += _background((0, 0, 0), 0.0)
-    xml += _diffuse_shader("white", (0.73, 0.73, 0.73))
-    xml += _diffuse_shader("red", (0.65, 0.05, 0.05))
-    xml += _diffuse_shader("green", (0.12, 0.45, 0.15))
-    if materials == "procedural":
+    if materials in ("closures", "closures2"):
+        xml += _closure_shaders(0 if materials == "closures" else 1)
+    else:
+        xml += _diffuse_shader("white", (0.73, 0.73, 0.73))
+        xml += _diffuse_shader("red", (0.65, 0.05, 0.05))
+        xml += _diffuse_shader("green", (0.12, 0.45, 0.15))
+    if materials in ("closures", "closures2"):
+        pass
+    elif materials == "procedural":
         xml += _procedural_shader("metal", 0)
     elif materials in ("principled", "metal"):
         xml += _principled_shader("metal", (0.9, 0.85, 0.7), 1.0, 0.2, 0.5, 0.0, 1.45, distribution)
     else:
         xml += _diffuse_shader("metal", (0.9, 0.85, 0.7))
-    if materials == "procedural":
+    if materials in ("closures", "closures2"):
+        pass
+    elif materials == "procedural":
         xml += _procedural_shader("glass", 1)
     elif materials in ("principled", "glass"):
         xml += _principled_shader("glass", (1, 1, 1), 0.0, 0.0, 0.5, 1.0, 1.45, distribution)

@@ -22,6 +22,15 @@ def principled_cases():
     }
 
 
+def closure_cases():
+    """BSDF nodes beyond Diffuse / Principled / Glossy-GGX: Glass and Refraction (GGX and
+    sharp), sharp Glossy, Translucent, Oren-Nayar - 8 bounces in a Cornell box."""
+    return {
+        "cornell_closures": scenes.cornell(W, H, materials="closures"),
+        "cornell_closures2": scenes.cornell(W, H, materials="closures2"),
+    }
+
+
 def light_cases():
     """Lamp types of kernel_light.h beyond the configs' point / sun / area: a spot with
     a smooth edge, and three lamps of different types in one light distribution."""

@@ -6,7 +6,7 @@ gates hold at any spp, not only at 1024."""
 import numpy as np
 import pytest
 
-from scene_cases import light_cases, principled_cases, small_cases
+from scene_cases import closure_cases, light_cases, principled_cases, small_cases
 
 pytestmark = pytest.mark.gpu
 
@@ -71,6 +71,20 @@ def test_lamp_types_match_reference(ref, device, name):
         ref_img, _ = rs.render(0, SPP, tile_size=64)
         got = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP)
         assert ref_img[..., :3].max() > 0.0
+        image_gates(ref_img, got, SPP, name)
+    finally:
+        rs.close()
+
+
+@pytest.mark.parametrize("name", ["cornell_closures", "cornell_closures2"])
+def test_closure_nodes_match_reference(ref, device, name):
+    desc = closure_cases()[name]
+    rs = ref.build_scene(desc)
+    try:
+        device.upload_scene(rs.device_arrays())
+        ref_img, _ = rs.render(0, SPP, tile_size=64)
+        got = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP)
+        print(name, device.stats())
         image_gates(ref_img, got, SPP, name)
     finally:
         rs.close()
