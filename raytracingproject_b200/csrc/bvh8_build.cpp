@@ -700,6 +700,14 @@ bool build_bvh8(const BVH2Input &in, BVH8Output &out, std::string &error)
     uint32_t r = b.blas_root8[p.second];
     memcpy(&out.records[p.first], &r, 4);
   }
+  /* The traversal stack (BVH8_STACK_SIZE = 64 entries, traverse.cuh) holds at most two
+   * entries per level of the TLAS and of one BLAS plus two for the instance push; a
+   * tree deeper than this bound (a degenerate BVH2 chain) is refused, not truncated. */
+  if (4u * b.max_depth + 2u > 64u) {
+    error = "BVH8 depth " + std::to_string(b.max_depth) +
+            " exceeds what the traversal stack covers (15)";
+    return false;
+  }
   out.max_depth = b.max_depth;
   out.sah_cost = (float)b.sah;
   out.build_ms =
