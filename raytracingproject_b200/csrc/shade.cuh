@@ -34,6 +34,23 @@ struct PathStateG {
   float min_ray_pdf, ray_pdf, ray_t;
 };
 
+/* the bounce counters the Light Path node reads, passed BY VALUE into the (out-of-line)
+ * SVM interpreter: handing it a pointer to the PathStateG would force the whole state of
+ * k_shade_surface out of registers */
+struct PathDepths {
+  short bounce, diffuse, glossy, transparent, transmission;
+};
+CY_DEV PathDepths path_depths(const PathStateG &s)
+{
+  PathDepths d;
+  d.bounce = (short)s.bounce;
+  d.diffuse = (short)s.diffuse_bounce;
+  d.glossy = (short)s.glossy_bounce;
+  d.transparent = (short)s.transparent_bounce;
+  d.transmission = (short)s.transmission_bounce;
+  return d;
+}
+
 /* ---------------------------------------------------------------- hashing */
 
 /* util/util_hash.h:28-93 (Jenkins lookup3 final) */
@@ -413,7 +430,8 @@ CY_DEV bool stack_valid(uint32_t a)
 /* svm/svm.h:220-300 for the supported opcodes.  max_closures = 0 evaluates only
  * emission / background weights (PATH_RAY_EMISSION / TERMINATE evaluation,
  * kernel_shader.h:1063-1075). */
-__device__ __noinline__ void svm_eval_nodes(ShaderDataG &sd, uint32_t path_flag, int max_closures)
+__device__ __noinline__ void svm_eval_nodes(ShaderDataG &sd, PathDepths depths,
+                                            uint32_t path_flag, int max_closures)
 {
   float stack[SVM_STACK_GPU];
   sd.num_closure = 0;
@@ -558,6 +576,19 @@ __device__ __noinline__ void svm_eval_nodes(ShaderDataG &sd, uint32_t path_flag,
       case CY_NODE_CLAMP:
         svm_node_clamp(stack, node, &offset);
         break;
+      case CY_NODE_LIGHT_PATH:
+        svm_node_light_path(sd, depths, stack, node.y, node.z, path_flag);
+        break;
+      case CY_NODE_LIGHT_FALLOFF:
+        svm_node_light_falloff(sd, stack, node);
+        break;
+      case CY_NODE_RGB_RAMP:
+        svm_node_rgb_ramp(stack, node, &offset);
+        break;
+      case CY_NODE_RGB_CURVES:
+      case CY_NODE_VECTOR_CURVES:
+        svm_node_curves(stack, node, &offset);
+        break;
       default:
         /* refused at bind time by svm_validate(); unreachable */
         return;
@@ -566,14 +597,14 @@ __device__ __noinline__ void svm_eval_nodes(ShaderDataG &sd, uint32_t path_flag,
 }
 
 /* kernel_shader.h:1057-1110 */
-CY_DEV void shader_eval_surface(ShaderDataG &sd, uint32_t path_flag)
+CY_DEV void shader_eval_surface(ShaderDataG &sd, PathDepths depths, uint32_t path_flag)
 {
   int max_closures;
   if (path_flag & (CY_PATH_RAY_TERMINATE | CY_PATH_RAY_SHADOW | CY_PATH_RAY_EMISSION))
     max_closures = 0;
   else
     max_closures = min(kd_int(KD_INT_MAX_CLOSURES), MAX_CLOSURES_GPU);
-  svm_eval_nodes(sd, path_flag, max_closures);
+  svm_eval_nodes(sd, depths, path_flag, max_closures);
 }
 
 /* kernel_shader.h:530-555 */
@@ -1098,7 +1129,8 @@ CY_DEV bool shader_constant_emission_eval(int shader, f3 *eval)
 }
 
 /* kernel_emission.h:20-98.  `emission_sd` is scratch. */
-CY_DEV f3 direct_emissive_eval(ShaderDataG &emission_sd, LightSampleG *ls, f3 I, float t)
+CY_DEV f3 direct_emissive_eval(ShaderDataG &emission_sd, PathDepths depths, LightSampleG *ls,
+                               f3 I, float t)
 {
   f3 eval = zero3();
   if (shader_constant_emission_eval(ls->shader, &eval)) {
@@ -1148,7 +1180,7 @@ CY_DEV f3 direct_emissive_eval(ShaderDataG &emission_sd, LightSampleG *ls, f3 I,
       }
     }
     ls->Ng = emission_sd.Ng;
-    shader_eval_surface(emission_sd, CY_PATH_RAY_EMISSION);
+    shader_eval_surface(emission_sd, depths, CY_PATH_RAY_EMISSION);
     /* shader_emissive_eval: emissive_simple_eval(Ng, I) * weight */
     if (emission_sd.flag & CY_SD_EMISSION) {
       float cosNO = fabsf(dot(emission_sd.Ng, emission_sd.I));
@@ -1193,7 +1225,7 @@ CY_DEV f3 indirect_background(ShaderDataG &emission_sd, const PathStateG &state,
     emission_sd.type = 0;
     emission_sd.u = emission_sd.v = 0.0f;
     emission_sd.dPdu = zero3();
-    shader_eval_surface(emission_sd, state.flag | CY_PATH_RAY_EMISSION);
+    shader_eval_surface(emission_sd, path_depths(state), state.flag | CY_PATH_RAY_EMISSION);
     if (emission_sd.flag & CY_SD_EMISSION)
       L = emission_sd.closure_emission_background;
   }

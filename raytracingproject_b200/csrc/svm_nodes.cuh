@@ -517,4 +517,158 @@ CY_DEV void svm_node_clamp(float *stack, uint4 node, int *offset)
     stack[node.w] = nodes_clamp(value, lo, hi);
 }
 
+/* svm_light_path.h:21-75 */
+CY_DEV void svm_node_light_path(const ShaderDataG &sd, PathDepths depths, float *stack,
+                                uint32_t type, uint32_t out_offset, uint32_t path_flag)
+{
+  float info = 0.0f;
+  switch (type) {
+    case CY_NODE_LP_camera:
+      info = (path_flag & CY_PATH_RAY_CAMERA) ? 1.0f : 0.0f;
+      break;
+    case CY_NODE_LP_shadow:
+      info = (path_flag & CY_PATH_RAY_SHADOW) ? 1.0f : 0.0f;
+      break;
+    case CY_NODE_LP_diffuse:
+      info = (path_flag & CY_PATH_RAY_DIFFUSE) ? 1.0f : 0.0f;
+      break;
+    case CY_NODE_LP_glossy:
+      info = (path_flag & CY_PATH_RAY_GLOSSY) ? 1.0f : 0.0f;
+      break;
+    case CY_NODE_LP_singular:
+      info = (path_flag & CY_PATH_RAY_SINGULAR) ? 1.0f : 0.0f;
+      break;
+    case CY_NODE_LP_reflection:
+      info = (path_flag & CY_PATH_RAY_REFLECT) ? 1.0f : 0.0f;
+      break;
+    case CY_NODE_LP_transmission:
+      info = (path_flag & CY_PATH_RAY_TRANSMIT) ? 1.0f : 0.0f;
+      break;
+    case CY_NODE_LP_volume_scatter:
+      info = (path_flag & CY_PATH_RAY_VOLUME_SCATTER) ? 1.0f : 0.0f;
+      break;
+    case CY_NODE_LP_backfacing:
+      info = (sd.flag & CY_SD_BACKFACING) ? 1.0f : 0.0f;
+      break;
+    case CY_NODE_LP_ray_length:
+      info = sd.ray_length;
+      break;
+    case CY_NODE_LP_ray_depth:
+      info = (float)depths.bounce;
+      break;
+    case CY_NODE_LP_ray_diffuse:
+      info = (float)depths.diffuse;
+      break;
+    case CY_NODE_LP_ray_glossy:
+      info = (float)depths.glossy;
+      break;
+    case CY_NODE_LP_ray_transparent:
+      info = (float)depths.transparent;
+      break;
+    case CY_NODE_LP_ray_transmission:
+      info = (float)depths.transmission;
+      break;
+  }
+  stack[out_offset] = info;
+}
+
+/* svm_light_path.h:79-112 */
+CY_DEV void svm_node_light_falloff(const ShaderDataG &sd, float *stack, uint4 node)
+{
+  uint32_t strength_offset, smooth_offset, out_offset;
+  unpack_uchar3(node.z, &strength_offset, &smooth_offset, &out_offset);
+  float strength = stack[strength_offset];
+  switch (node.y) {
+    case CY_NODE_LIGHT_FALLOFF_QUADRATIC:
+      break;
+    case CY_NODE_LIGHT_FALLOFF_LINEAR:
+      strength *= sd.ray_length;
+      break;
+    case CY_NODE_LIGHT_FALLOFF_CONSTANT:
+      strength *= sd.ray_length * sd.ray_length;
+      break;
+  }
+  const float smooth = stack[smooth_offset];
+  if (smooth > 0.0f) {
+    const float squared = sd.ray_length * sd.ray_length;
+    /* distant lamps have ray_length FLT_MAX: the square overflows */
+    if (isfinite_safe(squared))
+      strength *= squared / (smooth + squared);
+  }
+  stack[out_offset] = strength;
+}
+
+/* svm_ramp.h:24-110: ColorRamp and RGB / vector curves; the table is stored in the SVM
+ * program right behind the instruction, one float4 per entry */
+CY_DEV float4 ramp_fetch(int offset)
+{
+  const uint4 n = __ldg(&g_scene.svm_nodes[offset]);
+  return make_float4(__uint_as_float(n.x), __uint_as_float(n.y), __uint_as_float(n.z),
+                     __uint_as_float(n.w));
+}
+CY_DEV float4 f4_lerp_terms(float wa, float4 a, float wb, float4 b)
+{
+  return make_float4(wa * a.x + wb * b.x, wa * a.y + wb * b.y, wa * a.z + wb * b.z,
+                     wa * a.w + wb * b.w);
+}
+CY_DEV float4 rgb_ramp_lookup(int offset, float f, bool interpolate, bool extrapolate,
+                              int table_size)
+{
+  if ((f < 0.0f || f > 1.0f) && extrapolate) {
+    float4 t0, t1;
+    if (f < 0.0f) {
+      t0 = ramp_fetch(offset);
+      t1 = ramp_fetch(offset + 1);
+      f = -f;
+    }
+    else {
+      t0 = ramp_fetch(offset + table_size - 1);
+      t1 = ramp_fetch(offset + table_size - 2);
+      f = f - 1.0f;
+    }
+    /* t0 + (t0 - t1) * f * (table_size - 1), evaluated left to right */
+    const float n1 = (float)(table_size - 1);
+    return make_float4(t0.x + (t0.x - t1.x) * f * n1, t0.y + (t0.y - t1.y) * f * n1,
+                       t0.z + (t0.z - t1.z) * f * n1, t0.w + (t0.w - t1.w) * f * n1);
+  }
+  f = saturate(f) * (table_size - 1);
+  const int i = min(max((int)f, 0), table_size - 1);
+  const float t = f - (float)i;
+  float4 a = ramp_fetch(offset + i);
+  if (interpolate && t > 0.0f)
+    a = f4_lerp_terms(1.0f - t, a, t, ramp_fetch(offset + i + 1));
+  return a;
+}
+CY_DEV void svm_node_rgb_ramp(float *stack, uint4 node, int *offset)
+{
+  uint32_t fac_offset, color_offset, alpha_offset;
+  unpack_uchar3(node.y, &fac_offset, &color_offset, &alpha_offset);
+  const int table_size = (int)__ldg(&g_scene.svm_nodes[*offset]).x;
+  (*offset)++;
+  const float4 color = rgb_ramp_lookup(*offset, stack[fac_offset], node.z != 0, false, table_size);
+  if (stack_valid(color_offset))
+    stack_store_float3(stack, color_offset, mk3(color.x, color.y, color.z));
+  if (stack_valid(alpha_offset))
+    stack[alpha_offset] = color.w;
+  *offset += table_size;
+}
+CY_DEV void svm_node_curves(float *stack, uint4 node, int *offset)
+{
+  uint32_t fac_offset, color_offset, out_offset;
+  unpack_uchar3(node.y, &fac_offset, &color_offset, &out_offset);
+  const int table_size = (int)__ldg(&g_scene.svm_nodes[*offset]).x;
+  (*offset)++;
+  const float fac = stack[fac_offset];
+  f3 color = stack_load_float3(stack, color_offset);
+  const float min_x = __uint_as_float(node.z), max_x = __uint_as_float(node.w);
+  const float range_x = max_x - min_x;
+  const f3 relpos = (color - mk3(min_x, min_x, min_x)) / range_x;
+  const float r = rgb_ramp_lookup(*offset, relpos.x, true, true, table_size).x;
+  const float g = rgb_ramp_lookup(*offset, relpos.y, true, true, table_size).y;
+  const float b = rgb_ramp_lookup(*offset, relpos.z, true, true, table_size).z;
+  color = (1.0f - fac) * color + fac * mk3(r, g, b);
+  stack_store_float3(stack, out_offset, color);
+  *offset += table_size;
+}
+
 #endif /* B200_SVM_NODES_CUH */

@@ -545,7 +545,7 @@ CY_DEV void path_lamp_emission(PathStateG &st, f3 rayP, f3 rayD, float isect_t, 
             ((ls.shader & CY_SHADER_EXCLUDE_SCATTER) && (st.flag & CY_PATH_RAY_VOLUME_SCATTER)))
           continue;
       }
-      f3 lamp_L = direct_emissive_eval(emission_sd, &ls, -rayD, ls.t);
+      f3 lamp_L = direct_emissive_eval(emission_sd, path_depths(st), &ls, -rayD, ls.t);
       if (!(st.flag & CY_PATH_RAY_MIS_SKIP)) {
         float mis_weight = power_heuristic(st.ray_pdf, ls.pdf);
         lamp_L *= mis_weight;
@@ -560,7 +560,10 @@ CY_DEV void path_lamp_emission(PathStateG &st, f3 rayP, f3 rayD, float isect_t, 
 
 /* ----------------------------------------------------- shade_background */
 
-__global__ void __launch_bounds__(WF_BLOCK) k_shade_background(PathSoA p)
+#ifndef BG_MIN_BLOCKS
+#  define BG_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(PathSoA p)
 {
   WFCounters *c = p.counters;
   const unsigned int n = c->offsets[1]; /* key 0 segment */
@@ -653,7 +656,7 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS) k_shade_surface(Pa
       bool alive = !path_state_ao_bounce(st); /* kernel_path.h:560-562 */
       if (alive) {
         shader_setup_from_ray(sd, hit_prim, hit_object, hit.x, hit.y, hit.z, rayP, rayD);
-        shader_eval_surface(sd, st.flag);
+        shader_eval_surface(sd, path_depths(st), st.flag);
         shader_prepare_closures(sd, st);
 
         /* kernel_path_shader_apply - kernel_path.h:254-321 (no holdout / shadow catcher;
@@ -729,7 +732,7 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS) k_shade_surface(Pa
               }
               else {
                 ShaderDataG scratch;
-                light_eval = direct_emissive_eval(scratch, &ls, -ls.D, ls.t);
+                light_eval = direct_emissive_eval(scratch, path_depths(st), &ls, -ls.D, ls.t);
               }
             }
             if (!is_zero(light_eval)) {
@@ -1178,10 +1181,30 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
       case CY_NODE_COMBINE_VECTOR:
         i += 1;
         break;
+      case CY_NODE_LIGHT_PATH:
+      case CY_NODE_LIGHT_FALLOFF:
+        i += 1;
+        break;
       case CY_NODE_VALUE_V:
       case CY_NODE_CLAMP: /* + one node of default values */
         i += 2;
         break;
+      case CY_NODE_RGB_RAMP:
+      case CY_NODE_RGB_CURVES:
+      case CY_NODE_VECTOR_CURVES: {
+        /* the instruction, one node holding the table size, then the table itself */
+        if (i + 1 >= n_nodes) {
+          why = "truncated ramp node";
+          return false;
+        }
+        const size_t table_size = nodes[4 * (i + 1)];
+        if (table_size < 2 || i + 2 + table_size > n_nodes) {
+          why = "ramp table runs past the end of the SVM program";
+          return false;
+        }
+        i += 2 + table_size;
+        break;
+      }
       case CY_NODE_VECTOR_MATH: /* the three-input operator carries an extra node */
         i += (nodes[4 * i + 1] == CY_NODE_VECTOR_MATH_WRAP) ? 2 : 1;
         break;
@@ -1243,7 +1266,7 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
               " is outside the hot-path scope (supported: closures diffuse/principled-GGX/"
               "glossy-GGX/emission/background, mix closure, value, geometry, convert, fresnel, "
               "layer weight, math, vector math, mix, invert, gamma, bright/contrast, "
-              "separate/combine, clamp)";
+              "separate/combine, clamp, light path, light falloff, RGB ramp, curves)";
         return false;
     }
   }

@@ -179,6 +179,10 @@ def _procedural_shader(name, variant=0):
         '  <connect from="mx2 color" to="mx3 color1"/>\n'
         '  <brightness_contrast name="bc" bright="0.04" contrast="0.15"/>\n'
         '  <connect from="mx3 color" to="bc color"/>\n'
+        '  <light_path name="lp"/>\n'
+        '  <math name="m6" type="multiply_add" value2="0.03" value3="0.01"/>\n'
+        '  <connect from="lp ray_depth" to="m6 value1"/>\n'
+        '  <connect from="m6 value" to="bc bright"/>\n'
         '  <gamma name="gm" gamma="1.3"/>\n'
         '  <connect from="bc color" to="gm color"/>\n'
         '  <invert name="inv" fac="0.1"/>\n'
@@ -280,7 +284,8 @@ def default_cube(width=1920, height=1080, spp=64, material="principled", max_bou
                  lights="point"):
     """BASELINE config 1 - Blender's startup scene, values extracted from
     release/datafiles/startup.blend.  `lights`: "point" (the
-    startup scene), "spot" (the same lamp as a 50 degree spot aimed at the cube, soft
+    startup scene), "falloff" (its lamp shader goes through a Light Falloff node), "spot"
+    (the same lamp as a 50 degree spot aimed at the cube, soft
     edge) or "mixed" (point + round area + sun: three entries in the light
     distribution) - variants used by the parity tests only."""
     cam = euler_xyz_camera((7.358891, -6.925791, 4.958309), (1.109319, 0.0, 0.814928))
@@ -296,12 +301,19 @@ def default_cube(width=1920, height=1080, spp=64, material="principled", max_bou
         xml += _principled_shader("cube", (0.8, 0.8, 0.8), 0.0, 0.5, 0.5)
     else:
         xml += _diffuse_shader("cube", (0.8, 0.8, 0.8))
-    xml += _emission_shader("lamp", (1, 1, 1), 1.0)
+    if lights == "falloff":
+        # lamp shader with a Light Falloff node: evaluated per light sample, not constant
+        xml += _node_shader(
+            "lamp", '  <light_falloff name="lf" strength="1.4" smooth="2.5"/>\n'
+            '  <emission name="e" color="1 0.95 0.9"/>\n'
+            '  <connect from="lf linear" to="e strength"/>\n', "e emission")
+    else:
+        xml += _emission_shader("lamp", (1, 1, 1), 1.0)
     co = np.array([4.076245, 1.005454, 5.903862])
     aim = -co / np.linalg.norm(co)
     point = ('<light type="point" co="%s" size="0.1" strength="1000 1000 1000" '
              'use_mis="true"/>\n' % " ".join(_f(c) for c in co))
-    if lights == "point":
+    if lights in ("point", "falloff"):
         body = point
     elif lights == "spot":
         body = ('<light type="spot" co="%s" dir="%s" spot_angle="%s" spot_smooth="0.25" size="0.1" '
@@ -692,6 +704,46 @@ def node_chart(width=256, height=144, spp=1):
         '  <connect from="a value" to="e color"/>\n'           # float -> colour
         '  <connect from="e emission" to="output surface"/>\n')
     shaders.append(extra4)
+
+    # light path (camera-ray flags, ray length, depth), ColorRamp, RGB / vector curves
+    rng = np.random.default_rng(5)
+    ramp = np.sort(rng.random((8, 3)), axis=0)
+    ramp_attr = " ".join("%.6g" % v for v in ramp.ravel())
+    alpha_attr = " ".join("%.6g" % v for v in np.linspace(0.2, 1.0, 8))
+    curve = np.clip(np.linspace(0, 1, 16)[:, None] ** np.array([0.5, 1.0, 2.0]), 0, 1)
+    curve_attr = " ".join("%.6g" % v for v in curve.ravel())
+    extra5 = head + (
+        '  <light_path name="lp"/>\n'
+        '  <math name="rl" type="multiply" value2="0.08"/>\n'
+        '  <connect from="lp ray_length" to="rl value1"/>\n'
+        '  <math name="dp" type="add" value2="0.25"/>\n'
+        '  <connect from="lp ray_depth" to="dp value1"/>\n'
+        '  <combine_xyz name="out"/>\n'
+        '  <connect from="lp is_camera_ray" to="out x"/>\n'
+        '  <connect from="rl value" to="out y"/>\n'
+        '  <connect from="dp value" to="out z"/>\n')
+    shaders.append(extra5 + tail)
+    for interp in ("true", "false"):
+        extra6 = head + (
+            '  <rgb_ramp name="rr" ramp="%s" ramp_alpha="%s" interpolate="%s"/>\n'
+            '  <connect from="a value" to="rr fac"/>\n'
+            '  <mix name="mo" type="multiply" fac="1"/>\n'
+            '  <connect from="rr color" to="mo color1"/>\n'
+            '  <connect from="rr alpha" to="mo color2"/>\n'
+            '  <vector_math name="out" type="add" vector2="0 0 0"/>\n'
+            '  <connect from="mo color" to="out vector1"/>\n' % (ramp_attr, alpha_attr, interp))
+        shaders.append(extra6 + tail)
+    for kind in ("rgb_curves", "vector_curves"):
+        sock = "value"  # cycles_xml matches the socket's internal name
+        extra7 = head + (
+            '  <combine_xyz name="c1" z="0.3"/>\n'
+            '  <connect from="a value" to="c1 x"/>\n'
+            '  <connect from="b value" to="c1 y"/>\n'
+            '  <%s name="cv" curves="%s" min_x="-0.25" max_x="1.25" fac="0.8"/>\n'
+            '  <connect from="c1 vector" to="cv %s"/>\n'
+            '  <vector_math name="out" type="add" vector2="0 0 0"/>\n'
+            '  <connect from="cv %s" to="out vector1"/>\n' % (kind, curve_attr, sock, sock))
+        shaders.append(extra7 + tail)
 
     n = len(shaders)
     cols = 12

@@ -37,6 +37,7 @@ def light_cases():
     return {
         "cube_spot": scenes.default_cube(W, H, material="principled", lights="spot"),
         "cube_mixed_lights": scenes.default_cube(W, H, material="diffuse", lights="mixed"),
+        "cube_light_falloff": scenes.default_cube(W, H, material="diffuse", lights="falloff"),
         # emissive triangles in the light distribution (kernel_light.h:302-581)
         "cornell_mesh_light": scenes.cornell(W, H, materials="diffuse", light="mesh"),
         "cornell_mesh_light_instanced": scenes.cornell(W, H, materials="principled",

@@ -61,7 +61,7 @@ def test_principled_image_matches_reference(ref, device, name):
         rs.close()
 
 
-@pytest.mark.parametrize("name", ["cube_spot", "cube_mixed_lights", "cornell_mesh_light",
+@pytest.mark.parametrize("name", ["cube_spot", "cube_mixed_lights", "cube_light_falloff", "cornell_mesh_light",
                                   "cornell_mesh_light_instanced"])
 def test_lamp_types_match_reference(ref, device, name):
     desc = light_cases()[name]
