@@ -204,6 +204,12 @@ CY_DEV int bsdf_sample(const ShaderDataG &sd, const Closure &sc, float randu, fl
       return bsdf_reflection_sample(sc, sd.Ng, sd.I, eval, omega_in, pdf);
     case CY_CLOSURE_BSDF_REFRACTION_ID:
       return bsdf_refraction_sample(sc, sd.I, eval, omega_in, pdf);
+    case CY_CLOSURE_BSDF_TRANSPARENT_ID:
+      /* closure/bsdf_transparent.h:103-125: straight through */
+      *omega_in = -sd.I;
+      *pdf = 1;
+      *eval = one3();
+      return CY_LABEL_TRANSMIT | CY_LABEL_TRANSPARENT;
     case CY_CLOSURE_BSDF_MICROFACET_GGX_ID:
     case CY_CLOSURE_BSDF_MICROFACET_GGX_FRESNEL_ID:
     case CY_CLOSURE_BSDF_MICROFACET_GGX_CLEARCOAT_ID:

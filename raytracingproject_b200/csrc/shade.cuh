@@ -218,6 +218,7 @@ struct ShaderDataG {
   float u, v, ray_length;
   f3 svm_closure_weight;
   f3 closure_emission_background;
+  f3 closure_transparent_extinction; /* valid when flag & SD_TRANSPARENT */
   int num_closure, num_closure_left;
   Closure closure[MAX_CLOSURES_GPU];
 };

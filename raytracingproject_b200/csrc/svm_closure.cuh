@@ -277,6 +277,43 @@ CY_DEV void svm_node_closure_bsdf(ShaderDataG &sd, float *stack, uint4 node, uin
       }
       break;
     }
+    case CY_CLOSURE_BSDF_TRANSPARENT_ID: {
+      /* bsdf_transparent_setup - closure/bsdf_transparent.h:38-85: all transparent
+       * closures of a shader merge into one; the summed weight is what shadow rays
+       * multiply by (shader_bsdf_transparency) */
+      const f3 weight = sd.svm_closure_weight * mix_weight;
+      const float sample_weight = fabsf(average(weight));
+      if (!(sample_weight >= CLOSURE_WEIGHT_CUTOFF))
+        break;
+      if (sd.flag & CY_SD_TRANSPARENT) {
+        sd.closure_transparent_extinction += weight;
+        for (int i = 0; i < sd.num_closure; i++) {
+          Closure &sc = sd.closure[i];
+          if (sc.type == CY_CLOSURE_BSDF_TRANSPARENT_ID) {
+            sc.weight += weight;
+            sc.sample_weight += sample_weight;
+            break;
+          }
+        }
+      }
+      else {
+        sd.flag |= CY_SD_BSDF | CY_SD_TRANSPARENT;
+        sd.closure_transparent_extinction = weight;
+        /* a terminating path evaluates no closures, but still has to pass through */
+        if (path_flag & CY_PATH_RAY_TERMINATE)
+          sd.num_closure_left = 1;
+        Closure *bsdf = closure_alloc(sd, weight);
+        if (bsdf) {
+          bsdf->type = CY_CLOSURE_BSDF_TRANSPARENT_ID;
+          bsdf->sample_weight = sample_weight;
+          bsdf->N = sd.N;
+        }
+        else if (path_flag & CY_PATH_RAY_TERMINATE) {
+          sd.num_closure_left = 0;
+        }
+      }
+      break;
+    }
     case CY_CLOSURE_BSDF_REFRACTION_ID:
     case CY_CLOSURE_BSDF_MICROFACET_GGX_REFRACTION_ID: {
       /* svm_closure.h:571-608: Refraction BSDF node, sharp or GGX */

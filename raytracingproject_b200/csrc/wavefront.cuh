@@ -1249,6 +1249,7 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
           i += 2;
         }
         else if (type == CY_CLOSURE_BSDF_DIFFUSE_ID || type == CY_CLOSURE_BSDF_TRANSLUCENT_ID ||
+                 type == CY_CLOSURE_BSDF_TRANSPARENT_ID ||
                  type == CY_CLOSURE_BSDF_REFRACTION_ID ||
                  type == CY_CLOSURE_BSDF_MICROFACET_GGX_REFRACTION_ID ||
                  type == CY_CLOSURE_BSDF_SHARP_GLASS_ID ||

@@ -204,9 +204,9 @@ def _procedural_shader(name, variant=0):
     )
 
 
-def _node_shader(name, body, out):
-    return ('<shader name="%s">\n%s  <connect from="%s" to="output surface"/>\n</shader>\n'
-            % (name, body, out))
+def _node_shader(name, body, out, attrs=""):
+    return ('<shader name="%s"%s>\n%s  <connect from="%s" to="output surface"/>\n</shader>\n'
+            % (name, attrs, body, out))
 
 
 def _closure_shaders(variant):
@@ -226,7 +226,20 @@ def _closure_shaders(variant):
         '  <mix_closure name="m" fac="0.4"/>\n'
         '  <connect from="d bsdf" to="m closure1"/>\n  <connect from="t bsdf" to="m closure2"/>\n',
         "m closure")
-    if variant == 0:
+    if variant in (2, 3):
+        # Transparent BSDF: one box half transparent over diffuse, one a tinted pure
+        # transparent shell.  Variant 2 switches the shaders' transparent shadows off
+        # (opaque shadow rays), variant 3 leaves them on (integrator.transparent_shadows).
+        attrs = ' use_transparent_shadow="false"' if variant == 2 else ""
+        metal = _node_shader(
+            "metal", '  <diffuse_bsdf name="d" color="0.8 0.5 0.2"/>\n'
+            '  <transparent_bsdf name="t" color="1 1 1"/>\n'
+            '  <mix_closure name="m" fac="0.5"/>\n'
+            '  <connect from="d bsdf" to="m closure1"/>\n'
+            '  <connect from="t bsdf" to="m closure2"/>\n', "m closure", attrs)
+        glass = _node_shader("glass", '  <transparent_bsdf name="t" color="0.75 0.9 1"/>\n',
+                             "t bsdf", attrs)
+    elif variant == 0:
         metal = _node_shader("metal", '  <glass_bsdf name="g" distribution="GGX" roughness="0.15" '
                              'IOR="1.45" color="0.95 0.97 1"/>\n', "g bsdf")
         glass = _node_shader("glass", '  <glass_bsdf name="g" distribution="sharp" IOR="1.5" '
@@ -418,13 +431,15 @@ def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
     xml += _header(width, height, cam, fov,
                    _integrator(max_bounce, clamp_indirect=10.0), nearclip=0.01, farclip=100.0)
     xml += _background((0, 0, 0), 0.0)
-    if materials in ("closures", "closures2"):
-        xml += _closure_shaders(0 if materials == "closures" else 1)
+    closure_variants = {"closures": 0, "closures2": 1, "transparent_opaque_shadow": 2,
+                        "transparent": 3}
+    if materials in closure_variants:
+        xml += _closure_shaders(closure_variants[materials])
     else:
         xml += _diffuse_shader("white", (0.73, 0.73, 0.73))
         xml += _diffuse_shader("red", (0.65, 0.05, 0.05))
         xml += _diffuse_shader("green", (0.12, 0.45, 0.15))
-    if materials in ("closures", "closures2"):
+    if materials in closure_variants:
         pass
     elif materials == "procedural":
         xml += _procedural_shader("metal", 0)
@@ -432,7 +447,7 @@ def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
         xml += _principled_shader("metal", (0.9, 0.85, 0.7), 1.0, 0.2, 0.5, 0.0, 1.45, distribution)
     else:
         xml += _diffuse_shader("metal", (0.9, 0.85, 0.7))
-    if materials in ("closures", "closures2"):
+    if materials in closure_variants:
         pass
     elif materials == "procedural":
         xml += _procedural_shader("glass", 1)

@@ -28,6 +28,11 @@ def closure_cases():
     return {
         "cornell_closures": scenes.cornell(W, H, materials="closures"),
         "cornell_closures2": scenes.cornell(W, H, materials="closures2"),
+        # Transparent BSDF: straight-through bounces, alpha, terminate-after-transparent
+        "cornell_transparent_opaque_shadow": scenes.cornell(
+            W, H, materials="transparent_opaque_shadow"),
+        # ... and transparent shadows (kernel_shadow.h stepped loop)
+        "cornell_transparent": scenes.cornell(W, H, materials="transparent"),
     }
 
 

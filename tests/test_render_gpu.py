@@ -76,7 +76,8 @@ def test_lamp_types_match_reference(ref, device, name):
         rs.close()
 
 
-@pytest.mark.parametrize("name", ["cornell_closures", "cornell_closures2"])
+@pytest.mark.parametrize("name", ["cornell_closures", "cornell_closures2",
+                                  "cornell_transparent_opaque_shadow", "cornell_transparent"])
 def test_closure_nodes_match_reference(ref, device, name):
     desc = closure_cases()[name]
     rs = ref.build_scene(desc)
