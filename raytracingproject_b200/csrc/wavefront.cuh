@@ -40,7 +40,8 @@ struct WFCounters {
   unsigned int n_next;   /* paths appended to q_next by shade_surface */
   unsigned int n_shadow; /* shadow rays appended by shade_surface */
   unsigned int work_closest, work_shadow;
-  unsigned int pad[3];
+  /* transparent shadows: sizes of the two stepping queues, their traversal cursor */
+  unsigned int n_ts[2], work_ts;
   unsigned long long primary_rays, bounce_rays, shadow_rays;
   unsigned long long nodes, tris, instances;          /* intersect_closest */
   unsigned long long sh_nodes, sh_tris, sh_instances; /* intersect_shadow */
@@ -71,6 +72,14 @@ struct PathSoA {
   int *q_next;   /* next bounce's q_active */
   int2 *q_sorted; /* (queue position qi, path index) ordered by key */
   int *q_shadow; /* [shadow queue] -> path */
+  /* Transparent shadows (only allocated when integrator.transparent_shadows): shadow rays
+   * whose first hit is a transparent surface step from surface to surface
+   * (kernel_shadow.h:300-352).  Two ping-pong queues of (ray, index into the shadow
+   * queue); the running attenuation lives with the shadow-queue entry. */
+  float4 *ts_P_t[2];
+  float4 *ts_D[2];
+  int *ts_idx[2];
+  float4 *ts_thr; /* [shadow queue] attenuation so far, .w = transparent bounce count */
   WFCounters *counters;
   /* debugging aid: when debug != NULL the path in slot debug_slot records 32 floats
    * per bounce (ray, hit, shading point, closures, sampled direction) */
@@ -83,6 +92,7 @@ struct PathPool {
   PathSoA soa;
   void *block = nullptr;
   size_t bytes = 0;
+  bool has_ts = false; /* transparent-shadow arrays carved */
   WFCounters *h_counters = nullptr; /* pinned */
 };
 
@@ -769,7 +779,8 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS) k_shade_surface(Pa
                   out_sh_P = make_float4(sP.x, sP.y, sP.z, st_t);
                   out_sh_D = make_float4(sD.x, sD.y, sD.z,
                                          __uint_as_float(CY_PATH_RAY_SHADOW_OPAQUE));
-                  out_sh_C = make_float4(contribution.x, contribution.y, contribution.z, 0.0f);
+                  out_sh_C = make_float4(contribution.x, contribution.y, contribution.z,
+                                         __int_as_float(st.transparent_bounce));
                   want_shadow = true;
                 }
                 else {
@@ -861,7 +872,7 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS) k_shade_surface(Pa
 
 /* -------------------------------------- intersect_shadow + shade_shadow */
 
-struct ShadowJob {
+template<bool TRANSPARENT> struct ShadowJob {
   PathSoA p;
   __device__ __forceinline__ const float4 *ray_P(unsigned int qi) const
   {
@@ -871,7 +882,7 @@ struct ShadowJob {
   {
     return p.sh_D + qi; /* .w = PATH_RAY_SHADOW_OPAQUE: shadow_blocked_opaque, kernel_shadow.h:90 */
   }
-  __device__ __forceinline__ void store(unsigned int qi, const TraceHit &, bool blocked)
+  __device__ __forceinline__ void store(unsigned int qi, const TraceHit &h, bool blocked)
   {
     if (!blocked) {
       /* shade_shadow - path_radiance_accum_light, kernel_accumulate.h:402-459 */
@@ -883,16 +894,158 @@ struct ShadowJob {
       L.z += cn.z;
       p.L[i] = L;
     }
+    else if (TRANSPARENT) {
+      /* shadow_blocked_transparent_stepped (kernel_shadow.h:354-368): the first hit found
+       * is transparent -> walk the ray surface by surface; opaque -> blocked */
+      const unsigned int tri = __ldg(&g_scene.prim_index[h.prim]);
+      const uint32_t flags = shader_flags((int)__ldg(&g_scene.tri_shader[tri]));
+      const float4 cn = p.sh_contrib[qi];
+      const int bounce = __float_as_int(cn.w);
+      if ((flags & CY_SD_HAS_TRANSPARENT_SHADOW) &&
+          bounce < kd_int(KD_INT_TRANSPARENT_MAX_BOUNCE)) {
+        const unsigned int slot = atomicAdd(&p.counters->n_ts[0], 1u);
+        const float4 d = p.sh_D[qi];
+        p.ts_P_t[0][slot] = p.sh_P_t[qi];
+        p.ts_D[0][slot] = make_float4(d.x, d.y, d.z,
+                                      __uint_as_float(CY_PATH_RAY_SHADOW_TRANSPARENT));
+        p.ts_idx[0][slot] = (int)qi;
+        p.ts_thr[qi] = make_float4(1.0f, 1.0f, 1.0f, cn.w);
+      }
+    }
   }
 };
 
-template<bool COUNT>
-__global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS) k_intersect_shadow(PathSoA p, int refill_threshold)
+/* closest-hit traversal of one stepping queue; hits land in the (idle) hit arrays */
+struct TransparentShadowJob {
+  PathSoA p;
+  int cur;
+  __device__ __forceinline__ const float4 *ray_P(unsigned int qi) const
+  {
+    return p.ts_P_t[cur] + qi;
+  }
+  __device__ __forceinline__ const float4 *ray_D(unsigned int qi) const
+  {
+    return p.ts_D[cur] + qi;
+  }
+  __device__ __forceinline__ void store(unsigned int qi, const TraceHit &h, bool)
+  {
+    p.hit[qi] = make_float4(h.t, h.u, h.v, __int_as_float(h.prim));
+    p.hit_object[qi] = h.object;
+  }
+};
+
+__global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS)
+    k_intersect_shadow_step(PathSoA p, int cur, int refill_threshold)
+{
+  TraceCounters cnt;
+  cnt.nodes = cnt.tris = cnt.instances = 0;
+  TransparentShadowJob job;
+  job.p = p;
+  job.cur = cur;
+  trace_persistent<false, false>(job, p.counters->n_ts[cur], &p.counters->work_ts,
+                                 refill_threshold, cnt);
+}
+
+/* One step of the transparent-shadow walk for every ray of queue `cur`
+ * (shadow_blocked_transparent_stepped_loop + shadow_handle_transparent_isect,
+ * kernel_shadow.h:46-88, 300-352): nothing hit -> the light arrives, attenuated; an
+ * opaque surface -> blocked; a transparent one -> evaluate its shader as a shadow ray,
+ * multiply the attenuation by its transparency and continue behind it. */
+__global__ void __launch_bounds__(WF_BLOCK) k_shade_shadow_step(PathSoA p, int cur)
+{
+  WFCounters *c = p.counters;
+  const unsigned int n = c->n_ts[cur];
+  const int max_bounce = kd_int(KD_INT_TRANSPARENT_MAX_BOUNCE);
+  const unsigned int rounds = (n + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+  for (unsigned int r = 0; r < rounds; r++) {
+    const unsigned int qi = r * gridDim.x * blockDim.x + blockIdx.x * blockDim.x + threadIdx.x;
+    bool go_on = false;
+    float4 out_P = make_float4(0.0f, 0.0f, 0.0f, 0.0f), out_D = out_P;
+    int sh = 0;
+    if (qi < n) {
+      sh = p.ts_idx[cur][qi];
+      const float4 hit = p.hit[qi];
+      const int prim = __float_as_int(hit.w);
+      float4 thr = p.ts_thr[sh];
+      if (prim < 0) {
+        /* reached the light */
+        const int i = p.q_shadow[sh];
+        const float4 cn = p.sh_contrib[sh];
+        float4 L = p.L[i];
+        L.x += cn.x * thr.x;
+        L.y += cn.y * thr.y;
+        L.z += cn.z * thr.z;
+        p.L[i] = L;
+      }
+      else {
+        const unsigned int tri = __ldg(&g_scene.prim_index[prim]);
+        const uint32_t flags = shader_flags((int)__ldg(&g_scene.tri_shader[tri]));
+        if (flags & CY_SD_HAS_TRANSPARENT_SHADOW) {
+          const float4 r0 = p.ts_P_t[cur][qi];
+          const float4 r1 = p.ts_D[cur][qi];
+          const f3 rayP = mk3(r0), rayD = mk3(r1);
+          int bounce = __float_as_int(thr.w);
+          ShaderDataG sd;
+          shader_setup_from_ray(sd, prim, p.hit_object[qi], hit.x, hit.y, hit.z, rayP, rayD);
+          /* path_state_modify_bounce(state, true) around the evaluation; only the
+           * transparent counter is known here, which is what a shadow shader can vary by */
+          PathDepths depths;
+          depths.bounce = 1;
+          depths.diffuse = depths.glossy = depths.transmission = 0;
+          depths.transparent = (short)bounce;
+          shader_eval_surface(sd, depths, CY_PATH_RAY_SHADOW);
+          f3 t = (sd.flag & CY_SD_TRANSPARENT) ? sd.closure_transparent_extinction : zero3();
+          f3 nthr = mk3(thr.x, thr.y, thr.z) * t;
+          if (!is_zero(nthr)) {
+            bounce++;
+            if (bounce < max_bounce) {
+              /* move the ray behind the surface, keep aiming at the same end point */
+              const float4 s0 = p.sh_P_t[sh];
+              const float4 s1 = p.sh_D[sh];
+              f3 nP = ray_offset(sd.P, -sd.Ng);
+              f3 nD = rayD;
+              float nt = r0.w;
+              if (nt != FLT_MAX) {
+                const f3 Pend = mk3(s0) + mk3(s1) * s0.w;
+                nD = normalize_len(Pend - nP, &nt);
+              }
+              out_P = make_float4(nP.x, nP.y, nP.z, nt);
+              out_D = make_float4(nD.x, nD.y, nD.z,
+                                  __uint_as_float(CY_PATH_RAY_SHADOW_TRANSPARENT));
+              p.ts_thr[sh] = make_float4(nthr.x, nthr.y, nthr.z, __int_as_float(bounce));
+              go_on = true;
+            }
+          }
+        }
+      }
+    }
+    unsigned int slot, unused;
+    block_append2(&c->n_ts[cur ^ 1], go_on, 0u, &c->n_ts[cur ^ 1], false, &slot, &unused);
+    if (go_on) {
+      p.ts_P_t[cur ^ 1][slot] = out_P;
+      p.ts_D[cur ^ 1][slot] = out_D;
+      p.ts_idx[cur ^ 1][slot] = sh;
+    }
+  }
+}
+
+/* between two steps: the consumed queue becomes the empty target of the next step */
+__global__ void k_shadow_step_end(PathSoA p, int cur)
+{
+  WFCounters *c = p.counters;
+  c->shadow_rays += c->n_ts[cur];
+  c->n_ts[cur] = 0;
+  c->work_ts = 0;
+}
+
+template<bool COUNT, bool TRANSPARENT>
+__global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS)
+    k_intersect_shadow(PathSoA p, int refill_threshold)
 {
   const unsigned lane = threadIdx.x & 31u;
   TraceCounters cnt;
   cnt.nodes = cnt.tris = cnt.instances = 0;
-  ShadowJob job;
+  ShadowJob<TRANSPARENT> job;
   job.p = p;
   trace_persistent<true, COUNT>(job, p.counters->n_shadow, &p.counters->work_shadow,
                                 refill_threshold, cnt);
@@ -927,6 +1080,8 @@ __global__ void k_iteration_end(PathSoA p, int num_keys, int iteration)
     c->n_shadow = 0;
     c->work_closest = 0;
     c->work_shadow = 0;
+    c->n_ts[0] = c->n_ts[1] = 0;
+    c->work_ts = 0;
   }
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= num_keys; k += gridDim.x * blockDim.x)
     c->hist[k] = 0;
@@ -1066,13 +1221,15 @@ static void free_pool(b200_ctx *ctx)
 
 #define PATH_POOL_BYTES_PER_PATH 228 /* 12 float4 + 8 words per path, see the carve list */
 
-static int ensure_pool(b200_ctx *ctx, size_t capacity)
+static int ensure_pool(b200_ctx *ctx, size_t capacity, bool transparent_shadows)
 {
-  if (ctx->pool && ctx->pool->capacity >= capacity)
+  if (ctx->pool && ctx->pool->capacity >= capacity &&
+      (ctx->pool->has_ts || !transparent_shadows))
     return B200_OK;
   free_pool(ctx);
   PathPool *pool = new PathPool();
   pool->capacity = capacity;
+  pool->has_ts = transparent_shadows;
   /* carve one allocation; every array 256-byte aligned */
   size_t off = 0;
   auto carve = [&](size_t bytes) {
@@ -1087,6 +1244,11 @@ static int ensure_pool(b200_ctx *ctx, size_t capacity)
          o_sB = carve(n * 16), o_shP = carve(n * 16), o_shD = carve(n * 16), o_shC = carve(n * 16),
          o_key = carve(n * 4), o_qa = carve(n * 4), o_qn = carve(n * 4), o_qs = carve(n * 8),
          o_qsh = carve(n * 4), o_cnt = carve(sizeof(WFCounters));
+  /* transparent-shadow stepping queues: 88 bytes per path more, only when needed */
+  const size_t nts = transparent_shadows ? n : 0;
+  size_t o_tsP0 = carve(nts * 16), o_tsP1 = carve(nts * 16), o_tsD0 = carve(nts * 16),
+         o_tsD1 = carve(nts * 16), o_tsI0 = carve(nts * 4), o_tsI1 = carve(nts * 4),
+         o_tsT = carve(nts * 16);
   cudaError_t e = cudaMalloc(&pool->block, off);
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -1117,6 +1279,13 @@ static int ensure_pool(b200_ctx *ctx, size_t capacity)
   s.q_next = (int *)(b + o_qn);
   s.q_sorted = (int2 *)(b + o_qs);
   s.q_shadow = (int *)(b + o_qsh);
+  s.ts_P_t[0] = transparent_shadows ? (float4 *)(b + o_tsP0) : nullptr;
+  s.ts_P_t[1] = transparent_shadows ? (float4 *)(b + o_tsP1) : nullptr;
+  s.ts_D[0] = transparent_shadows ? (float4 *)(b + o_tsD0) : nullptr;
+  s.ts_D[1] = transparent_shadows ? (float4 *)(b + o_tsD1) : nullptr;
+  s.ts_idx[0] = transparent_shadows ? (int *)(b + o_tsI0) : nullptr;
+  s.ts_idx[1] = transparent_shadows ? (int *)(b + o_tsI1) : nullptr;
+  s.ts_thr = transparent_shadows ? (float4 *)(b + o_tsT) : nullptr;
   s.counters = (WFCounters *)(b + o_cnt);
   if (cudaMallocHost(&pool->h_counters, sizeof(WFCounters)) != cudaSuccess) {
     cudaFree(pool->block);
@@ -1294,8 +1463,6 @@ static int check_scope(b200_ctx *ctx)
     why = "only the Sobol sampling pattern is in scope";
   else if (I(KD_INT_BRANCHED))
     why = "branched path tracing is outside the hot-path scope";
-  else if (I(KD_INT_TRANSPARENT_SHADOWS))
-    why = "transparent shadows are outside the hot-path scope";
   else if (I(KD_INT_USE_VOLUMES))
     why = "volumes are outside the hot-path scope";
   else if (I(KD_INT_USE_AMBIENT_OCCLUSION))
@@ -1348,11 +1515,14 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
     if (!(ctx->pool && ctx->pool->capacity >= capacity) &&
         cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
       const size_t held = ctx->pool ? ctx->pool->capacity * PATH_POOL_BYTES_PER_PATH : 0;
-      const size_t fit = (free_b + held) / 4 / PATH_POOL_BYTES_PER_PATH;
+      const size_t per_path = PATH_POOL_BYTES_PER_PATH +
+                              (kd_host<int>(ctx, KD_INT_TRANSPARENT_SHADOWS) ? 88 : 0);
+      const size_t fit = (free_b + held) / 4 / per_path;
       capacity = std::max<size_t>(std::min(capacity, fit), (size_t)1 << 16);
     }
   }
-  rc = ensure_pool(ctx, std::max<size_t>(capacity, (size_t)tile->w));
+  const bool transparent_shadows = kd_host<int>(ctx, KD_INT_TRANSPARENT_SHADOWS) != 0;
+  rc = ensure_pool(ctx, std::max<size_t>(capacity, (size_t)tile->w), transparent_shadows);
   if (rc)
     return rc;
   PathPool *pool = ctx->pool;
@@ -1415,11 +1585,31 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
         k_shade_background<<<grid_wide, WF_BLOCK, 0, st>>>(soa);
         k_shade_surface<<<grid_wide, WF_BLOCK, 0, st>>>(soa, num_keys);
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev3, st));
-        if (count)
-          k_intersect_shadow<true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
+        if (transparent_shadows)
+          k_intersect_shadow<false, true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
+        else if (count)
+          k_intersect_shadow<true, false><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
         else
-          k_intersect_shadow<false><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
+          k_intersect_shadow<false, false><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev4, st));
+        if (transparent_shadows) {
+          /* shadow rays stopped by a transparent surface walk on, one surface per step */
+          CUDA_TRY(ctx, cudaMemcpyAsync(pool->h_counters, soa.counters, 64,
+                                        cudaMemcpyDeviceToHost, st));
+          CUDA_TRY(ctx, cudaStreamSynchronize(st));
+          int cur = 0;
+          while (pool->h_counters->n_ts[cur] != 0) {
+            k_intersect_shadow_step<<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, cur, refill);
+            k_shade_shadow_step<<<grid_wide, WF_BLOCK, 0, st>>>(soa, cur);
+            k_shadow_step_end<<<1, 1, 0, st>>>(soa, cur);
+            stats.kernel_launches += 3;
+            CUDA_TRY(ctx, cudaMemcpyAsync(pool->h_counters, soa.counters, 64,
+                                          cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            CUDA_TRY(ctx, cudaGetLastError());
+            cur ^= 1;
+          }
+        }
         k_iteration_end<<<8, 256, 0, st>>>(soa, num_keys, it);
         stats.kernel_launches += 8;
         stats.closest_launches += 1;

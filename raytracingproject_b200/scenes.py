@@ -418,18 +418,21 @@ def terrain(width=1920, height=1080, spp=256, n=708, max_bounce=0):
 
 # ---------------------------------------------------------------- config 3
 def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
-            materials="principled", light="area"):
+            materials="principled", light="area", panes=0, transparent_max=8):
     """BASELINE config 3 - Cornell box, ceiling area light, one metallic and one
     glass Principled box (materials="diffuse" gives the all-diffuse variant).
     light="mesh" replaces the lamp by an emissive quad (a mesh light: its two triangles
     enter the light distribution), light="mesh_instanced" by two instances of one small
     emissive quad with different rotations and non-uniform scales (mesh lights whose
-    object transform is not applied) - parity-test variants."""
+    object transform is not applied) - parity-test variants.  `panes` adds that many
+    horizontal sheets of the "glass" material under the light (stacked transparent
+    surfaces for the shadow rays), `transparent_max` is the transparent bounce limit."""
     xml = "<cycles>\n"
     cam = look_at((0.0, -3.6, 1.0), (0.0, 0.0, 1.0))
     fov = 2.0 * np.arctan(0.5 * 36.0 / 50.0 / (width / height)) * 1.6
     xml += _header(width, height, cam, fov,
-                   _integrator(max_bounce, clamp_indirect=10.0), nearclip=0.01, farclip=100.0)
+                   _integrator(max_bounce, clamp_indirect=10.0, transparent=transparent_max),
+                   nearclip=0.01, farclip=100.0)
     xml += _background((0, 0, 0), 0.0)
     closure_variants = {"closures": 0, "closures2": 1, "transparent_opaque_shadow": 2,
                         "transparent": 3}
@@ -493,6 +496,10 @@ def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
     add(Pb, Tb, "metal", rot_z(20.0, (-0.35, 0.3, 0.0)))
     Ps, Ts = box_mesh((-0.3, -0.3, 0.002), (0.3, 0.3, 0.6))
     add(Ps, Ts, "glass", rot_z(-18.0, (0.35, -0.3, 0.0)))
+    for k in range(panes):
+        z = 1.25 + 0.12 * k
+        add(*quad((-0.6, -0.7, z), (0.1 + 0.1 * k, -0.7, z), (0.1 + 0.1 * k, 0.7, z),
+                  (-0.6, 0.7, z)), "glass")
     if light == "mesh":
         add(*quad((-0.25, -0.25, 1.98), (-0.25, 0.25, 1.98), (0.25, 0.25, 1.98),
                   (0.25, -0.25, 1.98)), "lamp")

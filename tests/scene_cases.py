@@ -33,6 +33,11 @@ def closure_cases():
             W, H, materials="transparent_opaque_shadow"),
         # ... and transparent shadows (kernel_shadow.h stepped loop)
         "cornell_transparent": scenes.cornell(W, H, materials="transparent"),
+        # five stacked transparent sheets under the light; with a limit of 4 transparent
+        # bounces the shadow rays through all of them count as blocked
+        "cornell_transparent_panes": scenes.cornell(W, H, materials="transparent", panes=5),
+        "cornell_transparent_panes_limit": scenes.cornell(W, H, materials="transparent",
+                                                          panes=5, transparent_max=4),
     }
 
 

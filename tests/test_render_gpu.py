@@ -77,7 +77,9 @@ def test_lamp_types_match_reference(ref, device, name):
 
 
 @pytest.mark.parametrize("name", ["cornell_closures", "cornell_closures2",
-                                  "cornell_transparent_opaque_shadow", "cornell_transparent"])
+                                  "cornell_transparent_opaque_shadow", "cornell_transparent",
+                                  "cornell_transparent_panes",
+                                  "cornell_transparent_panes_limit"])
 def test_closure_nodes_match_reference(ref, device, name):
     desc = closure_cases()[name]
     rs = ref.build_scene(desc)
