@@ -29,6 +29,7 @@ struct f3 {
 #define CY_M_PI_F 3.1415926535897932f
 #define CY_M_PI_2_F 1.5707963267948966f
 #define CY_M_1_PI_F 0.3183098861837067f
+#define CY_M_PI_4_F 0.7853981633974483f
 
 CY_DEV f3 mk3(float x, float y, float z)
 {

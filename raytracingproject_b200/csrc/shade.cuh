@@ -6,7 +6,8 @@
  * to rounding of the transcendental functions.
  *
  * Scope (b200_cycles.cu:check_scope / svm_validate refuse anything else):
- * perspective camera without DOF / motion, static triangles and instances,
+ * perspective and orthographic cameras (with depth of field, without motion blur),
+ * static triangles and instances,
  * point / spot / area / distant lamps, emissive triangles (light_tri.cuh), background
  * colour, SVM nodes of
  * svm_nodes.cuh / svm_validate and the Diffuse / Oren-Nayar, Translucent, Principled(GGX),
@@ -154,6 +155,53 @@ CY_DEV f3 transform_perspective(const float4 tx, const float4 ty, const float4 t
 
 /* kernel_path_common.h:21-46 + kernel_random.h:129-153 + kernel_camera.h:355-427,
  * 42-170 (perspective, no DOF, no motion).  Returns Ray::t (0 = no ray). */
+/* kernel_montecarlo.h:150-194 */
+CY_DEV float2 concentric_sample_disk(float u1, float u2)
+{
+  float phi, r;
+  float a = 2.0f * u1 - 1.0f;
+  float b = 2.0f * u2 - 1.0f;
+  if (a == 0.0f && b == 0.0f) {
+    return make_float2(0.0f, 0.0f);
+  }
+  else if (a * a > b * b) {
+    r = a;
+    phi = CY_M_PI_4_F * (b / a);
+  }
+  else {
+    r = b;
+    phi = CY_M_PI_2_F - CY_M_PI_4_F * (a / b);
+  }
+  return make_float2(r * cosf(phi), r * sinf(phi));
+}
+CY_DEV float2 regular_polygon_sample(float corners, float rotation, float u, float v)
+{
+  /* pick a corner triangle, then a uniform point in it */
+  float corner = floorf(u * corners);
+  u = u * corners - corner;
+  u = sqrtf(u);
+  v = v * u;
+  u = 1.0f - u;
+  float angle = CY_M_PI_F / corners;
+  float2 p = make_float2((u + v) * cosf(angle), (u - v) * sinf(angle));
+  rotation += corner * 2.0f * angle;
+  float cr = cosf(rotation);
+  float sr = sinf(rotation);
+  return make_float2(cr * p.x - sr * p.y, sr * p.x + cr * p.y);
+}
+/* kernel_camera.h:21-40; the caller scales by the aperture size */
+CY_DEV float2 camera_sample_aperture(float u, float v)
+{
+  const float blades = kd_float(KD_CAM_BLADES);
+  float2 bokeh;
+  if (blades == 0.0f)
+    bokeh = concentric_sample_disk(u, v);
+  else
+    bokeh = regular_polygon_sample(blades, kd_float(KD_CAM_BLADESROTATION), u, v);
+  bokeh.x *= kd_float(KD_CAM_INV_APERTURE_RATIO); /* anamorphic bokeh */
+  return bokeh;
+}
+
 CY_DEV float camera_ray(int x, int y, int sample, uint32_t *rng_hash, f3 *P, f3 *D)
 {
   *rng_hash = hash_uint2((uint32_t)x, (uint32_t)y);
@@ -172,6 +220,12 @@ CY_DEV float camera_ray(int x, int y, int sample, uint32_t *rng_hash, f3 *P, f3 
   float raster_x = x + lookup_table_read(filter_u, filter_table_offset, CY_FILTER_TABLE_SIZE);
   float raster_y = y + lookup_table_read(filter_v, filter_table_offset, CY_FILTER_TABLE_SIZE);
 
+  /* lens sample only when there is an aperture - kernel_path_common.h:34-37 */
+  float lens_u = 0.0f, lens_v = 0.0f;
+  const float aperturesize = kd_float(KD_CAM_APERTURESIZE);
+  if (aperturesize > 0.0f)
+    path_rng_2D(*rng_hash, sample, CY_PRNG_LENS_U, &lens_u, &lens_v);
+
   const int r2c = KD_CAM_RASTERTOCAMERA;
   f3 raster = mk3(raster_x, raster_y, 0.0f);
   f3 Pcamera = transform_perspective(kd_float4(r2c), kd_float4(r2c + 16), kd_float4(r2c + 32),
@@ -182,8 +236,35 @@ CY_DEV float camera_ray(int x, int y, int sample, uint32_t *rng_hash, f3 *P, f3 
   c2w.y = kd_float4(KD_CAM_CAMERATOWORLD + 16);
   c2w.z = kd_float4(KD_CAM_CAMERATOWORLD + 32);
 
-  f3 Pw = transform_point(c2w, zero3());
-  f3 Dw = normalize(transform_direction(c2w, Pcamera));
+  if (kd_int(KD_CAM_TYPE) == CY_CAMERA_ORTHOGRAPHIC) {
+    /* camera_sample_orthographic - kernel_camera.h:174-235 */
+    f3 Po = Pcamera;
+    f3 Do = mk3(0.0f, 0.0f, 1.0f);
+    if (aperturesize > 0.0f) {
+      const float2 lensuv = camera_sample_aperture(lens_u, lens_v);
+      const f3 Pfocus = Do * kd_float(KD_CAM_FOCALDISTANCE);
+      const f3 lensuvw = mk3(lensuv.x * aperturesize, lensuv.y * aperturesize, 0.0f);
+      Po = Pcamera + lensuvw;
+      Do = normalize(Pfocus - lensuvw);
+    }
+    *P = transform_point(c2w, Po);
+    *D = normalize(transform_direction(c2w, Do));
+    return kd_float(KD_CAM_CLIPLENGTH);
+  }
+
+  /* camera_sample_perspective - kernel_camera.h:42-172 (no motion, no stereo) */
+  f3 Pc = zero3();
+  f3 Dc = Pcamera;
+  if (aperturesize > 0.0f) {
+    /* point on the aperture, point on the plane of focus */
+    const float2 lensuv = camera_sample_aperture(lens_u, lens_v);
+    const float ft = kd_float(KD_CAM_FOCALDISTANCE) / Dc.z;
+    const f3 Pfocus = Dc * ft;
+    Pc = mk3(lensuv.x * aperturesize, lensuv.y * aperturesize, 0.0f);
+    Dc = normalize(Pfocus - Pc);
+  }
+  f3 Pw = transform_point(c2w, Pc);
+  f3 Dw = normalize(transform_direction(c2w, Dc));
 
   /* clipping - kernel_camera.h:158-167 */
   float z_inv = 1.0f / normalize(Pcamera).z;

@@ -82,15 +82,19 @@ def euler_xyz_camera(loc, rot):
     return m
 
 
-def _header(width, height, cam_m34, fov, integrator, film="", nearclip=0.1, farclip=1000.0):
+def _header(width, height, cam_m34, fov, integrator, film="", nearclip=0.1, farclip=1000.0,
+            cam_type="perspective", cam_extra=""):
+    """cam_type: "perspective" or "orthograph" (cycles_xml's spelling); cam_extra: more
+    camera attributes, e.g. 'aperturesize="0.2" focaldistance="9" blades="6"'."""
     return (
         '<camera width="%d" height="%d"/>\n'
         '<transform matrix="%s">\n'
-        '  <camera type="perspective" fov="%s" nearclip="%s" farclip="%s" shuttertime="-1"/>\n'
+        '  <camera type="%s" fov="%s" nearclip="%s" farclip="%s" shuttertime="-1" %s/>\n'
         "</transform>\n"
         "<integrator %s/>\n"
         '<film filter_type="blackman_harris" filter_width="1.5" exposure="1" %s/>\n'
-        % (width, height, _matrix_attr(cam_m34), _f(fov), _f(nearclip), _f(farclip), integrator, film)
+        % (width, height, _matrix_attr(cam_m34), cam_type, _f(fov), _f(nearclip), _f(farclip),
+           cam_extra, integrator, film)
     )
 
 
@@ -294,7 +298,7 @@ def box_mesh(lo, hi):
 
 # ---------------------------------------------------------------- config 1
 def default_cube(width=1920, height=1080, spp=64, material="principled", max_bounce=12,
-                 lights="point"):
+                 lights="point", cam_type="perspective", cam_extra=""):
     """BASELINE config 1 - Blender's startup scene, values extracted from
     release/datafiles/startup.blend.  `lights`: "point" (the
     startup scene), "falloff" (its lamp shader goes through a Light Falloff node), "spot"
@@ -308,7 +312,7 @@ def default_cube(width=1920, height=1080, spp=64, material="principled", max_bou
         width, height, cam, fov,
         _integrator(max_bounce, diffuse=min(4, max_bounce), glossy=min(4, max_bounce),
                     transmission=max_bounce, clamp_indirect=10.0),
-        nearclip=0.1, farclip=100.0)
+        nearclip=0.1, farclip=100.0, cam_type=cam_type, cam_extra=cam_extra)
     xml += _background((0.05087609, 0.05087609, 0.05087609))
     if material == "principled":
         xml += _principled_shader("cube", (0.8, 0.8, 0.8), 0.0, 0.5, 0.5)

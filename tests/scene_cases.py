@@ -22,6 +22,21 @@ def principled_cases():
     }
 
 
+def camera_cases():
+    """Camera models beyond the pinhole: thin lens with a disk and with a rotated
+    six-blade anamorphic aperture (kernel_camera.h:21-40), orthographic with and
+    without a lens."""
+    cube = lambda **kw: scenes.default_cube(W, H, material="diffuse", **kw)
+    return {
+        "cube_dof_disk": cube(cam_extra='aperturesize="0.35" focaldistance="9.5"'),
+        "cube_dof_blades": cube(cam_extra='aperturesize="0.3" focaldistance="11" blades="6" '
+                                'bladesrotation="0.4" aperture_ratio="1.6"'),
+        "cube_ortho": cube(cam_type="orthograph"),
+        "cube_ortho_dof": cube(cam_type="orthograph",
+                               cam_extra='aperturesize="0.15" focaldistance="10"'),
+    }
+
+
 def closure_cases():
     """BSDF nodes beyond Diffuse / Principled / Glossy-GGX: Glass and Refraction (GGX and
     sharp), sharp Glossy, Translucent, Oren-Nayar - 8 bounces in a Cornell box."""

@@ -6,7 +6,8 @@ gates hold at any spp, not only at 1024."""
 import numpy as np
 import pytest
 
-from scene_cases import closure_cases, light_cases, principled_cases, small_cases
+from scene_cases import (camera_cases, closure_cases, light_cases, principled_cases,
+                         small_cases)
 
 pytestmark = pytest.mark.gpu
 
@@ -88,6 +89,21 @@ def test_closure_nodes_match_reference(ref, device, name):
         ref_img, _ = rs.render(0, SPP, tile_size=64)
         got = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP)
         print(name, device.stats())
+        image_gates(ref_img, got, SPP, name)
+    finally:
+        rs.close()
+
+
+@pytest.mark.parametrize("name", ["cube_dof_disk", "cube_dof_blades", "cube_ortho",
+                                  "cube_ortho_dof"])
+def test_camera_models_match_reference(ref, device, name):
+    desc = camera_cases()[name]
+    rs = ref.build_scene(desc)
+    try:
+        device.upload_scene(rs.device_arrays())
+        ref_img, _ = rs.render(0, SPP, tile_size=64)
+        got = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP)
+        assert ref_img[..., :3].max() > 0.0
         image_gates(ref_img, got, SPP, name)
     finally:
         rs.close()
