@@ -29,8 +29,10 @@
 #include "device/device_task.h"
 #include "render/buffers.h"
 #include "util/util_foreach.h"
+#include "util/util_map.h"
 #include "util/util_string.h"
 #include "util/util_task.h"
+#include "util/util_thread.h"
 #include "util/util_time.h"
 
 #include "../../include/b200_cycles.h"
@@ -270,6 +272,296 @@ class B200Device : public Device {
   }
 };
 
+/* One process, several B200s: the in-process counterpart of the reference's
+ * MultiDevice (device/device_multi.cpp), built on the same C ABI.
+ *
+ * The reference MultiDevice hands different TILES to its sub-devices and stitches
+ * the film on the host (mem_copy_from slicing, device_multi.cpp:374-393).  Here every
+ * GPU renders the whole tile for its share of the SAMPLES (the Sobol
+ * index is the sample number, so the shares jointly equal the single-device sample
+ * set) and the per-GPU films are summed on the device over NVLink
+ * (b200_film_reduce).  Scene arrays are replicated; device_memory::device_pointer
+ * is the pointer on the first GPU and keys a table of the per-GPU pointers. */
+class B200MultiDevice : public Device {
+ public:
+  struct Allocation {
+    vector<uint64_t> ptr; /* per GPU */
+    size_t size;
+  };
+  vector<b200_ctx *> ctxs;
+  map<device_ptr, Allocation> allocations;
+  thread_mutex alloc_mutex;
+  DedicatedTaskPool task_pool;
+  volatile int cancel_flag;
+  b200_stats last_stats;
+
+  B200MultiDevice(DeviceInfo &info, Stats &stats, Profiler &profiler, bool background_,
+                  const vector<int> &ordinals)
+      : Device(info, stats, profiler, background_), cancel_flag(0)
+  {
+    memset(&last_stats, 0, sizeof(last_stats));
+    foreach (int ordinal, ordinals) {
+      char err[512] = {0};
+      b200_ctx *ctx = b200_create(ordinal, err, sizeof(err));
+      if (!ctx) {
+        set_error(string("B200 multi device: ") + err);
+        break;
+      }
+      ctxs.push_back(ctx);
+    }
+  }
+
+  ~B200MultiDevice()
+  {
+    task_pool.cancel();
+    foreach (b200_ctx *ctx, ctxs)
+      b200_destroy(ctx);
+  }
+
+  bool check(size_t i, int rc, const char *what)
+  {
+    if (rc == B200_OK)
+      return true;
+    set_error(string_printf(
+        "B200 multi device: %s failed on GPU %d: %s", what, (int)i, b200_last_error(ctxs[i])));
+    return false;
+  }
+
+  Allocation *find(device_ptr primary)
+  {
+    thread_scoped_lock lock(alloc_mutex);
+    map<device_ptr, Allocation>::iterator it = allocations.find(primary);
+    return (it == allocations.end()) ? NULL : &it->second;
+  }
+
+  virtual BVHLayoutMask get_bvh_layout_mask() const
+  {
+    return BVH_LAYOUT_BVH2;
+  }
+  virtual bool load_kernels(const DeviceRequestedFeatures &)
+  {
+    return !ctxs.empty() && !have_error();
+  }
+  virtual bool show_samples() const
+  {
+    return false;
+  }
+
+  virtual void mem_alloc(device_memory &mem)
+  {
+    if (ctxs.empty() || mem.device_pointer || have_error())
+      return;
+    if (mem.type == MEM_TEXTURE) {
+      set_error("B200 device: image textures are outside the hot-path scope");
+      return;
+    }
+    Allocation a;
+    a.size = mem.memory_size();
+    for (size_t i = 0; i < ctxs.size(); i++) {
+      uint64_t dptr = 0;
+      if (!check(i, b200_alloc(ctxs[i], a.size, &dptr), "mem_alloc")) {
+        for (size_t j = 0; j < a.ptr.size(); j++)
+          b200_free(ctxs[j], a.ptr[j]);
+        return;
+      }
+      a.ptr.push_back(dptr);
+    }
+    mem.device_pointer = (device_ptr)a.ptr[0];
+    mem.device_size = a.size;
+    stats.mem_alloc(a.size * ctxs.size());
+    thread_scoped_lock lock(alloc_mutex);
+    allocations[mem.device_pointer] = a;
+  }
+
+  virtual void mem_copy_to(device_memory &mem)
+  {
+    if (ctxs.empty() || mem.type == MEM_PIXELS)
+      return;
+    if (mem.device_pointer && mem.device_size != mem.memory_size())
+      mem_free(mem);
+    if (!mem.device_pointer)
+      mem_alloc(mem);
+    Allocation *a = find(mem.device_pointer);
+    if (!a)
+      return;
+    for (size_t i = 0; i < ctxs.size(); i++) {
+      if (mem.host_pointer && mem.memory_size()) {
+        if (!check(i, b200_h2d(ctxs[i], a->ptr[i], mem.host_pointer, 0, mem.memory_size()),
+                   "mem_copy_to"))
+          return;
+      }
+      if (mem.type == MEM_GLOBAL) {
+        if (!check(i, b200_bind_global(ctxs[i], mem.name, a->ptr[i], mem.host_pointer,
+                                       mem.memory_size()),
+                   mem.name))
+          return;
+      }
+    }
+  }
+
+  virtual void mem_copy_from(device_memory &mem, int y, int w, int h, int elem)
+  {
+    if (ctxs.empty() || !mem.device_pointer || !mem.host_pointer)
+      return;
+    /* films are kept summed on the first GPU (thread_run) */
+    const size_t offset = (size_t)elem * y * w;
+    const size_t size = (size_t)elem * w * h;
+    check(0, b200_d2h(ctxs[0], (uint64_t)mem.device_pointer, (char *)mem.host_pointer + offset,
+                      offset, size),
+          "mem_copy_from");
+  }
+
+  virtual void mem_zero(device_memory &mem)
+  {
+    if (!mem.device_pointer)
+      mem_alloc(mem);
+    Allocation *a = find(mem.device_pointer);
+    if (!a)
+      return;
+    for (size_t i = 0; i < ctxs.size(); i++)
+      check(i, b200_zero(ctxs[i], a->ptr[i], 0, a->size), "mem_zero");
+    if (mem.host_pointer)
+      memset(mem.host_pointer, 0, mem.memory_size());
+  }
+
+  virtual void mem_free(device_memory &mem)
+  {
+    if (ctxs.empty() || !mem.device_pointer)
+      return;
+    task_pool.wait();
+    Allocation *a = find(mem.device_pointer);
+    if (a) {
+      for (size_t i = 0; i < ctxs.size(); i++)
+        check(i, b200_free(ctxs[i], a->ptr[i]), "mem_free");
+      stats.mem_free(a->size * ctxs.size());
+      thread_scoped_lock lock(alloc_mutex);
+      allocations.erase(mem.device_pointer);
+    }
+    mem.device_pointer = 0;
+    mem.device_size = 0;
+  }
+
+  virtual void const_copy_to(const char *name, void *host, size_t size)
+  {
+    if (strcmp(name, "__data") != 0) {
+      set_error(string("B200 device: unknown constant ") + name);
+      return;
+    }
+    for (size_t i = 0; i < ctxs.size(); i++)
+      check(i, b200_set_kernel_data(ctxs[i], host, size), "const_copy_to(__data)");
+  }
+
+  void thread_run(DeviceTask &task)
+  {
+    if (task.type != DeviceTask::RENDER) {
+      set_error("B200 device: only RENDER and FILM_CONVERT tasks are in scope");
+      return;
+    }
+    const int n = (int)ctxs.size();
+    RenderTile tile;
+    while (task.acquire_tile(this, tile, task.tile_types)) {
+      Allocation *film = find(tile.buffer);
+      if (tile.task != RenderTile::PATH_TRACE || !film) {
+        set_error("B200 multi device: unsupported tile (not a path-trace tile of a known film)");
+        task.release_tile(tile);
+        break;
+      }
+      {
+        scoped_timer timer(&tile.buffers->render_time);
+        /* contiguous sample ranges whose sizes differ by at most one */
+        const int base = tile.num_samples / n, rem = tile.num_samples % n;
+        vector<int> rcs(n, B200_OK);
+        vector<thread *> workers;
+        cancel_flag = 0;
+        for (int i = 0; i < n; i++) {
+          b200_work_tile wt;
+          wt.x = tile.x;
+          wt.y = tile.y;
+          wt.w = tile.w;
+          wt.h = tile.h;
+          wt.start_sample = tile.start_sample + i * base + min(i, rem);
+          wt.num_samples = base + (i < rem ? 1 : 0);
+          wt.offset = tile.offset;
+          wt.stride = tile.stride;
+          wt.buffer = film->ptr[i];
+          workers.push_back(new thread([this, i, wt, &rcs] {
+            rcs[i] = (wt.num_samples > 0) ? b200_render(ctxs[i], &wt, &cancel_flag) : B200_OK;
+          }));
+        }
+        foreach (thread *w, workers) {
+          w->join();
+          delete w;
+        }
+        bool ok = true;
+        for (int i = 0; i < n; i++) {
+          if (rcs[i] != B200_OK && rcs[i] != B200_ERR_CANCELLED)
+            ok = check(i, rcs[i], "render") && ok;
+          if (rcs[i] != B200_OK)
+            ok = false;
+        }
+        if (ok && n > 1) {
+          /* sum the per-GPU films into the first one, then clear the others so that
+           * the next tile / sample range starts from zero there */
+          ok = check(0, b200_film_reduce(ctxs.data(), n, film->ptr.data(), film->size / 4),
+                     "film_reduce");
+          for (int i = 1; ok && i < n; i++)
+            ok = check(i, b200_zero(ctxs[i], film->ptr[i], 0, film->size), "film clear");
+        }
+        if (ok) {
+          tile.sample = tile.start_sample + tile.num_samples;
+          memset(&last_stats, 0, sizeof(last_stats));
+          for (int i = 0; i < n; i++) {
+            b200_stats st;
+            b200_get_stats(ctxs[i], &st);
+            last_stats.primary_rays += st.primary_rays;
+            last_stats.bounce_rays += st.bounce_rays;
+            last_stats.shadow_rays += st.shadow_rays;
+            last_stats.kernel_launches += st.kernel_launches;
+            last_stats.device_ms = max(last_stats.device_ms, st.device_ms);
+          }
+          task.update_progress(&tile, tile.w * tile.h * tile.num_samples);
+        }
+      }
+      task.release_tile(tile);
+      if (have_error())
+        break;
+      if (task.get_cancel() || task_pool.canceled()) {
+        if (task.need_finish_queue == false)
+          break;
+      }
+    }
+  }
+
+  virtual void task_add(DeviceTask &task)
+  {
+    if (ctxs.empty() || have_error())
+      return;
+    if (task.type == DeviceTask::FILM_CONVERT) {
+      const bool half_float = task.rgba_half != 0;
+      check(0, b200_film_convert(ctxs[0], (uint64_t)task.buffer,
+                                 (uint64_t)(half_float ? task.rgba_half : task.rgba_byte),
+                                 half_float, 1.0f / (task.sample + 1), task.x, task.y, task.w,
+                                 task.h, task.offset, task.stride),
+            "film_convert");
+    }
+    else {
+      task_pool.push([=] {
+        DeviceTask task_copy = task;
+        thread_run(task_copy);
+      });
+    }
+  }
+  virtual void task_wait()
+  {
+    task_pool.wait();
+  }
+  virtual void task_cancel()
+  {
+    cancel_flag = 1;
+    task_pool.cancel();
+  }
+};
+
 bool device_b200_init()
 {
   return b200_device_count() > 0;
@@ -317,6 +609,14 @@ struct b200_host_device {
   ccl::Profiler profiler;
   ccl::DeviceInfo info;
   ccl::B200Device *device;
+  ccl::B200MultiDevice *multi;
+  b200_host_device() : device(NULL), multi(NULL)
+  {
+  }
+  ccl::Device *any()
+  {
+    return device ? static_cast<ccl::Device *>(device) : static_cast<ccl::Device *>(multi);
+  }
 };
 
 extern "C" {
@@ -349,23 +649,53 @@ void *b200_host_device_create(int ordinal, char *err, size_t errlen)
   return h;
 }
 
+/* One Device over several GPUs (B200MultiDevice): `ordinals` may repeat, which gives
+ * several contexts on one GPU (used by the tests on single-GPU boxes). */
+void *b200_host_multi_device_create(const int *ordinals, int n, char *err, size_t errlen)
+{
+  if (!ordinals || n <= 0) {
+    snprintf(err, errlen, "no ordinals given");
+    return NULL;
+  }
+  b200_host_device *h = new b200_host_device();
+  ccl::vector<ccl::DeviceInfo> infos;
+  ccl::device_b200_info(infos);
+  if (infos.empty()) {
+    snprintf(err, errlen, "no sm_100 device");
+    delete h;
+    return NULL;
+  }
+  h->info = infos[0];
+  h->info.id = "B200_MULTI";
+  ccl::vector<int> ords(ordinals, ordinals + n);
+  h->multi = new ccl::B200MultiDevice(h->info, h->stats, h->profiler, true, ords);
+  if (h->multi->have_error()) {
+    snprintf(err, errlen, "%s", h->multi->error_message().c_str());
+    delete h->multi;
+    delete h;
+    return NULL;
+  }
+  return h;
+}
+
 void *b200_host_device_ptr(void *handle)
 {
-  return handle ? (void *)static_cast<ccl::Device *>(((b200_host_device *)handle)->device) : NULL;
+  return handle ? (void *)((b200_host_device *)handle)->any() : NULL;
 }
 
 int b200_host_device_stats(void *handle, b200_stats *out)
 {
   if (!handle || !out)
     return B200_ERR_INVALID;
-  *out = ((b200_host_device *)handle)->device->last_stats;
+  b200_host_device *h = (b200_host_device *)handle;
+  *out = h->device ? h->device->last_stats : h->multi->last_stats;
   return B200_OK;
 }
 
 const char *b200_host_device_error(void *handle)
 {
   static thread_local std::string msg;
-  msg = handle ? ((b200_host_device *)handle)->device->error_message() : "null handle";
+  msg = handle ? ((b200_host_device *)handle)->any()->error_message() : "null handle";
   return msg.c_str();
 }
 
@@ -375,6 +705,7 @@ void b200_host_device_destroy(void *handle)
     return;
   b200_host_device *h = (b200_host_device *)handle;
   delete h->device;
+  delete h->multi;
   delete h;
 }
 

@@ -356,6 +356,9 @@ class B200HostDevice:
     are available) and the host application library it links to."""
 
     def __init__(self, ordinal=0):
+        """ordinal: one GPU (B200Device), or a list of GPUs for the in-process
+        B200MultiDevice (sample split + device-side film sum); a list may repeat an
+        ordinal, which puts several contexts on one GPU."""
         load_library()
         if not os.path.exists(SHIM_PATH):
             raise DeviceError("%s is missing (make -C raytracingproject_b200/csrc -f "
@@ -370,8 +373,15 @@ class B200HostDevice:
         S.b200_host_device_error.argtypes = [C.c_void_p]
         S.b200_host_device_destroy.argtypes = [C.c_void_p]
         self._S = S
+        S.b200_host_multi_device_create.restype = C.c_void_p
+        S.b200_host_multi_device_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_char_p,
+                                                    C.c_size_t]
         err = C.create_string_buffer(512)
-        self._h = S.b200_host_device_create(int(ordinal), err, len(err))
+        if isinstance(ordinal, (list, tuple)):
+            ords = (C.c_int * len(ordinal))(*[int(o) for o in ordinal])
+            self._h = S.b200_host_multi_device_create(ords, len(ordinal), err, len(err))
+        else:
+            self._h = S.b200_host_device_create(int(ordinal), err, len(err))
         if not self._h:
             raise DeviceError("B200Device: " + err.value.decode())
 

@@ -38,3 +38,37 @@ def test_reference_scene_drives_b200_device(ref, device, name):
             rs.close()
     finally:
         host.close()
+
+
+def test_multi_device_in_one_process(ref):
+    """B200MultiDevice: the reference Scene + DeviceTask drive several contexts through
+    ONE ccl::Device; every GPU renders its share of the samples, the films are summed on
+    the device (b200_film_reduce).  Equals the single-device film up to the order of the
+    float additions; FILM_CONVERT of the summed film works.  Uses two GPUs when the box
+    has them, else two contexts on one GPU."""
+    import numpy as np
+    import torch
+    from raytracingproject_b200 import scenes
+    from raytracingproject_b200.device import B200HostDevice
+    desc = scenes.cornell(160, 96, spp=9, materials="diffuse")   # 9 samples: uneven split
+    single = B200HostDevice(0)
+    rs = ref.build_scene(desc, external_device=single.ptr)
+    want, _ = rs.render(0, desc.spp, tile_size=0)
+    rs.close()
+    single.close()
+
+    ordinals = [0, 1] if torch.cuda.device_count() > 1 else [0, 0]
+    multi = B200HostDevice(ordinals)
+    rs = ref.build_scene(desc, external_device=multi.ptr)
+    got, _ = rs.render(0, desc.spp, tile_size=0)
+    st = multi.stats()
+    # a second task accumulates on top (the other GPUs' films were cleared after the sum)
+    got2, _ = rs.render(desc.spp, 3, tile_size=64, accumulate=True)
+    rgba = rs.film_convert(desc.spp + 3)
+    rs.close()
+    multi.close()
+
+    np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-6)
+    assert st["primary_rays"] == desc.width * desc.height * desc.spp
+    assert (got2[..., 3] == desc.spp + 3).all()      # alpha counts every sample once
+    assert rgba[..., :3].max() > 0
