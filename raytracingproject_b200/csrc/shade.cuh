@@ -104,9 +104,85 @@ CY_DEV uint32_t sobol_dimension(int index, int dimension)
   return result;
 }
 
-/* kernel/kernel_random.h:53-89 (SAMPLING_PATTERN_SOBOL branch) */
+/* Correlated multi-jittered sampling (Kensler 2013) as kernel/kernel_jitter.h:31-196
+ * implements it: a keyed permutation of the sample index plus a hashed jitter. */
+CY_DEV uint32_t cmj_permute(uint32_t i, uint32_t l, uint32_t p)
+{
+  uint32_t w = l - 1;
+  const bool pow2 = (l & w) == 0;
+  if (!pow2) /* smallest 2^k - 1 covering w */
+    w = (1u << (32 - __clz((int)w))) - 1u;
+  do {
+    i ^= p;
+    i *= 0xe170893du;
+    i ^= p >> 16;
+    i ^= (i & w) >> 4;
+    i ^= p >> 8;
+    i *= 0x0929eb3fu;
+    i ^= p >> 23;
+    i ^= (i & w) >> 1;
+    i *= 1u | p >> 27;
+    i *= 0x6935fa69u;
+    i ^= (i & w) >> 11;
+    i *= 0x74dcb303u;
+    i ^= (i & w) >> 2;
+    i *= 0x9e501cc3u;
+    i ^= (i & w) >> 2;
+    i *= 0xc860a3dfu;
+    i &= w;
+    i ^= i >> 5;
+  } while (!pow2 && i >= l); /* cycle-walk when l is not a power of two */
+  return pow2 ? ((i + p) & w) : ((i + p) % l);
+}
+CY_DEV uint32_t cmj_hash(uint32_t i, uint32_t p)
+{
+  i ^= p;
+  i ^= i >> 17;
+  i ^= i >> 10;
+  i *= 0xb36534e5u;
+  i ^= i >> 12;
+  i ^= i >> 21;
+  i *= 0x93fc4795u;
+  i ^= 0xdf6e307fu;
+  i ^= i >> 17;
+  i *= 1u | p >> 18;
+  return i;
+}
+CY_DEV float cmj_randfloat(uint32_t i, uint32_t p)
+{
+  return (float)cmj_hash(i, p) * (1.0f / 4294967808.0f);
+}
+CY_DEV float cmj_sample_1D(int s, int N, uint32_t p)
+{
+  const uint32_t x = cmj_permute((uint32_t)s, (uint32_t)N, p * 0x68bc21ebu);
+  const float jx = cmj_randfloat((uint32_t)s, p * 0x967a889bu);
+  const float invN = 1.0f / N;
+  return ((float)x + jx) * invN;
+}
+CY_DEV void cmj_sample_2D(int s, int N, uint32_t p, float *fx, float *fy)
+{
+  /* an m x n grid with m ~ sqrt(N); the CPU flavour of cmj_isqrt */
+  const int m = (int)(sqrtf((float)N) + 1e-6f);
+  const int n = (N - 1) / m + 1;
+  const float invN = 1.0f / N;
+  const float invm = 1.0f / m;
+  const float invn = 1.0f / n;
+  s = (int)cmj_permute((uint32_t)s, (uint32_t)N, p * 0x51633e2du);
+  const int sdivm = s / m; /* equals the shift / mask the reference uses for 2^k */
+  const int smodm = s - sdivm * m;
+  const uint32_t sx = cmj_permute((uint32_t)smodm, (uint32_t)m, p * 0x68bc21ebu);
+  const uint32_t sy = cmj_permute((uint32_t)sdivm, (uint32_t)n, p * 0x02e5be93u);
+  const float jx = cmj_randfloat((uint32_t)s, p * 0x967a889bu);
+  const float jy = cmj_randfloat((uint32_t)s, p * 0x368cc8b7u);
+  *fx = ((float)sx + ((float)sy + jx) * invn) * invm;
+  *fy = ((float)s + jy) * invN;
+}
+
+/* kernel/kernel_random.h:53-127: Sobol with a Cranley-Patterson rotation, or CMJ */
 CY_DEV float path_rng_1D(uint32_t rng_hash, int sample, int dimension)
 {
+  if (kd_int(KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_CMJ)
+    return cmj_sample_1D(sample, kd_int(KD_INT_AA_SAMPLES), rng_hash + (uint32_t)dimension);
   uint32_t result = sobol_dimension(sample, dimension);
   float r = (float)result * (1.0f / (float)0xFFFFFFFF);
   uint32_t tmp_rng = cmj_hash_simple((uint32_t)dimension, rng_hash);
@@ -115,6 +191,10 @@ CY_DEV float path_rng_1D(uint32_t rng_hash, int sample, int dimension)
 }
 CY_DEV void path_rng_2D(uint32_t rng_hash, int sample, int dimension, float *fx, float *fy)
 {
+  if (kd_int(KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_CMJ) {
+    cmj_sample_2D(sample, kd_int(KD_INT_AA_SAMPLES), rng_hash + (uint32_t)dimension, fx, fy);
+    return;
+  }
   *fx = path_rng_1D(rng_hash, sample, dimension);
   *fy = path_rng_1D(rng_hash, sample, dimension + 1);
 }

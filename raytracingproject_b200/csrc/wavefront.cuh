@@ -1459,8 +1459,9 @@ static int check_scope(b200_ctx *ctx)
     why = "motion blur is outside the hot-path scope";
   else if (I(KD_BVH_HAVE_CURVES))
     why = "hair curves are outside the hot-path scope";
-  else if (I(KD_INT_SAMPLING_PATTERN) != CY_SAMPLING_PATTERN_SOBOL)
-    why = "only the Sobol sampling pattern is in scope";
+  else if (I(KD_INT_SAMPLING_PATTERN) != CY_SAMPLING_PATTERN_SOBOL &&
+           I(KD_INT_SAMPLING_PATTERN) != CY_SAMPLING_PATTERN_CMJ)
+    why = "the PMJ sampling pattern is outside the hot-path scope (Sobol and CMJ are in)";
   else if (I(KD_INT_BRANCHED))
     why = "branched path tracing is outside the hot-path scope";
   else if (I(KD_INT_USE_VOLUMES))

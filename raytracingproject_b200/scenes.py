@@ -257,17 +257,19 @@ def _closure_shaders(variant):
 
 
 def _integrator(max_bounce, diffuse=None, glossy=None, transmission=None, transparent=8,
-                clamp_indirect=0.0, seed=0, light_threshold=0.01, caustics=True):
+                clamp_indirect=0.0, seed=0, light_threshold=0.01, caustics=True,
+                pattern="sobol", aa_samples=0):
     diffuse = max_bounce if diffuse is None else diffuse
     glossy = max_bounce if glossy is None else glossy
     transmission = max_bounce if transmission is None else transmission
     return (
-        'method="path" sampling_pattern="sobol" seed="%d" min_bounce="0" max_bounce="%d" '
+        'method="path" sampling_pattern="%s" aa_samples="%d" seed="%d" min_bounce="0" max_bounce="%d" '
         'max_diffuse_bounce="%d" max_glossy_bounce="%d" max_transmission_bounce="%d" '
         'transparent_min_bounce="0" transparent_max_bounce="%d" sample_clamp_direct="0" '
         'sample_clamp_indirect="%s" light_sampling_threshold="%s" caustics_reflective="%s" '
         'caustics_refractive="%s" filter_glossy="0"'
-        % (seed, max_bounce, diffuse, glossy, transmission, transparent, _f(clamp_indirect),
+        % (pattern, aa_samples, seed, max_bounce, diffuse, glossy, transmission, transparent,
+           _f(clamp_indirect),
            _f(light_threshold), "true" if caustics else "false", "true" if caustics else "false")
     )
 
@@ -422,7 +424,7 @@ def terrain(width=1920, height=1080, spp=256, n=708, max_bounce=0):
 
 # ---------------------------------------------------------------- config 3
 def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
-            materials="principled", light="area", panes=0, transparent_max=8):
+            materials="principled", light="area", panes=0, transparent_max=8, pattern="sobol"):
     """BASELINE config 3 - Cornell box, ceiling area light, one metallic and one
     glass Principled box (materials="diffuse" gives the all-diffuse variant).
     light="mesh" replaces the lamp by an emissive quad (a mesh light: its two triangles
@@ -435,7 +437,8 @@ def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
     cam = look_at((0.0, -3.6, 1.0), (0.0, 0.0, 1.0))
     fov = 2.0 * np.arctan(0.5 * 36.0 / 50.0 / (width / height)) * 1.6
     xml += _header(width, height, cam, fov,
-                   _integrator(max_bounce, clamp_indirect=10.0, transparent=transparent_max),
+                   _integrator(max_bounce, clamp_indirect=10.0, transparent=transparent_max,
+                               pattern=pattern, aa_samples=spp),
                    nearclip=0.01, farclip=100.0)
     xml += _background((0, 0, 0), 0.0)
     closure_variants = {"closures": 0, "closures2": 1, "transparent_opaque_shadow": 2,

@@ -22,6 +22,15 @@ def principled_cases():
     }
 
 
+def sampling_cases():
+    """Correlated multi-jittered sampling instead of Sobol (kernel_jitter.h); aa_samples
+    16 = a 4 x 4 grid, 12 = a 3 x 4 grid with the non-power-of-two permutation."""
+    return {
+        "cornell_cmj16": scenes.cornell(W, H, spp=16, materials="diffuse", pattern="cmj"),
+        "cornell_cmj12": scenes.cornell(W, H, spp=12, materials="principled", pattern="cmj"),
+    }
+
+
 def camera_cases():
     """Camera models beyond the pinhole: thin lens with a disk and with a rotated
     six-blade anamorphic aperture (kernel_camera.h:21-40), orthographic with and

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from scene_cases import (camera_cases, closure_cases, light_cases, principled_cases,
-                         small_cases)
+                         sampling_cases, small_cases)
 
 pytestmark = pytest.mark.gpu
 
@@ -105,6 +105,19 @@ def test_camera_models_match_reference(ref, device, name):
         got = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP)
         assert ref_img[..., :3].max() > 0.0
         image_gates(ref_img, got, SPP, name)
+    finally:
+        rs.close()
+
+
+@pytest.mark.parametrize("name", ["cornell_cmj16", "cornell_cmj12"])
+def test_cmj_sampling_matches_reference(ref, device, name):
+    desc = sampling_cases()[name]
+    rs = ref.build_scene(desc)
+    try:
+        device.upload_scene(rs.device_arrays())
+        ref_img, _ = rs.render(0, desc.spp, tile_size=64)
+        got = device.render(desc.width, desc.height, rs.pass_stride, 0, desc.spp)
+        image_gates(ref_img, got, desc.spp, name)
     finally:
         rs.close()
 
