@@ -155,6 +155,14 @@ ref_scene *ref_scene_new(const char *xml_path, int kernel, void *external_device
 
   if (xml_path && xml_path[0]) {
     xml_read_file(rs->scene, xml_path);
+    /* cycles_standalone.cpp:145 recomputes the view plane after reading the scene; for
+     * the panoramic cameras that is what makes the frame cover (u, v) in [0,1]^2 (the
+     * perspective / orthographic scenes of this repo keep the view plane the XML reader
+     * left, which the committed golden vectors were made with) */
+    if (rs->scene->camera->type == CAMERA_PANORAMA) {
+      rs->scene->camera->compute_auto_viewplane();
+      rs->scene->camera->need_update = true;
+    }
   }
   return rs;
 }

@@ -6,7 +6,8 @@
  * to rounding of the transcendental functions.
  *
  * Scope (b200_cycles.cu:check_scope / svm_validate refuse anything else):
- * perspective and orthographic cameras (with depth of field, without motion blur),
+ * perspective, orthographic and panoramic cameras (with depth of field, without motion
+ * blur or stereo),
  * static triangles and instances,
  * point / spot / area / distant lamps, emissive triangles (light_tri.cuh), background
  * colour, SVM nodes of
@@ -282,6 +283,59 @@ CY_DEV float2 camera_sample_aperture(float u, float v)
   return bokeh;
 }
 
+/* kernel_projection.h:50-215: raster-plane (u, v) of a panoramic camera -> direction in
+ * camera space; a zero vector means "outside the lens" */
+CY_DEV f3 panorama_to_direction(float u, float v)
+{
+  switch (kd_int(KD_CAM_PANORAMA_TYPE)) {
+    case CY_PANORAMA_EQUIRECTANGULAR: {
+      const float4 range = kd_float4(KD_CAM_EQUIRECTANGULAR_RANGE);
+      const float phi = range.x * u + range.y;
+      const float theta = range.z * v + range.w;
+      const float sin_theta = sinf(theta);
+      return mk3(sin_theta * cosf(phi), sin_theta * sinf(phi), cosf(theta));
+    }
+    case CY_PANORAMA_MIRRORBALL: {
+      /* point on the ball, then the reflection of the view axis */
+      f3 dir;
+      dir.x = 2.0f * u - 1.0f;
+      dir.z = 2.0f * v - 1.0f;
+      if (dir.x * dir.x + dir.z * dir.z > 1.0f)
+        return zero3();
+      dir.y = -sqrtf(fmaxf(1.0f - dir.x * dir.x - dir.z * dir.z, 0.0f));
+      const f3 I = mk3(0.0f, -1.0f, 0.0f);
+      return 2.0f * dot(dir, I) * dir - I;
+    }
+    case CY_PANORAMA_FISHEYE_EQUIDISTANT: {
+      const float fov = kd_float(KD_CAM_FISHEYE_FOV);
+      u = (u - 0.5f) * 2.0f;
+      v = (v - 0.5f) * 2.0f;
+      const float r = sqrtf(u * u + v * v);
+      if (r > 1.0f)
+        return zero3();
+      float phi = acosf(fminf(fmaxf((r != 0.0f) ? u / r : 0.0f, -1.0f), 1.0f));
+      const float theta = r * fov * 0.5f;
+      if (v < 0.0f)
+        phi = -phi;
+      return mk3(cosf(theta), -cosf(phi) * sinf(theta), sinf(phi) * sinf(theta));
+    }
+    default: { /* PANORAMA_FISHEYE_EQUISOLID */
+      const float lens = kd_float(KD_CAM_FISHEYE_LENS), fov = kd_float(KD_CAM_FISHEYE_FOV);
+      u = (u - 0.5f) * kd_float(KD_CAM_SENSORWIDTH);
+      v = (v - 0.5f) * kd_float(KD_CAM_SENSORHEIGHT);
+      const float rmax = 2.0f * lens * sinf(fov * 0.25f);
+      const float r = sqrtf(u * u + v * v);
+      if (r > rmax)
+        return zero3();
+      float phi = acosf(fminf(fmaxf((r != 0.0f) ? u / r : 0.0f, -1.0f), 1.0f));
+      const float theta = 2.0f * asinf(r / (2.0f * lens));
+      if (v < 0.0f)
+        phi = -phi;
+      return mk3(cosf(theta), -cosf(phi) * sinf(theta), sinf(phi) * sinf(theta));
+    }
+  }
+}
+
 CY_DEV float camera_ray(int x, int y, int sample, uint32_t *rng_hash, f3 *P, f3 *D)
 {
   *rng_hash = hash_uint2((uint32_t)x, (uint32_t)y);
@@ -315,6 +369,30 @@ CY_DEV float camera_ray(int x, int y, int sample, uint32_t *rng_hash, f3 *P, f3 
   c2w.x = kd_float4(KD_CAM_CAMERATOWORLD);
   c2w.y = kd_float4(KD_CAM_CAMERATOWORLD + 16);
   c2w.z = kd_float4(KD_CAM_CAMERATOWORLD + 32);
+
+  if (kd_int(KD_CAM_TYPE) == CY_CAMERA_PANORAMA) {
+    /* camera_sample_panorama - kernel_camera.h:238-351 (no stereo, no motion) */
+    f3 Dp = panorama_to_direction(Pcamera.x, Pcamera.y);
+    if (is_zero(Dp))
+      return 0.0f; /* outside the lens: the path receives no light (ray.t = 0) */
+    f3 Pp = zero3();
+    if (aperturesize > 0.0f) {
+      const float2 lensuv = camera_sample_aperture(lens_u, lens_v);
+      const f3 Dfocus = normalize(Dp);
+      const f3 Pfocus = Dfocus * kd_float(KD_CAM_FOCALDISTANCE);
+      /* orthonormal frame perpendicular to the focus direction */
+      const f3 U = normalize(mk3(1.0f, 0.0f, 0.0f) - Dfocus.x * Dfocus);
+      const f3 V = normalize(cross(Dfocus, U));
+      Pp = U * (lensuv.x * aperturesize) + V * (lensuv.y * aperturesize);
+      Dp = normalize(Pfocus - Pp);
+    }
+    f3 Pw = transform_point(c2w, Pp);
+    f3 Dw = normalize(transform_direction(c2w, Dp));
+    Pw += kd_float(KD_CAM_NEARCLIP) * Dw;
+    *P = Pw;
+    *D = Dw;
+    return kd_float(KD_CAM_CLIPLENGTH);
+  }
 
   if (kd_int(KD_CAM_TYPE) == CY_CAMERA_ORTHOGRAPHIC) {
     /* camera_sample_orthographic - kernel_camera.h:174-235 */

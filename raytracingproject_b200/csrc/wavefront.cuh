@@ -1450,8 +1450,9 @@ static int check_scope(b200_ctx *ctx)
   auto I = [&](int off) { return kd_host<int>(ctx, off); };
   auto F = [&](int off) { return kd_host<float>(ctx, off); };
   std::string why;
-  if (I(KD_CAM_TYPE) != CY_CAMERA_PERSPECTIVE && I(KD_CAM_TYPE) != CY_CAMERA_ORTHOGRAPHIC)
-    why = "panoramic cameras are outside the hot-path scope";
+  if (I(KD_CAM_TYPE) != CY_CAMERA_PERSPECTIVE && I(KD_CAM_TYPE) != CY_CAMERA_ORTHOGRAPHIC &&
+      I(KD_CAM_TYPE) != CY_CAMERA_PANORAMA)
+    why = "unknown camera type";
   else if (F(KD_CAM_INTEROCULAR_OFFSET) != 0.0f)
     why = "stereo cameras are outside the hot-path scope";
   else if (F(KD_CAM_SHUTTERTIME) != -1.0f || I(KD_CAM_NUM_MOTION_STEPS) != 0 ||

@@ -424,7 +424,8 @@ def terrain(width=1920, height=1080, spp=256, n=708, max_bounce=0):
 
 # ---------------------------------------------------------------- config 3
 def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
-            materials="principled", light="area", panes=0, transparent_max=8, pattern="sobol"):
+            materials="principled", light="area", panes=0, transparent_max=8, pattern="sobol",
+            cam_type="perspective", cam_extra="", cam_pose=None):
     """BASELINE config 3 - Cornell box, ceiling area light, one metallic and one
     glass Principled box (materials="diffuse" gives the all-diffuse variant).
     light="mesh" replaces the lamp by an emissive quad (a mesh light: its two triangles
@@ -434,12 +435,12 @@ def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
     horizontal sheets of the "glass" material under the light (stacked transparent
     surfaces for the shadow rays), `transparent_max` is the transparent bounce limit."""
     xml = "<cycles>\n"
-    cam = look_at((0.0, -3.6, 1.0), (0.0, 0.0, 1.0))
+    cam = look_at((0.0, -3.6, 1.0), (0.0, 0.0, 1.0)) if cam_pose is None else cam_pose
     fov = 2.0 * np.arctan(0.5 * 36.0 / 50.0 / (width / height)) * 1.6
     xml += _header(width, height, cam, fov,
                    _integrator(max_bounce, clamp_indirect=10.0, transparent=transparent_max,
                                pattern=pattern, aa_samples=spp),
-                   nearclip=0.01, farclip=100.0)
+                   nearclip=0.01, farclip=100.0, cam_type=cam_type, cam_extra=cam_extra)
     xml += _background((0, 0, 0), 0.0)
     closure_variants = {"closures": 0, "closures2": 1, "transparent_opaque_shadow": 2,
                         "transparent": 3}

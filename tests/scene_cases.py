@@ -36,6 +36,12 @@ def camera_cases():
     six-blade anamorphic aperture (kernel_camera.h:21-40), orthographic with and
     without a lens."""
     cube = lambda **kw: scenes.default_cube(W, H, material="diffuse", **kw)
+    # panoramic projections look down the camera's +X axis (kernel_projection.h): a pose
+    # inside the box, just behind its open front, with X pointing at the back wall
+    import numpy as np
+    inside = np.array([[0, 0, 1, 0.0], [1, 0, 0, -0.95], [0, 1, 0, 1.0]], np.float32)
+    box = lambda **kw: scenes.cornell(W, H, materials="diffuse", cam_type="panorama",
+                                      cam_pose=inside, **kw)
     return {
         "cube_dof_disk": cube(cam_extra='aperturesize="0.35" focaldistance="9.5"'),
         "cube_dof_blades": cube(cam_extra='aperturesize="0.3" focaldistance="11" blades="6" '
@@ -43,6 +49,17 @@ def camera_cases():
         "cube_ortho": cube(cam_type="orthograph"),
         "cube_ortho_dof": cube(cam_type="orthograph",
                                cam_extra='aperturesize="0.15" focaldistance="10"'),
+        # panoramic cameras from inside the Cornell box; the fisheyes leave the frame
+        # corners outside the lens (camera rays with t = 0)
+        "cornell_equirect": box(cam_extra='panorama_type="equirectangular"'),
+        "cornell_equirect_dof": box(cam_extra='panorama_type="equirectangular" '
+                                    'aperturesize="0.03" focaldistance="1.5"'),
+        "cornell_fisheye": box(cam_extra='panorama_type="fisheye_equidistant" '
+                               'fisheye_fov="3.4"'),
+        "cornell_fisheye_equisolid": box(cam_extra='panorama_type="fisheye_equisolid" '
+                                         'fisheye_lens="10.5" fisheye_fov="3.14159" '
+                                         'sensorwidth="36" sensorheight="20.25"'),
+        "cornell_mirrorball": box(cam_extra='panorama_type="mirrorball"'),
     }
 
 

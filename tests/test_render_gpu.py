@@ -95,7 +95,9 @@ def test_closure_nodes_match_reference(ref, device, name):
 
 
 @pytest.mark.parametrize("name", ["cube_dof_disk", "cube_dof_blades", "cube_ortho",
-                                  "cube_ortho_dof"])
+                                  "cube_ortho_dof", "cornell_equirect", "cornell_equirect_dof",
+                                  "cornell_fisheye", "cornell_fisheye_equisolid",
+                                  "cornell_mirrorball"])
 def test_camera_models_match_reference(ref, device, name):
     desc = camera_cases()[name]
     rs = ref.build_scene(desc)
