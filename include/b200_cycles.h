@@ -122,6 +122,14 @@ size_t b200_mem_used(b200_ctx *ctx);
 int b200_bind_global(b200_ctx *ctx, const char *name, uint64_t dptr, const void *host,
                      size_t bytes);
 
+/* Host-only scope check of a compiled SVM program (the `__svm_nodes` array built by
+ * SVMShaderManager::device_update_shader, render/svm.cpp:70-133): the same walk
+ * b200_bind_global runs, without a device or a context.  Returns B200_OK, or
+ * B200_ERR_UNSUPPORTED with the first opcode / closure / option outside the supported
+ * subset described in `err`.  Lets an integrator decide up front whether a scene can
+ * go to this device (the reference has no such query: its devices take every node). */
+int b200_validate_svm(const void *svm_nodes, size_t bytes, char *err, size_t errlen);
+
 /* Device::const_copy_to("__data", &KernelData, sizeof) (render/scene.cpp:307). */
 int b200_set_kernel_data(b200_ctx *ctx, const void *kernel_data, size_t bytes);
 

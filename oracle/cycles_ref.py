@@ -69,6 +69,8 @@ def lib():
             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.ref_init.argtypes = [C.c_int]
         L.ref_path_dump.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.ref_svm_node.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]
         L.ref_count_rays.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.ref_num_threads.restype = C.c_int
         _lib = L
@@ -84,6 +86,11 @@ def global_names():
             return out
         out.append(n.decode())
         i += 1
+
+
+SHADING_POINT_DTYPE = np.dtype([("P", "<f4", 3), ("N", "<f4", 3), ("I", "<f4", 3),
+                                ("dPdu", "<f4", 3), ("u", "<f4"), ("v", "<f4"),
+                                ("object", "<i4"), ("prim", "<i4"), ("lamp", "<i4")])
 
 
 class RefScene:
@@ -206,6 +213,16 @@ class RefScene:
         out = np.zeros((16, 32), np.float32)
         self._check(self._L.ref_path_dump(self._h, sample, x, y, out.ctypes.data))
         return out
+
+    def svm_node(self, nodes, offset, stack, point):
+        """Runs the node at `offset` of the uint4 program `nodes` through the reference's
+        svm_node_* function on one shading point (SHADING_POINT_DTYPE record); `stack`
+        (float32, >= 260) is updated in place.  Returns the offset after the node, -1
+        for an opcode the probe does not dispatch."""
+        nxt = C.c_int(-1)
+        self._check(self._L.ref_svm_node(self._h, nodes.ctypes.data, int(offset),
+                                         stack.ctypes.data, point.ctypes.data, C.byref(nxt)))
+        return nxt.value
 
     def count_rays(self, start_sample, num_samples):
         """(camera, bounce, shadow) rays the reference traces for these samples."""

@@ -214,6 +214,24 @@ int ref_scene_add_mesh(ref_scene *rs,
     mesh->add_vertex(make_float3(P[3 * i], P[3 * i + 1], P[3 * i + 2]));
   for (int i = 0; i < num_tris; i++)
     mesh->add_triangle(tris[3 * i], tris[3 * i + 1], tris[3 * i + 2], 0, smooth != 0);
+  /* Attributes the shader asks for, filled the way the standalone XML reader does
+   * (app/cycles_xml.cpp:528-533: generated coordinates = vertex positions) plus a
+   * planar per-corner UV map (the reader takes UVs from the file; here u, v = x, y of
+   * the corner's vertex, so that ATTR_ELEMENT_CORNER float2 data is exercised). */
+  if (mesh->need_attribute(rs->scene, ATTR_STD_GENERATED)) {
+    Attribute *attr = mesh->attributes.add(ATTR_STD_GENERATED);
+    memcpy(attr->data_float3(), mesh->verts.data(), sizeof(float3) * mesh->verts.size());
+  }
+  if (mesh->need_attribute(rs->scene, ATTR_STD_UV) ||
+      mesh->need_attribute(rs->scene, ustring("UVMap"))) {
+    Attribute *attr = mesh->attributes.add(ATTR_STD_UV, ustring("UVMap"));
+    float2 *uv = attr->data_float2();
+    for (int i = 0; i < num_tris; i++)
+      for (int c = 0; c < 3; c++) {
+        const int v = tris[3 * i + c];
+        uv[3 * i + c] = make_float2(P[3 * v], P[3 * v + 1]);
+      }
+  }
   rs->meshes.push_back(mesh);
   return (int)rs->meshes.size() - 1;
 }
@@ -568,6 +586,21 @@ int ref_path_dump(ref_scene *rs, int sample, int x, int y, float *out)
   {
     ScopedFlushToZero ftz;
     ref_probe_path_dump(&kg, sample, x, y, out);
+  }
+  rs->cpu->kg_free(&kg);
+  return 0;
+}
+
+/* One SVM node of `nodes` (uint4 words) on one shading point; *next = offset after it. */
+int ref_svm_node(ref_scene *rs, const void *nodes, int offset, float *stack,
+                 const RefShadingPoint *p, int *next)
+{
+  if (!rs->cpu)
+    return 1;
+  KernelGlobals kg = rs->cpu->kg_init();
+  {
+    ScopedFlushToZero ftz;
+    *next = ref_probe_svm_node(&kg, nodes, offset, stack, p);
   }
   rs->cpu->kg_free(&kg);
   return 0;

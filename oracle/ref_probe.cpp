@@ -345,4 +345,84 @@ void ref_probe_path_trace(
   kernel_path_trace(kg, buffer, sample, x, y, offset, stride);
 }
 
+/* Runs ONE node of a caller-supplied SVM program through the reference's own
+ * svm_node_* function (the dispatch of svm/svm.h:220-500 for the texture, attribute and
+ * mapping opcodes) on a caller-supplied shading point; returns the offset after the
+ * node or -1.  kg's scene arrays (objects, attributes, lights, camera) are the bound
+ * scene's; only __svm_nodes is swapped for the call. */
+int ref_probe_svm_node(KernelGlobals *kg, const void *nodes, int offset, float *stack,
+                       const RefShadingPoint *p)
+{
+  uint4 *saved = kg->__svm_nodes.data;
+  kg->__svm_nodes.data = (uint4 *)nodes;
+  ShaderData sd_storage;
+  ShaderData *sd = &sd_storage;
+  memset((void *)sd, 0, sizeof(ShaderData));
+  sd->P = make_float3(p->P[0], p->P[1], p->P[2]);
+  sd->N = make_float3(p->N[0], p->N[1], p->N[2]);
+  sd->Ng = sd->N;
+  sd->I = make_float3(p->I[0], p->I[1], p->I[2]);
+  sd->dPdu = make_float3(p->dPdu[0], p->dPdu[1], p->dPdu[2]);
+  sd->u = p->u;
+  sd->v = p->v;
+  sd->object = p->object;
+  sd->prim = p->prim;
+  sd->lamp = p->lamp;
+  sd->type = (p->prim != PRIM_NONE) ? PRIMITIVE_TRIANGLE :
+                                      ((p->lamp != LAMP_NONE) ? PRIMITIVE_LAMP : PRIMITIVE_NONE);
+  if (sd->object != OBJECT_NONE) {
+    sd->ob_tfm = object_fetch_transform(kg, sd->object, OBJECT_TRANSFORM);
+    sd->ob_itfm = object_fetch_transform(kg, sd->object, OBJECT_INVERSE_TRANSFORM);
+  }
+  else if (sd->lamp != LAMP_NONE) {
+    sd->ob_tfm = lamp_fetch_transform(kg, sd->lamp, false);
+    sd->ob_itfm = lamp_fetch_transform(kg, sd->lamp, true);
+  }
+  const int path_flag = 0;
+  uint4 node = read_node(kg, &offset);
+  switch (node.x) {
+    case NODE_ATTR:
+      svm_node_attr(kg, sd, stack, node);
+      break;
+    case NODE_GEOMETRY:
+      svm_node_geometry(kg, sd, stack, node.y, node.z);
+      break;
+    case NODE_TEX_COORD:
+      svm_node_tex_coord(kg, sd, path_flag, stack, node, &offset);
+      break;
+    case NODE_MAPPING:
+      svm_node_mapping(kg, sd, stack, node.y, node.z, node.w, &offset);
+      break;
+    case NODE_TEXTURE_MAPPING:
+      svm_node_texture_mapping(kg, sd, stack, node.y, node.z, &offset);
+      break;
+    case NODE_MIN_MAX:
+      svm_node_min_max(kg, sd, stack, node.y, node.z, &offset);
+      break;
+    case NODE_TEX_NOISE:
+      svm_node_tex_noise(kg, sd, stack, node.y, node.z, node.w, &offset);
+      break;
+    case NODE_TEX_CHECKER:
+      svm_node_tex_checker(kg, sd, stack, node);
+      break;
+    case NODE_TEX_GRADIENT:
+      svm_node_tex_gradient(sd, stack, node);
+      break;
+    case NODE_TEX_WAVE:
+      svm_node_tex_wave(kg, sd, stack, node, &offset);
+      break;
+    case NODE_TEX_MAGIC:
+      svm_node_tex_magic(kg, sd, stack, node, &offset);
+      break;
+    case NODE_TEX_BRICK:
+      svm_node_tex_brick(kg, sd, stack, node, &offset);
+      break;
+    default:
+      offset = -1;
+  }
+  kg->__svm_nodes.data = saved;
+  return offset;
+}
+
 CCL_NAMESPACE_END
+

@@ -22,8 +22,18 @@ struct RefProbeHit {
   int32_t type;
 };
 
+/* One shading point for ref_probe_svm_node (same layout as HostShadingPoint of
+ * tests/host_check/svm_tex_host.cpp). */
+struct RefShadingPoint {
+  float P[3], N[3], I[3], dPdu[3];
+  float u, v;
+  int32_t object, prim, lamp;
+};
+
 namespace ccl {
 struct KernelGlobals;
+int ref_probe_svm_node(KernelGlobals *kg, const void *nodes, int offset, float *stack,
+                       const RefShadingPoint *p);
 void ref_probe_intersect(KernelGlobals *kg, const RefProbeRay *rays, RefProbeHit *hits, size_t n);
 void ref_probe_camera_rays(KernelGlobals *kg, int sample, int x0, int y0, int w, int h,
                            RefProbeRay *rays, unsigned int *rng_hash);

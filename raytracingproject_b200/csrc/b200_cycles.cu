@@ -350,7 +350,8 @@ int b200_synchronize(b200_ctx *ctx)
 
 /* SVM opcodes / closures the shading kernels implement; anything else in a
  * bound __svm_nodes stream is refused up front instead of rendering wrongly. */
-static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why);
+static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why,
+                         uint32_t *features);
 
 int b200_bind_global(b200_ctx *ctx, const char *name, uint64_t dptr, const void *host,
                      size_t bytes)
@@ -390,7 +391,8 @@ int b200_bind_global(b200_ctx *ctx, const char *name, uint64_t dptr, const void 
   static const char *keep_host[] = {"__bvh_nodes",     "__bvh_leaf_nodes", "__prim_tri_verts",
                                     "__prim_tri_index", "__prim_type",      "__prim_visibility",
                                     "__prim_object",    "__object_node",    "__objects",
-                                    "__svm_nodes",      "__lights",         "__curves"};
+                                    "__svm_nodes",      "__lights",         "__curves",
+                                    "__tri_patch"};
   HostArray ha;
   ha.dptr = dptr;
   ha.bytes = bytes;
@@ -409,10 +411,20 @@ int b200_bind_global(b200_ctx *ctx, const char *name, uint64_t dptr, const void 
         return rc;
     }
   }
+  if (strcmp(name, "__svm_nodes") == 0 && !bytes)
+    ctx->svm_features = 0;
   if (strcmp(name, "__svm_nodes") == 0 && bytes) {
     std::string why;
-    if (!svm_validate((const uint32_t *)ha.host.data(), bytes / 16, why))
+    if (!svm_validate((const uint32_t *)ha.host.data(), bytes / 16, why, &ctx->svm_features))
       return fail(ctx, B200_ERR_UNSUPPORTED, why);
+  }
+  if (strcmp(name, "__tri_patch") == 0) {
+    ctx->has_subd_patches = false;
+    const uint32_t *patch = (const uint32_t *)ha.host.data();
+    for (size_t i = 0; i < bytes / 4; i++)
+      if (patch[i] != ~0u)
+        ctx->has_subd_patches = true;
+    ha.host = std::vector<uint8_t>(); /* only the flag is kept */
   }
   if ((strcmp(name, "__curves") == 0 || strcmp(name, "__curve_keys") == 0) && bytes)
     return fail(ctx, B200_ERR_UNSUPPORTED, "hair curves are outside the hot-path scope");
@@ -420,6 +432,21 @@ int b200_bind_global(b200_ctx *ctx, const char *name, uint64_t dptr, const void 
   ctx->globals[name] = std::move(ha);
   ctx->scene_dirty = true;
   return B200_OK;
+}
+
+int b200_validate_svm(const void *svm_nodes, size_t bytes, char *err, size_t errlen)
+{
+  std::string why;
+  uint32_t features = 0;
+  if (!svm_nodes || bytes % 16 != 0)
+    why = "an SVM program is an array of 16-byte nodes";
+  else if (svm_validate((const uint32_t *)svm_nodes, bytes / 16, why, &features))
+    return B200_OK;
+  if (err && errlen) {
+    strncpy(err, why.c_str(), errlen - 1);
+    err[errlen - 1] = 0;
+  }
+  return (svm_nodes && bytes % 16 == 0) ? B200_ERR_UNSUPPORTED : B200_ERR_INVALID;
 }
 
 int b200_set_kernel_data(b200_ctx *ctx, const void *kernel_data, size_t bytes)
@@ -548,6 +575,11 @@ static int prepare_scene(b200_ctx *ctx)
   ds.svm_nodes = (const uint4 *)ptr("__svm_nodes");
   ds.lookup_table = (const float *)ptr("__lookup_table");
   ds.sample_pattern_lut = (const uint32_t *)ptr("__sample_pattern_lut");
+  ds.attributes_map = (const uint4 *)ptr("__attributes_map");
+  ds.attributes_float = (const float *)ptr("__attributes_float");
+  ds.attributes_float2 = (const float2 *)ptr("__attributes_float2");
+  ds.attributes_float3 = (const float4 *)ptr("__attributes_float3");
+  ds.attributes_uchar4 = (const uchar4 *)ptr("__attributes_uchar4");
   memcpy(ds.kdata, ctx->kernel_data.data(), SIZEOF_KERNEL_DATA);
   CUDA_TRY(ctx, cudaMemcpyToSymbol(g_scene, &ds, sizeof(ds)));
   ctx->scene_dirty = false;

@@ -22,6 +22,11 @@ struct HostArray {
 
 struct PathPool; /* wavefront state, defined in b200_cycles.cu */
 
+/* what the bound SVM program reads beyond the geometry (checked against the scene in
+ * check_scope) */
+#define SVM_USES_ATTRIBUTES 1u
+#define SVM_USES_WINDOW_COORDINATES 2u
+
 struct b200_ctx {
   int ordinal = 0;
   int num_sms = 0;
@@ -39,6 +44,8 @@ struct b200_ctx {
   std::vector<uint8_t> kernel_data;
   bool scene_dirty = true; /* BVH8 / constant block must be (re)built */
   bool have_data = false;
+  uint32_t svm_features = 0;     /* SVM_USES_* of the bound __svm_nodes (svm_validate) */
+  bool has_subd_patches = false; /* __tri_patch holds a patch index */
 
   /* BVH8 on the device */
   void *d_nodes = nullptr;

@@ -156,6 +156,9 @@ CY_DEV f3 bsdf_eval(const ShaderDataG &sd, const Closure &sc, f3 omega_in, float
       case CY_CLOSURE_BSDF_PRINCIPLED_DIFFUSE_ID:
         eval = bsdf_principled_diffuse_eval_reflect(sc, sd.I, omega_in, pdf);
         break;
+      case CY_CLOSURE_BSDF_PRINCIPLED_SHEEN_ID:
+        eval = bsdf_principled_sheen_eval_reflect(sc, sd.I, omega_in, pdf);
+        break;
       case CY_CLOSURE_BSDF_OREN_NAYAR_ID:
         eval = bsdf_oren_nayar_eval_reflect(sc, sd.I, omega_in, pdf);
         break;
@@ -196,6 +199,8 @@ CY_DEV int bsdf_sample(const ShaderDataG &sd, const Closure &sc, float randu, fl
       return bsdf_diffuse_sample(sc, sd.Ng, randu, randv, eval, omega_in, pdf);
     case CY_CLOSURE_BSDF_PRINCIPLED_DIFFUSE_ID:
       return bsdf_principled_diffuse_sample(sc, sd.Ng, sd.I, randu, randv, eval, omega_in, pdf);
+    case CY_CLOSURE_BSDF_PRINCIPLED_SHEEN_ID:
+      return bsdf_principled_sheen_sample(sc, sd.Ng, sd.I, randu, randv, eval, omega_in, pdf);
     case CY_CLOSURE_BSDF_OREN_NAYAR_ID:
       return bsdf_oren_nayar_sample(sc, sd.Ng, sd.I, randu, randv, eval, omega_in, pdf);
     case CY_CLOSURE_BSDF_TRANSLUCENT_ID:

@@ -111,6 +111,44 @@ CY_DEV int bsdf_principled_diffuse_sample(const Closure &bsdf, f3 Ng, f3 I, floa
   return CY_LABEL_REFLECT | CY_LABEL_DIFFUSE;
 }
 
+/* ---- Principled sheen (closure/bsdf_principled_sheen.h:47-134) ---- */
+
+CY_DEV f3 principled_sheen_brdf(f3 N, f3 V, f3 L, f3 H, float *pdf)
+{
+  const float NdotL = dot(N, L), NdotV = dot(N, V);
+  if (NdotL < 0 || NdotV < 0) {
+    *pdf = 0.0f;
+    return zero3();
+  }
+  const float value = schlick_fresnel(dot(L, H)) * NdotL;
+  return mk3(value, value, value);
+}
+CY_DEV f3 bsdf_principled_sheen_eval_reflect(const Closure &bsdf, f3 I, f3 omega_in, float *pdf)
+{
+  const f3 N = bsdf.N;
+  const f3 H = normalize(omega_in + I);
+  if (dot(N, omega_in) > 0.0f) {
+    *pdf = fmaxf(dot(N, omega_in), 0.0f) * CY_M_1_PI_F;
+    return principled_sheen_brdf(N, I, omega_in, H, pdf);
+  }
+  *pdf = 0.0f;
+  return zero3();
+}
+CY_DEV int bsdf_principled_sheen_sample(const Closure &bsdf, f3 Ng, f3 I, float randu,
+                                        float randv, f3 *eval, f3 *omega_in, float *pdf)
+{
+  const f3 N = bsdf.N;
+  sample_cos_hemisphere(N, randu, randv, omega_in, pdf);
+  if (dot(Ng, *omega_in) > 0) {
+    const f3 H = normalize(I + *omega_in);
+    *eval = principled_sheen_brdf(N, I, *omega_in, H, pdf);
+  }
+  else {
+    *pdf = 0.0f;
+  }
+  return CY_LABEL_REFLECT | CY_LABEL_DIFFUSE;
+}
+
 /* ---- GGX microfacet ---- */
 
 /* kernel_montecarlo.h:50-54 */

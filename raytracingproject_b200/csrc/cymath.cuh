@@ -13,7 +13,9 @@
 #include <math.h>
 #include <stdint.h>
 
+#ifndef CY_DEV /* tests/host_check compiles the node files for the host */
 #define CY_DEV __device__ __forceinline__
+#endif
 
 #define CY_PI_F 3.1415926535897932f
 #define CY_2PI_F 6.2831853071795864f
@@ -28,6 +30,7 @@ struct f3 {
 
 #define CY_M_PI_F 3.1415926535897932f
 #define CY_M_PI_2_F 1.5707963267948966f
+#define CY_M_2PI_F 6.2831853071795864f
 #define CY_M_1_PI_F 0.3183098861837067f
 #define CY_M_PI_4_F 0.7853981633974483f
 

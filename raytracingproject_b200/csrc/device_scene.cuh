@@ -35,6 +35,11 @@ struct DeviceScene {
   const uint4 *svm_nodes;
   const float *lookup_table;
   const uint32_t *sample_pattern_lut;
+  const uint4 *attributes_map;
+  const float *attributes_float;
+  const float2 *attributes_float2;
+  const float4 *attributes_float3;
+  const uchar4 *attributes_uchar4;
 
   /* KernelData, byte-for-byte */
   alignas(16) uint8_t kdata[SIZEOF_KERNEL_DATA];

@@ -20,10 +20,7 @@
 
 #include "device_scene.cuh"
 #include "traverse.cuh"
-
-#define CLOSURE_WEIGHT_CUTOFF 1e-5f
-#define MAX_CLOSURES_GPU 8
-#define SVM_STACK_GPU 256 /* SVM_STACK_SIZE 255 (svm_types.h): any offset the compiler can emit is in range */
+#include "shader_data.cuh"
 
 /* ------------------------------------------------------------- path state */
 
@@ -224,16 +221,6 @@ CY_DEV float lookup_table_read(float x, int offset, int size)
 
 /* ------------------------------------------------------------- camera ray */
 
-/* util/util_projection.h:48-55 */
-CY_DEV f3 transform_perspective(const float4 tx, const float4 ty, const float4 tz,
-                                const float4 tw, f3 a)
-{
-  float4 b = make_float4(a.x, a.y, a.z, 1.0f);
-  f3 c = mk3(dot4(tx, b), dot4(ty, b), dot4(tz, b));
-  float w = dot4(tw, b);
-  return (w != 0.0f) ? c / w : zero3();
-}
-
 /* kernel_path_common.h:21-46 + kernel_random.h:129-153 + kernel_camera.h:355-427,
  * 42-170 (perspective, no DOF, no motion).  Returns Ray::t (0 = no ray). */
 /* kernel_montecarlo.h:150-194 */
@@ -433,54 +420,6 @@ CY_DEV float camera_ray(int x, int y, int sample, uint32_t *rng_hash, f3 *P, f3 
   return kd_float(KD_CAM_CLIPLENGTH) * z_inv;
 }
 
-/* ----------------------------------------------------------- ShaderData */
-
-struct Closure {
-  int type;
-  f3 weight;
-  float sample_weight;
-  f3 N;
-  /* microfacet / principled parameters (closure/bsdf_microfacet.h:38-56) */
-  float alpha_x, alpha_y, ior;
-  f3 T;
-  f3 color, cspec0, fresnel_color; /* MicrofacetExtra */
-  float clearcoat;
-  float roughness; /* PrincipledDiffuseBsdf */
-};
-
-struct ShaderDataG {
-  f3 P, N, Ng, I;
-  f3 dPdu;
-  int shader;
-  uint32_t flag, object_flag;
-  int prim, type, object;
-  float u, v, ray_length;
-  f3 svm_closure_weight;
-  f3 closure_emission_background;
-  f3 closure_transparent_extinction; /* valid when flag & SD_TRANSPARENT */
-  int num_closure, num_closure_left;
-  Closure closure[MAX_CLOSURES_GPU];
-};
-
-CY_DEV uint32_t shader_flags(int shader)
-{
-  return __ldg((const uint32_t *)(g_scene.shaders +
-                                  (size_t)(shader & CY_SHADER_MASK) * SIZEOF_KERNEL_SHADER +
-                                  KS_FLAGS));
-}
-
-/* geom/geom_object.h:166-186 */
-CY_DEV f3 object_normal_transform(int object, f3 N)
-{
-  tfm34 itfm = object_itfm(object);
-  return normalize(transform_direction_transposed(itfm, N));
-}
-CY_DEV f3 object_dir_transform(int object, f3 D)
-{
-  tfm34 tfm = object_tfm(object);
-  return transform_direction(tfm, D);
-}
-
 /* bvh/bvh.h:541-587 (__INTERSECTION_REFINE__ branch) */
 CY_DEV float ray_offset_1(float p, float ng)
 {
@@ -540,6 +479,7 @@ CY_DEV void shader_setup_from_ray(
 {
   sd.object = (isect_object == -1) ? (int)__ldg(&g_scene.prim_object[isect_prim]) : isect_object;
   sd.type = CY_PRIMITIVE_TRIANGLE;
+  sd.lamp = -1;
   sd.flag = 0;
   sd.object_flag = __ldg(&g_scene.object_flag[sd.object]);
   sd.prim = (int)__ldg(&g_scene.prim_index[isect_prim]);
@@ -649,23 +589,9 @@ CY_DEV void emission_setup(ShaderDataG &sd, f3 weight)
   }
 }
 
-CY_DEV f3 stack_load_float3(const float *stack, uint32_t a)
-{
-  return mk3(stack[a + 0], stack[a + 1], stack[a + 2]);
-}
-CY_DEV void stack_store_float3(float *stack, uint32_t a, f3 f)
-{
-  stack[a + 0] = f.x;
-  stack[a + 1] = f.y;
-  stack[a + 2] = f.z;
-}
-CY_DEV bool stack_valid(uint32_t a)
-{
-  return a != (uint32_t)CY_SVM_STACK_INVALID;
-}
-
 #include "svm_closure.cuh"
 #include "svm_nodes.cuh"
+#include "svm_tex.cuh"
 
 /* svm/svm.h:220-300 for the supported opcodes.  max_closures = 0 evaluates only
  * emission / background weights (PATH_RAY_EMISSION / TERMINATE evaluation,
@@ -745,9 +671,7 @@ __device__ __noinline__ void svm_eval_nodes(ShaderDataG &sd, PathDepths depths,
             data = sd.N;
             break;
           case CY_NODE_GEOM_T:
-            /* primitive_tangent without the generated-coordinates branch
-             * (geom_primitive.h:292-320); only read by anisotropic closures */
-            data = normalize(sd.dPdu);
+            data = primitive_tangent(sd);
             break;
           case CY_NODE_GEOM_I:
             data = sd.I;
@@ -828,6 +752,39 @@ __device__ __noinline__ void svm_eval_nodes(ShaderDataG &sd, PathDepths depths,
       case CY_NODE_RGB_CURVES:
       case CY_NODE_VECTOR_CURVES:
         svm_node_curves(stack, node, &offset);
+        break;
+      case CY_NODE_ATTR:
+        svm_node_attr(sd, stack, node);
+        break;
+      case CY_NODE_TEX_COORD:
+        svm_node_tex_coord(sd, stack, node, &offset);
+        break;
+      case CY_NODE_MAPPING:
+        svm_node_mapping(stack, node);
+        break;
+      case CY_NODE_TEXTURE_MAPPING:
+        svm_node_texture_mapping(stack, node, &offset);
+        break;
+      case CY_NODE_MIN_MAX:
+        svm_node_min_max(stack, node, &offset);
+        break;
+      case CY_NODE_TEX_NOISE:
+        svm_node_tex_noise(stack, node, &offset);
+        break;
+      case CY_NODE_TEX_CHECKER:
+        svm_node_tex_checker(stack, node);
+        break;
+      case CY_NODE_TEX_GRADIENT:
+        svm_node_tex_gradient(stack, node);
+        break;
+      case CY_NODE_TEX_WAVE:
+        svm_node_tex_wave(stack, node, &offset);
+        break;
+      case CY_NODE_TEX_MAGIC:
+        svm_node_tex_magic(stack, node, &offset);
+        break;
+      case CY_NODE_TEX_BRICK:
+        svm_node_tex_brick(stack, node, &offset);
         break;
       default:
         /* refused at bind time by svm_validate(); unreachable */
@@ -1388,6 +1345,7 @@ CY_DEV f3 direct_emissive_eval(ShaderDataG &emission_sd, PathDepths depths, Ligh
     emission_sd.type = (ls->prim != CY_PRIM_NONE) ? (int)CY_PRIMITIVE_TRIANGLE : 0;
     emission_sd.object = ls->object;
     emission_sd.prim = ls->prim;
+    emission_sd.lamp = (ls->prim != CY_PRIM_NONE) ? -1 : ls->lamp;
     emission_sd.u = ls->u;
     emission_sd.v = ls->v;
     emission_sd.ray_length = t;
@@ -1462,6 +1420,7 @@ CY_DEV f3 indirect_background(ShaderDataG &emission_sd, const PathStateG &state,
     emission_sd.ray_length = 0.0f;
     emission_sd.object = -1;
     emission_sd.prim = CY_PRIM_NONE;
+    emission_sd.lamp = -1;
     emission_sd.type = 0;
     emission_sd.u = emission_sd.v = 0.0f;
     emission_sd.dPdu = zero3();

@@ -1,0 +1,91 @@
+/* shader_data.cuh - the shading point record (ShaderData, kernel_types.h:1011-1110, cut
+ * to what the supported closures and nodes read), the closure record, the SVM stack
+ * accessors (svm/svm.h:53-113) and the small object / projection transforms the node
+ * implementations share.  Free of warp intrinsics, so that the node files
+ * (svm_nodes.cuh, svm_tex.cuh) also compile for the host in tests/test_svm_host_cpu.py. */
+#ifndef B200_SHADER_DATA_CUH
+#define B200_SHADER_DATA_CUH
+
+#include "device_scene.cuh"
+
+#define CLOSURE_WEIGHT_CUTOFF 1e-5f
+#define MAX_CLOSURES_GPU 32 /* two to four mixed Principled BSDFs (8 each, graph.cpp:1147) */
+#define SVM_STACK_GPU 256 /* SVM_STACK_SIZE 255 (svm_types.h): any offset the compiler can emit is in range */
+
+/* util/util_projection.h:48-55 */
+CY_DEV f3 transform_perspective(const float4 tx, const float4 ty, const float4 tz,
+                                const float4 tw, f3 a)
+{
+  float4 b = make_float4(a.x, a.y, a.z, 1.0f);
+  f3 c = mk3(dot4(tx, b), dot4(ty, b), dot4(tz, b));
+  float w = dot4(tw, b);
+  return (w != 0.0f) ? c / w : zero3();
+}
+
+/* ----------------------------------------------------------- ShaderData */
+
+struct Closure {
+  int type;
+  f3 weight;
+  float sample_weight;
+  f3 N;
+  /* microfacet / principled parameters (closure/bsdf_microfacet.h:38-56) */
+  float alpha_x, alpha_y, ior;
+  f3 T;
+  f3 color, cspec0, fresnel_color; /* MicrofacetExtra */
+  float clearcoat;
+  float roughness; /* PrincipledDiffuseBsdf */
+};
+
+struct ShaderDataG {
+  f3 P, N, Ng, I;
+  f3 dPdu;
+  int shader;
+  uint32_t flag, object_flag;
+  int prim, type, object;
+  int lamp; /* lamp index while its emission shader runs, else -1 (LAMP_NONE) */
+  float u, v, ray_length;
+  f3 svm_closure_weight;
+  f3 closure_emission_background;
+  f3 closure_transparent_extinction; /* valid when flag & SD_TRANSPARENT */
+  int num_closure, num_closure_left;
+  Closure closure[MAX_CLOSURES_GPU];
+};
+
+CY_DEV uint32_t shader_flags(int shader)
+{
+  return __ldg((const uint32_t *)(g_scene.shaders +
+                                  (size_t)(shader & CY_SHADER_MASK) * SIZEOF_KERNEL_SHADER +
+                                  KS_FLAGS));
+}
+
+/* geom/geom_object.h:166-186 */
+CY_DEV f3 object_normal_transform(int object, f3 N)
+{
+  tfm34 itfm = object_itfm(object);
+  return normalize(transform_direction_transposed(itfm, N));
+}
+CY_DEV f3 object_dir_transform(int object, f3 D)
+{
+  tfm34 tfm = object_tfm(object);
+  return transform_direction(tfm, D);
+}
+
+/* ------------------------------------------------------------ SVM stack */
+
+CY_DEV f3 stack_load_float3(const float *stack, uint32_t a)
+{
+  return mk3(stack[a + 0], stack[a + 1], stack[a + 2]);
+}
+CY_DEV void stack_store_float3(float *stack, uint32_t a, f3 f)
+{
+  stack[a + 0] = f.x;
+  stack[a + 1] = f.y;
+  stack[a + 2] = f.z;
+}
+CY_DEV bool stack_valid(uint32_t a)
+{
+  return a != (uint32_t)CY_SVM_STACK_INVALID;
+}
+
+#endif /* B200_SHADER_DATA_CUH */

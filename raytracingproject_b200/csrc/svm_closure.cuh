@@ -35,6 +35,20 @@ CY_DEV uint32_t bsdf_microfacet_ggx_fresnel_setup(Closure *bsdf, const ShaderDat
   bsdf_microfacet_fresnel_color(sd, bsdf);
   return CY_SD_BSDF | CY_SD_BSDF_HAS_EVAL;
 }
+/* util_math.h:563-582 */
+CY_DEV f3 rotate_around_axis(f3 p, f3 axis, float angle)
+{
+  const float c = cosf(angle), s = sinf(angle), ic = 1 - c;
+  f3 r;
+  r.x = ((c + ic * axis.x * axis.x) * p.x) + ((ic * axis.x * axis.y - axis.z * s) * p.y) +
+        ((ic * axis.x * axis.z + axis.y * s) * p.z);
+  r.y = ((ic * axis.x * axis.y + axis.z * s) * p.x) + ((c + ic * axis.y * axis.y) * p.y) +
+        ((ic * axis.y * axis.z - axis.x * s) * p.z);
+  r.z = ((ic * axis.x * axis.z - axis.y * s) * p.x) + ((ic * axis.y * axis.z + axis.x * s) * p.y) +
+        ((c + ic * axis.z * axis.z) * p.z);
+  return r;
+}
+
 CY_DEV uint32_t bsdf_microfacet_ggx_clearcoat_setup(Closure *bsdf, const ShaderDataG &sd)
 {
   bsdf->cspec0 = saturate3(bsdf->cspec0);
@@ -93,7 +107,8 @@ CY_DEV void svm_node_closure_bsdf(ShaderDataG &sd, float *stack, uint4 node, uin
                      roughness_offset = (data_node.z >> 8) & 0xff,
                      specular_tint_offset = (data_node.z >> 16) & 0xff,
                      anisotropic_offset = (data_node.z >> 24) & 0xff;
-      const uint32_t sheen_offset = data_node.w & 0xff, clearcoat_offset = (data_node.w >> 16) & 0xff,
+      const uint32_t sheen_offset = data_node.w & 0xff, sheen_tint_offset = (data_node.w >> 8) & 0xff,
+                     clearcoat_offset = (data_node.w >> 16) & 0xff,
                      clearcoat_roughness_offset = (data_node.w >> 24) & 0xff;
       const uint32_t eta_offset = data_node2.x & 0xff, transmission_offset = (data_node2.x >> 8) & 0xff,
                      anisotropic_rotation_offset = (data_node2.x >> 16) & 0xff,
@@ -106,6 +121,7 @@ CY_DEV void svm_node_closure_bsdf(ShaderDataG &sd, float *stack, uint4 node, uin
       float specular_tint = stack[specular_tint_offset];
       float anisotropic = stack[anisotropic_offset];
       float sheen = stack[sheen_offset];
+      float sheen_tint = stack[sheen_tint_offset];
       float clearcoat = stack[clearcoat_offset];
       float clearcoat_roughness = stack[clearcoat_roughness_offset];
       float transmission = stack[transmission_offset];
@@ -113,8 +129,8 @@ CY_DEV void svm_node_closure_bsdf(ShaderDataG &sd, float *stack, uint4 node, uin
       float transmission_roughness = stack[transmission_roughness_offset];
       float eta = fmaxf(stack[eta_offset], 1e-5f);
       const int distribution = (int)data_node2.y;
-      (void)anisotropic_rotation; /* rotation != 0 needs rotate_around_axis: tangent out of scope */
-      (void)sheen;
+      if (anisotropic_rotation != 0.0f)
+        T = rotate_around_axis(T, N, anisotropic_rotation * CY_M_2PI_F);
 
       float ior = (sd.flag & CY_SD_BACKFACING) ? 1.0f / eta : eta;
       float cosNO = dot(N, sd.I);
@@ -161,6 +177,24 @@ CY_DEV void svm_node_closure_bsdf(ShaderDataG &sd, float *stack, uint4 node, uin
             bsdf->type = CY_CLOSURE_BSDF_PRINCIPLED_DIFFUSE_ID;
             sd.flag |= CY_SD_BSDF | CY_SD_BSDF_HAS_EVAL;
           }
+        }
+      }
+
+      /* sheen (svm_closure.h:256-279) */
+      if (diffuse_weight > CLOSURE_WEIGHT_CUTOFF && sheen > CLOSURE_WEIGHT_CUTOFF) {
+        const float m_cdlum = dot(base_color, mk3(kd_float(KD_FILM_RGB_TO_Y),
+                                                  kd_float(KD_FILM_RGB_TO_Y + 4),
+                                                  kd_float(KD_FILM_RGB_TO_Y + 8)));
+        const f3 m_ctint = m_cdlum > 0.0f ? base_color / m_cdlum : one3();
+        const f3 sheen_color = one3() * (1.0f - sheen_tint) + m_ctint * sheen_tint;
+        Closure *bsdf = bsdf_alloc(sd, weight * sheen * sheen_color * diffuse_weight);
+        if (bsdf) {
+          bsdf->N = N;
+          /* bsdf_principled_sheen_setup (closure/bsdf_principled_sheen.h:67-73) */
+          bsdf->type = CY_CLOSURE_BSDF_PRINCIPLED_SHEEN_ID;
+          const float NdotI = dot(N, sd.I);
+          bsdf->sample_weight *= (NdotI < 0.0f) ? 0.0f : schlick_fresnel(NdotI) * NdotI;
+          sd.flag |= CY_SD_BSDF | CY_SD_BSDF_HAS_EVAL;
         }
       }
 

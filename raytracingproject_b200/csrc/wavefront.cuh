@@ -1319,8 +1319,10 @@ static bool svm_mix_supported_host(uint32_t type)
 }
 
 /* Opcodes and closure ids the kernels implement (svm.h switch subset). */
-static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why)
+static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why,
+                         uint32_t *features)
 {
+  *features = 0;
   /* Walk the stream linearly; NODE_CLOSURE_BSDF and NODE_VALUE_V carry data nodes
    * that must be skipped exactly as the interpreter does. */
   size_t i = 0;
@@ -1337,7 +1339,6 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
       case CY_NODE_MIX_CLOSURE:
       case CY_NODE_JUMP_IF_ZERO:
       case CY_NODE_JUMP_IF_ONE:
-      case CY_NODE_GEOMETRY:
       case CY_NODE_VALUE_F:
       case CY_NODE_CONVERT:
       case CY_NODE_FRESNEL:
@@ -1352,7 +1353,45 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
         break;
       case CY_NODE_LIGHT_PATH:
       case CY_NODE_LIGHT_FALLOFF:
+      case CY_NODE_MAPPING:
+      case CY_NODE_TEX_CHECKER:
+      case CY_NODE_TEX_GRADIENT:
         i += 1;
+        break;
+      case CY_NODE_GEOMETRY: /* the tangent reads the generated-coordinates attribute */
+        if (nodes[4 * i + 1] == 2 /* NODE_GEOM_T */)
+          *features |= SVM_USES_ATTRIBUTES;
+        i += 1;
+        break;
+      case CY_NODE_ATTR:
+        *features |= SVM_USES_ATTRIBUTES;
+        i += 1;
+        break;
+      case CY_NODE_TEX_COORD: {
+        const uint32_t type = nodes[4 * i + 1];
+        if (type == CY_NODE_TEXCO_WINDOW)
+          *features |= SVM_USES_WINDOW_COORDINATES;
+        else if (type != CY_NODE_TEXCO_NORMAL && type != CY_NODE_TEXCO_OBJECT &&
+                 type != CY_NODE_TEXCO_CAMERA && type != CY_NODE_TEXCO_REFLECTION) {
+          why = "texture coordinate type " + std::to_string(type) +
+                " (instancer / volume coordinates) is outside the hot-path scope";
+          return false;
+        }
+        /* object coordinates of another object carry its transform in three nodes */
+        i += (type == CY_NODE_TEXCO_OBJECT && nodes[4 * i + 3] != 0) ? 4 : 1;
+        break;
+      }
+      case CY_NODE_TEX_MAGIC:
+        i += 2;
+        break;
+      case CY_NODE_MIN_MAX:
+      case CY_NODE_TEX_NOISE:
+      case CY_NODE_TEX_WAVE:
+        i += 3;
+        break;
+      case CY_NODE_TEXTURE_MAPPING:
+      case CY_NODE_TEX_BRICK:
+        i += 4;
         break;
       case CY_NODE_VALUE_V:
       case CY_NODE_CLAMP: /* + one node of default values */
@@ -1436,7 +1475,8 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
               " is outside the hot-path scope (supported: closures diffuse/principled-GGX/"
               "glossy-GGX/emission/background, mix closure, value, geometry, convert, fresnel, "
               "layer weight, math, vector math, mix, invert, gamma, bright/contrast, "
-              "separate/combine, clamp, light path, light falloff, RGB ramp, curves)";
+              "separate/combine, clamp, light path, light falloff, RGB ramp, curves, attribute, "
+              "texture coordinate, mapping, noise/wave/magic/checker/brick/gradient textures)";
         return false;
     }
   }
@@ -1482,7 +1522,13 @@ static int check_scope(b200_ctx *ctx)
   else if (F(KD_BG_TRANSPARENT_ROUGHNESS_SQ_THRESHOLD) >= 0.0f)
     why = "transparent glass is outside the hot-path scope";
   else if (I(KD_INT_MAX_CLOSURES) > MAX_CLOSURES_GPU)
-    why = "more than 8 closures per shader";
+    why = "more than 32 closures per shader";
+  else if ((ctx->svm_features & SVM_USES_WINDOW_COORDINATES) &&
+           I(KD_CAM_TYPE) != CY_CAMERA_PERSPECTIVE)
+    why = "window texture coordinates with a non-perspective camera are outside the hot-path "
+          "scope";
+  else if ((ctx->svm_features & SVM_USES_ATTRIBUTES) && ctx->has_subd_patches)
+    why = "attributes on subdivision patches are outside the hot-path scope";
   const HostArray *sh = find_global(ctx, "__shaders");
   if (why.empty() && sh && sh->bytes / SIZEOF_KERNEL_SHADER > WF_MAX_KEYS - 1)
     why = "more than 4095 shaders";

@@ -36,6 +36,7 @@ EXPORTS = [
     "b200_mem_used", "b200_bind_global", "b200_set_kernel_data", "b200_build_bvh", "b200_render",
     "b200_trace_batch", "b200_film_convert", "b200_film_reduce", "b200_get_stats",
     "b200_synchronize", "b200_set_option", "b200_set_stream", "b200_debug_read",
+    "b200_validate_svm",
 ]
 
 
@@ -111,12 +112,23 @@ def load_library():
     L.b200_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.b200_set_stream.argtypes = [vp, u64]
     L.b200_debug_read.argtypes = [vp, vp, sz]
+    L.b200_validate_svm.argtypes = [vp, sz, C.c_char_p, sz]
     _lib = L
     return L
 
 
 class DeviceError(RuntimeError):
     pass
+
+
+def validate_svm(svm_nodes):
+    """b200_validate_svm: None when the compiled SVM program (uint4 array) lies inside
+    the supported subset, else the reason it would be refused.  Needs no GPU."""
+    import numpy as np
+    nodes = np.ascontiguousarray(svm_nodes).view(np.uint8).reshape(-1)
+    err = C.create_string_buffer(512)
+    rc = load_library().b200_validate_svm(nodes.ctypes.data, nodes.size, err, len(err))
+    return None if rc == 0 else err.value.decode()
 
 
 class DeviceMemory:

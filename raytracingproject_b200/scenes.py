@@ -256,6 +256,111 @@ def _closure_shaders(variant):
     return white + red + green + metal + glass
 
 
+def _textured_shaders(variant):
+    """Materials driven by texture coordinates, mesh attributes and the procedural
+    textures (svm_tex.cuh), plus the Principled features that need them: anisotropy
+    with a tangent from the generated coordinates, sheen, clearcoat, and a mix of two
+    Principled BSDFs (16 closures).  Two variants cover the texture types, noise
+    dimensions, mapping types and coordinate sources between them."""
+    c = lambda a, b: '  <connect from="%s" to="%s"/>\n' % (a, b)
+    if variant == 0:
+        white = _node_shader(
+            "white", '  <texture_coordinate name="tc"/>\n'
+            '  <checker_texture name="t" scale="3.0" color1="0.73 0.73 0.73" '
+            'color2="0.3 0.32 0.4"/>\n' + c("tc generated", "t vector") +
+            '  <diffuse_bsdf name="d"/>\n' + c("t color", "d color"), "d bsdf")
+        red = _node_shader(
+            "red", '  <brick_texture name="t" scale="2.5" color1="0.65 0.05 0.05" '
+            'color2="0.4 0.2 0.05" mortar="0.6 0.6 0.6" mortar_size="0.03" mortar_smooth="0.4" '
+            'bias="0.1" brick_width="0.6" row_height="0.3" offset="0.5" squash="0.8" '
+            'squash_frequency="3" tex_mapping.rotation="0 1.5707963 0"/>\n'
+            '  <diffuse_bsdf name="d"/>\n' + c("t color", "d color"), "d bsdf")
+        green = _node_shader(
+            "green", '  <texture_coordinate name="tc"/>\n'
+            '  <mapping name="mp" type="point" location="0.2 0.1 0" rotation="0.3 0.2 0.5" '
+            'scale="1.5 1 2"/>\n' + c("tc object", "mp vector") +
+            '  <wave_texture name="t" type="rings" rings_direction="spherical" profile="sine" '
+            'scale="0.4" distortion="2.5" detail="2.5" detail_scale="1.5" '
+            'detail_roughness="0.6" phase="0.3"/>\n' + c("mp vector", "t vector") +
+            '  <mix name="mx" type="mix" color1="0.12 0.45 0.15" color2="0.6 0.7 0.2"/>\n' +
+            c("t fac", "mx fac") + '  <diffuse_bsdf name="d"/>\n' + c("mx color", "d color"),
+            "d bsdf")
+        metal = _node_shader(
+            "metal", '  <noise_texture name="t" dimensions="4D" scale="3.0" w="0.7" detail="3.0" '
+            'roughness="0.55" distortion="0.6"/>\n'
+            '  <principled_bsdf name="p" distribution="GGX" metallic="1.0" roughness="0.35" '
+            'anisotropic="0.7" anisotropic_rotation="0.15" specular="0.5"/>\n' +
+            c("t color", "p base_color"), "p bsdf")
+        glass = _node_shader(
+            "glass", '  <magic_texture name="t" depth="4" scale="2.0" distortion="1.5"/>\n'
+            '  <gradient_texture name="gr" type="spherical"/>\n'
+            '  <principled_bsdf name="p1" distribution="GGX" roughness="0.6" sheen="1.0" '
+            'sheen_tint="0.5" specular="0.3"/>\n' + c("t color", "p1 base_color") +
+            '  <principled_bsdf name="p2" distribution="GGX" base_color="0.1 0.2 0.7" '
+            'roughness="0.4" clearcoat="1.0" clearcoat_roughness="0.05" metallic="0.3"/>\n'
+            '  <mix_closure name="m"/>\n' + c("gr fac", "m fac") +
+            c("p1 bsdf", "m closure1") + c("p2 bsdf", "m closure2"), "m closure")
+    else:
+        white = _node_shader(
+            "white", '  <texture_coordinate name="tc"/>\n'
+            '  <noise_texture name="t" dimensions="2D" scale="4.0" detail="2.0" '
+            'roughness="0.5"/>\n' + c("tc uv", "t vector") +
+            '  <mix name="mx" type="mix" color1="0.73 0.73 0.73" color2="0.35 0.3 0.25"/>\n' +
+            c("t fac", "mx fac") + '  <diffuse_bsdf name="d"/>\n' + c("mx color", "d color"),
+            "d bsdf")
+        red = _node_shader(
+            "red", '  <texture_coordinate name="tc"/>\n'
+            '  <wave_texture name="t" type="bands" bands_direction="diagonal" profile="saw" '
+            'scale="1.2" tex_mapping.scale="1 2 1" tex_mapping.use_minmax="true" '
+            'tex_mapping.min="-0.8 -0.8 -0.8" tex_mapping.max="0.8 0.8 0.8"/>\n' +
+            c("tc normal", "t vector") +
+            '  <gradient_texture name="gr" type="radial"/>\n' + c("tc camera", "gr vector") +
+            '  <mix name="mx" type="mix" color1="0.65 0.05 0.05" color2="0.7 0.5 0.1"/>\n' +
+            c("t fac", "mx fac") +
+            '  <mix name="mx2" type="multiply" color2="0.8 0.8 0.8" fac="0.5"/>\n' +
+            c("mx color", "mx2 color1") + c("gr color", "mx2 color2") +
+            '  <diffuse_bsdf name="d"/>\n' + c("mx2 color", "d color"), "d bsdf")
+        green = _node_shader(
+            "green", '  <attribute name="at" attribute="UVMap"/>\n'
+            '  <mapping name="mp" type="texture" location="0.1 0.2 0" rotation="0 0 0.4" '
+            'scale="0.5 0.25 1"/>\n' + c("at vector", "mp vector") +
+            '  <checker_texture name="t" scale="2.0" color1="0.12 0.45 0.15" '
+            'color2="0.5 0.6 0.1"/>\n' + c("mp vector", "t vector") +
+            '  <noise_texture name="n1" dimensions="1D" scale="3.0" detail="1.5" '
+            'distortion="0.3"/>\n' + c("at fac", "n1 w") +
+            '  <mix name="mx" type="mix" color2="0.9 0.9 0.9"/>\n' + c("t color", "mx color1") +
+            c("n1 fac", "mx fac") + '  <diffuse_bsdf name="d"/>\n' + c("mx color", "d color"),
+            "d bsdf")
+        metal = _node_shader(
+            "metal", '  <texture_coordinate name="tc"/>\n'
+            '  <mapping name="mp" type="normal" rotation="0.2 0.1 0" scale="1 2 1"/>\n' +
+            c("tc reflection", "mp vector") +
+            '  <wave_texture name="t" type="rings" rings_direction="z" profile="tri" '
+            'scale="0.5"/>\n' + c("mp vector", "t vector") +
+            '  <noise_texture name="n3" dimensions="3D" scale="2.0" detail="2.5" '
+            'roughness="0.7" distortion="0.4"/>\n'
+            '  <mix name="mx" type="mix" fac="0.5"/>\n' + c("t color", "mx color1") +
+            c("n3 color", "mx color2") +
+            '  <glossy_bsdf name="g" distribution="GGX" roughness="0.25"/>\n' +
+            c("mx color", "g color"), "g bsdf")
+        glass = _node_shader(
+            "glass", '  <texture_coordinate name="tc"/>\n'
+            '  <mapping name="mp" type="vector" rotation="0 0.5 0" scale="8 8 8"/>\n' +
+            c("tc window", "mp vector") +
+            '  <gradient_texture name="g1" type="easing"/>\n' + c("mp vector", "g1 vector") +
+            '  <gradient_texture name="g2" type="quadratic_sphere"/>\n'
+            '  <gradient_texture name="g3" type="diagonal"/>\n' + c("tc object", "g3 vector") +
+            '  <combine_xyz name="cmb"/>\n' + c("g1 fac", "cmb x") + c("g2 fac", "cmb y") +
+            c("g3 fac", "cmb z") +
+            '  <magic_texture name="t" depth="9" scale="1.5" distortion="0.8"/>\n' +
+            c("tc generated", "t vector") +
+            '  <mix name="mx" type="add" fac="0.4"/>\n' + c("cmb vector", "mx color1") +
+            c("t color", "mx color2") +
+            '  <principled_bsdf name="p" distribution="GGX" roughness="0.5" sheen="0.8" '
+            'clearcoat="0.5" anisotropic="0.4"/>\n' + c("mx color", "p base_color"), "p bsdf")
+    return white + red + green + metal + glass
+
+
 def _integrator(max_bounce, diffuse=None, glossy=None, transmission=None, transparent=8,
                 clamp_indirect=0.0, seed=0, light_threshold=0.01, caustics=True,
                 pattern="sobol", aa_samples=0):
@@ -443,8 +548,10 @@ def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
                    nearclip=0.01, farclip=100.0, cam_type=cam_type, cam_extra=cam_extra)
     xml += _background((0, 0, 0), 0.0)
     closure_variants = {"closures": 0, "closures2": 1, "transparent_opaque_shadow": 2,
-                        "transparent": 3}
-    if materials in closure_variants:
+                        "transparent": 3, "textured": 10, "textured2": 11}
+    if materials in ("textured", "textured2"):
+        xml += _textured_shaders(closure_variants[materials] - 10)
+    elif materials in closure_variants:
         xml += _closure_shaders(closure_variants[materials])
     else:
         xml += _diffuse_shader("white", (0.73, 0.73, 0.73))

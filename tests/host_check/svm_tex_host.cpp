@@ -1,0 +1,117 @@
+/* Host build of the device-side SVM texture / attribute nodes (csrc/svm_tex.cuh) for
+ * tests/test_svm_host_cpu.py: the SAME source the CUDA kernels include, compiled by g++
+ * with the handful of CUDA built-ins it uses mapped to their host meaning.  The test
+ * feeds identical node words, stacks and shading points to this library and to the
+ * reference's own svm_node_* functions (oracle/ref_probe.cpp) and compares the stacks.
+ * TEST INFRASTRUCTURE - never loaded by the product path. */
+#include <cuda_runtime.h> /* vector types and make_float4 & co: plain host headers */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#define CY_DEV static inline
+#undef __device__
+#define __device__
+#undef __noinline__
+#define __noinline__
+#undef __constant__
+#define __constant__
+template<class T> static inline T __ldg(const T *p) { return *p; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+
+#include "../../raytracingproject_b200/csrc/shader_data.cuh"
+#include "../../raytracingproject_b200/csrc/svm_tex.cuh"
+
+struct HostShadingPoint {
+  float P[3], N[3], I[3], dPdu[3];
+  float u, v;
+  int object, prim, lamp;
+};
+
+struct HostSceneArrays {
+  const void *svm_nodes, *objects, *tri_vindex, *lights, *attributes_map, *attributes_float,
+      *attributes_float2, *attributes_float3, *attributes_uchar4, *kernel_data;
+};
+
+extern "C" __attribute__((visibility("default"))) void host_svm_bind(const HostSceneArrays *a)
+{
+  memset(&g_scene, 0, sizeof(g_scene));
+  g_scene.svm_nodes = (const uint4 *)a->svm_nodes;
+  g_scene.objects = (const uint8_t *)a->objects;
+  g_scene.tri_vindex = (const uint4 *)a->tri_vindex;
+  g_scene.lights = (const uint8_t *)a->lights;
+  g_scene.attributes_map = (const uint4 *)a->attributes_map;
+  g_scene.attributes_float = (const float *)a->attributes_float;
+  g_scene.attributes_float2 = (const float2 *)a->attributes_float2;
+  g_scene.attributes_float3 = (const float4 *)a->attributes_float3;
+  g_scene.attributes_uchar4 = (const uchar4 *)a->attributes_uchar4;
+  if (a->kernel_data)
+    memcpy(g_scene.kdata, a->kernel_data, SIZEOF_KERNEL_DATA);
+}
+
+/* Runs the one node at `offset` of the bound program; returns the offset after it, or
+ * -1 for an opcode svm_tex.cuh does not implement. */
+extern "C" __attribute__((visibility("default"))) int host_svm_node(int offset, float *stack, const HostShadingPoint *p)
+{
+  ShaderDataG sd;
+  memset(&sd, 0, sizeof(sd));
+  sd.P = mk3(p->P[0], p->P[1], p->P[2]);
+  sd.N = mk3(p->N[0], p->N[1], p->N[2]);
+  sd.Ng = sd.N;
+  sd.I = mk3(p->I[0], p->I[1], p->I[2]);
+  sd.dPdu = mk3(p->dPdu[0], p->dPdu[1], p->dPdu[2]);
+  sd.u = p->u;
+  sd.v = p->v;
+  sd.object = p->object;
+  sd.prim = p->prim;
+  sd.lamp = p->lamp;
+  sd.type = (p->prim != -1) ? (int)CY_PRIMITIVE_TRIANGLE : 0;
+  const uint4 node = g_scene.svm_nodes[offset];
+  offset++;
+  switch (node.x) {
+    case CY_NODE_ATTR:
+      svm_node_attr(sd, stack, node);
+      break;
+    case CY_NODE_GEOMETRY: /* only the tangent lives in svm_tex.cuh */
+      if (node.y != 2)
+        return -1;
+      stack_store_float3(stack, node.z, primitive_tangent(sd));
+      break;
+    case CY_NODE_TEX_COORD:
+      svm_node_tex_coord(sd, stack, node, &offset);
+      break;
+    case CY_NODE_MAPPING:
+      svm_node_mapping(stack, node);
+      break;
+    case CY_NODE_TEXTURE_MAPPING:
+      svm_node_texture_mapping(stack, node, &offset);
+      break;
+    case CY_NODE_MIN_MAX:
+      svm_node_min_max(stack, node, &offset);
+      break;
+    case CY_NODE_TEX_NOISE:
+      svm_node_tex_noise(stack, node, &offset);
+      break;
+    case CY_NODE_TEX_CHECKER:
+      svm_node_tex_checker(stack, node);
+      break;
+    case CY_NODE_TEX_GRADIENT:
+      svm_node_tex_gradient(stack, node);
+      break;
+    case CY_NODE_TEX_WAVE:
+      svm_node_tex_wave(stack, node, &offset);
+      break;
+    case CY_NODE_TEX_MAGIC:
+      svm_node_tex_magic(stack, node, &offset);
+      break;
+    case CY_NODE_TEX_BRICK:
+      svm_node_tex_brick(stack, node, &offset);
+      break;
+    default:
+      return -1;
+  }
+  return offset;
+}

@@ -82,6 +82,22 @@ def closure_cases():
     }
 
 
+def texture_cases():
+    """Texture coordinates, mesh attributes (generated, UV), mapping, the procedural
+    textures (noise 1D-4D, wave, magic, checker, brick, gradient) and the Principled
+    features built on them: anisotropy with the generated-coordinates tangent, sheen,
+    clearcoat, and a mix of two Principled BSDFs (16 closures per shader)."""
+    return {
+        "cornell_textured": scenes.cornell(W, H, materials="textured"),
+        "cornell_textured2": scenes.cornell(W, H, materials="textured2"),
+        # the same programs under a lamp-less mesh light (emissive-triangle MIS evaluates
+        # the surface shader with PATH_RAY_EMISSION) and through an orthographic camera
+        "cornell_textured_mesh_light": scenes.cornell(W, H, materials="textured", light="mesh"),
+        "cornell_textured_ortho": scenes.cornell(
+            W, H, materials="textured", cam_type="orthograph"),
+    }
+
+
 def light_cases():
     """Lamp types of kernel_light.h beyond the configs' point / sun / area: a spot with
     a smooth edge, and three lamps of different types in one light distribution."""

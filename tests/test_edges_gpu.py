@@ -79,6 +79,7 @@ def test_empty_work_leaves_the_film_alone(ref, device):
     ("KD_INT_BRANCHED", 1, "branched"),
     ("KD_BVH_HAVE_CURVES", 1, "curves"),
     ("KD_BG_USE_MIS", 1, "background importance"),
+    ("KD_INT_MAX_CLOSURES", 33, "closures per shader"),
 ])
 def test_out_of_scope_scenes_are_refused(ref, device, field, value, needle):
     """KernelData asking for a feature outside SURVEY.md 8 is refused with

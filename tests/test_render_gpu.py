@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from scene_cases import (camera_cases, closure_cases, light_cases, principled_cases,
-                         sampling_cases, small_cases)
+                         sampling_cases, small_cases, texture_cases)
 
 pytestmark = pytest.mark.gpu
 
@@ -109,6 +109,41 @@ def test_camera_models_match_reference(ref, device, name):
         image_gates(ref_img, got, SPP, name)
     finally:
         rs.close()
+
+
+@pytest.mark.parametrize("name", ["cornell_textured", "cornell_textured2",
+                                  "cornell_textured_mesh_light", "cornell_textured_ortho"])
+def test_texture_nodes_match_reference(ref, device, name):
+    desc = texture_cases()[name]
+    rs = ref.build_scene(desc)
+    try:
+        device.upload_scene(rs.device_arrays())
+        ref_img, _ = rs.render(0, SPP, tile_size=64)
+        got = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP)
+        assert ref_img[..., :3].max() > 0.0
+        image_gates(ref_img, got, SPP, name)
+    finally:
+        rs.close()
+
+
+def test_window_coordinates_need_a_perspective_camera(ref, device):
+    """NODE_TEXCO_WINDOW reads the ray origin under an orthographic camera and the
+    panorama projection under a panoramic one; both are refused, not approximated."""
+    from raytracingproject_b200.device import DeviceError
+    ortho = scenes_cornell_ortho_textured2()  # the "glass" shader reads window coords
+    rs = ref.build_scene(ortho)
+    try:
+        device.upload_scene(rs.device_arrays())
+        with pytest.raises(DeviceError) as e:
+            device.render(ortho.width, ortho.height, rs.pass_stride, 0, 1)
+        assert "window texture coordinates" in str(e.value)
+    finally:
+        rs.close()
+
+
+def scenes_cornell_ortho_textured2():
+    from raytracingproject_b200 import scenes
+    return scenes.cornell(64, 48, spp=1, materials="textured2", cam_type="orthograph")
 
 
 @pytest.mark.parametrize("name", ["cornell_cmj16", "cornell_cmj12"])

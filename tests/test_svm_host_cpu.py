@@ -1,0 +1,229 @@
+"""Node-by-node parity of the device-side SVM texture / attribute / mapping nodes
+(csrc/svm_tex.cuh) with the reference's svm_node_* functions, on the CPU.
+
+tests/host_check/svm_tex_host.cpp compiles THE SAME svm_tex.cuh the CUDA kernels include
+for the host (g++, CUDA built-ins mapped to their host meaning); oracle/ref_probe.cpp
+runs the reference's own function for the same opcode.  Both get identical node words,
+stacks and shading points; the stacks they leave must agree.  Two sources of programs:
+
+ - every texture-family node of the real compiled programs of the "textured" Cornell
+   scenes (real attribute maps, objects, camera);
+ - random encodings of each opcode (random stack slots / defaults / enum values).
+
+This checks decoding and arithmetic of the nodes before any GPU time is spent; the GPU
+render-parity tests (test_render_gpu.py, texture_cases) check them in the kernels."""
+import ctypes as C
+import os
+import re
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+from raytracingproject_b200 import scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CUDA_INC = "/usr/local/cuda/include"
+
+
+def abi():
+    text = open(os.path.join(ROOT, "include", "cycles_abi.h")).read()
+    return {k: int(v) for k, v in re.findall(r"#define CY_(NODE_\w+)[ \t]+(\d+)", text)}
+
+
+@pytest.fixture(scope="module")
+def host_lib(tmp_path_factory):
+    if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not found")
+    out = tmp_path_factory.mktemp("host_check") / "libsvm_tex_host.so"
+    src = os.path.join(ROOT, "tests", "host_check", "svm_tex_host.cpp")
+    subprocess.run(["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-w", "-ffp-contract=off",
+                    "-fvisibility=hidden", "-Wl,-Bsymbolic",  # g_scene must not interpose
+                    "-I" + CUDA_INC, src, "-o", str(out)], check=True)
+    L = C.CDLL(str(out))
+    L.host_svm_node.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    L.host_svm_node.restype = C.c_int
+    L.host_svm_bind.argtypes = [C.c_void_p]
+    return L
+
+
+class Bound:
+    """The scene arrays svm_tex.cuh reads, bound to the host build; keeps them alive."""
+    FIELDS = ["svm_nodes", "objects", "tri_vindex", "lights", "attributes_map",
+              "attributes_float", "attributes_float2", "attributes_float3",
+              "attributes_uchar4", "kernel_data"]
+
+    def __init__(self, L, arrays, nodes):
+        self.keep = {"svm_nodes": nodes}
+        for f in self.FIELDS[1:]:
+            name = "__data" if f == "kernel_data" else "__" + f
+            if name in arrays:
+                self.keep[f] = np.ascontiguousarray(arrays[name][0])
+        ptrs = (C.c_void_p * len(self.FIELDS))(
+            *[self.keep[f].ctypes.data if f in self.keep else None for f in self.FIELDS])
+        L.host_svm_bind(ptrs)
+
+
+def shading_points(arrays, n, rng):
+    from oracle.cycles_ref import SHADING_POINT_DTYPE
+    prim_object = arrays["__prim_object"][0].view(np.int32)
+    prim_index = arrays["__prim_index"][0].view(np.int32)
+    ok = np.nonzero((prim_object >= 0) & (prim_index >= 0))[0]
+    pts = np.zeros(n, SHADING_POINT_DTYPE)
+    pick = rng.choice(ok, n)
+    pts["object"], pts["prim"], pts["lamp"] = prim_object[pick], prim_index[pick], -1
+    for k in ("P", "dPdu"):
+        pts[k] = rng.uniform(-1.5, 1.5, (n, 3))
+    for k in ("N", "I"):
+        v = rng.normal(size=(n, 3))
+        pts[k] = v / np.linalg.norm(v, axis=1, keepdims=True)
+    u = rng.uniform(0, 1, n)
+    pts["u"], pts["v"] = u, rng.uniform(0, 1, n) * (1 - u)
+    # a few points that are not on a surface: background, and a lamp's emission shader
+    pts["object"][: n // 16] = -1
+    pts["prim"][: n // 16] = -1
+    pts["lamp"][: n // 32] = 0
+    return pts
+
+
+def run_both(L, rs, nodes, offset, stack0, pt):
+    s_ref, s_dev = stack0.copy(), stack0.copy()
+    n_ref = rs.svm_node(nodes, offset, s_ref, pt)
+    n_dev = L.host_svm_node(offset, s_dev.ctypes.data, pt.ctypes.data)
+    return n_ref, n_dev, s_ref, s_dev
+
+
+def texture_ops():
+    a = abi()
+    return {a[k]: k for k in ("NODE_ATTR", "NODE_TEX_COORD", "NODE_MAPPING",
+                              "NODE_TEXTURE_MAPPING", "NODE_MIN_MAX", "NODE_TEX_NOISE",
+                              "NODE_TEX_CHECKER", "NODE_TEX_GRADIENT", "NODE_TEX_WAVE",
+                              "NODE_TEX_MAGIC", "NODE_TEX_BRICK", "NODE_GEOMETRY")}
+
+
+def compare(name, s_ref, s_dev, tol):
+    bad = ~np.isclose(s_ref, s_dev, rtol=tol, atol=tol, equal_nan=True)
+    assert not bad.any(), (name, np.nonzero(bad)[0][:8], s_ref[bad][:8], s_dev[bad][:8])
+
+
+@pytest.mark.parametrize("materials", ["textured", "textured2"])
+def test_compiled_texture_nodes_match_reference(ref, host_lib, materials):
+    desc = scenes.cornell(64, 48, spp=1, materials=materials)
+    rs = ref.build_scene(desc)
+    try:
+        arrays = rs.device_arrays()
+        nodes = np.zeros((arrays["__svm_nodes"][0].size // 16 + 8, 4), np.uint32)
+        real = arrays["__svm_nodes"][0].view(np.uint32).reshape(-1, 4)
+        nodes[: len(real)] = real
+        bound = Bound(host_lib, arrays, nodes)
+        ops = texture_ops()
+        a = abi()
+        rng = np.random.default_rng(7)
+        pts = shading_points(arrays, 64, rng)
+        seen = {}
+        for off in range(len(real)):
+            op = int(nodes[off, 0])
+            if op not in ops:
+                continue
+            if op == a["NODE_GEOMETRY"] and nodes[off, 1] != 2:  # only the tangent
+                continue
+            if op == a["NODE_TEX_COORD"] and nodes[off, 1] > 4:  # dupli / volume: refused
+                continue
+            if op == a["NODE_TEX_NOISE"] and not 1 <= nodes[off, 1] <= 4:  # a data word
+                continue
+            for i in range(len(pts)):
+                stack0 = rng.uniform(-2.0, 2.0, 264).astype(np.float32)
+                n_ref, n_dev, s_ref, s_dev = run_both(host_lib, rs, nodes, off, stack0,
+                                                      pts[i:i + 1])
+                assert n_ref == n_dev, (ops[op], off)
+                compare((ops[op], off, i), s_ref, s_dev, 3e-5)
+                if not np.array_equal(s_ref, stack0):
+                    seen[ops[op]] = seen.get(ops[op], 0) + 1
+        # every node family the scenes were written to contain did run and wrote output
+        want = {"NODE_ATTR", "NODE_TEX_NOISE", "NODE_TEX_CHECKER", "NODE_TEX_WAVE",
+                "NODE_TEX_MAGIC", "NODE_MAPPING", "NODE_TEX_GRADIENT", "NODE_TEXTURE_MAPPING"}
+        want |= {"NODE_TEX_BRICK", "NODE_GEOMETRY"} if materials == "textured" else \
+            {"NODE_TEX_COORD", "NODE_MIN_MAX"}
+        assert want <= set(seen), sorted(want - set(seen))
+        del bound
+    finally:
+        rs.close()
+
+
+def random_program(op_name, rng, a):
+    """One random encoding of `op_name` followed by its data words."""
+    slot = lambda: int(rng.choice([255, int(rng.integers(0, 60)) * 4]))  # invalid -> default
+    used = lambda: int(rng.integers(0, 60)) * 4
+    pack = lambda *b: int(sum(int(x) << (8 * i) for i, x in enumerate(b)))
+    fbits = lambda lo, hi: int(np.float32(rng.uniform(lo, hi)).view(np.uint32))
+    prog = np.zeros((8, 4), np.uint32)
+    prog[0, 0] = a[op_name]
+    if op_name == "NODE_MAPPING":
+        prog[0, 1:] = [rng.integers(0, 4), pack(used(), used(), used(), used()), used()]
+    elif op_name == "NODE_TEXTURE_MAPPING":
+        prog[0, 1:3] = [used(), used()]
+        prog[1:4] = rng.uniform(-2, 2, (3, 4)).astype(np.float32).view(np.uint32)
+    elif op_name == "NODE_MIN_MAX":
+        prog[0, 1:3] = [used(), used()]
+        prog[1] = rng.uniform(-2, 0, 4).astype(np.float32).view(np.uint32)
+        prog[2] = rng.uniform(0, 2, 4).astype(np.float32).view(np.uint32)
+    elif op_name == "NODE_TEX_NOISE":
+        prog[0, 1:] = [rng.integers(1, 5), pack(used(), slot(), slot(), slot()),
+                       pack(slot(), slot(), slot(), slot())]
+        prog[1] = [fbits(-2, 2), fbits(0.5, 4), fbits(0, 5), fbits(0, 1)]
+        prog[2, 0] = fbits(0, 1.5) if rng.random() < 0.7 else 0
+    elif op_name == "NODE_TEX_CHECKER":
+        prog[0, 1:] = [pack(used(), used(), used(), slot()), pack(slot(), slot()), fbits(0.5, 6)]
+    elif op_name == "NODE_TEX_GRADIENT":
+        prog[0, 1] = pack(rng.integers(0, 7), used(), slot(), slot())
+    elif op_name == "NODE_TEX_WAVE":
+        prog[0, 1:] = [pack(rng.integers(0, 2), rng.integers(0, 4), rng.integers(0, 4),
+                            rng.integers(0, 3)),
+                       pack(used(), slot(), slot()), pack(slot(), slot(), slot(), slot())]
+        prog[1] = [pack(slot(), slot()), fbits(0.2, 3), fbits(0, 2) if rng.random() < 0.7 else 0,
+                   fbits(0, 4)]
+        prog[2, :3] = [fbits(0.5, 2), fbits(0, 1), fbits(-3, 3)]
+    elif op_name == "NODE_TEX_MAGIC":
+        prog[0, 1:3] = [pack(rng.integers(0, 11), slot(), slot()), pack(used(), slot(), slot())]
+        prog[1, :2] = [fbits(0.5, 5), fbits(0, 2) if rng.random() < 0.8 else 0]
+    elif op_name == "NODE_TEX_BRICK":
+        prog[0, 1:] = [pack(used(), used(), used(), used()), pack(slot(), slot(), slot(), slot()),
+                       pack(slot(), slot(), slot(), slot())]
+        prog[1] = [pack(rng.integers(0, 4), rng.integers(0, 4)), fbits(1, 6), fbits(0, 0.1),
+                   fbits(-0.5, 0.5)]
+        prog[2] = [fbits(0.2, 1), fbits(0.1, 0.5), fbits(0, 1), fbits(0.5, 1.5)]
+        prog[3, 0] = fbits(0, 1) if rng.random() < 0.6 else 0
+    elif op_name == "NODE_TEX_COORD":
+        kind = int(rng.choice([0, 1, 1, 2, 3, 4]))
+        prog[0, 1:] = [kind, used(), int(kind == 1 and rng.random() < 0.5)]
+        prog[1:4] = rng.uniform(-2, 2, (3, 4)).astype(np.float32).view(np.uint32)
+    return prog
+
+
+@pytest.mark.parametrize("op_name", ["NODE_MAPPING", "NODE_TEXTURE_MAPPING", "NODE_MIN_MAX",
+                                     "NODE_TEX_NOISE", "NODE_TEX_CHECKER", "NODE_TEX_GRADIENT",
+                                     "NODE_TEX_WAVE", "NODE_TEX_MAGIC", "NODE_TEX_BRICK",
+                                     "NODE_TEX_COORD"])
+def test_random_node_encodings_match_reference(ref, host_lib, op_name):
+    desc = scenes.cornell(64, 48, spp=1, materials="textured2")
+    rs = ref.build_scene(desc)
+    try:
+        arrays = rs.device_arrays()
+        a = abi()
+        rng = np.random.default_rng(zlib.crc32(op_name.encode()))
+        pts = shading_points(arrays, 64, rng)
+        wrote = 0
+        for trial in range(300):
+            prog = random_program(op_name, rng, a)
+            bound = Bound(host_lib, arrays, prog)
+            stack0 = rng.uniform(-2.0, 2.0, 264).astype(np.float32)
+            pt = pts[trial % len(pts):trial % len(pts) + 1]
+            n_ref, n_dev, s_ref, s_dev = run_both(host_lib, rs, prog, 0, stack0, pt)
+            assert n_ref == n_dev and n_ref > 0, (op_name, trial, n_ref, n_dev)
+            compare((op_name, trial, prog[:4].tolist()), s_ref, s_dev, 3e-5)
+            wrote += int(not np.array_equal(s_ref, stack0))
+            del bound
+        assert wrote > 150
+    finally:
+        rs.close()
