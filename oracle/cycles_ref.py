@@ -90,7 +90,8 @@ def global_names():
 
 SHADING_POINT_DTYPE = np.dtype([("P", "<f4", 3), ("N", "<f4", 3), ("I", "<f4", 3),
                                 ("dPdu", "<f4", 3), ("u", "<f4"), ("v", "<f4"),
-                                ("object", "<i4"), ("prim", "<i4"), ("lamp", "<i4")])
+                                ("object", "<i4"), ("prim", "<i4"), ("lamp", "<i4"),
+                                ("shader", "<i4"), ("backfacing", "<i4")])
 
 
 class RefScene:

@@ -368,6 +368,8 @@ int ref_probe_svm_node(KernelGlobals *kg, const void *nodes, int offset, float *
   sd->object = p->object;
   sd->prim = p->prim;
   sd->lamp = p->lamp;
+  sd->shader = p->shader;
+  sd->flag = p->backfacing ? SD_BACKFACING : 0;
   sd->type = (p->prim != PRIM_NONE) ? PRIMITIVE_TRIANGLE :
                                       ((p->lamp != LAMP_NONE) ? PRIMITIVE_LAMP : PRIMITIVE_NONE);
   if (sd->object != OBJECT_NONE) {
@@ -416,6 +418,73 @@ int ref_probe_svm_node(KernelGlobals *kg, const void *nodes, int offset, float *
       break;
     case NODE_TEX_BRICK:
       svm_node_tex_brick(kg, sd, stack, node, &offset);
+      break;
+    case NODE_TEX_WHITE_NOISE:
+      svm_node_tex_white_noise(kg, sd, stack, node.y, node.z, node.w, &offset);
+      break;
+    case NODE_OBJECT_INFO:
+      svm_node_object_info(kg, sd, stack, node.y, node.z);
+      break;
+    case NODE_CAMERA:
+      svm_node_camera(kg, sd, stack, node.y, node.z, node.w);
+      break;
+    case NODE_VECTOR_TRANSFORM:
+      svm_node_vector_transform(kg, sd, stack, node);
+      break;
+    case NODE_VECTOR_ROTATE:
+      svm_node_vector_rotate(sd, stack, node.y, node.z, node.w);
+      break;
+    case NODE_NORMAL:
+      svm_node_normal(kg, sd, stack, node.y, node.z, node.w, &offset);
+      break;
+    case NODE_MAP_RANGE:
+      svm_node_map_range(kg, sd, stack, node.y, node.z, node.w, &offset);
+      break;
+    case NODE_HSV:
+      svm_node_hsv(kg, sd, stack, node, &offset);
+      break;
+    case NODE_SEPARATE_HSV:
+      svm_node_separate_hsv(kg, sd, stack, node.y, node.z, node.w, &offset);
+      break;
+    case NODE_COMBINE_HSV:
+      svm_node_combine_hsv(kg, sd, stack, node.y, node.z, node.w, &offset);
+      break;
+    case NODE_CONVERT:
+      svm_node_convert(kg, sd, stack, node.y, node.z, node.w);
+      break;
+    case NODE_FRESNEL:
+      svm_node_fresnel(sd, stack, node.y, node.z, node.w);
+      break;
+    case NODE_LAYER_WEIGHT:
+      svm_node_layer_weight(sd, stack, node);
+      break;
+    case NODE_MATH:
+      svm_node_math(kg, sd, stack, node.y, node.z, node.w, &offset);
+      break;
+    case NODE_VECTOR_MATH:
+      svm_node_vector_math(kg, sd, stack, node.y, node.z, node.w, &offset);
+      break;
+    case NODE_RGB_RAMP:
+      svm_node_rgb_ramp(kg, sd, stack, node, &offset);
+      break;
+    case NODE_RGB_CURVES:
+    case NODE_VECTOR_CURVES:
+      svm_node_curves(kg, sd, stack, node, &offset);
+      break;
+    case NODE_GAMMA:
+      svm_node_gamma(sd, stack, node.y, node.z, node.w);
+      break;
+    case NODE_BRIGHTCONTRAST:
+      svm_node_brightness(sd, stack, node.y, node.z, node.w);
+      break;
+    case NODE_INVERT:
+      svm_node_invert(sd, stack, node.y, node.z, node.w);
+      break;
+    case NODE_MIX:
+      svm_node_mix(kg, sd, stack, node.y, node.z, node.w, &offset);
+      break;
+    case NODE_CLAMP:
+      svm_node_clamp(kg, sd, stack, node.y, node.z, node.w, &offset);
       break;
     default:
       offset = -1;

@@ -27,7 +27,7 @@ struct RefProbeHit {
 struct RefShadingPoint {
   float P[3], N[3], I[3], dPdu[3];
   float u, v;
-  int32_t object, prim, lamp;
+  int32_t object, prim, lamp, shader, backfacing;
 };
 
 namespace ccl {

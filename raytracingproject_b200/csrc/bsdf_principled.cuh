@@ -4,20 +4,6 @@
 #ifndef B200_BSDF_PRINCIPLED_CUH
 #define B200_BSDF_PRINCIPLED_CUH
 
-/* bsdf_util.h:104-117 */
-CY_DEV float fresnel_dielectric_cos(float cosi, float eta)
-{
-  float c = fabsf(cosi);
-  float g = eta * eta - 1 + c * c;
-  if (g > 0) {
-    g = sqrtf(g);
-    float A = (g - c) / (g + c);
-    float B = (c * (g + c) - 1) / (c * (g - c) + 1);
-    return 0.5f * A * A * (1 + B * B);
-  }
-  return 1.0f;
-}
-
 /* bsdf_util.h:38-102, without differentials */
 CY_DEV float fresnel_dielectric(float eta, f3 N, f3 I, f3 *R, f3 *T, bool *is_inside)
 {

@@ -33,12 +33,6 @@ struct PathStateG {
   float min_ray_pdf, ray_pdf, ray_t;
 };
 
-/* the bounce counters the Light Path node reads, passed BY VALUE into the (out-of-line)
- * SVM interpreter: handing it a pointer to the PathStateG would force the whole state of
- * k_shade_surface out of registers */
-struct PathDepths {
-  short bounce, diffuse, glossy, transparent, transmission;
-};
 CY_DEV PathDepths path_depths(const PathStateG &s)
 {
   PathDepths d;
@@ -752,6 +746,36 @@ __device__ __noinline__ void svm_eval_nodes(ShaderDataG &sd, PathDepths depths,
       case CY_NODE_RGB_CURVES:
       case CY_NODE_VECTOR_CURVES:
         svm_node_curves(stack, node, &offset);
+        break;
+      case CY_NODE_HSV:
+        svm_node_hsv(stack, node);
+        break;
+      case CY_NODE_SEPARATE_HSV:
+        svm_node_separate_hsv(stack, node, &offset);
+        break;
+      case CY_NODE_COMBINE_HSV:
+        svm_node_combine_hsv(stack, node, &offset);
+        break;
+      case CY_NODE_MAP_RANGE:
+        svm_node_map_range(stack, node, &offset);
+        break;
+      case CY_NODE_NORMAL:
+        svm_node_normal(stack, node, &offset);
+        break;
+      case CY_NODE_VECTOR_ROTATE:
+        svm_node_vector_rotate(stack, node);
+        break;
+      case CY_NODE_VECTOR_TRANSFORM:
+        svm_node_vector_transform(sd, stack, node);
+        break;
+      case CY_NODE_OBJECT_INFO:
+        svm_node_object_info(sd, stack, node);
+        break;
+      case CY_NODE_CAMERA:
+        svm_node_camera(sd, stack, node);
+        break;
+      case CY_NODE_TEX_WHITE_NOISE:
+        svm_node_tex_white_noise(stack, node);
         break;
       case CY_NODE_ATTR:
         svm_node_attr(sd, stack, node);

@@ -71,6 +71,26 @@ CY_DEV f3 object_dir_transform(int object, f3 D)
   return transform_direction(tfm, D);
 }
 
+/* bsdf_util.h:104-117 */
+CY_DEV float fresnel_dielectric_cos(float cosi, float eta)
+{
+  float c = fabsf(cosi);
+  float g = eta * eta - 1 + c * c;
+  if (g > 0) {
+    g = sqrtf(g);
+    float A = (g - c) / (g + c);
+    float B = (c * (g + c) - 1) / (c * (g - c) + 1);
+    return 0.5f * A * A * (1 + B * B);
+  }
+  return 1.0f;
+}
+
+/* the bounce counters the Light Path node reads, passed BY VALUE into the (out-of-line)
+ * SVM interpreter: handing it a pointer to the PathStateG would force the whole state of
+ * k_shade_surface out of registers */
+struct PathDepths {
+  short bounce, diffuse, glossy, transparent, transmission;
+};
 /* ------------------------------------------------------------ SVM stack */
 
 CY_DEV f3 stack_load_float3(const float *stack, uint32_t a)

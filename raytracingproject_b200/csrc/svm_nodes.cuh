@@ -294,6 +294,79 @@ CY_DEV float mix_overlay_1(float c1, float c2, float t, float tm)
   return 1.0f - (tm + 2.0f * t * (1.0f - c2)) * (1.0f - c1);
 }
 
+/* ---- HSV (util/util_color.h:85-166) ---- */
+
+CY_DEV f3 rgb_to_hsv(f3 rgb)
+{
+  const float cmax = fmaxf(rgb.x, fmaxf(rgb.y, rgb.z));
+  const float cmin = fminf(rgb.x, fminf(rgb.y, rgb.z));
+  const float cdelta = cmax - cmin;
+  float h = 0.0f;
+  const float s = (cmax != 0.0f) ? cdelta / cmax : 0.0f;
+  if (s != 0.0f) {
+    const f3 c = (mk3(cmax, cmax, cmax) - rgb) / cdelta;
+    if (rgb.x == cmax)
+      h = c.z - c.y;
+    else if (rgb.y == cmax)
+      h = 2.0f + c.x - c.z;
+    else
+      h = 4.0f + c.y - c.x;
+    h /= 6.0f;
+    if (h < 0.0f)
+      h += 1.0f;
+  }
+  return mk3(h, s, cmax);
+}
+
+CY_DEV f3 hsv_to_rgb(f3 hsv)
+{
+  float h = hsv.x;
+  const float s = hsv.y, v = hsv.z;
+  if (s == 0.0f)
+    return mk3(v, v, v);
+  if (h == 1.0f)
+    h = 0.0f;
+  h *= 6.0f;
+  const float i = floorf(h);
+  const float f = h - i;
+  const float p = v * (1.0f - s);
+  const float q = v * (1.0f - (s * f));
+  const float t = v * (1.0f - (s * (1.0f - f)));
+  if (i == 0.0f)
+    return mk3(v, t, p);
+  if (i == 1.0f)
+    return mk3(q, v, p);
+  if (i == 2.0f)
+    return mk3(p, v, t);
+  if (i == 3.0f)
+    return mk3(p, q, v);
+  if (i == 4.0f)
+    return mk3(t, p, v);
+  return mk3(v, p, q);
+}
+
+/* one channel of svm_mix_dodge / svm_mix_burn (svm_color_util.h:103-175) */
+CY_DEV float mix_dodge_1(float c1, float c2, float t)
+{
+  if (c1 == 0.0f)
+    return c1;
+  float tmp = 1.0f - t * c2;
+  if (tmp <= 0.0f)
+    return 1.0f;
+  tmp = c1 / tmp;
+  return (tmp > 1.0f) ? 1.0f : tmp;
+}
+CY_DEV float mix_burn_1(float c1, float c2, float t, float tm)
+{
+  float tmp = tm + t * c2;
+  if (tmp <= 0.0f)
+    return 0.0f;
+  tmp = 1.0f - (1.0f - c1) / tmp;
+  if (tmp < 0.0f)
+    return 0.0f;
+  return (tmp > 1.0f) ? 1.0f : tmp;
+}
+
 SVM_NODES_FN f3 svm_mix(uint32_t type, float fac, f3 c1, f3 c2)
 {
   const float t = saturate(fac);
@@ -329,6 +402,38 @@ SVM_NODES_FN f3 svm_mix(uint32_t type, float fac, f3 c1, f3 c2)
       return nodes_interp(c1, mk3(fminf(c1.x, c2.x), fminf(c1.y, c2.y), fminf(c1.z, c2.z)), t);
     case CY_NODE_MIX_LIGHT:
       return nodes_interp(c1, mk3(fmaxf(c1.x, c2.x), fmaxf(c1.y, c2.y), fmaxf(c1.z, c2.z)), t);
+    case CY_NODE_MIX_DODGE:
+      return mk3(mix_dodge_1(c1.x, c2.x, t), mix_dodge_1(c1.y, c2.y, t),
+                 mix_dodge_1(c1.z, c2.z, t));
+    case CY_NODE_MIX_BURN:
+      return mk3(mix_burn_1(c1.x, c2.x, t, tm), mix_burn_1(c1.y, c2.y, t, tm),
+                 mix_burn_1(c1.z, c2.z, t, tm));
+    case CY_NODE_MIX_HUE:
+    case CY_NODE_MIX_COLOR: {
+      /* svm_mix_hue / svm_mix_color: take hue (and saturation) of the second colour */
+      const f3 hsv2 = rgb_to_hsv(c2);
+      if (hsv2.y == 0.0f)
+        return c1;
+      f3 hsv = rgb_to_hsv(c1);
+      hsv.x = hsv2.x;
+      if (type == CY_NODE_MIX_COLOR)
+        hsv.y = hsv2.y;
+      return nodes_interp(c1, hsv_to_rgb(hsv), t);
+    }
+    case CY_NODE_MIX_SAT: {
+      f3 hsv = rgb_to_hsv(c1);
+      if (hsv.y == 0.0f)
+        return c1;
+      const f3 hsv2 = rgb_to_hsv(c2);
+      hsv.y = tm * hsv.y + t * hsv2.y;
+      return hsv_to_rgb(hsv);
+    }
+    case CY_NODE_MIX_VAL: {
+      f3 hsv = rgb_to_hsv(c1);
+      const f3 hsv2 = rgb_to_hsv(c2);
+      hsv.z = tm * hsv.z + t * hsv2.z;
+      return hsv_to_rgb(hsv);
+    }
     case CY_NODE_MIX_SOFT: {
       const f3 scr = one - (one - c2) * (one - c1);
       return tm * c1 + t * ((one - c1) * c2 * c1 + c1 * scr);
@@ -669,6 +774,186 @@ CY_DEV void svm_node_curves(float *stack, uint4 node, int *offset)
   color = (1.0f - fac) * color + fac * mk3(r, g, b);
   stack_store_float3(stack, out_offset, color);
   *offset += table_size;
+}
+
+/* ---- HSV, map range, normal, vector rotate (svm_hsv.h, svm_sepcomb_hsv.h,
+ * svm_map_range.h, svm_normal.h, svm_vector_rotate.h) ---- */
+
+__device__ __noinline__ void svm_node_hsv(float *stack, uint4 node)
+{
+  uint32_t in_color_offset, fac_offset, out_color_offset, hue_offset, sat_offset, val_offset;
+  unpack_uchar3(node.y, &in_color_offset, &fac_offset, &out_color_offset);
+  unpack_uchar3(node.z, &hue_offset, &sat_offset, &val_offset);
+  const float fac = stack[fac_offset];
+  const f3 in_color = stack_load_float3(stack, in_color_offset);
+  f3 color = rgb_to_hsv(in_color);
+  color.x = fmodf(color.x + stack[hue_offset] + 0.5f, 1.0f);
+  color.y = saturate(color.y * stack[sat_offset]);
+  color.z *= stack[val_offset];
+  color = hsv_to_rgb(color);
+  color.x = fmaxf(fac * color.x + (1.0f - fac) * in_color.x, 0.0f);
+  color.y = fmaxf(fac * color.y + (1.0f - fac) * in_color.y, 0.0f);
+  color.z = fmaxf(fac * color.z + (1.0f - fac) * in_color.z, 0.0f);
+  if (stack_valid(out_color_offset))
+    stack_store_float3(stack, out_color_offset, color);
+}
+
+__device__ __noinline__ void svm_node_combine_hsv(float *stack, uint4 node, int *offset)
+{
+  const uint32_t color_out = __ldg(&g_scene.svm_nodes[*offset]).y;
+  (*offset)++;
+  const f3 color = hsv_to_rgb(mk3(stack[node.y], stack[node.z], stack[node.w]));
+  if (stack_valid(color_out))
+    stack_store_float3(stack, color_out, color);
+}
+
+__device__ __noinline__ void svm_node_separate_hsv(float *stack, uint4 node, int *offset)
+{
+  const uint32_t value_out = __ldg(&g_scene.svm_nodes[*offset]).y;
+  (*offset)++;
+  const f3 hsv = rgb_to_hsv(stack_load_float3(stack, node.y));
+  if (stack_valid(node.z))
+    stack[node.z] = hsv.x;
+  if (stack_valid(node.w))
+    stack[node.w] = hsv.y;
+  if (stack_valid(value_out))
+    stack[value_out] = hsv.z;
+}
+
+CY_DEV float nodes_smoothstep(float edge0, float edge1, float x)
+{
+  if (x < edge0)
+    return 0.0f;
+  if (x >= edge1)
+    return 1.0f;
+  const float t = (x - edge0) / (edge1 - edge0);
+  return (3.0f - 2.0f * t) * (t * t);
+}
+CY_DEV float nodes_smootherstep(float edge0, float edge1, float x)
+{
+  x = clampf(nodes_safe_divide(x - edge0, edge1 - edge0), 0.0f, 1.0f);
+  return x * x * x * (x * (x * 6.0f - 15.0f) + 10.0f);
+}
+
+__device__ __noinline__ void svm_node_map_range(float *stack, uint4 node, int *offset)
+{
+  const uint32_t from_min_offset = node.z & 0xff, from_max_offset = (node.z >> 8) & 0xff,
+                 to_min_offset = (node.z >> 16) & 0xff, to_max_offset = (node.z >> 24) & 0xff;
+  uint32_t type, steps_offset, result_offset;
+  unpack_uchar3(node.w, &type, &steps_offset, &result_offset);
+  const uint4 defaults = __ldg(&g_scene.svm_nodes[*offset]);
+  const uint4 defaults2 = __ldg(&g_scene.svm_nodes[*offset + 1]);
+  *offset += 2;
+  const float value = stack[node.y];
+  const float from_min = stack_load_float_default(stack, from_min_offset, defaults.x);
+  const float from_max = stack_load_float_default(stack, from_max_offset, defaults.y);
+  const float to_min = stack_load_float_default(stack, to_min_offset, defaults.z);
+  const float to_max = stack_load_float_default(stack, to_max_offset, defaults.w);
+  const float steps = stack_load_float_default(stack, steps_offset, defaults2.x);
+  float result = 0.0f;
+  if (from_max != from_min) {
+    float factor = value;
+    switch (type) {
+      default:
+      case CY_NODE_MAP_RANGE_LINEAR:
+        factor = (value - from_min) / (from_max - from_min);
+        break;
+      case CY_NODE_MAP_RANGE_STEPPED:
+        factor = (value - from_min) / (from_max - from_min);
+        factor = (steps > 0.0f) ? floorf(factor * (steps + 1.0f)) / steps : 0.0f;
+        break;
+      case CY_NODE_MAP_RANGE_SMOOTHSTEP:
+        factor = (from_min > from_max) ? 1.0f - nodes_smoothstep(from_max, from_min, factor) :
+                                         nodes_smoothstep(from_min, from_max, factor);
+        break;
+      case CY_NODE_MAP_RANGE_SMOOTHERSTEP:
+        factor = (from_min > from_max) ? 1.0f - nodes_smootherstep(from_max, from_min, factor) :
+                                         nodes_smootherstep(from_min, from_max, factor);
+        break;
+    }
+    result = to_min + factor * (to_max - to_min);
+  }
+  stack[result_offset] = result;
+}
+
+__device__ __noinline__ void svm_node_normal(float *stack, uint4 node, int *offset)
+{
+  const uint4 node1 = __ldg(&g_scene.svm_nodes[*offset]);
+  (*offset)++;
+  const f3 normal = stack_load_float3(stack, node.y);
+  const f3 direction = normalize(mk3(__uint_as_float(node1.x), __uint_as_float(node1.y),
+                                     __uint_as_float(node1.z)));
+  if (stack_valid(node.z))
+    stack_store_float3(stack, node.z, direction);
+  if (stack_valid(node.w))
+    stack[node.w] = dot(direction, normalize(normal));
+}
+
+/* util_math.h:563-582 */
+CY_DEV f3 nodes_rotate_around_axis(f3 p, f3 axis, float angle)
+{
+  const float c = cosf(angle), s = sinf(angle), ic = 1 - c;
+  f3 r;
+  r.x = ((c + ic * axis.x * axis.x) * p.x) + ((ic * axis.x * axis.y - axis.z * s) * p.y) +
+        ((ic * axis.x * axis.z + axis.y * s) * p.z);
+  r.y = ((ic * axis.x * axis.y + axis.z * s) * p.x) + ((c + ic * axis.y * axis.y) * p.y) +
+        ((ic * axis.y * axis.z - axis.x * s) * p.z);
+  r.z = ((ic * axis.x * axis.z - axis.y * s) * p.x) + ((ic * axis.y * axis.z + axis.x * s) * p.y) +
+        ((c + ic * axis.z * axis.z) * p.z);
+  return r;
+}
+
+CY_DEV tfm34 nodes_euler_to_transform(f3 e)
+{
+  const float cx = cosf(e.x), cy = cosf(e.y), cz = cosf(e.z);
+  const float sx = sinf(e.x), sy = sinf(e.y), sz = sinf(e.z);
+  tfm34 t;
+  t.x = make_float4(cy * cz, sy * sx * cz - cx * sz, sy * cx * cz + sx * sz, 0.0f);
+  t.y = make_float4(cy * sz, sy * sx * sz + cx * cz, sy * cx * sz - sx * cz, 0.0f);
+  t.z = make_float4(-sy, cy * sx, cy * cx, 0.0f);
+  return t;
+}
+
+__device__ __noinline__ void svm_node_vector_rotate(float *stack, uint4 node)
+{
+  const uint32_t type = node.y & 0xff, vector_offset = (node.y >> 8) & 0xff,
+                 rotation_offset = (node.y >> 16) & 0xff, invert = (node.y >> 24) & 0xff;
+  uint32_t center_offset, axis_offset, angle_offset;
+  unpack_uchar3(node.z, &center_offset, &axis_offset, &angle_offset);
+  if (!stack_valid(node.w))
+    return;
+  const f3 vector = stack_load_float3(stack, vector_offset);
+  const f3 center = stack_load_float3(stack, center_offset);
+  f3 result;
+  if (type == CY_NODE_VECTOR_ROTATE_TYPE_EULER_XYZ) {
+    const tfm34 rot = nodes_euler_to_transform(stack_load_float3(stack, rotation_offset));
+    result = (invert ? transform_direction_transposed(rot, vector - center) :
+                       transform_direction(rot, vector - center)) +
+             center;
+  }
+  else {
+    f3 axis;
+    switch (type) {
+      case CY_NODE_VECTOR_ROTATE_TYPE_AXIS_X:
+        axis = mk3(1.0f, 0.0f, 0.0f);
+        break;
+      case CY_NODE_VECTOR_ROTATE_TYPE_AXIS_Y:
+        axis = mk3(0.0f, 1.0f, 0.0f);
+        break;
+      case CY_NODE_VECTOR_ROTATE_TYPE_AXIS_Z:
+        axis = mk3(0.0f, 0.0f, 1.0f);
+        break;
+      default:
+        axis = normalize(stack_load_float3(stack, axis_offset));
+        break;
+    }
+    float angle = stack[angle_offset];
+    angle = invert ? -angle : angle;
+    result = (len_squared(axis) != 0.0f) ?
+                 nodes_rotate_around_axis(vector - center, axis, angle) + center :
+                 vector;
+  }
+  stack_store_float3(stack, node.w, result);
 }
 
 #endif /* B200_SVM_NODES_CUH */

@@ -19,6 +19,12 @@
 #ifndef B200_SVM_TEX_CUH
 #define B200_SVM_TEX_CUH
 
+/* node entry points stay out of line: they are rare next to the closure nodes and
+ * inlining them into the interpreter's switch costs it registers */
+#ifndef SVM_TEX_FN
+#  define SVM_TEX_FN __device__ __noinline__
+#endif
+
 /* ------------------------------------------------------------ attributes */
 
 struct AttrDesc {
@@ -161,7 +167,7 @@ CY_DEV f3 attribute_rgba_rgb(const ShaderDataG &sd, const AttrDesc &d)
   return sd.u * mk3(f0) + sd.v * mk3(f1) + (1.0f - sd.u - sd.v) * mk3(f2);
 }
 
-CY_DEV void svm_node_attr(const ShaderDataG &sd, float *stack, uint4 node)
+SVM_TEX_FN void svm_node_attr(const ShaderDataG &sd, float *stack, uint4 node)
 {
   const uint32_t out = node.z, want = node.w;
   AttrDesc d = find_attribute(sd, node.y);
@@ -237,7 +243,7 @@ CY_DEV f3 camera_position()
   return mk3(c2w.x.w, c2w.y.w, c2w.z.w);
 }
 
-CY_DEV void svm_node_tex_coord(const ShaderDataG &sd, float *stack, uint4 node, int *offset)
+SVM_TEX_FN void svm_node_tex_coord(const ShaderDataG &sd, float *stack, uint4 node, int *offset)
 {
   f3 data = zero3();
   switch (node.y) {
@@ -313,7 +319,7 @@ CY_DEV f3 tex_safe_divide3(f3 a, f3 b)
              (b.z != 0.0f) ? a.z / b.z : 0.0f);
 }
 
-CY_DEV void svm_node_mapping(float *stack, uint4 node)
+SVM_TEX_FN void svm_node_mapping(float *stack, uint4 node)
 {
   const f3 vector = stack_load_float3(stack, node.z & 0xff);
   const f3 location = stack_load_float3(stack, (node.z >> 8) & 0xff);
@@ -340,13 +346,13 @@ CY_DEV void svm_node_mapping(float *stack, uint4 node)
   stack_store_float3(stack, node.w, r);
 }
 
-CY_DEV void svm_node_texture_mapping(float *stack, uint4 node, int *offset)
+SVM_TEX_FN void svm_node_texture_mapping(float *stack, uint4 node, int *offset)
 {
   const f3 v = stack_load_float3(stack, node.y);
   stack_store_float3(stack, node.z, transform_point(node_transform(offset), v));
 }
 
-CY_DEV void svm_node_min_max(float *stack, uint4 node, int *offset)
+SVM_TEX_FN void svm_node_min_max(float *stack, uint4 node, int *offset)
 {
   const f3 v = stack_load_float3(stack, node.y);
   const f3 mn = mk3(__ldg((const float4 *)&g_scene.svm_nodes[*offset]));
@@ -542,7 +548,7 @@ CY_DEV float noise_seed_offset(float seed, int component, int dims)
   return 100.0f + hash_to_unit_float(hash_uint_n(key, dims == 1 ? 1 : 2)) * 100.0f;
 }
 
-CY_DEV void svm_node_tex_noise(float *stack, uint4 node, int *offset)
+SVM_TEX_FN void svm_node_tex_noise(float *stack, uint4 node, int *offset)
 {
   const int dims = (int)node.y;
   const uint32_t vector_off = node.z & 0xff, w_off = (node.z >> 8) & 0xff,
@@ -602,7 +608,7 @@ CY_DEV void svm_node_tex_noise(float *stack, uint4 node, int *offset)
 
 /* ------------------------------------------------ checker, gradient, wave */
 
-CY_DEV void svm_node_tex_checker(float *stack, uint4 node)
+SVM_TEX_FN void svm_node_tex_checker(float *stack, uint4 node)
 {
   const uint32_t co_off = node.y & 0xff, color1_off = (node.y >> 8) & 0xff,
                  color2_off = (node.y >> 16) & 0xff, scale_off = (node.y >> 24) & 0xff;
@@ -622,7 +628,7 @@ CY_DEV void svm_node_tex_checker(float *stack, uint4 node)
     stack[fac_off] = on ? 1.0f : 0.0f;
 }
 
-CY_DEV void svm_node_tex_gradient(float *stack, uint4 node)
+SVM_TEX_FN void svm_node_tex_gradient(float *stack, uint4 node)
 {
   const uint32_t type = node.y & 0xff, co_off = (node.y >> 8) & 0xff,
                  fac_off = (node.y >> 16) & 0xff, color_off = (node.y >> 24) & 0xff;
@@ -666,7 +672,7 @@ CY_DEV void svm_node_tex_gradient(float *stack, uint4 node)
     stack_store_float3(stack, color_off, mk3(f, f, f));
 }
 
-CY_DEV void svm_node_tex_wave(float *stack, uint4 node, int *offset)
+SVM_TEX_FN void svm_node_tex_wave(float *stack, uint4 node, int *offset)
 {
   const uint4 node2 = __ldg(&g_scene.svm_nodes[*offset]);
   const uint4 node3 = __ldg(&g_scene.svm_nodes[*offset + 1]);
@@ -736,7 +742,7 @@ CY_DEV void svm_node_tex_wave(float *stack, uint4 node, int *offset)
 
 /* ----------------------------------------------------------- magic, brick */
 
-CY_DEV void svm_node_tex_magic(float *stack, uint4 node, int *offset)
+SVM_TEX_FN void svm_node_tex_magic(float *stack, uint4 node, int *offset)
 {
   const int depth = (int)(node.y & 0xff);
   const uint32_t color_off = (node.y >> 8) & 0xff, fac_off = (node.y >> 16) & 0xff;
@@ -796,7 +802,7 @@ CY_DEV float brick_noise(uint32_t n)
   return 0.5f * ((float)nn / 1073741824.0f);
 }
 
-CY_DEV void svm_node_tex_brick(float *stack, uint4 node, int *offset)
+SVM_TEX_FN void svm_node_tex_brick(float *stack, uint4 node, int *offset)
 {
   const uint4 node2 = __ldg(&g_scene.svm_nodes[*offset]);
   const uint4 node3 = __ldg(&g_scene.svm_nodes[*offset + 1]);
@@ -858,6 +864,152 @@ CY_DEV void svm_node_tex_brick(float *stack, uint4 node, int *offset)
     stack_store_float3(stack, color_off, color1 * (1.0f - f) + mortar_color * f);
   if (stack_valid(fac_off))
     stack[fac_off] = f;
+}
+
+/* --------------------------------- object info, camera, vector transform */
+
+CY_DEV float ko_float(int object, int off)
+{
+  return __ldg((const float *)(g_scene.objects + (size_t)object * SIZEOF_KERNEL_OBJECT + off));
+}
+
+/* svm_geometry.h:102-139 */
+SVM_TEX_FN void svm_node_object_info(const ShaderDataG &sd, float *stack, uint4 node)
+{
+  float data = 0.0f;
+  switch (node.y) {
+    case CY_NODE_INFO_OB_LOCATION: {
+      f3 loc = zero3();
+      if (sd.object != -1) {
+        const tfm34 t = object_tfm(sd.object);
+        loc = mk3(t.x.w, t.y.w, t.z.w);
+      }
+      stack_store_float3(stack, node.z, loc);
+      return;
+    }
+    case CY_NODE_INFO_OB_COLOR:
+      stack_store_float3(stack, node.z,
+                         (sd.object == -1) ? zero3() :
+                                             mk3(ko_float(sd.object, KO_COLOR),
+                                                 ko_float(sd.object, KO_COLOR + 4),
+                                                 ko_float(sd.object, KO_COLOR + 8)));
+      return;
+    case CY_NODE_INFO_OB_INDEX:
+      data = (sd.object == -1) ? 0.0f : ko_float(sd.object, KO_PASS_ID);
+      break;
+    case CY_NODE_INFO_MAT_INDEX:
+      data = (float)__ldg((const int *)(g_scene.shaders +
+                                        (size_t)(sd.shader & CY_SHADER_MASK) * SIZEOF_KERNEL_SHADER +
+                                        KS_PASS_ID));
+      break;
+    case CY_NODE_INFO_OB_RANDOM:
+      if (sd.lamp != -1)
+        data = __ldg((const float *)(g_scene.lights + (size_t)sd.lamp * SIZEOF_KERNEL_LIGHT +
+                                     KL_RANDOM));
+      else
+        data = (sd.object == -1) ? 0.0f : ko_float(sd.object, KO_RANDOM_NUMBER);
+      break;
+    default:
+      break;
+  }
+  stack[node.z] = data;
+}
+
+/* svm_camera.h:19-43 */
+SVM_TEX_FN void svm_node_camera(const ShaderDataG &sd, float *stack, uint4 node)
+{
+  const f3 vector = transform_point(kd_transform(KD_CAM_WORLDTOCAMERA), sd.P);
+  if (stack_valid(node.y))
+    stack_store_float3(stack, node.y, normalize(vector));
+  if (stack_valid(node.z))
+    stack[node.z] = vector.z;
+  if (stack_valid(node.w))
+    stack[node.w] = len(vector);
+}
+
+/* svm_vector_transform.h:21-105 */
+SVM_TEX_FN void svm_node_vector_transform(const ShaderDataG &sd, float *stack, uint4 node)
+{
+  const uint32_t type = node.y & 0xff, from = (node.y >> 8) & 0xff, to = (node.y >> 16) & 0xff;
+  const uint32_t vector_in = node.z & 0xff, vector_out = (node.z >> 8) & 0xff;
+  f3 in = stack_load_float3(stack, vector_in);
+  const bool is_object = (sd.object != -1);
+  const bool is_direction = (type == CY_NODE_VECTOR_TRANSFORM_TYPE_VECTOR ||
+                             type == CY_NODE_VECTOR_TRANSFORM_TYPE_NORMAL);
+  const uint32_t WORLD = CY_NODE_VECTOR_TRANSFORM_CONVERT_SPACE_WORLD,
+                 OBJECT = CY_NODE_VECTOR_TRANSFORM_CONVERT_SPACE_OBJECT,
+                 CAMERA = CY_NODE_VECTOR_TRANSFORM_CONVERT_SPACE_CAMERA;
+  /* world <-> camera through the camera matrices, world <-> object through the object's */
+  const bool to_world_first = (from == CAMERA && (to == WORLD || to == OBJECT));
+  const bool from_object_first = (from == OBJECT && (to == WORLD || to == CAMERA) && is_object);
+  if (to_world_first) {
+    const tfm34 t = kd_transform(KD_CAM_CAMERATOWORLD);
+    in = is_direction ? transform_direction(t, in) : transform_point(t, in);
+  }
+  if (from_object_first) {
+    const tfm34 t = object_tfm(sd.object);
+    in = is_direction ? transform_direction(t, in) : transform_point(t, in);
+  }
+  if ((from == WORLD || from == CAMERA) && to == OBJECT && is_object) {
+    const tfm34 t = object_itfm(sd.object);
+    in = is_direction ? transform_direction(t, in) : transform_point(t, in);
+  }
+  if ((from == WORLD || from == OBJECT) && to == CAMERA) {
+    const tfm34 t = kd_transform(KD_CAM_WORLDTOCAMERA);
+    in = is_direction ? transform_direction(t, in) : transform_point(t, in);
+  }
+  if (type == CY_NODE_VECTOR_TRANSFORM_TYPE_NORMAL)
+    in = normalize(in);
+  if (stack_valid(vector_out))
+    stack_store_float3(stack, vector_out, in);
+}
+
+/* svm_white_noise.h:19-79; hash_float*_to_float3 of util_hash.h:180-216 */
+SVM_TEX_FN void svm_node_tex_white_noise(float *stack, uint4 node)
+{
+  const uint32_t dims = node.y;
+  const uint32_t vector_offset = node.z & 0xff, w_offset = (node.z >> 8) & 0xff;
+  const uint32_t value_offset = node.w & 0xff, color_offset = (node.w >> 8) & 0xff;
+  const f3 v = stack_load_float3(stack, vector_offset);
+  const float w = stack[w_offset];
+  const uint32_t x = __float_as_uint(v.x), y = __float_as_uint(v.y), z = __float_as_uint(v.z),
+                 ww = __float_as_uint(w);
+  const uint32_t one = __float_as_uint(1.0f), two = __float_as_uint(2.0f);
+  uint32_t k0[4], k1[4], k2[4];
+  int n0 = (int)dims, n12 = (int)dims + 1; /* the 2nd and 3rd channel append 1.0 / 2.0 */
+  switch (dims) {
+    case 1:
+      k0[0] = k1[0] = k2[0] = ww;
+      k1[1] = one;
+      k2[1] = two;
+      break;
+    case 2:
+      k0[0] = k1[0] = k2[0] = x;
+      k0[1] = k1[1] = k2[1] = y;
+      k1[2] = one;
+      k2[2] = two;
+      break;
+    case 3:
+      k0[0] = k1[0] = k2[0] = x;
+      k0[1] = k1[1] = k2[1] = y;
+      k0[2] = k1[2] = k2[2] = z;
+      k1[3] = one;
+      k2[3] = two;
+      break;
+    default: /* 4D: the other channels hash permutations of the key */
+      k0[0] = x, k0[1] = y, k0[2] = z, k0[3] = ww;
+      k1[0] = z, k1[1] = x, k1[2] = ww, k1[3] = y;
+      k2[0] = ww, k2[1] = z, k2[2] = y, k2[3] = x;
+      n0 = n12 = 4;
+      break;
+  }
+  const float value = hash_to_unit_float(hash_uint_n(k0, n0));
+  if (stack_valid(color_offset))
+    stack_store_float3(stack, color_offset,
+                       mk3(value, hash_to_unit_float(hash_uint_n(k1, n12)),
+                           hash_to_unit_float(hash_uint_n(k2, n12))));
+  if (stack_valid(value_offset))
+    stack[value_offset] = value;
 }
 
 #endif /* B200_SVM_TEX_CUH */

@@ -1309,6 +1309,12 @@ static bool svm_mix_supported_host(uint32_t type)
     case CY_NODE_MIX_DIFF:
     case CY_NODE_MIX_DARK:
     case CY_NODE_MIX_LIGHT:
+    case CY_NODE_MIX_DODGE:
+    case CY_NODE_MIX_BURN:
+    case CY_NODE_MIX_HUE:
+    case CY_NODE_MIX_SAT:
+    case CY_NODE_MIX_VAL:
+    case CY_NODE_MIX_COLOR:
     case CY_NODE_MIX_SOFT:
     case CY_NODE_MIX_LINEAR:
     case CY_NODE_MIX_CLAMP:
@@ -1356,7 +1362,21 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
       case CY_NODE_MAPPING:
       case CY_NODE_TEX_CHECKER:
       case CY_NODE_TEX_GRADIENT:
+      case CY_NODE_HSV:
+      case CY_NODE_VECTOR_ROTATE:
+      case CY_NODE_VECTOR_TRANSFORM:
+      case CY_NODE_OBJECT_INFO:
+      case CY_NODE_CAMERA:
+      case CY_NODE_TEX_WHITE_NOISE:
         i += 1;
+        break;
+      case CY_NODE_SEPARATE_HSV:
+      case CY_NODE_COMBINE_HSV:
+      case CY_NODE_NORMAL:
+        i += 2;
+        break;
+      case CY_NODE_MAP_RANGE:
+        i += 3;
         break;
       case CY_NODE_GEOMETRY: /* the tangent reads the generated-coordinates attribute */
         if (nodes[4 * i + 1] == 2 /* NODE_GEOM_T */)
@@ -1423,8 +1443,7 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
         }
         const uint32_t blend = nodes[4 * (i + 1) + 1];
         if (!svm_mix_supported_host(blend)) {
-          why = "MixRGB blend mode " + std::to_string(blend) +
-                " (hue/saturation/value/colour/dodge/burn) is outside the hot-path scope";
+          why = "unknown MixRGB blend mode " + std::to_string(blend);
           return false;
         }
         i += 2;
@@ -1476,7 +1495,8 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
               "glossy-GGX/emission/background, mix closure, value, geometry, convert, fresnel, "
               "layer weight, math, vector math, mix, invert, gamma, bright/contrast, "
               "separate/combine, clamp, light path, light falloff, RGB ramp, curves, attribute, "
-              "texture coordinate, mapping, noise/wave/magic/checker/brick/gradient textures)";
+              "texture coordinate, mapping, noise/wave/magic/checker/brick/gradient/white noise "
+              "textures, HSV, map range, normal, vector rotate/transform, object info, camera)";
         return false;
     }
   }

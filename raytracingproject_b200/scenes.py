@@ -300,6 +300,87 @@ def _textured_shaders(variant):
             'roughness="0.4" clearcoat="1.0" clearcoat_roughness="0.05" metallic="0.3"/>\n'
             '  <mix_closure name="m"/>\n' + c("gr fac", "m fac") +
             c("p1 bsdf", "m closure1") + c("p2 bsdf", "m closure2"), "m closure")
+    elif variant == 2:
+        # colour / range / vector / info nodes: HSV, separate + combine HSV, the HSV and
+        # dodge / burn blend modes, map range (all four kinds), normal, vector rotate,
+        # vector transform, object info, camera data, white noise
+        white = _node_shader(
+            "white", '  <texture_coordinate name="tc"/>\n'
+            '  <checker_texture name="t" scale="2.0" color1="0.7 0.3 0.2" color2="0.2 0.5 0.7"/>\n' +
+            c("tc generated", "t vector") + '  <geometry name="g"/>\n'
+            '  <separate_xyz name="sep"/>\n' + c("g position", "sep vector") +
+            '  <map_range name="mr" type="smoothstep" from_min="-1" from_max="1" to_min="0.2" '
+            'to_max="0.8"/>\n' + c("sep x", "mr value") +
+            '  <hsv name="h" saturation="0.8" value="0.9" fac="0.9"/>\n' + c("t color", "h color") +
+            c("mr result", "h hue") + '  <diffuse_bsdf name="d"/>\n' + c("h color", "d color"),
+            "d bsdf")
+        chain = ""
+        prev = "t color"
+        for i, mode in enumerate(("hue", "saturation", "value", "color", "dodge", "burn")):
+            col2 = ("0.2 0.6 0.9", "0.5 0.5 0.2", "0.3 0.3 0.3", "0.9 0.4 0.1", "0.3 0.2 0.1",
+                    "0.8 0.9 0.7")[i]
+            chain += '  <mix name="m%d" type="%s" fac="0.6" color2="%s"/>\n' % (i, mode, col2)
+            chain += c(prev, "m%d color1" % i)
+            prev = "m%d color" % i
+        red = _node_shader(
+            "red", '  <wave_texture name="t" type="bands" bands_direction="z" profile="sine" '
+            'scale="0.6"/>\n  <mix name="base" type="mix" color1="0.65 0.05 0.05" '
+            'color2="0.1 0.3 0.6"/>\n' + c("t fac", "base fac") +
+            chain.replace('"t color"', '"base color"') +
+            '  <diffuse_bsdf name="d"/>\n' + c(prev, "d color"), "d bsdf")
+        green = _node_shader(
+            "green", '  <texture_coordinate name="tc"/>\n'
+            '  <vector_math name="sc" type="scale" scale="3.0"/>\n' + c("tc object", "sc vector1") +
+            '  <vector_math name="fl" type="floor"/>\n' + c("sc vector", "fl vector1") +
+            '  <white_noise_texture name="t" dimensions="3D"/>\n' + c("fl vector", "t vector") +
+            '  <separate_hsv name="sh"/>\n' + c("t color", "sh color") +
+            '  <math name="ms" type="multiply" value2="0.5"/>\n' + c("sh s", "ms value1") +
+            '  <white_noise_texture name="t4" dimensions="4D" w="0.37"/>\n' +
+            c("fl vector", "t4 vector") +
+            '  <map_range name="mr" type="stepped" from_min="0" from_max="1" to_min="0.3" '
+            'to_max="0.9" steps="3"/>\n' + c("t4 value", "mr value") +
+            '  <combine_hsv name="ch"/>\n' + c("sh h", "ch h") + c("ms value", "ch s") +
+            c("mr result", "ch v") + '  <diffuse_bsdf name="d"/>\n' + c("ch color", "d color"),
+            "d bsdf")
+        metal = _node_shader(
+            "metal", '  <object_info name="oi"/>\n  <camera_info name="ci"/>\n'
+            '  <map_range name="mr" type="smootherstep" from_min="2.5" from_max="4.5" '
+            'to_min="0.1" to_max="0.9"/>\n' + c("ci view_z_depth", "mr value") +
+            '  <map_range name="mr2" type="linear" from_min="3" from_max="5"/>\n' +
+            c("ci view_distance", "mr2 value") +
+            '  <geometry name="g"/>\n'
+            '  <vector_rotate name="vr" type="euler_xyz" rotation="0.4 0.2 0.7" '
+            'center="0.1 0 0.2"/>\n' + c("g normal", "vr vector") +
+            '  <vector_transform name="vt" type="normal" convert_from="world" '
+            'convert_to="camera"/>\n' + c("vr vector", "vt vector") +
+            '  <vector_math name="ab" type="absolute"/>\n' + c("vt vector", "ab vector1") +
+            '  <combine_xyz name="cmb"/>\n' + c("mr result", "cmb x") + c("oi random", "cmb y") +
+            c("mr2 result", "cmb z") +
+            '  <mix name="mx" type="mix" fac="0.5"/>\n' + c("ab vector", "mx color1") +
+            c("cmb vector", "mx color2") +
+            '  <vector_math name="ad" type="add"/>\n' + c("mx color", "ad vector1") +
+            c("oi location", "ad vector2") +
+            '  <vector_math name="fr" type="fraction"/>\n' + c("ad vector", "fr vector1") +
+            '  <glossy_bsdf name="gl" distribution="GGX" roughness="0.3"/>\n' +
+            c("fr vector", "gl color"), "gl bsdf")
+        glass = _node_shader(
+            "glass", '  <geometry name="g"/>\n'
+            '  <normal name="nn" direction="0.3 -0.5 0.8"/>\n' + c("g normal", "nn normal") +
+            '  <camera_info name="ci"/>\n'
+            '  <vector_rotate name="vr" type="axis" axis="0.2 0.5 1.0" invert="true"/>\n' +
+            c("g position", "vr vector") + c("ci view_distance", "vr angle") +
+            '  <vector_rotate name="vr2" type="y_axis" angle="0.8"/>\n' + c("vr vector", "vr2 vector") +
+            '  <vector_transform name="vt" type="point" convert_from="object" '
+            'convert_to="camera"/>\n' + c("vr2 vector", "vt vector") +
+            '  <vector_transform name="vt2" type="vector" convert_from="camera" '
+            'convert_to="object"/>\n' + c("ci view_vector", "vt2 vector") +
+            '  <vector_math name="ad" type="add"/>\n' + c("vt vector", "ad vector1") +
+            c("vt2 vector", "ad vector2") +
+            '  <vector_math name="fr" type="fraction"/>\n' + c("ad vector", "fr vector1") +
+            '  <mix name="mx" type="mix" color2="0.9 0.9 0.9"/>\n' + c("fr vector", "mx color1") +
+            c("nn dot", "mx fac") +
+            '  <principled_bsdf name="p" distribution="GGX" roughness="0.4" sheen="0.5"/>\n' +
+            c("mx color", "p base_color"), "p bsdf")
     else:
         white = _node_shader(
             "white", '  <texture_coordinate name="tc"/>\n'
@@ -548,8 +629,8 @@ def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
                    nearclip=0.01, farclip=100.0, cam_type=cam_type, cam_extra=cam_extra)
     xml += _background((0, 0, 0), 0.0)
     closure_variants = {"closures": 0, "closures2": 1, "transparent_opaque_shadow": 2,
-                        "transparent": 3, "textured": 10, "textured2": 11}
-    if materials in ("textured", "textured2"):
+                        "transparent": 3, "textured": 10, "textured2": 11, "textured3": 12}
+    if materials in ("textured", "textured2", "textured3"):
         xml += _textured_shaders(closure_variants[materials] - 10)
     elif materials in closure_variants:
         xml += _closure_shaders(closure_variants[materials])

@@ -10,29 +10,36 @@
 #include <string.h>
 
 #define CY_DEV static inline
+#define SVM_TEX_FN static inline
+#define SVM_NODES_INLINE 1
 #undef __device__
 #define __device__
 #undef __noinline__
 #define __noinline__
+#undef __forceinline__
+#define __forceinline__ inline
 #undef __constant__
 #define __constant__
 template<class T> static inline T __ldg(const T *p) { return *p; }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
 static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 
 #include "../../raytracingproject_b200/csrc/shader_data.cuh"
+#include "../../raytracingproject_b200/csrc/svm_nodes.cuh"
 #include "../../raytracingproject_b200/csrc/svm_tex.cuh"
 
 struct HostShadingPoint {
   float P[3], N[3], I[3], dPdu[3];
   float u, v;
-  int object, prim, lamp;
+  int object, prim, lamp, shader, backfacing;
 };
 
 struct HostSceneArrays {
-  const void *svm_nodes, *objects, *tri_vindex, *lights, *attributes_map, *attributes_float,
+  const void *svm_nodes, *objects, *tri_vindex, *lights, *shaders, *attributes_map, *attributes_float,
       *attributes_float2, *attributes_float3, *attributes_uchar4, *kernel_data;
 };
 
@@ -43,6 +50,7 @@ extern "C" __attribute__((visibility("default"))) void host_svm_bind(const HostS
   g_scene.objects = (const uint8_t *)a->objects;
   g_scene.tri_vindex = (const uint4 *)a->tri_vindex;
   g_scene.lights = (const uint8_t *)a->lights;
+  g_scene.shaders = (const uint8_t *)a->shaders;
   g_scene.attributes_map = (const uint4 *)a->attributes_map;
   g_scene.attributes_float = (const float *)a->attributes_float;
   g_scene.attributes_float2 = (const float2 *)a->attributes_float2;
@@ -68,6 +76,8 @@ extern "C" __attribute__((visibility("default"))) int host_svm_node(int offset, 
   sd.object = p->object;
   sd.prim = p->prim;
   sd.lamp = p->lamp;
+  sd.shader = p->shader;
+  sd.flag = p->backfacing ? CY_SD_BACKFACING : 0;
   sd.type = (p->prim != -1) ? (int)CY_PRIMITIVE_TRIANGLE : 0;
   const uint4 node = g_scene.svm_nodes[offset];
   offset++;
@@ -109,6 +119,73 @@ extern "C" __attribute__((visibility("default"))) int host_svm_node(int offset, 
       break;
     case CY_NODE_TEX_BRICK:
       svm_node_tex_brick(stack, node, &offset);
+      break;
+    case CY_NODE_TEX_WHITE_NOISE:
+      svm_node_tex_white_noise(stack, node);
+      break;
+    case CY_NODE_OBJECT_INFO:
+      svm_node_object_info(sd, stack, node);
+      break;
+    case CY_NODE_CAMERA:
+      svm_node_camera(sd, stack, node);
+      break;
+    case CY_NODE_VECTOR_TRANSFORM:
+      svm_node_vector_transform(sd, stack, node);
+      break;
+    case CY_NODE_VECTOR_ROTATE:
+      svm_node_vector_rotate(stack, node);
+      break;
+    case CY_NODE_NORMAL:
+      svm_node_normal(stack, node, &offset);
+      break;
+    case CY_NODE_MAP_RANGE:
+      svm_node_map_range(stack, node, &offset);
+      break;
+    case CY_NODE_HSV:
+      svm_node_hsv(stack, node);
+      break;
+    case CY_NODE_SEPARATE_HSV:
+      svm_node_separate_hsv(stack, node, &offset);
+      break;
+    case CY_NODE_COMBINE_HSV:
+      svm_node_combine_hsv(stack, node, &offset);
+      break;
+    case CY_NODE_CONVERT:
+      svm_node_convert(stack, node.y, node.z, node.w);
+      break;
+    case CY_NODE_FRESNEL:
+      svm_node_fresnel(sd, stack, node);
+      break;
+    case CY_NODE_LAYER_WEIGHT:
+      svm_node_layer_weight(sd, stack, node);
+      break;
+    case CY_NODE_MATH:
+      svm_node_math(stack, node);
+      break;
+    case CY_NODE_VECTOR_MATH:
+      svm_node_vector_math(stack, node, &offset);
+      break;
+    case CY_NODE_RGB_RAMP:
+      svm_node_rgb_ramp(stack, node, &offset);
+      break;
+    case CY_NODE_RGB_CURVES:
+    case CY_NODE_VECTOR_CURVES:
+      svm_node_curves(stack, node, &offset);
+      break;
+    case CY_NODE_GAMMA:
+      svm_node_gamma(stack, node);
+      break;
+    case CY_NODE_BRIGHTCONTRAST:
+      svm_node_brightness(stack, node);
+      break;
+    case CY_NODE_INVERT:
+      svm_node_invert(stack, node);
+      break;
+    case CY_NODE_MIX:
+      svm_node_mix(stack, node, &offset);
+      break;
+    case CY_NODE_CLAMP:
+      svm_node_clamp(stack, node, &offset);
       break;
     default:
       return -1;

@@ -90,6 +90,8 @@ def texture_cases():
     return {
         "cornell_textured": scenes.cornell(W, H, materials="textured"),
         "cornell_textured2": scenes.cornell(W, H, materials="textured2"),
+        # HSV / map range / vector rotate + transform / object info / camera / white noise
+        "cornell_textured3": scenes.cornell(W, H, materials="textured3"),
         # the same programs under a lamp-less mesh light (emissive-triangle MIS evaluates
         # the surface shader with PATH_RAY_EMISSION) and through an orthographic camera
         "cornell_textured_mesh_light": scenes.cornell(W, H, materials="textured", light="mesh"),

@@ -111,7 +111,7 @@ def test_camera_models_match_reference(ref, device, name):
         rs.close()
 
 
-@pytest.mark.parametrize("name", ["cornell_textured", "cornell_textured2",
+@pytest.mark.parametrize("name", ["cornell_textured", "cornell_textured2", "cornell_textured3",
                                   "cornell_textured_mesh_light", "cornell_textured_ortho"])
 def test_texture_nodes_match_reference(ref, device, name):
     desc = texture_cases()[name]

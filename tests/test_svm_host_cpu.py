@@ -50,7 +50,7 @@ def host_lib(tmp_path_factory):
 
 class Bound:
     """The scene arrays svm_tex.cuh reads, bound to the host build; keeps them alive."""
-    FIELDS = ["svm_nodes", "objects", "tri_vindex", "lights", "attributes_map",
+    FIELDS = ["svm_nodes", "objects", "tri_vindex", "lights", "shaders", "attributes_map",
               "attributes_float", "attributes_float2", "attributes_float3",
               "attributes_uchar4", "kernel_data"]
 
@@ -83,7 +83,10 @@ def shading_points(arrays, n, rng):
     # a few points that are not on a surface: background, and a lamp's emission shader
     pts["object"][: n // 16] = -1
     pts["prim"][: n // 16] = -1
-    pts["lamp"][: n // 32] = 0
+    if "__lights" in arrays:
+        pts["lamp"][: n // 32] = 0
+    pts["shader"] = rng.integers(0, arrays["__shaders"][0].size // 32, n)  # SIZEOF_KERNEL_SHADER
+    pts["backfacing"] = rng.integers(0, 2, n)
     return pts
 
 
@@ -94,12 +97,24 @@ def run_both(L, rs, nodes, offset, stack0, pt):
     return n_ref, n_dev, s_ref, s_dev
 
 
+PRINCIPLED_ID = int(re.search(r"#define CY_CLOSURE_BSDF_PRINCIPLED_ID[ \t]+(\d+)",
+                              open(os.path.join(ROOT, "include", "cycles_abi.h")).read()).group(1))
+
+
 def texture_ops():
     a = abi()
     return {a[k]: k for k in ("NODE_ATTR", "NODE_TEX_COORD", "NODE_MAPPING",
                               "NODE_TEXTURE_MAPPING", "NODE_MIN_MAX", "NODE_TEX_NOISE",
                               "NODE_TEX_CHECKER", "NODE_TEX_GRADIENT", "NODE_TEX_WAVE",
-                              "NODE_TEX_MAGIC", "NODE_TEX_BRICK", "NODE_GEOMETRY")}
+                              "NODE_TEX_MAGIC", "NODE_TEX_BRICK", "NODE_GEOMETRY",
+                              "NODE_HSV", "NODE_SEPARATE_HSV", "NODE_COMBINE_HSV",
+                              "NODE_MAP_RANGE", "NODE_NORMAL", "NODE_VECTOR_ROTATE",
+                              "NODE_VECTOR_TRANSFORM", "NODE_OBJECT_INFO", "NODE_CAMERA",
+                              "NODE_TEX_WHITE_NOISE", "NODE_MIX", "NODE_MATH",
+                              "NODE_VECTOR_MATH", "NODE_CONVERT", "NODE_INVERT", "NODE_GAMMA",
+                              "NODE_BRIGHTCONTRAST", "NODE_CLAMP", "NODE_FRESNEL",
+                              "NODE_LAYER_WEIGHT", "NODE_RGB_RAMP", "NODE_RGB_CURVES",
+                              "NODE_VECTOR_CURVES")}
 
 
 def compare(name, s_ref, s_dev, tol):
@@ -107,9 +122,11 @@ def compare(name, s_ref, s_dev, tol):
     assert not bad.any(), (name, np.nonzero(bad)[0][:8], s_ref[bad][:8], s_dev[bad][:8])
 
 
-@pytest.mark.parametrize("materials", ["textured", "textured2"])
+@pytest.mark.parametrize("materials", ["textured", "textured2", "textured3", "procedural",
+                                       "node_chart"])
 def test_compiled_texture_nodes_match_reference(ref, host_lib, materials):
-    desc = scenes.cornell(64, 48, spp=1, materials=materials)
+    desc = scenes.node_chart() if materials == "node_chart" else \
+        scenes.cornell(64, 48, spp=1, materials=materials)
     rs = ref.build_scene(desc)
     try:
         arrays = rs.device_arrays()
@@ -122,33 +139,88 @@ def test_compiled_texture_nodes_match_reference(ref, host_lib, materials):
         rng = np.random.default_rng(7)
         pts = shading_points(arrays, 64, rng)
         seen = {}
-        for off in range(len(real)):
+        # walk the program instruction by instruction: nodes the probes dispatch report
+        # their own length, the rest (closures, jumps, constants) have a fixed one
+        one = {a[k] for k in ("NODE_END", "NODE_SHADER_JUMP", "NODE_CLOSURE_EMISSION",
+                              "NODE_CLOSURE_BACKGROUND", "NODE_CLOSURE_SET_WEIGHT",
+                              "NODE_CLOSURE_WEIGHT", "NODE_EMISSION_WEIGHT", "NODE_MIX_CLOSURE",
+                              "NODE_JUMP_IF_ZERO", "NODE_JUMP_IF_ONE", "NODE_GEOMETRY",
+                              "NODE_VALUE_F", "NODE_LIGHT_PATH", "NODE_LIGHT_FALLOFF",
+                              "NODE_SEPARATE_VECTOR", "NODE_COMBINE_VECTOR")}
+        off = 0
+        while off < len(real):
             op = int(nodes[off, 0])
-            if op not in ops:
+            probed = op in ops and not (op == a["NODE_GEOMETRY"] and nodes[off, 1] != 2)
+            if not probed:
+                if op in one:
+                    off += 1
+                elif op == a["NODE_VALUE_V"]:
+                    off += 2
+                elif op == a["NODE_CLOSURE_BSDF"]:
+                    off += 6 if (nodes[off, 1] & 0xff) == PRINCIPLED_ID else 2
+                else:
+                    raise AssertionError("walk: opcode %d at %d" % (op, off))
                 continue
-            if op == a["NODE_GEOMETRY"] and nodes[off, 1] != 2:  # only the tangent
-                continue
-            if op == a["NODE_TEX_COORD"] and nodes[off, 1] > 4:  # dupli / volume: refused
-                continue
-            if op == a["NODE_TEX_NOISE"] and not 1 <= nodes[off, 1] <= 4:  # a data word
-                continue
+            nxt = None
+            if os.environ.get("SVM_HOST_TRACE"):
+                print("node", ops[op], off, nodes[off].tolist(), flush=True)
             for i in range(len(pts)):
                 stack0 = rng.uniform(-2.0, 2.0, 264).astype(np.float32)
                 n_ref, n_dev, s_ref, s_dev = run_both(host_lib, rs, nodes, off, stack0,
                                                       pts[i:i + 1])
-                assert n_ref == n_dev, (ops[op], off)
+                assert n_ref == n_dev and n_ref > off, (ops[op], off, n_ref, n_dev)
                 compare((ops[op], off, i), s_ref, s_dev, 3e-5)
                 if not np.array_equal(s_ref, stack0):
                     seen[ops[op]] = seen.get(ops[op], 0) + 1
+                nxt = n_ref
+            off = nxt
         # every node family the scenes were written to contain did run and wrote output
-        want = {"NODE_ATTR", "NODE_TEX_NOISE", "NODE_TEX_CHECKER", "NODE_TEX_WAVE",
-                "NODE_TEX_MAGIC", "NODE_MAPPING", "NODE_TEX_GRADIENT", "NODE_TEXTURE_MAPPING"}
-        want |= {"NODE_TEX_BRICK", "NODE_GEOMETRY"} if materials == "textured" else \
-            {"NODE_TEX_COORD", "NODE_MIN_MAX"}
+        common = {"NODE_ATTR", "NODE_TEX_NOISE", "NODE_TEX_CHECKER", "NODE_TEX_WAVE",
+                  "NODE_TEX_MAGIC", "NODE_MAPPING", "NODE_TEX_GRADIENT", "NODE_TEXTURE_MAPPING"}
+        want = {"textured": common | {"NODE_TEX_BRICK", "NODE_GEOMETRY"},
+                "textured2": common | {"NODE_TEX_COORD", "NODE_MIN_MAX"},
+                "textured3": {"NODE_HSV", "NODE_SEPARATE_HSV", "NODE_COMBINE_HSV",
+                              "NODE_MAP_RANGE", "NODE_NORMAL", "NODE_VECTOR_ROTATE",
+                              "NODE_VECTOR_TRANSFORM", "NODE_OBJECT_INFO", "NODE_CAMERA",
+                              "NODE_TEX_WHITE_NOISE", "NODE_MIX", "NODE_MATH",
+                              "NODE_VECTOR_MATH"},
+                "procedural": {"NODE_MATH", "NODE_VECTOR_MATH", "NODE_MIX", "NODE_CLAMP",
+                               "NODE_GAMMA", "NODE_INVERT", "NODE_BRIGHTCONTRAST",
+                               "NODE_FRESNEL", "NODE_LAYER_WEIGHT"},
+                "node_chart": {"NODE_MATH", "NODE_VECTOR_MATH", "NODE_MIX"}}[materials]
         assert want <= set(seen), sorted(want - set(seen))
         del bound
     finally:
         rs.close()
+
+
+O = "off"
+# Encodings of the value nodes (svm/svm_*.h): what the y, z, w words of the instruction
+# and of its data nodes hold - a stack offset, four packed offsets, a float, an enum range
+# (int), or a tuple of packed bytes.
+VALUE_NODE_SPECS = {
+    "NODE_MATH": {"yzw": (41, "packed", O)},
+    "NODE_VECTOR_MATH": {"yzw": (25, "packed", "packed"), "extra": [("off", O, O, O)]},
+    "NODE_MIX": {"yzw": (O, O, O), "extra": [(O, 19, O, O)]},
+    "NODE_CONVERT": {"yzw": (12, O, O)},
+    "NODE_INVERT": {"yzw": (O, O, O)},
+    "NODE_GAMMA": {"yzw": (O, O, O)},
+    "NODE_BRIGHTCONTRAST": {"yzw": (O, O, "packed")},
+    "NODE_CLAMP": {"yzw": (O, (O, O, 2), O), "extra": [("float", "float", "float", "float")]},
+    "NODE_FRESNEL": {"yzw": (O, "float", "packed")},
+    "NODE_LAYER_WEIGHT": {"yzw": (O, "float", (2, O, O))},
+    "NODE_HSV": {"yzw": ("packed", "packed", O)},
+    "NODE_SEPARATE_HSV": {"yzw": (O, O, O), "extra": [(O, O, O, O)]},
+    "NODE_COMBINE_HSV": {"yzw": (O, O, O), "extra": [(O, O, O, O)]},
+    "NODE_MAP_RANGE": {"yzw": (O, "packed", (4, O, O)),
+                       "extra": [("float",) * 4, ("float",) * 4]},
+    "NODE_NORMAL": {"yzw": (O, O, O), "extra": [("float",) * 4]},
+    "NODE_VECTOR_ROTATE": {"yzw": ((5, O, O, 2), "packed", O)},
+    "NODE_VECTOR_TRANSFORM": {"yzw": ((3, 3, 3), "packed", O)},
+    "NODE_OBJECT_INFO": {"yzw": (5, O, O)},
+    "NODE_CAMERA": {"yzw": (O, O, O)},
+    "NODE_TEX_WHITE_NOISE": {"yzw": ("dims", "packed", "packed")},
+}
 
 
 def random_program(op_name, rng, a):
@@ -194,6 +266,26 @@ def random_program(op_name, rng, a):
                    fbits(-0.5, 0.5)]
         prog[2] = [fbits(0.2, 1), fbits(0.1, 0.5), fbits(0, 1), fbits(0.5, 1.5)]
         prog[3, 0] = fbits(0, 1) if rng.random() < 0.6 else 0
+    elif op_name in VALUE_NODE_SPECS:
+        spec = VALUE_NODE_SPECS[op_name]
+        word = {"off": used, "packed": lambda: pack(used(), used(), used(), used()),
+                "float": lambda: fbits(0.2, 2.5), "dims": lambda: int(rng.integers(1, 5))}
+        for col, kind in zip((1, 2, 3), spec["yzw"]):
+            if isinstance(kind, int):
+                prog[0, col] = rng.integers(0, kind)
+            elif isinstance(kind, tuple):  # packed bytes: ints are enum ranges
+                prog[0, col] = pack(*[rng.integers(0, k) if isinstance(k, int) else used()
+                                      for k in kind])
+            else:
+                prog[0, col] = word[kind]()
+        if op_name == "NODE_VECTOR_MATH":
+            # only the output the operator defines is given a slot: the reference leaves
+            # the other one uninitialised (svm_math_util.h svm_vector_math)
+            scalar = int(prog[0, 1]) in (7, 8, 9)  # dot product, distance, length
+            prog[0, 3] = pack(used(), 255) if scalar else pack(255, used())
+        for row, kinds in enumerate(spec.get("extra", []), start=1):
+            for col, kind in enumerate(kinds):
+                prog[row, col] = rng.integers(0, kind) if isinstance(kind, int) else word[kind]()
     elif op_name == "NODE_TEX_COORD":
         kind = int(rng.choice([0, 1, 1, 2, 3, 4]))
         prog[0, 1:] = [kind, used(), int(kind == 1 and rng.random() < 0.5)]
@@ -204,7 +296,7 @@ def random_program(op_name, rng, a):
 @pytest.mark.parametrize("op_name", ["NODE_MAPPING", "NODE_TEXTURE_MAPPING", "NODE_MIN_MAX",
                                      "NODE_TEX_NOISE", "NODE_TEX_CHECKER", "NODE_TEX_GRADIENT",
                                      "NODE_TEX_WAVE", "NODE_TEX_MAGIC", "NODE_TEX_BRICK",
-                                     "NODE_TEX_COORD"])
+                                     "NODE_TEX_COORD"] + sorted(VALUE_NODE_SPECS))
 def test_random_node_encodings_match_reference(ref, host_lib, op_name):
     desc = scenes.cornell(64, 48, spp=1, materials="textured2")
     rs = ref.build_scene(desc)
@@ -225,5 +317,30 @@ def test_random_node_encodings_match_reference(ref, host_lib, op_name):
             wrote += int(not np.array_equal(s_ref, stack0))
             del bound
         assert wrote > 150
+    finally:
+        rs.close()
+
+
+def test_scope_check_without_a_device(ref):
+    """b200_validate_svm: programs of the supported scenes pass, a Voronoi texture or a
+    truncated program is refused with a reason - on the host, no GPU involved."""
+    from raytracingproject_b200.device import validate_svm
+    for materials in ("principled", "closures", "procedural", "textured", "textured2",
+                      "textured3", "transparent"):
+        rs = ref.build_scene(scenes.cornell(64, 48, spp=1, materials=materials))
+        try:
+            assert validate_svm(rs.device_arrays()["__svm_nodes"][0]) is None, materials
+        finally:
+            rs.close()
+    desc = scenes.cornell(64, 36, materials="diffuse")
+    desc.xml = desc.xml.replace(
+        '  <diffuse_bsdf name="d" color="0.73 0.73 0.73"/>\n',
+        '  <diffuse_bsdf name="d"/>\n  <voronoi_texture name="m" scale="3.0"/>\n'
+        '  <connect from="m color" to="d color"/>\n', 1)
+    rs = ref.build_scene(desc)
+    try:
+        svm = rs.device_arrays()["__svm_nodes"][0]
+        assert "SVM node opcode" in validate_svm(svm)
+        assert validate_svm(svm[:-8]) is not None          # not a whole number of nodes
     finally:
         rs.close()

@@ -44,25 +44,24 @@ def test_procedural_material_image(ref, device):
         rs.close()
 
 
-def test_unsupported_blend_mode_is_refused(ref, device):
-    """MixRGB hue / saturation / value / colour / dodge / burn need RGB<->HSV: refused."""
+def test_unsupported_node_is_refused(ref, device):
+    """A node outside the supported subset (Voronoi texture) is refused when its program
+    is bound - never skipped or approximated."""
     from raytracingproject_b200.device import DeviceError
     desc = scenes.cornell(64, 36, materials="diffuse")
     desc.xml = desc.xml.replace(
         '  <diffuse_bsdf name="d" color="0.73 0.73 0.73"/>\n',
         '  <diffuse_bsdf name="d"/>\n  <geometry name="g"/>\n'
-        '  <mix name="m" type="hue" fac="0.5" color2="0.1 0.2 0.9"/>\n'
-        '  <connect from="g position" to="m color1"/>\n'
+        '  <voronoi_texture name="m" scale="3.0"/>\n'
+        '  <connect from="g position" to="m vector"/>\n'
         '  <connect from="m color" to="d color"/>\n', 1)
-    assert 'type="hue"' in desc.xml
+    assert "voronoi_texture" in desc.xml
     rs = ref.build_scene(desc)
     try:
         arrays = rs.device_arrays()
-        nodes = arrays["__svm_nodes"][0].view(np.uint32).reshape(-1, 4)
-        assert (nodes[:, 0] == 73).any()           # NODE_MIX is in the program
         with pytest.raises(DeviceError) as e:      # refused when the program is bound
             device.upload_scene(arrays)
             device.render(desc.width, desc.height, rs.pass_stride, 0, 1)
-        assert "blend mode" in str(e.value)
+        assert "SVM node opcode" in str(e.value)
     finally:
         rs.close()
