@@ -77,6 +77,8 @@ typedef struct b200_stats {
   double device_ms;          /* CUDA-event time of the call's device work */
   double closest_ms;         /* CUDA-event time inside intersect_closest launches */
   double shadow_ms;          /* CUDA-event time inside intersect_shadow launches */
+  uint64_t svm_extended;     /* 1: shading ran the full SVM interpreter kernels (the bound
+                              * program holds texture / attribute / colour nodes or sheen) */
 } b200_stats;
 
 /* BVH8 build report (host builder). */

@@ -392,7 +392,7 @@ int b200_bind_global(b200_ctx *ctx, const char *name, uint64_t dptr, const void 
                                     "__prim_tri_index", "__prim_type",      "__prim_visibility",
                                     "__prim_object",    "__object_node",    "__objects",
                                     "__svm_nodes",      "__lights",         "__curves",
-                                    "__tri_patch"};
+                                    "__tri_patch",      "__attributes_map"};
   HostArray ha;
   ha.dptr = dptr;
   ha.bytes = bytes;
@@ -417,6 +417,14 @@ int b200_bind_global(b200_ctx *ctx, const char *name, uint64_t dptr, const void 
     std::string why;
     if (!svm_validate((const uint32_t *)ha.host.data(), bytes / 16, why, &ctx->svm_features))
       return fail(ctx, B200_ERR_UNSUPPORTED, why);
+  }
+  if (strcmp(name, "__attributes_map") == 0) {
+    ctx->has_generated_attr = false;
+    const uint32_t *map = (const uint32_t *)ha.host.data(); /* uint4 entries, x = id */
+    for (size_t i = 0; i < bytes / 16; i++)
+      if (map[4 * i] == CY_ATTR_STD_GENERATED && map[4 * i + 1] != CY_ATTR_ELEMENT_NONE)
+        ctx->has_generated_attr = true;
+    ha.host = std::vector<uint8_t>();
   }
   if (strcmp(name, "__tri_patch") == 0) {
     ctx->has_subd_patches = false;

@@ -26,6 +26,8 @@ struct PathPool; /* wavefront state, defined in b200_cycles.cu */
  * check_scope) */
 #define SVM_USES_ATTRIBUTES 1u
 #define SVM_USES_WINDOW_COORDINATES 2u
+#define SVM_USES_EXTENDED_NODES 4u /* anything svm_eval_extended_node dispatches */
+#define SVM_USES_TANGENT 8u        /* NODE_GEOM_T: reads generated coordinates when present */
 
 struct b200_ctx {
   int ordinal = 0;
@@ -46,6 +48,7 @@ struct b200_ctx {
   bool have_data = false;
   uint32_t svm_features = 0;     /* SVM_USES_* of the bound __svm_nodes (svm_validate) */
   bool has_subd_patches = false; /* __tri_patch holds a patch index */
+  bool has_generated_attr = false; /* __attributes_map lists ATTR_STD_GENERATED */
 
   /* BVH8 on the device */
   void *d_nodes = nullptr;

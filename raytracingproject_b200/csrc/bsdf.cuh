@@ -145,6 +145,9 @@ CY_DEV int bsdf_refraction_sample(const Closure &sc, f3 I, f3 *eval, f3 *omega_i
 }
 
 /* closure/bsdf.h bsdf_eval: reflect side when dot(Ng, omega_in) >= 0 */
+/* EXT = false: the closures the lean interpreter can create (it hands shaders with sheen
+ * to the full one, shade.cuh svm_eval_nodes) */
+template<bool EXT>
 CY_DEV f3 bsdf_eval(const ShaderDataG &sd, const Closure &sc, f3 omega_in, float *pdf)
 {
   f3 eval = zero3();
@@ -157,7 +160,8 @@ CY_DEV f3 bsdf_eval(const ShaderDataG &sd, const Closure &sc, f3 omega_in, float
         eval = bsdf_principled_diffuse_eval_reflect(sc, sd.I, omega_in, pdf);
         break;
       case CY_CLOSURE_BSDF_PRINCIPLED_SHEEN_ID:
-        eval = bsdf_principled_sheen_eval_reflect(sc, sd.I, omega_in, pdf);
+        if (EXT)
+          eval = bsdf_principled_sheen_eval_reflect(sc, sd.I, omega_in, pdf);
         break;
       case CY_CLOSURE_BSDF_OREN_NAYAR_ID:
         eval = bsdf_oren_nayar_eval_reflect(sc, sd.I, omega_in, pdf);
@@ -191,6 +195,7 @@ CY_DEV f3 bsdf_eval(const ShaderDataG &sd, const Closure &sc, f3 omega_in, float
 }
 
 /* closure/bsdf.h bsdf_sample */
+template<bool EXT>
 CY_DEV int bsdf_sample(const ShaderDataG &sd, const Closure &sc, float randu, float randv,
                        f3 *eval, f3 *omega_in, float *pdf)
 {
@@ -200,7 +205,10 @@ CY_DEV int bsdf_sample(const ShaderDataG &sd, const Closure &sc, float randu, fl
     case CY_CLOSURE_BSDF_PRINCIPLED_DIFFUSE_ID:
       return bsdf_principled_diffuse_sample(sc, sd.Ng, sd.I, randu, randv, eval, omega_in, pdf);
     case CY_CLOSURE_BSDF_PRINCIPLED_SHEEN_ID:
-      return bsdf_principled_sheen_sample(sc, sd.Ng, sd.I, randu, randv, eval, omega_in, pdf);
+      if (EXT)
+        return bsdf_principled_sheen_sample(sc, sd.Ng, sd.I, randu, randv, eval, omega_in, pdf);
+      *pdf = 0.0f;
+      return CY_LABEL_NONE;
     case CY_CLOSURE_BSDF_OREN_NAYAR_ID:
       return bsdf_oren_nayar_sample(sc, sd.Ng, sd.I, randu, randv, eval, omega_in, pdf);
     case CY_CLOSURE_BSDF_TRANSLUCENT_ID:

@@ -98,6 +98,15 @@ CY_DEV int bsdf_principled_diffuse_sample(const Closure &bsdf, f3 Ng, f3 I, floa
 }
 
 /* ---- Principled sheen (closure/bsdf_principled_sheen.h:47-134) ---- */
+#ifndef SHEEN_INLINE
+#  define SHEEN_INLINE 0
+#endif
+#if SHEEN_INLINE
+#  define SHEEN_FN CY_DEV
+#else
+#  define SHEEN_FN __device__ __noinline__
+#endif
+
 
 CY_DEV f3 principled_sheen_brdf(f3 N, f3 V, f3 L, f3 H, float *pdf)
 {
@@ -109,7 +118,7 @@ CY_DEV f3 principled_sheen_brdf(f3 N, f3 V, f3 L, f3 H, float *pdf)
   const float value = schlick_fresnel(dot(L, H)) * NdotL;
   return mk3(value, value, value);
 }
-CY_DEV f3 bsdf_principled_sheen_eval_reflect(const Closure &bsdf, f3 I, f3 omega_in, float *pdf)
+SHEEN_FN f3 bsdf_principled_sheen_eval_reflect(const Closure &bsdf, f3 I, f3 omega_in, float *pdf)
 {
   const f3 N = bsdf.N;
   const f3 H = normalize(omega_in + I);
@@ -120,7 +129,7 @@ CY_DEV f3 bsdf_principled_sheen_eval_reflect(const Closure &bsdf, f3 I, f3 omega
   *pdf = 0.0f;
   return zero3();
 }
-CY_DEV int bsdf_principled_sheen_sample(const Closure &bsdf, f3 Ng, f3 I, float randu,
+SHEEN_FN int bsdf_principled_sheen_sample(const Closure &bsdf, f3 Ng, f3 I, float randu,
                                         float randv, f3 *eval, f3 *omega_in, float *pdf)
 {
   const f3 N = bsdf.N;

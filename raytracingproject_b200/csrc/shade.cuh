@@ -587,11 +587,99 @@ CY_DEV void emission_setup(ShaderDataG &sd, f3 weight)
 #include "svm_nodes.cuh"
 #include "svm_tex.cuh"
 
+/* The nodes beyond the closure and basic value set, behind ONE out-of-line call: with
+ * their cases in the interpreter's own switch the common shaders (Principled, diffuse,
+ * glossy) paid 3 % of a Cornell frame for code they never run, measured A/B on one
+ * box. */
+__device__ __noinline__ int svm_eval_extended_node(ShaderDataG &sd, float *stack, uint4 node,
+                                                   int offset)
+{
+  /* the program counter comes and goes BY VALUE: taking its address in the interpreter
+   * would move it from a register to local memory for every node of every shader */
+  switch (node.x) {
+    case CY_NODE_HSV:
+      svm_node_hsv(stack, node);
+      break;
+    case CY_NODE_SEPARATE_HSV:
+      svm_node_separate_hsv(stack, node, &offset);
+      break;
+    case CY_NODE_COMBINE_HSV:
+      svm_node_combine_hsv(stack, node, &offset);
+      break;
+    case CY_NODE_MAP_RANGE:
+      svm_node_map_range(stack, node, &offset);
+      break;
+    case CY_NODE_NORMAL:
+      svm_node_normal(stack, node, &offset);
+      break;
+    case CY_NODE_VECTOR_ROTATE:
+      svm_node_vector_rotate(stack, node);
+      break;
+    case CY_NODE_VECTOR_TRANSFORM:
+      svm_node_vector_transform(sd, stack, node);
+      break;
+    case CY_NODE_OBJECT_INFO:
+      svm_node_object_info(sd, stack, node);
+      break;
+    case CY_NODE_CAMERA:
+      svm_node_camera(sd, stack, node);
+      break;
+    case CY_NODE_TEX_WHITE_NOISE:
+      svm_node_tex_white_noise(stack, node);
+      break;
+    case CY_NODE_ATTR:
+      svm_node_attr(sd, stack, node);
+      break;
+    case CY_NODE_TEX_COORD:
+      svm_node_tex_coord(sd, stack, node, &offset);
+      break;
+    case CY_NODE_MAPPING:
+      svm_node_mapping(stack, node);
+      break;
+    case CY_NODE_TEXTURE_MAPPING:
+      svm_node_texture_mapping(stack, node, &offset);
+      break;
+    case CY_NODE_MIN_MAX:
+      svm_node_min_max(stack, node, &offset);
+      break;
+    case CY_NODE_TEX_NOISE:
+      svm_node_tex_noise(stack, node, &offset);
+      break;
+    case CY_NODE_TEX_CHECKER:
+      svm_node_tex_checker(stack, node);
+      break;
+    case CY_NODE_TEX_GRADIENT:
+      svm_node_tex_gradient(stack, node);
+      break;
+    case CY_NODE_TEX_WAVE:
+      svm_node_tex_wave(stack, node, &offset);
+      break;
+    case CY_NODE_TEX_MAGIC:
+      svm_node_tex_magic(stack, node, &offset);
+      break;
+    case CY_NODE_TEX_BRICK:
+      svm_node_tex_brick(stack, node, &offset);
+      break;
+    default:
+      return -1;
+  }
+  return offset;
+}
+
 /* svm/svm.h:220-300 for the supported opcodes.  max_closures = 0 evaluates only
  * emission / background weights (PATH_RAY_EMISSION / TERMINATE evaluation,
- * kernel_shader.h:1063-1075). */
-__device__ __noinline__ void svm_eval_nodes(ShaderDataG &sd, PathDepths depths,
-                                            uint32_t path_flag, int max_closures)
+ * kernel_shader.h:1063-1075).
+ *
+ * Two instances.  FULL = false knows the closure nodes and the basic value nodes, calls
+ * nothing (a leaf function, its program counter and temporaries all in registers) and
+ * returns false the moment a shader needs more - an extended node, or a Principled BSDF
+ * with sheen.  FULL = true runs everything; its extended nodes sit behind out-of-line
+ * calls.  Measured A/B on one box with the Cornell workload (Principled + diffuse
+ * shaders only): one interpreter carrying everything costs 4.5 % of the frame, the
+ * split costs nothing. */
+template<bool FULL>
+__device__ __noinline__ bool svm_eval_nodes_t(ShaderDataG &sd, PathDepths depths,
+                                              uint32_t path_flag, int max_closures)
 {
   float stack[SVM_STACK_GPU];
   sd.num_closure = 0;
@@ -604,12 +692,13 @@ __device__ __noinline__ void svm_eval_nodes(ShaderDataG &sd, PathDepths depths,
     offset++;
     switch (node.x) {
       case CY_NODE_END:
-        return;
+        return true;
       case CY_NODE_SHADER_JUMP:
         offset = (int)node.y; /* SHADER_TYPE_SURFACE */
         break;
       case CY_NODE_CLOSURE_BSDF:
-        svm_node_closure_bsdf(sd, stack, node, path_flag, &offset);
+        if (!svm_node_closure_bsdf<FULL>(sd, stack, node, path_flag, &offset))
+          return false;
         break;
       case CY_NODE_CLOSURE_EMISSION:
       case CY_NODE_CLOSURE_BACKGROUND: {
@@ -665,6 +754,8 @@ __device__ __noinline__ void svm_eval_nodes(ShaderDataG &sd, PathDepths depths,
             data = sd.N;
             break;
           case CY_NODE_GEOM_T:
+            /* every Principled BSDF carries this node (its tangent input defaults to
+             * it), so it belongs to the lean set too */
             data = primitive_tangent(sd);
             break;
           case CY_NODE_GEOM_I:
@@ -747,77 +838,43 @@ __device__ __noinline__ void svm_eval_nodes(ShaderDataG &sd, PathDepths depths,
       case CY_NODE_VECTOR_CURVES:
         svm_node_curves(stack, node, &offset);
         break;
-      case CY_NODE_HSV:
-        svm_node_hsv(stack, node);
-        break;
-      case CY_NODE_SEPARATE_HSV:
-        svm_node_separate_hsv(stack, node, &offset);
-        break;
-      case CY_NODE_COMBINE_HSV:
-        svm_node_combine_hsv(stack, node, &offset);
-        break;
-      case CY_NODE_MAP_RANGE:
-        svm_node_map_range(stack, node, &offset);
-        break;
-      case CY_NODE_NORMAL:
-        svm_node_normal(stack, node, &offset);
-        break;
-      case CY_NODE_VECTOR_ROTATE:
-        svm_node_vector_rotate(stack, node);
-        break;
-      case CY_NODE_VECTOR_TRANSFORM:
-        svm_node_vector_transform(sd, stack, node);
-        break;
-      case CY_NODE_OBJECT_INFO:
-        svm_node_object_info(sd, stack, node);
-        break;
-      case CY_NODE_CAMERA:
-        svm_node_camera(sd, stack, node);
-        break;
-      case CY_NODE_TEX_WHITE_NOISE:
-        svm_node_tex_white_noise(stack, node);
-        break;
-      case CY_NODE_ATTR:
-        svm_node_attr(sd, stack, node);
-        break;
-      case CY_NODE_TEX_COORD:
-        svm_node_tex_coord(sd, stack, node, &offset);
-        break;
-      case CY_NODE_MAPPING:
-        svm_node_mapping(stack, node);
-        break;
-      case CY_NODE_TEXTURE_MAPPING:
-        svm_node_texture_mapping(stack, node, &offset);
-        break;
-      case CY_NODE_MIN_MAX:
-        svm_node_min_max(stack, node, &offset);
-        break;
-      case CY_NODE_TEX_NOISE:
-        svm_node_tex_noise(stack, node, &offset);
-        break;
-      case CY_NODE_TEX_CHECKER:
-        svm_node_tex_checker(stack, node);
-        break;
-      case CY_NODE_TEX_GRADIENT:
-        svm_node_tex_gradient(stack, node);
-        break;
-      case CY_NODE_TEX_WAVE:
-        svm_node_tex_wave(stack, node, &offset);
-        break;
-      case CY_NODE_TEX_MAGIC:
-        svm_node_tex_magic(stack, node, &offset);
-        break;
-      case CY_NODE_TEX_BRICK:
-        svm_node_tex_brick(stack, node, &offset);
-        break;
       default:
-        /* refused at bind time by svm_validate(); unreachable */
-        return;
+        /* the texture / attribute / colour nodes; anything else was refused at bind
+         * time by svm_validate() */
+        if (!FULL)
+          return false;
+        offset = svm_eval_extended_node(sd, stack, node, offset);
+        if (offset < 0)
+          return true;
+        break;
     }
   }
 }
 
+/* Set when the lean interpreter met something only the full one handles although the
+ * host's scan of the program (svm_validate: SVM_USES_EXTENDED_NODES) promised there was
+ * none; b200_render reports it as an internal error instead of returning a wrong frame. */
+__device__ unsigned int g_svm_scope_miss;
+
+/* EXT is a property of the bound program, decided on the host, and selects the kernel
+ * instance: programs with extended nodes (or a Principled BSDF whose sheen is not a
+ * constant zero) run the full interpreter, all others the lean one. */
+template<bool EXT>
+CY_DEV void svm_eval_nodes(ShaderDataG &sd, PathDepths depths, uint32_t path_flag,
+                           int max_closures)
+{
+  if (EXT) {
+    svm_eval_nodes_t<true>(sd, depths, path_flag, max_closures);
+  }
+  else if (!svm_eval_nodes_t<false>(sd, depths, path_flag, max_closures)) {
+    g_svm_scope_miss = 1u;
+    sd.num_closure = 0;
+    sd.flag &= ~(CY_SD_BSDF | CY_SD_EMISSION);
+  }
+}
+
 /* kernel_shader.h:1057-1110 */
+template<bool EXT>
 CY_DEV void shader_eval_surface(ShaderDataG &sd, PathDepths depths, uint32_t path_flag)
 {
   int max_closures;
@@ -825,7 +882,7 @@ CY_DEV void shader_eval_surface(ShaderDataG &sd, PathDepths depths, uint32_t pat
     max_closures = 0;
   else
     max_closures = min(kd_int(KD_INT_MAX_CLOSURES), MAX_CLOSURES_GPU);
-  svm_eval_nodes(sd, depths, path_flag, max_closures);
+  svm_eval_nodes<EXT>(sd, depths, path_flag, max_closures);
 }
 
 /* kernel_shader.h:530-555 */
@@ -845,6 +902,7 @@ CY_DEV void shader_prepare_closures(ShaderDataG &sd, const PathStateG &state)
 }
 
 /* kernel_shader.h:556-582 (_shader_bsdf_multi_eval), use_light_pass = 0 */
+template<bool EXT>
 CY_DEV void shader_bsdf_multi_eval(const ShaderDataG &sd, f3 omega_in, float *pdf, int skip,
                                    f3 *result_eval, float sum_pdf, float sum_sample_weight)
 {
@@ -852,7 +910,7 @@ CY_DEV void shader_bsdf_multi_eval(const ShaderDataG &sd, f3 omega_in, float *pd
     const Closure &sc = sd.closure[i];
     if (i != skip && sc.type <= CY_CLOSURE_BSDF_TRANSPARENT_ID) {
       float bsdf_pdf = 0.0f;
-      f3 eval = bsdf_eval(sd, sc, omega_in, &bsdf_pdf);
+      f3 eval = bsdf_eval<EXT>(sd, sc, omega_in, &bsdf_pdf);
       if (bsdf_pdf != 0.0f) {
         *result_eval += eval * sc.weight;
         sum_pdf += bsdf_pdf * sc.sample_weight;
@@ -870,11 +928,12 @@ CY_DEV float power_heuristic(float a, float b)
 }
 
 /* kernel_shader.h:612-636 (non-branched) */
+template<bool EXT>
 CY_DEV f3 shader_bsdf_eval(const ShaderDataG &sd, f3 omega_in, float light_pdf, bool use_mis)
 {
   f3 eval = zero3();
   float pdf;
-  shader_bsdf_multi_eval(sd, omega_in, &pdf, -1, &eval, 0.0f, 0.0f);
+  shader_bsdf_multi_eval<EXT>(sd, omega_in, &pdf, -1, &eval, 0.0f, 0.0f);
   if (use_mis) {
     float weight = power_heuristic(light_pdf, pdf);
     eval *= weight;
@@ -883,6 +942,7 @@ CY_DEV f3 shader_bsdf_eval(const ShaderDataG &sd, f3 omega_in, float light_pdf, 
 }
 
 /* kernel_shader.h:638-680 + 739-775 */
+template<bool EXT>
 CY_DEV int shader_bsdf_sample(ShaderDataG &sd, float randu, float randv, f3 *bsdf_eval_out,
                               f3 *omega_in, float *pdf)
 {
@@ -915,12 +975,13 @@ CY_DEV int shader_bsdf_sample(ShaderDataG &sd, float randu, float randv, f3 *bsd
   }
   f3 eval = zero3();
   *pdf = 0.0f;
-  int label = bsdf_sample(sd, sc, randu, randv, &eval, omega_in, pdf);
+  int label = bsdf_sample<EXT>(sd, sc, randu, randv, &eval, omega_in, pdf);
   if (*pdf != 0.0f) {
     *bsdf_eval_out = eval * sc.weight;
     if (sd.num_closure > 1) {
       float sweight = sc.sample_weight;
-      shader_bsdf_multi_eval(sd, *omega_in, pdf, sampled, bsdf_eval_out, *pdf * sweight, sweight);
+      shader_bsdf_multi_eval<EXT>(sd, *omega_in, pdf, sampled, bsdf_eval_out, *pdf * sweight,
+                                  sweight);
     }
   }
   return label;
@@ -1350,6 +1411,7 @@ CY_DEV bool shader_constant_emission_eval(int shader, f3 *eval)
 }
 
 /* kernel_emission.h:20-98.  `emission_sd` is scratch. */
+template<bool EXT>
 CY_DEV f3 direct_emissive_eval(ShaderDataG &emission_sd, PathDepths depths, LightSampleG *ls,
                                f3 I, float t)
 {
@@ -1402,7 +1464,7 @@ CY_DEV f3 direct_emissive_eval(ShaderDataG &emission_sd, PathDepths depths, Ligh
       }
     }
     ls->Ng = emission_sd.Ng;
-    shader_eval_surface(emission_sd, depths, CY_PATH_RAY_EMISSION);
+    shader_eval_surface<EXT>(emission_sd, depths, CY_PATH_RAY_EMISSION);
     /* shader_emissive_eval: emissive_simple_eval(Ng, I) * weight */
     if (emission_sd.flag & CY_SD_EMISSION) {
       float cosNO = fabsf(dot(emission_sd.Ng, emission_sd.I));
@@ -1418,6 +1480,7 @@ CY_DEV f3 direct_emissive_eval(ShaderDataG &emission_sd, PathDepths depths, Ligh
 }
 
 /* kernel_emission.h:288-340 without background MIS (refused by check_scope) */
+template<bool EXT>
 CY_DEV f3 indirect_background(ShaderDataG &emission_sd, const PathStateG &state, f3 rayD)
 {
   int shader = kd_int(KD_BG_SURFACE_SHADER);
@@ -1448,7 +1511,7 @@ CY_DEV f3 indirect_background(ShaderDataG &emission_sd, const PathStateG &state,
     emission_sd.type = 0;
     emission_sd.u = emission_sd.v = 0.0f;
     emission_sd.dPdu = zero3();
-    shader_eval_surface(emission_sd, path_depths(state), state.flag | CY_PATH_RAY_EMISSION);
+    shader_eval_surface<EXT>(emission_sd, path_depths(state), state.flag | CY_PATH_RAY_EMISSION);
     if (emission_sd.flag & CY_SD_EMISSION)
       L = emission_sd.closure_emission_background;
   }

@@ -9,7 +9,9 @@
 #include "device_scene.cuh"
 
 #define CLOSURE_WEIGHT_CUTOFF 1e-5f
-#define MAX_CLOSURES_GPU 32 /* two to four mixed Principled BSDFs (8 each, graph.cpp:1147) */
+#ifndef MAX_CLOSURES_GPU
+#  define MAX_CLOSURES_GPU 32 /* two to four mixed Principled BSDFs (8 each, graph.cpp:1147) */
+#endif
 #define SVM_STACK_GPU 256 /* SVM_STACK_SIZE 255 (svm_types.h): any offset the compiler can emit is in range */
 
 /* util/util_projection.h:48-55 */

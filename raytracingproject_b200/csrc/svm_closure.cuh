@@ -77,7 +77,10 @@ CY_DEV Closure *microfacet_alloc(ShaderDataG &sd, f3 weight, bool with_extra)
   return bsdf;
 }
 
-CY_DEV void svm_node_closure_bsdf(ShaderDataG &sd, float *stack, uint4 node, uint32_t path_flag,
+/* FULL = false is the interpreter for the common shaders (see svm_eval_nodes); the
+ * return value is reserved for "this shader needs the full one". */
+template<bool FULL>
+CY_DEV bool svm_node_closure_bsdf(ShaderDataG &sd, float *stack, uint4 node, uint32_t path_flag,
                                   int *offset)
 {
   const uint32_t type = node.y & 0xff, param1_offset = (node.y >> 8) & 0xff;
@@ -90,7 +93,7 @@ CY_DEV void svm_node_closure_bsdf(ShaderDataG &sd, float *stack, uint4 node, uin
   if (mix_weight == 0.0f) {
     if (type == CY_CLOSURE_BSDF_PRINCIPLED_ID)
       (*offset) += 4;
-    return;
+    return true;
   }
 
   f3 N = stack_valid(data_node.x) ? stack_load_float3(stack, data_node.x) : sd.N;
@@ -180,8 +183,11 @@ CY_DEV void svm_node_closure_bsdf(ShaderDataG &sd, float *stack, uint4 node, uin
         }
       }
 
-      /* sheen (svm_closure.h:256-279) */
-      if (diffuse_weight > CLOSURE_WEIGHT_CUTOFF && sheen > CLOSURE_WEIGHT_CUTOFF) {
+      /* sheen (svm_closure.h:256-279).  Full interpreter only: the host routes every
+       * program whose Principled sheen input is not a constant zero to it (svm_validate,
+       * SVM_USES_EXTENDED_NODES), so the lean one never sees sheen - and a test for it
+       * here, of all places, cost the lean kernels 2 % (register allocation). */
+      if (FULL && diffuse_weight > CLOSURE_WEIGHT_CUTOFF && sheen > CLOSURE_WEIGHT_CUTOFF) {
         const float m_cdlum = dot(base_color, mk3(kd_float(KD_FILM_RGB_TO_Y),
                                                   kd_float(KD_FILM_RGB_TO_Y + 4),
                                                   kd_float(KD_FILM_RGB_TO_Y + 8)));
@@ -457,6 +463,7 @@ CY_DEV void svm_node_closure_bsdf(ShaderDataG &sd, float *stack, uint4 node, uin
     default:
       break; /* refused at bind time */
   }
+  return true;
 }
 
 #endif

@@ -534,6 +534,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_sort_scatter(PathSoA p)
 
 /* kernel_path.h:86-113 + kernel_emission.h:235-286: emission of lamps hit by the
  * ray segment, weighted against light sampling.  Returns the updated ray_t. */
+template<bool EXT>
 CY_DEV void path_lamp_emission(PathStateG &st, f3 rayP, f3 rayD, float isect_t, f3 throughput,
                                ShaderDataG &emission_sd, f3 &L_emission)
 {
@@ -555,7 +556,7 @@ CY_DEV void path_lamp_emission(PathStateG &st, f3 rayP, f3 rayD, float isect_t, 
             ((ls.shader & CY_SHADER_EXCLUDE_SCATTER) && (st.flag & CY_PATH_RAY_VOLUME_SCATTER)))
           continue;
       }
-      f3 lamp_L = direct_emissive_eval(emission_sd, path_depths(st), &ls, -rayD, ls.t);
+      f3 lamp_L = direct_emissive_eval<EXT>(emission_sd, path_depths(st), &ls, -rayD, ls.t);
       if (!(st.flag & CY_PATH_RAY_MIS_SKIP)) {
         float mis_weight = power_heuristic(st.ray_pdf, ls.pdf);
         lamp_L *= mis_weight;
@@ -573,6 +574,7 @@ CY_DEV void path_lamp_emission(PathStateG &st, f3 rayP, f3 rayD, float isect_t, 
 #ifndef BG_MIN_BLOCKS
 #  define BG_MIN_BLOCKS 1
 #endif
+template<bool EXT>
 __global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(PathSoA p)
 {
   WFCounters *c = p.counters;
@@ -595,7 +597,7 @@ __global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(Pa
     const float isect_t = p.hit[qpos].x; /* = ray t on a miss (bvh_traversal.h:62) */
 
     ShaderDataG esd;
-    path_lamp_emission(st, rayP, rayD, isect_t, throughput, esd, L);
+    path_lamp_emission<EXT>(st, rayP, rayD, isect_t, throughput, esd, L);
 
     /* kernel_path_background - kernel_path.h:115-144 */
     bool eval_bg = true;
@@ -606,7 +608,7 @@ __global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(Pa
     if (eval_bg) {
       if (path_state_ao_bounce(st))
         throughput *= kd_float(KD_BG_AO_BOUNCES_FACTOR);
-      f3 L_background = indirect_background(esd, st, rayD);
+      f3 L_background = indirect_background<EXT>(esd, st, rayD);
       /* path_radiance_accum_background - kernel_accumulate.h:478-515 */
       f3 contribution = throughput * L_background;
       path_radiance_clamp(&contribution, st.bounce - 1);
@@ -621,7 +623,9 @@ __global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(Pa
 #ifndef SHADE_MIN_BLOCKS
 #  define SHADE_MIN_BLOCKS 2
 #endif
-__global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS) k_shade_surface(PathSoA p, int num_keys)
+template<bool EXT>
+__global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS)
+    k_shade_surface(PathSoA p, int num_keys)
 {
   WFCounters *c = p.counters;
   const unsigned int begin = c->offsets[1];
@@ -660,13 +664,13 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS) k_shade_surface(Pa
       ShaderDataG sd;
       {
         /* lamps crossed before the hit (kernel_path.h:537) - uses `sd` as scratch */
-        path_lamp_emission(st, rayP, rayD, hit.x, throughput, sd, L);
+        path_lamp_emission<EXT>(st, rayP, rayD, hit.x, throughput, sd, L);
       }
 
       bool alive = !path_state_ao_bounce(st); /* kernel_path.h:560-562 */
       if (alive) {
         shader_setup_from_ray(sd, hit_prim, hit_object, hit.x, hit.y, hit.z, rayP, rayD);
-        shader_eval_surface(sd, path_depths(st), st.flag);
+        shader_eval_surface<EXT>(sd, path_depths(st), st.flag);
         shader_prepare_closures(sd, st);
 
         /* kernel_path_shader_apply - kernel_path.h:254-321 (no holdout / shadow catcher;
@@ -742,11 +746,11 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS) k_shade_surface(Pa
               }
               else {
                 ShaderDataG scratch;
-                light_eval = direct_emissive_eval(scratch, path_depths(st), &ls, -ls.D, ls.t);
+                light_eval = direct_emissive_eval<EXT>(scratch, path_depths(st), &ls, -ls.D, ls.t);
               }
             }
             if (!is_zero(light_eval)) {
-              f3 eval = shader_bsdf_eval(sd, ls.D, ls.pdf, (ls.shader & CY_SHADER_USE_MIS) != 0);
+              f3 eval = shader_bsdf_eval<EXT>(sd, ls.D, ls.pdf, (ls.shader & CY_SHADER_USE_MIS) != 0);
               eval *= light_eval / ls.pdf;
               bool ok = !is_zero(eval);
               if (ok && kd_float(KD_INT_LIGHT_INV_RR_THRESHOLD) > 0.0f) {
@@ -798,7 +802,7 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS) k_shade_surface(Pa
           path_state_rng_2D(st, CY_PRNG_BSDF_U, &bsdf_u, &bsdf_v);
           f3 bsdf_eval = zero3(), omega_in = zero3();
           float bsdf_pdf;
-          int label = shader_bsdf_sample(sd, bsdf_u, bsdf_v, &bsdf_eval, &omega_in, &bsdf_pdf);
+          int label = shader_bsdf_sample<EXT>(sd, bsdf_u, bsdf_v, &bsdf_eval, &omega_in, &bsdf_pdf);
           if (!(bsdf_pdf == 0.0f || is_zero(bsdf_eval))) {
             /* LABEL_TRANSMIT_TRANSPARENT (closure/bsdf.h:466-475) needs transparent glass,
              * which check_scope refuses (threshold < 0 here) */
@@ -951,6 +955,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS)
  * kernel_shadow.h:46-88, 300-352): nothing hit -> the light arrives, attenuated; an
  * opaque surface -> blocked; a transparent one -> evaluate its shader as a shadow ray,
  * multiply the attenuation by its transparency and continue behind it. */
+template<bool EXT>
 __global__ void __launch_bounds__(WF_BLOCK) k_shade_shadow_step(PathSoA p, int cur)
 {
   WFCounters *c = p.counters;
@@ -993,7 +998,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_shade_shadow_step(PathSoA p, int c
           depths.bounce = 1;
           depths.diffuse = depths.glossy = depths.transmission = 0;
           depths.transparent = (short)bounce;
-          shader_eval_surface(sd, depths, CY_PATH_RAY_SHADOW);
+          shader_eval_surface<EXT>(sd, depths, CY_PATH_RAY_SHADOW);
           f3 t = (sd.flag & CY_SD_TRANSPARENT) ? sd.closure_transparent_extinction : zero3();
           f3 nthr = mk3(thr.x, thr.y, thr.z) * t;
           if (!is_zero(nthr)) {
@@ -1329,11 +1334,32 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
                          uint32_t *features)
 {
   *features = 0;
+  /* Constants the program wrote with NODE_VALUE_F since the last node of any other kind:
+   * the SVM compiler emits a closure node's unlinked inputs as such a run right before
+   * it (SVMCompiler::stack_assign from ShaderNode::compile), which is enough to tell a
+   * Principled BSDF whose sheen is a constant zero from one that may have sheen. */
+  bool const_known[256] = {};
+  float const_value[256] = {};
+  size_t const_run_end = 0; /* node index the table is valid for */
   /* Walk the stream linearly; NODE_CLOSURE_BSDF and NODE_VALUE_V carry data nodes
    * that must be skipped exactly as the interpreter does. */
   size_t i = 0;
   while (i < n_nodes) {
     const uint32_t op = nodes[4 * i];
+    if (op == CY_NODE_VALUE_F) {
+      if (const_run_end != i)
+        memset(const_known, 0, sizeof(const_known));
+      const uint32_t slot = nodes[4 * i + 2] & 0xff;
+      const_known[slot] = true;
+      memcpy(&const_value[slot], &nodes[4 * i + 1], 4);
+      const_run_end = i + 1;
+    }
+    else if (op == CY_NODE_VALUE_V && const_run_end == i) {
+      const uint32_t slot = nodes[4 * i + 1] & 0xff; /* overwrites three slots */
+      for (uint32_t k = slot; k < slot + 3 && k < 256; k++)
+        const_known[k] = false;
+      const_run_end = i + 2;
+    }
     switch (op) {
       case CY_NODE_END:
       case CY_NODE_SHADER_JUMP:
@@ -1359,6 +1385,7 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
         break;
       case CY_NODE_LIGHT_PATH:
       case CY_NODE_LIGHT_FALLOFF:
+      /* from here on: the nodes of svm_eval_extended_node (shade.cuh) */
       case CY_NODE_MAPPING:
       case CY_NODE_TEX_CHECKER:
       case CY_NODE_TEX_GRADIENT:
@@ -1368,27 +1395,31 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
       case CY_NODE_OBJECT_INFO:
       case CY_NODE_CAMERA:
       case CY_NODE_TEX_WHITE_NOISE:
+        *features |= SVM_USES_EXTENDED_NODES;
         i += 1;
         break;
       case CY_NODE_SEPARATE_HSV:
       case CY_NODE_COMBINE_HSV:
       case CY_NODE_NORMAL:
+        *features |= SVM_USES_EXTENDED_NODES;
         i += 2;
         break;
       case CY_NODE_MAP_RANGE:
+        *features |= SVM_USES_EXTENDED_NODES;
         i += 3;
         break;
       case CY_NODE_GEOMETRY: /* the tangent reads the generated-coordinates attribute */
         if (nodes[4 * i + 1] == 2 /* NODE_GEOM_T */)
-          *features |= SVM_USES_ATTRIBUTES;
+          *features |= SVM_USES_TANGENT;
         i += 1;
         break;
       case CY_NODE_ATTR:
-        *features |= SVM_USES_ATTRIBUTES;
+        *features |= SVM_USES_ATTRIBUTES | SVM_USES_EXTENDED_NODES;
         i += 1;
         break;
       case CY_NODE_TEX_COORD: {
         const uint32_t type = nodes[4 * i + 1];
+        *features |= SVM_USES_EXTENDED_NODES;
         if (type == CY_NODE_TEXCO_WINDOW)
           *features |= SVM_USES_WINDOW_COORDINATES;
         else if (type != CY_NODE_TEXCO_NORMAL && type != CY_NODE_TEXCO_OBJECT &&
@@ -1402,15 +1433,18 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
         break;
       }
       case CY_NODE_TEX_MAGIC:
+        *features |= SVM_USES_EXTENDED_NODES;
         i += 2;
         break;
       case CY_NODE_MIN_MAX:
       case CY_NODE_TEX_NOISE:
       case CY_NODE_TEX_WAVE:
+        *features |= SVM_USES_EXTENDED_NODES;
         i += 3;
         break;
       case CY_NODE_TEXTURE_MAPPING:
       case CY_NODE_TEX_BRICK:
+        *features |= SVM_USES_EXTENDED_NODES;
         i += 4;
         break;
       case CY_NODE_VALUE_V:
@@ -1459,6 +1493,11 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
           const uint32_t distribution = nodes[4 * (i + 2) + 1];
           const uint32_t subsurface_method = nodes[4 * (i + 2) + 2];
           (void)subsurface_method;
+          /* sheen: handled by the full interpreter only (shade.cuh svm_eval_nodes) */
+          const uint32_t sheen_slot = nodes[4 * (i + 1) + 3] & 0xff;
+          if (!(const_run_end == i && const_known[sheen_slot] &&
+                const_value[sheen_slot] <= 1e-5f /* CLOSURE_WEIGHT_CUTOFF */))
+            *features |= SVM_USES_EXTENDED_NODES;
           if (distribution != CY_CLOSURE_BSDF_MICROFACET_GGX_GLASS_ID) {
             why = "Principled BSDF with the Multiscatter GGX distribution is outside the "
                   "hot-path scope (random-walk closure); set distribution to GGX";
@@ -1547,7 +1586,9 @@ static int check_scope(b200_ctx *ctx)
            I(KD_CAM_TYPE) != CY_CAMERA_PERSPECTIVE)
     why = "window texture coordinates with a non-perspective camera are outside the hot-path "
           "scope";
-  else if ((ctx->svm_features & SVM_USES_ATTRIBUTES) && ctx->has_subd_patches)
+  else if (ctx->has_subd_patches &&
+           ((ctx->svm_features & SVM_USES_ATTRIBUTES) ||
+            ((ctx->svm_features & SVM_USES_TANGENT) && ctx->has_generated_attr)))
     why = "attributes on subdivision patches are outside the hot-path scope";
   const HostArray *sh = find_global(ctx, "__shaders");
   if (why.empty() && sh && sh->bytes / SIZEOF_KERNEL_SHADER > WF_MAX_KEYS - 1)
@@ -1590,6 +1631,7 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
     }
   }
   const bool transparent_shadows = kd_host<int>(ctx, KD_INT_TRANSPARENT_SHADOWS) != 0;
+  const bool svm_ext = (ctx->svm_features & SVM_USES_EXTENDED_NODES) != 0;
   rc = ensure_pool(ctx, std::max<size_t>(capacity, (size_t)tile->w), transparent_shadows);
   if (rc)
     return rc;
@@ -1650,8 +1692,14 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
         k_sort_count<<<grid_wide, WF_BLOCK, 0, st>>>(soa);
         k_sort_scan<<<1, 256, 0, st>>>(soa, num_keys);
         k_sort_scatter<<<grid_wide, WF_BLOCK, 0, st>>>(soa);
-        k_shade_background<<<grid_wide, WF_BLOCK, 0, st>>>(soa);
-        k_shade_surface<<<grid_wide, WF_BLOCK, 0, st>>>(soa, num_keys);
+        if (svm_ext) {
+          k_shade_background<true><<<grid_wide, WF_BLOCK, 0, st>>>(soa);
+          k_shade_surface<true><<<grid_wide, WF_BLOCK, 0, st>>>(soa, num_keys);
+        }
+        else {
+          k_shade_background<false><<<grid_wide, WF_BLOCK, 0, st>>>(soa);
+          k_shade_surface<false><<<grid_wide, WF_BLOCK, 0, st>>>(soa, num_keys);
+        }
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev3, st));
         if (transparent_shadows)
           k_intersect_shadow<false, true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
@@ -1668,7 +1716,10 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
           int cur = 0;
           while (pool->h_counters->n_ts[cur] != 0) {
             k_intersect_shadow_step<<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, cur, refill);
-            k_shade_shadow_step<<<grid_wide, WF_BLOCK, 0, st>>>(soa, cur);
+            if (svm_ext)
+              k_shade_shadow_step<true><<<grid_wide, WF_BLOCK, 0, st>>>(soa, cur);
+            else
+              k_shade_shadow_step<false><<<grid_wide, WF_BLOCK, 0, st>>>(soa, cur);
             k_shadow_step_end<<<1, 1, 0, st>>>(soa, cur);
             stats.kernel_launches += 3;
             CUDA_TRY(ctx, cudaMemcpyAsync(pool->h_counters, soa.counters, 64,
@@ -1728,7 +1779,20 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
     stats.closest_ms = closest_ms;
     stats.shadow_ms = shadow_ms;
   }
+  stats.svm_extended = svm_ext ? 1 : 0;
   ctx->stats = stats;
+  if (!svm_ext) {
+    /* the lean shading kernels ran: no shader may have needed the full interpreter */
+    unsigned int miss = 0;
+    CUDA_TRY(ctx, cudaMemcpyFromSymbol(&miss, g_svm_scope_miss, sizeof(miss)));
+    if (miss) {
+      const unsigned int zero = 0;
+      cudaMemcpyToSymbol(g_svm_scope_miss, &zero, sizeof(zero));
+      return fail(ctx, B200_ERR_UNSUPPORTED,
+                  "a shader needed the full SVM interpreter although the program scan found "
+                  "no extended node (frame discarded)");
+    }
+  }
   return B200_OK;
 }
 

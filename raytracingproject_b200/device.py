@@ -55,7 +55,8 @@ class Stats(C.Structure):
                 ("shadow_instances", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("closest_launches", C.c_uint64),
                 ("shadow_launches", C.c_uint64),
-                ("device_ms", C.c_double), ("closest_ms", C.c_double), ("shadow_ms", C.c_double)]
+                ("device_ms", C.c_double), ("closest_ms", C.c_double), ("shadow_ms", C.c_double),
+                ("svm_extended", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

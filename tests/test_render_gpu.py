@@ -12,6 +12,7 @@ from scene_cases import (camera_cases, closure_cases, light_cases, principled_ca
 pytestmark = pytest.mark.gpu
 
 SPP = 16
+W_SMALL, H_SMALL = 256, 144
 
 
 def luminance(img):
@@ -57,6 +58,8 @@ def test_principled_image_matches_reference(ref, device, name):
         ref_img, _ = rs.render(0, SPP, tile_size=64)
         got = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP)
         print(name, device.stats())
+        # no texture / attribute node, sheen a constant zero: the lean shading kernels ran
+        assert device.stats()["svm_extended"] == 0
         image_gates(ref_img, got, SPP, name)
     finally:
         rs.close()
@@ -121,7 +124,27 @@ def test_texture_nodes_match_reference(ref, device, name):
         ref_img, _ = rs.render(0, SPP, tile_size=64)
         got = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP)
         assert ref_img[..., :3].max() > 0.0
+        assert device.stats()["svm_extended"] == 1  # the full-interpreter kernels ran
         image_gates(ref_img, got, SPP, name)
+    finally:
+        rs.close()
+
+
+def test_sheen_alone_selects_the_full_interpreter(ref, device):
+    """A Principled BSDF with sheen and no texture node: the host's scan of the program
+    (constant inputs of the closure node) must route it to the full interpreter."""
+    from raytracingproject_b200 import scenes
+    desc = scenes.cornell(W_SMALL, H_SMALL, materials="principled")
+    assert 'name="p" distribution="GGX"' in desc.xml
+    desc.xml = desc.xml.replace('<principled_bsdf name="p" ', '<principled_bsdf name="p" sheen="0.7" '
+                                'sheen_tint="0.3" ')
+    rs = ref.build_scene(desc)
+    try:
+        device.upload_scene(rs.device_arrays())
+        ref_img, _ = rs.render(0, SPP, tile_size=64)
+        got = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP)
+        assert device.stats()["svm_extended"] == 1
+        image_gates(ref_img, got, SPP, "principled with sheen")
     finally:
         rs.close()
 

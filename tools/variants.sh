@@ -2,7 +2,7 @@
 # Build compile-time variants of libb200cycles.so for A/B runs on the GPU box.
 #   tools/variants.sh build name1 "-DFOO=1" name2 "-DBAR=2" ...   (here, no GPU needed)
 #   tools/variants.sh run name1 name2 ...                         (on the box; prints one line each)
-set -e
+set -e; set +e
 cd "$(dirname "$0")/.."
 mode=$1; shift
 B=raytracingproject_b200/_build
