@@ -170,9 +170,38 @@ CY_DEV void cmj_sample_2D(int s, int N, uint32_t p, float *fx, float *fy)
   *fy = ((float)s + jy) * invN;
 }
 
-/* kernel/kernel_random.h:53-127: Sobol with a Cranley-Patterson rotation, or CMJ */
+/* kernel_jitter.h:198-232: progressive multi-jitter from the host's table
+ * (__sample_pattern_lut: NUM_PMJ_PATTERNS x NUM_PMJ_SAMPLES 2D points as floats in
+ * [1, 2)), scrambled per pixel and dimension by xor on the mantissa; beyond the table
+ * it falls back to hashed random numbers */
+CY_DEV float pmj_sample_1D(int sample, uint32_t rng_hash, int dimension)
+{
+  if (sample >= CY_NUM_PMJ_SAMPLES)
+    return cmj_randfloat((uint32_t)sample, rng_hash + (uint32_t)dimension);
+  const uint32_t mask = cmj_hash_simple((uint32_t)dimension, rng_hash) & 0x007fffffu;
+  const int index = ((dimension % CY_NUM_PMJ_PATTERNS) * CY_NUM_PMJ_SAMPLES + sample) * 2;
+  return __uint_as_float(__ldg(&g_scene.sample_pattern_lut[index]) ^ mask) - 1.0f;
+}
+CY_DEV void pmj_sample_2D(int sample, uint32_t rng_hash, int dimension, float *fx, float *fy)
+{
+  if (sample >= CY_NUM_PMJ_SAMPLES) {
+    const uint32_t p = rng_hash + (uint32_t)dimension;
+    *fx = cmj_randfloat((uint32_t)sample, p);
+    *fy = cmj_randfloat((uint32_t)sample, p + 1);
+    return;
+  }
+  const int index = ((dimension % CY_NUM_PMJ_PATTERNS) * CY_NUM_PMJ_SAMPLES + sample) * 2;
+  const uint32_t maskx = cmj_hash_simple((uint32_t)dimension, rng_hash) & 0x007fffffu;
+  const uint32_t masky = cmj_hash_simple((uint32_t)dimension + 1, rng_hash) & 0x007fffffu;
+  *fx = __uint_as_float(__ldg(&g_scene.sample_pattern_lut[index]) ^ maskx) - 1.0f;
+  *fy = __uint_as_float(__ldg(&g_scene.sample_pattern_lut[index + 1]) ^ masky) - 1.0f;
+}
+
+/* kernel/kernel_random.h:53-127: PMJ, CMJ, or Sobol with a Cranley-Patterson rotation */
 CY_DEV float path_rng_1D(uint32_t rng_hash, int sample, int dimension)
 {
+  if (kd_int(KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_PMJ)
+    return pmj_sample_1D(sample, rng_hash, dimension);
   if (kd_int(KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_CMJ)
     return cmj_sample_1D(sample, kd_int(KD_INT_AA_SAMPLES), rng_hash + (uint32_t)dimension);
   uint32_t result = sobol_dimension(sample, dimension);
@@ -183,6 +212,10 @@ CY_DEV float path_rng_1D(uint32_t rng_hash, int sample, int dimension)
 }
 CY_DEV void path_rng_2D(uint32_t rng_hash, int sample, int dimension, float *fx, float *fy)
 {
+  if (kd_int(KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_PMJ) {
+    pmj_sample_2D(sample, rng_hash, dimension, fx, fy);
+    return;
+  }
   if (kd_int(KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_CMJ) {
     cmj_sample_2D(sample, kd_int(KD_INT_AA_SAMPLES), rng_hash + (uint32_t)dimension, fx, fy);
     return;
@@ -644,6 +677,12 @@ __device__ __noinline__ int svm_eval_extended_node(ShaderDataG &sd, float *stack
       break;
     case CY_NODE_TEX_NOISE:
       svm_node_tex_noise(stack, node, &offset);
+      break;
+    case CY_NODE_TEX_MUSGRAVE:
+      svm_node_tex_musgrave(stack, node, &offset);
+      break;
+    case CY_NODE_TEX_VORONOI:
+      svm_node_tex_voronoi(stack, node, &offset);
       break;
     case CY_NODE_TEX_CHECKER:
       svm_node_tex_checker(stack, node);

@@ -1012,4 +1012,6 @@ SVM_TEX_FN void svm_node_tex_white_noise(float *stack, uint4 node)
     stack[value_offset] = value;
 }
 
+#include "svm_tex_cells.cuh"
+
 #endif /* B200_SVM_TEX_CUH */

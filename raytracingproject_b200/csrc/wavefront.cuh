@@ -1439,6 +1439,8 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
       case CY_NODE_MIN_MAX:
       case CY_NODE_TEX_NOISE:
       case CY_NODE_TEX_WAVE:
+      case CY_NODE_TEX_MUSGRAVE:
+      case CY_NODE_TEX_VORONOI:
         *features |= SVM_USES_EXTENDED_NODES;
         i += 3;
         break;
@@ -1534,7 +1536,7 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
               "glossy-GGX/emission/background, mix closure, value, geometry, convert, fresnel, "
               "layer weight, math, vector math, mix, invert, gamma, bright/contrast, "
               "separate/combine, clamp, light path, light falloff, RGB ramp, curves, attribute, "
-              "texture coordinate, mapping, noise/wave/magic/checker/brick/gradient/white noise "
+              "texture coordinate, mapping, noise/wave/magic/checker/brick/gradient/white noise/musgrave/voronoi "
               "textures, HSV, map range, normal, vector rotate/transform, object info, camera)";
         return false;
     }
@@ -1560,8 +1562,14 @@ static int check_scope(b200_ctx *ctx)
   else if (I(KD_BVH_HAVE_CURVES))
     why = "hair curves are outside the hot-path scope";
   else if (I(KD_INT_SAMPLING_PATTERN) != CY_SAMPLING_PATTERN_SOBOL &&
-           I(KD_INT_SAMPLING_PATTERN) != CY_SAMPLING_PATTERN_CMJ)
-    why = "the PMJ sampling pattern is outside the hot-path scope (Sobol and CMJ are in)";
+           I(KD_INT_SAMPLING_PATTERN) != CY_SAMPLING_PATTERN_CMJ &&
+           I(KD_INT_SAMPLING_PATTERN) != CY_SAMPLING_PATTERN_PMJ)
+    why = "unknown sampling pattern";
+  else if (I(KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_PMJ &&
+           (!find_global(ctx, "__sample_pattern_lut") ||
+            find_global(ctx, "__sample_pattern_lut")->bytes <
+                (size_t)CY_NUM_PMJ_PATTERNS * CY_NUM_PMJ_SAMPLES * 2 * 4))
+    why = "the PMJ sampling pattern needs the __sample_pattern_lut table";
   else if (I(KD_INT_BRANCHED))
     why = "branched path tracing is outside the hot-path scope";
   else if (I(KD_INT_USE_VOLUMES))

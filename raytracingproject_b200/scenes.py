@@ -300,6 +300,70 @@ def _textured_shaders(variant):
             'roughness="0.4" clearcoat="1.0" clearcoat_roughness="0.05" metallic="0.3"/>\n'
             '  <mix_closure name="m"/>\n' + c("gr fac", "m fac") +
             c("p1 bsdf", "m closure1") + c("p2 bsdf", "m closure2"), "m closure")
+    elif variant == 3:
+        # Voronoi (every feature, 1D-4D, all metrics) and Musgrave (all five types)
+        white = _node_shader(
+            "white", '  <texture_coordinate name="tc"/>\n'
+            '  <voronoi_texture name="t" dimensions="3D" feature="f1" metric="euclidean" '
+            'scale="3.0" randomness="0.9"/>\n' + c("tc generated", "t vector") +
+            '  <mix name="mx" type="mix" color1="0.73 0.73 0.73" fac="0.5"/>\n' +
+            c("t color", "mx color2") + '  <diffuse_bsdf name="d"/>\n' + c("mx color", "d color"),
+            "d bsdf")
+        red = _node_shader(
+            "red", '  <texture_coordinate name="tc"/>\n'
+            '  <voronoi_texture name="t" dimensions="2D" feature="smooth_f1" metric="manhattan" '
+            'scale="4.0" smoothness="0.6"/>\n' + c("tc object", "t vector") +
+            '  <voronoi_texture name="t1" dimensions="1D" feature="f2" scale="6.0"/>\n'
+            '  <separate_xyz name="sep"/>\n' + c("tc object", "sep vector") + c("sep z", "t1 w") +
+            '  <mix name="mx" type="mix" color1="0.65 0.05 0.05" color2="0.9 0.7 0.2"/>\n' +
+            c("t distance", "mx fac") +
+            '  <mix name="mx2" type="multiply" fac="0.7"/>\n' + c("mx color", "mx2 color1") +
+            c("t1 color", "mx2 color2") + '  <diffuse_bsdf name="d"/>\n' + c("mx2 color", "d color"),
+            "d bsdf")
+        green = _node_shader(
+            "green", '  <texture_coordinate name="tc"/>\n'
+            '  <musgrave_texture name="t" dimensions="3D" type="fBM" scale="2.5" detail="3.5" '
+            'dimension="1.2" lacunarity="2.1"/>\n' + c("tc object", "t vector") +
+            '  <musgrave_texture name="t2" dimensions="2D" type="multifractal" scale="3.0" '
+            'detail="2.0" dimension="0.8" lacunarity="1.9"/>\n' + c("tc object", "t2 vector") +
+            '  <math name="m" type="multiply_add" value2="0.3" value3="0.5"/>\n' +
+            c("t fac", "m value1") + '  <math name="m2" type="multiply" value2="0.4"/>\n' +
+            c("t2 fac", "m2 value1") + '  <combine_xyz name="cmb" x="0.12"/>\n' +
+            c("m value", "cmb y") + c("m2 value", "cmb z") + '  <diffuse_bsdf name="d"/>\n' +
+            c("cmb vector", "d color"), "d bsdf")
+        metal = _node_shader(
+            "metal", '  <texture_coordinate name="tc"/>\n'
+            '  <voronoi_texture name="t" dimensions="3D" feature="distance_to_edge" scale="3.0"/>\n' +
+            c("tc object", "t vector") +
+            '  <voronoi_texture name="t4" dimensions="4D" feature="n_sphere_radius" scale="2.5" '
+            'w="0.4"/>\n' + c("tc object", "t4 vector") +
+            '  <voronoi_texture name="t3" dimensions="3D" feature="f2" metric="chebychev" '
+            'scale="2.0"/>\n' + c("tc object", "t3 vector") +
+            '  <combine_xyz name="cmb"/>\n' + c("t distance", "cmb x") + c("t4 radius", "cmb y") +
+            c("t3 distance", "cmb z") +
+            '  <glossy_bsdf name="g" distribution="GGX" roughness="0.3"/>\n' +
+            c("cmb vector", "g color"), "g bsdf")
+        glass = _node_shader(
+            "glass", '  <texture_coordinate name="tc"/>\n'
+            '  <musgrave_texture name="t" dimensions="4D" type="ridged_multifractal" scale="2.0" '
+            'detail="3.0" dimension="1.0" lacunarity="2.0" offset="1.0" gain="2.0" w="0.3"/>\n' +
+            c("tc generated", "t vector") +
+            '  <musgrave_texture name="t2" dimensions="2D" type="hetero_terrain" scale="2.0" '
+            'detail="2.5" dimension="1.0" lacunarity="2.0" offset="0.5"/>\n' +
+            c("tc generated", "t2 vector") +
+            '  <musgrave_texture name="t3" dimensions="1D" type="hybrid_multifractal" scale="3.0" '
+            'detail="2.0" dimension="1.0" lacunarity="2.0" offset="0.6" gain="1.5"/>\n'
+            '  <separate_xyz name="sep"/>\n' + c("tc generated", "sep vector") + c("sep x", "t3 w") +
+            '  <voronoi_texture name="v" dimensions="4D" feature="f1" metric="minkowski" '
+            'exponent="1.5" scale="2.0" w="0.2"/>\n' + c("tc generated", "v vector") +
+            '  <combine_xyz name="cmb"/>\n' + c("t fac", "cmb x") + c("t2 fac", "cmb y") +
+            c("t3 fac", "cmb z") +
+            '  <mix name="mx" type="mix" fac="0.5"/>\n' + c("cmb vector", "mx color1") +
+            c("v position", "mx color2") +
+            '  <vector_math name="ab" type="absolute"/>\n' + c("mx color", "ab vector1") +
+            '  <vector_math name="fr" type="fraction"/>\n' + c("ab vector", "fr vector1") +
+            '  <principled_bsdf name="p" distribution="GGX" roughness="0.5"/>\n' +
+            c("fr vector", "p base_color"), "p bsdf")
     elif variant == 2:
         # colour / range / vector / info nodes: HSV, separate + combine HSV, the HSV and
         # dodge / burn blend modes, map range (all four kinds), normal, vector rotate,
@@ -629,8 +693,8 @@ def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
                    nearclip=0.01, farclip=100.0, cam_type=cam_type, cam_extra=cam_extra)
     xml += _background((0, 0, 0), 0.0)
     closure_variants = {"closures": 0, "closures2": 1, "transparent_opaque_shadow": 2,
-                        "transparent": 3, "textured": 10, "textured2": 11, "textured3": 12}
-    if materials in ("textured", "textured2", "textured3"):
+                        "transparent": 3, "textured": 10, "textured2": 11, "textured3": 12, "textured4": 13}
+    if materials in ("textured", "textured2", "textured3", "textured4"):
         xml += _textured_shaders(closure_variants[materials] - 10)
     elif materials in closure_variants:
         xml += _closure_shaders(closure_variants[materials])

@@ -123,6 +123,12 @@ extern "C" __attribute__((visibility("default"))) int host_svm_node(int offset, 
     case CY_NODE_TEX_WHITE_NOISE:
       svm_node_tex_white_noise(stack, node);
       break;
+    case CY_NODE_TEX_MUSGRAVE:
+      svm_node_tex_musgrave(stack, node, &offset);
+      break;
+    case CY_NODE_TEX_VORONOI:
+      svm_node_tex_voronoi(stack, node, &offset);
+      break;
     case CY_NODE_OBJECT_INFO:
       svm_node_object_info(sd, stack, node);
       break;

@@ -28,6 +28,8 @@ def sampling_cases():
     return {
         "cornell_cmj16": scenes.cornell(W, H, spp=16, materials="diffuse", pattern="cmj"),
         "cornell_cmj12": scenes.cornell(W, H, spp=12, materials="principled", pattern="cmj"),
+        # progressive multi-jitter: the host's 48 x 4096-point table, xor-scrambled
+        "cornell_pmj": scenes.cornell(W, H, spp=16, materials="principled", pattern="pmj"),
     }
 
 
@@ -92,6 +94,8 @@ def texture_cases():
         "cornell_textured2": scenes.cornell(W, H, materials="textured2"),
         # HSV / map range / vector rotate + transform / object info / camera / white noise
         "cornell_textured3": scenes.cornell(W, H, materials="textured3"),
+        # Voronoi (five features, 1D-4D, four metrics) and Musgrave (five types)
+        "cornell_textured4": scenes.cornell(W, H, materials="textured4"),
         # the same programs under a lamp-less mesh light (emissive-triangle MIS evaluates
         # the surface shader with PATH_RAY_EMISSION) and through an orthographic camera
         "cornell_textured_mesh_light": scenes.cornell(W, H, materials="textured", light="mesh"),

@@ -114,7 +114,7 @@ def test_camera_models_match_reference(ref, device, name):
         rs.close()
 
 
-@pytest.mark.parametrize("name", ["cornell_textured", "cornell_textured2", "cornell_textured3",
+@pytest.mark.parametrize("name", ["cornell_textured", "cornell_textured2", "cornell_textured3", "cornell_textured4",
                                   "cornell_textured_mesh_light", "cornell_textured_ortho"])
 def test_texture_nodes_match_reference(ref, device, name):
     desc = texture_cases()[name]
@@ -169,7 +169,7 @@ def scenes_cornell_ortho_textured2():
     return scenes.cornell(64, 48, spp=1, materials="textured2", cam_type="orthograph")
 
 
-@pytest.mark.parametrize("name", ["cornell_cmj16", "cornell_cmj12"])
+@pytest.mark.parametrize("name", ["cornell_cmj16", "cornell_cmj12", "cornell_pmj"])
 def test_cmj_sampling_matches_reference(ref, device, name):
     desc = sampling_cases()[name]
     rs = ref.build_scene(desc)

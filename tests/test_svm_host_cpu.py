@@ -111,6 +111,7 @@ def texture_ops():
                               "NODE_MAP_RANGE", "NODE_NORMAL", "NODE_VECTOR_ROTATE",
                               "NODE_VECTOR_TRANSFORM", "NODE_OBJECT_INFO", "NODE_CAMERA",
                               "NODE_TEX_WHITE_NOISE", "NODE_MIX", "NODE_MATH",
+                              "NODE_TEX_VORONOI", "NODE_TEX_MUSGRAVE",
                               "NODE_VECTOR_MATH", "NODE_CONVERT", "NODE_INVERT", "NODE_GAMMA",
                               "NODE_BRIGHTCONTRAST", "NODE_CLAMP", "NODE_FRESNEL",
                               "NODE_LAYER_WEIGHT", "NODE_RGB_RAMP", "NODE_RGB_CURVES",
@@ -122,7 +123,8 @@ def compare(name, s_ref, s_dev, tol):
     assert not bad.any(), (name, np.nonzero(bad)[0][:8], s_ref[bad][:8], s_dev[bad][:8])
 
 
-@pytest.mark.parametrize("materials", ["textured", "textured2", "textured3", "procedural",
+@pytest.mark.parametrize("materials", ["textured", "textured2", "textured3", "textured4",
+                                       "procedural",
                                        "node_chart"])
 def test_compiled_texture_nodes_match_reference(ref, host_lib, materials):
     desc = scenes.node_chart() if materials == "node_chart" else \
@@ -184,6 +186,7 @@ def test_compiled_texture_nodes_match_reference(ref, host_lib, materials):
                               "NODE_VECTOR_TRANSFORM", "NODE_OBJECT_INFO", "NODE_CAMERA",
                               "NODE_TEX_WHITE_NOISE", "NODE_MIX", "NODE_MATH",
                               "NODE_VECTOR_MATH"},
+                "textured4": {"NODE_TEX_VORONOI", "NODE_TEX_MUSGRAVE", "NODE_TEX_COORD"},
                 "procedural": {"NODE_MATH", "NODE_VECTOR_MATH", "NODE_MIX", "NODE_CLAMP",
                                "NODE_GAMMA", "NODE_INVERT", "NODE_BRIGHTCONTRAST",
                                "NODE_FRESNEL", "NODE_LAYER_WEIGHT"},
@@ -220,6 +223,10 @@ VALUE_NODE_SPECS = {
     "NODE_OBJECT_INFO": {"yzw": (5, O, O)},
     "NODE_CAMERA": {"yzw": (O, O, O)},
     "NODE_TEX_WHITE_NOISE": {"yzw": ("dims", "packed", "packed")},
+    "NODE_TEX_MUSGRAVE": {"yzw": ((5, "dims", O, O), "packed", "packed"),
+                          "extra": [("float",) * 4, ("float",) * 4]},
+    "NODE_TEX_VORONOI": {"yzw": ("dims", 5, 4),
+                         "extra": [("packed", "packed", "packed", "float"), ("float",) * 4]},
 }
 
 
@@ -274,7 +281,8 @@ def random_program(op_name, rng, a):
             if isinstance(kind, int):
                 prog[0, col] = rng.integers(0, kind)
             elif isinstance(kind, tuple):  # packed bytes: ints are enum ranges
-                prog[0, col] = pack(*[rng.integers(0, k) if isinstance(k, int) else used()
+                prog[0, col] = pack(*[rng.integers(0, k) if isinstance(k, int) else
+                                      (int(rng.integers(1, 5)) if k == "dims" else used())
                                       for k in kind])
             else:
                 prog[0, col] = word[kind]()
@@ -283,9 +291,28 @@ def random_program(op_name, rng, a):
             # the other one uninitialised (svm_math_util.h svm_vector_math)
             scalar = int(prog[0, 1]) in (7, 8, 9)  # dot product, distance, length
             prog[0, 3] = pack(used(), 255) if scalar else pack(255, used())
+        if op_name == "NODE_TEX_MUSGRAVE":
+            # parameters from the node's defaults (sane ranges): a negative lacunarity or
+            # dimension from a random stack slot turns the fractal sums into an amplifier
+            # of the 1e-7 differences between the SSE and the scalar Perlin noise
+            prog[0, 2] = pack(255, 255, 255, 255)
+            prog[0, 3] = pack(255, 255, used())
         for row, kinds in enumerate(spec.get("extra", []), start=1):
             for col, kind in enumerate(kinds):
                 prog[row, col] = rng.integers(0, kind) if isinstance(kind, int) else word[kind]()
+    if op_name == "NODE_TEX_VORONOI":
+        # outputs a feature does not define stay unassigned (the reference leaves its
+        # position locals uninitialised for distance-to-edge / n-sphere radius)
+        feature, dims = int(prog[0, 2]), int(prog[0, 1])
+        cells = feature in (0, 1, 2)
+        prog[1, 0] = pack(used(), slot(), slot(), slot())
+        prog[1, 1] = pack(slot(), slot(), used() if feature != 4 else 255,
+                          used() if cells else 255)
+        prog[1, 2] = pack(used() if cells and dims != 1 else 255,
+                          used() if cells and dims in (1, 4) else 255,
+                          used() if feature == 4 else 255)
+        prog[1, 3] = fbits(-2, 2)
+        prog[2] = [fbits(0.5, 4), fbits(0.1, 1.5), fbits(0.5, 3), fbits(0, 1.2)]
     elif op_name == "NODE_TEX_COORD":
         kind = int(rng.choice([0, 1, 1, 2, 3, 4]))
         prog[0, 1:] = [kind, used(), int(kind == 1 and rng.random() < 0.5)]
@@ -322,7 +349,7 @@ def test_random_node_encodings_match_reference(ref, host_lib, op_name):
 
 
 def test_scope_check_without_a_device(ref):
-    """b200_validate_svm: programs of the supported scenes pass, a Voronoi texture or a
+    """b200_validate_svm: programs of the supported scenes pass, a Blackbody node or a
     truncated program is refused with a reason - on the host, no GPU involved."""
     from raytracingproject_b200.device import validate_svm
     for materials in ("principled", "closures", "procedural", "textured", "textured2",
@@ -335,7 +362,13 @@ def test_scope_check_without_a_device(ref):
     desc = scenes.cornell(64, 36, materials="diffuse")
     desc.xml = desc.xml.replace(
         '  <diffuse_bsdf name="d" color="0.73 0.73 0.73"/>\n',
-        '  <diffuse_bsdf name="d"/>\n  <voronoi_texture name="m" scale="3.0"/>\n'
+        '  <diffuse_bsdf name="d"/>\n  <geometry name="g"/>\n'
+        '  <vector_math name="l" type="length"/>\n'
+        '  <connect from="g position" to="l vector1"/>\n'
+        '  <math name="t" type="multiply_add" value2="1500" value3="2500"/>\n'
+        '  <connect from="l value" to="t value1"/>\n'
+        '  <blackbody name="m"/>\n'
+        '  <connect from="t value" to="m temperature"/>\n'
         '  <connect from="m color" to="d color"/>\n', 1)
     rs = ref.build_scene(desc)
     try:

@@ -45,17 +45,21 @@ def test_procedural_material_image(ref, device):
 
 
 def test_unsupported_node_is_refused(ref, device):
-    """A node outside the supported subset (Voronoi texture) is refused when its program
+    """A node outside the supported subset (Blackbody) is refused when its program
     is bound - never skipped or approximated."""
     from raytracingproject_b200.device import DeviceError
     desc = scenes.cornell(64, 36, materials="diffuse")
     desc.xml = desc.xml.replace(
         '  <diffuse_bsdf name="d" color="0.73 0.73 0.73"/>\n',
         '  <diffuse_bsdf name="d"/>\n  <geometry name="g"/>\n'
-        '  <voronoi_texture name="m" scale="3.0"/>\n'
-        '  <connect from="g position" to="m vector"/>\n'
+        '  <vector_math name="l" type="length"/>\n'
+        '  <connect from="g position" to="l vector1"/>\n'
+        '  <math name="t" type="multiply_add" value2="1500" value3="2500"/>\n'
+        '  <connect from="l value" to="t value1"/>\n'
+        '  <blackbody name="m"/>\n'
+        '  <connect from="t value" to="m temperature"/>\n'
         '  <connect from="m color" to="d color"/>\n', 1)
-    assert "voronoi_texture" in desc.xml
+    assert "blackbody" in desc.xml
     rs = ref.build_scene(desc)
     try:
         arrays = rs.device_arrays()
