@@ -422,6 +422,9 @@ int ref_probe_svm_node(KernelGlobals *kg, const void *nodes, int offset, float *
     case NODE_TEX_WHITE_NOISE:
       svm_node_tex_white_noise(kg, sd, stack, node.y, node.z, node.w, &offset);
       break;
+    case NODE_BLACKBODY:
+      svm_node_blackbody(kg, sd, stack, node.y, node.z);
+      break;
     case NODE_TEX_MUSGRAVE:
       svm_node_tex_musgrave(kg, sd, stack, node.y, node.z, node.w, &offset);
       break;

@@ -678,6 +678,9 @@ __device__ __noinline__ int svm_eval_extended_node(ShaderDataG &sd, float *stack
     case CY_NODE_TEX_NOISE:
       svm_node_tex_noise(stack, node, &offset);
       break;
+    case CY_NODE_BLACKBODY:
+      svm_node_blackbody(stack, node);
+      break;
     case CY_NODE_TEX_MUSGRAVE:
       svm_node_tex_musgrave(stack, node, &offset);
       break;

@@ -450,6 +450,24 @@ CY_DEV bool svm_node_closure_bsdf(ShaderDataG &sd, float *stack, uint4 node, uin
         bsdf->alpha_x = roughness;
         bsdf->alpha_y = roughness;
         bsdf->T = zero3();
+        /* the Anisotropic BSDF node: tangent, rotation and anisotropy (svm_closure.h:
+         * 526-545).  Full interpreter only - the host routes programs with a tangent
+         * input here (svm_validate), the lean one never sees them. */
+        if (FULL && stack_valid(data_node.y)) {
+          bsdf->T = stack_load_float3(stack, data_node.y);
+          const float rotation = stack[data_node.z];
+          if (rotation != 0.0f)
+            bsdf->T = rotate_around_axis(bsdf->T, bsdf->N, rotation * CY_M_2PI_F);
+          const float anisotropy = clampf(param2, -0.99f, 0.99f);
+          if (anisotropy < 0.0f) {
+            bsdf->alpha_x = roughness / (1.0f + anisotropy);
+            bsdf->alpha_y = roughness * (1.0f + anisotropy);
+          }
+          else {
+            bsdf->alpha_x = roughness * (1.0f - anisotropy);
+            bsdf->alpha_y = roughness / (1.0f - anisotropy);
+          }
+        }
         if (type == CY_CLOSURE_BSDF_REFLECTION_ID) {
           bsdf->type = CY_CLOSURE_BSDF_REFLECTION_ID;
           sd.flag |= CY_SD_BSDF;

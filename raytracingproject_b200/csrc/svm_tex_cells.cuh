@@ -508,4 +508,46 @@ SVM_TEX_FN void svm_node_tex_voronoi(float *stack, uint4 node, int *offset)
     stack[radius_out] = r.radius;
 }
 
+/* --------------------------------------------------------------- Blackbody */
+
+/* svm_blackbody.h + svm_math_blackbody_color (svm_math_util.h:183-250): Rec.709 colour
+ * of a black body, piecewise rational fit in six temperature bands.  The coefficients
+ * are the reference's fit data: per band r = a/t + b t + c, g likewise, b a cubic. */
+SVM_TEX_FN void svm_node_blackbody(float *stack, uint4 node)
+{
+  const float band_from[5] = {1167.0f, 1449.0f, 1902.0f, 3315.0f, 6365.0f};
+  const float fit[6][10] = {
+      {2.52432244e+03f, -1.06185848e-03f, 3.11067539e+00f, -7.50343014e+02f, 3.15679613e-04f,
+       4.73464526e-01f, 0.0f, 0.0f, 0.0f, 0.0f},
+      {3.37763626e+03f, -4.34581697e-04f, 1.64843306e+00f, -1.00402363e+03f, 1.29189794e-04f,
+       9.08181524e-01f, 0.0f, 0.0f, 0.0f, 0.0f},
+      {4.10671449e+03f, -8.61949938e-05f, 6.41423749e-01f, -1.22075471e+03f, 2.56245413e-05f,
+       1.20753416e+00f, 0.0f, 0.0f, 0.0f, 0.0f},
+      {4.66849800e+03f, 2.85655028e-05f, 1.29075375e-01f, -1.42546105e+03f, -4.01730887e-05f,
+       1.44002695e+00f, -2.02524603e-11f, 1.79435860e-07f, -2.60561875e-04f, -1.41761141e-02f},
+      {4.60124770e+03f, 2.89727618e-05f, 1.48001316e-01f, -1.18134453e+03f, -2.18913373e-05f,
+       1.30656109e+00f, -2.22463426e-13f, -1.55078698e-08f, 3.81675160e-04f, -7.30646033e-01f},
+      {3.78765709e+03f, 9.36026367e-06f, 3.98995841e-01f, -5.00279505e+02f, -4.59745390e-06f,
+       1.09090465e+00f, 6.72595954e-13f, -2.73059993e-08f, 4.24068546e-04f, -7.52204323e-01f},
+  };
+  const float t = stack[node.y];
+  f3 rgb;
+  if (t >= 12000.0f) {
+    rgb = mk3(0.826270103f, 0.994478524f, 1.56626022f);
+  }
+  else if (t < 965.0f) {
+    rgb = mk3(4.70366907f, 0.0f, 0.0f);
+  }
+  else {
+    int band = 0;
+    for (int k = 0; k < 5; k++)
+      band += (t >= band_from[k]) ? 1 : 0;
+    const float *c = fit[band];
+    const float t_inv = 1.0f / t;
+    rgb = mk3(c[0] * t_inv + c[1] * t + c[2], c[3] * t_inv + c[4] * t + c[5],
+              ((c[6] * t + c[7]) * t + c[8]) * t + c[9]);
+  }
+  stack_store_float3(stack, node.z, rgb);
+}
+
 #endif /* B200_SVM_TEX_CELLS_CUH */

@@ -1395,6 +1395,7 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
       case CY_NODE_OBJECT_INFO:
       case CY_NODE_CAMERA:
       case CY_NODE_TEX_WHITE_NOISE:
+      case CY_NODE_BLACKBODY:
         *features |= SVM_USES_EXTENDED_NODES;
         i += 1;
         break;
@@ -1509,11 +1510,13 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
         }
         else if (type == CY_CLOSURE_BSDF_REFLECTION_ID ||
                  type == CY_CLOSURE_BSDF_MICROFACET_GGX_ID) {
-          /* the tangent input of the Anisotropic BSDF node is not implemented */
-          if (i + 1 >= n_nodes || nodes[4 * (i + 1) + 1] != (uint32_t)CY_SVM_STACK_INVALID) {
-            why = "anisotropic glossy closures (tangent input) are outside the hot-path scope";
+          /* the Anisotropic BSDF node (a tangent input) runs in the full interpreter */
+          if (i + 1 >= n_nodes) {
+            why = "truncated glossy BSDF node";
             return false;
           }
+          if (nodes[4 * (i + 1) + 1] != (uint32_t)CY_SVM_STACK_INVALID)
+            *features |= SVM_USES_EXTENDED_NODES;
           i += 2;
         }
         else if (type == CY_CLOSURE_BSDF_DIFFUSE_ID || type == CY_CLOSURE_BSDF_TRANSLUCENT_ID ||

@@ -306,8 +306,13 @@ def _textured_shaders(variant):
             "white", '  <texture_coordinate name="tc"/>\n'
             '  <voronoi_texture name="t" dimensions="3D" feature="f1" metric="euclidean" '
             'scale="3.0" randomness="0.9"/>\n' + c("tc generated", "t vector") +
+            '  <math name="tk" type="multiply_add" value2="9000" value3="1000"/>\n' +
+            c("t distance", "tk value1") + '  <blackbody name="bb"/>\n' +
+            c("tk value", "bb temperature") +
+            '  <mix name="mx0" type="multiply" fac="0.3"/>\n' + c("t color", "mx0 color1") +
+            c("bb color", "mx0 color2") +
             '  <mix name="mx" type="mix" color1="0.73 0.73 0.73" fac="0.5"/>\n' +
-            c("t color", "mx color2") + '  <diffuse_bsdf name="d"/>\n' + c("mx color", "d color"),
+            c("mx0 color", "mx color2") + '  <diffuse_bsdf name="d"/>\n' + c("mx color", "d color"),
             "d bsdf")
         red = _node_shader(
             "red", '  <texture_coordinate name="tc"/>\n'
@@ -341,8 +346,8 @@ def _textured_shaders(variant):
             'scale="2.0"/>\n' + c("tc object", "t3 vector") +
             '  <combine_xyz name="cmb"/>\n' + c("t distance", "cmb x") + c("t4 radius", "cmb y") +
             c("t3 distance", "cmb z") +
-            '  <glossy_bsdf name="g" distribution="GGX" roughness="0.3"/>\n' +
-            c("cmb vector", "g color"), "g bsdf")
+            '  <anisotropic_bsdf name="g" distribution="GGX" roughness="0.3" anisotropy="0.6" '
+            'rotation="0.2"/>\n' + c("cmb vector", "g color"), "g bsdf")
         glass = _node_shader(
             "glass", '  <texture_coordinate name="tc"/>\n'
             '  <musgrave_texture name="t" dimensions="4D" type="ridged_multifractal" scale="2.0" '
@@ -425,7 +430,7 @@ def _textured_shaders(variant):
             '  <vector_math name="ad" type="add"/>\n' + c("mx color", "ad vector1") +
             c("oi location", "ad vector2") +
             '  <vector_math name="fr" type="fraction"/>\n' + c("ad vector", "fr vector1") +
-            '  <glossy_bsdf name="gl" distribution="GGX" roughness="0.3"/>\n' +
+            '  <anisotropic_bsdf name="gl" distribution="GGX" roughness="0.3" anisotropy="-0.5"/>\n' +
             c("fr vector", "gl color"), "gl bsdf")
         glass = _node_shader(
             "glass", '  <geometry name="g"/>\n'

@@ -223,6 +223,7 @@ VALUE_NODE_SPECS = {
     "NODE_OBJECT_INFO": {"yzw": (5, O, O)},
     "NODE_CAMERA": {"yzw": (O, O, O)},
     "NODE_TEX_WHITE_NOISE": {"yzw": ("dims", "packed", "packed")},
+    "NODE_BLACKBODY": {"yzw": (O, O, O)},
     "NODE_TEX_MUSGRAVE": {"yzw": ((5, "dims", O, O), "packed", "packed"),
                           "extra": [("float",) * 4, ("float",) * 4]},
     "NODE_TEX_VORONOI": {"yzw": ("dims", 5, 4),
@@ -337,6 +338,8 @@ def test_random_node_encodings_match_reference(ref, host_lib, op_name):
             prog = random_program(op_name, rng, a)
             bound = Bound(host_lib, arrays, prog)
             stack0 = rng.uniform(-2.0, 2.0, 264).astype(np.float32)
+            if op_name == "NODE_BLACKBODY":  # temperatures across all six bands
+                stack0 = rng.uniform(500.0, 14000.0, 264).astype(np.float32)
             pt = pts[trial % len(pts):trial % len(pts) + 1]
             n_ref, n_dev, s_ref, s_dev = run_both(host_lib, rs, prog, 0, stack0, pt)
             assert n_ref == n_dev and n_ref > 0, (op_name, trial, n_ref, n_dev)
@@ -349,7 +352,7 @@ def test_random_node_encodings_match_reference(ref, host_lib, op_name):
 
 
 def test_scope_check_without_a_device(ref):
-    """b200_validate_svm: programs of the supported scenes pass, a Blackbody node or a
+    """b200_validate_svm: programs of the supported scenes pass, a Wavelength node or a
     truncated program is refused with a reason - on the host, no GPU involved."""
     from raytracingproject_b200.device import validate_svm
     for materials in ("principled", "closures", "procedural", "textured", "textured2",
@@ -365,10 +368,10 @@ def test_scope_check_without_a_device(ref):
         '  <diffuse_bsdf name="d"/>\n  <geometry name="g"/>\n'
         '  <vector_math name="l" type="length"/>\n'
         '  <connect from="g position" to="l vector1"/>\n'
-        '  <math name="t" type="multiply_add" value2="1500" value3="2500"/>\n'
+        '  <math name="t" type="multiply_add" value2="100" value3="450"/>\n'
         '  <connect from="l value" to="t value1"/>\n'
-        '  <blackbody name="m"/>\n'
-        '  <connect from="t value" to="m temperature"/>\n'
+        '  <wavelength name="m"/>\n'
+        '  <connect from="t value" to="m wavelength"/>\n'
         '  <connect from="m color" to="d color"/>\n', 1)
     rs = ref.build_scene(desc)
     try:

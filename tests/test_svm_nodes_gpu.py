@@ -45,7 +45,7 @@ def test_procedural_material_image(ref, device):
 
 
 def test_unsupported_node_is_refused(ref, device):
-    """A node outside the supported subset (Blackbody) is refused when its program
+    """A node outside the supported subset (Wavelength) is refused when its program
     is bound - never skipped or approximated."""
     from raytracingproject_b200.device import DeviceError
     desc = scenes.cornell(64, 36, materials="diffuse")
@@ -54,12 +54,12 @@ def test_unsupported_node_is_refused(ref, device):
         '  <diffuse_bsdf name="d"/>\n  <geometry name="g"/>\n'
         '  <vector_math name="l" type="length"/>\n'
         '  <connect from="g position" to="l vector1"/>\n'
-        '  <math name="t" type="multiply_add" value2="1500" value3="2500"/>\n'
+        '  <math name="t" type="multiply_add" value2="100" value3="450"/>\n'
         '  <connect from="l value" to="t value1"/>\n'
-        '  <blackbody name="m"/>\n'
-        '  <connect from="t value" to="m temperature"/>\n'
+        '  <wavelength name="m"/>\n'
+        '  <connect from="t value" to="m wavelength"/>\n'
         '  <connect from="m color" to="d color"/>\n', 1)
-    assert "blackbody" in desc.xml
+    assert "wavelength" in desc.xml
     rs = ref.build_scene(desc)
     try:
         arrays = rs.device_arrays()
