@@ -111,7 +111,7 @@ def texture_ops():
                               "NODE_MAP_RANGE", "NODE_NORMAL", "NODE_VECTOR_ROTATE",
                               "NODE_VECTOR_TRANSFORM", "NODE_OBJECT_INFO", "NODE_CAMERA",
                               "NODE_TEX_WHITE_NOISE", "NODE_MIX", "NODE_MATH",
-                              "NODE_TEX_VORONOI", "NODE_TEX_MUSGRAVE",
+                              "NODE_TEX_VORONOI", "NODE_TEX_MUSGRAVE", "NODE_BLACKBODY",
                               "NODE_VECTOR_MATH", "NODE_CONVERT", "NODE_INVERT", "NODE_GAMMA",
                               "NODE_BRIGHTCONTRAST", "NODE_CLAMP", "NODE_FRESNEL",
                               "NODE_LAYER_WEIGHT", "NODE_RGB_RAMP", "NODE_RGB_CURVES",
