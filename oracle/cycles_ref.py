@@ -69,6 +69,9 @@ def lib():
             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.ref_init.argtypes = [C.c_int]
         L.ref_path_dump.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.ref_svm_closure.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_uint, C.c_void_p, C.c_float, C.c_float,
+                                      C.c_void_p, C.c_void_p]
         L.ref_svm_node.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p]
         L.ref_count_rays.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -224,6 +227,20 @@ class RefScene:
         self._check(self._L.ref_svm_node(self._h, nodes.ctypes.data, int(offset),
                                          stack.ctypes.data, point.ctypes.data, C.byref(nxt)))
         return nxt.value
+
+    def svm_closure(self, nodes, offset, stack, point, closure_weight, path_flag, omega_in,
+                    randu, randv):
+        """NODE_CLOSURE_BSDF at `offset` through the reference, then bsdf_eval(omega_in) and
+        bsdf_sample(randu, randv) on every closure: (next offset, float32[1 + 20 * 32])."""
+        out = np.zeros(1 + 20 * 32, np.float32)
+        nxt = C.c_int(-1)
+        w = np.ascontiguousarray(closure_weight, np.float32)
+        wi = np.ascontiguousarray(omega_in, np.float32)
+        self._check(self._L.ref_svm_closure(self._h, nodes.ctypes.data, int(offset),
+                                            stack.ctypes.data, point.ctypes.data, w.ctypes.data,
+                                            int(path_flag), wi.ctypes.data, float(randu),
+                                            float(randv), out.ctypes.data, C.byref(nxt)))
+        return nxt.value, out
 
     def count_rays(self, start_sample, num_samples):
         """(camera, bounce, shadow) rays the reference traces for these samples."""

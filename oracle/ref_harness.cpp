@@ -606,6 +606,23 @@ int ref_svm_node(ref_scene *rs, const void *nodes, int offset, float *stack,
   return 0;
 }
 
+int ref_svm_closure(ref_scene *rs, const void *nodes, int offset, float *stack,
+                    const RefShadingPoint *p, const float *closure_weight,
+                    unsigned int path_flag, const float *omega_in, float randu, float randv,
+                    float *out, int *next)
+{
+  if (!rs->cpu)
+    return 1;
+  KernelGlobals kg = rs->cpu->kg_init();
+  {
+    ScopedFlushToZero ftz;
+    *next = ref_probe_svm_closure(&kg, nodes, offset, stack, p, closure_weight, path_flag,
+                                  omega_in, randu, randv, out);
+  }
+  rs->cpu->kg_free(&kg);
+  return 0;
+}
+
 int ref_shadow_rays(ref_scene *rs, int sample, int x0, int y0, int w, int h, RefProbeRay *rays)
 {
   if (!rs->cpu)

@@ -502,5 +502,57 @@ int ref_probe_svm_node(KernelGlobals *kg, const void *nodes, int offset, float *
   return offset;
 }
 
+/* NODE_CLOSURE_BSDF at `offset` through the reference's svm_node_closure_bsdf, then the
+ * reference's bsdf_eval / bsdf_sample on every closure it made.  Output layout as
+ * host_svm_closure (tests/host_check/svm_tex_host.cpp). */
+int ref_probe_svm_closure(KernelGlobals *kg, const void *nodes, int offset, float *stack,
+                          const RefShadingPoint *p, const float *closure_weight,
+                          unsigned int path_flag, const float *omega_in, float randu,
+                          float randv, float *out)
+{
+  uint4 *saved = kg->__svm_nodes.data;
+  kg->__svm_nodes.data = (uint4 *)nodes;
+  ShaderData sd_storage;
+  ShaderData *sd = &sd_storage;
+  memset((void *)sd, 0, sizeof(ShaderData));
+  sd->P = make_float3(p->P[0], p->P[1], p->P[2]);
+  sd->N = make_float3(p->N[0], p->N[1], p->N[2]);
+  sd->Ng = sd->N;
+  sd->I = make_float3(p->I[0], p->I[1], p->I[2]);
+  sd->flag = p->backfacing ? SD_BACKFACING : 0;
+  sd->object = p->object;
+  sd->prim = p->prim;
+  sd->lamp = p->lamp;
+  sd->type = PRIMITIVE_TRIANGLE;
+  sd->num_closure = 0;
+  sd->num_closure_left = 32;
+  sd->svm_closure_weight = make_float3(closure_weight[0], closure_weight[1], closure_weight[2]);
+  uint4 node = read_node(kg, &offset);
+  svm_node_closure_bsdf(kg, sd, stack, node, SHADER_TYPE_SURFACE, (int)path_flag, &offset);
+  out[0] = (float)sd->num_closure;
+  const float3 wi = make_float3(omega_in[0], omega_in[1], omega_in[2]);
+  for (int i = 0; i < sd->num_closure; i++) {
+    const ShaderClosure *sc = &sd->closure[i];
+    float *o = out + 1 + 20 * i;
+    o[0] = (float)sc->type;
+    o[1] = sc->weight.x, o[2] = sc->weight.y, o[3] = sc->weight.z;
+    o[4] = sc->sample_weight;
+    float pdf = 0.0f;
+    const float3 ev = bsdf_eval(kg, sd, sc, wi, &pdf);
+    o[5] = ev.x, o[6] = ev.y, o[7] = ev.z, o[8] = pdf;
+    float3 sev = make_float3(0.0f, 0.0f, 0.0f), swi = make_float3(0.0f, 0.0f, 0.0f);
+    differential3 dwi;
+    float spdf = 0.0f;
+    const int label = bsdf_sample(kg, sd, sc, randu, randv, &sev, &swi, &dwi, &spdf);
+    o[9] = (float)label;
+    o[10] = sev.x, o[11] = sev.y, o[12] = sev.z;
+    o[13] = swi.x, o[14] = swi.y, o[15] = swi.z;
+    o[16] = spdf;
+  }
+  kg->__svm_nodes.data = saved;
+  return offset;
+}
+
 CCL_NAMESPACE_END
+
 

@@ -32,6 +32,10 @@ struct RefShadingPoint {
 
 namespace ccl {
 struct KernelGlobals;
+int ref_probe_svm_closure(KernelGlobals *kg, const void *nodes, int offset, float *stack,
+                          const RefShadingPoint *p, const float *closure_weight,
+                          unsigned int path_flag, const float *omega_in, float randu,
+                          float randv, float *out);
 int ref_probe_svm_node(KernelGlobals *kg, const void *nodes, int offset, float *stack,
                        const RefShadingPoint *p);
 void ref_probe_intersect(KernelGlobals *kg, const RefProbeRay *rays, RefProbeHit *hits, size_t n);

@@ -145,6 +145,34 @@ CY_DEV int bsdf_refraction_sample(const Closure &sc, f3 I, f3 *eval, f3 *omega_i
 }
 
 /* closure/bsdf.h bsdf_eval: reflect side when dot(Ng, omega_in) >= 0 */
+/* closure/bsdf.h:82-111: softened terminator for closures whose normal is not the
+ * shading normal (a linked Normal input), and the per-object shadow terminator offset */
+CY_DEV float bump_shadowing_term(f3 Ng, f3 N, f3 I)
+{
+  const float g = safe_divide(dot(Ng, I), dot(N, I) * dot(Ng, N));
+  if (g >= 1.0f)
+    return 1.0f;
+  if (g < 0.0f)
+    return 0.0f;
+  const float g2 = sqr(g);
+  return -g2 * g + g2 + g;
+}
+CY_DEV float shift_cos_in(float cos_in, float frequency_multiplier)
+{
+  cos_in = fminf(cos_in, 1.0f);
+  const float angle = fast_acosf(cos_in);
+  return fmaxf(cosf(angle * frequency_multiplier), 0.0f) / cos_in;
+}
+CY_DEV float object_shadow_terminator_offset(int object)
+{
+  return __ldg((const float *)(g_scene.objects + (size_t)object * SIZEOF_KERNEL_OBJECT +
+                               KO_SHADOW_TERMINATOR_OFFSET));
+}
+CY_DEV bool closure_is_bsdf_diffuse(int type)
+{
+  return type >= CY_CLOSURE_BSDF_DIFFUSE_ID && type <= CY_CLOSURE_BSDF_TRANSLUCENT_ID;
+}
+
 /* EXT = false: the closures the lean interpreter can create (it hands shaders with sheen
  * to the full one, shade.cuh svm_eval_nodes) */
 template<bool EXT>
@@ -175,6 +203,11 @@ CY_DEV f3 bsdf_eval(const ShaderDataG &sd, const Closure &sc, f3 omega_in, float
       default:
         break;
     }
+    if (closure_is_bsdf_diffuse(sc.type) && !isequal3(sc.N, sd.N))
+      eval *= bump_shadowing_term(sd.N, sc.N, omega_in);
+    const float frequency_multiplier = object_shadow_terminator_offset(sd.object);
+    if (frequency_multiplier > 1.0f)
+      eval *= shift_cos_in(dot(omega_in, sc.N), frequency_multiplier);
   }
   else {
     switch (sc.type) {
@@ -190,14 +223,16 @@ CY_DEV f3 bsdf_eval(const ShaderDataG &sd, const Closure &sc, f3 omega_in, float
       default:
         break;
     }
+    if (closure_is_bsdf_diffuse(sc.type) && !isequal3(sc.N, sd.N))
+      eval *= bump_shadowing_term(-sd.N, sc.N, omega_in);
   }
   return eval;
 }
 
 /* closure/bsdf.h bsdf_sample */
 template<bool EXT>
-CY_DEV int bsdf_sample(const ShaderDataG &sd, const Closure &sc, float randu, float randv,
-                       f3 *eval, f3 *omega_in, float *pdf)
+CY_DEV int bsdf_sample_closure(const ShaderDataG &sd, const Closure &sc, float randu,
+                               float randv, f3 *eval, f3 *omega_in, float *pdf)
 {
   switch (sc.type) {
     case CY_CLOSURE_BSDF_DIFFUSE_ID:
@@ -232,6 +267,23 @@ CY_DEV int bsdf_sample(const ShaderDataG &sd, const Closure &sc, float randu, fl
       *pdf = 0.0f;
       return CY_LABEL_NONE;
   }
+}
+
+/* closure/bsdf.h bsdf_sample: the closure's own sampler, then the terminator terms on
+ * the reflection side (closure/bsdf.h:466-489) */
+template<bool EXT>
+CY_DEV int bsdf_sample(const ShaderDataG &sd, const Closure &sc, float randu, float randv,
+                       f3 *eval, f3 *omega_in, float *pdf)
+{
+  const int label = bsdf_sample_closure<EXT>(sd, sc, randu, randv, eval, omega_in, pdf);
+  if (!(label & CY_LABEL_TRANSMIT)) {
+    const float frequency_multiplier = object_shadow_terminator_offset(sd.object);
+    if (frequency_multiplier > 1.0f)
+      *eval *= shift_cos_in(dot(*omega_in, sc.N), frequency_multiplier);
+    if ((label & CY_LABEL_DIFFUSE) && !isequal3(sc.N, sd.N))
+      *eval *= bump_shadowing_term(sd.N, sc.N, *omega_in);
+  }
+  return label;
 }
 
 #endif

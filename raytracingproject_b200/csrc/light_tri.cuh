@@ -94,15 +94,6 @@ CY_DEV void fast_sincosf(float x, float *sine, float *cosine)
   *cosine = cu;
 }
 
-CY_DEV float fast_acosf(float x)
-{
-  const float f = fabsf(x);
-  const float m = (f < 1.0f) ? 1.0f - (1.0f - f) : 1.0f; /* clamp, crush denormals */
-  const float a = sqrtf(1.0f - m) *
-                  (1.5707963267f + m * (-0.213300989f + m * (0.077980478f + m * -0.02164095f)));
-  return x < 0 ? CY_M_PI_F - a : a;
-}
-
 CY_DEV f3 safe_normalize_len(f3 a, float *t)
 {
   *t = len(a);

@@ -573,49 +573,6 @@ CY_DEV void shader_setup_from_ray(
 #define CY_NODE_GEOM_Ng 4
 #define CY_NODE_GEOM_uv 5
 
-/* closure/alloc.h:19-68 */
-CY_DEV Closure *closure_alloc(ShaderDataG &sd, f3 weight)
-{
-  if (sd.num_closure_left == 0)
-    return NULL;
-  Closure *sc = &sd.closure[sd.num_closure];
-  sc->type = CY_CLOSURE_NONE_ID;
-  sc->weight = weight;
-  sd.num_closure++;
-  sd.num_closure_left--;
-  return sc;
-}
-CY_DEV bool closure_alloc_extra(ShaderDataG &sd)
-{
-  if (1 > sd.num_closure_left) {
-    sd.num_closure--;
-    sd.num_closure_left++;
-    return false;
-  }
-  sd.num_closure_left -= 1;
-  return true;
-}
-CY_DEV Closure *bsdf_alloc(ShaderDataG &sd, f3 weight)
-{
-  Closure *sc = closure_alloc(sd, weight);
-  if (sc == NULL)
-    return NULL;
-  float sample_weight = fabsf(average(weight));
-  sc->sample_weight = sample_weight;
-  return (sample_weight >= CLOSURE_WEIGHT_CUTOFF) ? sc : NULL;
-}
-
-CY_DEV void emission_setup(ShaderDataG &sd, f3 weight)
-{
-  if (sd.flag & CY_SD_EMISSION) {
-    sd.closure_emission_background += weight;
-  }
-  else {
-    sd.flag |= CY_SD_EMISSION;
-    sd.closure_emission_background = weight;
-  }
-}
-
 #include "svm_closure.cuh"
 #include "svm_nodes.cuh"
 #include "svm_tex.cuh"

@@ -93,6 +93,61 @@ CY_DEV float fresnel_dielectric_cos(float cosi, float eta)
 struct PathDepths {
   short bounce, diffuse, glossy, transparent, transmission;
 };
+/* util/util_math_fast.h:278-293 (used by the mesh-light pdf and the shadow terminator) */
+CY_DEV float fast_acosf(float x)
+{
+  const float f = fabsf(x);
+  const float m = (f < 1.0f) ? 1.0f - (1.0f - f) : 1.0f; /* clamp, crush denormals */
+  const float a = sqrtf(1.0f - m) *
+                  (1.5707963267f + m * (-0.213300989f + m * (0.077980478f + m * -0.02164095f)));
+  return x < 0 ? CY_M_PI_F - a : a;
+}
+
+/* -------------------------------------------------------- closure storage */
+
+/* closure/alloc.h:19-68 */
+CY_DEV Closure *closure_alloc(ShaderDataG &sd, f3 weight)
+{
+  if (sd.num_closure_left == 0)
+    return NULL;
+  Closure *sc = &sd.closure[sd.num_closure];
+  sc->type = CY_CLOSURE_NONE_ID;
+  sc->weight = weight;
+  sd.num_closure++;
+  sd.num_closure_left--;
+  return sc;
+}
+CY_DEV bool closure_alloc_extra(ShaderDataG &sd)
+{
+  if (1 > sd.num_closure_left) {
+    sd.num_closure--;
+    sd.num_closure_left++;
+    return false;
+  }
+  sd.num_closure_left -= 1;
+  return true;
+}
+CY_DEV Closure *bsdf_alloc(ShaderDataG &sd, f3 weight)
+{
+  Closure *sc = closure_alloc(sd, weight);
+  if (sc == NULL)
+    return NULL;
+  float sample_weight = fabsf(average(weight));
+  sc->sample_weight = sample_weight;
+  return (sample_weight >= CLOSURE_WEIGHT_CUTOFF) ? sc : NULL;
+}
+
+CY_DEV void emission_setup(ShaderDataG &sd, f3 weight)
+{
+  if (sd.flag & CY_SD_EMISSION) {
+    sd.closure_emission_background += weight;
+  }
+  else {
+    sd.flag |= CY_SD_EMISSION;
+    sd.closure_emission_background = weight;
+  }
+}
+
 /* ------------------------------------------------------------ SVM stack */
 
 CY_DEV f3 stack_load_float3(const float *stack, uint32_t a)

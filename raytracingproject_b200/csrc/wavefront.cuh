@@ -1496,6 +1496,23 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
           const uint32_t distribution = nodes[4 * (i + 2) + 1];
           const uint32_t subsurface_method = nodes[4 * (i + 2) + 2];
           (void)subsurface_method;
+          /* subsurface > 0 makes the reference emit a BSSRDF closure (random-walk / Burley
+           * scattering, outside the scope): the Principled node is accepted only when its
+           * subsurface input is provably zero - a node constant, or a NODE_VALUE_F of the
+           * run the SVM compiler emits right before the closure node */
+          {
+            const uint32_t ss_slot = (nodes[4 * i + 1] >> 16) & 0xff;
+            float ss = 1.0f;
+            if (ss_slot == (uint32_t)CY_SVM_STACK_INVALID)
+              memcpy(&ss, &nodes[4 * i + 3], 4);
+            else if (const_run_end == i && const_known[ss_slot])
+              ss = const_value[ss_slot];
+            if (!(ss <= 1e-5f)) {
+              why = "Principled BSDF with subsurface scattering (a subsurface input that is "
+                    "not a constant zero) is outside the hot-path scope";
+              return false;
+            }
+          }
           /* sheen: handled by the full interpreter only (shade.cuh svm_eval_nodes) */
           const uint32_t sheen_slot = nodes[4 * (i + 1) + 3] & 0xff;
           if (!(const_run_end == i && const_known[sheen_slot] &&

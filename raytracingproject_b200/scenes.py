@@ -381,7 +381,13 @@ def _textured_shaders(variant):
             '  <map_range name="mr" type="smoothstep" from_min="-1" from_max="1" to_min="0.2" '
             'to_max="0.8"/>\n' + c("sep x", "mr value") +
             '  <hsv name="h" saturation="0.8" value="0.9" fac="0.9"/>\n' + c("t color", "h color") +
-            c("mr result", "h hue") + '  <diffuse_bsdf name="d"/>\n' + c("h color", "d color"),
+            c("mr result", "h hue") +
+            # a linked BSDF normal (bent shading normal): the bump shadowing term of
+            # bsdf_eval / bsdf_sample
+            '  <vector_math name="bn" type="add" vector2="0.25 0.15 0.0"/>\n' +
+            c("g normal", "bn vector1") + '  <vector_math name="bnn" type="normalize"/>\n' +
+            c("bn vector", "bnn vector1") +
+            '  <diffuse_bsdf name="d"/>\n' + c("h color", "d color") + c("bnn vector", "d normal"),
             "d bsdf")
         chain = ""
         prev = "t color"

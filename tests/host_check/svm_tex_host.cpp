@@ -29,6 +29,8 @@ static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; 
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 
 #include "../../raytracingproject_b200/csrc/shader_data.cuh"
+#include "../../raytracingproject_b200/csrc/bsdf.cuh"
+#include "../../raytracingproject_b200/csrc/svm_closure.cuh"
 #include "../../raytracingproject_b200/csrc/svm_nodes.cuh"
 #include "../../raytracingproject_b200/csrc/svm_tex.cuh"
 
@@ -198,6 +200,52 @@ extern "C" __attribute__((visibility("default"))) int host_svm_node(int offset, 
       break;
     default:
       return -1;
+  }
+  return offset;
+}
+
+/* NODE_CLOSURE_BSDF at `offset` -> closures (csrc/svm_closure.cuh, the full variant), then
+ * bsdf_eval for `omega_in` and bsdf_sample for (randu, randv) on each of them
+ * (csrc/bsdf.cuh).  out: [0] = number of closures, then 20 floats per closure: type,
+ * weight xyz, sample_weight, eval xyz, pdf, label, sampled eval xyz, omega xyz, pdf. */
+extern "C" __attribute__((visibility("default"))) int host_svm_closure(
+    int offset, float *stack, const HostShadingPoint *p, const float *closure_weight,
+    unsigned int path_flag, const float *omega_in, float randu, float randv, float *out)
+{
+  static ShaderDataG sd;
+  memset(&sd, 0, sizeof(sd));
+  sd.P = mk3(p->P[0], p->P[1], p->P[2]);
+  sd.N = mk3(p->N[0], p->N[1], p->N[2]);
+  sd.Ng = sd.N;
+  sd.I = mk3(p->I[0], p->I[1], p->I[2]);
+  sd.flag = p->backfacing ? CY_SD_BACKFACING : 0;
+  sd.object = p->object;
+  sd.prim = p->prim;
+  sd.lamp = p->lamp;
+  sd.num_closure = 0;
+  sd.num_closure_left = MAX_CLOSURES_GPU;
+  sd.svm_closure_weight = mk3(closure_weight[0], closure_weight[1], closure_weight[2]);
+  const uint4 node = g_scene.svm_nodes[offset];
+  offset++;
+  svm_node_closure_bsdf<true>(sd, stack, node, path_flag, &offset);
+  out[0] = (float)sd.num_closure;
+  const f3 wi = mk3(omega_in[0], omega_in[1], omega_in[2]);
+  for (int i = 0; i < sd.num_closure; i++) {
+    const Closure &sc = sd.closure[i];
+    float *o = out + 1 + 20 * i;
+    o[0] = (float)sc.type;
+    o[1] = sc.weight.x, o[2] = sc.weight.y, o[3] = sc.weight.z;
+    o[4] = sc.sample_weight;
+    float pdf = 0.0f;
+    const f3 ev = bsdf_eval<true>(sd, sc, wi, &pdf);
+    o[5] = ev.x, o[6] = ev.y, o[7] = ev.z, o[8] = pdf;
+    f3 sev = zero3(), swi = zero3();
+    float spdf = 0.0f;
+    const int label = bsdf_sample<true>(sd, sc, randu, randv, &sev, &swi, &spdf);
+    o[9] = (float)label;
+    o[10] = sev.x, o[11] = sev.y, o[12] = sev.z;
+    o[13] = swi.x, o[14] = swi.y, o[15] = swi.z;
+    o[16] = spdf;
   }
   return offset;
 }

@@ -380,3 +380,81 @@ def test_scope_check_without_a_device(ref):
         assert validate_svm(svm[:-8]) is not None          # not a whole number of nodes
     finally:
         rs.close()
+
+
+CLOSURE_SCENES = ["principled", "closures", "closures2", "transparent", "textured", "textured3",
+                  "textured4", "procedural"]
+
+
+@pytest.mark.parametrize("materials", CLOSURE_SCENES)
+def test_closure_setup_eval_sample_match_reference(ref, host_lib, materials):
+    """Every NODE_CLOSURE_BSDF of the compiled programs: closure setup (svm_closure.cuh),
+    then bsdf_eval for a random direction and bsdf_sample for random numbers on each
+    closure it made (bsdf.cuh, bsdf_principled.cuh), against the reference's
+    svm_node_closure_bsdf / bsdf_eval / bsdf_sample - device source built for the host.
+    Parameters come from a stack of plausible values (0.05 .. 0.95)."""
+    host_lib.host_svm_closure.restype = C.c_int
+    host_lib.host_svm_closure.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint,
+                                          C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+    text = open(os.path.join(ROOT, "include", "cycles_abi.h")).read()
+    ray_diffuse = int(re.search(r"#define CY_PATH_RAY_DIFFUSE[ \t]+(\w+)", text).group(1)
+                      .rstrip("u"), 0)
+    desc = scenes.cornell(64, 48, spp=1, materials=materials)
+    rs = ref.build_scene(desc)
+    try:
+        arrays = rs.device_arrays()
+        real = arrays["__svm_nodes"][0].view(np.uint32).reshape(-1, 4)
+        nodes = np.zeros((len(real) + 8, 4), np.uint32)
+        nodes[: len(real)] = real
+        bound = Bound(host_lib, arrays, nodes)
+        a = abi()
+        rng = np.random.default_rng(11)
+        pts = shading_points(arrays, 32, rng)
+        pts["object"], pts["lamp"] = np.maximum(pts["object"], 0), -1
+        pts["prim"] = np.maximum(pts["prim"], 0)
+        closures_seen, types_seen = 0, set()
+        for off in range(len(real)):
+            # closure instructions are recognisable: opcode + a closure type in the low byte
+            if int(nodes[off, 0]) != a["NODE_CLOSURE_BSDF"] or off < 2:
+                continue
+            if int(nodes[off - 1, 0]) == a["NODE_VALUE_V"]:
+                continue  # the float3 payload of a value node, not an instruction
+            for i in range(len(pts)):
+                pt = pts[i:i + 1].copy()
+                n = pt["N"][0]
+                wo = rng.normal(size=3)
+                wo = wo / np.linalg.norm(wo)
+                pt["I"][0] = wo if wo @ n > 0 else -wo  # viewer above the surface
+                wi = rng.normal(size=3).astype(np.float32)
+                wi /= np.linalg.norm(wi)
+                stack0 = rng.uniform(0.05, 0.95, 264).astype(np.float32)
+                if (int(nodes[off, 1]) & 0xff) == PRINCIPLED_ID:
+                    # subsurface stays zero: anything else is a BSSRDF, refused on the host
+                    ss_slot = (int(nodes[off, 1]) >> 16) & 0xff
+                    if ss_slot != 255:
+                        stack0[ss_slot] = 0.0
+                weight = rng.uniform(0.1, 1.0, 3).astype(np.float32)
+                flag = ray_diffuse if i % 4 == 3 else 0
+                ru, rv = float(rng.uniform(0.01, 0.99)), float(rng.uniform(0.01, 0.99))
+                s_ref, s_dev = stack0.copy(), stack0.copy()
+                n_ref, o_ref = rs.svm_closure(nodes, off, s_ref, pt, weight, flag, wi, ru, rv)
+                o_dev = np.zeros_like(o_ref)
+                n_dev = host_lib.host_svm_closure(off, s_dev.ctypes.data, pt.ctypes.data,
+                                                  weight.ctypes.data, flag, wi.ctypes.data,
+                                                  ru, rv, o_dev.ctypes.data)
+                assert n_ref == n_dev, (off, n_ref, n_dev)
+                assert o_ref[0] == o_dev[0], (off, "closure count", o_ref[0], o_dev[0])
+                k = int(o_ref[0])
+                r = o_ref[1:1 + 20 * k].reshape(k, 20)
+                d = o_dev[1:1 + 20 * k].reshape(k, 20)
+                assert np.array_equal(r[:, 0], d[:, 0]), (off, "closure types", r[:, 0], d[:, 0])
+                assert np.array_equal(r[:, 9], d[:, 9]), (off, "sample labels", r[:, 9], d[:, 9])
+                bad = ~np.isclose(r, d, rtol=2e-4, atol=2e-5, equal_nan=True)
+                assert not bad.any(), (off, i, np.argwhere(bad)[:6].tolist(), r[bad][:6], d[bad][:6], r[0, :17].tolist(), d[0, :17].tolist(), pt.tolist(), wi.tolist())
+                closures_seen += k
+                types_seen |= set(int(t) for t in r[:, 0])
+        assert closures_seen > 0
+        print(materials, "closures compared:", closures_seen, "types:", sorted(types_seen))
+        del bound
+    finally:
+        rs.close()
