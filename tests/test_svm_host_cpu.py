@@ -428,6 +428,11 @@ def test_closure_setup_eval_sample_match_reference(ref, host_lib, materials):
                 wi = rng.normal(size=3).astype(np.float32)
                 wi /= np.linalg.norm(wi)
                 stack0 = rng.uniform(0.05, 0.95, 264).astype(np.float32)
+                if i % 8 == 5:
+                    # the zero-parameter branches: Lambert instead of Oren-Nayar, sharp
+                    # instead of rough, no sheen / clearcoat / transmission
+                    stack0[:] = 0.0
+                    stack0[rng.integers(0, 264, 40)] = rng.uniform(0.2, 0.9, 40)
                 if (int(nodes[off, 1]) & 0xff) == PRINCIPLED_ID:
                     # subsurface stays zero: anything else is a BSSRDF, refused on the host
                     ss_slot = (int(nodes[off, 1]) >> 16) & 0xff
