@@ -411,12 +411,24 @@ int b200_bind_global(b200_ctx *ctx, const char *name, uint64_t dptr, const void 
         return rc;
     }
   }
-  if (strcmp(name, "__svm_nodes") == 0 && !bytes)
-    ctx->svm_features = 0;
+  if (strcmp(name, "__svm_nodes") == 0) {
+    ctx->force_svm_ext = false;
+    if (!bytes)
+      ctx->svm_features = 0;
+  }
   if (strcmp(name, "__svm_nodes") == 0 && bytes) {
     std::string why;
     if (!svm_validate((const uint32_t *)ha.host.data(), bytes / 16, why, &ctx->svm_features))
       return fail(ctx, B200_ERR_UNSUPPORTED, why);
+  }
+  if (strcmp(name, "__objects") == 0) {
+    ctx->has_terminator_offset = false;
+    for (size_t o = 0; o < bytes / SIZEOF_KERNEL_OBJECT; o++) {
+      float f;
+      memcpy(&f, ha.host.data() + o * SIZEOF_KERNEL_OBJECT + KO_SHADOW_TERMINATOR_OFFSET, 4);
+      if (f > 1.0f)
+        ctx->has_terminator_offset = true;
+    }
   }
   if (strcmp(name, "__attributes_map") == 0) {
     ctx->has_generated_attr = false;

@@ -48,6 +48,8 @@ struct b200_ctx {
   bool have_data = false;
   uint32_t svm_features = 0;     /* SVM_USES_* of the bound __svm_nodes (svm_validate) */
   bool has_subd_patches = false; /* __tri_patch holds a patch index */
+  bool force_svm_ext = false; /* a lean batch had to be redone with the full kernels */
+  bool has_terminator_offset = false; /* an object with shadow_terminator_offset > 1 */
   bool has_generated_attr = false; /* __attributes_map lists ATTR_STD_GENERATED */
 
   /* BVH8 on the device */

@@ -174,7 +174,9 @@ CY_DEV void cmj_sample_2D(int s, int N, uint32_t p, float *fx, float *fy)
  * (__sample_pattern_lut: NUM_PMJ_PATTERNS x NUM_PMJ_SAMPLES 2D points as floats in
  * [1, 2)), scrambled per pixel and dimension by xor on the mantissa; beyond the table
  * it falls back to hashed random numbers */
-CY_DEV float pmj_sample_1D(int sample, uint32_t rng_hash, int dimension)
+/* out of line: the table patterns are rare next to Sobol, and inlined into the kernels'
+ * random-number paths they cost the shading-bound workload 4 % (register allocation) */
+__device__ __noinline__ float pmj_sample_1D(int sample, uint32_t rng_hash, int dimension)
 {
   if (sample >= CY_NUM_PMJ_SAMPLES)
     return cmj_randfloat((uint32_t)sample, rng_hash + (uint32_t)dimension);
@@ -182,25 +184,27 @@ CY_DEV float pmj_sample_1D(int sample, uint32_t rng_hash, int dimension)
   const int index = ((dimension % CY_NUM_PMJ_PATTERNS) * CY_NUM_PMJ_SAMPLES + sample) * 2;
   return __uint_as_float(__ldg(&g_scene.sample_pattern_lut[index]) ^ mask) - 1.0f;
 }
-CY_DEV void pmj_sample_2D(int sample, uint32_t rng_hash, int dimension, float *fx, float *fy)
+__device__ __noinline__ float2 pmj_sample_2D(int sample, uint32_t rng_hash, int dimension)
 {
   if (sample >= CY_NUM_PMJ_SAMPLES) {
     const uint32_t p = rng_hash + (uint32_t)dimension;
-    *fx = cmj_randfloat((uint32_t)sample, p);
-    *fy = cmj_randfloat((uint32_t)sample, p + 1);
-    return;
+    return make_float2(cmj_randfloat((uint32_t)sample, p), cmj_randfloat((uint32_t)sample, p + 1));
   }
   const int index = ((dimension % CY_NUM_PMJ_PATTERNS) * CY_NUM_PMJ_SAMPLES + sample) * 2;
   const uint32_t maskx = cmj_hash_simple((uint32_t)dimension, rng_hash) & 0x007fffffu;
   const uint32_t masky = cmj_hash_simple((uint32_t)dimension + 1, rng_hash) & 0x007fffffu;
-  *fx = __uint_as_float(__ldg(&g_scene.sample_pattern_lut[index]) ^ maskx) - 1.0f;
-  *fy = __uint_as_float(__ldg(&g_scene.sample_pattern_lut[index + 1]) ^ masky) - 1.0f;
+  return make_float2(
+      __uint_as_float(__ldg(&g_scene.sample_pattern_lut[index]) ^ maskx) - 1.0f,
+      __uint_as_float(__ldg(&g_scene.sample_pattern_lut[index + 1]) ^ masky) - 1.0f);
 }
 
-/* kernel/kernel_random.h:53-127: PMJ, CMJ, or Sobol with a Cranley-Patterson rotation */
+/* kernel/kernel_random.h:53-127: PMJ, CMJ, or Sobol with a Cranley-Patterson rotation.
+ * TABLE = false leaves the table pattern (PMJ) out: the lean shading kernels, which the
+ * host never selects for a PMJ scene (b200_render: svm_ext). */
+template<bool TABLE = true>
 CY_DEV float path_rng_1D(uint32_t rng_hash, int sample, int dimension)
 {
-  if (kd_int(KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_PMJ)
+  if (TABLE && kd_int(KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_PMJ)
     return pmj_sample_1D(sample, rng_hash, dimension);
   if (kd_int(KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_CMJ)
     return cmj_sample_1D(sample, kd_int(KD_INT_AA_SAMPLES), rng_hash + (uint32_t)dimension);
@@ -210,26 +214,31 @@ CY_DEV float path_rng_1D(uint32_t rng_hash, int sample, int dimension)
   float shift = (float)tmp_rng * (1.0f / (float)0xFFFFFFFF);
   return r + shift - floorf(r + shift);
 }
+template<bool TABLE = true>
 CY_DEV void path_rng_2D(uint32_t rng_hash, int sample, int dimension, float *fx, float *fy)
 {
-  if (kd_int(KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_PMJ) {
-    pmj_sample_2D(sample, rng_hash, dimension, fx, fy);
+  if (TABLE && kd_int(KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_PMJ) {
+    const float2 f = pmj_sample_2D(sample, rng_hash, dimension);
+    *fx = f.x;
+    *fy = f.y;
     return;
   }
   if (kd_int(KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_CMJ) {
     cmj_sample_2D(sample, kd_int(KD_INT_AA_SAMPLES), rng_hash + (uint32_t)dimension, fx, fy);
     return;
   }
-  *fx = path_rng_1D(rng_hash, sample, dimension);
-  *fy = path_rng_1D(rng_hash, sample, dimension + 1);
+  *fx = path_rng_1D<TABLE>(rng_hash, sample, dimension);
+  *fy = path_rng_1D<TABLE>(rng_hash, sample, dimension + 1);
 }
+template<bool TABLE = true>
 CY_DEV float path_state_rng_1D(const PathStateG &s, int dimension)
 {
-  return path_rng_1D(s.rng_hash, s.sample, s.rng_offset + dimension);
+  return path_rng_1D<TABLE>(s.rng_hash, s.sample, s.rng_offset + dimension);
 }
+template<bool TABLE = true>
 CY_DEV void path_state_rng_2D(const PathStateG &s, int dimension, float *fx, float *fy)
 {
-  path_rng_2D(s.rng_hash, s.sample, s.rng_offset + dimension, fx, fy);
+  path_rng_2D<TABLE>(s.rng_hash, s.sample, s.rng_offset + dimension, fx, fy);
 }
 
 /* kernel/kernel_globals.h:213-227 */
@@ -507,6 +516,7 @@ CY_DEV void shader_setup_from_ray(
   sd.object = (isect_object == -1) ? (int)__ldg(&g_scene.prim_object[isect_prim]) : isect_object;
   sd.type = CY_PRIMITIVE_TRIANGLE;
   sd.lamp = -1;
+  sd.terminator_freq = object_shadow_terminator_offset(sd.object);
   sd.flag = 0;
   sd.object_flag = __ldg(&g_scene.object_flag[sd.object]);
   sd.prim = (int)__ldg(&g_scene.prim_index[isect_prim]);
@@ -885,8 +895,11 @@ CY_DEV void shader_eval_surface(ShaderDataG &sd, PathDepths depths, uint32_t pat
 }
 
 /* kernel_shader.h:530-555 */
+template<bool EXT>
 CY_DEV void shader_prepare_closures(ShaderDataG &sd, const PathStateG &state)
 {
+  if (EXT)
+    bsdf_terminator_terms_setup(sd);
   if (state.bounce + state.transparent_bounce == 0 && sd.num_closure > 1) {
     float sum = 0.0f;
     for (int i = 0; i < sd.num_closure; i++) {

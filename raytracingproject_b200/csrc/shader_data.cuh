@@ -47,6 +47,8 @@ struct ShaderDataG {
   int prim, type, object;
   int lamp; /* lamp index while its emission shader runs, else -1 (LAMP_NONE) */
   float u, v, ray_length;
+  float terminator_freq; /* KernelObject::shadow_terminator_offset, fetched once per point */
+  int terminator_terms;  /* some closure needs the terms of bsdf_terminator_terms() */
   f3 svm_closure_weight;
   f3 closure_emission_background;
   f3 closure_transparent_extinction; /* valid when flag & SD_TRANSPARENT */
@@ -59,6 +61,13 @@ CY_DEV uint32_t shader_flags(int shader)
   return __ldg((const uint32_t *)(g_scene.shaders +
                                   (size_t)(shader & CY_SHADER_MASK) * SIZEOF_KERNEL_SHADER +
                                   KS_FLAGS));
+}
+
+/* KernelObject::shadow_terminator_offset (1 / (1 - offset), 1 = off) */
+CY_DEV float object_shadow_terminator_offset(int object)
+{
+  return __ldg((const float *)(g_scene.objects + (size_t)object * SIZEOF_KERNEL_OBJECT +
+                               KO_SHADOW_TERMINATOR_OFFSET));
 }
 
 /* geom/geom_object.h:166-186 */

@@ -97,6 +97,10 @@ CY_DEV bool svm_node_closure_bsdf(ShaderDataG &sd, float *stack, uint4 node, uin
   }
 
   f3 N = stack_valid(data_node.x) ? stack_load_float3(stack, data_node.x) : sd.N;
+  /* a linked normal that is not the shading normal needs the terminator terms of
+   * bsdf_eval / bsdf_sample, which only the full kernels carry */
+  if (!FULL && stack_valid(data_node.x) && !isequal3(N, sd.N))
+    return false;
   float param1 = stack_valid(param1_offset) ? stack[param1_offset] : __uint_as_float(node.z);
   float param2 = stack_valid(param2_offset) ? stack[param2_offset] : __uint_as_float(node.w);
 

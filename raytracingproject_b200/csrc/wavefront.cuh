@@ -671,7 +671,7 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS)
       if (alive) {
         shader_setup_from_ray(sd, hit_prim, hit_object, hit.x, hit.y, hit.z, rayP, rayD);
         shader_eval_surface<EXT>(sd, path_depths(st), st.flag);
-        shader_prepare_closures(sd, st);
+        shader_prepare_closures<EXT>(sd, st);
 
         /* kernel_path_shader_apply - kernel_path.h:254-321 (no holdout / shadow catcher;
          * filter_glossy handled below) */
@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS)
           alive = false;
         }
         else if (probability != 1.0f) {
-          float terminate = path_state_rng_1D(st, CY_PRNG_TERMINATE);
+          float terminate = path_state_rng_1D<EXT>(st, CY_PRNG_TERMINATE);
           if (terminate >= probability)
             alive = false;
           else
@@ -725,10 +725,10 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS)
         /* direct light - kernel_path_surface.h:22-125 with one light sample */
         if (kd_int(KD_INT_USE_DIRECT_LIGHT) && (sd.flag & CY_SD_BSDF_HAS_EVAL)) {
           float light_u, light_v;
-          path_state_rng_2D(st, CY_PRNG_LIGHT_U, &light_u, &light_v);
+          path_state_rng_2D<EXT>(st, CY_PRNG_LIGHT_U, &light_u, &light_v);
           float terminate = 0.0f;
           if (kd_float(KD_INT_LIGHT_INV_RR_THRESHOLD) > 0.0f)
-            terminate = path_state_rng_1D(st, CY_PRNG_LIGHT_TERMINATE);
+            terminate = path_state_rng_1D<EXT>(st, CY_PRNG_LIGHT_TERMINATE);
           LightSampleG ls;
           if (light_sample(light_u, light_v, sd.P, st.bounce, &ls) && ls.pdf != 0.0f) {
             /* direct_emission - kernel_emission.h:101-212 */
@@ -799,7 +799,7 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS)
         /* kernel_path_surface_bounce - kernel_path_surface.h:270-358 */
         if (sd.flag & CY_SD_BSDF) {
           float bsdf_u, bsdf_v;
-          path_state_rng_2D(st, CY_PRNG_BSDF_U, &bsdf_u, &bsdf_v);
+          path_state_rng_2D<EXT>(st, CY_PRNG_BSDF_U, &bsdf_u, &bsdf_v);
           f3 bsdf_eval = zero3(), omega_in = zero3();
           float bsdf_pdf;
           int label = shader_bsdf_sample<EXT>(sd, bsdf_u, bsdf_v, &bsdf_eval, &omega_in, &bsdf_pdf);
@@ -1659,7 +1659,13 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
     }
   }
   const bool transparent_shadows = kd_host<int>(ctx, KD_INT_TRANSPARENT_SHADOWS) != 0;
-  const bool svm_ext = (ctx->svm_features & SVM_USES_EXTENDED_NODES) != 0;
+  /* the full shading kernels: extended SVM nodes or sheen (svm_validate), an object with a
+   * shadow terminator offset (terminator terms of bsdf_eval / bsdf_sample), the table
+   * sampling pattern - or a lean batch that met a shader it could not run (a closure whose
+   * linked normal differs from the shading normal), see the retry below */
+  bool svm_ext = ctx->force_svm_ext || (ctx->svm_features & SVM_USES_EXTENDED_NODES) != 0 ||
+                       ctx->has_terminator_offset ||
+                       kd_host<int>(ctx, KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_PMJ;
   rc = ensure_pool(ctx, std::max<size_t>(capacity, (size_t)tile->w), transparent_shadows);
   if (rc)
     return rc;
@@ -1702,6 +1708,7 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
       bp.num_keys = num_keys;
       bp.count_stats = count;
 
+      for (int attempt = 0;; attempt++) {
       PathSoA soa = pool->soa;
       soa.debug = ctx->d_debug;
       soa.debug_slot = (int)ctx->opt_debug_slot;
@@ -1780,6 +1787,22 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
         if (pool->h_counters->n_active == 0)
           break;
       }
+      if (!svm_ext) {
+        /* Nothing of this batch has reached the film yet.  If a lean kernel met a shader
+         * only the full interpreter runs, the batch is thrown away and traced again with
+         * the full kernels, and the context stays on them until the program changes. */
+        unsigned int miss = 0;
+        CUDA_TRY(ctx, cudaMemcpyFromSymbol(&miss, g_svm_scope_miss, sizeof(miss)));
+        if (miss) {
+          const unsigned int zero = 0;
+          CUDA_TRY(ctx, cudaMemcpyToSymbol(g_svm_scope_miss, &zero, sizeof(zero)));
+          if (attempt > 0)
+            return fail(ctx, B200_ERR_UNSUPPORTED, "SVM scope miss in the full kernels");
+          svm_ext = true;
+          ctx->force_svm_ext = true;
+          continue;
+        }
+      }
       k_film_accumulate<<<grid_wide, WF_BLOCK, 0, st>>>(soa, bp, (float *)tile->buffer,
                                                         pass_stride, pass_combined);
       stats.kernel_launches += 1;
@@ -1796,6 +1819,8 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
       stats.shadow_nodes += pool->h_counters->sh_nodes;
       stats.shadow_tris += pool->h_counters->sh_tris;
       stats.shadow_instances += pool->h_counters->sh_instances;
+      break;
+      } /* attempt */
     }
   }
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev6, st));
@@ -1809,18 +1834,6 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
   }
   stats.svm_extended = svm_ext ? 1 : 0;
   ctx->stats = stats;
-  if (!svm_ext) {
-    /* the lean shading kernels ran: no shader may have needed the full interpreter */
-    unsigned int miss = 0;
-    CUDA_TRY(ctx, cudaMemcpyFromSymbol(&miss, g_svm_scope_miss, sizeof(miss)));
-    if (miss) {
-      const unsigned int zero = 0;
-      cudaMemcpyToSymbol(g_svm_scope_miss, &zero, sizeof(zero));
-      return fail(ctx, B200_ERR_UNSUPPORTED,
-                  "a shader needed the full SVM interpreter although the program scan found "
-                  "no extended node (frame discarded)");
-    }
-  }
   return B200_OK;
 }
 

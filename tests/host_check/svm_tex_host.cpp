@@ -222,12 +222,14 @@ extern "C" __attribute__((visibility("default"))) int host_svm_closure(
   sd.object = p->object;
   sd.prim = p->prim;
   sd.lamp = p->lamp;
+  sd.terminator_freq = object_shadow_terminator_offset(sd.object);
   sd.num_closure = 0;
   sd.num_closure_left = MAX_CLOSURES_GPU;
   sd.svm_closure_weight = mk3(closure_weight[0], closure_weight[1], closure_weight[2]);
   const uint4 node = g_scene.svm_nodes[offset];
   offset++;
   svm_node_closure_bsdf<true>(sd, stack, node, path_flag, &offset);
+  bsdf_terminator_terms_setup(sd);
   out[0] = (float)sd.num_closure;
   const f3 wi = mk3(omega_in[0], omega_in[1], omega_in[2]);
   for (int i = 0; i < sd.num_closure; i++) {

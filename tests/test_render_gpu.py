@@ -149,6 +149,35 @@ def test_sheen_alone_selects_the_full_interpreter(ref, device):
         rs.close()
 
 
+def test_bent_normal_redoes_the_batch_with_the_full_kernels(ref, device):
+    """Only lean nodes, but a BSDF normal that is not the shading normal: the host's scan
+    cannot know, the lean kernels notice on the device, nothing of that batch reaches
+    the film, the batch is traced again with the full kernels (bump shadowing term of
+    bsdf_eval / bsdf_sample) - and the frame matches the reference."""
+    from raytracingproject_b200 import scenes
+    desc = scenes.cornell(W_SMALL, H_SMALL, materials="diffuse")
+    desc.xml = desc.xml.replace(
+        '  <diffuse_bsdf name="d" color="0.73 0.73 0.73"/>\n',
+        '  <diffuse_bsdf name="d" color="0.73 0.73 0.73"/>\n  <geometry name="g"/>\n'
+        '  <vector_math name="bn" type="add" vector2="0.3 0.2 0.1"/>\n'
+        '  <connect from="g normal" to="bn vector1"/>\n'
+        '  <vector_math name="bnn" type="normalize"/>\n'
+        '  <connect from="bn vector" to="bnn vector1"/>\n'
+        '  <connect from="bnn vector" to="d normal"/>\n', 1)
+    assert "bnn vector" in desc.xml
+    rs = ref.build_scene(desc)
+    try:
+        device.upload_scene(rs.device_arrays())
+        ref_img, _ = rs.render(0, SPP, tile_size=64)
+        got = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP)
+        assert device.stats()["svm_extended"] == 1
+        image_gates(ref_img, got, SPP, "bent normal")
+        again = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP)
+        assert np.array_equal(again, got)  # the context stays on the full kernels
+    finally:
+        rs.close()
+
+
 def test_window_coordinates_need_a_perspective_camera(ref, device):
     """NODE_TEXCO_WINDOW reads the ray origin under an orthographic camera and the
     panorama projection under a panoramic one; both are refused, not approximated."""
