@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="terrain",
                     choices=["terrain", "instanced", "cube", "cornell"])
+    ap.add_argument("--materials", default="diffuse",
+                    help="cornell only: scenes.cornell(materials=...), e.g. principled, textured")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--spp", type=int, default=0, help="samples per step (0 = the config's)")
@@ -67,7 +69,7 @@ def make_desc(args):
     elif args.workload == "cube":
         d = scenes.default_cube(material="diffuse", **kw)
     else:
-        d = scenes.cornell(materials="diffuse", **kw)
+        d = scenes.cornell(materials=args.materials, **kw)
     if args.spp:
         d.spp = args.spp
     return d

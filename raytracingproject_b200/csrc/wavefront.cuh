@@ -623,8 +623,11 @@ __global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(Pa
 #ifndef SHADE_MIN_BLOCKS
 #  define SHADE_MIN_BLOCKS 2
 #endif
+#ifndef SHADE_MIN_BLOCKS_EXT
+#  define SHADE_MIN_BLOCKS_EXT 2
+#endif
 template<bool EXT>
-__global__ void __launch_bounds__(WF_BLOCK, SHADE_MIN_BLOCKS)
+__global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_MIN_BLOCKS)
     k_shade_surface(PathSoA p, int num_keys)
 {
   WFCounters *c = p.counters;
