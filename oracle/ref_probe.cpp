@@ -425,6 +425,9 @@ int ref_probe_svm_node(KernelGlobals *kg, const void *nodes, int offset, float *
     case NODE_BLACKBODY:
       svm_node_blackbody(kg, sd, stack, node.y, node.z);
       break;
+    case NODE_WAVELENGTH:
+      svm_node_wavelength(kg, sd, stack, node.y, node.z);
+      break;
     case NODE_TEX_MUSGRAVE:
       svm_node_tex_musgrave(kg, sd, stack, node.y, node.z, node.w, &offset);
       break;

@@ -648,6 +648,9 @@ __device__ __noinline__ int svm_eval_extended_node(ShaderDataG &sd, float *stack
     case CY_NODE_BLACKBODY:
       svm_node_blackbody(stack, node);
       break;
+    case CY_NODE_WAVELENGTH:
+      svm_node_wavelength(stack, node);
+      break;
     case CY_NODE_TEX_MUSGRAVE:
       svm_node_tex_musgrave(stack, node, &offset);
       break;

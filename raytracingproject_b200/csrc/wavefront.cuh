@@ -1399,6 +1399,7 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
       case CY_NODE_CAMERA:
       case CY_NODE_TEX_WHITE_NOISE:
       case CY_NODE_BLACKBODY:
+      case CY_NODE_WAVELENGTH:
         *features |= SVM_USES_EXTENDED_NODES;
         i += 1;
         break;

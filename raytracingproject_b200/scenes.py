@@ -334,8 +334,12 @@ def _textured_shaders(variant):
             '  <math name="m" type="multiply_add" value2="0.3" value3="0.5"/>\n' +
             c("t fac", "m value1") + '  <math name="m2" type="multiply" value2="0.4"/>\n' +
             c("t2 fac", "m2 value1") + '  <combine_xyz name="cmb" x="0.12"/>\n' +
-            c("m value", "cmb y") + c("m2 value", "cmb z") + '  <diffuse_bsdf name="d"/>\n' +
-            c("cmb vector", "d color"), "d bsdf")
+            c("m value", "cmb y") + c("m2 value", "cmb z") +
+            '  <math name="nm" type="multiply_add" value2="150" value3="520"/>\n' +
+            c("t fac", "nm value1") + '  <wavelength name="wl"/>\n' + c("nm value", "wl wavelength") +
+            '  <mix name="mxw" type="add" fac="0.3"/>\n' + c("cmb vector", "mxw color1") +
+            c("wl color", "mxw color2") + '  <diffuse_bsdf name="d"/>\n' +
+            c("mxw color", "d color"), "d bsdf")
         metal = _node_shader(
             "metal", '  <texture_coordinate name="tc"/>\n'
             '  <voronoi_texture name="t" dimensions="3D" feature="distance_to_edge" scale="3.0"/>\n' +

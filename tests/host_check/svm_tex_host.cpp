@@ -128,6 +128,9 @@ extern "C" __attribute__((visibility("default"))) int host_svm_node(int offset, 
     case CY_NODE_BLACKBODY:
       svm_node_blackbody(stack, node);
       break;
+    case CY_NODE_WAVELENGTH:
+      svm_node_wavelength(stack, node);
+      break;
     case CY_NODE_TEX_MUSGRAVE:
       svm_node_tex_musgrave(stack, node, &offset);
       break;

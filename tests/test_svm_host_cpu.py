@@ -112,6 +112,7 @@ def texture_ops():
                               "NODE_VECTOR_TRANSFORM", "NODE_OBJECT_INFO", "NODE_CAMERA",
                               "NODE_TEX_WHITE_NOISE", "NODE_MIX", "NODE_MATH",
                               "NODE_TEX_VORONOI", "NODE_TEX_MUSGRAVE", "NODE_BLACKBODY",
+                              "NODE_WAVELENGTH",
                               "NODE_VECTOR_MATH", "NODE_CONVERT", "NODE_INVERT", "NODE_GAMMA",
                               "NODE_BRIGHTCONTRAST", "NODE_CLAMP", "NODE_FRESNEL",
                               "NODE_LAYER_WEIGHT", "NODE_RGB_RAMP", "NODE_RGB_CURVES",
@@ -224,6 +225,7 @@ VALUE_NODE_SPECS = {
     "NODE_CAMERA": {"yzw": (O, O, O)},
     "NODE_TEX_WHITE_NOISE": {"yzw": ("dims", "packed", "packed")},
     "NODE_BLACKBODY": {"yzw": (O, O, O)},
+    "NODE_WAVELENGTH": {"yzw": (O, O, O)},
     "NODE_TEX_MUSGRAVE": {"yzw": ((5, "dims", O, O), "packed", "packed"),
                           "extra": [("float",) * 4, ("float",) * 4]},
     "NODE_TEX_VORONOI": {"yzw": ("dims", 5, 4),
@@ -340,6 +342,8 @@ def test_random_node_encodings_match_reference(ref, host_lib, op_name):
             stack0 = rng.uniform(-2.0, 2.0, 264).astype(np.float32)
             if op_name == "NODE_BLACKBODY":  # temperatures across all six bands
                 stack0 = rng.uniform(500.0, 14000.0, 264).astype(np.float32)
+            if op_name == "NODE_WAVELENGTH":  # nanometres, a little beyond the table
+                stack0 = rng.uniform(350.0, 810.0, 264).astype(np.float32)
             pt = pts[trial % len(pts):trial % len(pts) + 1]
             n_ref, n_dev, s_ref, s_dev = run_both(host_lib, rs, prog, 0, stack0, pt)
             assert n_ref == n_dev and n_ref > 0, (op_name, trial, n_ref, n_dev)
@@ -352,7 +356,7 @@ def test_random_node_encodings_match_reference(ref, host_lib, op_name):
 
 
 def test_scope_check_without_a_device(ref):
-    """b200_validate_svm: programs of the supported scenes pass, a Wavelength node or a
+    """b200_validate_svm: programs of the supported scenes pass, a Bump node or a
     truncated program is refused with a reason - on the host, no GPU involved."""
     from raytracingproject_b200.device import validate_svm
     for materials in ("principled", "closures", "procedural", "textured", "textured2",
@@ -370,9 +374,9 @@ def test_scope_check_without_a_device(ref):
         '  <connect from="g position" to="l vector1"/>\n'
         '  <math name="t" type="multiply_add" value2="100" value3="450"/>\n'
         '  <connect from="l value" to="t value1"/>\n'
-        '  <wavelength name="m"/>\n'
-        '  <connect from="t value" to="m wavelength"/>\n'
-        '  <connect from="m color" to="d color"/>\n', 1)
+        '  <bump name="m" strength="0.6"/>\n'
+        '  <connect from="t value" to="m height"/>\n'
+        '  <connect from="m normal" to="d normal"/>\n', 1)
     rs = ref.build_scene(desc)
     try:
         svm = rs.device_arrays()["__svm_nodes"][0]

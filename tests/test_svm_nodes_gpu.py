@@ -45,7 +45,7 @@ def test_procedural_material_image(ref, device):
 
 
 def test_unsupported_node_is_refused(ref, device):
-    """A node outside the supported subset (Wavelength) is refused when its program
+    """A node outside the supported subset (Bump: it needs ray differentials) is refused when its program
     is bound - never skipped or approximated."""
     from raytracingproject_b200.device import DeviceError
     desc = scenes.cornell(64, 36, materials="diffuse")
@@ -56,10 +56,10 @@ def test_unsupported_node_is_refused(ref, device):
         '  <connect from="g position" to="l vector1"/>\n'
         '  <math name="t" type="multiply_add" value2="100" value3="450"/>\n'
         '  <connect from="l value" to="t value1"/>\n'
-        '  <wavelength name="m"/>\n'
-        '  <connect from="t value" to="m wavelength"/>\n'
-        '  <connect from="m color" to="d color"/>\n', 1)
-    assert "wavelength" in desc.xml
+        '  <bump name="m" strength="0.6"/>\n'
+        '  <connect from="t value" to="m height"/>\n'
+        '  <connect from="m normal" to="d normal"/>\n', 1)
+    assert "<bump" in desc.xml
     rs = ref.build_scene(desc)
     try:
         arrays = rs.device_arrays()
