@@ -93,6 +93,7 @@ struct PathPool {
   void *block = nullptr;
   size_t bytes = 0;
   bool has_ts = false; /* transparent-shadow arrays carved */
+  bool has_ao = false; /* shadow queue sized for two entries per path (light + AO ray) */
   WFCounters *h_counters = nullptr; /* pinned */
 };
 
@@ -724,6 +725,44 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
         }
       }
 
+      if (EXT && alive && kd_int(KD_INT_USE_AMBIENT_OCCLUSION)) {
+        /* kernel_path_ao (kernel_path.h:328-372): one cosine-weighted ray of length
+         * ao_distance around the averaged diffuse normal; it joins the shadow queue as a
+         * second entry of this path, its contribution is throughput * ao_bsdf */
+        float bsdf_u, bsdf_v;
+        path_state_rng_2D<EXT>(st, CY_PRNG_BSDF_U, &bsdf_u, &bsdf_v);
+        const float ao_factor = kd_float(KD_BG_AO_FACTOR);
+        f3 ao_bsdf = zero3(), ao_N = zero3();
+        for (int k = 0; k < sd.num_closure; k++) { /* shader_bsdf_ao, kernel_shader.h */
+          const Closure &sc = sd.closure[k];
+          if (closure_is_bsdf_diffuse(sc.type)) {
+            ao_bsdf += sc.weight * ao_factor;
+            ao_N += sc.N * fabsf(average(sc.weight));
+          }
+        }
+        ao_N = is_zero(ao_N) ? sd.N : normalize(ao_N);
+        f3 ao_D;
+        float ao_pdf;
+        sample_cos_hemisphere(ao_N, bsdf_u, bsdf_v, &ao_D, &ao_pdf);
+        if (dot(sd.Ng, ao_D) > 0.0f && ao_pdf != 0.0f) {
+          const f3 aP = ray_offset(sd.P, sd.Ng);
+          const f3 contribution = throughput * ao_bsdf;
+          /* one returning atomic per warp */
+          const unsigned int m = __activemask();
+          const unsigned int lane = threadIdx.x & 31u;
+          unsigned int base = 0;
+          if (lane == (unsigned int)(__ffs(m) - 1))
+            base = atomicAdd(&c->n_shadow, (unsigned int)__popc(m));
+          base = __shfl_sync(m, base, __ffs(m) - 1);
+          const unsigned int slot = base + __popc(m & ((1u << lane) - 1u));
+          p.q_shadow[slot] = i;
+          p.sh_P_t[slot] = make_float4(aP.x, aP.y, aP.z, kd_float(KD_BG_AO_DISTANCE));
+          p.sh_D[slot] = make_float4(ao_D.x, ao_D.y, ao_D.z,
+                                     __uint_as_float(CY_PATH_RAY_SHADOW_OPAQUE));
+          p.sh_contrib[slot] = make_float4(contribution.x, contribution.y, contribution.z, 0.0f);
+        }
+      }
+
       if (alive) {
         /* direct light - kernel_path_surface.h:22-125 with one light sample */
         if (kd_int(KD_INT_USE_DIRECT_LIGHT) && (sd.flag & CY_SD_BSDF_HAS_EVAL)) {
@@ -895,11 +934,20 @@ template<bool TRANSPARENT> struct ShadowJob {
       /* shade_shadow - path_radiance_accum_light, kernel_accumulate.h:402-459 */
       const int i = p.q_shadow[qi];
       const float4 cn = p.sh_contrib[qi];
-      float4 L = p.L[i];
-      L.x += cn.x;
-      L.y += cn.y;
-      L.z += cn.z;
-      p.L[i] = L;
+      if (kd_int(KD_INT_USE_AMBIENT_OCCLUSION)) {
+        /* the light ray and the AO ray of one path are in the same launch */
+        float *L = (float *)&p.L[i];
+        atomicAdd(L + 0, cn.x);
+        atomicAdd(L + 1, cn.y);
+        atomicAdd(L + 2, cn.z);
+      }
+      else {
+        float4 L = p.L[i];
+        L.x += cn.x;
+        L.y += cn.y;
+        L.z += cn.z;
+        p.L[i] = L;
+      }
     }
     else if (TRANSPARENT) {
       /* shadow_blocked_transparent_stepped (kernel_shadow.h:354-368): the first hit found
@@ -1229,15 +1277,16 @@ static void free_pool(b200_ctx *ctx)
 
 #define PATH_POOL_BYTES_PER_PATH 228 /* 12 float4 + 8 words per path, see the carve list */
 
-static int ensure_pool(b200_ctx *ctx, size_t capacity, bool transparent_shadows)
+static int ensure_pool(b200_ctx *ctx, size_t capacity, bool transparent_shadows, bool ao)
 {
   if (ctx->pool && ctx->pool->capacity >= capacity &&
-      (ctx->pool->has_ts || !transparent_shadows))
+      (ctx->pool->has_ts || !transparent_shadows) && (ctx->pool->has_ao || !ao))
     return B200_OK;
   free_pool(ctx);
   PathPool *pool = new PathPool();
   pool->capacity = capacity;
   pool->has_ts = transparent_shadows;
+  pool->has_ao = ao;
   /* carve one allocation; every array 256-byte aligned */
   size_t off = 0;
   auto carve = [&](size_t bytes) {
@@ -1246,12 +1295,13 @@ static int ensure_pool(b200_ctx *ctx, size_t capacity, bool transparent_shadows)
     return o;
   };
   const size_t n = capacity;
+  const size_t nsh = ao ? 2 * n : n; /* ambient occlusion: a second shadow ray per path */
   size_t o_nrayP = carve(n * 16), o_nrayD = carve(n * 16), o_rpdf = carve(n * 4);
   size_t o_rayP = carve(n * 16), o_rayD = carve(n * 16), o_hit = carve(n * 16),
          o_hobj = carve(n * 4), o_thr = carve(n * 16), o_L = carve(n * 16), o_sA = carve(n * 16),
-         o_sB = carve(n * 16), o_shP = carve(n * 16), o_shD = carve(n * 16), o_shC = carve(n * 16),
+         o_sB = carve(n * 16), o_shP = carve(nsh * 16), o_shD = carve(nsh * 16), o_shC = carve(nsh * 16),
          o_key = carve(n * 4), o_qa = carve(n * 4), o_qn = carve(n * 4), o_qs = carve(n * 8),
-         o_qsh = carve(n * 4), o_cnt = carve(sizeof(WFCounters));
+         o_qsh = carve(nsh * 4), o_cnt = carve(sizeof(WFCounters));
   /* transparent-shadow stepping queues: 88 bytes per path more, only when needed */
   const size_t nts = transparent_shadows ? n : 0;
   size_t o_tsP0 = carve(nts * 16), o_tsP1 = carve(nts * 16), o_tsD0 = carve(nts * 16),
@@ -1598,8 +1648,8 @@ static int check_scope(b200_ctx *ctx)
     why = "branched path tracing is outside the hot-path scope";
   else if (I(KD_INT_USE_VOLUMES))
     why = "volumes are outside the hot-path scope";
-  else if (I(KD_INT_USE_AMBIENT_OCCLUSION))
-    why = "ambient occlusion is outside the hot-path scope";
+  else if (I(KD_INT_USE_AMBIENT_OCCLUSION) && I(KD_INT_TRANSPARENT_SHADOWS))
+    why = "ambient occlusion together with transparent shadows is outside the hot-path scope";
   else if (I(KD_BG_USE_MIS))
     why = "background importance sampling is outside the hot-path scope";
   else if (I(KD_FILM_USE_LIGHT_PASS) || I(KD_FILM_PASS_DENOISING_DATA) ||
@@ -1657,7 +1707,8 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
         cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
       const size_t held = ctx->pool ? ctx->pool->capacity * PATH_POOL_BYTES_PER_PATH : 0;
       const size_t per_path = PATH_POOL_BYTES_PER_PATH +
-                              (kd_host<int>(ctx, KD_INT_TRANSPARENT_SHADOWS) ? 88 : 0);
+                              (kd_host<int>(ctx, KD_INT_TRANSPARENT_SHADOWS) ? 88 : 0) +
+                              (kd_host<int>(ctx, KD_INT_USE_AMBIENT_OCCLUSION) ? 52 : 0);
       const size_t fit = (free_b + held) / 4 / per_path;
       capacity = std::max<size_t>(std::min(capacity, fit), (size_t)1 << 16);
     }
@@ -1665,12 +1716,14 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
   const bool transparent_shadows = kd_host<int>(ctx, KD_INT_TRANSPARENT_SHADOWS) != 0;
   /* the full shading kernels: extended SVM nodes or sheen (svm_validate), an object with a
    * shadow terminator offset (terminator terms of bsdf_eval / bsdf_sample), the table
-   * sampling pattern - or a lean batch that met a shader it could not run (a closure whose
+   * sampling pattern, ambient occlusion - or a lean batch that met a shader it could not run (a closure whose
    * linked normal differs from the shading normal), see the retry below */
   bool svm_ext = ctx->force_svm_ext || (ctx->svm_features & SVM_USES_EXTENDED_NODES) != 0 ||
                        ctx->has_terminator_offset ||
-                       kd_host<int>(ctx, KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_PMJ;
-  rc = ensure_pool(ctx, std::max<size_t>(capacity, (size_t)tile->w), transparent_shadows);
+                       kd_host<int>(ctx, KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_PMJ ||
+                       kd_host<int>(ctx, KD_INT_USE_AMBIENT_OCCLUSION) != 0;
+  const bool use_ao = kd_host<int>(ctx, KD_INT_USE_AMBIENT_OCCLUSION) != 0;
+  rc = ensure_pool(ctx, std::max<size_t>(capacity, (size_t)tile->w), transparent_shadows, use_ao);
   if (rc)
     return rc;
   PathPool *pool = ctx->pool;

@@ -98,9 +98,9 @@ def _header(width, height, cam_m34, fov, integrator, film="", nearclip=0.1, farc
     )
 
 
-def _background(color, strength=1.0):
+def _background(color, strength=1.0, attrs=""):
     return (
-        "<background>\n"
+        "<background%s>\n" % attrs +
         '  <background name="bg" color="%s" strength="%s"/>\n'
         '  <connect from="bg background" to="output surface"/>\n'
         "</background>\n" % (_f(color), _f(strength))
@@ -690,7 +690,7 @@ def terrain(width=1920, height=1080, spp=256, n=708, max_bounce=0):
 # ---------------------------------------------------------------- config 3
 def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
             materials="principled", light="area", panes=0, transparent_max=8, pattern="sobol",
-            cam_type="perspective", cam_extra="", cam_pose=None):
+            cam_type="perspective", cam_extra="", cam_pose=None, ao=None):
     """BASELINE config 3 - Cornell box, ceiling area light, one metallic and one
     glass Principled box (materials="diffuse" gives the all-diffuse variant).
     light="mesh" replaces the lamp by an emissive quad (a mesh light: its two triangles
@@ -706,7 +706,9 @@ def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
                    _integrator(max_bounce, clamp_indirect=10.0, transparent=transparent_max,
                                pattern=pattern, aa_samples=spp),
                    nearclip=0.01, farclip=100.0, cam_type=cam_type, cam_extra=cam_extra)
-    xml += _background((0, 0, 0), 0.0)
+    # ao = (factor, distance): world ambient occlusion (kernel_path_ao)
+    xml += _background((0, 0, 0), 0.0, "" if ao is None else
+                       ' use_ao="true" ao_factor="%s" ao_distance="%s"' % (_f(ao[0]), _f(ao[1])))
     closure_variants = {"closures": 0, "closures2": 1, "transparent_opaque_shadow": 2,
                         "transparent": 3, "textured": 10, "textured2": 11, "textured3": 12, "textured4": 13}
     if materials in ("textured", "textured2", "textured3", "textured4"):

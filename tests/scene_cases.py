@@ -104,6 +104,16 @@ def texture_cases():
     }
 
 
+def ao_cases():
+    """World ambient occlusion (kernel_path_ao): a second shadow ray per path and bounce,
+    cosine-sampled around the averaged diffuse normal, short and long reach."""
+    return {
+        "cornell_ao": scenes.cornell(W, H, materials="diffuse", ao=(0.6, 0.8)),
+        "cornell_ao_principled": scenes.cornell(W, H, materials="principled", ao=(0.3, 5.0)),
+        "cornell_ao_textured": scenes.cornell(W, H, materials="textured3", ao=(0.5, 0.4)),
+    }
+
+
 def light_cases():
     """Lamp types of kernel_light.h beyond the configs' point / sun / area: a spot with
     a smooth edge, and three lamps of different types in one light distribution."""

@@ -74,7 +74,6 @@ def test_empty_work_leaves_the_film_alone(ref, device):
 
 
 @pytest.mark.parametrize("field,value,needle", [
-    ("KD_INT_USE_AMBIENT_OCCLUSION", 1, "ambient occlusion"),
     ("KD_INT_USE_VOLUMES", 1, "volumes"),
     ("KD_INT_BRANCHED", 1, "branched"),
     ("KD_BVH_HAVE_CURVES", 1, "curves"),

@@ -6,7 +6,7 @@ gates hold at any spp, not only at 1024."""
 import numpy as np
 import pytest
 
-from scene_cases import (camera_cases, closure_cases, light_cases, principled_cases,
+from scene_cases import (ao_cases, camera_cases, closure_cases, light_cases, principled_cases,
                          sampling_cases, small_cases, texture_cases)
 
 pytestmark = pytest.mark.gpu
@@ -145,6 +145,22 @@ def test_sheen_alone_selects_the_full_interpreter(ref, device):
         got = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP)
         assert device.stats()["svm_extended"] == 1
         image_gates(ref_img, got, SPP, "principled with sheen")
+    finally:
+        rs.close()
+
+
+@pytest.mark.parametrize("name", ["cornell_ao", "cornell_ao_principled", "cornell_ao_textured"])
+def test_ambient_occlusion_matches_reference(ref, device, name):
+    desc = ao_cases()[name]
+    rs = ref.build_scene(desc)
+    try:
+        device.upload_scene(rs.device_arrays())
+        ref_img, _ = rs.render(0, SPP, tile_size=64)
+        got = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP)
+        st = device.stats()
+        # every surviving surface hit adds an AO ray to the light ray
+        assert st["shadow_rays"] > st["bounce_rays"]
+        image_gates(ref_img, got, SPP, name)
     finally:
         rs.close()
 
