@@ -918,7 +918,10 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
 
 /* -------------------------------------- intersect_shadow + shade_shadow */
 
-template<bool TRANSPARENT> struct ShadowJob {
+/* AO: the light ray and the ambient-occlusion ray of one path are in the same launch,
+ * so unoccluded contributions are added atomically (a compile-time variant: the test
+ * at run time cost the plain kernel 7 %) */
+template<bool TRANSPARENT, bool AO = false> struct ShadowJob {
   PathSoA p;
   __device__ __forceinline__ const float4 *ray_P(unsigned int qi) const
   {
@@ -934,8 +937,7 @@ template<bool TRANSPARENT> struct ShadowJob {
       /* shade_shadow - path_radiance_accum_light, kernel_accumulate.h:402-459 */
       const int i = p.q_shadow[qi];
       const float4 cn = p.sh_contrib[qi];
-      if (kd_int(KD_INT_USE_AMBIENT_OCCLUSION)) {
-        /* the light ray and the AO ray of one path are in the same launch */
+      if (AO) {
         float *L = (float *)&p.L[i];
         atomicAdd(L + 0, cn.x);
         atomicAdd(L + 1, cn.y);
@@ -1094,14 +1096,14 @@ __global__ void k_shadow_step_end(PathSoA p, int cur)
   c->work_ts = 0;
 }
 
-template<bool COUNT, bool TRANSPARENT>
+template<bool COUNT, bool TRANSPARENT, bool AO = false>
 __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS)
     k_intersect_shadow(PathSoA p, int refill_threshold)
 {
   const unsigned lane = threadIdx.x & 31u;
   TraceCounters cnt;
   cnt.nodes = cnt.tris = cnt.instances = 0;
-  ShadowJob<TRANSPARENT> job;
+  ShadowJob<TRANSPARENT, AO> job;
   job.p = p;
   trace_persistent<true, COUNT>(job, p.counters->n_shadow, &p.counters->work_shadow,
                                 refill_threshold, cnt);
@@ -1793,7 +1795,9 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
           k_shade_surface<false><<<grid_wide, WF_BLOCK, 0, st>>>(soa, num_keys);
         }
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev3, st));
-        if (transparent_shadows)
+        if (use_ao) /* never with transparent shadows (check_scope) */
+          k_intersect_shadow<false, false, true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
+        else if (transparent_shadows)
           k_intersect_shadow<false, true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
         else if (count)
           k_intersect_shadow<true, false><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
