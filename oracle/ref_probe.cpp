@@ -422,6 +422,12 @@ int ref_probe_svm_node(KernelGlobals *kg, const void *nodes, int offset, float *
     case NODE_TEX_WHITE_NOISE:
       svm_node_tex_white_noise(kg, sd, stack, node.y, node.z, node.w, &offset);
       break;
+    case NODE_TANGENT:
+      svm_node_tangent(kg, sd, stack, node);
+      break;
+    case NODE_NORMAL_MAP:
+      svm_node_normal_map(kg, sd, stack, node);
+      break;
     case NODE_BLACKBODY:
       svm_node_blackbody(kg, sd, stack, node.y, node.z);
       break;

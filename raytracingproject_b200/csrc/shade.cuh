@@ -645,6 +645,12 @@ __device__ __noinline__ int svm_eval_extended_node(ShaderDataG &sd, float *stack
     case CY_NODE_TEX_NOISE:
       svm_node_tex_noise(stack, node, &offset);
       break;
+    case CY_NODE_TANGENT:
+      svm_node_tangent(sd, stack, node);
+      break;
+    case CY_NODE_NORMAL_MAP:
+      svm_node_normal_map(sd, stack, node);
+      break;
     case CY_NODE_BLACKBODY:
       svm_node_blackbody(stack, node);
       break;

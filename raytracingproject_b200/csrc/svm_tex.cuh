@@ -1012,6 +1012,150 @@ SVM_TEX_FN void svm_node_tex_white_noise(float *stack, uint4 node)
     stack[value_offset] = value;
 }
 
+/* -------------------------------------------------- tangent, normal map */
+
+/* svm_tex_coord.h:363-411 (Tangent node): the UV-map tangent attribute, or a radial
+ * tangent from the generated coordinates (the position where the mesh has none) */
+SVM_TEX_FN void svm_node_tangent(const ShaderDataG &sd, float *stack, uint4 node)
+{
+  uint32_t tangent_offset, direction_type, axis;
+  unpack_uchar3(node.y, &tangent_offset, &direction_type, &axis);
+  const AttrDesc desc = find_attribute(sd, node.z);
+  const bool found = desc.offset != CY_ATTR_STD_NOT_FOUND;
+  f3 value = zero3();
+  if (found) {
+    if (desc.type == CY_NODE_ATTR_FLOAT2) {
+      const float2 v = attribute_float2(sd, desc);
+      value = mk3(v.x, v.y, 0.0f);
+    }
+    else {
+      value = attribute_float3(sd, desc);
+    }
+  }
+  f3 tangent;
+  if (direction_type == CY_NODE_TANGENT_UVMAP) {
+    tangent = found ? value : zero3();
+  }
+  else {
+    const f3 g = found ? value : sd.P;
+    if (axis == CY_NODE_TANGENT_AXIS_X)
+      tangent = mk3(0.0f, -(g.z - 0.5f), (g.y - 0.5f));
+    else if (axis == CY_NODE_TANGENT_AXIS_Y)
+      tangent = mk3(-(g.z - 0.5f), 0.0f, (g.x - 0.5f));
+    else
+      tangent = mk3(-(g.y - 0.5f), (g.x - 0.5f), 0.0f);
+  }
+  if (sd.object != -1) /* surfaces only: the reference reads an unset transform otherwise */
+    tangent = object_normal_transform(sd.object, tangent);
+  tangent = cross(sd.N, normalize(cross(tangent, sd.N)));
+  stack_store_float3(stack, tangent_offset, tangent);
+}
+
+/* kernel_montecarlo.h:196-299: bend a shading normal back until the reflection of I
+ * about it leaves the geometric surface */
+CY_DEV f3 ensure_valid_reflection(f3 Ng, f3 I, f3 N)
+{
+  const f3 R = 2 * dot(N, I) * N - I;
+  const float threshold = fminf(0.9f * dot(Ng, I), 0.01f);
+  if (dot(Ng, R) >= threshold)
+    return N;
+  const float NdotNg = dot(N, Ng);
+  const f3 X = normalize(N - NdotNg * Ng);
+  const float Ix = dot(I, X), Iz = dot(I, Ng);
+  const float Ix2 = sqr(Ix), Iz2 = sqr(Iz);
+  const float a = Ix2 + Iz2;
+  const float b = safe_sqrtf(Ix2 * (a - sqr(threshold)));
+  const float c = Iz * threshold + a;
+  const float fac = 0.5f / a;
+  const float N1_z2 = fac * (b + c), N2_z2 = fac * (-b + c);
+  bool valid1 = (N1_z2 > 1e-5f) && (N1_z2 <= (1.0f + 1e-5f));
+  bool valid2 = (N2_z2 > 1e-5f) && (N2_z2 <= (1.0f + 1e-5f));
+  float nx, ny;
+  if (valid1 && valid2) {
+    const float n1x = safe_sqrtf(1.0f - N1_z2), n1y = safe_sqrtf(N1_z2);
+    const float n2x = safe_sqrtf(1.0f - N2_z2), n2y = safe_sqrtf(N2_z2);
+    const float R1 = 2 * (n1x * Ix + n1y * Iz) * n1y - Iz;
+    const float R2 = 2 * (n2x * Ix + n2y * Iz) * n2y - Iz;
+    valid1 = (R1 >= 1e-5f);
+    valid2 = (R2 >= 1e-5f);
+    /* both valid: the shallower reflection; else the positive one */
+    const bool first = (valid1 && valid2) ? (R1 < R2) : (R1 > R2);
+    nx = first ? n1x : n2x;
+    ny = first ? n1y : n2y;
+  }
+  else if (valid1 || valid2) {
+    const float Nz2 = valid1 ? N1_z2 : N2_z2;
+    nx = safe_sqrtf(1.0f - Nz2);
+    ny = safe_sqrtf(Nz2);
+  }
+  else {
+    return Ng;
+  }
+  return nx * X + ny * Ng;
+}
+
+/* svm_tex_coord.h:264-361 (Normal Map node): tangent space with the host's tangent and
+ * sign attributes, object / world space and their Blender-convention variants */
+SVM_TEX_FN void svm_node_normal_map(const ShaderDataG &sd, float *stack, uint4 node)
+{
+  const uint32_t color_offset = node.y & 0xff, strength_offset = (node.y >> 8) & 0xff,
+                 normal_offset = (node.y >> 16) & 0xff, space = (node.y >> 24) & 0xff;
+  f3 color = stack_load_float3(stack, color_offset);
+  color = 2.0f * mk3(color.x - 0.5f, color.y - 0.5f, color.z - 0.5f);
+  const bool is_backfacing = (sd.flag & CY_SD_BACKFACING) != 0;
+  f3 N;
+  if (space == CY_NODE_NORMAL_MAP_TANGENT) {
+    if (sd.object == -1) {
+      stack_store_float3(stack, normal_offset, zero3());
+      return;
+    }
+    const AttrDesc attr = find_attribute(sd, node.z);
+    const AttrDesc attr_sign = find_attribute(sd, node.w);
+    const AttrDesc attr_normal = find_attribute(sd, CY_ATTR_STD_VERTEX_NORMAL);
+    if (attr.offset == CY_ATTR_STD_NOT_FOUND || attr_sign.offset == CY_ATTR_STD_NOT_FOUND ||
+        attr_normal.offset == CY_ATTR_STD_NOT_FOUND) {
+      stack_store_float3(stack, normal_offset, zero3());
+      return;
+    }
+    const f3 tangent = attribute_float3(sd, attr);
+    const float sign = attribute_float(sd, attr_sign);
+    f3 normal;
+    if (sd.shader & CY_SHADER_SMOOTH_NORMAL) {
+      normal = attribute_float3(sd, attr_normal);
+    }
+    else {
+      normal = is_backfacing ? -sd.Ng : sd.Ng;
+      normal = normalize(transform_direction_transposed(object_tfm(sd.object), normal));
+    }
+    const f3 B = sign * cross(normal, tangent);
+    N = safe_normalize(color.x * tangent + color.y * B + color.z * normal);
+    N = object_normal_transform(sd.object, N);
+  }
+  else {
+    if (space == CY_NODE_NORMAL_MAP_BLENDER_OBJECT || space == CY_NODE_NORMAL_MAP_BLENDER_WORLD) {
+      color.y = -color.y;
+      color.z = -color.z;
+    }
+    N = color;
+    if ((space == CY_NODE_NORMAL_MAP_OBJECT || space == CY_NODE_NORMAL_MAP_BLENDER_OBJECT) &&
+        sd.object != -1)
+      N = object_normal_transform(sd.object, N);
+    else
+      N = safe_normalize(N);
+  }
+  if (is_backfacing)
+    N = -N;
+  float strength = stack[strength_offset];
+  if (strength != 1.0f) {
+    strength = fmaxf(strength, 0.0f);
+    N = safe_normalize(sd.N + (N - sd.N) * strength);
+  }
+  N = ensure_valid_reflection(sd.Ng, sd.I, N);
+  if (is_zero(N))
+    N = sd.N;
+  stack_store_float3(stack, normal_offset, N);
+}
+
 #include "svm_tex_cells.cuh"
 
 #endif /* B200_SVM_TEX_CUH */

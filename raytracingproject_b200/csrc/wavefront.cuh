@@ -1450,6 +1450,10 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
       case CY_NODE_OBJECT_INFO:
       case CY_NODE_CAMERA:
       case CY_NODE_TEX_WHITE_NOISE:
+      case CY_NODE_TANGENT:
+      case CY_NODE_NORMAL_MAP:
+        *features |= SVM_USES_ATTRIBUTES;
+        /* fall through */
       case CY_NODE_BLACKBODY:
       case CY_NODE_WAVELENGTH:
         *features |= SVM_USES_EXTENDED_NODES;

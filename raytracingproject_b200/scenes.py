@@ -440,8 +440,9 @@ def _textured_shaders(variant):
             '  <vector_math name="ad" type="add"/>\n' + c("mx color", "ad vector1") +
             c("oi location", "ad vector2") +
             '  <vector_math name="fr" type="fraction"/>\n' + c("ad vector", "fr vector1") +
+            '  <tangent name="tg" direction_type="radial" axis="y"/>\n'
             '  <anisotropic_bsdf name="gl" distribution="GGX" roughness="0.3" anisotropy="-0.5"/>\n' +
-            c("fr vector", "gl color"), "gl bsdf")
+            c("fr vector", "gl color") + c("tg tangent", "gl tangent"), "gl bsdf")
         glass = _node_shader(
             "glass", '  <geometry name="g"/>\n'
             '  <normal name="nn" direction="0.3 -0.5 0.8"/>\n' + c("g normal", "nn normal") +
@@ -458,8 +459,10 @@ def _textured_shaders(variant):
             '  <vector_math name="fr" type="fraction"/>\n' + c("ad vector", "fr vector1") +
             '  <mix name="mx" type="mix" color2="0.9 0.9 0.9"/>\n' + c("fr vector", "mx color1") +
             c("nn dot", "mx fac") +
+            '  <normal_map name="nmap" space="object" strength="0.7"/>\n' +
+            c("fr vector", "nmap color") +
             '  <principled_bsdf name="p" distribution="GGX" roughness="0.4" sheen="0.5"/>\n' +
-            c("mx color", "p base_color"), "p bsdf")
+            c("mx color", "p base_color") + c("nmap normal", "p normal"), "p bsdf")
     else:
         white = _node_shader(
             "white", '  <texture_coordinate name="tc"/>\n'

@@ -125,6 +125,12 @@ extern "C" __attribute__((visibility("default"))) int host_svm_node(int offset, 
     case CY_NODE_TEX_WHITE_NOISE:
       svm_node_tex_white_noise(stack, node);
       break;
+    case CY_NODE_TANGENT:
+      svm_node_tangent(sd, stack, node);
+      break;
+    case CY_NODE_NORMAL_MAP:
+      svm_node_normal_map(sd, stack, node);
+      break;
     case CY_NODE_BLACKBODY:
       svm_node_blackbody(stack, node);
       break;

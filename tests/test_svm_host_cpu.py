@@ -112,7 +112,7 @@ def texture_ops():
                               "NODE_VECTOR_TRANSFORM", "NODE_OBJECT_INFO", "NODE_CAMERA",
                               "NODE_TEX_WHITE_NOISE", "NODE_MIX", "NODE_MATH",
                               "NODE_TEX_VORONOI", "NODE_TEX_MUSGRAVE", "NODE_BLACKBODY",
-                              "NODE_WAVELENGTH",
+                              "NODE_WAVELENGTH", "NODE_TANGENT", "NODE_NORMAL_MAP",
                               "NODE_VECTOR_MATH", "NODE_CONVERT", "NODE_INVERT", "NODE_GAMMA",
                               "NODE_BRIGHTCONTRAST", "NODE_CLAMP", "NODE_FRESNEL",
                               "NODE_LAYER_WEIGHT", "NODE_RGB_RAMP", "NODE_RGB_CURVES",
@@ -167,7 +167,10 @@ def test_compiled_texture_nodes_match_reference(ref, host_lib, materials):
             nxt = None
             if os.environ.get("SVM_HOST_TRACE"):
                 print("node", ops[op], off, nodes[off].tolist(), flush=True)
+            surface_only = ops[op] in ("NODE_TANGENT", "NODE_NORMAL_MAP")
             for i in range(len(pts)):
+                if surface_only and pts["object"][i] < 0:
+                    continue  # off a surface the reference transforms by an unset matrix
                 stack0 = rng.uniform(-2.0, 2.0, 264).astype(np.float32)
                 n_ref, n_dev, s_ref, s_dev = run_both(host_lib, rs, nodes, off, stack0,
                                                       pts[i:i + 1])
@@ -224,6 +227,8 @@ VALUE_NODE_SPECS = {
     "NODE_OBJECT_INFO": {"yzw": (5, O, O)},
     "NODE_CAMERA": {"yzw": (O, O, O)},
     "NODE_TEX_WHITE_NOISE": {"yzw": ("dims", "packed", "packed")},
+    "NODE_TANGENT": {"yzw": ((O, 2, 3), "attr", "attr")},
+    "NODE_NORMAL_MAP": {"yzw": ((O, O, O, 5), "attr", "attr")},
     "NODE_BLACKBODY": {"yzw": (O, O, O)},
     "NODE_WAVELENGTH": {"yzw": (O, O, O)},
     "NODE_TEX_MUSGRAVE": {"yzw": ((5, "dims", O, O), "packed", "packed"),
@@ -235,6 +240,8 @@ VALUE_NODE_SPECS = {
 
 def random_program(op_name, rng, a):
     """One random encoding of `op_name` followed by its data words."""
+    text = open(os.path.join(ROOT, "include", "cycles_abi.h")).read()
+    a_std = {k: int(v) for k, v in re.findall(r"#define CY_ATTR_STD_(\w+)[ \t]+(\d+)", text)}
     slot = lambda: int(rng.choice([255, int(rng.integers(0, 60)) * 4]))  # invalid -> default
     used = lambda: int(rng.integers(0, 60)) * 4
     pack = lambda *b: int(sum(int(x) << (8 * i) for i, x in enumerate(b)))
@@ -279,7 +286,10 @@ def random_program(op_name, rng, a):
     elif op_name in VALUE_NODE_SPECS:
         spec = VALUE_NODE_SPECS[op_name]
         word = {"off": used, "packed": lambda: pack(used(), used(), used(), used()),
-                "float": lambda: fbits(0.2, 2.5), "dims": lambda: int(rng.integers(1, 5))}
+                "float": lambda: fbits(0.2, 2.5), "dims": lambda: int(rng.integers(1, 5)),
+                # generated, UV, vertex normal, or an id no mesh has
+                "attr": lambda: int(rng.choice([a_std["GENERATED"], a_std["UV"],
+                                                a_std["VERTEX_NORMAL"], 4000]))}
         for col, kind in zip((1, 2, 3), spec["yzw"]):
             if isinstance(kind, int):
                 prog[0, col] = rng.integers(0, kind)
@@ -335,6 +345,10 @@ def test_random_node_encodings_match_reference(ref, host_lib, op_name):
         a = abi()
         rng = np.random.default_rng(zlib.crc32(op_name.encode()))
         pts = shading_points(arrays, 64, rng)
+        if op_name in ("NODE_TANGENT", "NODE_NORMAL_MAP"):
+            # surface points only: off a surface the reference transforms by an unset matrix
+            pts["object"], pts["prim"] = np.maximum(pts["object"], 0), np.maximum(pts["prim"], 0)
+            pts["lamp"] = -1
         wrote = 0
         for trial in range(300):
             prog = random_program(op_name, rng, a)
