@@ -15,6 +15,14 @@
 #include "device_scene.cuh"
 #include "traverse.cuh"
 
+/* one __constant__ DeviceScene per GPU: which context's block it holds, and a lock per GPU
+ * for the calls that launch kernels reading it (see DeviceUse) */
+#define MAX_GPUS 16
+static std::mutex g_owner_mutex;
+static std::mutex g_device_mutex[MAX_GPUS];
+static b200_ctx *g_constant_owner[MAX_GPUS] = {};
+
+
 /* ------------------------------------------------------------------ utils */
 
 #define CUDA_TRY(ctx, call) \
@@ -225,6 +233,11 @@ void b200_destroy(b200_ctx *ctx)
     return;
   DeviceGuard guard(ctx->ordinal);
   cudaStreamSynchronize(ctx->stream);
+  {
+    std::lock_guard<std::mutex> lock(g_owner_mutex);
+    if (g_constant_owner[ctx->ordinal & (MAX_GPUS - 1)] == ctx)
+      g_constant_owner[ctx->ordinal & (MAX_GPUS - 1)] = nullptr;
+  }
   free_pool(ctx);
   for (auto &a : ctx->allocs)
     cudaFree((void *)a.first);
@@ -601,10 +614,33 @@ static int prepare_scene(b200_ctx *ctx)
   ds.attributes_float3 = (const float4 *)ptr("__attributes_float3");
   ds.attributes_uchar4 = (const uchar4 *)ptr("__attributes_uchar4");
   memcpy(ds.kdata, ctx->kernel_data.data(), SIZEOF_KERNEL_DATA);
-  CUDA_TRY(ctx, cudaMemcpyToSymbol(g_scene, &ds, sizeof(ds)));
+  ctx->constant_block.assign((const uint8_t *)&ds, (const uint8_t *)&ds + sizeof(ds));
+  {
+    std::lock_guard<std::mutex> lock(g_owner_mutex);
+    CUDA_TRY(ctx, cudaMemcpyToSymbol(g_scene, &ds, sizeof(ds)));
+    g_constant_owner[ctx->ordinal & (MAX_GPUS - 1)] = ctx;
+  }
   ctx->scene_dirty = false;
   return B200_OK;
 }
+
+/* Held for the length of a call that launches kernels reading g_scene: serialises the
+ * contexts of ONE GPU (they share its constant block and the scope-miss flag) and makes
+ * sure the block is this context's.  Contexts of different GPUs never meet here. */
+struct DeviceUse {
+  std::unique_lock<std::mutex> lock;
+  explicit DeviceUse(b200_ctx *ctx) : lock(g_device_mutex[ctx->ordinal & (MAX_GPUS - 1)])
+  {
+    std::lock_guard<std::mutex> owner_lock(g_owner_mutex);
+    b200_ctx *&owner = g_constant_owner[ctx->ordinal & (MAX_GPUS - 1)];
+    if (owner != ctx && !ctx->constant_block.empty()) {
+      DeviceGuard guard(ctx->ordinal);
+      cudaDeviceSynchronize();
+      cudaMemcpyToSymbol(g_scene, ctx->constant_block.data(), ctx->constant_block.size());
+      owner = ctx;
+    }
+  }
+};
 
 static int launch_grid(const b200_ctx *ctx, int blocks_per_sm)
 {
@@ -625,6 +661,7 @@ int b200_build_bvh(b200_ctx *ctx, b200_bvh_info *info)
 {
   if (!ctx)
     return B200_ERR_INVALID;
+  DeviceUse device_use(ctx);
   ctx->scene_dirty = true;
   int rc = prepare_scene(ctx);
   if (rc)
@@ -640,6 +677,7 @@ int b200_trace_batch(b200_ctx *ctx, uint64_t rays, uint64_t hits, uint64_t n, in
     return B200_ERR_INVALID;
   if (n >= 0xffffffe0ull)
     return fail(ctx, B200_ERR_INVALID, "batch too large (max 2^32-32 rays)");
+  DeviceUse device_use(ctx);
   int rc = prepare_scene(ctx);
   if (rc)
     return rc;

@@ -45,6 +45,10 @@ struct b200_ctx {
   std::map<std::string, HostArray> globals; /* kernel_textures.h name -> binding */
   std::vector<uint8_t> kernel_data;
   bool scene_dirty = true; /* BVH8 / constant block must be (re)built */
+  /* this context's constant block: the __constant__ DeviceScene is one per GPU, so a
+   * context re-uploads its copy when another context of the same GPU used the device
+   * last (DeviceUse in b200_cycles.cu) */
+  std::vector<uint8_t> constant_block;
   bool have_data = false;
   uint32_t svm_features = 0;     /* SVM_USES_* of the bound __svm_nodes (svm_validate) */
   bool has_subd_patches = false; /* __tri_patch holds a patch index */

@@ -1694,6 +1694,7 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
     return B200_ERR_INVALID;
   if (tile->w <= 0 || tile->h <= 0 || tile->num_samples <= 0)
     return B200_OK;
+  DeviceUse device_use(ctx);
   int rc = prepare_scene(ctx);
   if (rc)
     return rc;

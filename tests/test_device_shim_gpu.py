@@ -72,3 +72,41 @@ def test_multi_device_in_one_process(ref):
     assert st["primary_rays"] == desc.width * desc.height * desc.spp
     assert (got2[..., 3] == desc.spp + 3).all()      # alpha counts every sample once
     assert rgba[..., :3].max() > 0
+
+
+def test_two_contexts_with_different_scenes_on_one_gpu(ref):
+    """The kernels read the scene from one __constant__ block per GPU.  Two contexts on
+    the same GPU holding DIFFERENT scenes, rendering in turn (and from two threads at
+    once): each frame must be the one its own scene gives alone."""
+    import threading
+    from raytracingproject_b200 import scenes
+    from raytracingproject_b200.device import B200Device
+    descs = [scenes.cornell(96, 64, spp=4, materials="diffuse"),
+             scenes.default_cube(96, 64, spp=4, material="principled")]
+    devs = [B200Device(0), B200Device(0)]
+    rss = [ref.build_scene(d) for d in descs]
+    try:
+        alone = []
+        for dev, rs, d in zip(devs, rss, descs):
+            dev.upload_scene(rs.device_arrays())
+            alone.append(dev.render(d.width, d.height, rs.pass_stride, 0, 4).copy())
+        assert not np.array_equal(alone[0], alone[1])
+        for _ in range(2):  # in turn: the other context used the GPU last each time
+            for k in (0, 1):
+                got = devs[k].render(descs[k].width, descs[k].height, rss[k].pass_stride, 0, 4)
+                assert np.array_equal(got, alone[k]), k
+        out = [None, None]
+
+        def work(k):
+            for _ in range(3):
+                out[k] = devs[k].render(descs[k].width, descs[k].height, rss[k].pass_stride,
+                                        0, 4).copy()
+        threads = [threading.Thread(target=work, args=(k,)) for k in (0, 1)]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+        assert np.array_equal(out[0], alone[0]) and np.array_equal(out[1], alone[1])
+    finally:
+        for rs in rss:
+            rs.close()
+        for dev in devs:
+            dev.close()
