@@ -283,6 +283,10 @@ def build_scene(desc, kernel=RefScene.GENERIC, external_device=None, threads=0, 
     rs = RefScene(path, kernel=kernel, external_device=external_device, threads=threads)
     handles = [rs.add_mesh(m.P, m.tris, m.shader, m.smooth) for m in desc.meshes]
     for mi, tfm in desc.objects:
-        rs.add_object(handles[mi], tfm)
+        o = rs.add_object(handles[mi], tfm)
+        off = getattr(desc, "terminator_offset", 0.0)
+        if off:
+            rs._L.ref_scene_set_terminator_offset.argtypes = [C.c_void_p, C.c_int, C.c_float]
+            rs._L.ref_scene_set_terminator_offset(rs._h, o, C.c_float(off))
     rs.update(desc.width, desc.height)
     return rs

@@ -252,6 +252,15 @@ int ref_scene_add_object(ref_scene *rs, int mesh, const float *tfm)
   return (int)rs->scene->objects.size() - 1;
 }
 
+/* Object::shadow_terminator_offset (render/object.cpp:105, 544) of one object. */
+int ref_scene_set_terminator_offset(ref_scene *rs, int object, float offset)
+{
+  if (object < 0 || object >= (int)rs->scene->objects.size())
+    return -1;
+  rs->scene->objects[object]->shadow_terminator_offset = offset;
+  return 0;
+}
+
 /* Equivalent of Session::update_scene (session.cpp:909-950). */
 int ref_scene_update(ref_scene *rs, int width, int height)
 {

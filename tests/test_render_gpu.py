@@ -165,6 +165,30 @@ def test_ambient_occlusion_matches_reference(ref, device, name):
         rs.close()
 
 
+def test_shadow_terminator_offset_matches_reference(ref, device):
+    """Object::shadow_terminator_offset on every object: the host sees it in __objects
+    and selects the full kernels, whose bsdf_eval / bsdf_sample apply shift_cos_in."""
+    from raytracingproject_b200 import scenes
+    desc = scenes.cornell(W_SMALL, H_SMALL, materials="principled")
+    desc.terminator_offset = 0.6
+    rs = ref.build_scene(desc)
+    try:
+        device.upload_scene(rs.device_arrays())
+        ref_img, _ = rs.render(0, SPP, tile_size=64)
+        got = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP)
+        assert device.stats()["svm_extended"] == 1
+        image_gates(ref_img, got, SPP, "terminator offset")
+        plain = scenes.cornell(W_SMALL, H_SMALL, materials="principled")
+        rs2 = ref.build_scene(plain)
+        try:
+            other, _ = rs2.render(0, SPP, tile_size=64)
+        finally:
+            rs2.close()
+        assert not np.array_equal(other, ref_img)  # the offset does change the picture
+    finally:
+        rs.close()
+
+
 def test_bent_normal_redoes_the_batch_with_the_full_kernels(ref, device):
     """Only lean nodes, but a BSDF normal that is not the shading normal: the host's scan
     cannot know, the lean kernels notice on the device, nothing of that batch reaches
