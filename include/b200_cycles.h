@@ -97,6 +97,9 @@ int b200_abi_version(void);
 int b200_device_count(void);
 int b200_device_name(int ordinal, char *name, size_t len, int *sm_major, int *sm_minor,
                      uint64_t *total_mem, int *num_sms);
+/* "dddd:bb:dd" PCI location of the device - the stable part of DeviceInfo::id, as
+ * device_cuda_info() builds it (device/device_cuda.cpp:144-152). */
+int b200_device_pci_id(int ordinal, char *buf, size_t len);
 
 /* Context - CUDADevice ctor/dtor (device/cuda/device_cuda_impl.cpp:199-262).
  * Fails (returns NULL, message in err) unless the device is sm_100. */
@@ -149,6 +152,12 @@ int b200_build_bvh(b200_ctx *ctx, b200_bvh_info *info);
  * (task.get_cancel(), device_cuda_impl.cpp:1908). */
 int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *cancel);
 
+/* task.get_cancel() (device/device_task.h:157-163; polled by CUDADevice::render every
+ * sample step, device_cuda_impl.cpp:1939): a host predicate b200_render asks between
+ * wavefront batches, next to the `cancel` flag.  NULL removes it. */
+typedef int (*b200_cancel_fn)(void *user);
+int b200_set_cancel_callback(b200_ctx *ctx, b200_cancel_fn fn, void *user);
+
 /* Parity / benchmark hook: scene_intersect (kernel/bvh/bvh.h:154-237) on a batch
  * of rays resident in device memory.  any_hit != 0 gives the shadow-ray
  * early-out (bvh_traversal.h:144-147): only `prim >= 0` is meaningful then. */
@@ -166,6 +175,14 @@ int b200_film_convert(b200_ctx *ctx, uint64_t film, uint64_t rgba, int half_floa
  * kernel per peer.  The one-process-per-GPU path uses NCCL all-reduce through
  * torch.distributed on the same device pointer instead (bench.py). */
 int b200_film_reduce(b200_ctx **ctxs, int n, const uint64_t *films, size_t n_floats);
+
+/* The same sum as ONE NCCL all-reduce over NVLink / NVSwitch for contexts on n DISTINCT
+ * GPUs of this process (ncclCommInitAll once per set of GPUs, ncclAllReduce on each
+ * context's stream inside a group): afterwards EVERY films[i] holds the sum.  This is
+ * what the in-process multi device uses where the reference's MultiDevice copies tile
+ * slices through the host (device/device_multi.cpp:374-393).  NCCL is resolved at first
+ * use (libnccl.so.2); B200_ERR_UNSUPPORTED when it is missing or a GPU repeats. */
+int b200_film_allreduce(b200_ctx **ctxs, int n, const uint64_t *films, size_t n_floats);
 
 int b200_get_stats(b200_ctx *ctx, b200_stats *out);
 int b200_synchronize(b200_ctx *ctx);

@@ -62,6 +62,8 @@ def lib():
         L.ref_render.argtypes = [
             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
         L.ref_film_convert.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ref_render_tile_buffers.argtypes = [
+            C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
         L.ref_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.ref_camera_rays.argtypes = [
             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -202,6 +204,18 @@ class RefScene:
             self._h, int(start_sample), int(num_samples), int(tile_size), int(accumulate),
             out.ctypes.data, C.byref(sec)))
         return out, sec.value
+
+    def render_tile_buffers(self, start_sample, num_samples, tile_size=64, cancel_after=-1):
+        """The background shape of Session's tile flow: a RenderBuffers per tile, deleted
+        in release_tile on the device's worker thread; task.get_cancel() turns true after
+        `cancel_after` released tiles.  Returns (film, tiles completed)."""
+        w, h, ps = self.width, self.height, self.pass_stride
+        out = np.empty((h, w, ps), dtype=np.float32)
+        done = C.c_int()
+        self._check(self._L.ref_render_tile_buffers(
+            self._h, int(start_sample), int(num_samples), int(tile_size), int(cancel_after),
+            out.ctypes.data, C.byref(done)))
+        return out, done.value
 
     def film_convert(self, num_samples, half_float=False):
         """DeviceTask::FILM_CONVERT of the last rendered film on this scene's device:

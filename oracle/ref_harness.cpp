@@ -11,8 +11,18 @@
  * from the reference sources where they lie (see oracle/Makefile). */
 
 /* CPUDevice is defined in a .cpp, not a header; include it here (in place, not
- * copied) so the probe can reach CPUDevice::kernel_globals. */
+ * copied) so the probe can reach CPUDevice::kernel_globals.  Its three factory
+ * functions are renamed on the way in: the host library (libcycles_host.so,
+ * ref_host_hooks.cpp) owns the names Device::create calls and forwards to these once
+ * this library has registered them (OracleCpuDeviceRegistration below). */
+#include "device/device_intern.h"
+#define device_cpu_create oracle_device_cpu_create
+#define device_cpu_info oracle_device_cpu_info
+#define device_cpu_capabilities oracle_device_cpu_capabilities
 #include "device/device_cpu.cpp"
+#undef device_cpu_create
+#undef device_cpu_info
+#undef device_cpu_capabilities
 
 #include "app/cycles_xml.h"
 #include "render/background.h"
@@ -42,6 +52,18 @@
 #include "ref_probe.h"
 
 using namespace ccl;
+
+extern "C" void ref_host_register_cpu_device(void *create, void *info, void *capabilities);
+namespace {
+struct OracleCpuDeviceRegistration {
+  OracleCpuDeviceRegistration()
+  {
+    ref_host_register_cpu_device((void *)&ccl::oracle_device_cpu_create,
+                                 (void *)&ccl::oracle_device_cpu_info,
+                                 (void *)&ccl::oracle_device_cpu_capabilities);
+  }
+} g_oracle_cpu_device_registration;
+}
 
 /* Only widens access to the per-thread KernelGlobals helpers; every virtual is
  * CPUDevice's own, so renders through it ARE the unmodified reference device. */
@@ -138,7 +160,7 @@ ref_scene *ref_scene_new(const char *xml_path, int kernel, void *external_device
     DebugFlags().cpu.bvh_layout = BVH_LAYOUT_BVH2;
     DebugFlags().cpu.split_kernel = false;
     vector<DeviceInfo> infos;
-    device_cpu_info(infos);
+    oracle_device_cpu_info(infos);
     rs->info = infos[0];
     rs->cpu = new ProbeCPUDevice(rs->info, rs->stats, rs->profiler, true);
     rs->device = rs->cpu;
@@ -444,6 +466,108 @@ int ref_render(ref_scene *rs,
     memcpy(out,
            buffers->buffer.data(),
            sizeof(float) * (size_t)width * height * bp.get_passes_size());
+  }
+  return 0;
+}
+
+/* The background, non-progressive shape of Session::acquire_tile / release_tile
+ * (render/session.cpp:449-460, 505-521): every tile gets its OWN RenderBuffers,
+ * allocated when the device's worker acquires the tile, and release_tile - called on
+ * that same worker thread - copies the pixels out (the write_render_tile_cb step) and
+ * DELETES the tile's RenderBuffers, i.e. Device::mem_free runs inside the running task.
+ * `cancel_after` >= 0 makes task.get_cancel() answer true once that many tiles were
+ * released (Session::cancel / progress.set_cancel).  `out` receives the full frame;
+ * tiles that were never rendered stay zero.  *tiles_done returns how many tiles were
+ * released with all their samples. */
+int ref_render_tile_buffers(ref_scene *rs,
+                            int start_sample,
+                            int num_samples,
+                            int tile_size,
+                            int cancel_after,
+                            float *out,
+                            int *tiles_done)
+{
+  Scene *scene = rs->scene;
+  Device *device = rs->device;
+  const int width = scene->camera->width;
+  const int height = scene->camera->height;
+
+  BufferParams full;
+  full.width = width;
+  full.height = height;
+  full.full_width = width;
+  full.full_height = height;
+  full.passes = scene->passes;
+  const int pass_stride = full.get_passes_size();
+  memset(out, 0, sizeof(float) * (size_t)width * height * pass_stride);
+
+  if (tile_size <= 0)
+    tile_size = max(width, height);
+  const int tiles_x = (width + tile_size - 1) / tile_size;
+  const int tiles_y = (height + tile_size - 1) / tile_size;
+  const int num_tiles = tiles_x * tiles_y;
+  std::atomic<int> next_tile(0), released(0), complete(0);
+  thread_mutex out_mutex;
+
+  DeviceTask task(DeviceTask::RENDER);
+  task.acquire_tile = [&](Device *tile_device, RenderTile &rtile, uint) -> bool {
+    int t = next_tile.fetch_add(1);
+    if (t >= num_tiles)
+      return false;
+    int tx = t % tiles_x, ty = t / tiles_x;
+    rtile.x = tx * tile_size;
+    rtile.y = ty * tile_size;
+    rtile.w = min(tile_size, width - rtile.x);
+    rtile.h = min(tile_size, height - rtile.y);
+    rtile.start_sample = start_sample;
+    rtile.num_samples = num_samples;
+    rtile.sample = start_sample;
+    rtile.resolution = 1;
+    rtile.tile_index = t;
+    rtile.task = RenderTile::PATH_TRACE;
+    BufferParams bp = full;
+    bp.full_x = rtile.x;
+    bp.full_y = rtile.y;
+    bp.width = rtile.w;
+    bp.height = rtile.h;
+    RenderBuffers *tb = new RenderBuffers(tile_device);
+    tb->reset(bp);
+    tb->params.get_offset_stride(rtile.offset, rtile.stride);
+    rtile.buffer = tb->buffer.device_pointer;
+    rtile.buffers = tb;
+    return true;
+  };
+  task.release_tile = [&](RenderTile &rtile) {
+    RenderBuffers *tb = rtile.buffers;
+    if (rtile.sample == rtile.start_sample + rtile.num_samples) {
+      tb->copy_from_device();
+      thread_scoped_lock lock(out_mutex);
+      const float *src = tb->buffer.data();
+      for (int y = 0; y < rtile.h; y++)
+        memcpy(out + ((size_t)(rtile.y + y) * width + rtile.x) * pass_stride,
+               src + (size_t)y * rtile.w * pass_stride, sizeof(float) * rtile.w * pass_stride);
+      complete++;
+    }
+    delete tb; /* on the device's worker thread, as Session::release_tile does */
+    released++;
+  };
+  task.get_cancel = [&]() -> bool { return cancel_after >= 0 && released >= cancel_after; };
+  task.update_tile_sample = [](RenderTile &) {};
+  task.update_progress_sample = [](long, int) {};
+  task.need_finish_queue = false;
+  task.integrator_branched = false;
+  task.adaptive_sampling.use = false;
+  task.tile_types = RenderTile::PATH_TRACE;
+
+  const unsigned int mxcsr = _mm_getcsr();
+  device->task_add(task);
+  device->task_wait();
+  _mm_setcsr(mxcsr);
+  if (tiles_done)
+    *tiles_done = complete;
+  if (device->have_error()) {
+    rs->error = device->error_message();
+    return 1;
   }
   return 0;
 }

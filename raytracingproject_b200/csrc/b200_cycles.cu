@@ -5,6 +5,8 @@
  * the wavefront launch loop.  No CPU fallback: without a B200 b200_create fails.
  */
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h> /* types only: the library is resolved at first use (nccl_api) */
 
 #include <algorithm>
 #include <chrono>
@@ -176,6 +178,19 @@ int b200_device_name(int ordinal, char *name, size_t len, int *sm_major, int *sm
   return B200_OK;
 }
 
+int b200_device_pci_id(int ordinal, char *buf, size_t len)
+{
+  if (!buf || len < 13)
+    return B200_ERR_INVALID;
+  /* cudaDeviceGetPCIBusId: "dddd:bb:dd.f" */
+  if (cudaDeviceGetPCIBusId(buf, (int)len, ordinal) != cudaSuccess)
+    return B200_ERR_CUDA;
+  char *dot = strchr(buf, '.');
+  if (dot)
+    *dot = 0;
+  return B200_OK;
+}
+
 b200_ctx *b200_create(int cuda_ordinal, char *err, size_t errlen)
 {
   auto report = [&](const std::string &m) {
@@ -249,6 +264,8 @@ void b200_destroy(b200_ctx *ctx)
     cudaFree(ctx->d_counters);
   if (ctx->d_debug)
     cudaFree(ctx->d_debug);
+  if (ctx->reduce_tmp)
+    cudaFree(ctx->reduce_tmp);
   if (ctx->h_counters)
     cudaFreeHost(ctx->h_counters);
   cudaEventDestroy(ctx->ev0);
@@ -441,6 +458,24 @@ int b200_bind_global(b200_ctx *ctx, const char *name, uint64_t dptr, const void 
       memcpy(&f, ha.host.data() + o * SIZEOF_KERNEL_OBJECT + KO_SHADOW_TERMINATOR_OFFSET, 4);
       if (f > 1.0f)
         ctx->has_terminator_offset = true;
+    }
+  }
+  if (strcmp(name, "__object_flag") == 0 && bytes) {
+    /* per-object holdout masks and shadow catchers change alpha and colour of every
+     * path that meets the object (kernel_path.h:254-321): not implemented, so refused
+     * rather than rendered as an ordinary surface */
+    std::vector<uint32_t> flags(bytes / 4);
+    if (host)
+      memcpy(flags.data(), host, flags.size() * 4);
+    else if (int rc = b200_d2h(ctx, dptr, flags.data(), 0, flags.size() * 4))
+      return rc;
+    for (uint32_t f : flags) {
+      if (f & CY_SD_OBJECT_HOLDOUT_MASK)
+        return fail(ctx, B200_ERR_UNSUPPORTED,
+                    "objects used as holdout masks are outside the hot-path scope");
+      if (f & CY_SD_OBJECT_SHADOW_CATCHER)
+        return fail(ctx, B200_ERR_UNSUPPORTED,
+                    "shadow catcher objects are outside the hot-path scope");
     }
   }
   if (strcmp(name, "__attributes_map") == 0) {
@@ -751,6 +786,15 @@ int b200_debug_read(b200_ctx *ctx, float *out, size_t n_floats)
   return B200_OK;
 }
 
+int b200_set_cancel_callback(b200_ctx *ctx, b200_cancel_fn fn, void *user)
+{
+  if (!ctx)
+    return B200_ERR_INVALID;
+  ctx->cancel_fn = fn;
+  ctx->cancel_user = user;
+  return B200_OK;
+}
+
 int b200_set_stream(b200_ctx *ctx, uint64_t cuda_stream)
 {
   if (!ctx)
@@ -793,3 +837,122 @@ int b200_set_option(b200_ctx *ctx, const char *name, int64_t value)
 }
 
 } /* extern "C" */
+
+/* ------------------------------------------------ NCCL film all-reduce */
+
+/* NCCL is bound at first use instead of at load time: a host that never renders on
+ * several GPUs in one process (one GPU, or one process per GPU with torch.distributed)
+ * does not need the library, and a process that already carries an NCCL (PyTorch's) gets
+ * that one. */
+namespace {
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  std::string error;
+  bool ok = false;
+};
+
+struct NcclClique {
+  std::vector<int> ordinals;
+  std::vector<ncclComm_t> comms;
+};
+
+std::mutex g_nccl_mutex;
+NcclApi g_nccl;
+std::vector<NcclClique> g_nccl_cliques; /* one communicator set per distinct GPU list */
+
+bool nccl_api()
+{
+  if (g_nccl.ok || !g_nccl.error.empty())
+    return g_nccl.ok;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.handle)
+      break;
+  }
+  if (!g_nccl.handle) {
+    g_nccl.error = std::string("libnccl.so.2 not found: ") + dlerror();
+    return false;
+  }
+  bool all = true;
+  auto sym = [&](const char *name) {
+    void *p = dlsym(g_nccl.handle, name);
+    if (!p)
+      all = false;
+    return p;
+  };
+  g_nccl.CommInitAll = (decltype(g_nccl.CommInitAll))sym("ncclCommInitAll");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))sym("ncclAllReduce");
+  g_nccl.GroupStart = (decltype(g_nccl.GroupStart))sym("ncclGroupStart");
+  g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))sym("ncclGroupEnd");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
+  if (!all) {
+    g_nccl.error = "libnccl.so.2 lacks an expected entry point";
+    return false;
+  }
+  g_nccl.ok = true;
+  return true;
+}
+} /* namespace */
+
+extern "C" int b200_film_allreduce(b200_ctx **ctxs, int n, const uint64_t *films,
+                                   size_t n_floats)
+{
+  if (!ctxs || n <= 0 || !films)
+    return B200_ERR_INVALID;
+  if (n == 1)
+    return B200_OK;
+  std::vector<int> ordinals(n);
+  for (int i = 0; i < n; i++) {
+    if (!ctxs[i] || !films[i])
+      return B200_ERR_INVALID;
+    ordinals[i] = ctxs[i]->ordinal;
+    for (int j = 0; j < i; j++)
+      if (ordinals[j] == ordinals[i])
+        return fail(ctxs[0], B200_ERR_UNSUPPORTED,
+                    "b200_film_allreduce needs one context per GPU (use b200_film_reduce for "
+                    "several contexts of one GPU)");
+  }
+  std::lock_guard<std::mutex> lock(g_nccl_mutex);
+  if (!nccl_api())
+    return fail(ctxs[0], B200_ERR_UNSUPPORTED, "NCCL: " + g_nccl.error);
+  NcclClique *clique = nullptr;
+  for (NcclClique &c : g_nccl_cliques)
+    if (c.ordinals == ordinals)
+      clique = &c;
+  if (!clique) {
+    NcclClique c;
+    c.ordinals = ordinals;
+    c.comms.resize(n);
+    const ncclResult_t r = g_nccl.CommInitAll(c.comms.data(), n, ordinals.data());
+    if (r != ncclSuccess)
+      return fail(ctxs[0], B200_ERR_CUDA,
+                  std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(r));
+    g_nccl_cliques.push_back(c);
+    clique = &g_nccl_cliques.back();
+  }
+  /* one in-place all-reduce per GPU, each on its context's stream (ordered after that
+   * GPU's render), submitted as one group */
+  ncclResult_t r = g_nccl.GroupStart();
+  for (int i = 0; i < n && r == ncclSuccess; i++)
+    r = g_nccl.AllReduce((const void *)films[i], (void *)films[i], n_floats, ncclFloat, ncclSum,
+                         clique->comms[i], ctxs[i]->stream);
+  const ncclResult_t e = g_nccl.GroupEnd();
+  if (r == ncclSuccess)
+    r = e;
+  if (r != ncclSuccess)
+    return fail(ctxs[0], B200_ERR_CUDA, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r));
+  for (int i = 0; i < n; i++) {
+    DeviceGuard guard(ctxs[i]->ordinal);
+    CUDA_TRY(ctxs[i], cudaStreamSynchronize(ctxs[i]->stream));
+  }
+  return B200_OK;
+}

@@ -70,6 +70,13 @@ struct b200_ctx {
   int64_t opt_refill_threshold = 0;
   int64_t opt_trace_blocks_per_sm = 0;
 
+  /* host cancel predicate (task.get_cancel()), polled between wavefront batches */
+  b200_cancel_fn cancel_fn = nullptr;
+  void *cancel_user = nullptr;
+  /* scratch of b200_film_reduce, kept between calls */
+  void *reduce_tmp = nullptr;
+  size_t reduce_tmp_bytes = 0;
+
   /* trace_batch work counter + stats */
   unsigned int *d_counters = nullptr; /* small block of device counters */
   unsigned int *h_counters = nullptr; /* pinned mirror */

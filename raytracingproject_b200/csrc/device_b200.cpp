@@ -43,6 +43,21 @@ CCL_NAMESPACE_BEGIN
  * it after DEVICE_OPTIX.  Standalone builds use the same value. */
 static const DeviceType DEVICE_B200_TYPE = (DeviceType)(DEVICE_OPTIX + 1);
 
+/* task.get_cancel() as the C ABI's cancel predicate: b200_render asks it between
+ * wavefront batches, the way CUDADevice::render polls it every sample step
+ * (device_cuda_impl.cpp:1939). */
+struct B200CancelProbe {
+  DeviceTask *task;
+  DedicatedTaskPool *pool;
+  static int ask(void *user)
+  {
+    B200CancelProbe *p = (B200CancelProbe *)user;
+    if (p->pool->canceled())
+      return 1;
+    return (p->task->get_cancel() && !p->task->need_finish_queue) ? 1 : 0;
+  }
+};
+
 class B200Device : public Device {
  public:
   b200_ctx *ctx;
@@ -165,7 +180,11 @@ class B200Device : public Device {
   {
     if (!ctx || !mem.device_pointer)
       return;
-    task_pool.wait();
+    /* No task_pool.wait() here: Session::release_tile deletes a finished tile's
+     * RenderBuffers ON the device's worker thread (session.cpp:517-518), so waiting for
+     * the pool from mem_free would wait for the caller itself.  b200_free synchronises
+     * the context's stream before the memory goes, as CUDADevice::mem_free relies on its
+     * context. */
     check(b200_free(ctx, (uint64_t)mem.device_pointer), "mem_free");
     stats.mem_free(mem.device_size);
     mem.device_pointer = 0;
@@ -206,6 +225,8 @@ class B200Device : public Device {
       set_error("B200 device: only RENDER and FILM_CONVERT tasks are in scope");
       return;
     }
+    B200CancelProbe probe = {&task, &task_pool};
+    b200_set_cancel_callback(ctx, B200CancelProbe::ask, &probe);
     RenderTile tile;
     while (task.acquire_tile(this, tile, task.tile_types)) {
       if (tile.task == RenderTile::PATH_TRACE) {
@@ -220,7 +241,6 @@ class B200Device : public Device {
         wt.offset = tile.offset;
         wt.stride = tile.stride;
         wt.buffer = (uint64_t)tile.buffer;
-        cancel_flag = 0;
         const int rc = b200_render(ctx, &wt, &cancel_flag);
         if (rc == B200_OK) {
           tile.sample = tile.start_sample + tile.num_samples;
@@ -242,6 +262,7 @@ class B200Device : public Device {
           break;
       }
     }
+    b200_set_cancel_callback(ctx, NULL, NULL);
   }
 
   virtual void task_add(DeviceTask &task)
@@ -253,6 +274,9 @@ class B200Device : public Device {
       film_convert(task);
     }
     else {
+      /* a new task after a task_cancel(): the flag is cleared here, where tasks are
+       * accepted, never by the worker (that could erase a cancel that just arrived) */
+      cancel_flag = 0;
       task_pool.push([=] {
         DeviceTask task_copy = task;
         thread_run(task_copy);
@@ -294,12 +318,17 @@ class B200MultiDevice : public Device {
   DedicatedTaskPool task_pool;
   volatile int cancel_flag;
   b200_stats last_stats;
+  bool distinct_gpus; /* one context per GPU: the film sum is an NCCL all-reduce */
 
   B200MultiDevice(DeviceInfo &info, Stats &stats, Profiler &profiler, bool background_,
                   const vector<int> &ordinals)
-      : Device(info, stats, profiler, background_), cancel_flag(0)
+      : Device(info, stats, profiler, background_), cancel_flag(0), distinct_gpus(true)
   {
     memset(&last_stats, 0, sizeof(last_stats));
+    for (size_t i = 0; i < ordinals.size(); i++)
+      for (size_t j = 0; j < i; j++)
+        if (ordinals[i] == ordinals[j])
+          distinct_gpus = false;
     foreach (int ordinal, ordinals) {
       char err[512] = {0};
       b200_ctx *ctx = b200_create(ordinal, err, sizeof(err));
@@ -428,7 +457,7 @@ class B200MultiDevice : public Device {
   {
     if (ctxs.empty() || !mem.device_pointer)
       return;
-    task_pool.wait();
+    /* no task_pool.wait(): may run on the worker thread itself (see B200Device) */
     Allocation *a = find(mem.device_pointer);
     if (a) {
       for (size_t i = 0; i < ctxs.size(); i++)
@@ -458,6 +487,9 @@ class B200MultiDevice : public Device {
       return;
     }
     const int n = (int)ctxs.size();
+    B200CancelProbe probe = {&task, &task_pool};
+    for (int i = 0; i < n; i++)
+      b200_set_cancel_callback(ctxs[i], B200CancelProbe::ask, &probe);
     RenderTile tile;
     while (task.acquire_tile(this, tile, task.tile_types)) {
       Allocation *film = find(tile.buffer);
@@ -472,7 +504,6 @@ class B200MultiDevice : public Device {
         const int base = tile.num_samples / n, rem = tile.num_samples % n;
         vector<int> rcs(n, B200_OK);
         vector<thread *> workers;
-        cancel_flag = 0;
         for (int i = 0; i < n; i++) {
           b200_work_tile wt;
           wt.x = tile.x;
@@ -500,10 +531,17 @@ class B200MultiDevice : public Device {
             ok = false;
         }
         if (ok && n > 1) {
-          /* sum the per-GPU films into the first one, then clear the others so that
-           * the next tile / sample range starts from zero there */
-          ok = check(0, b200_film_reduce(ctxs.data(), n, film->ptr.data(), film->size / 4),
-                     "film_reduce");
+          /* Sum the per-GPU films: one NCCL all-reduce over NVLink when every context
+           * sits on its own GPU; contexts sharing a GPU (single-GPU test boxes) fall back
+           * to peer copies + add kernels on the first one.  Then the films of the other
+           * GPUs are cleared so that the next tile / sample range starts from zero there
+           * (the first one holds the running sum the host reads). */
+          if (distinct_gpus)
+            ok = check(0, b200_film_allreduce(ctxs.data(), n, film->ptr.data(), film->size / 4),
+                       "film_allreduce");
+          else
+            ok = check(0, b200_film_reduce(ctxs.data(), n, film->ptr.data(), film->size / 4),
+                       "film_reduce");
           for (int i = 1; ok && i < n; i++)
             ok = check(i, b200_zero(ctxs[i], film->ptr[i], 0, film->size), "film clear");
         }
@@ -530,6 +568,8 @@ class B200MultiDevice : public Device {
           break;
       }
     }
+    for (int i = 0; i < n; i++)
+      b200_set_cancel_callback(ctxs[i], NULL, NULL);
   }
 
   virtual void task_add(DeviceTask &task)
@@ -545,6 +585,7 @@ class B200MultiDevice : public Device {
             "film_convert");
     }
     else {
+      cancel_flag = 0;
       task_pool.push([=] {
         DeviceTask task_copy = task;
         thread_run(task_copy);
@@ -587,7 +628,13 @@ void device_b200_info(vector<DeviceInfo> &devices)
     info.type = DEVICE_B200_TYPE;
     info.description = string(name);
     info.num = i;
-    info.id = string_printf("B200_%s_%d", name, i);
+    /* stable across reboots and re-enumeration: the PCI location, as device_cuda_info()
+     * does (device_cuda.cpp:144-152) */
+    char pci[32] = {0};
+    if (b200_device_pci_id(i, pci, sizeof(pci)) == B200_OK)
+      info.id = string_printf("B200_%s_%s", name, pci);
+    else
+      info.id = string_printf("B200_%s_%d", name, i);
     info.has_half_images = false;
     info.has_volume_decoupled = false;
     info.has_adaptive_stop_per_sample = false;

@@ -864,7 +864,8 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
             else
               ray_t = FLT_MAX;
             want_next = true;
-            if (p.debug && i == p.debug_slot && st.bounce < 16) {
+            if (p.debug && i == p.debug_slot && st.bounce + st.transparent_bounce >= 1 &&
+                st.bounce + st.transparent_bounce <= 16) {
               float *dbg = p.debug + 32 * (st.bounce + st.transparent_bounce - 1);
               dbg[0] = r0.x, dbg[1] = r0.y, dbg[2] = r0.z, dbg[3] = r0.w;
               dbg[4] = r1.x, dbg[5] = r1.y, dbg[6] = r1.z, dbg[7] = hit.x;
@@ -1436,11 +1437,15 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
       case CY_NODE_BRIGHTCONTRAST:
       case CY_NODE_SEPARATE_VECTOR:
       case CY_NODE_COMBINE_VECTOR:
+      case CY_NODE_LIGHT_PATH:    /* both run in the lean interpreter and read */
+      case CY_NODE_LIGHT_FALLOFF: /* nothing but the path state / the light sample */
         i += 1;
         break;
-      case CY_NODE_LIGHT_PATH:
-      case CY_NODE_LIGHT_FALLOFF:
       /* from here on: the nodes of svm_eval_extended_node (shade.cuh) */
+      case CY_NODE_TANGENT:    /* the only nodes of this group that read mesh */
+      case CY_NODE_NORMAL_MAP: /* attributes (tangent / generated coordinates) */
+        *features |= SVM_USES_ATTRIBUTES;
+        /* fall through */
       case CY_NODE_MAPPING:
       case CY_NODE_TEX_CHECKER:
       case CY_NODE_TEX_GRADIENT:
@@ -1450,10 +1455,6 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
       case CY_NODE_OBJECT_INFO:
       case CY_NODE_CAMERA:
       case CY_NODE_TEX_WHITE_NOISE:
-      case CY_NODE_TANGENT:
-      case CY_NODE_NORMAL_MAP:
-        *features |= SVM_USES_ATTRIBUTES;
-        /* fall through */
       case CY_NODE_BLACKBODY:
       case CY_NODE_WAVELENGTH:
         *features |= SVM_USES_EXTENDED_NODES;
@@ -1758,7 +1759,7 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
     const size_t npix = (size_t)tile->w * bh;
     const int spb = (int)std::max<size_t>(1, pool->capacity / npix);
     for (int s0 = 0; s0 < tile->num_samples; s0 += spb) {
-      if (cancel && *cancel)
+      if ((cancel && *cancel) || (ctx->cancel_fn && ctx->cancel_fn(ctx->cancel_user)))
         return fail(ctx, B200_ERR_CANCELLED, "cancelled");
       BatchParams bp;
       bp.x = tile->x;
@@ -1941,21 +1942,32 @@ int b200_film_reduce(b200_ctx **ctxs, int n, const uint64_t *films, size_t n_flo
     return fail(ctxs[0], B200_ERR_INVALID, "film size must be a multiple of 4 floats");
   b200_ctx *root = ctxs[0];
   DeviceGuard guard(root->ordinal);
-  void *tmp = nullptr;
-  CUDA_TRY(root, cudaMalloc(&tmp, n_floats * sizeof(float)));
+  /* the staging film lives with the root context and is reused by every call */
+  if (root->reduce_tmp_bytes < n_floats * sizeof(float)) {
+    CUDA_TRY(root, cudaStreamSynchronize(root->stream));
+    if (root->reduce_tmp)
+      cudaFree(root->reduce_tmp);
+    root->reduce_tmp = nullptr;
+    root->reduce_tmp_bytes = 0;
+    CUDA_TRY(root, cudaMalloc(&root->reduce_tmp, n_floats * sizeof(float)));
+    root->reduce_tmp_bytes = n_floats * sizeof(float);
+  }
+  void *tmp = root->reduce_tmp;
   for (int i = 1; i < n; i++) {
+    /* the peer's film must be complete before it is copied */
+    {
+      DeviceGuard peer(ctxs[i]->ordinal);
+      CUDA_TRY(ctxs[i], cudaStreamSynchronize(ctxs[i]->stream));
+    }
     /* peer copy over NVLink, then one vectorised add on the root */
     cudaError_t e = cudaMemcpyPeerAsync(tmp, root->ordinal, (const void *)films[i],
                                         ctxs[i]->ordinal, n_floats * sizeof(float), root->stream);
-    if (e != cudaSuccess) {
-      cudaFree(tmp);
+    if (e != cudaSuccess)
       return fail(root, B200_ERR_CUDA, std::string("peer copy: ") + cudaGetErrorString(e));
-    }
     k_film_add<<<launch_grid(root, 4), 256, 0, root->stream>>>((float4 *)films[0],
                                                                (const float4 *)tmp, n_floats / 4);
   }
   cudaError_t e = cudaStreamSynchronize(root->stream);
-  cudaFree(tmp);
   if (e != cudaSuccess)
     return fail(root, B200_ERR_CUDA, std::string("film reduce: ") + cudaGetErrorString(e));
   return B200_OK;

@@ -36,7 +36,7 @@ EXPORTS = [
     "b200_mem_used", "b200_bind_global", "b200_set_kernel_data", "b200_build_bvh", "b200_render",
     "b200_trace_batch", "b200_film_convert", "b200_film_reduce", "b200_get_stats",
     "b200_synchronize", "b200_set_option", "b200_set_stream", "b200_debug_read",
-    "b200_validate_svm",
+    "b200_validate_svm", "b200_device_pci_id", "b200_set_cancel_callback", "b200_film_allreduce",
 ]
 
 
@@ -108,6 +108,9 @@ def load_library():
     L.b200_film_convert.argtypes = [vp, u64, u64, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_int]
     L.b200_film_reduce.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(u64), sz]
+    L.b200_film_allreduce.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(u64), sz]
+    L.b200_device_pci_id.argtypes = [C.c_int, C.c_char_p, sz]
+    L.b200_set_cancel_callback.argtypes = [vp, vp, vp]
     L.b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.b200_synchronize.argtypes = [vp]
     L.b200_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
@@ -338,6 +341,16 @@ class B200Device:
         ptrs = (C.c_uint64 * n)(*[f.device_pointer for f in films])
         rc = devices[0]._L.b200_film_reduce(ctxs, n, ptrs, int(n_floats))
         devices[0]._check(rc, "film_reduce")
+
+    @staticmethod
+    def film_allreduce(devices, films, n_floats):
+        """The same sum as one NCCL all-reduce over NVLink (b200_film_allreduce): one
+        device per GPU, every film ends up holding the sum."""
+        n = len(devices)
+        ctxs = (C.c_void_p * n)(*[d._ctx for d in devices])
+        ptrs = (C.c_uint64 * n)(*[f.device_pointer for f in films])
+        rc = devices[0]._L.b200_film_allreduce(ctxs, n, ptrs, int(n_floats))
+        devices[0]._check(rc, "film_allreduce")
 
     def render(self, width, height, pass_stride, start_sample, num_samples, film=None):
         """Full-frame RENDER into a fresh (or given) RenderBuffers-like film and

@@ -61,3 +61,25 @@ def test_sm100_only_binary():
     out = subprocess.run([cuobjdump, "-lelf", lib], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", out))
     assert archs == {"100a"}, archs
+
+
+def test_product_libraries_have_no_path_to_the_oracle_kernels():
+    """The C-ABI library links only the CUDA runtime; the C++ shim links it and the
+    reference HOST library (Device base, Scene ... - no kernels, no CPU device).  Neither
+    depends on the oracle (libcycles_ref.so) nor references a kernel_cpu_* symbol."""
+    import subprocess
+    pkg = os.path.join(ROOT, "raytracingproject_b200")
+    libs = [os.path.join(pkg, "libb200cycles.so")]
+    shim = os.path.join(pkg, "libcycles_device_b200.so")
+    host = os.path.join(ROOT, "oracle", "_ref", "libcycles_host.so")
+    if os.path.exists(shim):
+        libs.append(shim)
+    if os.path.exists(host):
+        libs.append(host)
+    for lib in libs:
+        needed = subprocess.run(["readelf", "-d", lib], capture_output=True, text=True).stdout
+        assert "libcycles_ref" not in needed, lib
+        syms = subprocess.run(["nm", "-D", lib], capture_output=True, text=True).stdout
+        assert "kernel_cpu_" not in syms, lib
+    needed = subprocess.run(["readelf", "-d", libs[0]], capture_output=True, text=True).stdout
+    assert "libcycles" not in needed and "libnccl" not in needed  # NCCL is bound at first use

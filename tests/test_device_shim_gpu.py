@@ -110,3 +110,73 @@ def test_two_contexts_with_different_scenes_on_one_gpu(ref):
             rs.close()
         for dev in devs:
             dev.close()
+
+
+def test_session_style_tile_buffers_are_freed_on_the_worker_thread(ref):
+    """Background renders give every tile its own RenderBuffers and Session::release_tile
+    deletes it on the device's worker thread (session.cpp:449-460, 517-518): mem_free runs
+    INSIDE the running task and must not wait for the task pool.  The stitched tiles equal
+    the full-frame render bit for bit; the same flow on the two-context multi device."""
+    from raytracingproject_b200 import scenes
+    from raytracingproject_b200.device import B200HostDevice
+    desc = scenes.cornell(160, 96, spp=4, materials="diffuse")
+    for ordinals in (0, [0, 0]):
+        host = B200HostDevice(ordinals)
+        try:
+            rs = ref.build_scene(desc, external_device=host.ptr)
+            try:
+                full, _ = rs.render(0, desc.spp, tile_size=0)
+                tiles, done = rs.render_tile_buffers(0, desc.spp, tile_size=64)
+                assert host.error_message() == ""
+                assert done == 3 * 2
+                if ordinals == 0:
+                    assert np.array_equal(tiles, full)
+                else:
+                    np.testing.assert_allclose(tiles, full, rtol=2e-6, atol=1e-6)
+            finally:
+                rs.close()
+        finally:
+            host.close()
+
+
+def test_task_get_cancel_stops_the_render(ref):
+    """task.get_cancel() (Session::cancel / progress.set_cancel) ends the tile loop: after
+    two released tiles no further tile is completed, and the device stays usable."""
+    from raytracingproject_b200 import scenes
+    from raytracingproject_b200.device import B200HostDevice
+    desc = scenes.cornell(192, 128, spp=2, materials="diffuse")
+    host = B200HostDevice(0)
+    try:
+        rs = ref.build_scene(desc, external_device=host.ptr)
+        try:
+            _, done = rs.render_tile_buffers(0, desc.spp, tile_size=64, cancel_after=2)
+            assert host.error_message() == ""
+            assert done == 2
+            film, done = rs.render_tile_buffers(0, desc.spp, tile_size=64)
+            assert done == 6 and film[..., 3].min() == desc.spp
+        finally:
+            rs.close()
+    finally:
+        host.close()
+
+
+def test_holdout_and_shadow_catcher_objects_are_refused(ref, device):
+    """Per-object holdout masks / shadow catchers are not implemented: binding an
+    __object_flag array that carries them is refused, not rendered as a plain surface."""
+    from raytracingproject_b200.device import DeviceError, DeviceMemory, MEM_GLOBAL
+    desc = small_cases()["cornell"]
+    rs = ref.build_scene(desc)
+    try:
+        arrays = rs.device_arrays()
+    finally:
+        rs.close()
+    device.upload_scene(arrays)
+    for bit, what in ((0x1, "holdout"), (0x80, "shadow catcher")):
+        flags = arrays["__object_flag"][0].copy().view(np.uint32)
+        flags[1] |= bit
+        with pytest.raises(DeviceError, match=what):
+            device.mem_copy_to(DeviceMemory("__object_flag", flags.view(np.uint8), MEM_GLOBAL))
+    # the unmodified array binds again and the device still renders
+    device._error = ""
+    device.upload_scene(arrays)
+    assert device.render(desc.width, desc.height, 4, 0, 1)[..., 3].min() == 1.0
