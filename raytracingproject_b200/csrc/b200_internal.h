@@ -70,6 +70,8 @@ struct b200_ctx {
   int64_t opt_refill_threshold = 0;
   int64_t opt_trace_blocks_per_sm = 0;
 
+  int shade_blocks_per_sm[2] = {0, 0}; /* k_shade_surface<lean / full>: grid size per SM */
+
   /* host cancel predicate (task.get_cancel()), polled between wavefront batches */
   b200_cancel_fn cancel_fn = nullptr;
   void *cancel_user = nullptr;

@@ -1,152 +1,100 @@
-/* bsdf.cuh - closure evaluation and sampling (kernel/closure/bsdf.h dispatch).
- * Included by shade.cuh. */
+/* bsdf.cuh - evaluation and sampling of one lobe (lobes.cuh), dispatching on its kind.
+ *
+ * Reference semantics (blender/intern/cycles/kernel/closure): bsdf.h bsdf_eval /
+ * bsdf_sample (which side of the geometric normal is evaluated, the softened-terminator
+ * factors for bent normals and the per-object terminator offset), bsdf_diffuse.h,
+ * bsdf_oren_nayar.h, bsdf_principled_diffuse.h, bsdf_principled_sheen.h,
+ * bsdf_reflection.h, bsdf_refraction.h, bsdf_transparent.h; kernel_montecarlo.h for the
+ * hemisphere mappings.  All BSDF values include the cosine of the incoming direction.
+ * Included by shade.cuh; host-compilable. */
 #ifndef B200_BSDF_CUH
 #define B200_BSDF_CUH
 
-/* kernel_montecarlo.h:57-66 */
+#include "lobes.cuh"
+
+/* ------------------------------------------------ hemisphere mappings */
+
+/* polar mapping of the unit square onto the unit disk */
+CY_DEV float2 square_to_disk_polar(float u, float v)
+{
+  const float phi = CY_2PI_F * u;
+  const float r = sqrtf(v);
+  return make_float2(r * cosf(phi), r * sinf(phi));
+}
+
+/* cosine-weighted direction about N; pdf = cos / pi */
 CY_DEV void sample_cos_hemisphere(f3 N, float randu, float randv, f3 *omega_in, float *pdf)
 {
-  /* to_unit_disk - kernel_montecarlo.h:39-46 */
-  float phi = CY_2PI_F * randu;
-  float r = sqrtf(randv);
-  randu = r * cosf(phi);
-  randv = r * sinf(phi);
-  float costheta = sqrtf(fmaxf(1.0f - randu * randu - randv * randv, 0.0f));
+  const float2 d = square_to_disk_polar(randu, randv);
+  const float costheta = sqrtf(fmaxf(1.0f - d.x * d.x - d.y * d.y, 0.0f));
   f3 T, B;
   make_orthonormals(N, &T, &B);
-  *omega_in = randu * T + randv * B + costheta * N;
+  *omega_in = d.x * T + d.y * B + costheta * N;
   *pdf = costheta * CY_1_PI_F;
 }
 
-/* closure/bsdf_diffuse.h:55-110 */
-CY_DEV f3 bsdf_diffuse_eval_reflect(const Closure &sc, f3 omega_in, float *pdf)
-{
-  float cos_pi = fmaxf(dot(sc.N, omega_in), 0.0f) * CY_1_PI_F;
-  *pdf = cos_pi;
-  return mk3(cos_pi, cos_pi, cos_pi);
-}
-CY_DEV int bsdf_diffuse_sample(const Closure &sc, f3 Ng, float randu, float randv, f3 *eval,
-                               f3 *omega_in, float *pdf)
-{
-  sample_cos_hemisphere(sc.N, randu, randv, omega_in, pdf);
-  if (dot(Ng, *omega_in) > 0.0f)
-    *eval = mk3(*pdf, *pdf, *pdf);
-  else
-    *pdf = 0.0f;
-  return CY_LABEL_REFLECT | CY_LABEL_DIFFUSE;
-}
-
-/* kernel_montecarlo.h:69-82 */
+/* uniform direction about N; pdf = 1 / 2pi */
 CY_DEV void sample_uniform_hemisphere(f3 N, float randu, float randv, f3 *omega_in, float *pdf)
 {
-  float z = randu;
-  float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
-  float phi = CY_2PI_F * randv;
-  float x = r * cosf(phi);
-  float y = r * sinf(phi);
+  const float z = randu;
+  const float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+  const float phi = CY_2PI_F * randv;
   f3 T, B;
   make_orthonormals(N, &T, &B);
-  *omega_in = x * T + y * B + z * N;
+  *omega_in = (r * cosf(phi)) * T + (r * sinf(phi)) * B + z * N;
   *pdf = 0.5f * CY_1_PI_F;
 }
 
-/* closure/bsdf_oren_nayar.h: Diffuse BSDF with roughness > 0.  The two precomputed
- * coefficients a, b live in alpha_x, alpha_y of the closure record. */
-CY_DEV uint32_t bsdf_oren_nayar_setup(Closure *bsdf, float roughness)
+#include "microfacet.cuh"
+#include "microfacet_multi.cuh"
+
+/* ------------------------------------------------------ diffuse family */
+
+/* Oren-Nayar in Cycles' two-coefficient form: value = n.l * (a + b * t) */
+CY_DEV void oren_nayar_coefficients(float roughness, float *a, float *b)
 {
-  bsdf->type = CY_CLOSURE_BSDF_OREN_NAYAR_ID;
   const float sigma = saturate(roughness);
   const float div = 1.0f / (CY_M_PI_F + ((3.0f * CY_M_PI_F - 4.0f) / 6.0f) * sigma);
-  bsdf->roughness = roughness;
-  bsdf->alpha_x = 1.0f * div;
-  bsdf->alpha_y = sigma * div;
-  return CY_SD_BSDF | CY_SD_BSDF_HAS_EVAL;
+  *a = 1.0f * div;
+  *b = sigma * div;
 }
-CY_DEV f3 bsdf_oren_nayar_get_intensity(const Closure &sc, f3 n, f3 v, f3 l)
+CY_DEV float oren_nayar_value(const Lobe &l, f3 v, f3 wi)
 {
-  float nl = fmaxf(dot(n, l), 0.0f);
-  float nv = fmaxf(dot(n, v), 0.0f);
-  float t = dot(l, v) - nl * nv;
+  const float nl = fmaxf(dot(l.N, wi), 0.0f);
+  const float nv = fmaxf(dot(l.N, v), 0.0f);
+  float t = dot(wi, v) - nl * nv;
   if (t > 0.0f)
     t /= fmaxf(nl, nv) + FLT_MIN;
-  float is = nl * (sc.alpha_x + sc.alpha_y * t);
-  return mk3(is, is, is);
-}
-CY_DEV f3 bsdf_oren_nayar_eval_reflect(const Closure &sc, f3 I, f3 omega_in, float *pdf)
-{
-  if (dot(sc.N, omega_in) > 0.0f) {
-    *pdf = 0.5f * CY_1_PI_F;
-    return bsdf_oren_nayar_get_intensity(sc, sc.N, I, omega_in);
-  }
-  *pdf = 0.0f;
-  return zero3();
-}
-CY_DEV int bsdf_oren_nayar_sample(const Closure &sc, f3 Ng, f3 I, float randu, float randv,
-                                  f3 *eval, f3 *omega_in, float *pdf)
-{
-  sample_uniform_hemisphere(sc.N, randu, randv, omega_in, pdf);
-  if (dot(Ng, *omega_in) > 0.0f) {
-    *eval = bsdf_oren_nayar_get_intensity(sc, sc.N, I, *omega_in);
-  }
-  else {
-    *pdf = 0.0f;
-    *eval = zero3();
-  }
-  return CY_LABEL_REFLECT | CY_LABEL_DIFFUSE;
+  return nl * (l.ax + l.aux * t);
 }
 
-/* closure/bsdf_diffuse.h:112-170: Translucent BSDF (Lambert on the far side) */
-CY_DEV f3 bsdf_translucent_eval_transmit(const Closure &sc, f3 omega_in, float *pdf)
+/* Burley's diffuse with the retro-reflective rim (Principled BSDF) */
+CY_DEV float disney_diffuse_value(const Lobe &l, f3 V, f3 L)
 {
-  float cos_pi = fmaxf(-dot(sc.N, omega_in), 0.0f) * CY_1_PI_F;
-  *pdf = cos_pi;
-  return mk3(cos_pi, cos_pi, cos_pi);
-}
-CY_DEV int bsdf_translucent_sample(const Closure &sc, f3 Ng, float randu, float randv, f3 *eval,
-                                   f3 *omega_in, float *pdf)
-{
-  sample_cos_hemisphere(-sc.N, randu, randv, omega_in, pdf);
-  if (dot(Ng, *omega_in) < 0)
-    *eval = mk3(*pdf, *pdf, *pdf);
-  else
-    *pdf = 0;
-  return CY_LABEL_TRANSMIT | CY_LABEL_DIFFUSE;
+  const float NdotL = fmaxf(dot(l.N, L), 0.0f);
+  const float NdotV = fmaxf(dot(l.N, V), 0.0f);
+  const f3 H = normalize(L + V);
+  const float LdotH = dot(L, H);
+  const float FL = schlick_weight(NdotL), FV = schlick_weight(NdotV);
+  const float Fd90 = 0.5f + 2.0f * LdotH * LdotH * l.aux;
+  const float Fd = (1.0f * (1.0f - FL) + Fd90 * FL) * (1.0f * (1.0f - FV) + Fd90 * FV);
+  return CY_1_PI_F * NdotL * Fd;
 }
 
-#include "bsdf_principled.cuh"
-
-/* closure/bsdf_reflection.h, bsdf_refraction.h: the singular (sharp) closures - one
- * possible direction, evaluation is zero, the sample carries "some high number" */
-CY_DEV int bsdf_reflection_sample(const Closure &sc, f3 Ng, f3 I, f3 *eval, f3 *omega_in,
-                                  float *pdf)
+/* Principled sheen: Schlick weight of the half-vector angle; zero (and pdf zero) below
+ * the horizon of either direction */
+CY_DEV bool sheen_value(const Lobe &l, f3 V, f3 L, float *value)
 {
-  const f3 N = sc.N;
-  float cosNO = dot(N, I);
-  if (cosNO > 0) {
-    *omega_in = (2 * cosNO) * N - I;
-    if (dot(Ng, *omega_in) > 0) {
-      *pdf = 1e6f;
-      *eval = mk3(1e6f, 1e6f, 1e6f);
-    }
-  }
-  return CY_LABEL_REFLECT | CY_LABEL_SINGULAR;
-}
-CY_DEV int bsdf_refraction_sample(const Closure &sc, f3 I, f3 *eval, f3 *omega_in, float *pdf)
-{
-  f3 R, T;
-  bool inside;
-  float fresnel = fresnel_dielectric(sc.ior, sc.N, I, &R, &T, &inside);
-  if (!inside && fresnel != 1.0f) {
-    *pdf = 1e6f;
-    *eval = mk3(1e6f, 1e6f, 1e6f);
-    *omega_in = T;
-  }
-  return CY_LABEL_TRANSMIT | CY_LABEL_SINGULAR;
+  const float NdotL = dot(l.N, L), NdotV = dot(l.N, V);
+  if (NdotL < 0.0f || NdotV < 0.0f)
+    return false;
+  const f3 H = normalize(L + V);
+  *value = schlick_weight(dot(L, H)) * NdotL;
+  return true;
 }
 
-/* closure/bsdf.h bsdf_eval: reflect side when dot(Ng, omega_in) >= 0 */
-/* closure/bsdf.h:82-111: softened terminator for closures whose normal is not the
- * shading normal (a linked Normal input), and the per-object shadow terminator offset */
+/* -------------------------------------------- softened shadow terminator */
+
 CY_DEV float bump_shadowing_term(f3 Ng, f3 N, f3 I)
 {
   const float g = safe_divide(dot(Ng, I), dot(N, I) * dot(Ng, N));
@@ -163,133 +111,231 @@ CY_DEV float shift_cos_in(float cos_in, float frequency_multiplier)
   const float angle = fast_acosf(cos_in);
   return fmaxf(cosf(angle * frequency_multiplier), 0.0f) / cos_in;
 }
-CY_DEV bool closure_is_bsdf_diffuse(int type)
-{
-  return type >= CY_CLOSURE_BSDF_DIFFUSE_ID && type <= CY_CLOSURE_BSDF_TRANSLUCENT_ID;
-}
 
-/* Decided once per shading point, after the shader ran: does any closure need the
- * terminator terms at all?  Almost never - and testing it per closure inside the
+/* Decided once per shading point, after the shader ran: does any lobe need the
+ * terminator factors at all?  Almost never - and testing it per lobe inside the
  * eval / sample loops cost the Cornell workload 11 %. */
-CY_DEV void bsdf_terminator_terms_setup(ShaderDataG &sd)
+CY_DEV void bsdf_terminator_terms_setup(ShaderDataG &sd, const LobeArena &arena)
 {
   int need = (sd.terminator_freq > 1.0f) ? 1 : 0;
-  for (int i = 0; i < sd.num_closure; i++)
-    if (closure_is_bsdf_diffuse(sd.closure[i].type) && !isequal3(sd.closure[i].N, sd.N))
+  int at = 0;
+  for (int i = 0; i < arena.n; i++) {
+    const uint32_t kind = lobe_kind_at(arena, at);
+    if (lobe_is_diffuse(kind) && !isequal3(lobe_normal_at(arena, at), sd.N))
       need = 1;
+    at += lobe_words(kind);
+  }
   sd.terminator_terms = need;
 }
 
-/* EXT = false: the closures the lean interpreter can create (it hands shaders with sheen
- * to the full one, shade.cuh svm_eval_nodes) */
+/* ----------------------------------------------------------- evaluation */
+
+/* EXT = false: the lobes the lean interpreter can create (it hands shaders with sheen,
+ * multi-scatter GGX or bent normals to the full one, shade.cuh svm_eval_nodes) */
 template<bool EXT>
-CY_DEV f3 bsdf_eval(const ShaderDataG &sd, const Closure &sc, f3 omega_in, float *pdf)
+CY_DEV f3 bsdf_eval(ShaderDataG &sd, const Lobe &l, f3 omega_in, float *pdf)
 {
-  f3 eval = zero3();
-  if (dot(sd.Ng, omega_in) >= 0.0f) {
-    switch (sc.type) {
-      case CY_CLOSURE_BSDF_DIFFUSE_ID:
-        eval = bsdf_diffuse_eval_reflect(sc, omega_in, pdf);
-        break;
-      case CY_CLOSURE_BSDF_PRINCIPLED_DIFFUSE_ID:
-        eval = bsdf_principled_diffuse_eval_reflect(sc, sd.I, omega_in, pdf);
-        break;
-      case CY_CLOSURE_BSDF_PRINCIPLED_SHEEN_ID:
-        if (EXT)
-          eval = bsdf_principled_sheen_eval_reflect(sc, sd.I, omega_in, pdf);
-        break;
-      case CY_CLOSURE_BSDF_OREN_NAYAR_ID:
-        eval = bsdf_oren_nayar_eval_reflect(sc, sd.I, omega_in, pdf);
-        break;
-      case CY_CLOSURE_BSDF_MICROFACET_GGX_ID:
-      case CY_CLOSURE_BSDF_MICROFACET_GGX_FRESNEL_ID:
-      case CY_CLOSURE_BSDF_MICROFACET_GGX_CLEARCOAT_ID:
-      case CY_CLOSURE_BSDF_MICROFACET_GGX_REFRACTION_ID:
-        eval = bsdf_microfacet_ggx_eval_reflect(sc, sd.I, omega_in, pdf);
-        break;
-      default:
-        break;
-    }
-    if (EXT && sd.terminator_terms) {
-      if (closure_is_bsdf_diffuse(sc.type) && !isequal3(sc.N, sd.N))
-        eval *= bump_shadowing_term(sd.N, sc.N, omega_in);
-      if (sd.terminator_freq > 1.0f)
-        eval *= shift_cos_in(dot(omega_in, sc.N), sd.terminator_freq);
-    }
+  const bool same_side = dot(sd.Ng, omega_in) >= 0.0f;
+  const int id = lobe_id(l.kind);
+  float v = 0.0f;
+  f3 value = zero3();
+  switch (id) {
+    case CY_CLOSURE_BSDF_DIFFUSE_ID:
+      if (same_side) {
+        v = fmaxf(dot(l.N, omega_in), 0.0f) * CY_1_PI_F;
+        *pdf = v;
+        value = mk3(v, v, v);
+      }
+      break;
+    case CY_CLOSURE_BSDF_TRANSLUCENT_ID:
+      if (!same_side) {
+        v = fmaxf(-dot(l.N, omega_in), 0.0f) * CY_1_PI_F;
+        *pdf = v;
+        value = mk3(v, v, v);
+      }
+      break;
+    case CY_CLOSURE_BSDF_OREN_NAYAR_ID:
+      if (same_side) {
+        if (dot(l.N, omega_in) > 0.0f) {
+          *pdf = 0.5f * CY_1_PI_F;
+          v = oren_nayar_value(l, sd.I, omega_in);
+          value = mk3(v, v, v);
+        }
+        else {
+          *pdf = 0.0f;
+        }
+      }
+      break;
+    case CY_CLOSURE_BSDF_PRINCIPLED_DIFFUSE_ID:
+      if (same_side) {
+        if (dot(l.N, omega_in) > 0.0f) {
+          *pdf = fmaxf(dot(l.N, omega_in), 0.0f) * CY_1_PI_F;
+          v = disney_diffuse_value(l, sd.I, omega_in);
+          value = mk3(v, v, v);
+        }
+        else {
+          *pdf = 0.0f;
+        }
+      }
+      break;
+    case CY_CLOSURE_BSDF_PRINCIPLED_SHEEN_ID:
+      if (EXT && same_side) {
+        *pdf = 0.0f;
+        if (dot(l.N, omega_in) > 0.0f && sheen_value(l, sd.I, omega_in, &v)) {
+          *pdf = fmaxf(dot(l.N, omega_in), 0.0f) * CY_M_1_PI_F;
+          value = mk3(v, v, v);
+        }
+      }
+      break;
+    case CY_CLOSURE_BSDF_MICROFACET_GGX_ID:
+    case CY_CLOSURE_BSDF_MICROFACET_GGX_FRESNEL_ID:
+    case CY_CLOSURE_BSDF_MICROFACET_GGX_CLEARCOAT_ID:
+    case CY_CLOSURE_BSDF_MICROFACET_GGX_REFRACTION_ID:
+      value = ggx_eval(l, sd.I, omega_in, same_side, pdf);
+      break;
+    case CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_ID:
+    case CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_FRESNEL_ID:
+    case CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_GLASS_ID:
+    case CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_GLASS_FRESNEL_ID:
+      if (EXT)
+        value = multi_ggx_eval(l, sd.I, omega_in, same_side, pdf, &sd.lcg_state);
+      break;
+    default: /* sharp lobes, transparent, placeholders: nothing to evaluate */
+      break;
   }
-  else {
-    switch (sc.type) {
-      case CY_CLOSURE_BSDF_TRANSLUCENT_ID:
-        eval = bsdf_translucent_eval_transmit(sc, omega_in, pdf);
-        break;
-      case CY_CLOSURE_BSDF_MICROFACET_GGX_ID:
-      case CY_CLOSURE_BSDF_MICROFACET_GGX_FRESNEL_ID:
-      case CY_CLOSURE_BSDF_MICROFACET_GGX_CLEARCOAT_ID:
-      case CY_CLOSURE_BSDF_MICROFACET_GGX_REFRACTION_ID:
-        eval = bsdf_microfacet_ggx_eval_transmit(sc, sd.I, omega_in, pdf);
-        break;
-      default:
-        break;
-    }
-    if (EXT && sd.terminator_terms && closure_is_bsdf_diffuse(sc.type) &&
-        !isequal3(sc.N, sd.N))
-      eval *= bump_shadowing_term(-sd.N, sc.N, omega_in);
+  if (EXT && sd.terminator_terms) {
+    if (lobe_is_diffuse(l.kind) && !isequal3(l.N, sd.N))
+      value *= bump_shadowing_term(same_side ? sd.N : -sd.N, l.N, omega_in);
+    if (same_side && sd.terminator_freq > 1.0f)
+      value *= shift_cos_in(dot(omega_in, l.N), sd.terminator_freq);
   }
-  return eval;
+  return value;
 }
 
-/* closure/bsdf.h bsdf_sample */
-template<bool EXT>
-CY_DEV int bsdf_sample_closure(const ShaderDataG &sd, const Closure &sc, float randu,
-                               float randv, f3 *eval, f3 *omega_in, float *pdf)
+/* ------------------------------------------------------------ sampling */
+
+/* a cosine- or uniformly-sampled diffuse direction counts only on the side the lobe
+ * scatters to */
+CY_DEV bool keep_side(f3 Ng, f3 omega_in, bool reflect)
 {
-  switch (sc.type) {
+  const float c = dot(Ng, omega_in);
+  return reflect ? (c > 0.0f) : (c < 0.0f);
+}
+
+template<bool EXT>
+CY_DEV int bsdf_sample_lobe(ShaderDataG &sd, const Lobe &l, float randu, float randv, f3 *value,
+                            f3 *omega_in, float *pdf)
+{
+  float v = 0.0f;
+  switch (lobe_id(l.kind)) {
     case CY_CLOSURE_BSDF_DIFFUSE_ID:
-      return bsdf_diffuse_sample(sc, sd.Ng, randu, randv, eval, omega_in, pdf);
-    case CY_CLOSURE_BSDF_PRINCIPLED_DIFFUSE_ID:
-      return bsdf_principled_diffuse_sample(sc, sd.Ng, sd.I, randu, randv, eval, omega_in, pdf);
-    case CY_CLOSURE_BSDF_PRINCIPLED_SHEEN_ID:
-      if (EXT)
-        return bsdf_principled_sheen_sample(sc, sd.Ng, sd.I, randu, randv, eval, omega_in, pdf);
-      *pdf = 0.0f;
-      return CY_LABEL_NONE;
-    case CY_CLOSURE_BSDF_OREN_NAYAR_ID:
-      return bsdf_oren_nayar_sample(sc, sd.Ng, sd.I, randu, randv, eval, omega_in, pdf);
+      sample_cos_hemisphere(l.N, randu, randv, omega_in, pdf);
+      if (keep_side(sd.Ng, *omega_in, true))
+        *value = mk3(*pdf, *pdf, *pdf);
+      else
+        *pdf = 0.0f;
+      return CY_LABEL_REFLECT | CY_LABEL_DIFFUSE;
     case CY_CLOSURE_BSDF_TRANSLUCENT_ID:
-      return bsdf_translucent_sample(sc, sd.Ng, randu, randv, eval, omega_in, pdf);
-    case CY_CLOSURE_BSDF_REFLECTION_ID:
-      return bsdf_reflection_sample(sc, sd.Ng, sd.I, eval, omega_in, pdf);
-    case CY_CLOSURE_BSDF_REFRACTION_ID:
-      return bsdf_refraction_sample(sc, sd.I, eval, omega_in, pdf);
+      sample_cos_hemisphere(-l.N, randu, randv, omega_in, pdf);
+      if (keep_side(sd.Ng, *omega_in, false))
+        *value = mk3(*pdf, *pdf, *pdf);
+      else
+        *pdf = 0.0f;
+      return CY_LABEL_TRANSMIT | CY_LABEL_DIFFUSE;
+    case CY_CLOSURE_BSDF_OREN_NAYAR_ID:
+      sample_uniform_hemisphere(l.N, randu, randv, omega_in, pdf);
+      if (keep_side(sd.Ng, *omega_in, true)) {
+        v = oren_nayar_value(l, sd.I, *omega_in);
+        *value = mk3(v, v, v);
+      }
+      else {
+        *pdf = 0.0f;
+        *value = zero3();
+      }
+      return CY_LABEL_REFLECT | CY_LABEL_DIFFUSE;
+    case CY_CLOSURE_BSDF_PRINCIPLED_DIFFUSE_ID:
+      sample_cos_hemisphere(l.N, randu, randv, omega_in, pdf);
+      if (keep_side(sd.Ng, *omega_in, true)) {
+        v = disney_diffuse_value(l, sd.I, *omega_in);
+        *value = mk3(v, v, v);
+      }
+      else {
+        *pdf = 0.0f;
+      }
+      return CY_LABEL_REFLECT | CY_LABEL_DIFFUSE;
+    case CY_CLOSURE_BSDF_PRINCIPLED_SHEEN_ID:
+      if (!EXT) {
+        *pdf = 0.0f;
+        return CY_LABEL_NONE;
+      }
+      sample_cos_hemisphere(l.N, randu, randv, omega_in, pdf);
+      if (keep_side(sd.Ng, *omega_in, true)) {
+        if (sheen_value(l, sd.I, *omega_in, &v))
+          *value = mk3(v, v, v);
+        else
+          *pdf = 0.0f;
+      }
+      else {
+        *pdf = 0.0f;
+      }
+      return CY_LABEL_REFLECT | CY_LABEL_DIFFUSE;
+    case CY_CLOSURE_BSDF_REFLECTION_ID: {
+      /* perfect mirror: one direction, "some high number" as density */
+      const float cosNO = dot(l.N, sd.I);
+      if (cosNO > 0.0f) {
+        *omega_in = (2.0f * cosNO) * l.N - sd.I;
+        if (dot(sd.Ng, *omega_in) > 0.0f) {
+          *pdf = 1e6f;
+          *value = mk3(1e6f, 1e6f, 1e6f);
+        }
+      }
+      return CY_LABEL_REFLECT | CY_LABEL_SINGULAR;
+    }
+    case CY_CLOSURE_BSDF_REFRACTION_ID: {
+      const DielectricSplit split = dielectric_split(l.ior, l.N, sd.I);
+      if (!split.inside && split.reflectance != 1.0f) {
+        *pdf = 1e6f;
+        *value = mk3(1e6f, 1e6f, 1e6f);
+        *omega_in = split.refracted;
+      }
+      return CY_LABEL_TRANSMIT | CY_LABEL_SINGULAR;
+    }
     case CY_CLOSURE_BSDF_TRANSPARENT_ID:
-      /* closure/bsdf_transparent.h:103-125: straight through */
+      /* straight through */
       *omega_in = -sd.I;
-      *pdf = 1;
-      *eval = one3();
+      *pdf = 1.0f;
+      *value = one3();
       return CY_LABEL_TRANSMIT | CY_LABEL_TRANSPARENT;
     case CY_CLOSURE_BSDF_MICROFACET_GGX_ID:
     case CY_CLOSURE_BSDF_MICROFACET_GGX_FRESNEL_ID:
     case CY_CLOSURE_BSDF_MICROFACET_GGX_CLEARCOAT_ID:
     case CY_CLOSURE_BSDF_MICROFACET_GGX_REFRACTION_ID:
-      return bsdf_microfacet_ggx_sample(sc, sd.Ng, sd.I, randu, randv, eval, omega_in, pdf);
+      return ggx_sample(l, sd.Ng, sd.I, randu, randv, value, omega_in, pdf);
+    case CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_ID:
+    case CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_FRESNEL_ID:
+    case CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_GLASS_ID:
+    case CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_GLASS_FRESNEL_ID:
+      if (EXT)
+        return multi_ggx_sample(l, sd.I, randu, randv, value, omega_in, pdf, &sd.lcg_state);
+      *pdf = 0.0f;
+      return CY_LABEL_NONE;
     default:
       *pdf = 0.0f;
       return CY_LABEL_NONE;
   }
 }
 
-/* closure/bsdf.h bsdf_sample: the closure's own sampler, then the terminator terms on
- * the reflection side (closure/bsdf.h:466-489) */
+/* the lobe's own sampler, then the terminator factors on the reflection side */
 template<bool EXT>
-CY_DEV int bsdf_sample(const ShaderDataG &sd, const Closure &sc, float randu, float randv,
-                       f3 *eval, f3 *omega_in, float *pdf)
+CY_DEV int bsdf_sample(ShaderDataG &sd, const Lobe &l, float randu, float randv, f3 *value,
+                       f3 *omega_in, float *pdf)
 {
-  const int label = bsdf_sample_closure<EXT>(sd, sc, randu, randv, eval, omega_in, pdf);
+  const int label = bsdf_sample_lobe<EXT>(sd, l, randu, randv, value, omega_in, pdf);
   if (EXT && sd.terminator_terms && !(label & CY_LABEL_TRANSMIT)) {
     if (sd.terminator_freq > 1.0f)
-      *eval *= shift_cos_in(dot(*omega_in, sc.N), sd.terminator_freq);
-    if ((label & CY_LABEL_DIFFUSE) && !isequal3(sc.N, sd.N))
-      *eval *= bump_shadowing_term(sd.N, sc.N, *omega_in);
+      *value *= shift_cos_in(dot(*omega_in, l.N), sd.terminator_freq);
+    if ((label & CY_LABEL_DIFFUSE) && !isequal3(l.N, sd.N))
+      *value *= bump_shadowing_term(sd.N, l.N, *omega_in);
   }
   return label;
 }

@@ -1,9 +1,19 @@
-/* cymath.cuh - scalar float3/float4 arithmetic with the SAME operation order as the
+/* cymath.cuh - scalar float3/float4 arithmetic, in two flavours.
+ *
+ * The plain operators (dot, cross, normalize ...) keep the operation ORDER of the
  * reference's generic (non-SSE) CPU math (intern/cycles/util/util_math_float3.h
- * :113-160,233-270,353-390, util_math_float4.h:243-250, util_transform.h:56-108),
- * so that, compiled with -fmad=false, every expression rounds exactly like the
- * oracle built with -ffp-contract=off.  Fused multiply-adds appear only where
- * written explicitly (fmaf) - the BVH8 slab test, where parity is not affected.
+ * :113-160,233-270,353-390, util_math_float4.h:243-250, util_transform.h:56-108); how
+ * each operation rounds is the build's choice (Makefile FPFLAGS).  The shipped build
+ * compiles them without FMA contraction and with IEEE division / square root, so every
+ * expression rounds like the oracle built with -ffp-contract=off.
+ *
+ * The x-prefixed functions (xdot, xcross, xnormalize_len, xtransform_point ...) are EXACT
+ * under any flags: every operation is an IEEE round-to-nearest intrinsic that the compiler
+ * neither fuses nor approximates, in the reference's association order.  Everything a hit
+ * id depends on goes through them - the ray / triangle test, the instance transforms of
+ * the traversal - so u, v, t and the accept / reject decisions are the oracle's bits even
+ * in a build that trades shading precision for speed.  Fused multiply-adds appear only
+ * where written explicitly (fmaf): the BVH8 slab test, conservative by construction.
  */
 #ifndef B200_CYMATH_CUH
 #define B200_CYMATH_CUH
@@ -240,6 +250,92 @@ CY_DEV void make_orthonormals(f3 N, f3 *a, f3 *b)
     *a = mk3(N.z - N.y, N.x + N.z, -N.y - N.x);
   *a = normalize(*a);
   *b = cross(N, *a);
+}
+
+/* ----------------------------------------------------------- exact flavour */
+
+#ifdef __CUDA_ARCH__
+CY_DEV float xmul(float a, float b)
+{
+  return __fmul_rn(a, b);
+}
+CY_DEV float xadd(float a, float b)
+{
+  return __fadd_rn(a, b);
+}
+CY_DEV float xsub(float a, float b)
+{
+  return __fsub_rn(a, b);
+}
+CY_DEV float xdiv(float a, float b)
+{
+  return __fdiv_rn(a, b);
+}
+CY_DEV float xsqrt(float a)
+{
+  return __fsqrt_rn(a);
+}
+#else /* host builds are compiled with -ffp-contract=off */
+CY_DEV float xmul(float a, float b)
+{
+  return a * b;
+}
+CY_DEV float xadd(float a, float b)
+{
+  return a + b;
+}
+CY_DEV float xsub(float a, float b)
+{
+  return a - b;
+}
+CY_DEV float xdiv(float a, float b)
+{
+  return a / b;
+}
+CY_DEV float xsqrt(float a)
+{
+  return sqrtf(a);
+}
+#endif
+
+CY_DEV f3 xadd3(f3 a, f3 b)
+{
+  return mk3(xadd(a.x, b.x), xadd(a.y, b.y), xadd(a.z, b.z));
+}
+CY_DEV f3 xsub3(f3 a, f3 b)
+{
+  return mk3(xsub(a.x, b.x), xsub(a.y, b.y), xsub(a.z, b.z));
+}
+CY_DEV f3 xscale3(f3 a, float f)
+{
+  return mk3(xmul(a.x, f), xmul(a.y, f), xmul(a.z, f));
+}
+CY_DEV float xdot(f3 a, f3 b)
+{
+  return xadd(xadd(xmul(a.x, b.x), xmul(a.y, b.y)), xmul(a.z, b.z));
+}
+CY_DEV f3 xcross(f3 a, f3 b)
+{
+  return mk3(xsub(xmul(a.y, b.z), xmul(a.z, b.y)), xsub(xmul(a.z, b.x), xmul(a.x, b.z)),
+             xsub(xmul(a.x, b.y), xmul(a.y, b.x)));
+}
+/* normalize_len: length, then a multiply by its reciprocal */
+CY_DEV f3 xnormalize_len(f3 a, float *t)
+{
+  *t = xsqrt(xdot(a, a));
+  return xscale3(a, xdiv(1.0f, *t));
+}
+CY_DEV f3 xtransform_point(const tfm34 &t, f3 a)
+{
+  return mk3(xadd(xadd(xadd(xmul(a.x, t.x.x), xmul(a.y, t.x.y)), xmul(a.z, t.x.z)), t.x.w),
+             xadd(xadd(xadd(xmul(a.x, t.y.x), xmul(a.y, t.y.y)), xmul(a.z, t.y.z)), t.y.w),
+             xadd(xadd(xadd(xmul(a.x, t.z.x), xmul(a.y, t.z.y)), xmul(a.z, t.z.z)), t.z.w));
+}
+CY_DEV f3 xtransform_direction(const tfm34 &t, f3 a)
+{
+  return mk3(xadd(xadd(xmul(a.x, t.x.x), xmul(a.y, t.x.y)), xmul(a.z, t.x.z)),
+             xadd(xadd(xmul(a.x, t.y.x), xmul(a.y, t.y.y)), xmul(a.z, t.y.z)),
+             xadd(xadd(xmul(a.x, t.z.x), xmul(a.y, t.z.y)), xmul(a.z, t.z.z)));
 }
 
 #endif /* B200_CYMATH_CUH */

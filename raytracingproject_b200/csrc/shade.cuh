@@ -84,6 +84,18 @@ CY_DEV uint32_t cmj_hash_simple(uint32_t i, uint32_t p)
   return i;
 }
 
+/* Sobol points of the samples a wavefront batch covers, tabulated once per batch by
+ * k_sobol_table: every path of a batch asks for the same few (sample, dimension) pairs -
+ * a batch holds a handful of sample indices, a bounce touches eight dimensions - and the
+ * bit loop over the direction vectors was 9 % of the instructions of the shading kernel.
+ * tab == NULL (batch too wide for the table): computed on the fly as before. */
+struct SobolTable {
+  const uint32_t *tab; /* [sample - s0][dimension] */
+  int s0;
+  uint32_t ns, nd;
+};
+__constant__ SobolTable g_sobol;
+
 /* kernel/kernel_random.h:40-50 - Sobol via the uploaded direction vectors */
 CY_DEV uint32_t sobol_dimension(int index, int dimension)
 {
@@ -208,7 +220,12 @@ CY_DEV float path_rng_1D(uint32_t rng_hash, int sample, int dimension)
     return pmj_sample_1D(sample, rng_hash, dimension);
   if (kd_int(KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_CMJ)
     return cmj_sample_1D(sample, kd_int(KD_INT_AA_SAMPLES), rng_hash + (uint32_t)dimension);
-  uint32_t result = sobol_dimension(sample, dimension);
+  uint32_t result;
+  const uint32_t si = (uint32_t)(sample - g_sobol.s0);
+  if (g_sobol.tab && si < g_sobol.ns && (uint32_t)dimension < g_sobol.nd)
+    result = __ldg(&g_sobol.tab[si * g_sobol.nd + (uint32_t)dimension]);
+  else
+    result = sobol_dimension(sample, dimension);
   float r = (float)result * (1.0f / (float)0xFFFFFFFF);
   uint32_t tmp_rng = cmj_hash_simple((uint32_t)dimension, rng_hash);
   float shift = (float)tmp_rng * (1.0f / (float)0xFFFFFFFF);
@@ -696,12 +713,13 @@ __device__ __noinline__ int svm_eval_extended_node(ShaderDataG &sd, float *stack
  * shaders only): one interpreter carrying everything costs 4.5 % of the frame, the
  * split costs nothing. */
 template<bool FULL>
-__device__ __noinline__ bool svm_eval_nodes_t(ShaderDataG &sd, PathDepths depths,
-                                              uint32_t path_flag, int max_closures)
+__device__ __noinline__ bool svm_eval_nodes_t(ShaderDataG &sd, LobeArena &arena,
+                                              PathDepths depths, uint32_t path_flag,
+                                              int max_closures)
 {
   float stack[SVM_STACK_GPU];
-  sd.num_closure = 0;
-  sd.num_closure_left = max_closures;
+  arena_reset(arena, max_closures);
+  sd.transparent_at = -1;
   sd.svm_closure_weight = zero3();
   int offset = sd.shader & CY_SHADER_MASK;
 
@@ -715,7 +733,7 @@ __device__ __noinline__ bool svm_eval_nodes_t(ShaderDataG &sd, PathDepths depths
         offset = (int)node.y; /* SHADER_TYPE_SURFACE */
         break;
       case CY_NODE_CLOSURE_BSDF:
-        if (!svm_node_closure_bsdf<FULL>(sd, stack, node, path_flag, &offset))
+        if (!svm_node_closure_bsdf<FULL>(sd, arena, stack, node, path_flag, &offset))
           return false;
         break;
       case CY_NODE_CLOSURE_EMISSION:
@@ -876,133 +894,184 @@ __device__ unsigned int g_svm_scope_miss;
 
 /* EXT is a property of the bound program, decided on the host, and selects the kernel
  * instance: programs with extended nodes (or a Principled BSDF whose sheen is not a
- * constant zero) run the full interpreter, all others the lean one. */
+ * constant zero, or a multi-scatter lobe) run the full interpreter, all others the lean
+ * one. */
 template<bool EXT>
-CY_DEV void svm_eval_nodes(ShaderDataG &sd, PathDepths depths, uint32_t path_flag,
-                           int max_closures)
+CY_DEV void svm_eval_nodes(ShaderDataG &sd, LobeArena &arena, PathDepths depths,
+                           uint32_t path_flag, int max_closures)
 {
   if (EXT) {
-    svm_eval_nodes_t<true>(sd, depths, path_flag, max_closures);
+    svm_eval_nodes_t<true>(sd, arena, depths, path_flag, max_closures);
   }
-  else if (!svm_eval_nodes_t<false>(sd, depths, path_flag, max_closures)) {
+  else if (!svm_eval_nodes_t<false>(sd, arena, depths, path_flag, max_closures)) {
     g_svm_scope_miss = 1u;
-    sd.num_closure = 0;
+    arena_reset(arena, 0);
     sd.flag &= ~(CY_SD_BSDF | CY_SD_EMISSION);
   }
 }
 
-/* kernel_shader.h:1057-1110 */
+/* kernel_shader.h:1057-1112: the surface shader of a hit.  `rng_seed` = rng_hash +
+ * rng_offset + sample * 0xb4bc3953 of the path (lcg_state_init): the seed of the random
+ * walks of multi-scatter lobes, drawn from only when the shader made one. */
 template<bool EXT>
-CY_DEV void shader_eval_surface(ShaderDataG &sd, PathDepths depths, uint32_t path_flag)
+CY_DEV void shader_eval_surface(ShaderDataG &sd, LobeArena &arena, PathDepths depths,
+                                uint32_t path_flag, uint32_t rng_seed)
 {
   int max_closures;
   if (path_flag & (CY_PATH_RAY_TERMINATE | CY_PATH_RAY_SHADOW | CY_PATH_RAY_EMISSION))
     max_closures = 0;
   else
     max_closures = min(kd_int(KD_INT_MAX_CLOSURES), MAX_CLOSURES_GPU);
-  svm_eval_nodes<EXT>(sd, depths, path_flag, max_closures);
+  svm_eval_nodes<EXT>(sd, arena, depths, path_flag, max_closures);
+  if (EXT && (sd.flag & CY_SD_BSDF_NEEDS_LCG))
+    sd.lcg_state = lcg_seed(rng_seed);
 }
 
-/* kernel_shader.h:530-555 */
+/* A shader that can only emit (a lamp, the background, an emission-only evaluation of a
+ * surface): no lobes, so no arena behind it. */
 template<bool EXT>
-CY_DEV void shader_prepare_closures(ShaderDataG &sd, const PathStateG &state)
+CY_DEV void shader_eval_emission(ShaderDataG &sd, PathDepths depths, uint32_t path_flag)
+{
+  LobeArena none;
+  none.q = nullptr;
+  svm_eval_nodes<EXT>(sd, none, depths, path_flag, 0);
+}
+
+/* First hit of a path with several lobes: every lobe keeps at least an eighth of the
+ * total sample weight, so that a lobe that matters after the bounce is not starved by
+ * how it looks from the camera (shader_prepare_closures, kernel_shader.h:530-555);
+ * EXT also decides whether the terminator factors are needed at this point. */
+template<bool EXT>
+CY_DEV void shader_prepare_lobes(ShaderDataG &sd, LobeArena &arena, bool first_hit)
 {
   if (EXT)
-    bsdf_terminator_terms_setup(sd);
-  if (state.bounce + state.transparent_bounce == 0 && sd.num_closure > 1) {
+    bsdf_terminator_terms_setup(sd, arena);
+  if (first_hit && arena.n > 1) {
     float sum = 0.0f;
-    for (int i = 0; i < sd.num_closure; i++) {
-      if (sd.closure[i].type <= CY_CLOSURE_BSSRDF_PRINCIPLED_RANDOM_WALK_ID)
-        sum += sd.closure[i].sample_weight;
+    int at = 0;
+    for (int i = 0; i < arena.n; i++) {
+      const uint32_t kind = lobe_kind_at(arena, at);
+      if (lobe_is_sampled(kind))
+        sum += lobe_sample_weight_at(arena, at);
+      at += lobe_words(kind);
     }
-    for (int i = 0; i < sd.num_closure; i++) {
-      if (sd.closure[i].type <= CY_CLOSURE_BSSRDF_PRINCIPLED_RANDOM_WALK_ID)
-        sd.closure[i].sample_weight = fmaxf(sd.closure[i].sample_weight, 0.125f * sum);
+    at = 0;
+    for (int i = 0; i < arena.n; i++) {
+      const uint32_t kind = lobe_kind_at(arena, at);
+      if (lobe_is_sampled(kind))
+        lobe_set_sample_weight_at(arena, at,
+                                  fmaxf(lobe_sample_weight_at(arena, at), 0.125f * sum));
+      at += lobe_words(kind);
     }
   }
 }
 
-/* kernel_shader.h:556-582 (_shader_bsdf_multi_eval), use_light_pass = 0 */
-template<bool EXT>
-CY_DEV void shader_bsdf_multi_eval(const ShaderDataG &sd, f3 omega_in, float *pdf, int skip,
-                                   f3 *result_eval, float sum_pdf, float sum_sample_weight)
+/* filter_glossy (kernel_path.h:280-299): widen the roughness of the GGX lobes after a
+ * blurry bounce */
+CY_DEV void shader_blur_lobes(LobeArena &arena, float roughness)
 {
-  for (int i = 0; i < sd.num_closure; i++) {
-    const Closure &sc = sd.closure[i];
-    if (i != skip && sc.type <= CY_CLOSURE_BSDF_TRANSPARENT_ID) {
-      float bsdf_pdf = 0.0f;
-      f3 eval = bsdf_eval<EXT>(sd, sc, omega_in, &bsdf_pdf);
-      if (bsdf_pdf != 0.0f) {
-        *result_eval += eval * sc.weight;
-        sum_pdf += bsdf_pdf * sc.sample_weight;
-      }
-      sum_sample_weight += sc.sample_weight;
-    }
+  int at = 0;
+  for (int i = 0; i < arena.n; i++) {
+    lobe_blur_at(arena, at, roughness);
+    at += lobe_words(lobe_kind_at(arena, at));
   }
-  *pdf = (sum_sample_weight > 0.0f) ? sum_pdf / sum_sample_weight : 0.0f;
 }
 
-/* kernel_montecarlo.h:133-136 */
+/* power heuristic of multiple importance sampling (beta = 2) */
 CY_DEV float power_heuristic(float a, float b)
 {
   return (a * a) / (a * a + b * b);
 }
 
-/* kernel_shader.h:612-636 (non-branched) */
+/* Sum of all lobes but `skip` for direction omega_in (value weighted by the lobe's
+ * colour, pdf by its sample weight), continuing the running sums of a sampled lobe
+ * (_shader_bsdf_multi_eval, kernel_shader.h:556-582, no light passes) */
 template<bool EXT>
-CY_DEV f3 shader_bsdf_eval(const ShaderDataG &sd, f3 omega_in, float light_pdf, bool use_mis)
+CY_DEV void shader_bsdf_multi_eval(ShaderDataG &sd, const LobeArena &arena, f3 omega_in,
+                                   float *pdf, int skip, f3 *result_eval, float sum_pdf,
+                                   float sum_sample_weight)
+{
+  int at = 0;
+  for (int i = 0; i < arena.n; i++) {
+    const uint32_t kind = lobe_kind_at(arena, at);
+    if (i != skip && lobe_is_bsdf(kind)) {
+      const Lobe l = lobe_fetch(arena, at);
+      float bsdf_pdf = 0.0f;
+      const f3 eval = bsdf_eval<EXT>(sd, l, omega_in, &bsdf_pdf);
+      if (bsdf_pdf != 0.0f) {
+        *result_eval += eval * l.weight;
+        sum_pdf += bsdf_pdf * l.sample_weight;
+      }
+      sum_sample_weight += l.sample_weight;
+    }
+    at += lobe_words(kind);
+  }
+  *pdf = (sum_sample_weight > 0.0f) ? sum_pdf / sum_sample_weight : 0.0f;
+}
+
+/* BSDF towards a light sample, MIS-weighted against BSDF sampling
+ * (shader_bsdf_eval, kernel_shader.h:612-636, non-branched) */
+template<bool EXT>
+CY_DEV f3 shader_bsdf_eval(ShaderDataG &sd, const LobeArena &arena, f3 omega_in, float light_pdf,
+                           bool use_mis)
 {
   f3 eval = zero3();
   float pdf;
-  shader_bsdf_multi_eval<EXT>(sd, omega_in, &pdf, -1, &eval, 0.0f, 0.0f);
-  if (use_mis) {
-    float weight = power_heuristic(light_pdf, pdf);
-    eval *= weight;
-  }
+  shader_bsdf_multi_eval<EXT>(sd, arena, omega_in, &pdf, -1, &eval, 0.0f, 0.0f);
+  if (use_mis)
+    eval *= power_heuristic(light_pdf, pdf);
   return eval;
 }
 
-/* kernel_shader.h:638-680 + 739-775 */
+/* Picks a lobe in proportion to its sample weight, samples it, then adds the other lobes
+ * for the sampled direction (shader_bsdf_pick + shader_bsdf_sample,
+ * kernel_shader.h:638-680, 739-775) */
 template<bool EXT>
-CY_DEV int shader_bsdf_sample(ShaderDataG &sd, float randu, float randv, f3 *bsdf_eval_out,
-                              f3 *omega_in, float *pdf)
+CY_DEV int shader_bsdf_sample(ShaderDataG &sd, const LobeArena &arena, float randu, float randv,
+                              f3 *bsdf_eval_out, f3 *omega_in, float *pdf)
 {
-  int sampled = 0;
-  if (sd.num_closure > 1) {
+  int sampled = 0, sampled_at = 0;
+  if (arena.n > 1) {
     float sum = 0.0f;
-    for (int i = 0; i < sd.num_closure; i++) {
-      if (sd.closure[i].type <= CY_CLOSURE_BSSRDF_PRINCIPLED_RANDOM_WALK_ID)
-        sum += sd.closure[i].sample_weight;
+    int at = 0;
+    for (int i = 0; i < arena.n; i++) {
+      const uint32_t kind = lobe_kind_at(arena, at);
+      if (lobe_is_sampled(kind))
+        sum += lobe_sample_weight_at(arena, at);
+      at += lobe_words(kind);
     }
-    float r = randu * sum;
+    const float r = randu * sum;
     float partial_sum = 0.0f;
-    for (int i = 0; i < sd.num_closure; i++) {
-      const Closure &sc = sd.closure[i];
-      if (sc.type <= CY_CLOSURE_BSSRDF_PRINCIPLED_RANDOM_WALK_ID) {
-        float next_sum = partial_sum + sc.sample_weight;
+    at = 0;
+    for (int i = 0; i < arena.n; i++) {
+      const uint32_t kind = lobe_kind_at(arena, at);
+      if (lobe_is_sampled(kind)) {
+        const float sw = lobe_sample_weight_at(arena, at);
+        const float next_sum = partial_sum + sw;
         if (r < next_sum) {
           sampled = i;
-          randu = (r - partial_sum) / sc.sample_weight;
+          sampled_at = at;
+          /* rescale so the number can be reused for the lobe's own sampling */
+          randu = (r - partial_sum) / sw;
           break;
         }
         partial_sum = next_sum;
       }
+      at += lobe_words(kind);
     }
   }
-  const Closure &sc = sd.closure[sampled];
-  if (!(sc.type <= CY_CLOSURE_BSDF_TRANSPARENT_ID)) {
-    *pdf = 0.0f;
-    return CY_LABEL_NONE;
-  }
-  f3 eval = zero3();
   *pdf = 0.0f;
-  int label = bsdf_sample<EXT>(sd, sc, randu, randv, &eval, omega_in, pdf);
+  if (!lobe_is_bsdf(lobe_kind_at(arena, sampled_at)))
+    return CY_LABEL_NONE;
+  const Lobe l = lobe_fetch(arena, sampled_at);
+  f3 eval = zero3();
+  const int label = bsdf_sample<EXT>(sd, l, randu, randv, &eval, omega_in, pdf);
   if (*pdf != 0.0f) {
-    *bsdf_eval_out = eval * sc.weight;
-    if (sd.num_closure > 1) {
-      float sweight = sc.sample_weight;
-      shader_bsdf_multi_eval<EXT>(sd, *omega_in, pdf, sampled, bsdf_eval_out, *pdf * sweight,
-                                  sweight);
+    *bsdf_eval_out = eval * l.weight;
+    if (arena.n > 1) {
+      const float sweight = l.sample_weight;
+      shader_bsdf_multi_eval<EXT>(sd, arena, *omega_in, pdf, sampled, bsdf_eval_out,
+                                  *pdf * sweight, sweight);
     }
   }
   return label;
@@ -1485,7 +1554,7 @@ CY_DEV f3 direct_emissive_eval(ShaderDataG &emission_sd, PathDepths depths, Ligh
       }
     }
     ls->Ng = emission_sd.Ng;
-    shader_eval_surface<EXT>(emission_sd, depths, CY_PATH_RAY_EMISSION);
+    shader_eval_emission<EXT>(emission_sd, depths, CY_PATH_RAY_EMISSION);
     /* shader_emissive_eval: emissive_simple_eval(Ng, I) * weight */
     if (emission_sd.flag & CY_SD_EMISSION) {
       float cosNO = fabsf(dot(emission_sd.Ng, emission_sd.I));
@@ -1532,7 +1601,7 @@ CY_DEV f3 indirect_background(ShaderDataG &emission_sd, const PathStateG &state,
     emission_sd.type = 0;
     emission_sd.u = emission_sd.v = 0.0f;
     emission_sd.dPdu = zero3();
-    shader_eval_surface<EXT>(emission_sd, path_depths(state), state.flag | CY_PATH_RAY_EMISSION);
+    shader_eval_emission<EXT>(emission_sd, path_depths(state), state.flag | CY_PATH_RAY_EMISSION);
     if (emission_sd.flag & CY_SD_EMISSION)
       L = emission_sd.closure_emission_background;
   }

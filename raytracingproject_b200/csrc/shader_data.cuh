@@ -1,5 +1,5 @@
 /* shader_data.cuh - the shading point record (ShaderData, kernel_types.h:1011-1110, cut
- * to what the supported closures and nodes read), the closure record, the SVM stack
+ * to what the supported closures and nodes read), the SVM stack
  * accessors (svm/svm.h:53-113) and the small object / projection transforms the node
  * implementations share.  Free of warp intrinsics, so that the node files
  * (svm_nodes.cuh, svm_tex.cuh) also compile for the host in tests/test_svm_host_cpu.py. */
@@ -26,19 +26,9 @@ CY_DEV f3 transform_perspective(const float4 tx, const float4 ty, const float4 t
 
 /* ----------------------------------------------------------- ShaderData */
 
-struct Closure {
-  int type;
-  f3 weight;
-  float sample_weight;
-  f3 N;
-  /* microfacet / principled parameters (closure/bsdf_microfacet.h:38-56) */
-  float alpha_x, alpha_y, ior;
-  f3 T;
-  f3 color, cspec0, fresnel_color; /* MicrofacetExtra */
-  float clearcoat;
-  float roughness; /* PrincipledDiffuseBsdf */
-};
-
+/* The shading point.  Its BSDF lobes are NOT part of it: they live in the shared-memory
+ * arena of lobes.cuh, so this record is small enough to stay in registers and an
+ * emission-only evaluation (a lamp or the background) costs no closure storage at all. */
 struct ShaderDataG {
   f3 P, N, Ng, I;
   f3 dPdu;
@@ -48,12 +38,12 @@ struct ShaderDataG {
   int lamp; /* lamp index while its emission shader runs, else -1 (LAMP_NONE) */
   float u, v, ray_length;
   float terminator_freq; /* KernelObject::shadow_terminator_offset, fetched once per point */
-  int terminator_terms;  /* some closure needs the terms of bsdf_terminator_terms() */
+  int terminator_terms;  /* some lobe needs the factors of bsdf_terminator_terms_setup() */
   f3 svm_closure_weight;
   f3 closure_emission_background;
   f3 closure_transparent_extinction; /* valid when flag & SD_TRANSPARENT */
-  int num_closure, num_closure_left;
-  Closure closure[MAX_CLOSURES_GPU];
+  int transparent_at;  /* arena offset of the merged transparent lobe, -1 = none yet */
+  uint32_t lcg_state;  /* random walk of the multi-scatter lobes (SD_BSDF_NEEDS_LCG) */
 };
 
 CY_DEV uint32_t shader_flags(int shader)
@@ -112,39 +102,7 @@ CY_DEV float fast_acosf(float x)
   return x < 0 ? CY_M_PI_F - a : a;
 }
 
-/* -------------------------------------------------------- closure storage */
-
-/* closure/alloc.h:19-68 */
-CY_DEV Closure *closure_alloc(ShaderDataG &sd, f3 weight)
-{
-  if (sd.num_closure_left == 0)
-    return NULL;
-  Closure *sc = &sd.closure[sd.num_closure];
-  sc->type = CY_CLOSURE_NONE_ID;
-  sc->weight = weight;
-  sd.num_closure++;
-  sd.num_closure_left--;
-  return sc;
-}
-CY_DEV bool closure_alloc_extra(ShaderDataG &sd)
-{
-  if (1 > sd.num_closure_left) {
-    sd.num_closure--;
-    sd.num_closure_left++;
-    return false;
-  }
-  sd.num_closure_left -= 1;
-  return true;
-}
-CY_DEV Closure *bsdf_alloc(ShaderDataG &sd, f3 weight)
-{
-  Closure *sc = closure_alloc(sd, weight);
-  if (sc == NULL)
-    return NULL;
-  float sample_weight = fabsf(average(weight));
-  sc->sample_weight = sample_weight;
-  return (sample_weight >= CLOSURE_WEIGHT_CUTOFF) ? sc : NULL;
-}
+/* ------------------------------------------------------------ emission */
 
 CY_DEV void emission_setup(ShaderDataG &sd, f3 weight)
 {

@@ -70,44 +70,45 @@ CY_DEV float2 bytes_to_float2(uint32_t x, int jj)
 }
 
 /* util_math_intersect.h:88-195, scalar branch.  Returns true and u,v,t on a hit
- * closer than ray_t. */
+ * closer than ray_t.  Exact arithmetic (cymath.cuh, x-functions): the signs of U, V, W,
+ * the depth test and u, v, t are the reference's bits, whatever the build flags. */
 CY_DEV bool ray_triangle_intersect(
     f3 P, f3 dir, float ray_t, f3 tri_a, f3 tri_b, f3 tri_c, float *isect_u, float *isect_v,
     float *isect_t)
 {
-  const f3 v0 = tri_c - P;
-  const f3 v1 = tri_a - P;
-  const f3 v2 = tri_b - P;
+  const f3 v0 = xsub3(tri_c, P);
+  const f3 v1 = xsub3(tri_a, P);
+  const f3 v2 = xsub3(tri_b, P);
 
-  const f3 e0 = v2 - v0;
-  const f3 e1 = v0 - v1;
-  const f3 e2 = v1 - v2;
+  const f3 e0 = xsub3(v2, v0);
+  const f3 e1 = xsub3(v0, v1);
+  const f3 e2 = xsub3(v1, v2);
 
-  const float U = dot(cross(v2 + v0, e0), dir);
-  const float V = dot(cross(v0 + v1, e1), dir);
-  const float W = dot(cross(v1 + v2, e2), dir);
+  const float U = xdot(xcross(xadd3(v2, v0), e0), dir);
+  const float V = xdot(xcross(xadd3(v0, v1), e1), dir);
+  const float W = xdot(xcross(xadd3(v1, v2), e2), dir);
 
   const float minUVW = fminf(U, fminf(V, W));
   const float maxUVW = fmaxf(U, fmaxf(V, W));
   if (minUVW < 0.0f && maxUVW > 0.0f)
     return false;
 
-  const f3 Ng1 = cross(e1, e0);
-  const f3 Ng = Ng1 + Ng1;
-  const float den = dot(Ng, dir);
+  const f3 Ng1 = xcross(e1, e0);
+  const f3 Ng = xadd3(Ng1, Ng1);
+  const float den = xdot(Ng, dir);
   if (den == 0.0f)
     return false;
 
-  const float T = dot(v0, Ng);
+  const float T = xdot(v0, Ng);
   const int sign_den = (__float_as_int(den) & 0x80000000);
   const float sign_T = xor_signmask(T, sign_den);
-  if ((sign_T < 0.0f) || (sign_T > ray_t * xor_signmask(den, sign_den)))
+  if ((sign_T < 0.0f) || (sign_T > xmul(ray_t, xor_signmask(den, sign_den))))
     return false;
 
-  const float inv_den = 1.0f / den;
-  *isect_u = U * inv_den;
-  *isect_v = V * inv_den;
-  *isect_t = T * inv_den;
+  const float inv_den = xdiv(1.0f, den);
+  *isect_u = xmul(U, inv_den);
+  *isect_v = xmul(V, inv_den);
+  *isect_t = xmul(T, inv_den);
   return true;
 }
 
@@ -341,16 +342,17 @@ template<bool ANY_HIT, bool COUNT> struct Traversal {
       if (inst_bits != 0u)
         push(stack, make_uint2(Gt.x, inst_bits));
 
+      /* exact arithmetic: the object-space ray and the rescaled limit decide hits */
       const tfm34 itfm = object_itfm(object);
       float len;
-      const f3 oP = transform_point(itfm, mk3(__ldg(job.ray_P(qi))));
-      const f3 oD = normalize_len(transform_direction(itfm, mk3(__ldg(job.ray_D(qi)))), &len);
+      const f3 oP = xtransform_point(itfm, mk3(__ldg(job.ray_P(qi))));
+      const f3 oD = xnormalize_len(xtransform_direction(itfm, mk3(__ldg(job.ray_D(qi)))), &len);
       ray_space_setup(rs, oP, oD);
       push(stack, make_uint2(__float_as_uint(tmax), __float_as_uint(len)));
       push(stack, make_uint2(BVH8_SENTINEL, 0u));
       inst_hit = false;
       if (tmax != FLT_MAX)
-        tmax *= len;
+        tmax = xmul(tmax, len);
       cur_object = object;
 
       G = make_uint2(__float_as_uint(ra.x), 0x80000000u);
@@ -367,7 +369,7 @@ template<bool ANY_HIT, bool COUNT> struct Traversal {
           /* instance pop - geom_object.h:447-460 */
           const uint2 saved = stack[--sp]; /* (world-space limit, direction scale) */
           if (inst_hit)
-            tmax = tmax / __uint_as_float(saved.y);
+            tmax = xdiv(tmax, __uint_as_float(saved.y));
           else
             tmax = __uint_as_float(saved.x);
           ray_space_setup(rs, mk3(__ldg(job.ray_P(qi))), mk3(__ldg(job.ray_D(qi))));

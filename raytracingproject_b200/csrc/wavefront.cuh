@@ -28,9 +28,6 @@
 
 #define WF_MAX_KEYS 4096
 #define WF_BLOCK 256
-#ifndef WF_OCTANT_SORT
-#  define WF_OCTANT_SORT 1
-#endif
 /* sort keys below this are histogrammed / ranked in shared memory, the (rare) rest by
  * global atomics */
 #define WF_SMALL_KEYS 64
@@ -95,6 +92,7 @@ struct PathPool {
   bool has_ts = false; /* transparent-shadow arrays carved */
   bool has_ao = false; /* shadow queue sized for two entries per path (light + AO ray) */
   WFCounters *h_counters = nullptr; /* pinned */
+  uint32_t *sobol_tab = nullptr;    /* SOBOL_TABLE_MAX entries */
 };
 
 struct BatchParams {
@@ -126,71 +124,43 @@ CY_DEV unsigned int warp_append(unsigned int *counter, bool pred)
  * addresses, and same-address atomics with a return value serialise in L2 at about
  * 2 ns each - per warp that was the whole cost of init_from_camera and a third of
  * shade_surface.  Must be reached by every thread of the block (WF_BLOCK threads).
- *
- * Queue a is additionally ordered by `bin_a` (0..7) inside the block's slot range:
- * shade_surface passes the direction octant of the new ray, so that the 32 consecutive
- * rays a traversal warp stages share origin neighbourhood AND child visiting order. */
-CY_DEV void block_append2(unsigned int *counter_a, bool pred_a, unsigned int bin_a,
-                          unsigned int *counter_b, bool pred_b, unsigned int *slot_a,
-                          unsigned int *slot_b)
+ * Lanes get consecutive slots in thread order, so what a block appends stays in the
+ * (sorted, spatially coherent) order it was read in. */
+CY_DEV void block_append2(unsigned int *counter_a, bool pred_a, unsigned int *counter_b,
+                          bool pred_b, unsigned int *slot_a, unsigned int *slot_b)
 {
   constexpr int NW = WF_BLOCK / 32;
-  static_assert(NW == 8, "the scan below covers an 8 x 8 table with two entries per lane");
-  __shared__ unsigned int s_tab[9][NW]; /* rows 0..7: queue a by bin, row 8: queue b */
+  __shared__ unsigned int s_tab[2][NW];
   const unsigned int lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
   const unsigned int lt_mask = (1u << lane) - 1u;
-  if (threadIdx.x < 9 * NW)
-    (&s_tab[0][0])[threadIdx.x] = 0u;
-  __syncthreads();
-  const unsigned int key_a = pred_a ? (bin_a & 7u) : 8u;
-  const unsigned int peers = __match_any_sync(0xffffffffu, key_a);
+  const unsigned int ma = __ballot_sync(0xffffffffu, pred_a);
   const unsigned int mb = __ballot_sync(0xffffffffu, pred_b);
-  if (pred_a && lane == (unsigned)(__ffs(peers) - 1))
-    s_tab[key_a][w] = __popc(peers);
-  if (lane == 0)
-    s_tab[8][w] = __popc(mb);
-  __syncthreads();
-  if (w == 0) {
-    /* queue a: exclusive scan of the 8 x NW table in (bin, warp) order, two entries a lane */
-    unsigned int *tab = &s_tab[0][0];
-    const unsigned int v0 = tab[lane], v1 = tab[lane + 32];
-    unsigned int i0 = v0, i1 = v1;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned int u0 = __shfl_up_sync(0xffffffffu, i0, o);
-      const unsigned int u1 = __shfl_up_sync(0xffffffffu, i1, o);
-      if (lane >= (unsigned)o) {
-        i0 += u0;
-        i1 += u1;
-      }
-    }
-    const unsigned int t0 = __shfl_sync(0xffffffffu, i0, 31);
-    const unsigned int ta = t0 + __shfl_sync(0xffffffffu, i1, 31);
-    /* queue b: lanes 0..NW-1 */
-    const unsigned int vb = (lane < NW) ? s_tab[8][lane] : 0u;
-    unsigned int ib = vb;
-#pragma unroll
-    for (int o = 1; o < NW; o <<= 1) {
-      const unsigned int ub = __shfl_up_sync(0xffffffffu, ib, o);
-      if (lane >= (unsigned)o)
-        ib += ub;
-    }
-    const unsigned int tb = __shfl_sync(0xffffffffu, ib, NW - 1);
-    unsigned int base_a = 0, base_b = 0;
-    if (lane == 0 && ta != 0u)
-      base_a = atomicAdd(counter_a, ta);
-    if (lane == 1 && tb != 0u)
-      base_b = atomicAdd(counter_b, tb);
-    base_a = __shfl_sync(0xffffffffu, base_a, 0);
-    base_b = __shfl_sync(0xffffffffu, base_b, 1);
-    tab[lane] = base_a + i0 - v0;
-    tab[lane + 32] = base_a + t0 + i1 - v1;
-    if (lane < NW)
-      s_tab[8][lane] = base_b + ib - vb;
+  if (lane == 0) {
+    s_tab[0][w] = __popc(ma);
+    s_tab[1][w] = __popc(mb);
   }
   __syncthreads();
-  *slot_a = pred_a ? s_tab[key_a][w] + __popc(peers & lt_mask) : 0u;
-  *slot_b = s_tab[8][w] + __popc(mb & lt_mask);
+  if (w == 0) {
+    /* lanes 0..NW-1 scan queue a, lanes 16..16+NW-1 queue b */
+    const unsigned int q = lane >> 4, j = lane & 15u;
+    const unsigned int v = (j < NW) ? s_tab[q][j] : 0u;
+    unsigned int inc = v;
+#pragma unroll
+    for (int o = 1; o < NW; o <<= 1) {
+      const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o, 16);
+      if (j >= (unsigned)o)
+        inc += u;
+    }
+    unsigned int base = 0;
+    if (j == NW - 1 && inc != 0u)
+      base = atomicAdd(q ? counter_b : counter_a, inc);
+    base = __shfl_sync(0xffffffffu, base, NW - 1, 16);
+    if (j < NW)
+      s_tab[q][j] = base + inc - v;
+  }
+  __syncthreads();
+  *slot_a = s_tab[0][w] + __popc(ma & lt_mask);
+  *slot_b = s_tab[1][w] + __popc(mb & lt_mask);
   __syncthreads(); /* the table is reused by the next call */
 }
 
@@ -325,6 +295,18 @@ CY_DEV void batch_pixel(const BatchParams &bp, unsigned int pix, int *x, int *y)
   }
 }
 
+/* ----------------------------------------------------------- Sobol table */
+
+#define SOBOL_TABLE_MAX (1u << 16) /* entries: 256 KB */
+
+__global__ void k_sobol_table(uint32_t *tab, int s0, unsigned int ns, unsigned int nd)
+{
+  const unsigned int n = ns * nd;
+  for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < n;
+       e += gridDim.x * blockDim.x)
+    tab[e] = sobol_dimension(s0 + (int)(e / nd), (int)(e % nd));
+}
+
 /* ------------------------------------------------------ init_from_camera */
 
 __global__ void __launch_bounds__(WF_BLOCK)
@@ -367,8 +349,7 @@ __global__ void __launch_bounds__(WF_BLOCK)
       p.L[i] = make_float4(0.0f, 0.0f, 0.0f, (t == 0.0f) ? 1.0f : 0.0f);
     }
     unsigned int slot, unused;
-    block_append2(&p.counters->n_active, t != 0.0f, 0u, &p.counters->n_active, false, &slot,
-                  &unused);
+    block_append2(&p.counters->n_active, t != 0.0f, &p.counters->n_active, false, &slot, &unused);
     if (t != 0.0f) {
       p.q_active[slot] = (int)i;
       p.ray_P_t[slot] = make_float4(P.x, P.y, P.z, t);
@@ -627,25 +608,43 @@ __global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(Pa
 #ifndef SHADE_MIN_BLOCKS_EXT
 #  define SHADE_MIN_BLOCKS_EXT 2
 #endif
+/* Dynamic shared memory of the surface-shading kernel, per block:
+ *   [SHADE_STAGE_WORDS][WF_BLOCK] floats   the staged shadow-ray record of each thread,
+ * a column per thread: a warp touches one 128-byte row per word, no conflicts. */
+#define SHADE_STAGE_WORDS 12
+#define SHADE_SMEM_BYTES (SHADE_STAGE_WORDS * WF_BLOCK * sizeof(float))
+
+/* kernel_path_shader_apply .. kernel_path_surface_bounce (kernel_path.h:254-321, 540-640;
+ * kernel_path_surface.h:22-125, 270-358) for the hits of one bounce, in shader order.
+ *
+ * What a thread keeps where: the lobes of its shading point in its arena (lobes.cuh);
+ * the shadow ray it wants traced (origin, direction, contribution - 12 words) in
+ * its staging column from the moment the light connection is done, so the BSDF sampling
+ * that follows does not carry them in registers; slots in the next-bounce and shadow
+ * queues come from one block-wide reservation at the end of the round, after which the
+ * staged record is copied out to its slot. */
 template<bool EXT>
 __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_MIN_BLOCKS)
     k_shade_surface(PathSoA p, int num_keys)
 {
+  extern __shared__ float s_shade[];
+  float *const stage = s_shade + threadIdx.x;
+  float4 arena_words[ARENA_QUADS];
+  LobeArena arena;
+  arena.q = arena_words;
+
   WFCounters *c = p.counters;
   const unsigned int begin = c->offsets[1];
   const unsigned int end = c->offsets[num_keys + 1];
   const unsigned int total = end - begin;
-  /* the grid-stride loop is uniform per warp so that warp_append's ballots see
-   * every lane of the warp that is still looping */
+  /* the grid-stride loop is uniform per block: block_append2 has barriers */
   const unsigned int rounds = (total + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
   for (unsigned int r = 0; r < rounds; r++) {
     const unsigned int k = r * gridDim.x * blockDim.x + blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = k < total;
     bool want_next = false, want_shadow = false;
     int i = -1;
     float4 out_ray_P = make_float4(0.0f, 0.0f, 0.0f, 0.0f), out_ray_D = out_ray_P;
-    float4 out_sh_P = out_ray_P, out_sh_D = out_ray_P, out_sh_C = out_ray_P;
-    if (valid) {
+    if (k < total) {
       const int2 qs = p.q_sorted[begin + k];
       const int qpos = qs.x;
       i = qs.y;
@@ -661,43 +660,32 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
       st.ray_t = tp.w;
       f3 throughput = mk3(tp);
       f3 L = mk3(Lr);
-      f3 rayP = mk3(r0), rayD = mk3(r1);
       float ray_t = r0.w;
-      const int hit_prim = __float_as_int(hit.w);
 
       ShaderDataG sd;
-      {
-        /* lamps crossed before the hit (kernel_path.h:537) - uses `sd` as scratch */
-        path_lamp_emission<EXT>(st, rayP, rayD, hit.x, throughput, sd, L);
-      }
+      /* lamps crossed before the hit (kernel_path.h:537) - uses `sd` as scratch */
+      path_lamp_emission<EXT>(st, mk3(r0), mk3(r1), hit.x, throughput, sd, L);
 
       bool alive = !path_state_ao_bounce(st); /* kernel_path.h:560-562 */
       if (alive) {
-        shader_setup_from_ray(sd, hit_prim, hit_object, hit.x, hit.y, hit.z, rayP, rayD);
-        shader_eval_surface<EXT>(sd, path_depths(st), st.flag);
-        shader_prepare_closures<EXT>(sd, st);
+        shader_setup_from_ray(sd, __float_as_int(hit.w), hit_object, hit.x, hit.y, hit.z, mk3(r0),
+                              mk3(r1));
+        shader_eval_surface<EXT>(sd, arena, path_depths(st), st.flag,
+                                 st.rng_hash + (uint32_t)st.rng_offset +
+                                     (uint32_t)st.sample * 0xb4bc3953u);
+        shader_prepare_lobes<EXT>(sd, arena, st.bounce + st.transparent_bounce == 0);
 
-        /* kernel_path_shader_apply - kernel_path.h:254-321 (no holdout / shadow catcher;
-         * filter_glossy handled below) */
+        /* kernel_path_shader_apply - kernel_path.h:254-321 (no holdout / shadow catcher:
+         * refused at bind time) */
         if (kd_float(KD_INT_FILTER_GLOSSY) != FLT_MAX) {
-          float blur_pdf = kd_float(KD_INT_FILTER_GLOSSY) * st.min_ray_pdf;
-          if (blur_pdf < 1.0f) {
-            float blur_roughness = sqrtf(1.0f - blur_pdf) * 0.5f;
-            for (int ci = 0; ci < sd.num_closure; ci++) {
-              Closure &sc = sd.closure[ci];
-              if (sc.type >= CY_CLOSURE_BSDF_MICROFACET_GGX_ID &&
-                  sc.type <= CY_CLOSURE_BSDF_MICROFACET_GGX_REFRACTION_ID &&
-                  sc.type != CY_CLOSURE_BSDF_MICROFACET_BECKMANN_ID) {
-                sc.alpha_x = fmaxf(blur_roughness, sc.alpha_x);
-                sc.alpha_y = fmaxf(blur_roughness, sc.alpha_y);
-              }
-            }
-          }
+          const float blur_pdf = kd_float(KD_INT_FILTER_GLOSSY) * st.min_ray_pdf;
+          if (blur_pdf < 1.0f)
+            shader_blur_lobes(arena, sqrtf(1.0f - blur_pdf) * 0.5f);
         }
         if (sd.flag & CY_SD_EMISSION) {
           /* indirect_primitive_emission - kernel_emission.h:214-233 */
-          float cosNO = fabsf(dot(sd.Ng, sd.I));
-          float res = (cosNO > 0.0f) ? 1.0f : 0.0f;
+          const float cosNO = fabsf(dot(sd.Ng, sd.I));
+          const float res = (cosNO > 0.0f) ? 1.0f : 0.0f;
           f3 emission = mk3(res, res, res) * sd.closure_emission_background;
           if (!(st.flag & CY_PATH_RAY_MIS_SKIP) && (sd.flag & CY_SD_USE_MIS)) {
             /* this triangle is also in the light distribution: weight the BSDF-sampled
@@ -712,12 +700,12 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
         }
 
         /* russian roulette - kernel_path.h:578-589 */
-        float probability = path_state_continuation_probability(st, throughput);
+        const float probability = path_state_continuation_probability(st, throughput);
         if (probability == 0.0f) {
           alive = false;
         }
         else if (probability != 1.0f) {
-          float terminate = path_state_rng_1D<EXT>(st, CY_PRNG_TERMINATE);
+          const float terminate = path_state_rng_1D<EXT>(st, CY_PRNG_TERMINATE);
           if (terminate >= probability)
             alive = false;
           else
@@ -733,12 +721,15 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
         path_state_rng_2D<EXT>(st, CY_PRNG_BSDF_U, &bsdf_u, &bsdf_v);
         const float ao_factor = kd_float(KD_BG_AO_FACTOR);
         f3 ao_bsdf = zero3(), ao_N = zero3();
-        for (int k = 0; k < sd.num_closure; k++) { /* shader_bsdf_ao, kernel_shader.h */
-          const Closure &sc = sd.closure[k];
-          if (closure_is_bsdf_diffuse(sc.type)) {
-            ao_bsdf += sc.weight * ao_factor;
-            ao_N += sc.N * fabsf(average(sc.weight));
+        int at = 0;
+        for (int n = 0; n < arena.n; n++) { /* shader_bsdf_ao, kernel_shader.h */
+          const uint32_t kind = lobe_kind_at(arena, at);
+          if (lobe_is_diffuse(kind)) {
+            const f3 w = lobe_weight_at(arena, at);
+            ao_bsdf += w * ao_factor;
+            ao_N += lobe_normal_at(arena, at) * fabsf(average(w));
           }
+          at += lobe_words(kind);
         }
         ao_N = is_zero(ao_N) ? sd.N : normalize(ao_N);
         f3 ao_D;
@@ -776,8 +767,8 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
             /* direct_emission - kernel_emission.h:101-212 */
             f3 light_eval;
             {
-              /* the emission ShaderData must not clobber sd: evaluate constant
-               * emission directly, fall back to a scratch copy otherwise */
+              /* constant emission needs no shader run; anything else evaluates the
+               * light's shader on a scratch shading point */
               f3 ce;
               if (shader_constant_emission_eval(ls.shader, &ce)) {
                 if ((ls.prim != CY_PRIM_NONE) && dot(ls.Ng, -ls.D) < 0.0f)
@@ -792,11 +783,13 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
               }
             }
             if (!is_zero(light_eval)) {
-              f3 eval = shader_bsdf_eval<EXT>(sd, ls.D, ls.pdf, (ls.shader & CY_SHADER_USE_MIS) != 0);
+              f3 eval = shader_bsdf_eval<EXT>(sd, arena, ls.D, ls.pdf,
+                                              (ls.shader & CY_SHADER_USE_MIS) != 0);
               eval *= light_eval / ls.pdf;
               bool ok = !is_zero(eval);
               if (ok && kd_float(KD_INT_LIGHT_INV_RR_THRESHOLD) > 0.0f) {
-                float probability = max3(fabs3(eval)) * kd_float(KD_INT_LIGHT_INV_RR_THRESHOLD);
+                const float probability = max3(fabs3(eval)) *
+                                          kd_float(KD_INT_LIGHT_INV_RR_THRESHOLD);
                 if (probability < 1.0f) {
                   if (terminate >= probability)
                     ok = false;
@@ -810,8 +803,8 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
                 f3 contribution = throughput * eval;
                 path_radiance_clamp(&contribution, st.bounce);
                 if (ls.shader & CY_SHADER_CAST_SHADOW) {
-                  bool transmit = (dot(sd.Ng, ls.D) < 0.0f);
-                  f3 sP = ray_offset(sd.P, transmit ? -sd.Ng : sd.Ng);
+                  const bool transmit = (dot(sd.Ng, ls.D) < 0.0f);
+                  const f3 sP = ray_offset(sd.P, transmit ? -sd.Ng : sd.Ng);
                   f3 sD;
                   float st_t;
                   if (ls.t == FLT_MAX) {
@@ -822,11 +815,17 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
                     sD = ray_offset(ls.P, ls.Ng) - sP;
                     sD = normalize_len(sD, &st_t);
                   }
-                  out_sh_P = make_float4(sP.x, sP.y, sP.z, st_t);
-                  out_sh_D = make_float4(sD.x, sD.y, sD.z,
-                                         __uint_as_float(CY_PATH_RAY_SHADOW_OPAQUE));
-                  out_sh_C = make_float4(contribution.x, contribution.y, contribution.z,
-                                         __int_as_float(st.transparent_bounce));
+                  stage[0 * WF_BLOCK] = sP.x;
+                  stage[1 * WF_BLOCK] = sP.y;
+                  stage[2 * WF_BLOCK] = sP.z;
+                  stage[3 * WF_BLOCK] = st_t;
+                  stage[4 * WF_BLOCK] = sD.x;
+                  stage[5 * WF_BLOCK] = sD.y;
+                  stage[6 * WF_BLOCK] = sD.z;
+                  stage[7 * WF_BLOCK] = contribution.x;
+                  stage[8 * WF_BLOCK] = contribution.y;
+                  stage[9 * WF_BLOCK] = contribution.z;
+                  stage[10 * WF_BLOCK] = __int_as_float(st.transparent_bounce);
                   want_shadow = true;
                 }
                 else {
@@ -844,21 +843,21 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
           path_state_rng_2D<EXT>(st, CY_PRNG_BSDF_U, &bsdf_u, &bsdf_v);
           f3 bsdf_eval = zero3(), omega_in = zero3();
           float bsdf_pdf;
-          int label = shader_bsdf_sample<EXT>(sd, bsdf_u, bsdf_v, &bsdf_eval, &omega_in, &bsdf_pdf);
+          const int label = shader_bsdf_sample<EXT>(sd, arena, bsdf_u, bsdf_v, &bsdf_eval,
+                                                    &omega_in, &bsdf_pdf);
           if (!(bsdf_pdf == 0.0f || is_zero(bsdf_eval))) {
             /* LABEL_TRANSMIT_TRANSPARENT (closure/bsdf.h:466-475) needs transparent glass,
              * which check_scope refuses (threshold < 0 here) */
             /* path_radiance_bsdf_bounce, no light passes */
-            float inverse_pdf = 1.0f / bsdf_pdf;
-            throughput *= bsdf_eval * inverse_pdf;
+            throughput *= bsdf_eval * (1.0f / bsdf_pdf);
             if (!(label & CY_LABEL_TRANSPARENT)) {
               st.ray_pdf = bsdf_pdf;
               st.ray_t = 0.0f;
               st.min_ray_pdf = fminf(bsdf_pdf, st.min_ray_pdf);
             }
             path_state_next(st, label);
-            rayP = ray_offset(sd.P, (label & CY_LABEL_TRANSMIT) ? -sd.Ng : sd.Ng);
-            rayD = normalize(omega_in);
+            const f3 nP = ray_offset(sd.P, (label & CY_LABEL_TRANSMIT) ? -sd.Ng : sd.Ng);
+            const f3 nD = normalize(omega_in);
             if (st.bounce == 0)
               ray_t -= sd.ray_length;
             else
@@ -869,40 +868,35 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
               float *dbg = p.debug + 32 * (st.bounce + st.transparent_bounce - 1);
               dbg[0] = r0.x, dbg[1] = r0.y, dbg[2] = r0.z, dbg[3] = r0.w;
               dbg[4] = r1.x, dbg[5] = r1.y, dbg[6] = r1.z, dbg[7] = hit.x;
-              dbg[8] = (float)hit_prim, dbg[9] = (float)hit_object, dbg[10] = sd.P.x;
+              dbg[8] = (float)__float_as_int(hit.w), dbg[9] = (float)hit_object, dbg[10] = sd.P.x;
               dbg[11] = sd.P.y, dbg[12] = sd.P.z, dbg[13] = sd.N.x, dbg[14] = sd.N.y;
-              dbg[15] = sd.N.z, dbg[16] = (float)(sd.flag & 0xffff), dbg[17] = (float)sd.num_closure;
-              dbg[18] = (float)sd.closure[0].type, dbg[19] = sd.closure[0].sample_weight;
-              dbg[20] = (float)sd.closure[1].type, dbg[21] = sd.closure[1].sample_weight;
+              dbg[15] = sd.N.z, dbg[16] = (float)(sd.flag & 0xffff), dbg[17] = (float)arena.n;
+              dbg[18] = (float)lobe_id(lobe_kind_at(arena, 0)),
+              dbg[19] = lobe_sample_weight_at(arena, 0);
+              dbg[20] = 0.0f, dbg[21] = 0.0f;
               dbg[22] = (float)label, dbg[23] = bsdf_pdf, dbg[24] = omega_in.x;
               dbg[25] = omega_in.y, dbg[26] = omega_in.z, dbg[27] = throughput.x;
               dbg[28] = throughput.y, dbg[29] = throughput.z, dbg[30] = bsdf_u, dbg[31] = bsdf_v;
             }
+            /* visibility and AO-bounce clipping of the NEXT segment, decided here so the
+             * traversal kernel needs nothing but the 32-byte ray (kernel_path.h:66-71) */
+            uint32_t vis = path_state_ray_visibility(st.flag);
+            if (path_state_ao_bounce(st)) {
+              vis = CY_PATH_RAY_SHADOW;
+              ray_t = kd_float(KD_BG_AO_DISTANCE);
+            }
+            out_ray_P = make_float4(nP.x, nP.y, nP.z, ray_t);
+            out_ray_D = make_float4(nD.x, nD.y, nD.z, __uint_as_float(vis));
+            p.ray_pdf[i] = st.ray_pdf;
+            p.throughput[i] = make_float4(throughput.x, throughput.y, throughput.z, st.ray_t);
+            state_store(p, i, st);
           }
         }
       }
-
-      /* write back */
       p.L[i] = make_float4(L.x, L.y, L.z, Lr.w);
-      if (want_next) {
-        /* visibility and AO-bounce clipping of the NEXT segment, decided here so the
-         * traversal kernel needs nothing but the 32-byte ray (kernel_path.h:66-71) */
-        uint32_t vis = path_state_ray_visibility(st.flag);
-        if (path_state_ao_bounce(st)) {
-          vis = CY_PATH_RAY_SHADOW;
-          ray_t = kd_float(KD_BG_AO_DISTANCE);
-        }
-        out_ray_P = make_float4(rayP.x, rayP.y, rayP.z, ray_t);
-        out_ray_D = make_float4(rayD.x, rayD.y, rayD.z, __uint_as_float(vis));
-        p.ray_pdf[i] = st.ray_pdf;
-        p.throughput[i] = make_float4(throughput.x, throughput.y, throughput.z, st.ray_t);
-        state_store(p, i, st);
-      }
     }
     unsigned int s_next, s_sh;
-    const unsigned int octant = (out_ray_D.x < 0.0f ? 1u : 0u) | (out_ray_D.y < 0.0f ? 2u : 0u) |
-                                (out_ray_D.z < 0.0f ? 4u : 0u);
-    block_append2(&c->n_next, want_next, WF_OCTANT_SORT ? octant : 0u, &c->n_shadow, want_shadow, &s_next, &s_sh);
+    block_append2(&c->n_next, want_next, &c->n_shadow, want_shadow, &s_next, &s_sh);
     if (want_next) {
       p.q_next[s_next] = i;
       p.nray_P_t[s_next] = out_ray_P;
@@ -910,9 +904,12 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
     }
     if (want_shadow) {
       p.q_shadow[s_sh] = i;
-      p.sh_P_t[s_sh] = out_sh_P;
-      p.sh_D[s_sh] = out_sh_D;
-      p.sh_contrib[s_sh] = out_sh_C;
+      p.sh_P_t[s_sh] = make_float4(stage[0 * WF_BLOCK], stage[1 * WF_BLOCK], stage[2 * WF_BLOCK],
+                                   stage[3 * WF_BLOCK]);
+      p.sh_D[s_sh] = make_float4(stage[4 * WF_BLOCK], stage[5 * WF_BLOCK], stage[6 * WF_BLOCK],
+                                 __uint_as_float(CY_PATH_RAY_SHADOW_OPAQUE));
+      p.sh_contrib[s_sh] = make_float4(stage[7 * WF_BLOCK], stage[8 * WF_BLOCK],
+                                       stage[9 * WF_BLOCK], stage[10 * WF_BLOCK]);
     }
   }
 }
@@ -1052,7 +1049,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_shade_shadow_step(PathSoA p, int c
           depths.bounce = 1;
           depths.diffuse = depths.glossy = depths.transmission = 0;
           depths.transparent = (short)bounce;
-          shader_eval_surface<EXT>(sd, depths, CY_PATH_RAY_SHADOW);
+          shader_eval_emission<EXT>(sd, depths, CY_PATH_RAY_SHADOW);
           f3 t = (sd.flag & CY_SD_TRANSPARENT) ? sd.closure_transparent_extinction : zero3();
           f3 nthr = mk3(thr.x, thr.y, thr.z) * t;
           if (!is_zero(nthr)) {
@@ -1079,7 +1076,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_shade_shadow_step(PathSoA p, int c
       }
     }
     unsigned int slot, unused;
-    block_append2(&c->n_ts[cur ^ 1], go_on, 0u, &c->n_ts[cur ^ 1], false, &slot, &unused);
+    block_append2(&c->n_ts[cur ^ 1], go_on, &c->n_ts[cur ^ 1], false, &slot, &unused);
     if (go_on) {
       p.ts_P_t[cur ^ 1][slot] = out_P;
       p.ts_D[cur ^ 1][slot] = out_D;
@@ -1273,6 +1270,8 @@ static void free_pool(b200_ctx *ctx)
     cudaFree(ctx->pool->block);
   if (ctx->pool->h_counters)
     cudaFreeHost(ctx->pool->h_counters);
+  if (ctx->pool->sobol_tab)
+    cudaFree(ctx->pool->sobol_tab);
   delete ctx->pool;
   ctx->pool = nullptr;
   ctx->pool_bytes = 0;
@@ -1348,10 +1347,13 @@ static int ensure_pool(b200_ctx *ctx, size_t capacity, bool transparent_shadows,
   s.ts_idx[1] = transparent_shadows ? (int *)(b + o_tsI1) : nullptr;
   s.ts_thr = transparent_shadows ? (float4 *)(b + o_tsT) : nullptr;
   s.counters = (WFCounters *)(b + o_cnt);
-  if (cudaMallocHost(&pool->h_counters, sizeof(WFCounters)) != cudaSuccess) {
+  if (cudaMallocHost(&pool->h_counters, sizeof(WFCounters)) != cudaSuccess ||
+      cudaMalloc(&pool->sobol_tab, SOBOL_TABLE_MAX * sizeof(uint32_t)) != cudaSuccess) {
     cudaFree(pool->block);
+    if (pool->h_counters)
+      cudaFreeHost(pool->h_counters);
     delete pool;
-    return fail(ctx, B200_ERR_CUDA, "pinned counter allocation failed");
+    return fail(ctx, B200_ERR_CUDA, "pinned counter / Sobol table allocation failed");
   }
   ctx->pool = pool;
   return B200_OK;
@@ -1579,12 +1581,17 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
           if (!(const_run_end == i && const_known[sheen_slot] &&
                 const_value[sheen_slot] <= 1e-5f /* CLOSURE_WEIGHT_CUTOFF */))
             *features |= SVM_USES_EXTENDED_NODES;
-          if (distribution != CY_CLOSURE_BSDF_MICROFACET_GGX_GLASS_ID) {
-            why = "Principled BSDF with the Multiscatter GGX distribution is outside the "
-                  "hot-path scope (random-walk closure); set distribution to GGX";
-            return false;
-          }
+          /* Multiscatter GGX (the node's default): the random-walk lobes live in the full
+           * kernels */
+          if (distribution != CY_CLOSURE_BSDF_MICROFACET_GGX_GLASS_ID)
+            *features |= SVM_USES_EXTENDED_NODES;
           i += 6;
+        }
+        else if (type == CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_ID ||
+                 type == CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_GLASS_ID) {
+          /* Glossy / Anisotropic / Glass BSDF nodes with Multiscatter GGX */
+          *features |= SVM_USES_EXTENDED_NODES;
+          i += 2;
         }
         else if (type == CY_CLOSURE_BSDF_REFLECTION_ID ||
                  type == CY_CLOSURE_BSDF_MICROFACET_GGX_ID) {
@@ -1687,6 +1694,32 @@ static int check_scope(b200_ctx *ctx)
   return B200_OK;
 }
 
+/* The surface-shading kernels use more dynamic shared memory than the default limit;
+ * their grids are sized to what is resident (blocks per SM x SMs), each block loops. */
+static int shade_kernel_setup(b200_ctx *ctx)
+{
+  if (ctx->shade_blocks_per_sm[0] > 0)
+    return B200_OK;
+  DeviceGuard guard(ctx->ordinal);
+  CUDA_TRY(ctx, cudaFuncSetAttribute(k_shade_surface<false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)SHADE_SMEM_BYTES));
+  CUDA_TRY(ctx, cudaFuncSetAttribute(k_shade_surface<true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)SHADE_SMEM_BYTES));
+  int lean = 0, full = 0;
+  CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lean, k_shade_surface<false>,
+                                                              WF_BLOCK, SHADE_SMEM_BYTES));
+  CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&full, k_shade_surface<true>,
+                                                              WF_BLOCK, SHADE_SMEM_BYTES));
+  if (lean < 1 || full < 1)
+    return fail(ctx, B200_ERR_CUDA, "surface-shading kernel does not fit on an SM");
+  /* a few waves of blocks per SM even the tail out; more only adds reservation atomics */
+  ctx->shade_blocks_per_sm[0] = lean * 2;
+  ctx->shade_blocks_per_sm[1] = full * 2;
+  return B200_OK;
+}
+
 extern "C" {
 
 int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *cancel)
@@ -1745,6 +1778,10 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
       ctx, ctx->opt_trace_blocks_per_sm > 0 ? (int)ctx->opt_trace_blocks_per_sm : 8);
   const int refill = refill_threshold(ctx);
   cudaStream_t st = ctx->stream;
+  rc = shade_kernel_setup(ctx);
+  if (rc)
+    return rc;
+  const int grid_shade = ctx->num_sms * ctx->shade_blocks_per_sm[svm_ext ? 1 : 0];
 
   b200_stats stats;
   memset(&stats, 0, sizeof(stats));
@@ -1778,6 +1815,27 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
       soa.debug = ctx->d_debug;
       soa.debug_slot = (int)ctx->opt_debug_slot;
       CUDA_TRY(ctx, cudaMemsetAsync(soa.counters, 0, sizeof(WFCounters), st));
+      if (attempt == 0) {
+        /* the Sobol points of this batch's samples, for every dimension a path can reach */
+        SobolTable sobol = {nullptr, bp.sample0, 0u, 0u};
+        const HostArray *lut = find_global(ctx, "__sample_pattern_lut");
+        if (kd_host<int>(ctx, KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_SOBOL && lut) {
+          const unsigned int reach = CY_PRNG_BASE_NUM +
+                                     (unsigned int)(kd_host<int>(ctx, KD_INT_MAX_BOUNCE) +
+                                                    kd_host<int>(ctx, KD_INT_TRANSPARENT_MAX_BOUNCE) +
+                                                    3) * CY_PRNG_BOUNCE_NUM;
+          const unsigned int nd = std::min<unsigned int>(reach, (unsigned int)(lut->bytes / 128));
+          if (nd > 0 && (size_t)nd * bp.nsamples <= SOBOL_TABLE_MAX) {
+            sobol.tab = pool->sobol_tab;
+            sobol.ns = (unsigned int)bp.nsamples;
+            sobol.nd = nd;
+            k_sobol_table<<<64, 256, 0, st>>>(pool->sobol_tab, bp.sample0, sobol.ns, nd);
+            stats.kernel_launches += 1;
+          }
+        }
+        CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(g_sobol, &sobol, sizeof(sobol), 0,
+                                              cudaMemcpyHostToDevice, st));
+      }
       k_init_from_camera<<<grid_wide, WF_BLOCK, 0, st>>>(soa, bp);
       stats.kernel_launches += 1;
 
@@ -1794,11 +1852,11 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
         k_sort_scatter<<<grid_wide, WF_BLOCK, 0, st>>>(soa);
         if (svm_ext) {
           k_shade_background<true><<<grid_wide, WF_BLOCK, 0, st>>>(soa);
-          k_shade_surface<true><<<grid_wide, WF_BLOCK, 0, st>>>(soa, num_keys);
+          k_shade_surface<true><<<grid_shade, WF_BLOCK, SHADE_SMEM_BYTES, st>>>(soa, num_keys);
         }
         else {
           k_shade_background<false><<<grid_wide, WF_BLOCK, 0, st>>>(soa);
-          k_shade_surface<false><<<grid_wide, WF_BLOCK, 0, st>>>(soa, num_keys);
+          k_shade_surface<false><<<grid_shade, WF_BLOCK, SHADE_SMEM_BYTES, st>>>(soa, num_keys);
         }
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev3, st));
         if (use_ao) /* never with transparent shadows (check_scope) */

@@ -243,6 +243,12 @@ def _closure_shaders(variant):
             '  <connect from="t bsdf" to="m closure2"/>\n', "m closure", attrs)
         glass = _node_shader("glass", '  <transparent_bsdf name="t" color="0.75 0.9 1"/>\n',
                              "t bsdf", attrs)
+    elif variant == 4:
+        # the multi-scatter options of the Glossy and Glass nodes (random-walk lobes)
+        metal = _node_shader("metal", '  <glossy_bsdf name="g" distribution="Multiscatter GGX" '
+                             'roughness="0.45" color="0.9 0.7 0.3"/>\n', "g bsdf")
+        glass = _node_shader("glass", '  <glass_bsdf name="g" distribution="Multiscatter GGX" '
+                             'roughness="0.3" IOR="1.45" color="0.9 0.97 1"/>\n', "g bsdf")
     elif variant == 0:
         metal = _node_shader("metal", '  <glass_bsdf name="g" distribution="GGX" roughness="0.15" '
                              'IOR="1.45" color="0.95 0.97 1"/>\n', "g bsdf")
@@ -713,7 +719,7 @@ def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
     xml += _background((0, 0, 0), 0.0, "" if ao is None else
                        ' use_ao="true" ao_factor="%s" ao_distance="%s"' % (_f(ao[0]), _f(ao[1])))
     closure_variants = {"closures": 0, "closures2": 1, "transparent_opaque_shadow": 2,
-                        "transparent": 3, "textured": 10, "textured2": 11, "textured3": 12, "textured4": 13}
+                        "transparent": 3, "closures_multi": 4, "textured": 10, "textured2": 11, "textured3": 12, "textured4": 13}
     if materials in ("textured", "textured2", "textured3", "textured4"):
         xml += _textured_shaders(closure_variants[materials] - 10)
     elif materials in closure_variants:

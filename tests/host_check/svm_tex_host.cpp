@@ -213,15 +213,18 @@ extern "C" __attribute__((visibility("default"))) int host_svm_node(int offset, 
   return offset;
 }
 
-/* NODE_CLOSURE_BSDF at `offset` -> closures (csrc/svm_closure.cuh, the full variant), then
- * bsdf_eval for `omega_in` and bsdf_sample for (randu, randv) on each of them
- * (csrc/bsdf.cuh).  out: [0] = number of closures, then 20 floats per closure: type,
- * weight xyz, sample_weight, eval xyz, pdf, label, sampled eval xyz, omega xyz, pdf. */
+/* NODE_CLOSURE_BSDF at `offset` -> lobes in an arena (csrc/svm_closure.cuh, the full
+ * variant), then bsdf_eval for `omega_in` and bsdf_sample for (randu, randv) on each of
+ * them (csrc/bsdf.cuh, microfacet.cuh, microfacet_multi.cuh).  out: [0] = number of lobes,
+ * then 20 floats per lobe: type, weight xyz, sample_weight, eval xyz, pdf, label, sampled
+ * eval xyz, omega xyz, pdf.  The LCG of the multi-scatter lobes starts at 0 and runs on
+ * from lobe to lobe, like the reference probe's zeroed ShaderData. */
 extern "C" __attribute__((visibility("default"))) int host_svm_closure(
     int offset, float *stack, const HostShadingPoint *p, const float *closure_weight,
     unsigned int path_flag, const float *omega_in, float randu, float randv, float *out)
 {
   static ShaderDataG sd;
+  static float4 arena_words[ARENA_QUADS];
   memset(&sd, 0, sizeof(sd));
   sd.P = mk3(p->P[0], p->P[1], p->P[2]);
   sd.N = mk3(p->N[0], p->N[1], p->N[2]);
@@ -232,27 +235,32 @@ extern "C" __attribute__((visibility("default"))) int host_svm_closure(
   sd.prim = p->prim;
   sd.lamp = p->lamp;
   sd.terminator_freq = object_shadow_terminator_offset(sd.object);
-  sd.num_closure = 0;
-  sd.num_closure_left = MAX_CLOSURES_GPU;
+  sd.transparent_at = -1;
+  sd.lcg_state = 0;
+  LobeArena arena;
+  arena.q = arena_words;
+  arena_reset(arena, MAX_CLOSURES_GPU);
   sd.svm_closure_weight = mk3(closure_weight[0], closure_weight[1], closure_weight[2]);
   const uint4 node = g_scene.svm_nodes[offset];
   offset++;
-  svm_node_closure_bsdf<true>(sd, stack, node, path_flag, &offset);
-  bsdf_terminator_terms_setup(sd);
-  out[0] = (float)sd.num_closure;
+  svm_node_closure_bsdf<true>(sd, arena, stack, node, path_flag, &offset);
+  bsdf_terminator_terms_setup(sd, arena);
+  out[0] = (float)arena.n;
   const f3 wi = mk3(omega_in[0], omega_in[1], omega_in[2]);
-  for (int i = 0; i < sd.num_closure; i++) {
-    const Closure &sc = sd.closure[i];
+  int at = 0;
+  for (int i = 0; i < arena.n; i++) {
+    const Lobe l = lobe_fetch(arena, at);
+    at += lobe_words(l.kind);
     float *o = out + 1 + 20 * i;
-    o[0] = (float)sc.type;
-    o[1] = sc.weight.x, o[2] = sc.weight.y, o[3] = sc.weight.z;
-    o[4] = sc.sample_weight;
+    o[0] = (float)lobe_id(l.kind);
+    o[1] = l.weight.x, o[2] = l.weight.y, o[3] = l.weight.z;
+    o[4] = l.sample_weight;
     float pdf = 0.0f;
-    const f3 ev = bsdf_eval<true>(sd, sc, wi, &pdf);
+    const f3 ev = bsdf_eval<true>(sd, l, wi, &pdf);
     o[5] = ev.x, o[6] = ev.y, o[7] = ev.z, o[8] = pdf;
     f3 sev = zero3(), swi = zero3();
     float spdf = 0.0f;
-    const int label = bsdf_sample<true>(sd, sc, randu, randv, &sev, &swi, &spdf);
+    const int label = bsdf_sample<true>(sd, l, randu, randv, &sev, &swi, &spdf);
     o[9] = (float)label;
     o[10] = sev.x, o[11] = sev.y, o[12] = sev.z;
     o[13] = swi.x, o[14] = swi.y, o[15] = swi.z;

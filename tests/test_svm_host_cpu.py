@@ -401,7 +401,8 @@ def test_scope_check_without_a_device(ref):
 
 
 CLOSURE_SCENES = ["principled", "closures", "closures2", "transparent", "textured", "textured3",
-                  "textured4", "procedural", "principled+terminator_offset"]
+                  "textured4", "procedural", "principled+terminator_offset",
+                  "principled+multiscatter", "closures_multi"]
 
 
 @pytest.mark.parametrize("materials", CLOSURE_SCENES)
@@ -417,7 +418,9 @@ def test_closure_setup_eval_sample_match_reference(ref, host_lib, materials):
     text = open(os.path.join(ROOT, "include", "cycles_abi.h")).read()
     ray_diffuse = int(re.search(r"#define CY_PATH_RAY_DIFFUSE[ \t]+(\w+)", text).group(1)
                       .rstrip("u"), 0)
-    desc = scenes.cornell(64, 48, spp=1, materials=materials.split("+")[0])
+    desc = scenes.cornell(64, 48, spp=1, materials=materials.split("+")[0],
+                          distribution="Multiscatter GGX" if materials.endswith("+multiscatter")
+                          else "GGX")
     if materials.endswith("+terminator_offset"):
         desc.terminator_offset = 0.6  # every object: shift_cos_in in bsdf_eval / bsdf_sample
     rs = ref.build_scene(desc)

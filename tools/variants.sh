@@ -17,7 +17,7 @@ else
   for name in "$@"; do
     lib=$PWD/$B/lib_$name.so
     [ "$name" = base ] && lib=$PWD/raytracingproject_b200/libb200cycles.so
-    B200_CYCLES_LIB=$lib python bench.py --steps 3 --warmup 2 ${BENCH_ARGS:---spp 64} --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
+    B200_CYCLES_LIB=$lib python bench.py --steps 3 --warmup 2 ${BENCH_ARGS:---spp 64} --no-cpu-baseline --no-e2e --configs none 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 r=d['roofline']
