@@ -91,9 +91,13 @@ def make_desc(workload, materials=None, width=0, height=0, spp=0):
     elif workload == "instanced":
         d = scenes.instanced(**kw)
     elif workload == "cube":
-        d = scenes.default_cube(material=materials or "principled", **kw)
+        # config 1: Blender's default material = a default Principled BSDF, whose
+        # distribution is Multiscatter GGX (render/nodes.cpp:2728-2730)
+        d = scenes.default_cube(material=materials or "principled",
+                                distribution="Multiscatter GGX", **kw)
     else:
-        d = scenes.cornell(materials=materials or "principled", **kw)
+        d = scenes.cornell(materials=materials or "principled",
+                           distribution="Multiscatter GGX", **kw)
     if spp:
         d.spp = spp
     return d

@@ -574,7 +574,7 @@ def box_mesh(lo, hi):
 
 # ---------------------------------------------------------------- config 1
 def default_cube(width=1920, height=1080, spp=64, material="principled", max_bounce=12,
-                 lights="point", cam_type="perspective", cam_extra=""):
+                 lights="point", cam_type="perspective", cam_extra="", distribution="GGX"):
     """BASELINE config 1 - Blender's startup scene, values extracted from
     release/datafiles/startup.blend.  `lights`: "point" (the
     startup scene), "falloff" (its lamp shader goes through a Light Falloff node), "spot"
@@ -591,7 +591,8 @@ def default_cube(width=1920, height=1080, spp=64, material="principled", max_bou
         nearclip=0.1, farclip=100.0, cam_type=cam_type, cam_extra=cam_extra)
     xml += _background((0.05087609, 0.05087609, 0.05087609))
     if material == "principled":
-        xml += _principled_shader("cube", (0.8, 0.8, 0.8), 0.0, 0.5, 0.5)
+        xml += _principled_shader("cube", (0.8, 0.8, 0.8), 0.0, 0.5, 0.5,
+                                  distribution=distribution)
     else:
         xml += _diffuse_shader("cube", (0.8, 0.8, 0.8))
     if lights == "falloff":
@@ -625,9 +626,10 @@ def default_cube(width=1920, height=1080, spp=64, material="principled", max_bou
     xml += _state("lamp", body)
     xml += "</cycles>\n"
     P, tris = box_mesh((-1, -1, -1), (1, 1, 1))
+    multi = "_multiscatter" if (material == "principled" and distribution != "GGX") else ""
     return SceneDesc(
-        "default_cube_" + material + ("" if lights == "point" else "_" + lights), xml, width,
-        height,
+        "default_cube_" + material + multi + ("" if lights == "point" else "_" + lights), xml,
+        width, height,
         meshes=[MeshDesc(P, tris, "cube")], objects=[(0, np.eye(4, dtype=np.float32)[:3])],
         spp=spp, notes="config 1")
 
@@ -801,8 +803,10 @@ def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
             objects.append((mi, m))
     elif light != "area":
         raise ValueError(light)
-    return SceneDesc("cornell_" + materials + ("" if light == "area" else "_" + light), xml, width,
-                     height, meshes=meshes, objects=objects, spp=spp, notes="config 3")
+    multi = "_multiscatter" if (materials in ("principled", "metal", "glass") and
+                                distribution != "GGX") else ""
+    return SceneDesc("cornell_" + materials + multi + ("" if light == "area" else "_" + light),
+                     xml, width, height, meshes=meshes, objects=objects, spp=spp, notes="config 3")
 
 
 # ---------------------------------------------------------------- config 4

@@ -19,6 +19,11 @@ def principled_cases():
     return {
         "cube_principled": scenes.default_cube(W, H, material="principled"),
         "cornell_principled": scenes.cornell(W, H, materials="principled"),
+        # the node's own default distribution: random-walk lobes (microfacet_multi.cuh)
+        "cube_principled_multiscatter": scenes.default_cube(
+            W, H, material="principled", distribution="Multiscatter GGX"),
+        "cornell_principled_multiscatter": scenes.cornell(
+            W, H, materials="principled", distribution="Multiscatter GGX"),
     }
 
 
@@ -71,6 +76,8 @@ def closure_cases():
     return {
         "cornell_closures": scenes.cornell(W, H, materials="closures"),
         "cornell_closures2": scenes.cornell(W, H, materials="closures2"),
+        # the Multiscatter GGX option of the Glossy and the Glass node
+        "cornell_closures_multi": scenes.cornell(W, H, materials="closures_multi"),
         # Transparent BSDF: straight-through bounces, alpha, terminate-after-transparent
         "cornell_transparent_opaque_shadow": scenes.cornell(
             W, H, materials="transparent_opaque_shadow"),

@@ -1,4 +1,5 @@
 """The north-star gates at CONFIGURATION size under `-m gpu` (tests/gates.py):
+config 1 (default cube, Principled with Multiscatter GGX) - the full 1080p / 64 spp frame;
 config 2 (1M-triangle terrain) - 2 M dumped primary rays + the shadow rays of the same
 pixels at one sample index, bit-exact hit ids, and the 1080p / 64 spp image; config 3
 (Cornell box, Principled metal + glass, 8 bounces) - the 1080p / 64 spp image; config 4
@@ -50,8 +51,18 @@ def test_config2_terrain_full_size(ref):
     _check(report)
 
 
+def test_config1_default_cube_full_size(ref):
+    """Blender's startup scene with its real default material (Principled BSDF,
+    Multiscatter GGX), 1080p / 64 spp = the whole of config 1."""
+    report = gates.run(scenes.default_cube(1920, 1080, distribution="Multiscatter GGX"), 64,
+                       samples=(0,), max_rays=1 << 21)
+    _keep("config1", report)
+    _check(report)
+
+
 def test_config3_cornell_full_size(ref):
-    report = gates.run(scenes.cornell(1920, 1080), 64, samples=(1,), max_rays=1 << 21)
+    report = gates.run(scenes.cornell(1920, 1080, distribution="Multiscatter GGX"), 64,
+                       samples=(1,), max_rays=1 << 21)
     _keep("config3", report)
     _check(report)
 
