@@ -60,6 +60,9 @@ def parse_args():
                     choices=["terrain", "instanced", "cube", "cornell"])
     ap.add_argument("--materials", default=None,
                     help="scenes.cornell(materials=...) / scenes.default_cube(material=...)")
+    ap.add_argument("--distribution", default="Multiscatter GGX",
+                    help="Principled distribution of the cube / cornell workloads "
+                         "(the node's default, or GGX)")
     ap.add_argument("--width", type=int, default=0, help="0 = the config's")
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--spp", type=int, default=0, help="samples per step (0 = the config's)")
@@ -79,7 +82,8 @@ def parse_args():
     return ap.parse_args()
 
 
-def make_desc(workload, materials=None, width=0, height=0, spp=0):
+def make_desc(workload, materials=None, width=0, height=0, spp=0,
+              distribution="Multiscatter GGX"):
     from raytracingproject_b200 import scenes
     kw = {}
     if width:
@@ -94,10 +98,10 @@ def make_desc(workload, materials=None, width=0, height=0, spp=0):
         # config 1: Blender's default material = a default Principled BSDF, whose
         # distribution is Multiscatter GGX (render/nodes.cpp:2728-2730)
         d = scenes.default_cube(material=materials or "principled",
-                                distribution="Multiscatter GGX", **kw)
+                                distribution=distribution, **kw)
     else:
         d = scenes.cornell(materials=materials or "principled",
-                           distribution="Multiscatter GGX", **kw)
+                           distribution=distribution, **kw)
     if spp:
         d.spp = spp
     return d
@@ -218,7 +222,8 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import cycles_ref
-    desc = make_desc(args.workload, args.materials, args.width, args.height, args.spp)
+    desc = make_desc(args.workload, args.materials, args.width, args.height, args.spp,
+                     args.distribution)
     rs = cycles_ref.build_scene(desc, kernel=cycles_ref.RefScene.AVX2)
     cpu_spp = args.cpu_spp or auto_cpu_spp(rs, desc)
     for _ in range(min(args.warmup, 1)):
@@ -255,7 +260,25 @@ def workload_name(desc):
 
 
 STAT_KEYS = ("primary_rays", "bounce_rays", "shadow_rays", "kernel_launches",
-             "closest_launches", "shadow_launches", "closest_ms", "shadow_ms", "device_ms")
+             "closest_launches", "shadow_launches", "closest_ms", "shadow_ms", "device_ms",
+             "shade_ms", "batches", "iterations", "host_syncs", "host_waits")
+
+
+def control_of(agg, steps):
+    """Wavefront control of the timed steps (this rank): where the device time went and how
+    often the host stopped the stream.  Phase times are CUDA-event sums; `other` is what is
+    left of the call (init_from_camera, film, iteration roll-over, idle gaps)."""
+    dev_ms = max(agg["device_ms"], 1e-9)
+    return {
+        "batches_per_step": agg["batches"] / steps, "iterations_per_step": agg["iterations"] / steps,
+        "launches_per_step": agg["kernel_launches"] / steps,
+        "stream_syncs_per_step": agg["host_syncs"] / steps,
+        "lagged_counter_reads_per_step": agg["host_waits"] / steps,
+        "share": {"intersect_closest": agg["closest_ms"] / dev_ms,
+                  "sort_and_shade": agg["shade_ms"] / dev_ms,
+                  "intersect_shadow": agg["shadow_ms"] / dev_ms,
+                  "other": 1.0 - (agg["closest_ms"] + agg["shade_ms"] + agg["shadow_ms"]) / dev_ms},
+    }
 
 
 class Arm:
@@ -423,7 +446,7 @@ def sub_record(name, desc, args, stream, rank, world, local, scaling="strong", s
             "rays": {"primary": prim, "bounce": bnc, "shadow": shd},
             "gpu_launches": int(launches), "allreduce_ms": reduce_ms if world > 1 else None,
             "bvh8": arm.bvh, "host_bvh_s": host_bvh_seconds(arm),
-            "path_pool_mb": pool_bytes / 1e6,
+            "path_pool_mb": pool_bytes / 1e6, "control": control_of(agg, steps),
         }
         if with_roofline and rank == 0:
             rec["roofline"] = roofline_of(arm, reducer.films[0], agg, name, spp)
@@ -457,7 +480,8 @@ def run_b200(args):
     torch.cuda.set_stream(stream)
 
     # ------------------------------------------------------------ headline
-    desc = make_desc(args.workload, args.materials, args.width, args.height, args.spp)
+    desc = make_desc(args.workload, args.materials, args.width, args.height, args.spp,
+                     args.distribution)
     spp = desc.spp
     w, h = desc.width, desc.height
     arm = Arm(desc, local, stream, args.opt)
@@ -578,6 +602,7 @@ def run_b200(args):
             "rays": {"primary": agg["primary_rays"], "bounce": agg["bounce_rays"],
                      "shadow": agg["shadow_rays"], "per_rank_per_run": rays_rank},
             "gpu_launches": launches_total,
+            "control": control_of(agg, args.steps),
             "allreduce_ms": reduce_ms if world > 1 else None,
             "clocks": clocks,
             "roofline": roofline,

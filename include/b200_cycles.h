@@ -79,6 +79,14 @@ typedef struct b200_stats {
   double shadow_ms;          /* CUDA-event time inside intersect_shadow launches */
   uint64_t svm_extended;     /* 1: shading ran the full SVM interpreter kernels (the bound
                               * program holds texture / attribute / colour nodes or sheen) */
+  /* wavefront control (b200_render): the bounce loop is queued ahead of the host, which
+   * reads each iteration's counters one iteration late - see DESIGN.md section 5 */
+  double shade_ms;           /* CUDA-event time of sort + shade_background + shade_surface */
+  uint64_t batches;          /* wavefront batches (pixels x samples that fit the path pool) */
+  uint64_t iterations;       /* bounce iterations that had paths to work on */
+  uint64_t host_syncs;       /* stream synchronisations: the device drains, then waits for
+                              * the host (one per call; one per step of a transparent shadow) */
+  uint64_t host_waits;       /* waits on an iteration's counters while later work is queued */
 } b200_stats;
 
 /* BVH8 build report (host builder). */
@@ -126,6 +134,17 @@ size_t b200_mem_used(b200_ctx *ctx);
  * B200_ERR_UNSUPPORTED). */
 int b200_bind_global(b200_ctx *ctx, const char *name, uint64_t dptr, const void *host,
                      size_t bytes);
+
+/* Image textures - CUDADevice::tex_alloc / tex_free (device_cuda_impl.cpp:1105-1304) for
+ * the device_texture the ImageManager hands over per image slot (render/image.cpp:
+ * 700-790).  The pixels are an ordinary allocation of this context (b200_alloc + b200_h2d);
+ * `texture_info` is the reference's TextureInfo record for the slot (util/util_texture.h:
+ * 93-107, SIZEOF_TEXTURE_INFO bytes) - its `data` member is replaced by `pixels`.  The
+ * kernels sample with the CPU device's arithmetic (kernel_cpu_image.h), not a texture
+ * unit.  2D images of every pixel format; 3D (volume) images are refused. */
+int b200_texture_set(b200_ctx *ctx, int slot, const void *texture_info, size_t bytes,
+                     uint64_t pixels);
+int b200_texture_clear(b200_ctx *ctx, int slot);
 
 /* Host-only scope check of a compiled SVM program (the `__svm_nodes` array built by
  * SVMShaderManager::device_update_shader, render/svm.cpp:70-133): the same walk

@@ -266,6 +266,8 @@ void b200_destroy(b200_ctx *ctx)
     cudaFree(ctx->d_debug);
   if (ctx->reduce_tmp)
     cudaFree(ctx->reduce_tmp);
+  if (ctx->d_texture_info)
+    cudaFree(ctx->d_texture_info);
   if (ctx->h_counters)
     cudaFreeHost(ctx->h_counters);
   cudaEventDestroy(ctx->ev0);
@@ -318,6 +320,16 @@ int b200_free(b200_ctx *ctx, uint64_t dptr)
       return fail(ctx, B200_ERR_INVALID, "b200_free: unknown pointer");
     ctx->mem_used -= it->second;
     ctx->allocs.erase(it);
+    /* an image slot whose pixels these were goes back to "no image" */
+    for (size_t t = 0; t + SIZEOF_TEXTURE_INFO <= ctx->texture_info.size();
+         t += SIZEOF_TEXTURE_INFO) {
+      uint64_t data = 0;
+      memcpy(&data, ctx->texture_info.data() + t + TI_DATA, 8);
+      if (data == dptr) {
+        memset(ctx->texture_info.data() + t, 0, SIZEOF_TEXTURE_INFO);
+        ctx->scene_dirty = true;
+      }
+    }
     /* drop any by-name binding of this buffer */
     for (auto g = ctx->globals.begin(); g != ctx->globals.end();) {
       if (g->second.dptr == dptr) {
@@ -502,6 +514,44 @@ int b200_bind_global(b200_ctx *ctx, const char *name, uint64_t dptr, const void 
   return B200_OK;
 }
 
+int b200_texture_set(b200_ctx *ctx, int slot, const void *texture_info, size_t bytes,
+                     uint64_t pixels)
+{
+  if (!ctx || slot < 0 || !texture_info)
+    return B200_ERR_INVALID;
+  if (bytes != SIZEOF_TEXTURE_INFO)
+    return fail(ctx, B200_ERR_INVALID, "TextureInfo size mismatch (ABI)");
+  uint32_t depth = 0, type = 0;
+  memcpy(&depth, (const uint8_t *)texture_info + TI_DEPTH, 4);
+  memcpy(&type, (const uint8_t *)texture_info + TI_DATA_TYPE, 4);
+  if (depth > 1)
+    return fail(ctx, B200_ERR_UNSUPPORTED,
+                "3D (volume) image textures are outside the hot-path scope");
+  if (type > CY_IMAGE_DATA_TYPE_USHORT)
+    return fail(ctx, B200_ERR_UNSUPPORTED, "unknown image data type");
+  std::lock_guard<std::mutex> lock(ctx->mutex);
+  const size_t need = ((size_t)slot + 1) * SIZEOF_TEXTURE_INFO;
+  if (ctx->texture_info.size() < need)
+    ctx->texture_info.resize(need, 0); /* unset slots: data == NULL reads as black */
+  uint8_t *rec = ctx->texture_info.data() + (size_t)slot * SIZEOF_TEXTURE_INFO;
+  memcpy(rec, texture_info, SIZEOF_TEXTURE_INFO);
+  memcpy(rec + TI_DATA, &pixels, 8);
+  ctx->scene_dirty = true;
+  return B200_OK;
+}
+
+int b200_texture_clear(b200_ctx *ctx, int slot)
+{
+  if (!ctx || slot < 0)
+    return B200_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(ctx->mutex);
+  if (((size_t)slot + 1) * SIZEOF_TEXTURE_INFO <= ctx->texture_info.size()) {
+    memset(ctx->texture_info.data() + (size_t)slot * SIZEOF_TEXTURE_INFO, 0, SIZEOF_TEXTURE_INFO);
+    ctx->scene_dirty = true;
+  }
+  return B200_OK;
+}
+
 int b200_validate_svm(const void *svm_nodes, size_t bytes, char *err, size_t errlen)
 {
   std::string why;
@@ -648,6 +698,17 @@ static int prepare_scene(b200_ctx *ctx)
   ds.attributes_float2 = (const float2 *)ptr("__attributes_float2");
   ds.attributes_float3 = (const float4 *)ptr("__attributes_float3");
   ds.attributes_uchar4 = (const uchar4 *)ptr("__attributes_uchar4");
+  if (ctx->d_texture_info) {
+    cudaFree(ctx->d_texture_info);
+    ctx->d_texture_info = nullptr;
+  }
+  if (!ctx->texture_info.empty()) {
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_texture_info, ctx->texture_info.size()));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->d_texture_info, ctx->texture_info.data(),
+                             ctx->texture_info.size(), cudaMemcpyHostToDevice));
+    ds.texture_info = (const uint8_t *)ctx->d_texture_info;
+    ds.num_textures = (uint32_t)(ctx->texture_info.size() / SIZEOF_TEXTURE_INFO);
+  }
   memcpy(ds.kdata, ctx->kernel_data.data(), SIZEOF_KERNEL_DATA);
   ctx->constant_block.assign((const uint8_t *)&ds, (const uint8_t *)&ds + sizeof(ds));
   {
@@ -686,6 +747,19 @@ static int launch_grid(const b200_ctx *ctx, int blocks_per_sm)
 static int refill_threshold(const b200_ctx *ctx)
 {
   return ctx->opt_refill_threshold > 0 ? (int)ctx->opt_refill_threshold : 24;
+}
+
+/* traverse.cuh: g_trace_overflow.  Checked once per wavefront batch / trace call. */
+static int check_trace_overflow(b200_ctx *ctx)
+{
+  unsigned int flag = 0;
+  CUDA_TRY(ctx, cudaMemcpyFromSymbol(&flag, g_trace_overflow, sizeof(flag)));
+  if (!flag)
+    return B200_OK;
+  const unsigned int zero = 0;
+  CUDA_TRY(ctx, cudaMemcpyToSymbol(g_trace_overflow, &zero, sizeof(zero)));
+  return fail(ctx, B200_ERR_UNSUPPORTED,
+              "BVH8 traversal stack overflow: hits of this call are not reliable");
 }
 
 #include "wavefront.cuh"
@@ -741,6 +815,9 @@ int b200_trace_batch(b200_ctx *ctx, uint64_t rays, uint64_t hits, uint64_t n, in
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, CNT_NUM * sizeof(unsigned int),
                                 cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  rc = check_trace_overflow(ctx);
+  if (rc)
+    return rc;
   float ms = 0.0f;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   memset(&ctx->stats, 0, sizeof(ctx->stats));
@@ -831,6 +908,8 @@ int b200_set_option(b200_ctx *ctx, const char *name, int64_t value)
     ctx->opt_refill_threshold = value;
   else if (strcmp(name, "trace_blocks_per_sm") == 0)
     ctx->opt_trace_blocks_per_sm = value;
+  else if (strcmp(name, "sync_iterations") == 0)
+    ctx->opt_sync_iterations = value;
   else
     return fail(ctx, B200_ERR_INVALID, std::string("unknown option ") + name);
   return B200_OK;

@@ -28,6 +28,8 @@ struct PathPool; /* wavefront state, defined in b200_cycles.cu */
 #define SVM_USES_WINDOW_COORDINATES 2u
 #define SVM_USES_EXTENDED_NODES 4u /* anything svm_eval_extended_node dispatches */
 #define SVM_USES_TANGENT 8u        /* NODE_GEOM_T: reads generated coordinates when present */
+#define SVM_USES_IMAGES 32u        /* an image / environment texture node: needs bound textures */
+#define SVM_USES_MULTISCATTER 16u  /* a Multiscatter GGX lobe: kernels with the random walks */
 
 struct b200_ctx {
   int ordinal = 0;
@@ -43,6 +45,10 @@ struct b200_ctx {
   size_t mem_used = 0;
 
   std::map<std::string, HostArray> globals; /* kernel_textures.h name -> binding */
+  /* image slots: the reference's TextureInfo records (data = device pointer), uploaded as
+   * one array when the scene is prepared */
+  std::vector<uint8_t> texture_info;
+  void *d_texture_info = nullptr;
   std::vector<uint8_t> kernel_data;
   bool scene_dirty = true; /* BVH8 / constant block must be (re)built */
   /* this context's constant block: the __constant__ DeviceScene is one per GPU, so a
@@ -69,8 +75,10 @@ struct b200_ctx {
   float *d_debug = nullptr; /* 16 bounces x 32 floats when "debug_slot" >= 0 */
   int64_t opt_refill_threshold = 0;
   int64_t opt_trace_blocks_per_sm = 0;
+  int64_t opt_sync_iterations = 0; /* A/B: stop the stream for the counters every bounce */
 
-  int shade_blocks_per_sm[2] = {0, 0}; /* k_shade_surface<lean / full>: grid size per SM */
+  /* k_shade_surface<lean / lean + multi-scatter / full>: grid size per SM */
+  int shade_blocks_per_sm[3] = {0, 0, 0};
 
   /* host cancel predicate (task.get_cancel()), polled between wavefront batches */
   b200_cancel_fn cancel_fn = nullptr;

@@ -130,9 +130,12 @@ CY_DEV void bsdf_terminator_terms_setup(ShaderDataG &sd, const LobeArena &arena)
 
 /* ----------------------------------------------------------- evaluation */
 
-/* EXT = false: the lobes the lean interpreter can create (it hands shaders with sheen,
- * multi-scatter GGX or bent normals to the full one, shade.cuh svm_eval_nodes) */
-template<bool EXT>
+/* EXT = false: the lobes the lean interpreter can create (it hands shaders with sheen or
+ * bent normals to the full one, shade.cuh svm_eval_nodes).  MS: the kernel carries the
+ * multi-scatter lobes (two out-of-line calls); its own switch, because even unreachable
+ * code in the lean kernels costs the common shaders time (measured: +11 % on the GGX
+ * Cornell box, +4 % on the terrain when every lean kernel carried the calls). */
+template<bool EXT, bool MS = EXT>
 CY_DEV f3 bsdf_eval(ShaderDataG &sd, const Lobe &l, f3 omega_in, float *pdf)
 {
   const bool same_side = dot(sd.Ng, omega_in) >= 0.0f;
@@ -197,7 +200,7 @@ CY_DEV f3 bsdf_eval(ShaderDataG &sd, const Lobe &l, f3 omega_in, float *pdf)
     case CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_FRESNEL_ID:
     case CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_GLASS_ID:
     case CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_GLASS_FRESNEL_ID:
-      if (EXT)
+      if (MS)
         value = multi_ggx_eval(l, sd.I, omega_in, same_side, pdf, &sd.lcg_state);
       break;
     default: /* sharp lobes, transparent, placeholders: nothing to evaluate */
@@ -222,7 +225,7 @@ CY_DEV bool keep_side(f3 Ng, f3 omega_in, bool reflect)
   return reflect ? (c > 0.0f) : (c < 0.0f);
 }
 
-template<bool EXT>
+template<bool EXT, bool MS = EXT>
 CY_DEV int bsdf_sample_lobe(ShaderDataG &sd, const Lobe &l, float randu, float randv, f3 *value,
                             f3 *omega_in, float *pdf)
 {
@@ -315,7 +318,7 @@ CY_DEV int bsdf_sample_lobe(ShaderDataG &sd, const Lobe &l, float randu, float r
     case CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_FRESNEL_ID:
     case CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_GLASS_ID:
     case CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_GLASS_FRESNEL_ID:
-      if (EXT)
+      if (MS)
         return multi_ggx_sample(l, sd.I, randu, randv, value, omega_in, pdf, &sd.lcg_state);
       *pdf = 0.0f;
       return CY_LABEL_NONE;
@@ -326,11 +329,11 @@ CY_DEV int bsdf_sample_lobe(ShaderDataG &sd, const Lobe &l, float randu, float r
 }
 
 /* the lobe's own sampler, then the terminator factors on the reflection side */
-template<bool EXT>
+template<bool EXT, bool MS = EXT>
 CY_DEV int bsdf_sample(ShaderDataG &sd, const Lobe &l, float randu, float randv, f3 *value,
                        f3 *omega_in, float *pdf)
 {
-  const int label = bsdf_sample_lobe<EXT>(sd, l, randu, randv, value, omega_in, pdf);
+  const int label = bsdf_sample_lobe<EXT, MS>(sd, l, randu, randv, value, omega_in, pdf);
   if (EXT && sd.terminator_terms && !(label & CY_LABEL_TRANSMIT)) {
     if (sd.terminator_freq > 1.0f)
       *value *= shift_cos_in(dot(*omega_in, l.N), sd.terminator_freq);

@@ -40,6 +40,9 @@ struct DeviceScene {
   const float2 *attributes_float2;
   const float4 *attributes_float3;
   const uchar4 *attributes_uchar4;
+  const uint8_t *texture_info; /* TextureInfo[], SIZEOF_TEXTURE_INFO each, data = device ptr */
+  uint32_t num_textures;
+  uint32_t pad1;
 
   /* KernelData, byte-for-byte */
   alignas(16) uint8_t kdata[SIZEOF_KERNEL_DATA];

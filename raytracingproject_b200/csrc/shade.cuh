@@ -603,6 +603,7 @@ CY_DEV void shader_setup_from_ray(
 #include "svm_closure.cuh"
 #include "svm_nodes.cuh"
 #include "svm_tex.cuh"
+#include "svm_image.cuh"
 
 /* The nodes beyond the closure and basic value set, behind ONE out-of-line call: with
  * their cases in the interpreter's own switch the common shaders (Principled, diffuse,
@@ -695,6 +696,15 @@ __device__ __noinline__ int svm_eval_extended_node(ShaderDataG &sd, float *stack
     case CY_NODE_TEX_BRICK:
       svm_node_tex_brick(stack, node, &offset);
       break;
+    case CY_NODE_TEX_IMAGE:
+      offset = svm_node_tex_image(stack, node, offset);
+      break;
+    case CY_NODE_TEX_IMAGE_BOX:
+      svm_node_tex_image_box(sd, stack, node);
+      break;
+    case CY_NODE_TEX_ENVIRONMENT:
+      svm_node_tex_environment(stack, node);
+      break;
     default:
       return -1;
   }
@@ -712,7 +722,7 @@ __device__ __noinline__ int svm_eval_extended_node(ShaderDataG &sd, float *stack
  * calls.  Measured A/B on one box with the Cornell workload (Principled + diffuse
  * shaders only): one interpreter carrying everything costs 4.5 % of the frame, the
  * split costs nothing. */
-template<bool FULL>
+template<bool FULL, bool MS = FULL>
 __device__ __noinline__ bool svm_eval_nodes_t(ShaderDataG &sd, LobeArena &arena,
                                               PathDepths depths, uint32_t path_flag,
                                               int max_closures)
@@ -733,7 +743,7 @@ __device__ __noinline__ bool svm_eval_nodes_t(ShaderDataG &sd, LobeArena &arena,
         offset = (int)node.y; /* SHADER_TYPE_SURFACE */
         break;
       case CY_NODE_CLOSURE_BSDF:
-        if (!svm_node_closure_bsdf<FULL>(sd, arena, stack, node, path_flag, &offset))
+        if (!svm_node_closure_bsdf<FULL, MS>(sd, arena, stack, node, path_flag, &offset))
           return false;
         break;
       case CY_NODE_CLOSURE_EMISSION:
@@ -896,14 +906,14 @@ __device__ unsigned int g_svm_scope_miss;
  * instance: programs with extended nodes (or a Principled BSDF whose sheen is not a
  * constant zero, or a multi-scatter lobe) run the full interpreter, all others the lean
  * one. */
-template<bool EXT>
+template<bool EXT, bool MS = EXT>
 CY_DEV void svm_eval_nodes(ShaderDataG &sd, LobeArena &arena, PathDepths depths,
                            uint32_t path_flag, int max_closures)
 {
   if (EXT) {
-    svm_eval_nodes_t<true>(sd, arena, depths, path_flag, max_closures);
+    svm_eval_nodes_t<true, true>(sd, arena, depths, path_flag, max_closures);
   }
-  else if (!svm_eval_nodes_t<false>(sd, arena, depths, path_flag, max_closures)) {
+  else if (!svm_eval_nodes_t<false, MS>(sd, arena, depths, path_flag, max_closures)) {
     g_svm_scope_miss = 1u;
     arena_reset(arena, 0);
     sd.flag &= ~(CY_SD_BSDF | CY_SD_EMISSION);
@@ -913,7 +923,7 @@ CY_DEV void svm_eval_nodes(ShaderDataG &sd, LobeArena &arena, PathDepths depths,
 /* kernel_shader.h:1057-1112: the surface shader of a hit.  `rng_seed` = rng_hash +
  * rng_offset + sample * 0xb4bc3953 of the path (lcg_state_init): the seed of the random
  * walks of multi-scatter lobes, drawn from only when the shader made one. */
-template<bool EXT>
+template<bool EXT, bool MS = EXT>
 CY_DEV void shader_eval_surface(ShaderDataG &sd, LobeArena &arena, PathDepths depths,
                                 uint32_t path_flag, uint32_t rng_seed)
 {
@@ -922,8 +932,8 @@ CY_DEV void shader_eval_surface(ShaderDataG &sd, LobeArena &arena, PathDepths de
     max_closures = 0;
   else
     max_closures = min(kd_int(KD_INT_MAX_CLOSURES), MAX_CLOSURES_GPU);
-  svm_eval_nodes<EXT>(sd, arena, depths, path_flag, max_closures);
-  if (EXT && (sd.flag & CY_SD_BSDF_NEEDS_LCG))
+  svm_eval_nodes<EXT, MS>(sd, arena, depths, path_flag, max_closures);
+  if (MS && (sd.flag & CY_SD_BSDF_NEEDS_LCG))
     sd.lcg_state = lcg_seed(rng_seed);
 }
 
@@ -986,7 +996,7 @@ CY_DEV float power_heuristic(float a, float b)
 /* Sum of all lobes but `skip` for direction omega_in (value weighted by the lobe's
  * colour, pdf by its sample weight), continuing the running sums of a sampled lobe
  * (_shader_bsdf_multi_eval, kernel_shader.h:556-582, no light passes) */
-template<bool EXT>
+template<bool EXT, bool MS = EXT>
 CY_DEV void shader_bsdf_multi_eval(ShaderDataG &sd, const LobeArena &arena, f3 omega_in,
                                    float *pdf, int skip, f3 *result_eval, float sum_pdf,
                                    float sum_sample_weight)
@@ -997,7 +1007,7 @@ CY_DEV void shader_bsdf_multi_eval(ShaderDataG &sd, const LobeArena &arena, f3 o
     if (i != skip && lobe_is_bsdf(kind)) {
       const Lobe l = lobe_fetch(arena, at);
       float bsdf_pdf = 0.0f;
-      const f3 eval = bsdf_eval<EXT>(sd, l, omega_in, &bsdf_pdf);
+      const f3 eval = bsdf_eval<EXT, MS>(sd, l, omega_in, &bsdf_pdf);
       if (bsdf_pdf != 0.0f) {
         *result_eval += eval * l.weight;
         sum_pdf += bsdf_pdf * l.sample_weight;
@@ -1011,13 +1021,13 @@ CY_DEV void shader_bsdf_multi_eval(ShaderDataG &sd, const LobeArena &arena, f3 o
 
 /* BSDF towards a light sample, MIS-weighted against BSDF sampling
  * (shader_bsdf_eval, kernel_shader.h:612-636, non-branched) */
-template<bool EXT>
+template<bool EXT, bool MS = EXT>
 CY_DEV f3 shader_bsdf_eval(ShaderDataG &sd, const LobeArena &arena, f3 omega_in, float light_pdf,
                            bool use_mis)
 {
   f3 eval = zero3();
   float pdf;
-  shader_bsdf_multi_eval<EXT>(sd, arena, omega_in, &pdf, -1, &eval, 0.0f, 0.0f);
+  shader_bsdf_multi_eval<EXT, MS>(sd, arena, omega_in, &pdf, -1, &eval, 0.0f, 0.0f);
   if (use_mis)
     eval *= power_heuristic(light_pdf, pdf);
   return eval;
@@ -1026,7 +1036,7 @@ CY_DEV f3 shader_bsdf_eval(ShaderDataG &sd, const LobeArena &arena, f3 omega_in,
 /* Picks a lobe in proportion to its sample weight, samples it, then adds the other lobes
  * for the sampled direction (shader_bsdf_pick + shader_bsdf_sample,
  * kernel_shader.h:638-680, 739-775) */
-template<bool EXT>
+template<bool EXT, bool MS = EXT>
 CY_DEV int shader_bsdf_sample(ShaderDataG &sd, const LobeArena &arena, float randu, float randv,
                               f3 *bsdf_eval_out, f3 *omega_in, float *pdf)
 {
@@ -1065,12 +1075,12 @@ CY_DEV int shader_bsdf_sample(ShaderDataG &sd, const LobeArena &arena, float ran
     return CY_LABEL_NONE;
   const Lobe l = lobe_fetch(arena, sampled_at);
   f3 eval = zero3();
-  const int label = bsdf_sample<EXT>(sd, l, randu, randv, &eval, omega_in, pdf);
+  const int label = bsdf_sample<EXT, MS>(sd, l, randu, randv, &eval, omega_in, pdf);
   if (*pdf != 0.0f) {
     *bsdf_eval_out = eval * l.weight;
     if (arena.n > 1) {
       const float sweight = l.sample_weight;
-      shader_bsdf_multi_eval<EXT>(sd, arena, *omega_in, pdf, sampled, bsdf_eval_out,
+      shader_bsdf_multi_eval<EXT, MS>(sd, arena, *omega_in, pdf, sampled, bsdf_eval_out,
                                   *pdf * sweight, sweight);
     }
   }

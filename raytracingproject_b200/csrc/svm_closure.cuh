@@ -192,7 +192,7 @@ CY_DEV void principled_sheen_layer(ShaderDataG &sd, LobeArena &arena,
   }
 }
 
-template<bool FULL>
+template<bool MS>
 CY_DEV bool principled_specular_layer(ShaderDataG &sd, LobeArena &arena,
                                       const PrincipledInputs &in, float specular_weight)
 {
@@ -221,14 +221,14 @@ CY_DEV bool principled_specular_layer(ShaderDataG &sd, LobeArena &arena,
     commit_ggx_fresnel(sd, arena, l);
   }
   else {
-    if (!FULL)
-      return false; /* the random walk lives in the full kernels */
+    if (!MS)
+      return false; /* this kernel does not carry the random walk */
     commit_multi_ggx(sd, arena, l, true);
   }
   return true;
 }
 
-template<bool FULL>
+template<bool MS>
 CY_DEV bool principled_transmission_layers(ShaderDataG &sd, LobeArena &arena,
                                            const PrincipledInputs &in, float final_transmission)
 {
@@ -260,7 +260,9 @@ CY_DEV bool principled_transmission_layers(ShaderDataG &sd, LobeArena &arena,
     }
     return true;
   }
-  if (!FULL)
+  if (arena.left == 0)
+    return true;
+  if (!MS)
     return false;
   if (lobe_open(arena, l, glass_weight, true)) {
     l.N = in.N;
@@ -294,8 +296,9 @@ CY_DEV void principled_clearcoat_layer(ShaderDataG &sd, LobeArena &arena,
 /* ------------------------------------------------------------ the node */
 
 /* FULL = false is the interpreter for the common shaders (see svm_eval_nodes); false is
- * returned when the shader needs the full one (a bent normal, a multi-scatter lobe). */
-template<bool FULL>
+ * returned when the shader needs more than this kernel carries (a bent normal -> the full
+ * interpreter; a multi-scatter lobe -> a kernel with MS). */
+template<bool FULL, bool MS = FULL>
 CY_DEV bool svm_node_closure_bsdf(ShaderDataG &sd, LobeArena &arena, float *stack, uint4 node,
                                   uint32_t path_flag, int *offset)
 {
@@ -394,9 +397,9 @@ CY_DEV bool svm_node_closure_bsdf(ShaderDataG &sd, LobeArena &arena, float *stac
         if (FULL)
           principled_sheen_layer(sd, arena, in, diffuse_weight);
       }
-      if (!principled_specular_layer<FULL>(sd, arena, in, specular_weight))
+      if (!principled_specular_layer<MS>(sd, arena, in, specular_weight))
         return false;
-      if (!principled_transmission_layers<FULL>(sd, arena, in, final_transmission))
+      if (!principled_transmission_layers<MS>(sd, arena, in, final_transmission))
         return false;
       principled_clearcoat_layer(sd, arena, in);
       break;
@@ -518,7 +521,9 @@ CY_DEV bool svm_node_closure_bsdf(ShaderDataG &sd, LobeArena &arena, float *stac
       /* Glass BSDF node, Multiscatter GGX: one lobe for both sides of the interface */
       if (!may_reflect && !may_refract)
         break;
-      if (!FULL)
+      if (arena.left == 0)
+        break;
+      if (!MS)
         return false;
       if (lobe_open(arena, l, weight, true)) {
         l.N = N;
@@ -537,8 +542,11 @@ CY_DEV bool svm_node_closure_bsdf(ShaderDataG &sd, LobeArena &arena, float *stac
       if (!may_reflect)
         break;
       const bool multi = (type == CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_ID);
-      if (multi && !FULL)
+      if (multi && !MS) {
+        if (arena.left == 0)
+          break;
         return false;
+      }
       /* the multi-scatter variant takes its MicrofacetExtra slot AFTER the closure's own:
        * same budget arithmetic as asking for both up front */
       if (!lobe_open(arena, l, weight, multi))

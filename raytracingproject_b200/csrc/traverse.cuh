@@ -42,6 +42,11 @@ struct TraceHit {
   int object; /* -1 = OBJECT_NONE */
 };
 
+/* Set when a traversal had to drop a stack entry (the stack is sized for the depth the
+ * BVH8 builder accepts, so this cannot happen for a tree it produced; if it ever does the
+ * host refuses the result instead of returning hits that may be wrong). */
+__device__ unsigned int g_trace_overflow;
+
 struct TraceCounters {
   uint32_t nodes, tris, instances;
 };
@@ -273,6 +278,8 @@ template<bool ANY_HIT, bool COUNT> struct Traversal {
   {
     if (sp < BVH8_STACK_SIZE)
       stack[sp++] = e;
+    else
+      g_trace_overflow = 1u;
   }
 
   __device__ __forceinline__ void node_phase(uint2 *stack, TraceCounters &cnt)

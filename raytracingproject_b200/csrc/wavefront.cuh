@@ -32,6 +32,14 @@
  * global atomics */
 #define WF_SMALL_KEYS 64
 
+#define WF_RING 4
+#define WF_RING_BYTES 64
+#define WF_RING_EVENTS 5 /* start, after closest, after shading, after shadow, counters home */
+#define WF_BATCH_SLOTS 1024
+#define WF_BATCH_STAT_BYTES 128
+#define WF_FLAG_SCOPE_MISS 1u
+#define WF_FLAG_TRACE_OVERFLOW 2u
+
 struct WFCounters {
   unsigned int n_active; /* paths in q_active (input of intersect_closest) */
   unsigned int n_next;   /* paths appended to q_next by shade_surface */
@@ -39,6 +47,9 @@ struct WFCounters {
   unsigned int work_closest, work_shadow;
   /* transparent shadows: sizes of the two stepping queues, their traversal cursor */
   unsigned int n_ts[2], work_ts;
+  /* device flags folded in by k_iteration_end so that they travel with the 64-byte
+   * counter read-back: bit 0 = g_svm_scope_miss, bit 1 = g_trace_overflow */
+  unsigned int flags, pad_flags;
   unsigned long long primary_rays, bounce_rays, shadow_rays;
   unsigned long long nodes, tris, instances;          /* intersect_closest */
   unsigned long long sh_nodes, sh_tris, sh_instances; /* intersect_shadow */
@@ -93,6 +104,14 @@ struct PathPool {
   bool has_ao = false; /* shadow queue sized for two entries per path (light + AO ray) */
   WFCounters *h_counters = nullptr; /* pinned */
   uint32_t *sobol_tab = nullptr;    /* SOBOL_TABLE_MAX entries */
+  /* The bounce loop runs ahead of the host: iteration `it` copies the head of the
+   * counters into ring slot it % WF_RING and records the slot's events; the host reads
+   * slot it - 1 while iteration `it` is already queued, so the GPU never waits for it. */
+  unsigned char *h_ring = nullptr;  /* pinned, WF_RING * WF_RING_BYTES */
+  cudaEvent_t ring_ev[WF_RING][WF_RING_EVENTS] = {};
+  /* ray / traversal statistics of each batch (the first WF_BATCH_STAT_BYTES of its
+   * counters), summed on the host when the call ends */
+  unsigned char *h_batch = nullptr; /* pinned, WF_BATCH_SLOTS * WF_BATCH_STAT_BYTES */
 };
 
 struct BatchParams {
@@ -623,7 +642,7 @@ __global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(Pa
  * that follows does not carry them in registers; slots in the next-bounce and shadow
  * queues come from one block-wide reservation at the end of the round, after which the
  * staged record is copied out to its slot. */
-template<bool EXT>
+template<bool EXT, bool MS = EXT>
 __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_MIN_BLOCKS)
     k_shade_surface(PathSoA p, int num_keys)
 {
@@ -670,7 +689,7 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
       if (alive) {
         shader_setup_from_ray(sd, __float_as_int(hit.w), hit_object, hit.x, hit.y, hit.z, mk3(r0),
                               mk3(r1));
-        shader_eval_surface<EXT>(sd, arena, path_depths(st), st.flag,
+        shader_eval_surface<EXT, MS>(sd, arena, path_depths(st), st.flag,
                                  st.rng_hash + (uint32_t)st.rng_offset +
                                      (uint32_t)st.sample * 0xb4bc3953u);
         shader_prepare_lobes<EXT>(sd, arena, st.bounce + st.transparent_bounce == 0);
@@ -783,7 +802,7 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
               }
             }
             if (!is_zero(light_eval)) {
-              f3 eval = shader_bsdf_eval<EXT>(sd, arena, ls.D, ls.pdf,
+              f3 eval = shader_bsdf_eval<EXT, MS>(sd, arena, ls.D, ls.pdf,
                                               (ls.shader & CY_SHADER_USE_MIS) != 0);
               eval *= light_eval / ls.pdf;
               bool ok = !is_zero(eval);
@@ -843,7 +862,7 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
           path_state_rng_2D<EXT>(st, CY_PRNG_BSDF_U, &bsdf_u, &bsdf_v);
           f3 bsdf_eval = zero3(), omega_in = zero3();
           float bsdf_pdf;
-          const int label = shader_bsdf_sample<EXT>(sd, arena, bsdf_u, bsdf_v, &bsdf_eval,
+          const int label = shader_bsdf_sample<EXT, MS>(sd, arena, bsdf_u, bsdf_v, &bsdf_eval,
                                                     &omega_in, &bsdf_pdf);
           if (!(bsdf_pdf == 0.0f || is_zero(bsdf_eval))) {
             /* LABEL_TRANSMIT_TRANSPARENT (closure/bsdf.h:466-475) needs transparent glass,
@@ -1138,6 +1157,8 @@ __global__ void k_iteration_end(PathSoA p, int num_keys, int iteration)
     c->work_shadow = 0;
     c->n_ts[0] = c->n_ts[1] = 0;
     c->work_ts = 0;
+    c->flags = (g_svm_scope_miss ? WF_FLAG_SCOPE_MISS : 0u) |
+               (g_trace_overflow ? WF_FLAG_TRACE_OVERFLOW : 0u);
   }
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= num_keys; k += gridDim.x * blockDim.x)
     c->hist[k] = 0;
@@ -1270,6 +1291,14 @@ static void free_pool(b200_ctx *ctx)
     cudaFree(ctx->pool->block);
   if (ctx->pool->h_counters)
     cudaFreeHost(ctx->pool->h_counters);
+  if (ctx->pool->h_ring)
+    cudaFreeHost(ctx->pool->h_ring);
+  if (ctx->pool->h_batch)
+    cudaFreeHost(ctx->pool->h_batch);
+  for (int r = 0; r < WF_RING; r++)
+    for (int e = 0; e < WF_RING_EVENTS; e++)
+      if (ctx->pool->ring_ev[r][e])
+        cudaEventDestroy(ctx->pool->ring_ev[r][e]);
   if (ctx->pool->sobol_tab)
     cudaFree(ctx->pool->sobol_tab);
   delete ctx->pool;
@@ -1347,15 +1376,18 @@ static int ensure_pool(b200_ctx *ctx, size_t capacity, bool transparent_shadows,
   s.ts_idx[1] = transparent_shadows ? (int *)(b + o_tsI1) : nullptr;
   s.ts_thr = transparent_shadows ? (float4 *)(b + o_tsT) : nullptr;
   s.counters = (WFCounters *)(b + o_cnt);
-  if (cudaMallocHost(&pool->h_counters, sizeof(WFCounters)) != cudaSuccess ||
-      cudaMalloc(&pool->sobol_tab, SOBOL_TABLE_MAX * sizeof(uint32_t)) != cudaSuccess) {
-    cudaFree(pool->block);
-    if (pool->h_counters)
-      cudaFreeHost(pool->h_counters);
-    delete pool;
+  bool ok = cudaMallocHost(&pool->h_counters, sizeof(WFCounters)) == cudaSuccess &&
+            cudaMallocHost(&pool->h_ring, WF_RING * WF_RING_BYTES) == cudaSuccess &&
+            cudaMallocHost(&pool->h_batch, WF_BATCH_SLOTS * WF_BATCH_STAT_BYTES) == cudaSuccess &&
+            cudaMalloc(&pool->sobol_tab, SOBOL_TABLE_MAX * sizeof(uint32_t)) == cudaSuccess;
+  for (int r = 0; ok && r < WF_RING; r++)
+    for (int e = 0; ok && e < WF_RING_EVENTS; e++)
+      ok = cudaEventCreate(&pool->ring_ev[r][e]) == cudaSuccess;
+  ctx->pool = pool;
+  if (!ok) {
+    free_pool(ctx);
     return fail(ctx, B200_ERR_CUDA, "pinned counter / Sobol table allocation failed");
   }
-  ctx->pool = pool;
   return B200_OK;
 }
 
@@ -1500,6 +1532,18 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
         *features |= SVM_USES_EXTENDED_NODES;
         i += 2;
         break;
+      case CY_NODE_TEX_IMAGE: {
+        /* followed by its UDIM tile nodes (two tiles each) when it has any */
+        const int tiles = (int)nodes[4 * i + 1];
+        *features |= SVM_USES_EXTENDED_NODES | SVM_USES_IMAGES;
+        i += 1 + (size_t)(tiles > 0 ? tiles : 0);
+        break;
+      }
+      case CY_NODE_TEX_IMAGE_BOX:
+      case CY_NODE_TEX_ENVIRONMENT:
+        *features |= SVM_USES_EXTENDED_NODES | SVM_USES_IMAGES;
+        i += 1;
+        break;
       case CY_NODE_MIN_MAX:
       case CY_NODE_TEX_NOISE:
       case CY_NODE_TEX_WAVE:
@@ -1584,13 +1628,17 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
           /* Multiscatter GGX (the node's default): the random-walk lobes live in the full
            * kernels */
           if (distribution != CY_CLOSURE_BSDF_MICROFACET_GGX_GLASS_ID)
-            *features |= SVM_USES_EXTENDED_NODES;
+            *features |= SVM_USES_MULTISCATTER;
           i += 6;
         }
         else if (type == CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_ID ||
                  type == CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_GLASS_ID) {
-          /* Glossy / Anisotropic / Glass BSDF nodes with Multiscatter GGX */
-          *features |= SVM_USES_EXTENDED_NODES;
+          /* Glossy / Anisotropic / Glass BSDF nodes with Multiscatter GGX; a tangent
+           * input (the Anisotropic node) runs in the full interpreter */
+          *features |= SVM_USES_MULTISCATTER;
+          if (type == CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_ID && i + 1 < n_nodes &&
+              nodes[4 * (i + 1) + 1] != (uint32_t)CY_SVM_STACK_INVALID)
+            *features |= SVM_USES_EXTENDED_NODES;
           i += 2;
         }
         else if (type == CY_CLOSURE_BSDF_REFLECTION_ID ||
@@ -1701,22 +1749,20 @@ static int shade_kernel_setup(b200_ctx *ctx)
   if (ctx->shade_blocks_per_sm[0] > 0)
     return B200_OK;
   DeviceGuard guard(ctx->ordinal);
-  CUDA_TRY(ctx, cudaFuncSetAttribute(k_shade_surface<false>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)SHADE_SMEM_BYTES));
-  CUDA_TRY(ctx, cudaFuncSetAttribute(k_shade_surface<true>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)SHADE_SMEM_BYTES));
-  int lean = 0, full = 0;
-  CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lean, k_shade_surface<false>,
-                                                              WF_BLOCK, SHADE_SMEM_BYTES));
-  CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&full, k_shade_surface<true>,
-                                                              WF_BLOCK, SHADE_SMEM_BYTES));
-  if (lean < 1 || full < 1)
-    return fail(ctx, B200_ERR_CUDA, "surface-shading kernel does not fit on an SM");
-  /* a few waves of blocks per SM even the tail out; more only adds reservation atomics */
-  ctx->shade_blocks_per_sm[0] = lean * 2;
-  ctx->shade_blocks_per_sm[1] = full * 2;
+  const void *kernels[3] = {(const void *)k_shade_surface<false, false>,
+                            (const void *)k_shade_surface<false, true>,
+                            (const void *)k_shade_surface<true, true>};
+  for (int k = 0; k < 3; k++) {
+    CUDA_TRY(ctx, cudaFuncSetAttribute(kernels[k], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)SHADE_SMEM_BYTES));
+    int blocks = 0;
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernels[k], WF_BLOCK,
+                                                                SHADE_SMEM_BYTES));
+    if (blocks < 1)
+      return fail(ctx, B200_ERR_CUDA, "surface-shading kernel does not fit on an SM");
+    /* a few waves of blocks per SM even the tail out */
+    ctx->shade_blocks_per_sm[k] = blocks * 2;
+  }
   return B200_OK;
 }
 
@@ -1764,6 +1810,8 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
                        kd_host<int>(ctx, KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_PMJ ||
                        kd_host<int>(ctx, KD_INT_USE_AMBIENT_OCCLUSION) != 0;
   const bool use_ao = kd_host<int>(ctx, KD_INT_USE_AMBIENT_OCCLUSION) != 0;
+  /* lean kernels with the multi-scatter lobes: the Principled default distribution */
+  const bool multiscatter = (ctx->svm_features & SVM_USES_MULTISCATTER) != 0;
   rc = ensure_pool(ctx, std::max<size_t>(capacity, (size_t)tile->w), transparent_shadows, use_ao);
   if (rc)
     return rc;
@@ -1781,12 +1829,135 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
   rc = shade_kernel_setup(ctx);
   if (rc)
     return rc;
-  const int grid_shade = ctx->num_sms * ctx->shade_blocks_per_sm[svm_ext ? 1 : 0];
 
   b200_stats stats;
   memset(&stats, 0, sizeof(stats));
-  float closest_ms = 0.0f, shadow_ms = 0.0f;
+  float closest_ms = 0.0f, shade_ms = 0.0f, shadow_ms = 0.0f;
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev5, st));
+
+  /* How far the host reads behind the device.  The bounce loop ends when a counter says
+   * the queue is empty; instead of stopping the stream for that read every iteration, the
+   * host queues iteration `it`, and only then looks at the counters iteration it - 1
+   * copied into its ring slot.  The price is one iteration over empty queues per batch
+   * (8 launches that find nothing to do); the device never idles.  Transparent shadows
+   * size their stepping loop from a counter inside the iteration and stay in step. */
+  const int lag = (transparent_shadows || ctx->opt_sync_iterations) ? 0 : 1;
+  int batch_slot = 0;
+  auto sum_batch_stats = [&]() -> int {
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    stats.host_syncs += 1;
+    for (int k = 0; k < batch_slot; k++) {
+      const WFCounters *h = (const WFCounters *)(pool->h_batch + (size_t)k * WF_BATCH_STAT_BYTES);
+      stats.primary_rays += h->primary_rays;
+      stats.bounce_rays += h->bounce_rays;
+      stats.shadow_rays += h->shadow_rays;
+      stats.closest_nodes += h->nodes;
+      stats.closest_tris += h->tris;
+      stats.closest_instances += h->instances;
+      stats.shadow_nodes += h->sh_nodes;
+      stats.shadow_tris += h->sh_tris;
+      stats.shadow_instances += h->sh_instances;
+    }
+    batch_slot = 0;
+    return B200_OK;
+  };
+
+  /* one bounce of the whole batch: 8 launches, the head of the counters into the
+   * iteration's ring slot, events around the three phases */
+  auto enqueue_iteration = [&](const PathSoA &soa, int it) -> int {
+    cudaEvent_t *ev = pool->ring_ev[it % WF_RING];
+    const int grid_shade = ctx->num_sms *
+                           ctx->shade_blocks_per_sm[svm_ext ? 2 : (multiscatter ? 1 : 0)];
+    CUDA_TRY(ctx, cudaEventRecord(ev[0], st));
+    if (count)
+      k_intersect_closest<true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
+    else
+      k_intersect_closest<false><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
+    CUDA_TRY(ctx, cudaEventRecord(ev[1], st));
+    k_sort_count<<<grid_wide, WF_BLOCK, 0, st>>>(soa);
+    k_sort_scan<<<1, 256, 0, st>>>(soa, num_keys);
+    k_sort_scatter<<<grid_wide, WF_BLOCK, 0, st>>>(soa);
+    if (svm_ext) {
+      k_shade_background<true><<<grid_wide, WF_BLOCK, 0, st>>>(soa);
+      k_shade_surface<true, true><<<grid_shade, WF_BLOCK, SHADE_SMEM_BYTES, st>>>(soa, num_keys);
+    }
+    else {
+      k_shade_background<false><<<grid_wide, WF_BLOCK, 0, st>>>(soa);
+      if (multiscatter)
+        k_shade_surface<false, true><<<grid_shade, WF_BLOCK, SHADE_SMEM_BYTES, st>>>(soa,
+                                                                                     num_keys);
+      else
+        k_shade_surface<false, false><<<grid_shade, WF_BLOCK, SHADE_SMEM_BYTES, st>>>(soa,
+                                                                                      num_keys);
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ev[2], st));
+    if (use_ao) /* never with transparent shadows (check_scope) */
+      k_intersect_shadow<false, false, true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
+    else if (transparent_shadows)
+      k_intersect_shadow<false, true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
+    else if (count)
+      k_intersect_shadow<true, false><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
+    else
+      k_intersect_shadow<false, false><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
+    CUDA_TRY(ctx, cudaEventRecord(ev[3], st));
+    if (transparent_shadows) {
+      /* shadow rays stopped by a transparent surface walk on, one surface per step */
+      CUDA_TRY(ctx, cudaMemcpyAsync(pool->h_counters, soa.counters, 64, cudaMemcpyDeviceToHost,
+                                    st));
+      CUDA_TRY(ctx, cudaStreamSynchronize(st));
+      stats.host_syncs += 1;
+      int cur = 0;
+      while (pool->h_counters->n_ts[cur] != 0) {
+        k_intersect_shadow_step<<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, cur, refill);
+        if (svm_ext)
+          k_shade_shadow_step<true><<<grid_wide, WF_BLOCK, 0, st>>>(soa, cur);
+        else
+          k_shade_shadow_step<false><<<grid_wide, WF_BLOCK, 0, st>>>(soa, cur);
+        k_shadow_step_end<<<1, 1, 0, st>>>(soa, cur);
+        stats.kernel_launches += 3;
+        CUDA_TRY(ctx, cudaMemcpyAsync(pool->h_counters, soa.counters, 64,
+                                      cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        stats.host_syncs += 1;
+        CUDA_TRY(ctx, cudaGetLastError());
+        cur ^= 1;
+      }
+    }
+    k_iteration_end<<<8, 256, 0, st>>>(soa, num_keys, it);
+    stats.kernel_launches += 8;
+    /* the reference copies the whole ray_state array every 16 iterations
+     * (device_split_kernel.cpp:302-318); here 64 bytes per bounce */
+    CUDA_TRY(ctx, cudaMemcpyAsync(pool->h_ring + (size_t)(it % WF_RING) * WF_RING_BYTES,
+                                  soa.counters, WF_RING_BYTES, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaEventRecord(ev[4], st));
+    CUDA_TRY(ctx, cudaGetLastError());
+    return B200_OK;
+  };
+  /* wait for iteration `it` to have finished (later ones may be queued behind it) and
+   * read what it left: queue length, flags, phase times */
+  auto harvest_iteration = [&](int it, bool had_work, unsigned int *n_active,
+                               unsigned int *flags) -> int {
+    cudaEvent_t *ev = pool->ring_ev[it % WF_RING];
+    CUDA_TRY(ctx, cudaEventSynchronize(ev[4]));
+    stats.host_waits += 1;
+    const WFCounters *h = (const WFCounters *)(pool->h_ring +
+                                               (size_t)(it % WF_RING) * WF_RING_BYTES);
+    *n_active = h->n_active;
+    *flags = h->flags;
+    if (had_work) {
+      float a = 0.0f, b = 0.0f, d = 0.0f;
+      cudaEventElapsedTime(&a, ev[0], ev[1]);
+      cudaEventElapsedTime(&b, ev[1], ev[2]);
+      cudaEventElapsedTime(&d, ev[2], ev[3]);
+      closest_ms += a;
+      shade_ms += b;
+      shadow_ms += d;
+      stats.closest_launches += 1;
+      stats.shadow_launches += 1;
+      stats.iterations += 1;
+    }
+    return B200_OK;
+  };
 
   /* bands of rows so that one sample of a band fits the pool */
   const int band_h = (int)std::max<size_t>(1, std::min<size_t>((size_t)tile->h,
@@ -1811,114 +1982,63 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
       bp.count_stats = count;
 
       for (int attempt = 0;; attempt++) {
-      PathSoA soa = pool->soa;
-      soa.debug = ctx->d_debug;
-      soa.debug_slot = (int)ctx->opt_debug_slot;
-      CUDA_TRY(ctx, cudaMemsetAsync(soa.counters, 0, sizeof(WFCounters), st));
-      if (attempt == 0) {
-        /* the Sobol points of this batch's samples, for every dimension a path can reach */
-        SobolTable sobol = {nullptr, bp.sample0, 0u, 0u};
-        const HostArray *lut = find_global(ctx, "__sample_pattern_lut");
-        if (kd_host<int>(ctx, KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_SOBOL && lut) {
-          const unsigned int reach = CY_PRNG_BASE_NUM +
-                                     (unsigned int)(kd_host<int>(ctx, KD_INT_MAX_BOUNCE) +
-                                                    kd_host<int>(ctx, KD_INT_TRANSPARENT_MAX_BOUNCE) +
-                                                    3) * CY_PRNG_BOUNCE_NUM;
-          const unsigned int nd = std::min<unsigned int>(reach, (unsigned int)(lut->bytes / 128));
-          if (nd > 0 && (size_t)nd * bp.nsamples <= SOBOL_TABLE_MAX) {
-            sobol.tab = pool->sobol_tab;
-            sobol.ns = (unsigned int)bp.nsamples;
-            sobol.nd = nd;
-            k_sobol_table<<<64, 256, 0, st>>>(pool->sobol_tab, bp.sample0, sobol.ns, nd);
-            stats.kernel_launches += 1;
+        PathSoA soa = pool->soa;
+        soa.debug = ctx->d_debug;
+        soa.debug_slot = (int)ctx->opt_debug_slot;
+        CUDA_TRY(ctx, cudaMemsetAsync(soa.counters, 0, sizeof(WFCounters), st));
+        if (attempt == 0) {
+          /* the Sobol points of this batch's samples, for every dimension a path can reach */
+          SobolTable sobol = {nullptr, bp.sample0, 0u, 0u};
+          const HostArray *lut = find_global(ctx, "__sample_pattern_lut");
+          if (kd_host<int>(ctx, KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_SOBOL && lut) {
+            const unsigned int reach =
+                CY_PRNG_BASE_NUM + (unsigned int)(kd_host<int>(ctx, KD_INT_MAX_BOUNCE) +
+                                                  kd_host<int>(ctx, KD_INT_TRANSPARENT_MAX_BOUNCE) +
+                                                  3) * CY_PRNG_BOUNCE_NUM;
+            const unsigned int nd = std::min<unsigned int>(reach, (unsigned int)(lut->bytes / 128));
+            if (nd > 0 && (size_t)nd * bp.nsamples <= SOBOL_TABLE_MAX) {
+              sobol.tab = pool->sobol_tab;
+              sobol.ns = (unsigned int)bp.nsamples;
+              sobol.nd = nd;
+              k_sobol_table<<<64, 256, 0, st>>>(pool->sobol_tab, bp.sample0, sobol.ns, nd);
+              stats.kernel_launches += 1;
+            }
           }
+          CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(g_sobol, &sobol, sizeof(sobol), 0,
+                                                cudaMemcpyHostToDevice, st));
         }
-        CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(g_sobol, &sobol, sizeof(sobol), 0,
-                                              cudaMemcpyHostToDevice, st));
-      }
-      k_init_from_camera<<<grid_wide, WF_BLOCK, 0, st>>>(soa, bp);
-      stats.kernel_launches += 1;
+        k_init_from_camera<<<grid_wide, WF_BLOCK, 0, st>>>(soa, bp);
+        stats.kernel_launches += 1;
 
-      const int max_iterations = 4096;
-      for (int it = 0; it < max_iterations; it++) {
-        CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
-        if (count)
-          k_intersect_closest<true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
-        else
-          k_intersect_closest<false><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
-        CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
-        k_sort_count<<<grid_wide, WF_BLOCK, 0, st>>>(soa);
-        k_sort_scan<<<1, 256, 0, st>>>(soa, num_keys);
-        k_sort_scatter<<<grid_wide, WF_BLOCK, 0, st>>>(soa);
-        if (svm_ext) {
-          k_shade_background<true><<<grid_wide, WF_BLOCK, 0, st>>>(soa);
-          k_shade_surface<true><<<grid_shade, WF_BLOCK, SHADE_SMEM_BYTES, st>>>(soa, num_keys);
-        }
-        else {
-          k_shade_background<false><<<grid_wide, WF_BLOCK, 0, st>>>(soa);
-          k_shade_surface<false><<<grid_shade, WF_BLOCK, SHADE_SMEM_BYTES, st>>>(soa, num_keys);
-        }
-        CUDA_TRY(ctx, cudaEventRecord(ctx->ev3, st));
-        if (use_ao) /* never with transparent shadows (check_scope) */
-          k_intersect_shadow<false, false, true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
-        else if (transparent_shadows)
-          k_intersect_shadow<false, true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
-        else if (count)
-          k_intersect_shadow<true, false><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
-        else
-          k_intersect_shadow<false, false><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
-        CUDA_TRY(ctx, cudaEventRecord(ctx->ev4, st));
-        if (transparent_shadows) {
-          /* shadow rays stopped by a transparent surface walk on, one surface per step */
-          CUDA_TRY(ctx, cudaMemcpyAsync(pool->h_counters, soa.counters, 64,
-                                        cudaMemcpyDeviceToHost, st));
-          CUDA_TRY(ctx, cudaStreamSynchronize(st));
-          int cur = 0;
-          while (pool->h_counters->n_ts[cur] != 0) {
-            k_intersect_shadow_step<<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, cur, refill);
-            if (svm_ext)
-              k_shade_shadow_step<true><<<grid_wide, WF_BLOCK, 0, st>>>(soa, cur);
-            else
-              k_shade_shadow_step<false><<<grid_wide, WF_BLOCK, 0, st>>>(soa, cur);
-            k_shadow_step_end<<<1, 1, 0, st>>>(soa, cur);
-            stats.kernel_launches += 3;
-            CUDA_TRY(ctx, cudaMemcpyAsync(pool->h_counters, soa.counters, 64,
-                                          cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(ctx, cudaStreamSynchronize(st));
-            CUDA_TRY(ctx, cudaGetLastError());
-            cur ^= 1;
+        const int max_iterations = 4096;
+        unsigned int n_active = 1u, prev_n_active = 1u, flags = 0u;
+        int harvested = 0;
+        for (int it = 0; it < max_iterations && n_active != 0u; it++) {
+          rc = enqueue_iteration(soa, it);
+          if (rc)
+            return rc;
+          std::swap(soa.q_active, soa.q_next);
+          std::swap(soa.ray_P_t, soa.nray_P_t);
+          std::swap(soa.ray_D, soa.nray_D);
+          while (harvested <= it - lag && n_active != 0u) {
+            prev_n_active = n_active;
+            rc = harvest_iteration(harvested, prev_n_active != 0u, &n_active, &flags);
+            if (rc)
+              return rc;
+            harvested++;
           }
         }
-        k_iteration_end<<<8, 256, 0, st>>>(soa, num_keys, it);
-        stats.kernel_launches += 8;
-        stats.closest_launches += 1;
-        stats.shadow_launches += 1;
-        /* one counter back per bounce (the reference copies the whole ray_state
-         * array every 16 iterations, device_split_kernel.cpp:302-318) */
-        CUDA_TRY(ctx, cudaMemcpyAsync(pool->h_counters, soa.counters, 64,
-                                      cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(ctx, cudaStreamSynchronize(st));
-        CUDA_TRY(ctx, cudaGetLastError());
-        {
-          float a = 0.0f, b = 0.0f;
-          cudaEventElapsedTime(&a, ctx->ev0, ctx->ev1);
-          cudaEventElapsedTime(&b, ctx->ev3, ctx->ev4);
-          closest_ms += a;
-          shadow_ms += b;
+        /* iterations queued behind the one that emptied the queue find nothing to do */
+        if (flags & WF_FLAG_TRACE_OVERFLOW) {
+          const unsigned int zero = 0;
+          CUDA_TRY(ctx, cudaMemcpyToSymbol(g_trace_overflow, &zero, sizeof(zero)));
+          return fail(ctx, B200_ERR_UNSUPPORTED,
+                      "BVH8 traversal stack overflow: hits of this batch are not reliable");
         }
-        std::swap(soa.q_active, soa.q_next);
-        std::swap(soa.ray_P_t, soa.nray_P_t);
-        std::swap(soa.ray_D, soa.nray_D);
-        if (pool->h_counters->n_active == 0)
-          break;
-      }
-      if (!svm_ext) {
-        /* Nothing of this batch has reached the film yet.  If a lean kernel met a shader
-         * only the full interpreter runs, the batch is thrown away and traced again with
-         * the full kernels, and the context stays on them until the program changes. */
-        unsigned int miss = 0;
-        CUDA_TRY(ctx, cudaMemcpyFromSymbol(&miss, g_svm_scope_miss, sizeof(miss)));
-        if (miss) {
+        if (!svm_ext && (flags & WF_FLAG_SCOPE_MISS)) {
+          /* Nothing of this batch has reached the film yet.  A lean kernel met a shader
+           * only the full interpreter runs: the batch is thrown away and traced again with
+           * the full kernels, and the context stays on them until the program changes. */
           const unsigned int zero = 0;
           CUDA_TRY(ctx, cudaMemcpyToSymbol(g_svm_scope_miss, &zero, sizeof(zero)));
           if (attempt > 0)
@@ -1927,34 +2047,33 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
           ctx->force_svm_ext = true;
           continue;
         }
-      }
-      k_film_accumulate<<<grid_wide, WF_BLOCK, 0, st>>>(soa, bp, (float *)tile->buffer,
-                                                        pass_stride, pass_combined);
-      stats.kernel_launches += 1;
-      CUDA_TRY(ctx, cudaMemcpyAsync(pool->h_counters, soa.counters, 256, cudaMemcpyDeviceToHost,
-                                    st));
-      CUDA_TRY(ctx, cudaStreamSynchronize(st));
-      CUDA_TRY(ctx, cudaGetLastError());
-      stats.primary_rays += pool->h_counters->primary_rays;
-      stats.bounce_rays += pool->h_counters->bounce_rays;
-      stats.shadow_rays += pool->h_counters->shadow_rays;
-      stats.closest_nodes += pool->h_counters->nodes;
-      stats.closest_tris += pool->h_counters->tris;
-      stats.closest_instances += pool->h_counters->instances;
-      stats.shadow_nodes += pool->h_counters->sh_nodes;
-      stats.shadow_tris += pool->h_counters->sh_tris;
-      stats.shadow_instances += pool->h_counters->sh_instances;
-      break;
+        k_film_accumulate<<<grid_wide, WF_BLOCK, 0, st>>>(soa, bp, (float *)tile->buffer,
+                                                          pass_stride, pass_combined);
+        stats.kernel_launches += 1;
+        CUDA_TRY(ctx, cudaMemcpyAsync(pool->h_batch + (size_t)batch_slot * WF_BATCH_STAT_BYTES,
+                                      soa.counters, WF_BATCH_STAT_BYTES, cudaMemcpyDeviceToHost,
+                                      st));
+        CUDA_TRY(ctx, cudaGetLastError());
+        stats.batches += 1;
+        if (++batch_slot == WF_BATCH_SLOTS) {
+          rc = sum_batch_stats();
+          if (rc)
+            return rc;
+        }
+        break;
       } /* attempt */
     }
   }
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev6, st));
-  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  rc = sum_batch_stats();
+  if (rc)
+    return rc;
   {
     float total = 0.0f;
     cudaEventElapsedTime(&total, ctx->ev5, ctx->ev6);
     stats.device_ms = total;
     stats.closest_ms = closest_ms;
+    stats.shade_ms = shade_ms;
     stats.shadow_ms = shadow_ms;
   }
   stats.svm_extended = svm_ext ? 1 : 0;

@@ -37,6 +37,7 @@ EXPORTS = [
     "b200_trace_batch", "b200_film_convert", "b200_film_reduce", "b200_get_stats",
     "b200_synchronize", "b200_set_option", "b200_set_stream", "b200_debug_read",
     "b200_validate_svm", "b200_device_pci_id", "b200_set_cancel_callback", "b200_film_allreduce",
+    "b200_texture_set", "b200_texture_clear",
 ]
 
 
@@ -56,7 +57,9 @@ class Stats(C.Structure):
                 ("kernel_launches", C.c_uint64), ("closest_launches", C.c_uint64),
                 ("shadow_launches", C.c_uint64),
                 ("device_ms", C.c_double), ("closest_ms", C.c_double), ("shadow_ms", C.c_double),
-                ("svm_extended", C.c_uint64)]
+                ("svm_extended", C.c_uint64),
+                ("shade_ms", C.c_double), ("batches", C.c_uint64), ("iterations", C.c_uint64),
+                ("host_syncs", C.c_uint64), ("host_waits", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -111,6 +114,8 @@ def load_library():
     L.b200_film_allreduce.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(u64), sz]
     L.b200_device_pci_id.argtypes = [C.c_int, C.c_char_p, sz]
     L.b200_set_cancel_callback.argtypes = [vp, vp, vp]
+    L.b200_texture_set.argtypes = [vp, C.c_int, vp, sz, u64]
+    L.b200_texture_clear.argtypes = [vp, C.c_int]
     L.b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.b200_synchronize.argtypes = [vp]
     L.b200_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
@@ -162,6 +167,7 @@ class B200Device:
             raise DeviceError("b200_create: " + err.value.decode())
         self.ordinal = ordinal
         self._globals = {}
+        self._textures = {}
 
     # -- error latch (Device::set_error / have_error / error_message) --
     def have_error(self):
@@ -251,9 +257,38 @@ class B200Device:
         self._check(self._L.b200_set_kernel_data(self._ctx, buf.ctypes.data, buf.nbytes),
                     "const_copy_to(__data)")
 
+    # -- image textures (CUDADevice::tex_alloc / tex_free) --
+    def tex_alloc(self, slot, texture_info, pixels):
+        """One image slot: `texture_info` = the reference's TextureInfo record (bytes),
+        `pixels` = the host pixel array (any dtype; uploaded as it is)."""
+        mem = DeviceMemory("tex_%d" % slot, np.ascontiguousarray(pixels).view(np.uint8),
+                           MEM_TEXTURE)
+        old = self._textures.pop(slot, None)
+        if old is not None:
+            self.mem_free(old)
+        self.mem_alloc(mem)
+        host = np.ascontiguousarray(mem.host)
+        self._check(self._L.b200_h2d(self._ctx, mem.device_pointer, host.ctypes.data, 0,
+                                     host.nbytes), "tex_alloc(%d)" % slot)
+        info = np.ascontiguousarray(texture_info).view(np.uint8)
+        self._check(self._L.b200_texture_set(self._ctx, int(slot), info.ctypes.data, info.nbytes,
+                                             mem.device_pointer), "tex_alloc(%d)" % slot)
+        self._textures[slot] = mem
+
+    def tex_free(self, slot):
+        mem = self._textures.pop(slot, None)
+        if mem is not None:
+            self._check(self._L.b200_texture_clear(self._ctx, int(slot)), "tex_free")
+            self.mem_free(mem)
+
     # -- convenience: upload everything Scene::device_update would --
-    def upload_scene(self, arrays):
-        """arrays: {kernel_textures name: (uint8 bytes, elem_size)} + "__data"."""
+    def upload_scene(self, arrays, textures=None):
+        """arrays: {kernel_textures name: (uint8 bytes, elem_size)} + "__data";
+        textures: [(slot, TextureInfo bytes, pixels)] - the ImageManager's images."""
+        for slot in list(self._textures):
+            self.tex_free(slot)
+        for slot, info, pixels in (textures or []):
+            self.tex_alloc(slot, info, pixels)
         for name, (data, _es) in arrays.items():
             if name == "__data":
                 continue

@@ -837,9 +837,39 @@ def icosphere(subdiv):
     return V, F
 
 
-def rock_mesh(subdiv=6, seed=42, amplitude=0.18):
-    """Icosphere (20*4^subdiv tris; subdiv 6 -> 81 920) with lumpy radial noise."""
-    V, F = icosphere(subdiv)
+def geodesic_sphere(freq):
+    """Icosahedron with every face cut into freq x freq triangles, pushed out onto the unit
+    sphere: 20 * freq^2 triangles (freq 71 -> 100 820), vertices shared along the edges."""
+    V0, F0 = icosphere(0)
+    verts, index, faces = [], {}, []
+
+    def vid(p):
+        key = tuple(np.round(p, 9))
+        if key not in index:
+            index[key] = len(verts)
+            verts.append(p)
+        return index[key]
+
+    n = int(freq)
+    for a, b, c in F0:
+        A, B, C = V0[a], V0[b], V0[c]
+        grid = {}
+        for i in range(n + 1):
+            for j in range(n + 1 - i):
+                p = (A * (n - i - j) + B * i + C * j) / n
+                grid[(i, j)] = vid(p / np.linalg.norm(p))
+        for i in range(n):
+            for j in range(n - i):
+                faces.append((grid[(i, j)], grid[(i + 1, j)], grid[(i, j + 1)]))
+                if i + j < n - 1:
+                    faces.append((grid[(i + 1, j)], grid[(i + 1, j + 1)], grid[(i, j + 1)]))
+    return np.array(verts, dtype=np.float64), np.array(faces, dtype=np.int64)
+
+
+def rock_mesh(subdiv=6, seed=42, amplitude=0.18, freq=0):
+    """A sphere with lumpy radial noise: an icosphere (20*4^subdiv tris; subdiv 6 ->
+    81 920) or, with freq > 0, a geodesic sphere of 20*freq^2 triangles."""
+    V, F = geodesic_sphere(freq) if freq > 0 else icosphere(subdiv)
     rng = np.random.default_rng(seed)
     r = np.ones(len(V))
     for k in range(1, 5):
@@ -851,10 +881,16 @@ def rock_mesh(subdiv=6, seed=42, amplitude=0.18):
     return (V * r[:, None]).astype(np.float32), F.astype(np.int32)
 
 
-def instanced(width=3840, height=2160, spp=256, grid=100, subdiv=6, max_bounce=2, seed=7):
-    """BASELINE config 4 - grid x grid instances of one lumpy icosphere BLAS
-    (two-level BVH, transform_applied=false) over a ground plane."""
-    P, T = rock_mesh(subdiv)
+def instanced(width=3840, height=2160, spp=256, grid=100, subdiv=6, max_bounce=2, seed=7,
+              freq=None):
+    """BASELINE config 4 - grid x grid instances of one lumpy sphere BLAS (two-level BVH,
+    transform_applied=false) over a ground plane.  At the configuration's size (grid 100)
+    the BLAS is a geodesic sphere of 20 * 71^2 = 100 820 triangles: 10 000 instances of
+    a 100k-triangle mesh, ~1 G effective triangles; the small test variants keep the
+    icosphere (20 * 4^subdiv)."""
+    if freq is None:
+        freq = 71 if grid >= 100 else 0
+    P, T = rock_mesh(subdiv, freq=freq)
     rng = np.random.default_rng(seed)
     meshes = [MeshDesc(P, T, "rock")]
     objects = []

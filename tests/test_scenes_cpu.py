@@ -33,7 +33,7 @@ def test_config_sizes():
     assert c.num_triangles == 12 and (c.width, c.height, c.spp) == (1920, 1080, 64)
     full = scenes.instanced()
     assert (full.width, full.height) == (3840, 2160) and len(full.objects) == 10001
-    assert full.meshes[0].tris.shape[0] == 81920
+    assert full.meshes[0].tris.shape[0] == 100820  # 20 * 71^2: BASELINE config 4's 100k-triangle BLAS
 
 
 def test_meshes_are_valid():
