@@ -59,6 +59,9 @@ def lib():
         L.ref_global_name.restype = C.c_char_p
         L.ref_global_name.argtypes = [C.c_int]
         L.ref_scene_data.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.ref_scene_num_textures.argtypes = [C.c_void_p]
+        L.ref_scene_texture.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64,
+                                        C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.ref_render.argtypes = [
             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
         L.ref_film_convert.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -195,6 +198,23 @@ class RefScene:
         out["__data"] = (self.kernel_data(), 1)
         return out
 
+    def textures(self):
+        """[(slot, TextureInfo bytes, pixel bytes)] - the images the reference's
+        ImageManager loaded into its device (CPUDevice::tex_alloc), for
+        B200Device.upload_scene(arrays, textures)."""
+        from raytracingproject_b200.device import SIZEOF_TEXTURE_INFO
+        out = []
+        for slot in range(self._L.ref_scene_num_textures(self._h)):
+            info = np.zeros(SIZEOF_TEXTURE_INFO, np.uint8)
+            p, n = C.c_void_p(), C.c_uint64()
+            if self._L.ref_scene_texture(self._h, slot, info.ctypes.data, info.nbytes,
+                                         C.byref(p), C.byref(n)) != 0:
+                raise RuntimeError("ref_scene_texture(%d)" % slot)
+            if n.value and p.value:
+                pix = np.ctypeslib.as_array((C.c_uint8 * n.value).from_address(p.value)).copy()
+                out.append((slot, info, pix))
+        return out
+
     def render(self, start_sample, num_samples, tile_size=64, accumulate=False):
         """Film sums, shape (h, w, pass_stride) float32, and the wall seconds."""
         w, h, ps = self.width, self.height, self.pass_stride
@@ -294,6 +314,10 @@ def build_scene(desc, kernel=RefScene.GENERIC, external_device=None, threads=0, 
     path = os.path.join(d, desc.name + ".xml")
     with open(path, "w") as f:
         f.write(desc.xml)
+    if getattr(desc, "images", None):
+        from raytracingproject_b200.scenes import write_b2im
+        for fname, pixels in desc.images.items():
+            write_b2im(os.path.join(d, fname), pixels)
     rs = RefScene(path, kernel=kernel, external_device=external_device, threads=threads)
     handles = [rs.add_mesh(m.P, m.tris, m.shader, m.smooth) for m in desc.meshes]
     for mi, tfm in desc.objects:
@@ -302,5 +326,11 @@ def build_scene(desc, kernel=RefScene.GENERIC, external_device=None, threads=0, 
         if off:
             rs._L.ref_scene_set_terminator_offset.argtypes = [C.c_void_p, C.c_int, C.c_float]
             rs._L.ref_scene_set_terminator_offset(rs._h, o, C.c_float(off))
+    for shader, node, tiles in getattr(desc, "image_tiles", None) or []:
+        arr = (C.c_int * len(tiles))(*tiles)
+        rs._L.ref_scene_set_image_tiles.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p,
+                                                    C.POINTER(C.c_int), C.c_int]
+        rs._check(rs._L.ref_scene_set_image_tiles(rs._h, shader.encode(), node.encode(), arr,
+                                                  len(tiles)))
     rs.update(desc.width, desc.height)
     return rs

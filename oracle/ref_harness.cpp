@@ -32,6 +32,9 @@
 #include "render/integrator.h"
 #include "render/light.h"
 #include "render/mesh.h"
+#include "render/nodes.h"
+#include "render/graph.h"
+#include "render/image.h"
 #include "render/object.h"
 #include "render/scene.h"
 #include "render/shader.h"
@@ -283,6 +286,28 @@ int ref_scene_set_terminator_offset(ref_scene *rs, int object, float offset)
   return 0;
 }
 
+/* UDIM tiles of one Image Texture node.  (The node's tile list is a plain member, not a
+ * socket, so the XML reader cannot set it - Blender's exporter does, blender_shader.cpp.)
+ * To be called before the first ref_scene_update. */
+int ref_scene_set_image_tiles(
+    ref_scene *rs, const char *shader_name, const char *node_name, const int *tiles, int num_tiles)
+{
+  Shader *shader = find_shader(rs->scene, shader_name);
+  if (!shader || !shader->graph)
+    return 1;
+  foreach (ShaderNode *node, shader->graph->nodes) {
+    if (node->type == ImageTextureNode::node_type && node->name == node_name) {
+      ImageTextureNode *img = (ImageTextureNode *)node;
+      img->tiles.clear();
+      for (int i = 0; i < num_tiles; i++)
+        img->tiles.push_back(tiles[i]);
+      shader->tag_update(rs->scene);
+      return 0;
+    }
+  }
+  return 1;
+}
+
 /* Equivalent of Session::update_scene (session.cpp:909-950). */
 int ref_scene_update(ref_scene *rs, int width, int height)
 {
@@ -298,6 +323,10 @@ int ref_scene_update(ref_scene *rs, int width, int height)
   }
   bool kernel_switch_needed = false;
   scene->update(rs->progress, kernel_switch_needed);
+  /* CPUDevice publishes its image table to the kernel globals at the next task_add
+   * (device_cpu.cpp:360-366); the probes call kernel functions without a task */
+  if (rs->cpu)
+    rs->cpu->load_texture_info();
   /* session.cpp:282,702 - size the profiler's per-shader / per-object counters. */
   rs->profiler.reset(scene->shaders.size(), scene->objects.size());
   if (rs->device->have_error()) {
@@ -364,6 +393,52 @@ const char *ref_global_name(int index)
       NULL};
   int n = (int)(sizeof(names) / sizeof(names[0])) - 1;
   return (index >= 0 && index < n) ? names[index] : NULL;
+}
+
+/* Image textures as the ImageManager handed them to the device (CPUDevice::tex_alloc,
+ * device_cpu.cpp:483-504): the TextureInfo record of a slot and the host pixels it points
+ * at.  Slots that hold no image report 0 bytes.  Only for the oracle's own CPU device. */
+static bool scene_uses_image_slot(Scene *scene, int slot)
+{
+  /* CPUDevice grows its table 128 slots at a time without clearing them, so the slots in
+   * use are taken from the shader graphs' image nodes */
+  foreach (Shader *shader, scene->shaders) {
+    if (!shader->graph)
+      continue;
+    foreach (ShaderNode *node, shader->graph->nodes) {
+      if (node->special_type != SHADER_SPECIAL_TYPE_IMAGE_SLOT)
+        continue;
+      ImageHandle &handle = ((ImageSlotTextureNode *)node)->handle;
+      for (int t = 0; t < handle.num_tiles(); t++)
+        if (handle.svm_slot(t) == slot)
+          return true;
+    }
+  }
+  return false;
+}
+int ref_scene_num_textures(ref_scene *rs)
+{
+  return rs->cpu ? (int)rs->cpu->texture_info.size() : 0;
+}
+int ref_scene_texture(
+    ref_scene *rs, int slot, void *info_out, uint64_t info_bytes, const void **pixels, uint64_t *bytes)
+{
+  if (!rs->cpu || slot < 0 || slot >= (int)rs->cpu->texture_info.size() ||
+      info_bytes != sizeof(TextureInfo))
+    return 1;
+  *pixels = NULL;
+  *bytes = 0;
+  memset(info_out, 0, sizeof(TextureInfo));
+  if (!scene_uses_image_slot(rs->scene, slot))
+    return 0;
+  const TextureInfo &info = rs->cpu->texture_info[slot];
+  memcpy(info_out, &info, sizeof(TextureInfo));
+  static const uint64_t texel_bytes[IMAGE_DATA_NUM_TYPES] = {16, 4, 8, 4, 1, 2, 8, 2};
+  *pixels = (const void *)info.data;
+  *bytes = info.data ? (uint64_t)info.width * info.height * (info.depth > 1 ? info.depth : 1u) *
+                           texel_bytes[info.data_type % IMAGE_DATA_NUM_TYPES] :
+                       0;
+  return 0;
 }
 
 int ref_scene_data(ref_scene *rs, const void **ptr, uint64_t *size)

@@ -504,6 +504,15 @@ int ref_probe_svm_node(KernelGlobals *kg, const void *nodes, int offset, float *
     case NODE_CLAMP:
       svm_node_clamp(kg, sd, stack, node.y, node.z, node.w, &offset);
       break;
+    case NODE_TEX_IMAGE:
+      svm_node_tex_image(kg, sd, stack, node, &offset);
+      break;
+    case NODE_TEX_IMAGE_BOX:
+      svm_node_tex_image_box(kg, sd, stack, node);
+      break;
+    case NODE_TEX_ENVIRONMENT:
+      svm_node_tex_environment(kg, sd, stack, node);
+      break;
     default:
       offset = -1;
   }

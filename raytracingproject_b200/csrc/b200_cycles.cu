@@ -393,7 +393,7 @@ int b200_synchronize(b200_ctx *ctx)
 /* SVM opcodes / closures the shading kernels implement; anything else in a
  * bound __svm_nodes stream is refused up front instead of rendering wrongly. */
 static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why,
-                         uint32_t *features);
+                         uint32_t *features, int *max_image_slot);
 
 int b200_bind_global(b200_ctx *ctx, const char *name, uint64_t dptr, const void *host,
                      size_t bytes)
@@ -460,7 +460,9 @@ int b200_bind_global(b200_ctx *ctx, const char *name, uint64_t dptr, const void 
   }
   if (strcmp(name, "__svm_nodes") == 0 && bytes) {
     std::string why;
-    if (!svm_validate((const uint32_t *)ha.host.data(), bytes / 16, why, &ctx->svm_features))
+    ctx->svm_max_image_slot = -1;
+    if (!svm_validate((const uint32_t *)ha.host.data(), bytes / 16, why, &ctx->svm_features,
+                      &ctx->svm_max_image_slot))
       return fail(ctx, B200_ERR_UNSUPPORTED, why);
   }
   if (strcmp(name, "__objects") == 0) {
@@ -558,7 +560,7 @@ int b200_validate_svm(const void *svm_nodes, size_t bytes, char *err, size_t err
   uint32_t features = 0;
   if (!svm_nodes || bytes % 16 != 0)
     why = "an SVM program is an array of 16-byte nodes";
-  else if (svm_validate((const uint32_t *)svm_nodes, bytes / 16, why, &features))
+  else if (svm_validate((const uint32_t *)svm_nodes, bytes / 16, why, &features, nullptr))
     return B200_OK;
   if (err && errlen) {
     strncpy(err, why.c_str(), errlen - 1);

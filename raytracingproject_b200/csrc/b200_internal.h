@@ -49,6 +49,7 @@ struct b200_ctx {
    * one array when the scene is prepared */
   std::vector<uint8_t> texture_info;
   void *d_texture_info = nullptr;
+  int svm_max_image_slot = -1; /* highest image slot the bound program names */
   std::vector<uint8_t> kernel_data;
   bool scene_dirty = true; /* BVH8 / constant block must be (re)built */
   /* this context's constant block: the __constant__ DeviceScene is one per GPU, so a

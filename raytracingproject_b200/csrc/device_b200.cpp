@@ -113,10 +113,6 @@ class B200Device : public Device {
   {
     if (!ctx || mem.device_pointer)
       return;
-    if (mem.type == MEM_TEXTURE) {
-      set_error("B200 device: image textures are outside the hot-path scope");
-      return;
-    }
     uint64_t dptr = 0;
     const size_t size = mem.memory_size();
     if (!check(b200_alloc(ctx, size, &dptr), "mem_alloc"))
@@ -151,6 +147,16 @@ class B200Device : public Device {
       check(b200_bind_global(ctx, mem.name, (uint64_t)mem.device_pointer, mem.host_pointer,
                              mem.memory_size()),
             mem.name);
+    }
+    else if (mem.type == MEM_TEXTURE) {
+      /* CUDADevice::tex_alloc (device_cuda_impl.cpp:1105-1304): the ImageManager's pixels
+       * are an ordinary allocation; the slot's TextureInfo goes to the device's table with
+       * `data` = the device address (the kernels sample with the CPU device's arithmetic,
+       * so no CUDA array / texture object is made) */
+      device_texture &tex = (device_texture &)mem;
+      check(b200_texture_set(ctx, (int)tex.slot, &tex.info, sizeof(TextureInfo),
+                             (uint64_t)mem.device_pointer),
+            "tex_alloc");
     }
   }
 
@@ -380,10 +386,6 @@ class B200MultiDevice : public Device {
   {
     if (ctxs.empty() || mem.device_pointer || have_error())
       return;
-    if (mem.type == MEM_TEXTURE) {
-      set_error("B200 device: image textures are outside the hot-path scope");
-      return;
-    }
     Allocation a;
     a.size = mem.memory_size();
     for (size_t i = 0; i < ctxs.size(); i++) {
@@ -423,6 +425,13 @@ class B200MultiDevice : public Device {
         if (!check(i, b200_bind_global(ctxs[i], mem.name, a->ptr[i], mem.host_pointer,
                                        mem.memory_size()),
                    mem.name))
+          return;
+      }
+      else if (mem.type == MEM_TEXTURE) {
+        device_texture &tex = (device_texture &)mem;
+        if (!check(i, b200_texture_set(ctxs[i], (int)tex.slot, &tex.info, sizeof(TextureInfo),
+                                       a->ptr[i]),
+                   "tex_alloc"))
           return;
       }
     }
@@ -635,7 +644,7 @@ void device_b200_info(vector<DeviceInfo> &devices)
       info.id = string_printf("B200_%s_%s", name, pci);
     else
       info.id = string_printf("B200_%s_%d", name, i);
-    info.has_half_images = false;
+    info.has_half_images = true; /* half images are sampled as stored (svm_image.cuh) */
     info.has_volume_decoupled = false;
     info.has_adaptive_stop_per_sample = false;
     info.has_osl = false;

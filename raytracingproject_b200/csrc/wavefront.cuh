@@ -1421,7 +1421,7 @@ static bool svm_mix_supported_host(uint32_t type)
 
 /* Opcodes and closure ids the kernels implement (svm.h switch subset). */
 static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why,
-                         uint32_t *features)
+                         uint32_t *features, int *max_image_slot)
 {
   *features = 0;
   /* Constants the program wrote with NODE_VALUE_F since the last node of any other kind:
@@ -1533,15 +1533,26 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
         i += 2;
         break;
       case CY_NODE_TEX_IMAGE: {
-        /* followed by its UDIM tile nodes (two tiles each) when it has any */
+        /* followed by its UDIM tile nodes (two (tile, slot) pairs each) when it has any;
+         * otherwise the slot is the negated count */
         const int tiles = (int)nodes[4 * i + 1];
         *features |= SVM_USES_EXTENDED_NODES | SVM_USES_IMAGES;
+        if (max_image_slot) {
+          if (tiles <= 0)
+            *max_image_slot = std::max(*max_image_slot, -tiles);
+          for (int t = 0; t < tiles && i + 1 + (size_t)t < n_nodes; t++) {
+            const uint32_t *tn = nodes + 4 * (i + 1 + (size_t)t);
+            *max_image_slot = std::max(*max_image_slot, std::max((int)tn[1], (int)tn[3]));
+          }
+        }
         i += 1 + (size_t)(tiles > 0 ? tiles : 0);
         break;
       }
       case CY_NODE_TEX_IMAGE_BOX:
       case CY_NODE_TEX_ENVIRONMENT:
         *features |= SVM_USES_EXTENDED_NODES | SVM_USES_IMAGES;
+        if (max_image_slot)
+          *max_image_slot = std::max(*max_image_slot, (int)nodes[4 * i + 1]);
         i += 1;
         break;
       case CY_NODE_MIN_MAX:
@@ -1682,6 +1693,19 @@ static bool svm_validate(const uint32_t *nodes, size_t n_nodes, std::string &why
 
 /* Features of KernelData the kernels do not implement are refused, never
  * silently approximated. */
+/* one past the highest image slot that has pixels */
+static int bound_image_slots(const b200_ctx *ctx)
+{
+  int n = 0;
+  for (size_t t = 0; t + SIZEOF_TEXTURE_INFO <= ctx->texture_info.size(); t += SIZEOF_TEXTURE_INFO) {
+    uint64_t data = 0;
+    memcpy(&data, ctx->texture_info.data() + t + TI_DATA, 8);
+    if (data)
+      n = (int)(t / SIZEOF_TEXTURE_INFO) + 1;
+  }
+  return n;
+}
+
 static int check_scope(b200_ctx *ctx)
 {
   auto I = [&](int off) { return kd_host<int>(ctx, off); };
@@ -1712,6 +1736,10 @@ static int check_scope(b200_ctx *ctx)
     why = "volumes are outside the hot-path scope";
   else if (I(KD_INT_USE_AMBIENT_OCCLUSION) && I(KD_INT_TRANSPARENT_SHADOWS))
     why = "ambient occlusion together with transparent shadows is outside the hot-path scope";
+  else if ((ctx->svm_features & SVM_USES_IMAGES) && ctx->svm_max_image_slot >= bound_image_slots(ctx))
+    why = "the shader program samples image slot " + std::to_string(ctx->svm_max_image_slot) +
+          " but only " + std::to_string(bound_image_slots(ctx)) +
+          " image slots are bound (tex_alloc / b200_texture_set)";
   else if (I(KD_BG_USE_MIS))
     why = "background importance sampling is outside the hot-path scope";
   else if (I(KD_FILM_USE_LIGHT_PASS) || I(KD_FILM_PASS_DENOISING_DATA) ||

@@ -29,6 +29,7 @@ HIT_DTYPE = np.dtype(
 
 # device_memory.h:35-42
 MEM_READ_ONLY, MEM_READ_WRITE, MEM_DEVICE_ONLY, MEM_GLOBAL, MEM_TEXTURE, MEM_PIXELS = range(6)
+SIZEOF_TEXTURE_INFO = 96  # util/util_texture.h TextureInfo (include/cycles_abi.h; checked in tests)
 
 EXPORTS = [
     "b200_abi_version", "b200_device_count", "b200_device_name", "b200_create", "b200_destroy",

@@ -9,7 +9,7 @@ flattens it into the device arrays that both the CPU oracle and the B200 device
 consume.  All generators are seeded and deterministic.
 """
 from dataclasses import dataclass, field
-from typing import List, Optional, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
@@ -33,6 +33,11 @@ class SceneDesc:
     objects: List[Tuple[int, np.ndarray]] = field(default_factory=list)
     spp: int = 64
     notes: str = ""
+    # image textures: file name (as the XML names it, relative to the scene file) -> pixels,
+    # (h, w) or (h, w, c) of uint8 / uint16 / float16 / float32, row 0 = bottom row
+    images: Dict[str, np.ndarray] = field(default_factory=dict)
+    # UDIM tile numbers of Image Texture nodes: (shader name, node name, [tiles])
+    image_tiles: List[Tuple[str, str, List[int]]] = field(default_factory=list)
 
     @property
     def num_triangles(self):
@@ -530,6 +535,160 @@ def _textured_shaders(variant):
     return white + red + green + metal + glass
 
 
+
+# ---------------------------------------------------------------- image textures
+_B2IM_KINDS = {np.dtype(np.uint8): 0, np.dtype(np.float32): 1, np.dtype(np.float16): 2,
+               np.dtype(np.uint16): 3}
+
+
+def write_b2im(path, pixels):
+    """The raw image container of this repo's scenes: "B2IM", uint32 width, height,
+    channels, kind (0 uint8, 1 float32, 2 float16, 3 uint16), then the rows bottom-up.
+    (There is no OpenImageIO in the image; the test harness's stand-in for the reference's
+    image loader reads this, oracle/ref_stubs.cpp.)"""
+    a = np.ascontiguousarray(pixels)
+    if a.ndim == 2:
+        a = a[:, :, None]
+    h, w, c = a.shape
+    with open(path, "wb") as f:
+        f.write(b"B2IM")
+        f.write(np.array([w, h, c, _B2IM_KINDS[a.dtype]], np.uint32).tobytes())
+        f.write(a.tobytes())
+
+
+def test_image(kind, width, height, channels, seed):
+    """A small deterministic test image: smooth colour ramps, a coarse checker and noise,
+    alpha (when there is a fourth channel) with fully transparent, partial and opaque
+    regions.  `kind`: "u8" | "u16" | "f16" | "f32" (float images reach above 1)."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:height, 0:width]
+    u, v = (x + 0.5) / width, (y + 0.5) / height
+    chan = [0.5 + 0.5 * np.sin(6.0 * u + 2.0 * v + seed), v * (0.3 + 0.7 * u),
+            0.25 + 0.75 * (((x // 3) + (y // 2)) % 2)]
+    img = np.stack(chan[:max(1, min(channels, 3))], axis=-1)
+    img = np.clip(img + rng.uniform(-0.08, 0.08, img.shape), 0.0, 1.0)
+    if channels == 2 or channels == 4:
+        alpha = np.clip(1.6 * np.abs(np.sin(3.0 * u * np.pi) * np.cos(2.0 * v * np.pi)) - 0.15,
+                        0.0, 1.0)
+        img = np.concatenate([img[..., :channels - 1], alpha[..., None]], axis=-1)
+    if kind == "u8":
+        return np.round(img * 255.0).astype(np.uint8)
+    if kind == "u16":
+        return np.round(img * 65535.0).astype(np.uint16)
+    if kind == "f16":
+        return (img * 1.5).astype(np.float16)
+    return (img * 2.0).astype(np.float32)
+
+
+def _image_shaders(variant):
+    """Cornell materials that read image textures (svm_image.cuh): every pixel format,
+    interpolation, extension and projection between the two variants, alpha handling,
+    UDIM tiles.  Returns (xml, {file name: pixels})."""
+    c = lambda a, b: '  <connect from="%s" to="%s"/>\n' % (a, b)
+    images = {}
+    if variant == 0:
+        images["rgba8.b2im"] = test_image("u8", 37, 23, 4, 1)
+        images["rgb32f.b2im"] = test_image("f32", 32, 32, 3, 2)
+        images["gray8.b2im"] = test_image("u8", 16, 12, 1, 3)
+        images["rgba16f.b2im"] = test_image("f16", 24, 20, 4, 4)
+        images["tile.1001.b2im"] = test_image("u8", 16, 16, 3, 5)
+        images["tile.1002.b2im"] = test_image("u8", 20, 12, 4, 6)
+        white = _node_shader(
+            "white", '  <texture_coordinate name="tc"/>\n'
+            '  <image_texture name="t" filename="rgba8.b2im" colorspace="sRGB" '
+            'interpolation="linear" extension="periodic" tex_mapping.scale="1.7 2.3 1"/>\n' +
+            c("tc generated", "t vector") +
+            '  <diffuse_bsdf name="d"/>\n' + c("t color", "d color"), "d bsdf")
+        red = _node_shader(
+            "red", '  <texture_coordinate name="tc"/>\n'
+            '  <image_texture name="t" filename="rgb32f.b2im" interpolation="cubic" '
+            'extension="clamp" projection="box" projection_blend="0.35"/>\n' +
+            c("tc object", "t vector") +
+            '  <mix name="mx" type="multiply" fac="1.0" color2="0.65 0.2 0.2"/>\n' +
+            c("t color", "mx color1") +
+            '  <diffuse_bsdf name="d"/>\n' + c("mx color", "d color"), "d bsdf")
+        green = _node_shader(
+            "green", '  <texture_coordinate name="tc"/>\n'
+            '  <image_texture name="t" filename="gray8.b2im" colorspace="Raw" '
+            'interpolation="closest" extension="black" '
+            'tex_mapping.scale="0.8 0.7 1" tex_mapping.location="-0.1 -0.2 0"/>\n' +
+            c("tc generated", "t vector") +
+            '  <mix name="mx" type="mix" color1="0.12 0.45 0.15" color2="0.8 0.8 0.3"/>\n' +
+            c("t color", "mx fac") +
+            '  <diffuse_bsdf name="d"/>\n' + c("mx color", "d color"), "d bsdf")
+        metal = _node_shader(
+            "metal", '  <texture_coordinate name="tc"/>\n'
+            '  <image_texture name="t" filename="rgba16f.b2im" interpolation="linear" '
+            'extension="periodic" projection="sphere"/>\n' + c("tc generated", "t vector") +
+            '  <principled_bsdf name="p" distribution="GGX" metallic="1.0" specular="0.5"/>\n' +
+            c("t color", "p base_color") + c("t alpha", "p roughness"), "p bsdf")
+        glass = _node_shader(
+            "glass", '  <texture_coordinate name="tc"/>\n'
+            '  <image_texture name="t" filename="tile.&lt;UDIM&gt;.b2im" '
+            'colorspace="sRGB" interpolation="linear" extension="clamp" '
+            'tex_mapping.scale="2.5 1.2 1" tex_mapping.location="-0.1 0 0"/>\n' +
+            c("tc generated", "t vector") +
+            '  <diffuse_bsdf name="d"/>\n' + c("t color", "d color"), "d bsdf")
+    else:
+        images["rgba8.b2im"] = test_image("u8", 29, 31, 4, 11)
+        images["rgba16.b2im"] = test_image("u16", 18, 22, 4, 12)
+        images["gray16.b2im"] = test_image("u16", 16, 16, 1, 13)
+        images["gray32f.b2im"] = test_image("f32", 12, 20, 1, 14)
+        images["gray16f.b2im"] = test_image("f16", 14, 14, 1, 15)
+        images["rgb32f.b2im"] = test_image("f32", 20, 16, 3, 16)
+        white = _node_shader(
+            "white", '  <texture_coordinate name="tc"/>\n'
+            '  <image_texture name="t" filename="rgba8.b2im" colorspace="sRGB" '
+            'alpha_type="channel_packed" interpolation="smart" extension="black" '
+            'tex_mapping.scale="1.3 1.3 1" tex_mapping.location="-0.15 -0.1 0"/>\n' +
+            c("tc generated", "t vector") +
+            '  <mix name="mx" type="mix" color1="0.73 0.73 0.73"/>\n' + c("t color", "mx color2") +
+            c("t alpha", "mx fac") +
+            '  <diffuse_bsdf name="d"/>\n' + c("mx color", "d color"), "d bsdf")
+        red = _node_shader(
+            "red", '  <texture_coordinate name="tc"/>\n'
+            '  <image_texture name="t" filename="rgba16.b2im" colorspace="Raw" '
+            'interpolation="linear" extension="clamp" projection="tube"/>\n' +
+            c("tc generated", "t vector") +
+            '  <image_texture name="t2" filename="gray16.b2im" colorspace="Raw" '
+            'interpolation="cubic" extension="periodic" tex_mapping.scale="3 3 1"/>\n' +
+            c("tc generated", "t2 vector") +
+            '  <mix name="mx" type="multiply" fac="1.0"/>\n' + c("t color", "mx color1") +
+            c("t2 color", "mx color2") +
+            '  <diffuse_bsdf name="d"/>\n' + c("mx color", "d color"), "d bsdf")
+        green = _node_shader(
+            "green", '  <texture_coordinate name="tc"/>\n'
+            '  <image_texture name="t" filename="gray32f.b2im" interpolation="linear" '
+            'extension="black" projection="box" projection_blend="0.0"/>\n' +
+            c("tc object", "t vector") +
+            '  <image_texture name="t2" filename="gray16f.b2im" interpolation="closest" '
+            'extension="periodic" tex_mapping.scale="4 4 1"/>\n' + c("tc generated", "t2 vector") +
+            '  <mix name="mx" type="mix" color1="0.12 0.45 0.15" color2="0.1 0.2 0.6"/>\n' +
+            c("t color", "mx fac") +
+            '  <mix name="mx2" type="multiply" fac="0.7"/>\n' + c("mx color", "mx2 color1") +
+            c("t2 color", "mx2 color2") +
+            '  <diffuse_bsdf name="d"/>\n' + c("mx2 color", "d color"), "d bsdf")
+        metal = _node_shader(
+            "metal", '  <texture_coordinate name="tc"/>\n'
+            '  <image_texture name="t" filename="rgb32f.b2im" colorspace="sRGB" '
+            'interpolation="cubic" extension="black" projection="box" projection_blend="1.0"/>\n' +
+            c("tc object", "t vector") +
+            '  <principled_bsdf name="p" distribution="GGX" metallic="0.6" roughness="0.3" '
+            'specular="0.5"/>\n' + c("t color", "p base_color"), "p bsdf")
+        glass = _node_shader(
+            "glass", '  <texture_coordinate name="tc"/>\n'
+            '  <image_texture name="t" filename="rgba8.b2im" colorspace="sRGB" '
+            'alpha_type="ignore" interpolation="closest" extension="clamp"/>\n' +
+            c("tc uv", "t vector") +
+            '  <image_texture name="missing" filename="does_not_exist.b2im"/>\n' +
+            c("tc uv", "missing vector") +
+            '  <mix name="mx" type="mix" fac="0.25"/>\n' + c("t color", "mx color1") +
+            c("missing color", "mx color2") +
+            '  <diffuse_bsdf name="d"/>\n' + c("mx color", "d color"), "d bsdf")
+    tiles = [("glass", "t", [1001, 1002])] if variant == 0 else []
+    return white + red + green + metal + glass, images, tiles
+
+
 def _integrator(max_bounce, diffuse=None, glossy=None, transmission=None, transparent=8,
                 clamp_indirect=0.0, seed=0, light_threshold=0.01, caustics=True,
                 pattern="sobol", aa_samples=0):
@@ -574,13 +733,17 @@ def box_mesh(lo, hi):
 
 # ---------------------------------------------------------------- config 1
 def default_cube(width=1920, height=1080, spp=64, material="principled", max_bounce=12,
-                 lights="point", cam_type="perspective", cam_extra="", distribution="GGX"):
+                 lights="point", cam_type="perspective", cam_extra="", distribution="GGX",
+                 world="grey"):
     """BASELINE config 1 - Blender's startup scene, values extracted from
     release/datafiles/startup.blend.  `lights`: "point" (the
     startup scene), "falloff" (its lamp shader goes through a Light Falloff node), "spot"
     (the same lamp as a 50 degree spot aimed at the cube, soft
     edge) or "mixed" (point + round area + sun: three entries in the light
-    distribution) - variants used by the parity tests only."""
+    distribution) - variants used by the parity tests only.  `world`: "grey" (the
+    startup scene), "env_equirect" / "env_mirrorball" (an Environment Texture node lights
+    the scene: a float image looked up by the ray direction; no background importance
+    sampling, which would need a background light)."""
     cam = euler_xyz_camera((7.358891, -6.925791, 4.958309), (1.109319, 0.0, 0.814928))
     fov = 2.0 * np.arctan(0.5 * 36.0 / 50.0 / (width / height))
     xml = "<cycles>\n"
@@ -589,7 +752,20 @@ def default_cube(width=1920, height=1080, spp=64, material="principled", max_bou
         _integrator(max_bounce, diffuse=min(4, max_bounce), glossy=min(4, max_bounce),
                     transmission=max_bounce, clamp_indirect=10.0),
         nearclip=0.1, farclip=100.0, cam_type=cam_type, cam_extra=cam_extra)
-    xml += _background((0.05087609, 0.05087609, 0.05087609))
+    images = {}
+    if world == "grey":
+        xml += _background((0.05087609, 0.05087609, 0.05087609))
+    else:
+        images["env.b2im"] = test_image("f32", 48, 24, 3, 21)
+        xml += ("<background>\n"
+                '  <environment_texture name="env" filename="env.b2im" interpolation="%s" '
+                'projection="%s"/>\n'
+                '  <background name="bg" strength="0.6"/>\n'
+                '  <connect from="env color" to="bg color"/>\n'
+                '  <connect from="bg background" to="output surface"/>\n'
+                "</background>\n"
+                % (("linear", "equirectangular") if world == "env_equirect" else
+                   ("cubic", "mirror_ball")))
     if material == "principled":
         xml += _principled_shader("cube", (0.8, 0.8, 0.8), 0.0, 0.5, 0.5,
                                   distribution=distribution)
@@ -628,10 +804,11 @@ def default_cube(width=1920, height=1080, spp=64, material="principled", max_bou
     P, tris = box_mesh((-1, -1, -1), (1, 1, 1))
     multi = "_multiscatter" if (material == "principled" and distribution != "GGX") else ""
     return SceneDesc(
-        "default_cube_" + material + multi + ("" if lights == "point" else "_" + lights), xml,
+        "default_cube_" + material + multi + ("" if lights == "point" else "_" + lights) +
+        ("" if world == "grey" else "_" + world), xml,
         width, height,
         meshes=[MeshDesc(P, tris, "cube")], objects=[(0, np.eye(4, dtype=np.float32)[:3])],
-        spp=spp, notes="config 1")
+        spp=spp, notes="config 1", images=images)
 
 
 # ---------------------------------------------------------------- config 2
@@ -721,8 +898,13 @@ def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
     xml += _background((0, 0, 0), 0.0, "" if ao is None else
                        ' use_ao="true" ao_factor="%s" ao_distance="%s"' % (_f(ao[0]), _f(ao[1])))
     closure_variants = {"closures": 0, "closures2": 1, "transparent_opaque_shadow": 2,
-                        "transparent": 3, "closures_multi": 4, "textured": 10, "textured2": 11, "textured3": 12, "textured4": 13}
-    if materials in ("textured", "textured2", "textured3", "textured4"):
+                        "transparent": 3, "closures_multi": 4, "textured": 10, "textured2": 11,
+                        "textured3": 12, "textured4": 13, "image": 20, "image2": 21}
+    images, image_tiles = {}, []
+    if materials in ("image", "image2"):
+        shaders, images, image_tiles = _image_shaders(closure_variants[materials] - 20)
+        xml += shaders
+    elif materials in ("textured", "textured2", "textured3", "textured4"):
         xml += _textured_shaders(closure_variants[materials] - 10)
     elif materials in closure_variants:
         xml += _closure_shaders(closure_variants[materials])
@@ -806,7 +988,8 @@ def cornell(width=1920, height=1080, spp=512, max_bounce=8, distribution="GGX",
     multi = "_multiscatter" if (materials in ("principled", "metal", "glass") and
                                 distribution != "GGX") else ""
     return SceneDesc("cornell_" + materials + multi + ("" if light == "area" else "_" + light),
-                     xml, width, height, meshes=meshes, objects=objects, spp=spp, notes="config 3")
+                     xml, width, height, meshes=meshes, objects=objects, spp=spp, notes="config 3",
+                     images=images, image_tiles=image_tiles)
 
 
 # ---------------------------------------------------------------- config 4

@@ -33,6 +33,7 @@ static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f
 #include "../../raytracingproject_b200/csrc/svm_closure.cuh"
 #include "../../raytracingproject_b200/csrc/svm_nodes.cuh"
 #include "../../raytracingproject_b200/csrc/svm_tex.cuh"
+#include "../../raytracingproject_b200/csrc/svm_image.cuh"
 
 struct HostShadingPoint {
   float P[3], N[3], I[3], dPdu[3];
@@ -43,6 +44,9 @@ struct HostShadingPoint {
 struct HostSceneArrays {
   const void *svm_nodes, *objects, *tri_vindex, *lights, *shaders, *attributes_map, *attributes_float,
       *attributes_float2, *attributes_float3, *attributes_uchar4, *kernel_data;
+  /* image textures: TextureInfo records whose `data` are host addresses */
+  const void *texture_info;
+  uint64_t num_textures;
 };
 
 extern "C" __attribute__((visibility("default"))) void host_svm_bind(const HostSceneArrays *a)
@@ -58,6 +62,8 @@ extern "C" __attribute__((visibility("default"))) void host_svm_bind(const HostS
   g_scene.attributes_float2 = (const float2 *)a->attributes_float2;
   g_scene.attributes_float3 = (const float4 *)a->attributes_float3;
   g_scene.attributes_uchar4 = (const uchar4 *)a->attributes_uchar4;
+  g_scene.texture_info = (const uint8_t *)a->texture_info;
+  g_scene.num_textures = (uint32_t)a->num_textures;
   if (a->kernel_data)
     memcpy(g_scene.kdata, a->kernel_data, SIZEOF_KERNEL_DATA);
 }
@@ -206,6 +212,15 @@ extern "C" __attribute__((visibility("default"))) int host_svm_node(int offset, 
       break;
     case CY_NODE_CLAMP:
       svm_node_clamp(stack, node, &offset);
+      break;
+    case CY_NODE_TEX_IMAGE:
+      offset = svm_node_tex_image(stack, node, offset);
+      break;
+    case CY_NODE_TEX_IMAGE_BOX:
+      svm_node_tex_image_box(sd, stack, node);
+      break;
+    case CY_NODE_TEX_ENVIRONMENT:
+      svm_node_tex_environment(stack, node);
       break;
     default:
       return -1;

@@ -111,6 +111,20 @@ def texture_cases():
     }
 
 
+def image_cases():
+    """Image textures (svm_image.cuh): byte / ushort / half / float images with one and
+    four channels, closest / linear / cubic lookups, repeat / extend / clip, flat / box /
+    sphere / tube projections, sRGB decompression, alpha handling, UDIM tiles, a missing
+    image - and the Environment Texture node lighting the startup scene."""
+    return {
+        "cornell_image": scenes.cornell(W, H, materials="image"),
+        "cornell_image2": scenes.cornell(W, H, materials="image2"),
+        "cube_env_equirect": scenes.default_cube(W, H, world="env_equirect"),
+        "cube_env_mirrorball": scenes.default_cube(W, H, world="env_mirrorball",
+                                                   material="diffuse"),
+    }
+
+
 def ao_cases():
     """World ambient occlusion (kernel_path_ao): a second shadow ray per path and bounce,
     cosine-sampled around the averaged diffuse normal, short and long reach."""

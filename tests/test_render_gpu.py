@@ -6,8 +6,8 @@ gates hold at any spp, not only at 1024."""
 import numpy as np
 import pytest
 
-from scene_cases import (ao_cases, camera_cases, closure_cases, light_cases, principled_cases,
-                         sampling_cases, small_cases, texture_cases)
+from scene_cases import (ao_cases, camera_cases, closure_cases, image_cases, light_cases,
+                         principled_cases, sampling_cases, small_cases, texture_cases)
 
 pytestmark = pytest.mark.gpu
 
@@ -146,6 +146,56 @@ def test_texture_nodes_match_reference(ref, device, name):
         assert ref_img[..., :3].max() > 0.0
         assert device.stats()["svm_extended"] == 1  # the full-interpreter kernels ran
         image_gates(ref_img, got, SPP, name)
+    finally:
+        rs.close()
+
+
+@pytest.mark.parametrize("name", ["cornell_image", "cornell_image2", "cube_env_equirect",
+                                  "cube_env_mirrorball"])
+def test_image_textures_match_reference(ref, device, name):
+    """Image / Environment Texture nodes: the images the reference's ImageManager loaded
+    are bound per slot (tex_alloc -> b200_texture_set) and sampled with the CPU device's
+    arithmetic.  Through the Python mirror, and through the C++ shim with the reference's
+    own ImageManager handing the device_texture to Device::mem_copy_to."""
+    from raytracingproject_b200.device import B200HostDevice
+    desc = image_cases()[name]
+    rs = ref.build_scene(desc)
+    try:
+        textures = rs.textures()
+        assert textures
+        device.upload_scene(rs.device_arrays(), textures)
+        ref_img, _ = rs.render(0, SPP, tile_size=64)
+        got = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP).copy()
+        assert ref_img[..., :3].max() > 0.0
+        assert device.stats()["svm_extended"] == 1
+        image_gates(ref_img, got, SPP, name)
+    finally:
+        rs.close()
+    host = B200HostDevice(0)
+    try:
+        rs = ref.build_scene(desc, external_device=host.ptr)
+        try:
+            shim, _ = rs.render(0, SPP, tile_size=0)
+            assert host.error_message() == ""
+            assert np.array_equal(shim, got), ("C++ shim and Python mirror disagree",
+                                               float(np.abs(shim - got).max()),
+                                               int((shim != got).any(axis=-1).sum()))
+        finally:
+            rs.close()
+    finally:
+        host.close()
+
+
+def test_program_with_image_nodes_needs_bound_images(ref, device):
+    """A compiled program that names image slots while none is bound is refused, not
+    rendered with missing textures."""
+    from raytracingproject_b200.device import DeviceError
+    desc = image_cases()["cornell_image"]
+    rs = ref.build_scene(desc)
+    try:
+        device.upload_scene(rs.device_arrays())        # no textures
+        with pytest.raises(DeviceError, match="image"):
+            device.render(desc.width, desc.height, rs.pass_stride, 0, 1)
     finally:
         rs.close()
 

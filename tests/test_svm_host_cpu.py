@@ -54,14 +54,27 @@ class Bound:
               "attributes_float", "attributes_float2", "attributes_float3",
               "attributes_uchar4", "kernel_data"]
 
-    def __init__(self, L, arrays, nodes):
+    def __init__(self, L, arrays, nodes, textures=()):
         self.keep = {"svm_nodes": nodes}
         for f in self.FIELDS[1:]:
             name = "__data" if f == "kernel_data" else "__" + f
             if name in arrays:
                 self.keep[f] = np.ascontiguousarray(arrays[name][0])
-        ptrs = (C.c_void_p * len(self.FIELDS))(
-            *[self.keep[f].ctypes.data if f in self.keep else None for f in self.FIELDS])
+        # image slots: the reference's TextureInfo records, `data` = where the host copy of
+        # the pixels lives (what B200Device.tex_alloc does with a device address)
+        from raytracingproject_b200.device import SIZEOF_TEXTURE_INFO
+        n_tex = 1 + max([slot for slot, _, _ in textures], default=-1)
+        table = np.zeros((n_tex, SIZEOF_TEXTURE_INFO), np.uint8)
+        self.pixels = []
+        for slot, info, pix in textures:
+            pix = np.ascontiguousarray(pix)
+            self.pixels.append(pix)
+            table[slot] = info
+            table[slot, :8] = np.array([pix.ctypes.data], np.uint64).view(np.uint8)
+        self.keep["texture_info"] = table
+        ptrs = (C.c_void_p * (len(self.FIELDS) + 2))(
+            *([self.keep[f].ctypes.data if f in self.keep else None for f in self.FIELDS] +
+              [table.ctypes.data if n_tex else None, n_tex]))
         L.host_svm_bind(ptrs)
 
 
@@ -116,7 +129,8 @@ def texture_ops():
                               "NODE_VECTOR_MATH", "NODE_CONVERT", "NODE_INVERT", "NODE_GAMMA",
                               "NODE_BRIGHTCONTRAST", "NODE_CLAMP", "NODE_FRESNEL",
                               "NODE_LAYER_WEIGHT", "NODE_RGB_RAMP", "NODE_RGB_CURVES",
-                              "NODE_VECTOR_CURVES")}
+                              "NODE_VECTOR_CURVES", "NODE_TEX_IMAGE", "NODE_TEX_IMAGE_BOX",
+                              "NODE_TEX_ENVIRONMENT")}
 
 
 def compare(name, s_ref, s_dev, tol):
@@ -126,17 +140,22 @@ def compare(name, s_ref, s_dev, tol):
 
 @pytest.mark.parametrize("materials", ["textured", "textured2", "textured3", "textured4",
                                        "procedural",
-                                       "node_chart"])
+                                       "node_chart", "image", "image2", "env_equirect",
+                                       "env_mirrorball"])
 def test_compiled_texture_nodes_match_reference(ref, host_lib, materials):
-    desc = scenes.node_chart() if materials == "node_chart" else \
-        scenes.cornell(64, 48, spp=1, materials=materials)
+    if materials == "node_chart":
+        desc = scenes.node_chart()
+    elif materials.startswith("env_"):
+        desc = scenes.default_cube(64, 48, spp=1, world=materials)
+    else:
+        desc = scenes.cornell(64, 48, spp=1, materials=materials)
     rs = ref.build_scene(desc)
     try:
         arrays = rs.device_arrays()
         nodes = np.zeros((arrays["__svm_nodes"][0].size // 16 + 8, 4), np.uint32)
         real = arrays["__svm_nodes"][0].view(np.uint32).reshape(-1, 4)
         nodes[: len(real)] = real
-        bound = Bound(host_lib, arrays, nodes)
+        bound = Bound(host_lib, arrays, nodes, rs.textures())
         ops = texture_ops()
         a = abi()
         rng = np.random.default_rng(7)
@@ -172,6 +191,10 @@ def test_compiled_texture_nodes_match_reference(ref, host_lib, materials):
                 if surface_only and pts["object"][i] < 0:
                     continue  # off a surface the reference transforms by an unset matrix
                 stack0 = rng.uniform(-2.0, 2.0, 264).astype(np.float32)
+                if i % 4 == 0 and ops[op] in ("NODE_TEX_IMAGE", "NODE_TEX_IMAGE_BOX"):
+                    # lookups near and across the image borders and the texel centres
+                    stack0 = np.round(stack0 * 8.0) / 16.0 + np.float32(rng.choice(
+                        [0.0, 1e-7, -1e-7, 0.5 / 16, 1.0]))
                 n_ref, n_dev, s_ref, s_dev = run_both(host_lib, rs, nodes, off, stack0,
                                                       pts[i:i + 1])
                 assert n_ref == n_dev and n_ref > off, (ops[op], off, n_ref, n_dev)
@@ -194,7 +217,11 @@ def test_compiled_texture_nodes_match_reference(ref, host_lib, materials):
                 "procedural": {"NODE_MATH", "NODE_VECTOR_MATH", "NODE_MIX", "NODE_CLAMP",
                                "NODE_GAMMA", "NODE_INVERT", "NODE_BRIGHTCONTRAST",
                                "NODE_FRESNEL", "NODE_LAYER_WEIGHT"},
-                "node_chart": {"NODE_MATH", "NODE_VECTOR_MATH", "NODE_MIX"}}[materials]
+                "node_chart": {"NODE_MATH", "NODE_VECTOR_MATH", "NODE_MIX"},
+                "image": {"NODE_TEX_IMAGE", "NODE_TEX_IMAGE_BOX", "NODE_TEX_COORD"},
+                "image2": {"NODE_TEX_IMAGE", "NODE_TEX_IMAGE_BOX"},
+                "env_equirect": {"NODE_TEX_ENVIRONMENT"},
+                "env_mirrorball": {"NODE_TEX_ENVIRONMENT"}}[materials]
         assert want <= set(seen), sorted(want - set(seen))
         del bound
     finally:
