@@ -559,8 +559,12 @@ def run_b200(args):
             try:
                 from raytracingproject_b200.device import B200HostDevice
                 host = B200HostDevice(local)
+                t_host = time.perf_counter()
                 rs_gpu = cycles_ref.build_scene(desc, external_device=host.ptr)
+                t_host = time.perf_counter() - t_host
                 rs_gpu.render(0, spp, tile_size=0)
+                bvh_dev = host.bvh_info()
+                _, pack_s, _ = host.host_bvh8_report()
                 t0 = time.perf_counter()
                 p_rays = 0
                 for _ in range(e2e_steps):
@@ -572,7 +576,17 @@ def run_b200(args):
                     "value": p_rays / p_sec / 1e6, "unit": "Mrays/s",
                     "ms_per_step": 1e3 * p_sec / e2e_steps, "h2d_bytes_per_step": 64,
                     "d2h_bytes_per_step": int(host_film.numel() * 4),
-                    "api": "reference Scene + DeviceTask::RENDER -> C++ B200Device -> C ABI"}
+                    "api": "reference Scene + DeviceTask::RENDER -> C++ B200Device -> C ABI",
+                    # BVH as a host layout of the reference: Scene::device_update builds the
+                    # SAH binary tree, BVH8::pack_nodes (csrc/bvh8_host.cpp) collapses it and
+                    # hands the device ITS arrays - the whole host BVH cost is inside
+                    # scene_update_s, nothing is built on the device (host_packed = 1)
+                    "host_bvh": {"layout": "BVH_LAYOUT_BVH8" if bvh_dev["host_packed"]
+                                 else "BVH_LAYOUT_BVH2 + device-side collapse",
+                                 "scene_update_s": t_host,
+                                 "bvh8_pack_nodes_s": pack_s if bvh_dev["host_packed"] else None,
+                                 "device_build_ms": bvh_dev["build_ms"],
+                                 "nodes": bvh_dev["num_nodes"]}}
                 rs_gpu.close()
                 host.close()
             except Exception as exc:  # the shim needs the reference headers to be built

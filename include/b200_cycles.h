@@ -96,7 +96,58 @@ typedef struct b200_bvh_info {
   double build_ms;
   float sah_cost;
   uint32_t max_depth;
+  uint32_t host_packed; /* 1: the host bound BVH8 arrays (layout below), nothing was built here */
+  uint32_t pad;
 } b200_bvh_info;
+
+/* The device's own host BVH layout - what `BVH_LAYOUT_BVH8` is in the reference's
+ * BVHLayout enum once the patch of INTEGRATION.md section 2 is applied
+ * (kernel/kernel_types.h:1396-1406; BVH_LAYOUT_BVH2/EMBREE/OPTIX are bits 0..2).
+ * With KernelData.bvh.bvh_layout == B200_BVH_LAYOUT_BVH8 the host's `BVH8 : BVH`
+ * (csrc/bvh8_host.cpp, standing where bvh/bvh2.cpp stands) has packed
+ *   __bvh_nodes       the 80-byte BVH8 nodes (five uint4 each, csrc/bvh8.h)
+ *   __bvh_leaf_nodes  the 48-byte leaf records (three float4 each)
+ *   KernelData.bvh.root = the BVH8 root, __object_node = BVH8 root of each object's BLAS
+ * and the device traverses them as bound: no BVH2 reaches the device and nothing is built
+ * at bind time.  With BVH_LAYOUT_BVH2 (an unpatched host) the device derives the same
+ * BVH8 from the packed binary tree itself (b200_build_bvh). */
+#define B200_BVH_LAYOUT_BVH2 (1u << 0)
+#define B200_BVH_LAYOUT_BVH8 (1u << 3)
+
+/* Host-only: the reference's packed binary BVH (PackedBVH, bvh/bvh.h:38-77, as
+ * BVH2::pack_nodes leaves it) -> BVH8 nodes + leaf records.  No device, no context: this
+ * is what `BVH8::pack_nodes` calls on the host.  `object_tfm` = 12 floats (3x4, row-major,
+ * Object::tfm) per object.  The output arrays are owned by the library until
+ * b200_bvh8_free.  Returns B200_OK, or B200_ERR_UNSUPPORTED with the reason in `err`
+ * (curve / motion / unaligned nodes, a tree deeper than the traversal stack). */
+typedef struct b200_packed_bvh2 {
+  const void *nodes;           /* PackedBVH::nodes, int4 units */
+  size_t num_nodes_f4;
+  const void *leaf_nodes;      /* PackedBVH::leaf_nodes */
+  size_t num_leaf_nodes_f4;
+  const void *prim_tri_verts;  /* float4 */
+  const void *prim_tri_index;  /* uint */
+  const void *prim_visibility; /* uint */
+  const void *prim_object;     /* int */
+  size_t num_prims;
+  const void *object_node;     /* int per object: root of its BLAS in `nodes` */
+  const float *object_tfm;
+  size_t num_objects;
+  int root;                    /* PackedBVH::root_index */
+} b200_packed_bvh2;
+
+typedef struct b200_packed_bvh8 {
+  void *nodes;          /* 80 bytes each */
+  size_t node_bytes;
+  void *records;        /* 48 bytes each */
+  size_t record_bytes;
+  int *object_node;     /* num_objects entries: BVH8 root of the object's BLAS, -1 if none */
+  uint32_t root;
+  b200_bvh_info info;
+} b200_packed_bvh8;
+
+int b200_bvh8_pack(const b200_packed_bvh2 *in, b200_packed_bvh8 *out, char *err, size_t errlen);
+void b200_bvh8_free(b200_packed_bvh8 *out);
 
 int b200_abi_version(void);
 

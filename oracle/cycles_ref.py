@@ -198,6 +198,23 @@ class RefScene:
         out["__data"] = (self.kernel_data(), 1)
         return out
 
+    def pack_bvh(self, layout):
+        """The scene's top-level BVH packed in `layout` by the reference's own
+        BVH::create / BVH::build (no device): (nodes bytes, leaf_nodes bytes, object_node
+        int32[], root)."""
+        L = self._L
+        L.ref_scene_pack_bvh.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
+        n, nb, l, lb = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
+        o, no, root = C.c_void_p(), C.c_uint64(), C.c_int()
+        self._check(L.ref_scene_pack_bvh(self._h, int(layout), C.byref(n), C.byref(nb),
+                                         C.byref(l), C.byref(lb), C.byref(o), C.byref(no),
+                                         C.byref(root)))
+        grab = lambda p, nbytes: (np.ctypeslib.as_array(
+            (C.c_uint8 * nbytes).from_address(p.value)).copy() if nbytes and p.value
+            else np.zeros(0, np.uint8))
+        return (grab(n, nb.value), grab(l, lb.value),
+                grab(o, no.value * 4).view(np.int32), root.value)
+
     def textures(self):
         """[(slot, TextureInfo bytes, pixel bytes)] - the images the reference's
         ImageManager loaded into its device (CPUDevice::tex_alloc), for

@@ -25,6 +25,8 @@
 #undef device_cpu_capabilities
 
 #include "app/cycles_xml.h"
+#include "bvh/bvh.h"
+#include "bvh/bvh_params.h"
 #include "render/background.h"
 #include "render/buffers.h"
 #include "render/camera.h"
@@ -98,6 +100,7 @@ struct ref_scene {
   RenderBuffers *buffers;
   vector<Mesh *> meshes;
   std::string error;
+  BVH *packed_bvh; /* ref_scene_pack_bvh */
 };
 
 static bool g_sched_init = false;
@@ -146,6 +149,7 @@ ref_scene *ref_scene_new(const char *xml_path, int kernel, void *external_device
   ref_scene *rs = new ref_scene();
   rs->buffers = NULL;
   rs->cpu = NULL;
+  rs->packed_bvh = NULL;
 
   if (external_device) {
     rs->device = (Device *)external_device;
@@ -197,6 +201,7 @@ void ref_scene_free(ref_scene *rs)
   if (!rs)
     return;
   delete rs->buffers;
+  delete rs->packed_bvh;
   delete rs->scene;
   if (rs->own_device)
     delete rs->device;
@@ -438,6 +443,50 @@ int ref_scene_texture(
   *bytes = info.data ? (uint64_t)info.width * info.height * (info.depth > 1 ? info.depth : 1u) *
                            texel_bytes[info.data_type % IMAGE_DATA_NUM_TYPES] :
                        0;
+  return 0;
+}
+
+/* The top-level BVH of the updated scene packed once more in `layout` through the
+ * reference's own BVH::create + BVH::build (the few lines of
+ * GeometryManager::device_update_bvh, render/geometry.cpp:1019-1034) - without a device,
+ * so that a host layout class a device plug-in registered (BVH8, see
+ * raytracingproject_b200/csrc/bvh8_host.cpp) can be checked on a machine without a GPU.
+ * The arrays stay valid until the next call or ref_scene_free. */
+int ref_scene_pack_bvh(ref_scene *rs,
+                       int layout,
+                       const void **nodes,
+                       uint64_t *node_bytes,
+                       const void **leaf_nodes,
+                       uint64_t *leaf_bytes,
+                       const int **object_node,
+                       uint64_t *num_objects,
+                       int *root)
+{
+  Scene *scene = rs->scene;
+  BVHParams bparams;
+  bparams.top_level = true;
+  bparams.bvh_layout = (BVHLayout)layout;
+  bparams.use_spatial_split = scene->params.use_bvh_spatial_split;
+  bparams.use_unaligned_nodes = false;
+  bparams.num_motion_triangle_steps = scene->params.num_bvh_time_steps;
+  bparams.num_motion_curve_steps = scene->params.num_bvh_time_steps;
+  bparams.bvh_type = scene->params.bvh_type;
+  bparams.curve_subdivisions = scene->params.curve_subdivisions();
+  delete rs->packed_bvh;
+  rs->packed_bvh = BVH::create(bparams, scene->geometry, scene->objects);
+  if (!rs->packed_bvh) {
+    rs->error = "BVH::create does not know this layout";
+    return 1;
+  }
+  rs->packed_bvh->build(rs->progress, &rs->stats);
+  PackedBVH &pack = rs->packed_bvh->pack;
+  *nodes = pack.nodes.data();
+  *node_bytes = pack.nodes.size() * sizeof(int4);
+  *leaf_nodes = pack.leaf_nodes.data();
+  *leaf_bytes = pack.leaf_nodes.size() * sizeof(int4);
+  *object_node = pack.object_node.data();
+  *num_objects = pack.object_node.size();
+  *root = pack.root_index;
   return 0;
 }
 

@@ -47,3 +47,40 @@ extern "C" void ref_host_register_cpu_device(void *create, void *info, void *cap
   ccl::g_cpu_info = (ccl::cpu_info_fn)info;
   ccl::g_cpu_capabilities = (ccl::cpu_capabilities_fn)capabilities;
 }
+
+/* ---- BVH layouts added by a device plug-in ----
+ * BVH::create (bvh/bvh.cpp:99-124) knows BVH2 / Embree / OptiX.  The patched copy of
+ * bvh.cpp this library is built with (oracle/Makefile, bvh_layout_hook.sed) asks here
+ * first, so that a device library can bring its own `BVH` subclass the way
+ * device_optix.cpp brings BVHOptiX - without the subclass living in this tree. */
+#include "bvh/bvh.h"
+#include "bvh/bvh_params.h"
+
+CCL_NAMESPACE_BEGIN
+
+typedef BVH *(*bvh_create_fn)(const BVHParams &, const vector<Geometry *> &,
+                              const vector<Object *> &);
+static int g_bvh_hook_layout = 0;
+static bvh_create_fn g_bvh_hook_create = NULL;
+
+BVH *bvh_layout_hook_create(const BVHParams &params,
+                            const vector<Geometry *> &geometry,
+                            const vector<Object *> &objects)
+{
+  if (g_bvh_hook_create && (int)params.bvh_layout == g_bvh_hook_layout)
+    return g_bvh_hook_create(params, geometry, objects);
+  return NULL;
+}
+
+CCL_NAMESPACE_END
+
+extern "C" void ref_host_register_bvh_layout(int layout, void *create)
+{
+  ccl::g_bvh_hook_layout = layout;
+  ccl::g_bvh_hook_create = (ccl::bvh_create_fn)create;
+}
+
+extern "C" int ref_host_has_bvh_layout(int layout)
+{
+  return ccl::g_bvh_hook_create != NULL && ccl::g_bvh_hook_layout == layout;
+}

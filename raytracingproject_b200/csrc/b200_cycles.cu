@@ -569,6 +569,79 @@ int b200_validate_svm(const void *svm_nodes, size_t bytes, char *err, size_t err
   return (svm_nodes && bytes % 16 == 0) ? B200_ERR_UNSUPPORTED : B200_ERR_INVALID;
 }
 
+int b200_bvh8_pack(const b200_packed_bvh2 *in, b200_packed_bvh8 *out, char *err, size_t errlen)
+{
+  if (!in || !out)
+    return B200_ERR_INVALID;
+  memset(out, 0, sizeof(*out));
+  b200::BVH2Input bi;
+  memset(&bi, 0, sizeof(bi));
+  bi.nodes = (const float *)in->nodes;
+  bi.num_nodes_f4 = in->num_nodes_f4;
+  bi.leaf_nodes = (const float *)in->leaf_nodes;
+  bi.num_leaf_nodes_f4 = in->num_leaf_nodes_f4;
+  bi.prim_tri_verts = (const float *)in->prim_tri_verts;
+  bi.prim_tri_index = (const uint32_t *)in->prim_tri_index;
+  bi.prim_visibility = (const uint32_t *)in->prim_visibility;
+  bi.prim_object = (const uint32_t *)in->prim_object;
+  bi.num_prims = in->num_prims;
+  bi.object_node = (const int32_t *)in->object_node;
+  bi.objects = (const uint8_t *)in->object_tfm;
+  bi.object_stride = 12 * sizeof(float);
+  bi.object_tfm_offset = 0;
+  bi.num_objects = in->num_objects;
+  bi.root = in->root;
+  bi.node_unaligned_flag = CY_PATH_RAY_NODE_UNALIGNED;
+  bi.primitive_all = CY_PRIMITIVE_ALL;
+  bi.primitive_triangle = CY_PRIMITIVE_TRIANGLE;
+  b200::BVH8Output bo;
+  std::string why;
+  if (!bi.leaf_nodes || !b200::build_bvh8(bi, bo, why)) {
+    if (why.empty())
+      why = "no packed BVH2 to convert";
+    if (err && errlen) {
+      strncpy(err, why.c_str(), errlen - 1);
+      err[errlen - 1] = 0;
+    }
+    return B200_ERR_UNSUPPORTED;
+  }
+  out->node_bytes = bo.nodes.size() * sizeof(BVH8Node);
+  out->record_bytes = bo.records.size() * sizeof(float);
+  out->nodes = malloc(std::max<size_t>(out->node_bytes, 16));
+  out->records = malloc(std::max<size_t>(out->record_bytes, 16));
+  out->object_node = (int *)malloc(std::max<size_t>(bo.object_root8.size() * sizeof(int), 16));
+  if (!out->nodes || !out->records || !out->object_node) {
+    b200_bvh8_free(out);
+    return B200_ERR_OOM;
+  }
+  memcpy(out->nodes, bo.nodes.data(), out->node_bytes);
+  memcpy(out->records, bo.records.data(), out->record_bytes);
+  memcpy(out->object_node, bo.object_root8.data(), bo.object_root8.size() * sizeof(int));
+  out->root = bo.root;
+  out->info.num_nodes = bo.nodes.size();
+  out->info.num_tri_records = bo.records.size() / 12;
+  out->info.num_triangles = bo.num_triangles;
+  out->info.num_instances = bo.num_instances;
+  out->info.node_bytes = out->node_bytes;
+  out->info.tri_bytes = out->record_bytes;
+  out->info.build_ms = bo.build_ms;
+  out->info.sah_cost = bo.sah_cost;
+  out->info.max_depth = bo.max_depth;
+  out->info.host_packed = 1;
+  return B200_OK;
+}
+
+void b200_bvh8_free(b200_packed_bvh8 *out)
+{
+  if (!out)
+    return;
+  free(out->nodes);
+  free(out->records);
+  free(out->object_node);
+  out->nodes = out->records = nullptr;
+  out->object_node = nullptr;
+}
+
 int b200_set_kernel_data(b200_ctx *ctx, const void *kernel_data, size_t bytes)
 {
   if (!ctx || !kernel_data)
@@ -620,32 +693,6 @@ static int prepare_scene(b200_ctx *ctx)
   if (rc)
     return rc;
 
-  b200::BVH2Input in;
-  memset(&in, 0, sizeof(in));
-  in.nodes = nodes ? (const float *)nodes->host.data() : nullptr;
-  in.num_nodes_f4 = nodes ? nodes->bytes / 16 : 0;
-  in.leaf_nodes = (const float *)leaves->host.data();
-  in.num_leaf_nodes_f4 = leaves->bytes / 16;
-  in.prim_tri_verts = (const float *)verts->host.data();
-  in.prim_tri_index = (const uint32_t *)tri_index->host.data();
-  in.prim_visibility = (const uint32_t *)vis->host.data();
-  in.prim_object = (const uint32_t *)pobj->host.data();
-  in.num_prims = tri_index->bytes / 4;
-  in.object_node = onode ? (const int32_t *)onode->host.data() : nullptr;
-  in.objects = objects->host.data();
-  in.object_stride = SIZEOF_KERNEL_OBJECT;
-  in.object_tfm_offset = KO_TFM;
-  in.num_objects = objects->bytes / SIZEOF_KERNEL_OBJECT;
-  in.root = kd_host<int>(ctx, KD_BVH_ROOT);
-  in.node_unaligned_flag = CY_PATH_RAY_NODE_UNALIGNED;
-  in.primitive_all = CY_PRIMITIVE_ALL;
-  in.primitive_triangle = CY_PRIMITIVE_TRIANGLE;
-
-  b200::BVH8Output out;
-  std::string err;
-  if (!b200::build_bvh8(in, out, err))
-    return fail(ctx, B200_ERR_UNSUPPORTED, "BVH8 build: " + err);
-
   DeviceGuard guard(ctx->ordinal);
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   if (ctx->d_nodes)
@@ -653,29 +700,82 @@ static int prepare_scene(b200_ctx *ctx)
   if (ctx->d_records)
     cudaFree(ctx->d_records);
   ctx->d_nodes = ctx->d_records = nullptr;
-  const size_t node_bytes = out.nodes.size() * sizeof(BVH8Node);
-  const size_t rec_bytes = out.records.size() * sizeof(float);
-  CUDA_TRY(ctx, cudaMalloc(&ctx->d_nodes, std::max<size_t>(node_bytes, 16)));
-  CUDA_TRY(ctx, cudaMalloc(&ctx->d_records, std::max<size_t>(rec_bytes, 16)));
-  CUDA_TRY(ctx, cudaMemcpy(ctx->d_nodes, out.nodes.data(), node_bytes, cudaMemcpyHostToDevice));
-  CUDA_TRY(ctx,
-           cudaMemcpy(ctx->d_records, out.records.data(), rec_bytes, cudaMemcpyHostToDevice));
+  const uint4 *dev_nodes = nullptr;
+  const float4 *dev_records = nullptr;
+  uint32_t bvh_root = 0;
+  const uint32_t layout = (uint32_t)kd_host<int>(ctx, KD_BVH_LAYOUT);
+  if (layout == B200_BVH_LAYOUT_BVH8) {
+    /* the host's BVH8 class packed the device layout: traverse the arrays as bound */
+    if (!nodes || nodes->bytes % sizeof(BVH8Node) != 0 || leaves->bytes % 48 != 0)
+      return fail(ctx, B200_ERR_INVALID, "BVH_LAYOUT_BVH8: __bvh_nodes / __bvh_leaf_nodes are "
+                                         "not whole BVH8 nodes / leaf records");
+    dev_nodes = (const uint4 *)nodes->dptr;
+    dev_records = (const float4 *)leaves->dptr;
+    bvh_root = (uint32_t)kd_host<int>(ctx, KD_BVH_ROOT);
+    if ((size_t)bvh_root >= nodes->bytes / sizeof(BVH8Node))
+      return fail(ctx, B200_ERR_INVALID, "BVH_LAYOUT_BVH8: root outside the node array");
+    memset(&ctx->bvh_info, 0, sizeof(ctx->bvh_info));
+    ctx->bvh_info.num_nodes = nodes->bytes / sizeof(BVH8Node);
+    ctx->bvh_info.num_tri_records = leaves->bytes / 48;
+    ctx->bvh_info.node_bytes = nodes->bytes;
+    ctx->bvh_info.tri_bytes = leaves->bytes;
+    ctx->bvh_info.host_packed = 1;
+  }
+  else {
+    b200::BVH2Input in;
+    memset(&in, 0, sizeof(in));
+    in.nodes = nodes ? (const float *)nodes->host.data() : nullptr;
+    in.num_nodes_f4 = nodes ? nodes->bytes / 16 : 0;
+    in.leaf_nodes = (const float *)leaves->host.data();
+    in.num_leaf_nodes_f4 = leaves->bytes / 16;
+    in.prim_tri_verts = (const float *)verts->host.data();
+    in.prim_tri_index = (const uint32_t *)tri_index->host.data();
+    in.prim_visibility = (const uint32_t *)vis->host.data();
+    in.prim_object = (const uint32_t *)pobj->host.data();
+    in.num_prims = tri_index->bytes / 4;
+    in.object_node = onode ? (const int32_t *)onode->host.data() : nullptr;
+    in.objects = objects->host.data();
+    in.object_stride = SIZEOF_KERNEL_OBJECT;
+    in.object_tfm_offset = KO_TFM;
+    in.num_objects = objects->bytes / SIZEOF_KERNEL_OBJECT;
+    in.root = kd_host<int>(ctx, KD_BVH_ROOT);
+    in.node_unaligned_flag = CY_PATH_RAY_NODE_UNALIGNED;
+    in.primitive_all = CY_PRIMITIVE_ALL;
+    in.primitive_triangle = CY_PRIMITIVE_TRIANGLE;
 
-  ctx->bvh_info.num_nodes = out.nodes.size();
-  ctx->bvh_info.num_tri_records = out.records.size() / 12;
-  ctx->bvh_info.num_triangles = out.num_triangles;
-  ctx->bvh_info.num_instances = out.num_instances;
-  ctx->bvh_info.node_bytes = node_bytes;
-  ctx->bvh_info.tri_bytes = rec_bytes;
-  ctx->bvh_info.build_ms = out.build_ms;
-  ctx->bvh_info.sah_cost = out.sah_cost;
-  ctx->bvh_info.max_depth = out.max_depth;
+    b200::BVH8Output out;
+    std::string err;
+    if (!b200::build_bvh8(in, out, err))
+      return fail(ctx, B200_ERR_UNSUPPORTED, "BVH8 build: " + err);
+
+    const size_t node_bytes = out.nodes.size() * sizeof(BVH8Node);
+    const size_t rec_bytes = out.records.size() * sizeof(float);
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_nodes, std::max<size_t>(node_bytes, 16)));
+    CUDA_TRY(ctx, cudaMalloc(&ctx->d_records, std::max<size_t>(rec_bytes, 16)));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->d_nodes, out.nodes.data(), node_bytes, cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx,
+             cudaMemcpy(ctx->d_records, out.records.data(), rec_bytes, cudaMemcpyHostToDevice));
+    dev_nodes = (const uint4 *)ctx->d_nodes;
+    dev_records = (const float4 *)ctx->d_records;
+    bvh_root = out.root;
+
+    memset(&ctx->bvh_info, 0, sizeof(ctx->bvh_info));
+    ctx->bvh_info.num_nodes = out.nodes.size();
+    ctx->bvh_info.num_tri_records = out.records.size() / 12;
+    ctx->bvh_info.num_triangles = out.num_triangles;
+    ctx->bvh_info.num_instances = out.num_instances;
+    ctx->bvh_info.node_bytes = node_bytes;
+    ctx->bvh_info.tri_bytes = rec_bytes;
+    ctx->bvh_info.build_ms = out.build_ms;
+    ctx->bvh_info.sah_cost = out.sah_cost;
+    ctx->bvh_info.max_depth = out.max_depth;
+  }
 
   DeviceScene ds;
   memset(&ds, 0, sizeof(ds));
-  ds.nodes = (const uint4 *)ctx->d_nodes;
-  ds.records = (const float4 *)ctx->d_records;
-  ds.bvh_root = out.root;
+  ds.nodes = dev_nodes;
+  ds.records = dev_records;
+  ds.bvh_root = bvh_root;
   auto ptr = [&](const char *name) -> uint64_t {
     const HostArray *h = find_global(ctx, name);
     return h ? h->dptr : 0;

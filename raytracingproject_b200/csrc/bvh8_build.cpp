@@ -700,6 +700,14 @@ bool build_bvh8(const BVH2Input &in, BVH8Output &out, std::string &error)
     uint32_t r = b.blas_root8[p.second];
     memcpy(&out.records[p.first], &r, 4);
   }
+  out.object_root8.assign(in.num_objects, -1);
+  if (in.object_node) {
+    for (size_t o = 0; o < in.num_objects; o++) {
+      auto it = b.blas_root8.find(in.object_node[o]);
+      if (it != b.blas_root8.end())
+        out.object_root8[o] = (int32_t)it->second;
+    }
+  }
   /* The traversal stack (BVH8_STACK_SIZE = 64 entries, traverse.cuh) holds at most two
    * entries per level of the TLAS and of one BLAS plus two for the instance push; a
    * tree deeper than this bound (a degenerate BVH2 chain) is refused, not truncated. */

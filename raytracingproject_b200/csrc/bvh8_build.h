@@ -38,6 +38,8 @@ struct BVH8Output {
   /* (index into records of the blas-root word, BVH2 root it refers to) */
   std::vector<std::pair<size_t, int32_t>> instance_patches;
   uint32_t root = 0;
+  /* per object: BVH8 root of its BLAS, -1 for objects that are not instanced */
+  std::vector<int32_t> object_root8;
   uint64_t num_triangles = 0, num_instances = 0;
   uint32_t max_depth = 0;
   float sah_cost = 0.0f;

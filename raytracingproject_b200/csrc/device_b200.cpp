@@ -19,9 +19,11 @@
  *   - task_add(RENDER) does not block: a DedicatedTaskPool worker runs the
  *     acquire_tile / render / release_tile loop of CUDADevice::thread_run
  *     (device_cuda_impl.cpp:2342-2390); FILM_CONVERT runs on the caller;
- *   - get_bvh_layout_mask() asks the host for the packed BVH2 arrays, from which
- *     the device builds its own compressed BVH8 (as OptiX builds its own
- *     structure in build_optix_bvh, device_optix.cpp:1199).
+ *   - get_bvh_layout_mask() asks the host for BVH_LAYOUT_BVH8, the device's own layout,
+ *     packed on the host by `BVH8 : BVH` (bvh8_host.cpp) - when the host application
+ *     knows that layout.  An unpatched host is asked for the
+ *     packed BVH2 arrays instead, from which the device derives the same BVH8 itself (as
+ *     OptiX builds its own structure in build_optix_bvh, device_optix.cpp:1199).
  */
 #include "device/device.h"
 #include "device/device_intern.h"
@@ -36,6 +38,26 @@
 #include "util/util_time.h"
 
 #include "../../include/b200_cycles.h"
+
+/* oracle/ref_host_hooks.cpp in this repo's host library; in a patched reference tree the
+ * layout is simply part of BVH::create */
+extern "C" int ref_host_has_bvh_layout(int layout);
+
+CCL_NAMESPACE_BEGIN
+string bvh8_last_error();                                        /* bvh8_host.cpp */
+void bvh8_last_info(b200_bvh_info *info, double *pack_seconds);
+
+/* B200_HOST_BVH=bvh2 keeps the device-side derivation even on a host that knows BVH8 (A/B
+ * and parity of the two routes) */
+static BVHLayoutMask b200_bvh_layout_mask()
+{
+  const char *force = getenv("B200_HOST_BVH");
+  if (force && strcmp(force, "bvh2") == 0)
+    return BVH_LAYOUT_BVH2;
+  return ref_host_has_bvh_layout((int)B200_BVH_LAYOUT_BVH8) ? (BVHLayoutMask)B200_BVH_LAYOUT_BVH8 :
+                                                              (BVHLayoutMask)BVH_LAYOUT_BVH2;
+}
+CCL_NAMESPACE_END
 
 CCL_NAMESPACE_BEGIN
 
@@ -86,14 +108,16 @@ class B200Device : public Device {
   {
     if (rc == B200_OK)
       return true;
-    set_error(string_printf("B200 device: %s failed: %s", what, b200_last_error(ctx)));
+    const string bvh_error = bvh8_last_error();
+    set_error(string_printf("B200 device: %s failed: %s%s%s", what, b200_last_error(ctx),
+                            bvh_error.empty() ? "" : " (host BVH8 pack: ",
+                            bvh_error.empty() ? "" : (bvh_error + ")").c_str()));
     return false;
   }
 
   virtual BVHLayoutMask get_bvh_layout_mask() const
   {
-    /* The device consumes the host's packed BVH2 and derives its BVH8 from it. */
-    return BVH_LAYOUT_BVH2;
+    return b200_bvh_layout_mask();
   }
 
   virtual bool load_kernels(const DeviceRequestedFeatures & /*requested_features*/)
@@ -371,7 +395,7 @@ class B200MultiDevice : public Device {
 
   virtual BVHLayoutMask get_bvh_layout_mask() const
   {
-    return BVH_LAYOUT_BVH2;
+    return b200_bvh_layout_mask();
   }
   virtual bool load_kernels(const DeviceRequestedFeatures &)
   {
@@ -737,6 +761,33 @@ void *b200_host_multi_device_create(const int *ordinals, int n, char *err, size_
 void *b200_host_device_ptr(void *handle)
 {
   return handle ? (void *)((b200_host_device *)handle)->any() : NULL;
+}
+
+/* Report of the last top-level BVH8 the host class packed (bvh8_host.cpp) and the seconds
+ * BVH8::pack_nodes spent on the 2 -> 8 collapse; `err` receives the reason when the last
+ * pack was refused. */
+int b200_host_bvh8_report(b200_bvh_info *info, double *pack_seconds, char *err, size_t errlen)
+{
+  if (!info || !pack_seconds)
+    return B200_ERR_INVALID;
+  ccl::bvh8_last_info(info, pack_seconds);
+  if (err && errlen) {
+    const std::string e = ccl::bvh8_last_error();
+    strncpy(err, e.c_str(), errlen - 1);
+    err[errlen - 1] = 0;
+  }
+  return B200_OK;
+}
+
+/* The BVH the device traverses for the scene bound last (b200_build_bvh on the first
+ * context): host_packed = 1 when the host's BVH8 class delivered the device layout. */
+int b200_host_device_bvh_info(void *handle, b200_bvh_info *out)
+{
+  if (!handle || !out)
+    return B200_ERR_INVALID;
+  b200_host_device *h = (b200_host_device *)handle;
+  b200_ctx *ctx = h->device ? h->device->ctx : (h->multi->ctxs.empty() ? NULL : h->multi->ctxs[0]);
+  return ctx ? b200_build_bvh(ctx, out) : B200_ERR_INVALID;
 }
 
 int b200_host_device_stats(void *handle, b200_stats *out)

@@ -38,8 +38,10 @@ EXPORTS = [
     "b200_trace_batch", "b200_film_convert", "b200_film_reduce", "b200_get_stats",
     "b200_synchronize", "b200_set_option", "b200_set_stream", "b200_debug_read",
     "b200_validate_svm", "b200_device_pci_id", "b200_set_cancel_callback", "b200_film_allreduce",
-    "b200_texture_set", "b200_texture_clear",
+    "b200_texture_set", "b200_texture_clear", "b200_bvh8_pack", "b200_bvh8_free",
 ]
+
+BVH_LAYOUT_BVH2, BVH_LAYOUT_BVH8 = 1 << 0, 1 << 3  # kernel_types.h BVHLayout + INTEGRATION.md
 
 
 class WorkTile(C.Structure):
@@ -70,10 +72,29 @@ class BVHInfo(C.Structure):
     _fields_ = [("num_nodes", C.c_uint64), ("num_tri_records", C.c_uint64),
                 ("num_triangles", C.c_uint64), ("num_instances", C.c_uint64),
                 ("node_bytes", C.c_uint64), ("tri_bytes", C.c_uint64),
-                ("build_ms", C.c_double), ("sah_cost", C.c_float), ("max_depth", C.c_uint32)]
+                ("build_ms", C.c_double), ("sah_cost", C.c_float), ("max_depth", C.c_uint32),
+                ("host_packed", C.c_uint32), ("pad", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class PackedBVH2(C.Structure):
+    """b200_packed_bvh2: the reference's PackedBVH arrays as BVH2::pack_nodes leaves them."""
+    _fields_ = [("nodes", C.c_void_p), ("num_nodes_f4", C.c_size_t),
+                ("leaf_nodes", C.c_void_p), ("num_leaf_nodes_f4", C.c_size_t),
+                ("prim_tri_verts", C.c_void_p), ("prim_tri_index", C.c_void_p),
+                ("prim_visibility", C.c_void_p), ("prim_object", C.c_void_p),
+                ("num_prims", C.c_size_t), ("object_node", C.c_void_p),
+                ("object_tfm", C.c_void_p), ("num_objects", C.c_size_t), ("root", C.c_int)]
+
+
+class PackedBVH8(C.Structure):
+    _fields_ = [("nodes", C.c_void_p), ("node_bytes", C.c_size_t),
+                ("records", C.c_void_p), ("record_bytes", C.c_size_t),
+                ("object_node", C.POINTER(C.c_int)), ("root", C.c_uint32),
+                ("info", BVHInfo)]
+
 
 
 _lib = None
@@ -117,6 +138,9 @@ def load_library():
     L.b200_set_cancel_callback.argtypes = [vp, vp, vp]
     L.b200_texture_set.argtypes = [vp, C.c_int, vp, sz, u64]
     L.b200_texture_clear.argtypes = [vp, C.c_int]
+    L.b200_bvh8_pack.argtypes = [C.POINTER(PackedBVH2), C.POINTER(PackedBVH8), C.c_char_p, sz]
+    L.b200_bvh8_free.argtypes = [C.POINTER(PackedBVH8)]
+    L.b200_bvh8_free.restype = None
     L.b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.b200_synchronize.argtypes = [vp]
     L.b200_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
@@ -125,6 +149,49 @@ def load_library():
     L.b200_validate_svm.argtypes = [vp, sz, C.c_char_p, sz]
     _lib = L
     return L
+
+
+def pack_bvh8(arrays, object_tfm=None):
+    """Host-only b200_bvh8_pack over {kernel array name: (bytes, elem size)} holding the
+    reference's packed BVH2 (RefScene.device_arrays()): what `BVH8::pack_nodes` does on
+    the host.  Returns (nodes bytes, records bytes, object_node int32[], root, info)."""
+    import re
+    L = load_library()
+    g = lambda n: np.ascontiguousarray(arrays[n][0]) if n in arrays else np.zeros(0, np.uint8)
+    keep = {n: g(n) for n in ("__bvh_nodes", "__bvh_leaf_nodes", "__prim_tri_verts",
+                              "__prim_tri_index", "__prim_visibility", "__prim_object",
+                              "__object_node", "__objects", "__data")}
+    p = lambda n: keep[n].ctypes.data if keep[n].size else None
+    abi = open(os.path.join(os.path.dirname(_HERE), "include", "cycles_abi.h")).read()
+    num = lambda k: int(re.search(r"#define %s\s+(\d+)" % k, abi).group(1))
+    n_obj = keep["__objects"].size // num("SIZEOF_KERNEL_OBJECT")
+    if object_tfm is None and n_obj == 0:
+        object_tfm = np.zeros(0, np.float32)
+    if object_tfm is None:  # KernelObject::tfm, the first 48 bytes of each record
+        rec = keep["__objects"].reshape(n_obj, -1)
+        object_tfm = np.ascontiguousarray(rec[:, num("KO_TFM"):num("KO_TFM") + 48]).view(np.float32)
+    object_tfm = np.ascontiguousarray(object_tfm, np.float32)
+    src = PackedBVH2(p("__bvh_nodes"), keep["__bvh_nodes"].size // 16,
+                     p("__bvh_leaf_nodes"), keep["__bvh_leaf_nodes"].size // 16,
+                     p("__prim_tri_verts"), p("__prim_tri_index"), p("__prim_visibility"),
+                     p("__prim_object"), keep["__prim_tri_index"].size // 4,
+                     p("__object_node"), object_tfm.ctypes.data if object_tfm.size else None,
+                     min(n_obj, keep["__object_node"].size // 4),
+                     int(keep["__data"][num("KD_BVH_ROOT"):num("KD_BVH_ROOT") + 4].view(np.int32)[0]))
+    out = PackedBVH8()
+    err = C.create_string_buffer(512)
+    rc = L.b200_bvh8_pack(C.byref(src), C.byref(out), err, len(err))
+    if rc != 0:
+        raise DeviceError("b200_bvh8_pack: " + err.value.decode())
+    try:
+        nodes = np.ctypeslib.as_array((C.c_uint8 * out.node_bytes).from_address(out.nodes)).copy()
+        recs = np.ctypeslib.as_array(
+            (C.c_uint8 * out.record_bytes).from_address(out.records)).copy() \
+            if out.record_bytes else np.zeros(0, np.uint8)
+        onode = np.array([out.object_node[i] for i in range(src.num_objects)], np.int32)
+        return nodes, recs, onode, int(out.root), out.info.as_dict()
+    finally:
+        L.b200_bvh8_free(C.byref(out))
 
 
 class DeviceError(RuntimeError):
@@ -434,6 +501,9 @@ class B200HostDevice:
         S.b200_host_device_error.restype = C.c_char_p
         S.b200_host_device_error.argtypes = [C.c_void_p]
         S.b200_host_device_destroy.argtypes = [C.c_void_p]
+        S.b200_host_device_bvh_info.argtypes = [C.c_void_p, C.POINTER(BVHInfo)]
+        S.b200_host_bvh8_report.argtypes = [C.POINTER(BVHInfo), C.POINTER(C.c_double),
+                                            C.c_char_p, C.c_size_t]
         self._S = S
         S.b200_host_multi_device_create.restype = C.c_void_p
         S.b200_host_multi_device_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_char_p,
@@ -458,6 +528,22 @@ class B200HostDevice:
 
     def error_message(self):
         return self._S.b200_host_device_error(self._h).decode()
+
+    def bvh_info(self):
+        """The BVH the device traverses for the scene bound last; host_packed = 1 when the
+        host's `BVH8 : BVH` delivered it (BVH_LAYOUT_BVH8), 0 when the device derived it
+        from packed BVH2 arrays."""
+        info = BVHInfo()
+        rc = self._S.b200_host_device_bvh_info(self._h, C.byref(info))
+        if rc != 0:
+            raise DeviceError("bvh_info: " + self.error_message())
+        return info.as_dict()
+
+    def host_bvh8_report(self):
+        """(info, seconds, error) of the last top-level BVH8::pack_nodes on the host."""
+        info, sec, err = BVHInfo(), C.c_double(), C.create_string_buffer(512)
+        self._S.b200_host_bvh8_report(C.byref(info), C.byref(sec), err, len(err))
+        return info.as_dict(), sec.value, err.value.decode()
 
     def close(self):
         if getattr(self, "_h", None):

@@ -83,3 +83,44 @@ def test_product_libraries_have_no_path_to_the_oracle_kernels():
         assert "kernel_cpu_" not in syms, lib
     needed = subprocess.run(["readelf", "-d", libs[0]], capture_output=True, text=True).stdout
     assert "libcycles" not in needed and "libnccl" not in needed  # NCCL is bound at first use
+
+
+def test_bvh8_is_a_host_layout_of_the_reference(ref):
+    """BVH_LAYOUT_BVH8 as a first-class host layout: the reference's own BVH::create +
+    BVH::build, asked for that layout, reach `BVH8 : BVH` (csrc/bvh8_host.cpp, registered
+    by the device library) and come back with the device's node / record arrays - byte for
+    byte what b200_bvh8_pack makes of the packed binary tree, which is the BVH the device
+    derives itself on a host that only knows BVH2 (and whose traversal the GPU parity tests
+    check).  Host-only: no GPU involved."""
+    import ctypes as C
+    import numpy as np
+    from raytracingproject_b200 import device as D, scenes
+    D.load_library()
+    if not os.path.exists(D.SHIM_PATH):
+        pytest.skip("device shim not built (needs the reference headers)")
+    C.CDLL(D.SHIM_PATH, mode=C.RTLD_GLOBAL)   # registers the layout with the host library
+    for desc in (scenes.cornell(64, 36, materials="diffuse"),
+                 scenes.instanced(64, 36, grid=4, subdiv=2),
+                 scenes.terrain(64, 36, n=48)):
+        rs = ref.build_scene(desc)
+        try:
+            arrays = rs.device_arrays()
+            nodes, recs, onode, root, info = D.pack_bvh8(arrays)
+            assert info["host_packed"] == 1 and info["num_nodes"] * 80 == nodes.size
+            h_nodes, h_recs, h_onode, h_root = rs.pack_bvh(D.BVH_LAYOUT_BVH8)
+            assert h_root == root
+            assert np.array_equal(h_nodes, nodes) and np.array_equal(h_recs, recs)
+            assert np.array_equal(h_onode[:len(onode)], onode)
+            # and the layout the scene was built with is still the binary one
+            b_nodes, _, _, b_root = rs.pack_bvh(D.BVH_LAYOUT_BVH2)
+            assert np.array_equal(b_nodes, np.ascontiguousarray(arrays["__bvh_nodes"][0])) \
+                if "__bvh_nodes" in arrays else b_nodes.size == 0
+        finally:
+            rs.close()
+
+
+def test_bvh8_pack_refuses_what_the_device_cannot_traverse():
+    import numpy as np
+    from raytracingproject_b200 import device as D
+    with pytest.raises(D.DeviceError, match="BVH2"):
+        D.pack_bvh8({"__data": (np.zeros(4096, np.uint8), 1)})

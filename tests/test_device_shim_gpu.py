@@ -3,6 +3,8 @@ DeviceTask::RENDER (acquire_tile / release_tile callbacks) drive the C++
 `B200Device : ccl::Device`; the film read back through RenderBuffers must equal
 the film rendered through the Python mirror of the same C ABI, and match the
 reference CPU device."""
+import os
+
 import numpy as np
 import pytest
 
@@ -34,10 +36,35 @@ def test_reference_scene_drives_b200_device(ref, device, name):
             rmse = np.sqrt(np.mean((full[..., :3] / spp - ref_img[..., :3] / spp) ** 2))
             print(name, "shim vs CPU rmse", rmse, host.stats())
             assert rmse <= 1e-3
+            # the device asked the host for ITS layout: the reference's BVH::create built a
+            # `BVH8 : BVH`, no packed BVH2 reached the device and nothing was built there
+            info = host.bvh_info()
+            packed, seconds, err = host.host_bvh8_report()
+            print(name, "bvh", info, "host pack s", seconds)
+            assert info["host_packed"] == 1 and info["build_ms"] == 0.0 and err == ""
+            assert info["num_nodes"] == packed["num_nodes"] > 0
         finally:
             rs.close()
     finally:
         host.close()
+
+    # the other route (a host that only knows BVH2): same film
+    os.environ["B200_HOST_BVH"] = "bvh2"
+    try:
+        host = B200HostDevice(0)
+        try:
+            rs = ref.build_scene(desc, external_device=host.ptr)
+            try:
+                full2, _ = rs.render(0, spp, tile_size=0)
+                info = host.bvh_info()
+                assert info["host_packed"] == 0 and info["build_ms"] > 0.0
+                assert np.array_equal(full2, py_img)
+            finally:
+                rs.close()
+        finally:
+            host.close()
+    finally:
+        del os.environ["B200_HOST_BVH"]
 
 
 def test_multi_device_in_one_process(ref):
