@@ -215,6 +215,13 @@ class RefScene:
         return (grab(n, nb.value), grab(l, lb.value),
                 grab(o, no.value * 4).view(np.int32), root.value)
 
+    def pass_offset(self, pass_type):
+        """(float offset inside a film pixel, components) of a render pass, or None."""
+        self._L.ref_scene_pass_offset.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        n = C.c_int()
+        off = self._L.ref_scene_pass_offset(self._h, int(pass_type), C.byref(n))
+        return None if off < 0 else (off, n.value)
+
     def textures(self):
         """[(slot, TextureInfo bytes, pixel bytes)] - the images the reference's
         ImageManager loaded into its device (CPUDevice::tex_alloc), for
@@ -336,6 +343,9 @@ def build_scene(desc, kernel=RefScene.GENERIC, external_device=None, threads=0, 
         for fname, pixels in desc.images.items():
             write_b2im(os.path.join(d, fname), pixels)
     rs = RefScene(path, kernel=kernel, external_device=external_device, threads=threads)
+    for pass_type in getattr(desc, "passes", None) or []:
+        rs._L.ref_scene_add_pass.argtypes = [C.c_void_p, C.c_int]
+        rs._L.ref_scene_add_pass(rs._h, int(pass_type))
     handles = [rs.add_mesh(m.P, m.tris, m.shader, m.smooth) for m in desc.meshes]
     for mi, tfm in desc.objects:
         o = rs.add_object(handles[mi], tfm)

@@ -313,6 +313,37 @@ int ref_scene_set_image_tiles(
   return 1;
 }
 
+/* Adds a render pass (PassType) next to the combined one - what BlenderSync::sync_render_passes
+ * does from the view layer (blender_sync.cpp) - before the scene is updated.  Returns the
+ * number of floats per pixel the film holds now. */
+int ref_scene_add_pass(ref_scene *rs, int pass_type)
+{
+  Scene *scene = rs->scene;
+  vector<Pass> passes = scene->passes;
+  Pass::add((PassType)pass_type, passes);
+  scene->film->tag_passes_update(scene, passes);
+  scene->film->tag_update(scene);
+  BufferParams bp;
+  bp.passes = scene->passes;
+  return bp.get_passes_size();
+}
+
+/* Float offset of a pass inside a pixel of the film (RenderBuffers layout: the passes in
+ * scene->passes order), -1 when the film does not hold it; `components` as stored. */
+int ref_scene_pass_offset(ref_scene *rs, int pass_type, int *components)
+{
+  int offset = 0;
+  foreach (const Pass &pass, rs->scene->passes) {
+    if ((int)pass.type == pass_type) {
+      if (components)
+        *components = pass.components;
+      return offset;
+    }
+    offset += pass.components;
+  }
+  return -1;
+}
+
 /* Equivalent of Session::update_scene (session.cpp:909-950). */
 int ref_scene_update(ref_scene *rs, int width, int height)
 {

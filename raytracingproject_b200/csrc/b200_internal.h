@@ -78,8 +78,9 @@ struct b200_ctx {
   int64_t opt_trace_blocks_per_sm = 0;
   int64_t opt_sync_iterations = 0; /* A/B: stop the stream for the counters every bounce */
 
-  /* k_shade_surface<lean / lean + multi-scatter / full>: grid size per SM */
-  int shade_blocks_per_sm[3] = {0, 0, 0};
+  /* k_shade_surface<lean / lean + multi-scatter / full / full + render passes>: grid size
+   * per SM */
+  int shade_blocks_per_sm[4] = {0, 0, 0, 0};
 
   /* host cancel predicate (task.get_cancel()), polled between wavefront batches */
   b200_cancel_fn cancel_fn = nullptr;

@@ -25,6 +25,7 @@
 #include <cuda_fp16.h>
 
 #include "shade.cuh"
+#include "passes.cuh"
 
 #define WF_MAX_KEYS 4096
 #define WF_BLOCK 256
@@ -80,6 +81,12 @@ struct PathSoA {
   int *q_next;   /* next bounce's q_active */
   int2 *q_sorted; /* (queue position qi, path index) ordered by key */
   int *q_shadow; /* [shadow queue] -> path */
+  /* Render passes beyond the combined one (passes.cuh), null otherwise: the per-path
+   * accumulator block, and two more colours per shadow-queue entry - a light sample on a
+   * directly visible surface arrives split per BSDF class (sh_contrib = diffuse,
+   * sh_pass[2 qi] = glossy | shadow-pass weight, sh_pass[2 qi + 1] = transmission | 1) */
+  float *pass;
+  float4 *sh_pass;
   /* Transparent shadows (only allocated when integrator.transparent_shadows): shadow rays
    * whose first hit is a transparent surface step from surface to surface
    * (kernel_shadow.h:300-352).  Two ping-pong queues of (ray, index into the shadow
@@ -102,6 +109,7 @@ struct PathPool {
   size_t bytes = 0;
   bool has_ts = false; /* transparent-shadow arrays carved */
   bool has_ao = false; /* shadow queue sized for two entries per path (light + AO ray) */
+  bool has_passes = false; /* per-path pass accumulators + split shadow contributions */
   WFCounters *h_counters = nullptr; /* pinned */
   uint32_t *sobol_tab = nullptr;    /* SOBOL_TABLE_MAX entries */
   /* The bounce loop runs ahead of the host: iteration `it` copies the head of the
@@ -366,6 +374,8 @@ __global__ void __launch_bounds__(WF_BLOCK)
       /* kernel_path_trace returns before kernel_write_result when ray.t == 0
        * (kernel_path.h:668-670): transparent = 1 makes the film add (0,0,0,0). */
       p.L[i] = make_float4(0.0f, 0.0f, 0.0f, (t == 0.0f) ? 1.0f : 0.0f);
+      if (p.pass && t == 0.0f) /* the block was cleared for the batch */
+        p.pass[(size_t)i * PASS_WORDS + PB_UNTRACED] = 1.0f;
     }
     unsigned int slot, unused;
     block_append2(&p.counters->n_active, t != 0.0f, &p.counters->n_active, false, &slot, &unused);
@@ -575,7 +585,7 @@ CY_DEV void path_lamp_emission(PathStateG &st, f3 rayP, f3 rayD, float isect_t, 
 #ifndef BG_MIN_BLOCKS
 #  define BG_MIN_BLOCKS 1
 #endif
-template<bool EXT>
+template<bool EXT, bool PASSES = false>
 __global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(PathSoA p)
 {
   WFCounters *c = p.counters;
@@ -596,15 +606,28 @@ __global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(Pa
     f3 L = mk3(Lr);
     const f3 rayP = mk3(r0), rayD = mk3(r1);
     const float isect_t = p.hit[qpos].x; /* = ray t on a miss (bvh_traversal.h:62) */
+    /* with light passes a contribution goes to the emission pass (L), to "seen after one
+     * bounce" or to "later", by the path's bounce (kernel_accumulate.h:302-340) */
+    float *pb = PASSES ? p.pass + (size_t)i * PASS_WORDS : nullptr;
+    const bool use_light_pass = PASSES && kd_int(KD_FILM_USE_LIGHT_PASS);
+    const int bucket = use_light_pass ? emission_bucket(st.bounce) : -1;
 
     ShaderDataG esd;
-    path_lamp_emission<EXT>(st, rayP, rayD, isect_t, throughput, esd, L);
+    if (bucket < 0) {
+      path_lamp_emission<EXT>(st, rayP, rayD, isect_t, throughput, esd, L);
+    }
+    else {
+      f3 lamp = zero3();
+      path_lamp_emission<EXT>(st, rayP, rayD, isect_t, throughput, esd, lamp);
+      pb_add3(pb, bucket, lamp);
+    }
 
     /* kernel_path_background - kernel_path.h:115-144 */
     bool eval_bg = true;
     if (kd_int(KD_BG_TRANSPARENT) && (st.flag & CY_PATH_RAY_TRANSPARENT_BACKGROUND)) {
       Lr.w += average(throughput);
-      eval_bg = false; /* no light passes: return */
+      /* the background pass still wants the colour behind a transparent film */
+      eval_bg = use_light_pass && light_pass_on(CY_PASS_BACKGROUND);
     }
     if (eval_bg) {
       if (path_state_ao_bounce(st))
@@ -613,7 +636,12 @@ __global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(Pa
       /* path_radiance_accum_background - kernel_accumulate.h:478-515 */
       f3 contribution = throughput * L_background;
       path_radiance_clamp(&contribution, st.bounce - 1);
-      L += contribution;
+      if (!use_light_pass)
+        L += contribution;
+      else if (st.flag & CY_PATH_RAY_TRANSPARENT_BACKGROUND)
+        pb_add3(pb, PB_BACKGROUND, contribution);
+      else
+        pb_add3(pb, (st.bounce == 1) ? PB_DIRECT_EMISSION : PB_INDIRECT, contribution);
     }
     p.L[i] = make_float4(L.x, L.y, L.z, Lr.w);
   }
@@ -632,6 +660,9 @@ __global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(Pa
  * a column per thread: a warp touches one 128-byte row per word, no conflicts. */
 #define SHADE_STAGE_WORDS 12
 #define SHADE_SMEM_BYTES (SHADE_STAGE_WORDS * WF_BLOCK * sizeof(float))
+/* with render passes the record carries two more colours and two flags */
+#define SHADE_STAGE_WORDS_PASSES 20
+#define SHADE_SMEM_BYTES_PASSES (SHADE_STAGE_WORDS_PASSES * WF_BLOCK * sizeof(float))
 
 /* kernel_path_shader_apply .. kernel_path_surface_bounce (kernel_path.h:254-321, 540-640;
  * kernel_path_surface.h:22-125, 270-358) for the hits of one bounce, in shader order.
@@ -642,7 +673,7 @@ __global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(Pa
  * that follows does not carry them in registers; slots in the next-bounce and shadow
  * queues come from one block-wide reservation at the end of the round, after which the
  * staged record is copied out to its slot. */
-template<bool EXT, bool MS = EXT>
+template<bool EXT, bool MS = EXT, bool PASSES = false>
 __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_MIN_BLOCKS)
     k_shade_surface(PathSoA p, int num_keys)
 {
@@ -682,8 +713,20 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
       float ray_t = r0.w;
 
       ShaderDataG sd;
+      /* light passes (passes.cuh): the path's accumulator block; where emission seen by
+       * this segment goes (the emission pass = L, "after one bounce", or "later") */
+      float *pb = PASSES ? p.pass + (size_t)i * PASS_WORDS : nullptr;
+      const bool use_light_pass = PASSES && kd_int(KD_FILM_USE_LIGHT_PASS);
+      const int bucket = use_light_pass ? emission_bucket(st.bounce) : -1;
       /* lamps crossed before the hit (kernel_path.h:537) - uses `sd` as scratch */
-      path_lamp_emission<EXT>(st, mk3(r0), mk3(r1), hit.x, throughput, sd, L);
+      if (bucket < 0) {
+        path_lamp_emission<EXT>(st, mk3(r0), mk3(r1), hit.x, throughput, sd, L);
+      }
+      else {
+        f3 lamp = zero3();
+        path_lamp_emission<EXT>(st, mk3(r0), mk3(r1), hit.x, throughput, sd, lamp);
+        pb_add3(pb, bucket, lamp);
+      }
 
       bool alive = !path_state_ao_bounce(st); /* kernel_path.h:560-562 */
       if (alive) {
@@ -693,6 +736,9 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
                                  st.rng_hash + (uint32_t)st.rng_offset +
                                      (uint32_t)st.sample * 0xb4bc3953u);
         shader_prepare_lobes<EXT>(sd, arena, st.bounce + st.transparent_bounce == 0);
+
+        if (PASSES) /* kernel_write_data_passes - kernel_path.h:569, kernel_passes.h:174-282 */
+          pass_write_data(sd, arena, st, throughput, pb);
 
         /* kernel_path_shader_apply - kernel_path.h:254-321 (no holdout / shadow catcher:
          * refused at bind time) */
@@ -715,7 +761,10 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
           }
           f3 contribution = throughput * emission;
           path_radiance_clamp(&contribution, st.bounce - 1);
-          L += contribution;
+          if (bucket < 0)
+            L += contribution;
+          else
+            pb_add3(pb, bucket, contribution);
         }
 
         /* russian roulette - kernel_path.h:578-589 */
@@ -802,25 +851,84 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
               }
             }
             if (!is_zero(light_eval)) {
-              f3 eval = shader_bsdf_eval<EXT, MS>(sd, arena, ls.D, ls.pdf,
-                                              (ls.shader & CY_SHADER_USE_MIS) != 0);
-              eval *= light_eval / ls.pdf;
-              bool ok = !is_zero(eval);
+              /* BSDF towards the light: one colour, or - with light passes - one per BSDF
+               * class (diffuse / glossy / transmission), which a lamp's ray-visibility
+               * flags may zero (kernel_emission.h:146-157) */
+              f3 eval = zero3();
+              EvalSplit ev;
+              bool ok;
+              if (use_light_pass) {
+                shader_bsdf_eval_split<EXT, MS>(sd, arena, ls.D, ls.pdf,
+                                                (ls.shader & CY_SHADER_USE_MIS) != 0, ev);
+                eval_split_mul3(ev, light_eval / ls.pdf);
+                if (ls.shader & CY_SHADER_EXCLUDE_ANY) {
+                  if (ls.shader & CY_SHADER_EXCLUDE_DIFFUSE)
+                    ev.diffuse = zero3();
+                  if (ls.shader & CY_SHADER_EXCLUDE_GLOSSY)
+                    ev.glossy = zero3();
+                  if (ls.shader & CY_SHADER_EXCLUDE_TRANSMIT)
+                    ev.transmission = zero3();
+                }
+                ok = !eval_split_is_zero(ev);
+                eval = eval_split_sum(ev);
+              }
+              else {
+                eval = shader_bsdf_eval<EXT, MS>(sd, arena, ls.D, ls.pdf,
+                                                 (ls.shader & CY_SHADER_USE_MIS) != 0);
+                eval *= light_eval / ls.pdf;
+                ok = !is_zero(eval);
+              }
               if (ok && kd_float(KD_INT_LIGHT_INV_RR_THRESHOLD) > 0.0f) {
                 const float probability = max3(fabs3(eval)) *
                                           kd_float(KD_INT_LIGHT_INV_RR_THRESHOLD);
                 if (probability < 1.0f) {
                   if (terminate >= probability)
                     ok = false;
-                  else
+                  else {
                     eval *= 1.0f / probability;
+                    if (use_light_pass)
+                      eval_split_mul(ev, 1.0f / probability);
+                  }
                 }
               }
               if (ok) {
-                /* path_radiance_accum_light (no light passes): contribution =
-                 * throughput * shadow(=1) * eval, clamped by bounce */
-                f3 contribution = throughput * eval;
-                path_radiance_clamp(&contribution, st.bounce);
+                /* path_radiance_accum_light (kernel_accumulate.h:402-459), shadow = 1:
+                 * without light passes one clamped colour; with them the clamp factor of
+                 * the total scales every class, a directly visible surface keeps the
+                 * classes apart (A, B, C = diffuse, glossy, transmission), a later one
+                 * adds the total to the indirect light (A) */
+                f3 contribution, part_b = zero3(), part_c = zero3();
+                float shadow_add = 0.0f;
+                if (use_light_pass) {
+                  f3 shaded_throughput = throughput;
+                  f3 full = shaded_throughput * eval_split_sum(ev);
+                  {
+                    const float limit = (st.bounce > 0) ? kd_float(KD_INT_SAMPLE_CLAMP_INDIRECT) :
+                                                          kd_float(KD_INT_SAMPLE_CLAMP_DIRECT);
+                    const float sum = reduce_add(fabs3(full));
+                    if (sum > limit) {
+                      const float clamp_factor = limit / sum;
+                      full *= clamp_factor;
+                      shaded_throughput *= clamp_factor;
+                    }
+                  }
+                  if (st.bounce == 0) {
+                    contribution = shaded_throughput * ev.diffuse;
+                    part_b = shaded_throughput * ev.glossy;
+                    part_c = shaded_throughput * ev.transmission;
+                    /* the shadow pass counts lamps only (kernel_emission.h:208) */
+                    shadow_add = (ls.prim == CY_PRIM_NONE && ls.type != CY_LIGHT_BACKGROUND) ?
+                                     1.0f :
+                                     0.0f;
+                  }
+                  else {
+                    contribution = full;
+                  }
+                }
+                else {
+                  contribution = throughput * eval;
+                  path_radiance_clamp(&contribution, st.bounce);
+                }
                 if (ls.shader & CY_SHADER_CAST_SHADOW) {
                   const bool transmit = (dot(sd.Ng, ls.D) < 0.0f);
                   const f3 sP = ray_offset(sd.P, transmit ? -sd.Ng : sd.Ng);
@@ -845,11 +953,30 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
                   stage[8 * WF_BLOCK] = contribution.y;
                   stage[9 * WF_BLOCK] = contribution.z;
                   stage[10 * WF_BLOCK] = __int_as_float(st.transparent_bounce);
+                  if (PASSES) {
+                    stage[12 * WF_BLOCK] = part_b.x;
+                    stage[13 * WF_BLOCK] = part_b.y;
+                    stage[14 * WF_BLOCK] = part_b.z;
+                    stage[15 * WF_BLOCK] = shadow_add;
+                    stage[16 * WF_BLOCK] = part_c.x;
+                    stage[17 * WF_BLOCK] = part_c.y;
+                    stage[18 * WF_BLOCK] = part_c.z;
+                    stage[19 * WF_BLOCK] = (use_light_pass && st.bounce == 0) ? 1.0f : 0.0f;
+                  }
                   want_shadow = true;
                 }
-                else {
+                else if (!use_light_pass) {
                   /* ray.t = 0: shadow_blocked returns false immediately */
                   L += contribution;
+                }
+                else if (st.bounce == 0) {
+                  pb_add3(pb, PB_DIRECT_DIFFUSE, contribution);
+                  pb_add3(pb, PB_DIRECT_GLOSSY, part_b);
+                  pb_add3(pb, PB_DIRECT_TRANSMISSION, part_c);
+                  pb_add3(pb, PB_SHADOW, mk3(shadow_add, shadow_add, shadow_add));
+                }
+                else {
+                  pb_add3(pb, PB_INDIRECT, contribution);
                 }
               }
             }
@@ -862,13 +989,41 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
           path_state_rng_2D<EXT>(st, CY_PRNG_BSDF_U, &bsdf_u, &bsdf_v);
           f3 bsdf_eval = zero3(), omega_in = zero3();
           float bsdf_pdf;
-          const int label = shader_bsdf_sample<EXT, MS>(sd, arena, bsdf_u, bsdf_v, &bsdf_eval,
-                                                    &omega_in, &bsdf_pdf);
-          if (!(bsdf_pdf == 0.0f || is_zero(bsdf_eval))) {
+          EvalSplit bs;
+          int label;
+          bool scattered;
+          if (use_light_pass) {
+            label = shader_bsdf_sample_split<EXT, MS>(sd, arena, bsdf_u, bsdf_v, bs, &omega_in,
+                                                      &bsdf_pdf);
+            scattered = !(bsdf_pdf == 0.0f || eval_split_is_zero(bs));
+          }
+          else {
+            label = shader_bsdf_sample<EXT, MS>(sd, arena, bsdf_u, bsdf_v, &bsdf_eval, &omega_in,
+                                                &bsdf_pdf);
+            scattered = !(bsdf_pdf == 0.0f || is_zero(bsdf_eval));
+          }
+          if (scattered) {
             /* LABEL_TRANSMIT_TRANSPARENT (closure/bsdf.h:466-475) needs transparent glass,
              * which check_scope refuses (threshold < 0 here) */
-            /* path_radiance_bsdf_bounce, no light passes */
-            throughput *= bsdf_eval * (1.0f / bsdf_pdf);
+            /* path_radiance_bsdf_bounce (kernel_accumulate.h:235-268) */
+            if (!use_light_pass) {
+              throughput *= bsdf_eval * (1.0f / bsdf_pdf);
+            }
+            else if (st.bounce == 0 && !(label & CY_LABEL_TRANSPARENT)) {
+              /* first bounce off a directly visible surface: the throughput per BSDF class
+               * is remembered, the path goes on with their sum */
+              const f3 value = throughput * (1.0f / bsdf_pdf);
+              const f3 sd_ = bs.diffuse * value, sg_ = bs.glossy * value,
+                       st_ = bs.transmission * value;
+              throughput = sd_ + sg_ + st_ + zero3();
+              pb_set3(pb, PB_STATE_DIFFUSE, sd_);
+              pb_set3(pb, PB_STATE_GLOSSY, sg_);
+              pb_set3(pb, PB_STATE_TRANSMISSION, st_);
+              pb_set3(pb, PB_STATE_DIRECT, throughput);
+            }
+            else {
+              throughput *= (eval_split_sum(bs) + bs.transparent) * (1.0f / bsdf_pdf);
+            }
             if (!(label & CY_LABEL_TRANSPARENT)) {
               st.ray_pdf = bsdf_pdf;
               st.ray_t = 0.0f;
@@ -929,6 +1084,12 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
                                  __uint_as_float(CY_PATH_RAY_SHADOW_OPAQUE));
       p.sh_contrib[s_sh] = make_float4(stage[7 * WF_BLOCK], stage[8 * WF_BLOCK],
                                        stage[9 * WF_BLOCK], stage[10 * WF_BLOCK]);
+      if (PASSES) {
+        p.sh_pass[2 * (size_t)s_sh] = make_float4(stage[12 * WF_BLOCK], stage[13 * WF_BLOCK],
+                                                  stage[14 * WF_BLOCK], stage[15 * WF_BLOCK]);
+        p.sh_pass[2 * (size_t)s_sh + 1] = make_float4(stage[16 * WF_BLOCK], stage[17 * WF_BLOCK],
+                                                      stage[18 * WF_BLOCK], stage[19 * WF_BLOCK]);
+      }
     }
   }
 }
@@ -938,7 +1099,7 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
 /* AO: the light ray and the ambient-occlusion ray of one path are in the same launch,
  * so unoccluded contributions are added atomically (a compile-time variant: the test
  * at run time cost the plain kernel 7 %) */
-template<bool TRANSPARENT, bool AO = false> struct ShadowJob {
+template<bool TRANSPARENT, bool AO = false, bool PASSES = false> struct ShadowJob {
   PathSoA p;
   __device__ __forceinline__ const float4 *ray_P(unsigned int qi) const
   {
@@ -954,7 +1115,22 @@ template<bool TRANSPARENT, bool AO = false> struct ShadowJob {
       /* shade_shadow - path_radiance_accum_light, kernel_accumulate.h:402-459 */
       const int i = p.q_shadow[qi];
       const float4 cn = p.sh_contrib[qi];
-      if (AO) {
+      if (PASSES && kd_int(KD_FILM_USE_LIGHT_PASS)) {
+        /* light passes: a directly visible surface adds per BSDF class (and counts the
+         * lamp in the shadow pass), a later one adds to the indirect light */
+        float *pb = p.pass + (size_t)i * PASS_WORDS;
+        const float4 b = p.sh_pass[2 * (size_t)qi], cc = p.sh_pass[2 * (size_t)qi + 1];
+        if (cc.w != 0.0f) {
+          pb_add3(pb, PB_DIRECT_DIFFUSE, mk3(cn));
+          pb_add3(pb, PB_DIRECT_GLOSSY, mk3(b));
+          pb_add3(pb, PB_DIRECT_TRANSMISSION, mk3(cc));
+          pb_add3(pb, PB_SHADOW, mk3(b.w, b.w, b.w));
+        }
+        else {
+          pb_add3(pb, PB_INDIRECT, mk3(cn));
+        }
+      }
+      else if (AO) {
         float *L = (float *)&p.L[i];
         atomicAdd(L + 0, cn.x);
         atomicAdd(L + 1, cn.y);
@@ -1113,14 +1289,14 @@ __global__ void k_shadow_step_end(PathSoA p, int cur)
   c->work_ts = 0;
 }
 
-template<bool COUNT, bool TRANSPARENT, bool AO = false>
+template<bool COUNT, bool TRANSPARENT, bool AO = false, bool PASSES = false>
 __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS)
     k_intersect_shadow(PathSoA p, int refill_threshold)
 {
   const unsigned lane = threadIdx.x & 31u;
   TraceCounters cnt;
   cnt.nodes = cnt.tris = cnt.instances = 0;
-  ShadowJob<TRANSPARENT, AO> job;
+  ShadowJob<TRANSPARENT, AO, PASSES> job;
   job.p = p;
   trace_persistent<true, COUNT>(job, p.counters->n_shadow, &p.counters->work_shadow,
                                 refill_threshold, cnt);
@@ -1195,6 +1371,126 @@ __global__ void __launch_bounds__(WF_BLOCK)
       acc.w += alpha;
     }
     *dst = acc;
+  }
+}
+
+/* kernel_write_result + kernel_write_light_passes + the data passes
+ * (kernel_passes.h:285-350, 174-224; path_radiance_clamp_and_sum,
+ * kernel_accumulate.h:537-560, 640-700) for the whole batch when the film holds more than
+ * the combined pass: one thread owns a pixel and folds its samples into every pass in
+ * sample order. */
+__global__ void __launch_bounds__(WF_BLOCK)
+    k_film_accumulate_passes(PathSoA p, BatchParams bp, float *film, int pass_stride)
+{
+  const unsigned int npix = (unsigned)bp.w * (unsigned)bp.h;
+  const int flag = kd_int(KD_FILM_PASS_FLAG), light_flag = kd_int(KD_FILM_LIGHT_PASS_FLAG);
+  const bool use_light_pass = kd_int(KD_FILM_USE_LIGHT_PASS) != 0;
+  auto add3 = [](float *dst, f3 v) {
+    dst[0] += v.x;
+    dst[1] += v.y;
+    dst[2] += v.z;
+  };
+  auto lp = [&](int pass_type) { return (light_flag & (1 << (pass_type % 32))) != 0; };
+  for (unsigned int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
+       pix += gridDim.x * blockDim.x) {
+    int x, y;
+    batch_pixel(bp, pix, &x, &y);
+    const long long index = (long long)bp.offset + x + (long long)y * bp.stride;
+    float *buf = film + index * pass_stride;
+    for (int s = 0; s < bp.nsamples; s++) {
+      /* a pixel sample whose camera ray was never traced (t = 0, outside the lens of a
+       * panoramic camera) writes nothing at all: kernel_path_trace returns early */
+      const size_t path = (size_t)s * npix + pix;
+      const float4 Lr = p.L[path];
+      const float *pb = p.pass + path * PASS_WORDS;
+      if (pb[PB_UNTRACED] != 0.0f)
+        continue;
+      const f3 emission = mk3(Lr);
+      const float transparent = Lr.w;
+      f3 L_sum;
+      f3 dd = zero3(), dg = zero3(), dt = zero3(), id = zero3(), ig = zero3(), it = zero3();
+      if (use_light_pass) {
+        const f3 s_d = pb_get3(pb, PB_STATE_DIFFUSE), s_g = pb_get3(pb, PB_STATE_GLOSSY),
+                 s_t = pb_get3(pb, PB_STATE_TRANSMISSION), s_all = pb_get3(pb, PB_STATE_DIRECT);
+        /* path_radiance_sum_indirect: light that arrived after the first bounce is divided
+         * by that bounce's total throughput and handed to the classes in proportion */
+        const f3 de = safe_divide_color(pb_get3(pb, PB_DIRECT_EMISSION), s_all);
+        dd = pb_get3(pb, PB_DIRECT_DIFFUSE) + s_d * de;
+        dg = pb_get3(pb, PB_DIRECT_GLOSSY) + s_g * de;
+        dt = pb_get3(pb, PB_DIRECT_TRANSMISSION) + s_t * de;
+        const f3 ind = safe_divide_color(pb_get3(pb, PB_INDIRECT), s_all);
+        id = s_d * ind;
+        ig = s_g * ind;
+        it = s_t * ind;
+        f3 L_direct = dd + dg + dt + zero3() + emission;
+        const f3 L_indirect = id + ig + it + zero3();
+        if (!kd_int(KD_BG_TRANSPARENT))
+          L_direct += pb_get3(pb, PB_BACKGROUND);
+        L_sum = L_direct + L_indirect;
+      }
+      else {
+        L_sum = emission;
+      }
+      const float sum = fabsf(L_sum.x) + fabsf(L_sum.y) + fabsf(L_sum.z);
+      bool finite = isfinite_safe(sum);
+      if (!finite) {
+        L_sum = zero3();
+        dd = dg = dt = id = ig = it = zero3();
+      }
+      const float alpha = 1.0f - transparent;
+      if (flag & (1 << CY_PASS_COMBINED)) {
+        float *dst = buf + kd_int(KD_FILM_PASS_COMBINED);
+        dst[0] += L_sum.x;
+        dst[1] += L_sum.y;
+        dst[2] += L_sum.z;
+        dst[3] += alpha;
+      }
+      if (use_light_pass) {
+        if (lp(CY_PASS_DIFFUSE_INDIRECT))
+          add3(buf + kd_int(KD_FILM_PASS_DIFFUSE_INDIRECT), id);
+        if (lp(CY_PASS_GLOSSY_INDIRECT))
+          add3(buf + kd_int(KD_FILM_PASS_GLOSSY_INDIRECT), ig);
+        if (lp(CY_PASS_TRANSMISSION_INDIRECT))
+          add3(buf + kd_int(KD_FILM_PASS_TRANSMISSION_INDIRECT), it);
+        if (lp(CY_PASS_DIFFUSE_DIRECT))
+          add3(buf + kd_int(KD_FILM_PASS_DIFFUSE_DIRECT), dd);
+        if (lp(CY_PASS_GLOSSY_DIRECT))
+          add3(buf + kd_int(KD_FILM_PASS_GLOSSY_DIRECT), dg);
+        if (lp(CY_PASS_TRANSMISSION_DIRECT))
+          add3(buf + kd_int(KD_FILM_PASS_TRANSMISSION_DIRECT), dt);
+        if (lp(CY_PASS_EMISSION))
+          add3(buf + kd_int(KD_FILM_PASS_EMISSION), finite ? emission : zero3());
+        if (lp(CY_PASS_BACKGROUND))
+          add3(buf + kd_int(KD_FILM_PASS_BACKGROUND), pb_get3(pb, PB_BACKGROUND));
+        if (lp(CY_PASS_DIFFUSE_COLOR))
+          add3(buf + kd_int(KD_FILM_PASS_DIFFUSE_COLOR), pb_get3(pb, PB_COLOR_DIFFUSE));
+        if (lp(CY_PASS_GLOSSY_COLOR))
+          add3(buf + kd_int(KD_FILM_PASS_GLOSSY_COLOR), pb_get3(pb, PB_COLOR_GLOSSY));
+        if (lp(CY_PASS_TRANSMISSION_COLOR))
+          add3(buf + kd_int(KD_FILM_PASS_TRANSMISSION_COLOR), pb_get3(pb, PB_COLOR_TRANSMISSION));
+        if (lp(CY_PASS_SHADOW)) {
+          float *dst = buf + kd_int(KD_FILM_PASS_SHADOW);
+          add3(dst, pb_get3(pb, PB_SHADOW));
+          dst[3] += kd_float(KD_FILM_PASS_SHADOW_SCALE);
+        }
+        if (lp(CY_PASS_MIST))
+          buf[kd_int(KD_FILM_PASS_MIST)] += 1.0f - pb[PB_MIST];
+      }
+      if (pb[PB_HAS_DATA] != 0.0f) {
+        if (bp.sample0 + s == 0) {
+          if (flag & (1 << CY_PASS_DEPTH))
+            buf[kd_int(KD_FILM_PASS_DEPTH)] += pb[PB_DEPTH];
+          if (flag & (1 << CY_PASS_OBJECT_ID))
+            buf[kd_int(KD_FILM_PASS_OBJECT_ID)] += pb[PB_OBJECT_ID];
+          if (flag & (1 << CY_PASS_MATERIAL_ID))
+            buf[kd_int(KD_FILM_PASS_MATERIAL_ID)] += pb[PB_MATERIAL_ID];
+        }
+        if (flag & (1 << CY_PASS_NORMAL))
+          add3(buf + kd_int(KD_FILM_PASS_NORMAL), pb_get3(pb, PB_NORMAL));
+        if (flag & (1 << CY_PASS_UV))
+          add3(buf + kd_int(KD_FILM_PASS_UV), pb_get3(pb, PB_UV));
+      }
+    }
   }
 }
 
@@ -1308,16 +1604,19 @@ static void free_pool(b200_ctx *ctx)
 
 #define PATH_POOL_BYTES_PER_PATH 228 /* 12 float4 + 8 words per path, see the carve list */
 
-static int ensure_pool(b200_ctx *ctx, size_t capacity, bool transparent_shadows, bool ao)
+static int ensure_pool(b200_ctx *ctx, size_t capacity, bool transparent_shadows, bool ao,
+                       bool passes)
 {
   if (ctx->pool && ctx->pool->capacity >= capacity &&
-      (ctx->pool->has_ts || !transparent_shadows) && (ctx->pool->has_ao || !ao))
+      (ctx->pool->has_ts || !transparent_shadows) && (ctx->pool->has_ao || !ao) &&
+      (ctx->pool->has_passes || !passes))
     return B200_OK;
   free_pool(ctx);
   PathPool *pool = new PathPool();
   pool->capacity = capacity;
   pool->has_ts = transparent_shadows;
   pool->has_ao = ao;
+  pool->has_passes = passes;
   /* carve one allocation; every array 256-byte aligned */
   size_t off = 0;
   auto carve = [&](size_t bytes) {
@@ -1338,6 +1637,9 @@ static int ensure_pool(b200_ctx *ctx, size_t capacity, bool transparent_shadows,
   size_t o_tsP0 = carve(nts * 16), o_tsP1 = carve(nts * 16), o_tsD0 = carve(nts * 16),
          o_tsD1 = carve(nts * 16), o_tsI0 = carve(nts * 4), o_tsI1 = carve(nts * 4),
          o_tsT = carve(nts * 16);
+  /* render passes: PASS_WORDS floats per path, two more colours per shadow entry */
+  const size_t npass = passes ? n : 0;
+  size_t o_pass = carve(npass * PASS_WORDS * sizeof(float)), o_shpass = carve((passes ? nsh : 0) * 32);
   cudaError_t e = cudaMalloc(&pool->block, off);
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -1376,6 +1678,8 @@ static int ensure_pool(b200_ctx *ctx, size_t capacity, bool transparent_shadows,
   s.ts_idx[1] = transparent_shadows ? (int *)(b + o_tsI1) : nullptr;
   s.ts_thr = transparent_shadows ? (float4 *)(b + o_tsT) : nullptr;
   s.counters = (WFCounters *)(b + o_cnt);
+  s.pass = passes ? (float *)(b + o_pass) : nullptr;
+  s.sh_pass = passes ? (float4 *)(b + o_shpass) : nullptr;
   bool ok = cudaMallocHost(&pool->h_counters, sizeof(WFCounters)) == cudaSuccess &&
             cudaMallocHost(&pool->h_ring, WF_RING * WF_RING_BYTES) == cudaSuccess &&
             cudaMallocHost(&pool->h_batch, WF_BATCH_SLOTS * WF_BATCH_STAT_BYTES) == cudaSuccess &&
@@ -1706,6 +2010,14 @@ static int bound_image_slots(const b200_ctx *ctx)
   return n;
 }
 
+/* the film holds more than the combined pass, or a lamp's ray-visibility flags need the
+ * light split per BSDF class: the kernels with the pass accumulators run (passes.cuh) */
+static bool film_wants_passes(const b200_ctx *ctx)
+{
+  return kd_host<int>(ctx, KD_FILM_USE_LIGHT_PASS) != 0 ||
+         (kd_host<int>(ctx, KD_FILM_PASS_FLAG) & ~(1 << CY_PASS_COMBINED)) != 0;
+}
+
 static int check_scope(b200_ctx *ctx)
 {
   auto I = [&](int off) { return kd_host<int>(ctx, off); };
@@ -1742,10 +2054,23 @@ static int check_scope(b200_ctx *ctx)
           " image slots are bound (tex_alloc / b200_texture_set)";
   else if (I(KD_BG_USE_MIS))
     why = "background importance sampling is outside the hot-path scope";
-  else if (I(KD_FILM_USE_LIGHT_PASS) || I(KD_FILM_PASS_DENOISING_DATA) ||
-           I(KD_FILM_PASS_ADAPTIVE_AUX_BUFFER) || I(KD_FILM_PASS_SAMPLE_COUNT) ||
-           I(KD_FILM_CRYPTOMATTE_PASSES))
-    why = "only the combined pass is in scope";
+  else if (I(KD_FILM_PASS_DENOISING_DATA) || I(KD_FILM_PASS_ADAPTIVE_AUX_BUFFER) ||
+           I(KD_FILM_PASS_SAMPLE_COUNT) || I(KD_FILM_CRYPTOMATTE_PASSES))
+    why = "denoising data, adaptive sampling and cryptomatte passes are outside the hot-path "
+          "scope";
+  else if (I(KD_FILM_PASS_FLAG) & ~((1 << CY_PASS_COMBINED) | (1 << CY_PASS_DEPTH) |
+                                    (1 << CY_PASS_NORMAL) | (1 << CY_PASS_UV) |
+                                    (1 << CY_PASS_OBJECT_ID) | (1 << CY_PASS_MATERIAL_ID)))
+    why = "of the data passes depth, normal, UV, object id and material id are in scope "
+          "(motion, AOV and render-time passes are not)";
+  else if (I(KD_FILM_LIGHT_PASS_FLAG) &
+           ((1 << (CY_PASS_AO % 32)) | (1 << (CY_PASS_VOLUME_DIRECT % 32)) |
+            (1 << (CY_PASS_VOLUME_INDIRECT % 32))))
+    why = "the AO and volume light passes are outside the hot-path scope";
+  else if (film_wants_passes(ctx) &&
+           (I(KD_INT_USE_AMBIENT_OCCLUSION) || I(KD_INT_TRANSPARENT_SHADOWS)))
+    why = "render passes together with world ambient occlusion or transparent shadows are "
+          "outside the hot-path scope";
   else if (!(I(KD_FILM_PASS_FLAG) & (1u << CY_PASS_COMBINED)))
     why = "the combined pass must be enabled";
   else if (I(KD_FILM_PASS_STRIDE) % 4 != 0)
@@ -1777,15 +2102,17 @@ static int shade_kernel_setup(b200_ctx *ctx)
   if (ctx->shade_blocks_per_sm[0] > 0)
     return B200_OK;
   DeviceGuard guard(ctx->ordinal);
-  const void *kernels[3] = {(const void *)k_shade_surface<false, false>,
+  const void *kernels[4] = {(const void *)k_shade_surface<false, false>,
                             (const void *)k_shade_surface<false, true>,
-                            (const void *)k_shade_surface<true, true>};
-  for (int k = 0; k < 3; k++) {
+                            (const void *)k_shade_surface<true, true>,
+                            (const void *)k_shade_surface<true, true, true>};
+  for (int k = 0; k < 4; k++) {
+    const size_t smem = (k == 3) ? SHADE_SMEM_BYTES_PASSES : SHADE_SMEM_BYTES;
     CUDA_TRY(ctx, cudaFuncSetAttribute(kernels[k], cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)SHADE_SMEM_BYTES));
+                                       (int)smem));
     int blocks = 0;
     CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernels[k], WF_BLOCK,
-                                                                SHADE_SMEM_BYTES));
+                                                                smem));
     if (blocks < 1)
       return fail(ctx, B200_ERR_CUDA, "surface-shading kernel does not fit on an SM");
     /* a few waves of blocks per SM even the tail out */
@@ -1823,7 +2150,8 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
       const size_t held = ctx->pool ? ctx->pool->capacity * PATH_POOL_BYTES_PER_PATH : 0;
       const size_t per_path = PATH_POOL_BYTES_PER_PATH +
                               (kd_host<int>(ctx, KD_INT_TRANSPARENT_SHADOWS) ? 88 : 0) +
-                              (kd_host<int>(ctx, KD_INT_USE_AMBIENT_OCCLUSION) ? 52 : 0);
+                              (kd_host<int>(ctx, KD_INT_USE_AMBIENT_OCCLUSION) ? 52 : 0) +
+                              (film_wants_passes(ctx) ? PASS_WORDS * 4 + 32 : 0);
       const size_t fit = (free_b + held) / 4 / per_path;
       capacity = std::max<size_t>(std::min(capacity, fit), (size_t)1 << 16);
     }
@@ -1838,9 +2166,14 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
                        kd_host<int>(ctx, KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_PMJ ||
                        kd_host<int>(ctx, KD_INT_USE_AMBIENT_OCCLUSION) != 0;
   const bool use_ao = kd_host<int>(ctx, KD_INT_USE_AMBIENT_OCCLUSION) != 0;
+  /* render passes beyond the combined one: the full kernels with the pass accumulators */
+  const bool passes = film_wants_passes(ctx);
+  if (passes)
+    svm_ext = true;
   /* lean kernels with the multi-scatter lobes: the Principled default distribution */
   const bool multiscatter = (ctx->svm_features & SVM_USES_MULTISCATTER) != 0;
-  rc = ensure_pool(ctx, std::max<size_t>(capacity, (size_t)tile->w), transparent_shadows, use_ao);
+  rc = ensure_pool(ctx, std::max<size_t>(capacity, (size_t)tile->w), transparent_shadows, use_ao,
+                   passes);
   if (rc)
     return rc;
   PathPool *pool = ctx->pool;
@@ -1905,7 +2238,13 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
     k_sort_count<<<grid_wide, WF_BLOCK, 0, st>>>(soa);
     k_sort_scan<<<1, 256, 0, st>>>(soa, num_keys);
     k_sort_scatter<<<grid_wide, WF_BLOCK, 0, st>>>(soa);
-    if (svm_ext) {
+    if (passes) {
+      k_shade_background<true, true><<<grid_wide, WF_BLOCK, 0, st>>>(soa);
+      k_shade_surface<true, true, true>
+          <<<ctx->num_sms * ctx->shade_blocks_per_sm[3], WF_BLOCK, SHADE_SMEM_BYTES_PASSES, st>>>(
+              soa, num_keys);
+    }
+    else if (svm_ext) {
       k_shade_background<true><<<grid_wide, WF_BLOCK, 0, st>>>(soa);
       k_shade_surface<true, true><<<grid_shade, WF_BLOCK, SHADE_SMEM_BYTES, st>>>(soa, num_keys);
     }
@@ -1919,7 +2258,10 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
                                                                                       num_keys);
     }
     CUDA_TRY(ctx, cudaEventRecord(ev[2], st));
-    if (use_ao) /* never with transparent shadows (check_scope) */
+    if (passes) /* never with AO or transparent shadows (check_scope) */
+      k_intersect_shadow<false, false, false, true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa,
+                                                                                        refill);
+    else if (use_ao) /* never with transparent shadows (check_scope) */
       k_intersect_shadow<false, false, true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
     else if (transparent_shadows)
       k_intersect_shadow<false, true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
@@ -2014,6 +2356,11 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
         soa.debug = ctx->d_debug;
         soa.debug_slot = (int)ctx->opt_debug_slot;
         CUDA_TRY(ctx, cudaMemsetAsync(soa.counters, 0, sizeof(WFCounters), st));
+        if (passes)
+          CUDA_TRY(ctx, cudaMemsetAsync(soa.pass, 0,
+                                        (size_t)bp.w * bp.h * bp.nsamples * PASS_WORDS *
+                                            sizeof(float),
+                                        st));
         if (attempt == 0) {
           /* the Sobol points of this batch's samples, for every dimension a path can reach */
           SobolTable sobol = {nullptr, bp.sample0, 0u, 0u};
@@ -2075,8 +2422,13 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
           ctx->force_svm_ext = true;
           continue;
         }
-        k_film_accumulate<<<grid_wide, WF_BLOCK, 0, st>>>(soa, bp, (float *)tile->buffer,
-                                                          pass_stride, pass_combined);
+        if (passes)
+          k_film_accumulate_passes<<<grid_wide, WF_BLOCK, 0, st>>>(soa, bp,
+                                                                   (float *)tile->buffer,
+                                                                   pass_stride);
+        else
+          k_film_accumulate<<<grid_wide, WF_BLOCK, 0, st>>>(soa, bp, (float *)tile->buffer,
+                                                            pass_stride, pass_combined);
         stats.kernel_launches += 1;
         CUDA_TRY(ctx, cudaMemcpyAsync(pool->h_batch + (size_t)batch_slot * WF_BATCH_STAT_BYTES,
                                       soa.counters, WF_BATCH_STAT_BYTES, cudaMemcpyDeviceToHost,

@@ -36,6 +36,9 @@ class SceneDesc:
     # image textures: file name (as the XML names it, relative to the scene file) -> pixels,
     # (h, w) or (h, w, c) of uint8 / uint16 / float16 / float32, row 0 = bottom row
     images: Dict[str, np.ndarray] = field(default_factory=dict)
+    # render passes next to the combined one: PassType values (kernel_types.h:353-402),
+    # see PASS below
+    passes: List[int] = field(default_factory=list)
     # UDIM tile numbers of Image Texture nodes: (shader name, node name, [tiles])
     image_tiles: List[Tuple[str, str, List[int]]] = field(default_factory=list)
 
@@ -46,6 +49,14 @@ class SceneDesc:
     @property
     def num_instanced_triangles(self):
         return int(sum(len(self.meshes[m].tris) for m, _ in self.objects))
+
+
+# kernel_types.h PassType (checked against include/cycles_abi.h by tests/test_scenes_cpu.py)
+PASS = {"depth": 2, "normal": 3, "uv": 4, "object_id": 5, "material_id": 6, "mist": 32,
+        "emission": 33, "background": 34, "shadow": 36, "diffuse_direct": 38,
+        "diffuse_indirect": 39, "diffuse_color": 40, "glossy_direct": 41, "glossy_indirect": 42,
+        "glossy_color": 43, "transmission_direct": 44, "transmission_indirect": 45,
+        "transmission_color": 46}
 
 
 def _f(v):

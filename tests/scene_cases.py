@@ -125,6 +125,55 @@ def image_cases():
     }
 
 
+ALL_PASSES = ("depth", "normal", "uv", "object_id", "material_id", "mist", "emission",
+              "background", "shadow", "diffuse_direct", "diffuse_indirect", "diffuse_color",
+              "glossy_direct", "glossy_indirect", "glossy_color", "transmission_direct",
+              "transmission_indirect", "transmission_color")
+
+
+def pass_cases():
+    """Render passes next to the combined one (passes.cuh): every light and data pass in
+    scope on the Cornell box with the Principled metal / glass boxes and on the textured
+    variant; the startup scene under an environment texture with a transparent film (the
+    background pass keeps the colour behind it); a mesh-light scene (emission seen
+    directly, after one bounce and later); only data passes (no light-pass machinery);
+    and a lamp that glossy rays do not see - its ray-visibility flags alone switch the
+    per-class split on and remove that class of its light."""
+    with_mist = lambda d: _replace(d, 'exposure="1" ', 'exposure="1" mist_start="2.5" '
+                                   'mist_depth="3.0" mist_falloff="2.0" ')
+    cases = {}
+    d = with_mist(scenes.cornell(W, H, materials="principled"))
+    # rough glass instead of the sharp one: light sampling then reaches the transmission class
+    d = _replace(d, 'metallic="0" roughness="0" ', 'metallic="0" roughness="0.2" ')
+    d.passes = [scenes.PASS[k] for k in ALL_PASSES]
+    cases["passes_cornell_principled"] = d
+    d = scenes.cornell(W, H, materials="image")
+    d.passes = [scenes.PASS[k] for k in ALL_PASSES if k != "mist"]
+    cases["passes_cornell_image"] = d
+    d = _replace(scenes.default_cube(W, H, world="env_equirect"), "<background>",
+                 '<background transparent="true">')
+    d.passes = [scenes.PASS[k] for k in ("background", "emission", "diffuse_direct",
+                                         "glossy_direct", "normal", "depth", "mist")]
+    cases["passes_cube_env_transparent_film"] = d
+    d = scenes.cornell(W, H, materials="principled", light="mesh")
+    d.passes = [scenes.PASS[k] for k in ("emission", "diffuse_direct", "diffuse_indirect",
+                                         "glossy_direct", "glossy_indirect", "shadow")]
+    cases["passes_cornell_mesh_light"] = d
+    d = scenes.cornell(W, H, materials="principled")
+    d.passes = [scenes.PASS[k] for k in ("depth", "normal", "uv", "object_id", "material_id")]
+    cases["passes_data_only"] = d
+    d = _replace(scenes.cornell(W, H, materials="principled"), 'use_mis="true"',
+                 'use_mis="true" use_glossy="false"')
+    cases["light_invisible_to_glossy_rays"] = d
+    return cases
+
+
+def _replace(desc, old, new):
+    assert old in desc.xml, old
+    desc.xml = desc.xml.replace(old, new)
+    return desc
+
+
 def ao_cases():
     """World ambient occlusion (kernel_path_ao): a second shadow ray per path and bounce,
     cosine-sampled around the averaged diffuse normal, short and long reach."""
