@@ -1012,6 +1012,8 @@ int b200_set_option(b200_ctx *ctx, const char *name, int64_t value)
     ctx->opt_trace_blocks_per_sm = value;
   else if (strcmp(name, "sync_iterations") == 0)
     ctx->opt_sync_iterations = value;
+  else if (strcmp(name, "sort_tiles") == 0)
+    ctx->opt_sort_tiles = value;
   else
     return fail(ctx, B200_ERR_INVALID, std::string("unknown option ") + name);
   return B200_OK;

@@ -76,6 +76,7 @@ struct b200_ctx {
   float *d_debug = nullptr; /* 16 bounces x 32 floats when "debug_slot" >= 0 */
   int64_t opt_refill_threshold = 0;
   int64_t opt_trace_blocks_per_sm = 0;
+  int64_t opt_sort_tiles = 0;      /* experiment: sort by shader inside 2048-entry tiles */
   int64_t opt_sync_iterations = 0; /* A/B: stop the stream for the counters every bounce */
 
   /* k_shade_surface<lean / lean + multi-scatter / full / full + render passes>: grid size

@@ -87,6 +87,10 @@ struct PathSoA {
    * sh_pass[2 qi] = glossy | shadow-pass weight, sh_pass[2 qi + 1] = transmission | 1) */
   float *pass;
   float4 *sh_pass;
+  /* 1: q_sorted is ordered by key inside every tile of SORT_TILE queue entries
+   * (k_sort_tiles), misses flagged in the sign bit of the queue position; 0: one global
+   * counting sort, segment bounds in the counters */
+  int sort_tiles;
   /* Transparent shadows (only allocated when integrator.transparent_shadows): shadow rays
    * whose first hit is a transparent surface step from surface to surface
    * (kernel_shadow.h:300-352).  Two ping-pong queues of (ray, index into the shadow
@@ -541,6 +545,75 @@ __global__ void __launch_bounds__(WF_BLOCK) k_sort_scatter(PathSoA p)
   }
 }
 
+
+/* Sort by shader INSIDE tiles of SORT_TILE consecutive queue entries - an experiment kept
+ * behind b200_set_option("sort_tiles", 1), NOT the default.
+ *
+ * Idea: a global sort by shader makes warps run one shader program, but consecutive
+ * threads then hold paths from anywhere in the queue; sorting only within a 2048-entry
+ * window would keep a block's gathers inside one window (every sector used in full while
+ * it is in L1) at the price of a few mixed warps per tile.  Measured on B200 (tools/
+ * r02_run12.sh, profiles/r02i_sort_tiles_ab.txt): Cornell 128 spp 372 -> 567 ms, startup
+ * scene 51 -> 65 ms, terrain 77 -> 88 ms, instanced 349 -> 362 ms - clearly slower.  With
+ * the global sort the whole device runs ONE shader program at a time (the shade kernel is
+ * ~100 KB of SASS; per-tile order has every SM cycling through all programs at once and
+ * the instruction-cache stalls, already 3.7 per issue, take over), and the locality the
+ * tiles were meant to add is largely there already: k_sort_scatter reserves a key's
+ * output range per tile, so a warp's 32 entries of the global order come from one or two
+ * 2048-entry windows anyway.  Entry = (queue position | miss flag in the sign bit, path
+ * index); key 0 (miss) comes first in a tile. */
+#define SORT_TILE (SORT_ITEMS * WF_BLOCK)
+#define SORT_TILE_MAX_KEYS 16
+__global__ void __launch_bounds__(WF_BLOCK) k_sort_tiles(PathSoA p)
+{
+  __shared__ unsigned int s_cnt[WF_SMALL_KEYS], s_off[WF_SMALL_KEYS];
+  WFCounters *c = p.counters;
+  const unsigned int n = c->n_active;
+  const unsigned int lane = threadIdx.x & 31u;
+  const unsigned int lt_mask = (1u << lane) - 1u;
+  for (unsigned int tile = blockIdx.x * SORT_TILE; tile < n; tile += gridDim.x * SORT_TILE) {
+    if (threadIdx.x < WF_SMALL_KEYS)
+      s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    unsigned int key[SORT_ITEMS], rank[SORT_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; k++) {
+      const unsigned int qi = tile + k * WF_BLOCK + threadIdx.x;
+      key[k] = (qi < n) ? min(p.key[qi], (unsigned int)(WF_SMALL_KEYS - 1)) : 0xffffffffu;
+      const unsigned int peers = __match_any_sync(0xffffffffu, key[k]);
+      const unsigned int leader = __ffs(peers) - 1u;
+      unsigned int base = 0;
+      if (lane == leader && qi < n)
+        base = atomicAdd(&s_cnt[key[k]], __popc(peers));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      rank[k] = base + __popc(peers & lt_mask);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) { /* exclusive scan of the 64 counters, two per lane */
+      const unsigned int a = s_cnt[2 * lane], b = s_cnt[2 * lane + 1];
+      unsigned int incl = a + b;
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o)
+          incl += v;
+      }
+      s_off[2 * lane] = incl - (a + b);
+      s_off[2 * lane + 1] = incl - b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; k++) {
+      const unsigned int qi = tile + k * WF_BLOCK + threadIdx.x;
+      if (qi < n) {
+        const unsigned int pos = tile + s_off[key[k]] + rank[k];
+        p.q_sorted[pos] = make_int2((int)(qi | (key[k] == 0u ? 0x80000000u : 0u)),
+                                    p.q_active[qi]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 /* --------------------------------------------------- lamp emission (MIS) */
 
 /* kernel_path.h:86-113 + kernel_emission.h:235-286: emission of lamps hit by the
@@ -589,11 +662,14 @@ template<bool EXT, bool PASSES = false>
 __global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(PathSoA p)
 {
   WFCounters *c = p.counters;
-  const unsigned int n = c->offsets[1]; /* key 0 segment */
+  /* the key 0 segment of the global sort, or the flagged entries of every tile */
+  const unsigned int n = p.sort_tiles ? c->n_active : c->offsets[1];
   for (unsigned int qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n;
        qi += gridDim.x * blockDim.x) {
     const int2 qs = p.q_sorted[qi];
-    const int qpos = qs.x, i = qs.y;
+    if (p.sort_tiles && qs.x >= 0)
+      continue;
+    const int qpos = qs.x & 0x7fffffff, i = qs.y;
     const float4 r0 = p.ray_P_t[qpos];
     const float4 r1 = p.ray_D[qpos];
     const float4 tp = p.throughput[i];
@@ -684,8 +760,8 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
   arena.q = arena_words;
 
   WFCounters *c = p.counters;
-  const unsigned int begin = c->offsets[1];
-  const unsigned int end = c->offsets[num_keys + 1];
+  const unsigned int begin = p.sort_tiles ? 0u : c->offsets[1];
+  const unsigned int end = p.sort_tiles ? c->n_active : c->offsets[num_keys + 1];
   const unsigned int total = end - begin;
   /* the grid-stride loop is uniform per block: block_append2 has barriers */
   const unsigned int rounds = (total + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
@@ -694,8 +770,10 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
     bool want_next = false, want_shadow = false;
     int i = -1;
     float4 out_ray_P = make_float4(0.0f, 0.0f, 0.0f, 0.0f), out_ray_D = out_ray_P;
-    if (k < total) {
-      const int2 qs = p.q_sorted[begin + k];
+    int2 qs = make_int2(-1, -1);
+    if (k < total)
+      qs = p.q_sorted[begin + k]; /* tile order: a miss carries the sign bit */
+    if (qs.x >= 0) {
       const int qpos = qs.x;
       i = qs.y;
       const float4 r0 = p.ray_P_t[qpos];
@@ -2235,9 +2313,16 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
     else
       k_intersect_closest<false><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
     CUDA_TRY(ctx, cudaEventRecord(ev[1], st));
-    k_sort_count<<<grid_wide, WF_BLOCK, 0, st>>>(soa);
-    k_sort_scan<<<1, 256, 0, st>>>(soa, num_keys);
-    k_sort_scatter<<<grid_wide, WF_BLOCK, 0, st>>>(soa);
+    if (soa.sort_tiles) {
+      k_sort_tiles<<<grid_wide, WF_BLOCK, 0, st>>>(soa);
+      stats.kernel_launches += 6;
+    }
+    else {
+      k_sort_count<<<grid_wide, WF_BLOCK, 0, st>>>(soa);
+      k_sort_scan<<<1, 256, 0, st>>>(soa, num_keys);
+      k_sort_scatter<<<grid_wide, WF_BLOCK, 0, st>>>(soa);
+      stats.kernel_launches += 8;
+    }
     if (passes) {
       k_shade_background<true, true><<<grid_wide, WF_BLOCK, 0, st>>>(soa);
       k_shade_surface<true, true, true>
@@ -2294,7 +2379,6 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
       }
     }
     k_iteration_end<<<8, 256, 0, st>>>(soa, num_keys, it);
-    stats.kernel_launches += 8;
     /* the reference copies the whole ray_state array every 16 iterations
      * (device_split_kernel.cpp:302-318); here 64 bytes per bounce */
     CUDA_TRY(ctx, cudaMemcpyAsync(pool->h_ring + (size_t)(it % WF_RING) * WF_RING_BYTES,
@@ -2353,6 +2437,7 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
 
       for (int attempt = 0;; attempt++) {
         PathSoA soa = pool->soa;
+        soa.sort_tiles = (num_keys <= SORT_TILE_MAX_KEYS && ctx->opt_sort_tiles) ? 1 : 0;
         soa.debug = ctx->d_debug;
         soa.debug_slot = (int)ctx->opt_debug_slot;
         CUDA_TRY(ctx, cudaMemsetAsync(soa.counters, 0, sizeof(WFCounters), st));
