@@ -197,6 +197,15 @@ int b200_texture_set(b200_ctx *ctx, int slot, const void *texture_info, size_t b
                      uint64_t pixels);
 int b200_texture_clear(b200_ctx *ctx, int slot);
 
+/* DeviceTask::SHADER with SHADER_EVAL_BACKGROUND - CUDADevice::shader
+ * (device_cuda_impl.cpp:2019-2093) for the one use the render path has of it: the light
+ * manager evaluates the world shader over an equirectangular grid to build the importance
+ * map of the background light (shade_background_pixels, render/light.cpp:38-102).
+ * `input` = uint4 per point, (u, v) as float bits; `output` = float4 per point, the colour
+ * is ADDED; points [shader_x, shader_x + shader_w).  Synchronous. */
+int b200_shader_eval_background(b200_ctx *ctx, uint64_t input, uint64_t output, int shader_x,
+                                int shader_w);
+
 /* Host-only scope check of a compiled SVM program (the `__svm_nodes` array built by
  * SVMShaderManager::device_update_shader, render/svm.cpp:70-133): the same walk
  * b200_bind_global runs, without a device or a context.  Returns B200_OK, or

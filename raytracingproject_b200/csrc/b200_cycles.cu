@@ -435,6 +435,12 @@ int b200_bind_global(b200_ctx *ctx, const char *name, uint64_t dptr, const void 
                                     "__prim_object",    "__object_node",    "__objects",
                                     "__svm_nodes",      "__lights",         "__curves",
                                     "__tri_patch",      "__attributes_map"};
+  static const char *bvh_inputs[] = {"__bvh_nodes",       "__bvh_leaf_nodes",  "__prim_tri_verts",
+                                     "__prim_tri_index",  "__prim_visibility", "__prim_object",
+                                     "__object_node",     "__objects"};
+  for (const char *k : bvh_inputs)
+    if (strcmp(k, name) == 0)
+      ctx->bvh_dirty = true;
   HostArray ha;
   ha.dptr = dptr;
   ha.bytes = bytes;
@@ -673,7 +679,10 @@ static const HostArray *find_global(b200_ctx *ctx, const char *name)
 
 static int check_scope(b200_ctx *ctx);
 
-static int prepare_scene(b200_ctx *ctx)
+/* for_shader_task: DeviceTask::SHADER runs in the middle of Scene::device_update (the light
+ * manager evaluates the world shader before the film / integrator are final), so the
+ * scope check waits for the first render */
+static int prepare_scene(b200_ctx *ctx, bool for_shader_task = false)
 {
   if (!ctx->scene_dirty)
     return B200_OK;
@@ -689,22 +698,23 @@ static int prepare_scene(b200_ctx *ctx)
   const HostArray *objects = find_global(ctx, "__objects");
   if (!leaves || !verts || !tri_index || !vis || !pobj || !objects)
     return fail(ctx, B200_ERR_NOT_READY, "BVH arrays are not bound (scene without geometry?)");
-  int rc = check_scope(ctx);
+  int rc = for_shader_task ? B200_OK : check_scope(ctx);
   if (rc)
     return rc;
 
   DeviceGuard guard(ctx->ordinal);
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-  if (ctx->d_nodes)
-    cudaFree(ctx->d_nodes);
-  if (ctx->d_records)
-    cudaFree(ctx->d_records);
-  ctx->d_nodes = ctx->d_records = nullptr;
   const uint4 *dev_nodes = nullptr;
   const float4 *dev_records = nullptr;
   uint32_t bvh_root = 0;
   const uint32_t layout = (uint32_t)kd_host<int>(ctx, KD_BVH_LAYOUT);
-  if (layout == B200_BVH_LAYOUT_BVH8) {
+  if (layout != B200_BVH_LAYOUT_BVH8 && !ctx->bvh_dirty && ctx->d_nodes && ctx->d_records) {
+    /* only KernelData or non-BVH arrays changed: the BVH8 derived last time still holds */
+    dev_nodes = (const uint4 *)ctx->d_nodes;
+    dev_records = (const float4 *)ctx->d_records;
+    bvh_root = ctx->bvh_root8;
+  }
+  else if (layout == B200_BVH_LAYOUT_BVH8) {
     /* the host's BVH8 class packed the device layout: traverse the arrays as bound */
     if (!nodes || nodes->bytes % sizeof(BVH8Node) != 0 || leaves->bytes % 48 != 0)
       return fail(ctx, B200_ERR_INVALID, "BVH_LAYOUT_BVH8: __bvh_nodes / __bvh_leaf_nodes are "
@@ -722,6 +732,11 @@ static int prepare_scene(b200_ctx *ctx)
     ctx->bvh_info.host_packed = 1;
   }
   else {
+    if (ctx->d_nodes)
+      cudaFree(ctx->d_nodes);
+    if (ctx->d_records)
+      cudaFree(ctx->d_records);
+    ctx->d_nodes = ctx->d_records = nullptr;
     b200::BVH2Input in;
     memset(&in, 0, sizeof(in));
     in.nodes = nodes ? (const float *)nodes->host.data() : nullptr;
@@ -758,6 +773,8 @@ static int prepare_scene(b200_ctx *ctx)
     dev_nodes = (const uint4 *)ctx->d_nodes;
     dev_records = (const float4 *)ctx->d_records;
     bvh_root = out.root;
+    ctx->bvh_root8 = out.root;
+    ctx->bvh_dirty = false;
 
     memset(&ctx->bvh_info, 0, sizeof(ctx->bvh_info));
     ctx->bvh_info.num_nodes = out.nodes.size();
@@ -800,6 +817,8 @@ static int prepare_scene(b200_ctx *ctx)
   ds.attributes_float2 = (const float2 *)ptr("__attributes_float2");
   ds.attributes_float3 = (const float4 *)ptr("__attributes_float3");
   ds.attributes_uchar4 = (const uchar4 *)ptr("__attributes_uchar4");
+  ds.light_background_marginal_cdf = (const float2 *)ptr("__light_background_marginal_cdf");
+  ds.light_background_conditional_cdf = (const float2 *)ptr("__light_background_conditional_cdf");
   if (ctx->d_texture_info) {
     cudaFree(ctx->d_texture_info);
     ctx->d_texture_info = nullptr;

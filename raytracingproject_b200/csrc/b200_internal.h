@@ -52,6 +52,8 @@ struct b200_ctx {
   int svm_max_image_slot = -1; /* highest image slot the bound program names */
   std::vector<uint8_t> kernel_data;
   bool scene_dirty = true; /* BVH8 / constant block must be (re)built */
+  bool bvh_dirty = true;   /* an array the BVH8 is derived from was (re)bound */
+  uint32_t bvh_root8 = 0;  /* root of the BVH8 derived last (BVH2 hosts) */
   /* this context's constant block: the __constant__ DeviceScene is one per GPU, so a
    * context re-uploads its copy when another context of the same GPU used the device
    * last (DeviceUse in b200_cycles.cu) */

@@ -41,6 +41,7 @@ struct f3 {
 #define CY_M_PI_F 3.1415926535897932f
 #define CY_M_PI_2_F 1.5707963267948966f
 #define CY_M_2PI_F 6.2831853071795864f
+#define CY_M_4PI_F 12.566370614359172f
 #define CY_M_1_PI_F 0.3183098861837067f
 #define CY_M_PI_4_F 0.7853981633974483f
 

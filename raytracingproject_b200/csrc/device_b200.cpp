@@ -251,8 +251,18 @@ class B200Device : public Device {
 
   void thread_run(DeviceTask &task)
   {
+    if (task.type == DeviceTask::SHADER && task.shader_eval_type == SHADER_EVAL_BACKGROUND) {
+      /* the light manager's evaluation of the world shader for the background importance
+       * map (render/light.cpp:38-102; CUDADevice::shader, device_cuda_impl.cpp:2019-2093) */
+      check(b200_shader_eval_background(ctx, (uint64_t)task.shader_input,
+                                        (uint64_t)task.shader_output, task.shader_x,
+                                        task.shader_w),
+            "shader(background)");
+      return;
+    }
     if (task.type != DeviceTask::RENDER) {
-      set_error("B200 device: only RENDER and FILM_CONVERT tasks are in scope");
+      set_error("B200 device: of the SHADER tasks only the background evaluation is in scope "
+                "(no baking, no displacement)");
       return;
     }
     B200CancelProbe probe = {&task, &task_pool};
@@ -515,8 +525,17 @@ class B200MultiDevice : public Device {
 
   void thread_run(DeviceTask &task)
   {
+    if (task.type == DeviceTask::SHADER && task.shader_eval_type == SHADER_EVAL_BACKGROUND) {
+      /* on the first GPU: its allocation is the one mem_copy_from reads */
+      check(0, b200_shader_eval_background(ctxs[0], (uint64_t)task.shader_input,
+                                           (uint64_t)task.shader_output, task.shader_x,
+                                           task.shader_w),
+            "shader(background)");
+      return;
+    }
     if (task.type != DeviceTask::RENDER) {
-      set_error("B200 device: only RENDER and FILM_CONVERT tasks are in scope");
+      set_error("B200 device: of the SHADER tasks only the background evaluation is in scope "
+                "(no baking, no displacement)");
       return;
     }
     const int n = (int)ctxs.size();

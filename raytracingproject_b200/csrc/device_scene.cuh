@@ -40,6 +40,9 @@ struct DeviceScene {
   const float2 *attributes_float2;
   const float4 *attributes_float3;
   const uchar4 *attributes_uchar4;
+  /* world importance map (light_background.cuh): float2 (function value, CDF) entries */
+  const float2 *light_background_marginal_cdf;
+  const float2 *light_background_conditional_cdf;
   const uint8_t *texture_info; /* TextureInfo[], SIZEOF_TEXTURE_INFO each, data = device ptr */
   uint32_t num_textures;
   uint32_t pad1;

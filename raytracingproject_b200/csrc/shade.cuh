@@ -1226,7 +1226,9 @@ CY_DEV float rect_light_sample(f3 P, f3 *light_p, f3 axisu, f3 axisv, float rand
     return 0.0f;
 }
 
-/* kernel_light.h:40-168 (no background light; triangle lights: light_tri.cuh) */
+#include "light_background.cuh"
+
+/* kernel_light.h:40-168 (triangle lights: light_tri.cuh) */
 CY_DEV bool lamp_light_sample(int lamp, float randu, float randv, f3 P, LightSampleG *ls)
 {
   const uint8_t *kl = light_ptr(lamp);
@@ -1255,7 +1257,13 @@ CY_DEV bool lamp_light_sample(int lamp, float randu, float randv, f3 P, LightSam
     ls->eval_fac = ls->pdf;
   }
   else if (type == CY_LIGHT_BACKGROUND) {
-    return false; /* refused by check_scope */
+    /* the world as a light dome (kernel_light.h:72-83), importance-sampled by its map */
+    const f3 D = -background_light_sample(randu, randv, &ls->pdf);
+    ls->P = D;
+    ls->Ng = D;
+    ls->D = -D;
+    ls->t = FLT_MAX;
+    ls->eval_fac = 1.0f;
   }
   else {
     ls->P = kl_float3(kl, KL_CO);
@@ -1520,6 +1528,28 @@ CY_DEV f3 direct_emissive_eval(ShaderDataG &emission_sd, PathDepths depths, Ligh
     if ((ls->prim != CY_PRIM_NONE) && dot(ls->Ng, I) < 0.0f)
       ls->Ng = -ls->Ng;
   }
+  else if (ls->type == CY_LIGHT_BACKGROUND) {
+    /* kernel_emission.h:64-77: the world shader for the sampled direction
+     * (shader_setup_from_background with ray.D = ls->D) */
+    const f3 rayD = ls->D;
+    emission_sd.P = rayD;
+    emission_sd.N = -rayD;
+    emission_sd.Ng = -rayD;
+    emission_sd.I = -rayD;
+    emission_sd.shader = kd_int(KD_BG_SURFACE_SHADER);
+    emission_sd.flag = shader_flags(emission_sd.shader);
+    emission_sd.object_flag = 0;
+    emission_sd.ray_length = 0.0f;
+    emission_sd.object = -1;
+    emission_sd.prim = CY_PRIM_NONE;
+    emission_sd.lamp = -1;
+    emission_sd.type = 0;
+    emission_sd.u = emission_sd.v = 0.0f;
+    emission_sd.dPdu = zero3();
+    shader_eval_emission<EXT>(emission_sd, depths, CY_PATH_RAY_EMISSION);
+    if (emission_sd.flag & CY_SD_EMISSION)
+      eval = emission_sd.closure_emission_background;
+  }
   else {
     /* shader_setup_from_sample (kernel_shader.h:244-345): a lamp, or a point on an
      * emissive triangle */
@@ -1579,7 +1609,7 @@ CY_DEV f3 direct_emissive_eval(ShaderDataG &emission_sd, PathDepths depths, Ligh
   return eval;
 }
 
-/* kernel_emission.h:288-340 without background MIS (refused by check_scope) */
+/* kernel_emission.h:288-340 */
 template<bool EXT>
 CY_DEV f3 indirect_background(ShaderDataG &emission_sd, const PathStateG &state, f3 rayD)
 {
@@ -1614,6 +1644,12 @@ CY_DEV f3 indirect_background(ShaderDataG &emission_sd, const PathStateG &state,
     shader_eval_emission<EXT>(emission_sd, path_depths(state), state.flag | CY_PATH_RAY_EMISSION);
     if (emission_sd.flag & CY_SD_EMISSION)
       L = emission_sd.closure_emission_background;
+  }
+  /* the world is also in the light distribution: weight the BSDF-sampled hit against the
+   * pdf light sampling would have had for this direction (kernel_emission.h:325-337) */
+  if (!(state.flag & CY_PATH_RAY_MIS_SKIP) && kd_int(KD_BG_USE_MIS)) {
+    const float pdf = background_light_pdf(rayD);
+    return L * power_heuristic(state.ray_pdf, pdf);
   }
   return L;
 }

@@ -1653,6 +1653,55 @@ __global__ void k_film_add(float4 *dst, const float4 *src, size_t n4)
   }
 }
 
+
+/* ------------------------------------------------------- DeviceTask::SHADER */
+
+/* kernel_background_evaluate (kernel_bake.h:474-510) - what the host runs once per scene
+ * to build the world importance map (shade_background_pixels, render/light.cpp:38-102):
+ * input[i] = (u, v) of an equirectangular pixel as float bits, output[i] += the world
+ * shader's colour in that direction. */
+template<bool EXT>
+__global__ void __launch_bounds__(WF_BLOCK) k_background_evaluate(const uint4 *input,
+                                                                  float4 *output, int first,
+                                                                  int count)
+{
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+    const int i = first + k;
+    const uint4 in = input[i];
+    const f3 D = equirectangular_to_direction(__uint_as_float(in.x), __uint_as_float(in.y));
+    const int shader = kd_int(KD_BG_SURFACE_SHADER);
+    f3 color = zero3();
+    if (!shader_constant_emission_eval(shader, &color)) {
+      ShaderDataG sd;
+      sd.P = D;
+      sd.N = -D;
+      sd.Ng = -D;
+      sd.I = -D;
+      sd.shader = shader;
+      sd.flag = shader_flags(shader);
+      sd.object_flag = 0;
+      sd.ray_length = 0.0f;
+      sd.object = -1;
+      sd.prim = CY_PRIM_NONE;
+      sd.lamp = -1;
+      sd.type = 0;
+      sd.u = sd.v = 0.0f;
+      sd.dPdu = zero3();
+      PathDepths depths;
+      depths.bounce = depths.diffuse = depths.glossy = depths.transmission = 0;
+      depths.transparent = 0;
+      shader_eval_emission<EXT>(sd, depths, CY_PATH_RAY_EMISSION);
+      if (sd.flag & CY_SD_EMISSION)
+        color = sd.closure_emission_background;
+    }
+    float4 o = output[i];
+    o.x += color.x;
+    o.y += color.y;
+    o.z += color.z;
+    output[i] = o;
+  }
+}
+
 /* ============================================================ host side */
 
 static void free_pool(b200_ctx *ctx)
@@ -2130,8 +2179,18 @@ static int check_scope(b200_ctx *ctx)
     why = "the shader program samples image slot " + std::to_string(ctx->svm_max_image_slot) +
           " but only " + std::to_string(bound_image_slots(ctx)) +
           " image slots are bound (tex_alloc / b200_texture_set)";
-  else if (I(KD_BG_USE_MIS))
-    why = "background importance sampling is outside the hot-path scope";
+  else if (I(KD_BG_USE_MIS) && (F(KD_BG_PORTAL_WEIGHT) > 0.0f || I(KD_BG_NUM_PORTALS) > 0))
+    why = "light portals are outside the hot-path scope";
+  else if (I(KD_BG_USE_MIS) && F(KD_BG_SUN_WEIGHT) > 0.0f)
+    why = "the sky texture's sun disc (background sun sampling) is outside the hot-path scope";
+  else if (I(KD_BG_USE_MIS) && F(KD_BG_MAP_WEIGHT) > 0.0f &&
+           (!find_global(ctx, "__light_background_marginal_cdf") ||
+            !find_global(ctx, "__light_background_conditional_cdf") ||
+            find_global(ctx, "__light_background_marginal_cdf")->bytes <
+                (size_t)(I(KD_BG_MAP_RES_Y) + 1) * 8 ||
+            find_global(ctx, "__light_background_conditional_cdf")->bytes <
+                (size_t)(I(KD_BG_MAP_RES_X) + 1) * I(KD_BG_MAP_RES_Y) * 8))
+    why = "background importance sampling needs the world map CDF arrays";
   else if (I(KD_FILM_PASS_DENOISING_DATA) || I(KD_FILM_PASS_ADAPTIVE_AUX_BUFFER) ||
            I(KD_FILM_PASS_SAMPLE_COUNT) || I(KD_FILM_CRYPTOMATTE_PASSES))
     why = "denoising data, adaptive sampling and cryptomatte passes are outside the hot-path "
@@ -2543,6 +2602,31 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
   }
   stats.svm_extended = svm_ext ? 1 : 0;
   ctx->stats = stats;
+  return B200_OK;
+}
+
+/* DeviceTask::SHADER with SHADER_EVAL_BACKGROUND (CUDADevice::shader,
+ * device_cuda_impl.cpp:2019-2093): the world shader evaluated for `shader_w` directions
+ * starting at `shader_x`.  Runs before the scene's BVH exists (the light manager updates
+ * ahead of the geometry), so only the constant block's shader arrays are needed. */
+int b200_shader_eval_background(b200_ctx *ctx, uint64_t input, uint64_t output, int shader_x,
+                                int shader_w)
+{
+  if (!ctx || !input || !output || shader_w < 0)
+    return B200_ERR_INVALID;
+  if (!ctx->have_data)
+    return fail(ctx, B200_ERR_NOT_READY, "KernelData not uploaded");
+  DeviceUse device_use(ctx);
+  int rc = prepare_scene(ctx, true);
+  if (rc)
+    return rc;
+  ctx->scene_dirty = true; /* the scope check is still due at the first render */
+  DeviceGuard guard(ctx->ordinal);
+  const int grid = std::max(1, std::min(launch_grid(ctx, 8), (shader_w + WF_BLOCK - 1) / WF_BLOCK));
+  k_background_evaluate<true><<<grid, WF_BLOCK, 0, ctx->stream>>>(
+      (const uint4 *)input, (float4 *)output, shader_x, shader_w);
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return B200_OK;
 }
 

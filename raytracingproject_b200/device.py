@@ -39,6 +39,7 @@ EXPORTS = [
     "b200_synchronize", "b200_set_option", "b200_set_stream", "b200_debug_read",
     "b200_validate_svm", "b200_device_pci_id", "b200_set_cancel_callback", "b200_film_allreduce",
     "b200_texture_set", "b200_texture_clear", "b200_bvh8_pack", "b200_bvh8_free",
+    "b200_shader_eval_background",
 ]
 
 BVH_LAYOUT_BVH2, BVH_LAYOUT_BVH8 = 1 << 0, 1 << 3  # kernel_types.h BVHLayout + INTEGRATION.md
@@ -141,6 +142,7 @@ def load_library():
     L.b200_bvh8_pack.argtypes = [C.POINTER(PackedBVH2), C.POINTER(PackedBVH8), C.c_char_p, sz]
     L.b200_bvh8_free.argtypes = [C.POINTER(PackedBVH8)]
     L.b200_bvh8_free.restype = None
+    L.b200_shader_eval_background.argtypes = [vp, u64, u64, C.c_int, C.c_int]
     L.b200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.b200_synchronize.argtypes = [vp]
     L.b200_set_option.argtypes = [vp, C.c_char_p, C.c_int64]

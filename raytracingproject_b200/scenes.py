@@ -745,7 +745,7 @@ def box_mesh(lo, hi):
 # ---------------------------------------------------------------- config 1
 def default_cube(width=1920, height=1080, spp=64, material="principled", max_bounce=12,
                  lights="point", cam_type="perspective", cam_extra="", distribution="GGX",
-                 world="grey"):
+                 world="grey", world_light=0):
     """BASELINE config 1 - Blender's startup scene, values extracted from
     release/datafiles/startup.blend.  `lights`: "point" (the
     startup scene), "falloff" (its lamp shader goes through a Light Falloff node), "spot"
@@ -753,8 +753,10 @@ def default_cube(width=1920, height=1080, spp=64, material="principled", max_bou
     edge) or "mixed" (point + round area + sun: three entries in the light
     distribution) - variants used by the parity tests only.  `world`: "grey" (the
     startup scene), "env_equirect" / "env_mirrorball" (an Environment Texture node lights
-    the scene: a float image looked up by the ray direction; no background importance
-    sampling, which would need a background light)."""
+    the scene: a float image looked up by the ray direction).  `world_light` > 0 adds a
+    background light of that map resolution: the world enters the light distribution and
+    is importance-sampled by its luminance map (background MIS, kernel_light_background.h),
+    which the host builds from one DeviceTask::SHADER evaluation of the world shader."""
     cam = euler_xyz_camera((7.358891, -6.925791, 4.958309), (1.109319, 0.0, 0.814928))
     fov = 2.0 * np.arctan(0.5 * 36.0 / 50.0 / (width / height))
     xml = "<cycles>\n"
@@ -811,12 +813,16 @@ def default_cube(width=1920, height=1080, spp=64, material="principled", max_bou
     else:
         raise ValueError(lights)
     xml += _state("lamp", body)
+    if world_light:
+        xml += _state("default_background",
+                      '<light type="background" map_resolution="%d" use_mis="true" '
+                      'strength="1 1 1"/>\n' % int(world_light))
     xml += "</cycles>\n"
     P, tris = box_mesh((-1, -1, -1), (1, 1, 1))
     multi = "_multiscatter" if (material == "principled" and distribution != "GGX") else ""
     return SceneDesc(
         "default_cube_" + material + multi + ("" if lights == "point" else "_" + lights) +
-        ("" if world == "grey" else "_" + world), xml,
+        ("" if world == "grey" else "_" + world) + ("_mis" if world_light else ""), xml,
         width, height,
         meshes=[MeshDesc(P, tris, "cube")], objects=[(0, np.eye(4, dtype=np.float32)[:3])],
         spp=spp, notes="config 1", images=images)

@@ -125,6 +125,27 @@ def image_cases():
     }
 
 
+def world_light_cases():
+    """The world as a light (background MIS): an environment texture lights the startup
+    scene and is importance-sampled through the luminance map the host builds from a
+    DeviceTask::SHADER evaluation of the world shader; diffuse and Principled cube, and the
+    passes on top (the world's light arrives in the direct passes, is_lamp = false)."""
+    cases = {
+        "cube_world_light": scenes.default_cube(W, H, world="env_equirect", world_light=64,
+                                                material="diffuse"),
+        "cube_world_light_principled": scenes.default_cube(W, H, world="env_equirect",
+                                                           world_light=128),
+        "cube_world_light_mirrorball": scenes.default_cube(W, H, world="env_mirrorball",
+                                                           world_light=64),
+    }
+    d = scenes.default_cube(W, H, world="env_equirect", world_light=64)
+    d.passes = [scenes.PASS[k] for k in ("diffuse_direct", "glossy_direct", "shadow",
+                                         "background", "diffuse_indirect")]
+    d.name += "_passes"
+    cases["cube_world_light_passes"] = d
+    return cases
+
+
 ALL_PASSES = ("depth", "normal", "uv", "object_id", "material_id", "mist", "emission",
               "background", "shadow", "diffuse_direct", "diffuse_indirect", "diffuse_color",
               "glossy_direct", "glossy_indirect", "glossy_color", "transmission_direct",

@@ -8,7 +8,7 @@ import pytest
 
 from scene_cases import (ao_cases, camera_cases, closure_cases, image_cases, light_cases,
                          pass_cases, principled_cases, sampling_cases, small_cases,
-                         texture_cases)
+                         texture_cases, world_light_cases)
 
 pytestmark = pytest.mark.gpu
 
@@ -256,6 +256,54 @@ def test_render_passes_match_reference(ref, device, name):
                 rs.close()
         finally:
             host.close()
+
+
+@pytest.mark.parametrize("name", ["cube_world_light", "cube_world_light_principled",
+                                  "cube_world_light_mirrorball", "cube_world_light_passes"])
+def test_world_light_matches_reference(ref, device, name):
+    """Background MIS (kernel_light_background.h): the world is in the light distribution,
+    sampled by its importance map, and BSDF-sampled background hits are MIS-weighted.
+    Python mirror: the map comes from the reference's own host update.  C++ shim: the
+    reference's LightManager runs DeviceTask::SHADER on THIS device
+    (b200_shader_eval_background) and builds the map from its answer - the map must agree
+    with the CPU device's, the film with the gates."""
+    from raytracingproject_b200.device import B200HostDevice
+    desc = world_light_cases()[name]
+    rs = ref.build_scene(desc)
+    try:
+        arrays = rs.device_arrays()
+        assert "__light_background_marginal_cdf" in arrays
+        cpu_marg = arrays["__light_background_marginal_cdf"][0].view(np.float32).copy()
+        cpu_cond = arrays["__light_background_conditional_cdf"][0].view(np.float32).copy()
+        device.upload_scene(arrays, rs.textures())
+        ref_img, _ = rs.render(0, SPP, tile_size=64)
+        got = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP).copy()
+        off, _ = rs.pass_offset(1)
+        image_gates(ref_img[..., off:off + 4], got[..., off:off + 4], SPP, name)
+        if desc.passes:
+            d = np.abs(ref_img - got).max() / SPP
+            print(name, "all passes max|d|", d)
+            assert d < 1e-3 * max(1.0, float(np.abs(ref_img).max()) / SPP)
+    finally:
+        rs.close()
+    host = B200HostDevice(0)
+    try:
+        rs = ref.build_scene(desc, external_device=host.ptr)
+        try:
+            marg = rs.global_array("__light_background_marginal_cdf")[0].view(np.float32)
+            cond = rs.global_array("__light_background_conditional_cdf")[0].view(np.float32)
+            assert marg.shape == cpu_marg.shape and cond.shape == cpu_cond.shape
+            print(name, "importance map: max|d| marginal %.3e conditional %.3e" % (
+                np.abs(marg - cpu_marg).max(), np.abs(cond - cpu_cond).max()))
+            np.testing.assert_allclose(marg, cpu_marg, rtol=1e-4, atol=1e-6)
+            np.testing.assert_allclose(cond, cpu_cond, rtol=1e-4, atol=1e-6)
+            shim, _ = rs.render(0, SPP, tile_size=64)
+            assert host.error_message() == ""
+            image_gates(ref_img[..., off:off + 4], shim[..., off:off + 4], SPP, name + " (shim)")
+        finally:
+            rs.close()
+    finally:
+        host.close()
 
 
 def test_program_with_image_nodes_needs_bound_images(ref, device):
