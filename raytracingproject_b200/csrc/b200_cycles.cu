@@ -600,6 +600,7 @@ int b200_bvh8_pack(const b200_packed_bvh2 *in, b200_packed_bvh8 *out, char *err,
   bi.node_unaligned_flag = CY_PATH_RAY_NODE_UNALIGNED;
   bi.primitive_all = CY_PRIMITIVE_ALL;
   bi.primitive_triangle = CY_PRIMITIVE_TRIANGLE;
+  bi.tighten_instances = true;
   b200::BVH8Output bo;
   std::string why;
   if (!bi.leaf_nodes || !b200::build_bvh8(bi, bo, why)) {
@@ -757,6 +758,8 @@ static int prepare_scene(b200_ctx *ctx, bool for_shader_task = false)
     in.node_unaligned_flag = CY_PATH_RAY_NODE_UNALIGNED;
     in.primitive_all = CY_PRIMITIVE_ALL;
     in.primitive_triangle = CY_PRIMITIVE_TRIANGLE;
+    in.tighten_instances = ctx->opt_loose_instances == 0;
+    in.instance_detail_boxes = (int)ctx->opt_instance_detail_boxes;
 
     b200::BVH8Output out;
     std::string err;
@@ -1033,6 +1036,17 @@ int b200_set_option(b200_ctx *ctx, const char *name, int64_t value)
     ctx->opt_sync_iterations = value;
   else if (strcmp(name, "sort_tiles") == 0)
     ctx->opt_sort_tiles = value;
+  else if (strcmp(name, "instance_detail_boxes") == 0) {
+    ctx->opt_instance_detail_boxes = value;
+    ctx->bvh_dirty = true;
+    ctx->scene_dirty = true;
+  }
+  else if (strcmp(name, "loose_instances") == 0) {
+    /* A/B: keep the host's instance bounds in the TLAS (BVH2 hosts only) */
+    ctx->opt_loose_instances = value;
+    ctx->bvh_dirty = true;
+    ctx->scene_dirty = true;
+  }
   else
     return fail(ctx, B200_ERR_INVALID, std::string("unknown option ") + name);
   return B200_OK;

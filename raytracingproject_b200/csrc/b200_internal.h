@@ -78,6 +78,8 @@ struct b200_ctx {
   float *d_debug = nullptr; /* 16 bounces x 32 floats when "debug_slot" >= 0 */
   int64_t opt_refill_threshold = 0;
   int64_t opt_trace_blocks_per_sm = 0;
+  int64_t opt_instance_detail_boxes = 0; /* 0 = builder default */
+  int64_t opt_loose_instances = 0; /* A/B: host's instance bounds, no tightening */
   int64_t opt_sort_tiles = 0;      /* experiment: sort by shader inside 2048-entry tiles */
   int64_t opt_sync_iterations = 0; /* A/B: stop the stream for the counters every bounce */
 

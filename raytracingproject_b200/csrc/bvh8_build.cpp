@@ -145,6 +145,113 @@ struct Builder {
     return wb;
   }
 
+  /* ---- tighter world bounds for instances ----
+   * The reference bounds an instance by transforming the mesh's AABB
+   * (Object::compute_bounds, render/object.cpp): for a rotated object that is the AABB of
+   * a rotated box, up to sqrt(3) wider per axis than the object.  The union of the
+   * transformed boxes of the BLAS nodes a few levels down hugs the geometry instead (for
+   * the rocks of config 4 the boxes at the mesh AABB's corners are simply not there), and
+   * a ray that misses it never pays the instance push / pop - the least efficient part of
+   * the traversal kernel.  Both boxes are conservative, so is their intersection. */
+  std::unordered_map<int, std::vector<Box>> blas_detail_cache;
+
+  const std::vector<Box> &blas_detail(int blas_addr)
+  {
+    auto it = blas_detail_cache.find(blas_addr);
+    if (it != blas_detail_cache.end())
+      return it->second;
+    struct Open {
+      int addr;
+      Box box;
+    };
+    std::vector<Open> open;
+    std::vector<Box> done;
+    open.push_back({blas_addr, bvh2_box(blas_addr)});
+    /* split the box with the largest surface until there are enough of them */
+    /* default: as many boxes as a budget of 8 M box transforms over all instances allows,
+     * between 16 and 1024 (measured on config 4, profiles/r02j_instance_bounds_sweep.txt:
+     * 64 boxes recover most of it, 1024 the rest at 0.2 s of host time for 10 k instances) */
+    size_t want = (size_t)in.instance_detail_boxes;
+    if (want == 0) {
+      want = ((size_t)8 << 20) / std::max<size_t>(in.num_objects, 1);
+      want = std::min<size_t>(std::max<size_t>(want, 16), 1024);
+    }
+    while (!open.empty() && open.size() + done.size() < want) {
+      size_t best = 0;
+      for (size_t k = 1; k < open.size(); k++)
+        if (open[k].box.half_area() > open[best].box.half_area())
+          best = k;
+      Open o = open[best];
+      open.erase(open.begin() + best);
+      if (o.addr < 0 || (size_t)o.addr + 4 > in.num_nodes_f4) {
+        done.push_back(o.box); /* a leaf: as tight as it gets here */
+        continue;
+      }
+      const float *n = &in.nodes[4 * (size_t)o.addr];
+      Box c0, c1;
+      c0.lo[0] = n[4], c1.lo[0] = n[5], c0.hi[0] = n[6], c1.hi[0] = n[7];
+      c0.lo[1] = n[8], c1.lo[1] = n[9], c0.hi[1] = n[10], c1.hi[1] = n[11];
+      c0.lo[2] = n[12], c1.lo[2] = n[13], c0.hi[2] = n[14], c1.hi[2] = n[15];
+      open.push_back({as_int(n[2]), c0});
+      open.push_back({as_int(n[3]), c1});
+    }
+    for (const Open &o : open)
+      done.push_back(o.box);
+    return blas_detail_cache.emplace(blas_addr, std::move(done)).first->second;
+  }
+
+  Box instance_tight_box(int object, const Box &host_box)
+  {
+    const float *tfm = (const float *)(in.objects + (size_t)object * in.object_stride +
+                                       in.object_tfm_offset);
+    Box wb;
+    wb.reset();
+    for (const Box &ob : blas_detail(in.object_node[object])) {
+      if (!(ob.lo[0] <= ob.hi[0]))
+        continue; /* empty */
+      for (int c = 0; c < 8; c++) {
+        float p[3] = {(c & 1) ? ob.hi[0] : ob.lo[0], (c & 2) ? ob.hi[1] : ob.lo[1],
+                      (c & 4) ? ob.hi[2] : ob.lo[2]};
+        float q[3];
+        for (int r = 0; r < 3; r++)
+          q[r] = tfm[4 * r] * p[0] + tfm[4 * r + 1] * p[1] + tfm[4 * r + 2] * p[2] +
+                 tfm[4 * r + 3];
+        wb.grow(q);
+      }
+    }
+    /* the transform above is float arithmetic, and the kernel goes the other way through
+     * the inverse matrix: keep a margin */
+    for (int k = 0; k < 3; k++) {
+      float pad = 1e-5f * std::max(std::fabs(wb.lo[k]), std::fabs(wb.hi[k])) +
+                  1e-5f * (wb.hi[k] - wb.lo[k]) + 1e-30f;
+      wb.lo[k] = std::max(wb.lo[k] - pad, host_box.lo[k]);
+      wb.hi[k] = std::min(wb.hi[k] + pad, host_box.hi[k]);
+    }
+    if (!(wb.lo[0] <= wb.hi[0] && wb.lo[1] <= wb.hi[1] && wb.lo[2] <= wb.hi[2]))
+      return host_box; /* not a number somewhere: keep what the host said */
+    return wb;
+  }
+
+  /* instance leaves of bn[first ..) get their tight box, inner nodes the union of their
+   * children again (children are decoded after their parent: one backward sweep) */
+  void tighten_instances(int first)
+  {
+    bool any = false;
+    for (int i = first; i < (int)bn.size(); i++)
+      if (bn[i].object >= 0 && in.object_node && bn[i].box.lo[0] <= bn[i].box.hi[0]) {
+        bn[i].box = instance_tight_box(bn[i].object, bn[i].box);
+        any = true;
+      }
+    if (!any)
+      return;
+    for (int i = (int)bn.size() - 1; i >= first; i--)
+      if (bn[i].left >= 0 && bn[i].right >= 0) {
+        Box b = bn[bn[i].left].box;
+        b.grow(bn[bn[i].right].box);
+        bn[i].box = b;
+      }
+  }
+
   /* Split an oversized triangle leaf by the median of the centroids on the
    * longest axis until every leaf holds <= BVH8_MAX_LEAF_RECORDS. */
   int make_tri_leaf(std::vector<int> &prims)
@@ -661,9 +768,12 @@ struct Builder {
   /* Convert one BVH2 tree (TLAS or one BLAS) into BVH8; returns its root node. */
   uint32_t convert(int root_addr)
   {
+    const int first = (int)bn.size();
     int root = decode(root_addr);
     if (root < 0)
       return 0xffffffffu;
+    if (in.tighten_instances)
+      tighten_instances(first);
     run_dp(root);
     uint32_t root_index = (uint32_t)out.nodes.size();
     out.nodes.resize(out.nodes.size() + 1);

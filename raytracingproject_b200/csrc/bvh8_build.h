@@ -30,6 +30,10 @@ struct BVH2Input {
   size_t num_objects;
   int32_t root;                /* KernelData.bvh.root */
   uint32_t node_unaligned_flag, primitive_all, primitive_triangle;
+  /* bound instances by the transformed boxes of their BLAS's upper nodes instead of the
+   * host's transformed mesh AABB (see Builder::instance_tight_box) */
+  bool tighten_instances = true;
+  int instance_detail_boxes = 0; /* BLAS boxes per instance bound, 0 = the default (64) */
 };
 
 struct BVH8Output {

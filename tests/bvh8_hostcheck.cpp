@@ -137,6 +137,7 @@ void *hostcheck_build(const float *nodes, size_t n_nodes_f4, const float *leaves
   in.num_objects = num_objects; in.root = root;
   in.node_unaligned_flag = CY_PATH_RAY_NODE_UNALIGNED; in.primitive_all = CY_PRIMITIVE_ALL;
   in.primitive_triangle = CY_PRIMITIVE_TRIANGLE;
+  in.tighten_instances = true;
   Check *ck = new Check(); ck->objects = objects;
   std::string e;
   if (!build_bvh8(in, ck->out, e)) {
