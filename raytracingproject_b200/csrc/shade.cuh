@@ -24,6 +24,15 @@
 
 /* ------------------------------------------------------------- path state */
 
+/* inlining of the two largest shared pieces of the shading kernels, overridable for A/B
+ * builds (tools/variants.sh): -DMULTI_EVAL_ATTR="__device__ __noinline__" ... */
+#ifndef MULTI_EVAL_ATTR
+#  define MULTI_EVAL_ATTR CY_DEV
+#endif
+#ifndef LIGHT_SAMPLE_ATTR
+#  define LIGHT_SAMPLE_ATTR CY_DEV
+#endif
+
 struct PathStateG {
   uint32_t flag;
   uint32_t rng_hash;
@@ -997,7 +1006,7 @@ CY_DEV float power_heuristic(float a, float b)
  * colour, pdf by its sample weight), continuing the running sums of a sampled lobe
  * (_shader_bsdf_multi_eval, kernel_shader.h:556-582, no light passes) */
 template<bool EXT, bool MS = EXT>
-CY_DEV void shader_bsdf_multi_eval(ShaderDataG &sd, const LobeArena &arena, f3 omega_in,
+MULTI_EVAL_ATTR void shader_bsdf_multi_eval(ShaderDataG &sd, const LobeArena &arena, f3 omega_in,
                                    float *pdf, int skip, f3 *result_eval, float sum_pdf,
                                    float sum_sample_weight)
 {
@@ -1483,7 +1492,7 @@ CY_DEV int light_distribution_sample(float *randu)
 #include "light_tri.cuh"
 
 /* kernel_light.h:624-660 (lamp < 0: pick from the distribution) */
-CY_DEV bool light_sample(float randu, float randv, f3 P, int bounce, LightSampleG *ls)
+LIGHT_SAMPLE_ATTR bool light_sample(float randu, float randv, f3 P, int bounce, LightSampleG *ls)
 {
   int index = light_distribution_sample(&randu);
   const uint8_t *kd = g_scene.light_distribution + (size_t)index * SIZEOF_KERNEL_LIGHT_DISTRIBUTION;

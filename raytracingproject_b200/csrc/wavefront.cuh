@@ -27,6 +27,10 @@
 #include "shade.cuh"
 #include "passes.cuh"
 
+/* bit 30 of a shadow-queue entry's transparent-bounce word: the path was past its first
+ * bounce when it sampled the light (selects the indirect clamp in shadow_light_arrives) */
+#define SH_INDIRECT_FLAG 0x40000000
+
 #define WF_MAX_KEYS 4096
 #define WF_BLOCK 256
 /* sort keys below this are histogrammed / ranked in shared memory, the (rare) rest by
@@ -977,10 +981,14 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
                  * adds the total to the indirect light (A) */
                 f3 contribution, part_b = zero3(), part_c = zero3();
                 float shadow_add = 0.0f;
+                /* with transparent shadows the clamp waits for the attenuation
+                 * (shadow_light_arrives) */
+                const bool defer_clamp = kd_int(KD_INT_TRANSPARENT_SHADOWS) != 0 &&
+                                         (ls.shader & CY_SHADER_CAST_SHADOW) != 0;
                 if (use_light_pass) {
                   f3 shaded_throughput = throughput;
                   f3 full = shaded_throughput * eval_split_sum(ev);
-                  {
+                  if (!defer_clamp) {
                     const float limit = (st.bounce > 0) ? kd_float(KD_INT_SAMPLE_CLAMP_INDIRECT) :
                                                           kd_float(KD_INT_SAMPLE_CLAMP_DIRECT);
                     const float sum = reduce_add(fabs3(full));
@@ -1005,7 +1013,8 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
                 }
                 else {
                   contribution = throughput * eval;
-                  path_radiance_clamp(&contribution, st.bounce);
+                  if (!defer_clamp)
+                    path_radiance_clamp(&contribution, st.bounce);
                 }
                 if (ls.shader & CY_SHADER_CAST_SHADOW) {
                   const bool transmit = (dot(sd.Ng, ls.D) < 0.0f);
@@ -1030,7 +1039,8 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
                   stage[7 * WF_BLOCK] = contribution.x;
                   stage[8 * WF_BLOCK] = contribution.y;
                   stage[9 * WF_BLOCK] = contribution.z;
-                  stage[10 * WF_BLOCK] = __int_as_float(st.transparent_bounce);
+                  stage[10 * WF_BLOCK] = __int_as_float(
+                      st.transparent_bounce | (st.bounce > 0 ? SH_INDIRECT_FLAG : 0));
                   if (PASSES) {
                     stage[12 * WF_BLOCK] = part_b.x;
                     stage[13 * WF_BLOCK] = part_b.y;
@@ -1177,6 +1187,56 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
 /* AO: the light ray and the ambient-occlusion ray of one path are in the same launch,
  * so unoccluded contributions are added atomically (a compile-time variant: the test
  * at run time cost the plain kernel 7 %) */
+/* Scenes with transparent shadows: a light contribution is clamped when it ARRIVES, after
+ * the attenuation of the surfaces it crossed (path_radiance_accum_light clamps
+ * throughput * shadow * eval, kernel_accumulate.h:402-459), so the shading kernel hands it
+ * over unclamped and marks which limit applies. */
+template<bool PASSES>
+CY_DEV void shadow_light_arrives(const PathSoA &p, unsigned int sh, f3 shadow)
+{
+  const int i = p.q_shadow[sh];
+  const float4 cn = p.sh_contrib[sh];
+  const float limit = (__float_as_int(cn.w) & SH_INDIRECT_FLAG) ?
+                          kd_float(KD_INT_SAMPLE_CLAMP_INDIRECT) :
+                          kd_float(KD_INT_SAMPLE_CLAMP_DIRECT);
+  if (PASSES && kd_int(KD_FILM_USE_LIGHT_PASS)) {
+    float *pb = p.pass + (size_t)i * PASS_WORDS;
+    const float4 b = p.sh_pass[2 * (size_t)sh], cc = p.sh_pass[2 * (size_t)sh + 1];
+    if (cc.w != 0.0f) {
+      f3 A = mk3(cn) * shadow, B = mk3(b) * shadow, C = mk3(cc) * shadow;
+      const float sum = reduce_add(fabs3(A + B + C));
+      if (sum > limit) {
+        const float f = limit / sum;
+        A *= f;
+        B *= f;
+        C *= f;
+      }
+      pb_add3(pb, PB_DIRECT_DIFFUSE, A);
+      pb_add3(pb, PB_DIRECT_GLOSSY, B);
+      pb_add3(pb, PB_DIRECT_TRANSMISSION, C);
+      pb_add3(pb, PB_SHADOW, shadow * b.w);
+    }
+    else {
+      f3 full = mk3(cn) * shadow;
+      const float sum = reduce_add(fabs3(full));
+      if (sum > limit)
+        full *= limit / sum;
+      pb_add3(pb, PB_INDIRECT, full);
+    }
+  }
+  else {
+    f3 c = mk3(cn) * shadow;
+    const float sum = reduce_add(fabs3(c));
+    if (sum > limit)
+      c *= limit / sum;
+    float4 L = p.L[i];
+    L.x += c.x;
+    L.y += c.y;
+    L.z += c.z;
+    p.L[i] = L;
+  }
+}
+
 template<bool TRANSPARENT, bool AO = false, bool PASSES = false> struct ShadowJob {
   PathSoA p;
   __device__ __forceinline__ const float4 *ray_P(unsigned int qi) const
@@ -1189,7 +1249,10 @@ template<bool TRANSPARENT, bool AO = false, bool PASSES = false> struct ShadowJo
   }
   __device__ __forceinline__ void store(unsigned int qi, const TraceHit &h, bool blocked)
   {
-    if (!blocked) {
+    if (!blocked && TRANSPARENT) {
+      shadow_light_arrives<PASSES>(p, qi, mk3(1.0f, 1.0f, 1.0f));
+    }
+    else if (!blocked) {
       /* shade_shadow - path_radiance_accum_light, kernel_accumulate.h:402-459 */
       const int i = p.q_shadow[qi];
       const float4 cn = p.sh_contrib[qi];
@@ -1228,7 +1291,7 @@ template<bool TRANSPARENT, bool AO = false, bool PASSES = false> struct ShadowJo
       const unsigned int tri = __ldg(&g_scene.prim_index[h.prim]);
       const uint32_t flags = shader_flags((int)__ldg(&g_scene.tri_shader[tri]));
       const float4 cn = p.sh_contrib[qi];
-      const int bounce = __float_as_int(cn.w);
+      const int bounce = __float_as_int(cn.w) & ~SH_INDIRECT_FLAG;
       if ((flags & CY_SD_HAS_TRANSPARENT_SHADOW) &&
           bounce < kd_int(KD_INT_TRANSPARENT_MAX_BOUNCE)) {
         const unsigned int slot = atomicAdd(&p.counters->n_ts[0], 1u);
@@ -1237,7 +1300,7 @@ template<bool TRANSPARENT, bool AO = false, bool PASSES = false> struct ShadowJo
         p.ts_D[0][slot] = make_float4(d.x, d.y, d.z,
                                       __uint_as_float(CY_PATH_RAY_SHADOW_TRANSPARENT));
         p.ts_idx[0][slot] = (int)qi;
-        p.ts_thr[qi] = make_float4(1.0f, 1.0f, 1.0f, cn.w);
+        p.ts_thr[qi] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(bounce));
       }
     }
   }
@@ -1279,7 +1342,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_MIN_BLOCKS)
  * kernel_shadow.h:46-88, 300-352): nothing hit -> the light arrives, attenuated; an
  * opaque surface -> blocked; a transparent one -> evaluate its shader as a shadow ray,
  * multiply the attenuation by its transparency and continue behind it. */
-template<bool EXT>
+template<bool EXT, bool PASSES = false>
 __global__ void __launch_bounds__(WF_BLOCK) k_shade_shadow_step(PathSoA p, int cur)
 {
   WFCounters *c = p.counters;
@@ -1298,13 +1361,7 @@ __global__ void __launch_bounds__(WF_BLOCK) k_shade_shadow_step(PathSoA p, int c
       float4 thr = p.ts_thr[sh];
       if (prim < 0) {
         /* reached the light */
-        const int i = p.q_shadow[sh];
-        const float4 cn = p.sh_contrib[sh];
-        float4 L = p.L[i];
-        L.x += cn.x * thr.x;
-        L.y += cn.y * thr.y;
-        L.z += cn.z * thr.z;
-        p.L[i] = L;
+        shadow_light_arrives<PASSES>(p, (unsigned int)sh, mk3(thr.x, thr.y, thr.z));
       }
       else {
         const unsigned int tri = __ldg(&g_scene.prim_index[prim]);
@@ -2204,10 +2261,8 @@ static int check_scope(b200_ctx *ctx)
            ((1 << (CY_PASS_AO % 32)) | (1 << (CY_PASS_VOLUME_DIRECT % 32)) |
             (1 << (CY_PASS_VOLUME_INDIRECT % 32))))
     why = "the AO and volume light passes are outside the hot-path scope";
-  else if (film_wants_passes(ctx) &&
-           (I(KD_INT_USE_AMBIENT_OCCLUSION) || I(KD_INT_TRANSPARENT_SHADOWS)))
-    why = "render passes together with world ambient occlusion or transparent shadows are "
-          "outside the hot-path scope";
+  else if (film_wants_passes(ctx) && I(KD_INT_USE_AMBIENT_OCCLUSION))
+    why = "render passes together with world ambient occlusion are outside the hot-path scope";
   else if (!(I(KD_FILM_PASS_FLAG) & (1u << CY_PASS_COMBINED)))
     why = "the combined pass must be enabled";
   else if (I(KD_FILM_PASS_STRIDE) % 4 != 0)
@@ -2402,7 +2457,10 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
                                                                                       num_keys);
     }
     CUDA_TRY(ctx, cudaEventRecord(ev[2], st));
-    if (passes) /* never with AO or transparent shadows (check_scope) */
+    if (passes && transparent_shadows) /* passes never with AO (check_scope) */
+      k_intersect_shadow<false, true, false, true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa,
+                                                                                       refill);
+    else if (passes)
       k_intersect_shadow<false, false, false, true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa,
                                                                                         refill);
     else if (use_ao) /* never with transparent shadows (check_scope) */
@@ -2423,7 +2481,9 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
       int cur = 0;
       while (pool->h_counters->n_ts[cur] != 0) {
         k_intersect_shadow_step<<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, cur, refill);
-        if (svm_ext)
+        if (passes)
+          k_shade_shadow_step<true, true><<<grid_wide, WF_BLOCK, 0, st>>>(soa, cur);
+        else if (svm_ext)
           k_shade_shadow_step<true><<<grid_wide, WF_BLOCK, 0, st>>>(soa, cur);
         else
           k_shade_shadow_step<false><<<grid_wide, WF_BLOCK, 0, st>>>(soa, cur);

@@ -186,6 +186,19 @@ def pass_cases():
     d = _replace(scenes.cornell(W, H, materials="principled"), 'use_mis="true"',
                  'use_mis="true" use_glossy="false"')
     cases["light_invisible_to_glossy_rays"] = d
+    # transparent shadows: the light crosses stacked transparent sheets on its way, every
+    # class of it attenuated; the shadow pass holds the attenuation colour.  With a direct
+    # clamp low enough to bite: the clamp applies to the ATTENUATED light
+    d = _replace(scenes.cornell(W, H, materials="transparent", panes=3),
+                 'sample_clamp_direct="0"', 'sample_clamp_direct="0.02"')
+    d.passes = [scenes.PASS[k] for k in ("diffuse_direct", "diffuse_indirect", "glossy_direct",
+                                         "shadow", "diffuse_color", "normal", "depth")]
+    d.name += "_passes"
+    cases["passes_transparent_shadows"] = d
+    d = _replace(scenes.cornell(W, H, materials="transparent", panes=3),
+                 'sample_clamp_direct="0"', 'sample_clamp_direct="0.02"')
+    d.name += "_clamped"
+    cases["clamp_after_transparent_shadows"] = d
     return cases
 
 

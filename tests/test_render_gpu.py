@@ -190,7 +190,9 @@ def test_image_textures_match_reference(ref, device, name):
 @pytest.mark.parametrize("name", ["passes_cornell_principled", "passes_cornell_image",
                                   "passes_cube_env_transparent_film",
                                   "passes_cornell_mesh_light", "passes_data_only",
-                                  "light_invisible_to_glossy_rays"])
+                                  "light_invisible_to_glossy_rays",
+                                  "passes_transparent_shadows",
+                                  "clamp_after_transparent_shadows"])
 def test_render_passes_match_reference(ref, device, name):
     """Light and data passes (kernel_passes.h, kernel_accumulate.h with use_light_pass):
     every pass of the film against the reference CPU kernel - the colour passes to the
@@ -218,8 +220,9 @@ def test_render_passes_match_reference(ref, device, name):
             rel = abs(float(a.mean()) - float(b.mean())) / scale
             print("%s %-22s rmse=%.3e mean ref=%.6f got=%.6f rel=%.2e max|d|=%.2e" % (
                 name, names[pass_type], rmse, a.mean(), b.mean(), rel, np.abs(a - b).max()))
-            must_have = {"diffuse_direct", "diffuse_indirect", "glossy_indirect", "shadow",
-                         "depth", "normal"}
+            must_have = {"diffuse_direct", "diffuse_indirect", "shadow", "depth", "normal"}
+            if "transparent" not in name:
+                must_have.add("glossy_indirect")
             if "mesh_light" in name:
                 must_have.add("emission")       # lamps are not visible to the camera
             if "env" in name:
