@@ -2236,7 +2236,7 @@ static int check_scope(b200_ctx *ctx)
     why = "the shader program samples image slot " + std::to_string(ctx->svm_max_image_slot) +
           " but only " + std::to_string(bound_image_slots(ctx)) +
           " image slots are bound (tex_alloc / b200_texture_set)";
-  else if (I(KD_BG_USE_MIS) && (F(KD_BG_PORTAL_WEIGHT) > 0.0f || I(KD_BG_NUM_PORTALS) > 0))
+  else if (F(KD_BG_PORTAL_WEIGHT) > 0.0f || I(KD_BG_NUM_PORTALS) > 0)
     why = "light portals are outside the hot-path scope";
   else if (I(KD_BG_USE_MIS) && F(KD_BG_SUN_WEIGHT) > 0.0f)
     why = "the sky texture's sun disc (background sun sampling) is outside the hot-path scope";
