@@ -598,7 +598,11 @@ int ref_render(ref_scene *rs,
   task.update_progress_sample = [](long, int) {};
   task.need_finish_queue = false;
   task.integrator_branched = false;
-  task.adaptive_sampling.use = false;
+  /* Session::render (render/session.cpp:1077-1080) */
+  task.adaptive_sampling.use = (scene->integrator->sampling_pattern == SAMPLING_PATTERN_PMJ) &&
+                               scene->dscene.data.film.pass_adaptive_aux_buffer;
+  task.adaptive_sampling.min_samples = scene->dscene.data.integrator.adaptive_min_samples;
+  task.adaptive_sampling.adaptive_step = scene->dscene.data.integrator.adaptive_step;
   task.tile_types = RenderTile::PATH_TRACE;
 
   /* CPUDevice::render sets FTZ/DAZ (SIMD_SET_FLUSH_TO_ZERO) on whichever thread
@@ -711,7 +715,11 @@ int ref_render_tile_buffers(ref_scene *rs,
   task.update_progress_sample = [](long, int) {};
   task.need_finish_queue = false;
   task.integrator_branched = false;
-  task.adaptive_sampling.use = false;
+  /* Session::render (render/session.cpp:1077-1080) */
+  task.adaptive_sampling.use = (scene->integrator->sampling_pattern == SAMPLING_PATTERN_PMJ) &&
+                               scene->dscene.data.film.pass_adaptive_aux_buffer;
+  task.adaptive_sampling.min_samples = scene->dscene.data.integrator.adaptive_min_samples;
+  task.adaptive_sampling.adaptive_step = scene->dscene.data.integrator.adaptive_step;
   task.tile_types = RenderTile::PATH_TRACE;
 
   const unsigned int mxcsr = _mm_getcsr();

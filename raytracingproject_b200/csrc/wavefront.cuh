@@ -33,6 +33,8 @@
 
 #define WF_MAX_KEYS 4096
 #define WF_BLOCK 256
+
+#include "adaptive.cuh"
 /* sort keys below this are histogrammed / ranked in shared memory, the (rare) rest by
  * global atomics */
 #define WF_SMALL_KEYS 64
@@ -61,6 +63,7 @@ struct WFCounters {
   unsigned int hist[WF_MAX_KEYS + 1];
   unsigned int offsets[WF_MAX_KEYS + 2];
   unsigned int cursor[WF_MAX_KEYS + 1];
+  unsigned int adaptive_any; /* adaptive filter: some pixel of the tile still samples */
 };
 
 struct PathSoA {
@@ -136,6 +139,9 @@ struct BatchParams {
   int offset, stride;  /* film addressing (buffers.cpp:50-54) */
   int num_keys;
   int count_stats;
+  /* adaptive sampling (adaptive.cuh): the film, to leave converged pixels out; null = off */
+  const float *adaptive_film;
+  int pass_stride, adaptive_aux;
 };
 
 /* ------------------------------------------------------------ helpers */
@@ -364,6 +370,14 @@ __global__ void __launch_bounds__(WF_BLOCK)
 
       uint32_t rng_hash;
       t = camera_ray(x, y, sample, &rng_hash, &P, &D);
+      /* a pixel the adaptive sampler has stopped traces nothing (kernel_path.h:660-666) */
+      bool stopped = false;
+      if (bp.adaptive_film) {
+        const long long index = (long long)bp.offset + x + (long long)y * bp.stride;
+        stopped = bp.adaptive_film[index * bp.pass_stride + bp.adaptive_aux + 3] > 0.0f;
+        if (stopped)
+          t = 0.0f;
+      }
 
       /* path_state_init - kernel_path_state.h:19-70 */
       PathStateG st;
@@ -377,7 +391,8 @@ __global__ void __launch_bounds__(WF_BLOCK)
       state_store(p, i, st);
       vis = path_state_ray_visibility(st.flag);
 
-      p.ray_pdf[i] = 0.0f;
+      /* ray_pdf < 0 marks a pixel sample that writes nothing to the adaptive film */
+      p.ray_pdf[i] = (bp.adaptive_film && t == 0.0f) ? -1.0f : 0.0f;
       p.throughput[i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);    /* ray_t = 0 */
       /* kernel_path_trace returns before kernel_write_result when ray.t == 0
        * (kernel_path.h:668-670): transparent = 1 makes the film add (0,0,0,0). */
@@ -1509,6 +1524,52 @@ __global__ void __launch_bounds__(WF_BLOCK)
   }
 }
 
+/* kernel_write_result with adaptive sampling (kernel_passes.h:338-350, 392-425): the
+ * combined pass, twice the even samples into the aux buffer, and the sample count kept
+ * negative while the tile is in progress. */
+__global__ void __launch_bounds__(WF_BLOCK)
+    k_film_accumulate_adaptive(PathSoA p, BatchParams bp, float *film, int pass_stride, int aux,
+                               int sample_count)
+{
+  const unsigned int npix = (unsigned)bp.w * (unsigned)bp.h;
+  const int pattern = kd_int(KD_INT_SAMPLING_PATTERN);
+  const bool write_aux = kd_float(KD_INT_ADAPTIVE_THRESHOLD) > 0.0f;
+  for (unsigned int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix;
+       pix += gridDim.x * blockDim.x) {
+    int x, y;
+    batch_pixel(bp, pix, &x, &y);
+    const long long index = (long long)bp.offset + x + (long long)y * bp.stride;
+    float *buf = film + index * pass_stride;
+    float4 acc = *(float4 *)buf;
+    float4 a = *(float4 *)(buf + aux);
+    float count = sample_count ? buf[sample_count] : 0.0f;
+    for (int s = 0; s < bp.nsamples; s++) {
+      const size_t path = (size_t)s * npix + pix;
+      if (p.ray_pdf[path] < 0.0f)
+        continue; /* stopped pixel, or no camera ray: nothing is written */
+      const float4 L = p.L[path];
+      float3 Ls = make_float3(L.x, L.y, L.z);
+      const float sum = fabsf(Ls.x) + fabsf(Ls.y) + fabsf(Ls.z);
+      if (!isfinite_safe(sum))
+        Ls = make_float3(0.0f, 0.0f, 0.0f);
+      acc.x += Ls.x;
+      acc.y += Ls.y;
+      acc.z += Ls.z;
+      acc.w += 1.0f - L.w;
+      if (write_aux && sample_is_even(pattern, bp.sample0 + s)) {
+        a.x += Ls.x * 2.0f;
+        a.y += Ls.y * 2.0f;
+        a.z += Ls.z * 2.0f;
+      }
+      count = -fabsf(count) - 1.0f;
+    }
+    *(float4 *)buf = acc;
+    *(float4 *)(buf + aux) = a;
+    if (sample_count)
+      buf[sample_count] = count;
+  }
+}
+
 /* kernel_write_result + kernel_write_light_passes + the data passes
  * (kernel_passes.h:285-350, 174-224; path_radiance_clamp_and_sum,
  * kernel_accumulate.h:537-560, 640-700) for the whole batch when the film holds more than
@@ -2199,7 +2260,9 @@ static int bound_image_slots(const b200_ctx *ctx)
 static bool film_wants_passes(const b200_ctx *ctx)
 {
   return kd_host<int>(ctx, KD_FILM_USE_LIGHT_PASS) != 0 ||
-         (kd_host<int>(ctx, KD_FILM_PASS_FLAG) & ~(1 << CY_PASS_COMBINED)) != 0;
+         (kd_host<int>(ctx, KD_FILM_PASS_FLAG) &
+          ~((1 << CY_PASS_COMBINED) | (1 << CY_PASS_ADAPTIVE_AUX_BUFFER) |
+            (1 << CY_PASS_SAMPLE_COUNT))) != 0;
 }
 
 static int check_scope(b200_ctx *ctx)
@@ -2248,13 +2311,19 @@ static int check_scope(b200_ctx *ctx)
             find_global(ctx, "__light_background_conditional_cdf")->bytes <
                 (size_t)(I(KD_BG_MAP_RES_X) + 1) * I(KD_BG_MAP_RES_Y) * 8))
     why = "background importance sampling needs the world map CDF arrays";
-  else if (I(KD_FILM_PASS_DENOISING_DATA) || I(KD_FILM_PASS_ADAPTIVE_AUX_BUFFER) ||
-           I(KD_FILM_PASS_SAMPLE_COUNT) || I(KD_FILM_CRYPTOMATTE_PASSES))
-    why = "denoising data, adaptive sampling and cryptomatte passes are outside the hot-path "
-          "scope";
+  else if (I(KD_FILM_PASS_DENOISING_DATA) || I(KD_FILM_CRYPTOMATTE_PASSES))
+    why = "denoising data and cryptomatte passes are outside the hot-path scope";
+  else if (I(KD_FILM_PASS_ADAPTIVE_AUX_BUFFER) &&
+           (I(KD_INT_SAMPLING_PATTERN) != CY_SAMPLING_PATTERN_PMJ || film_wants_passes(ctx) ||
+            I(KD_FILM_PASS_ADAPTIVE_AUX_BUFFER) % 4 != 0))
+    why = "adaptive sampling is in scope with the PMJ pattern and the combined pass only";
+  else if (I(KD_FILM_PASS_SAMPLE_COUNT) && !I(KD_FILM_PASS_ADAPTIVE_AUX_BUFFER))
+    why = "the sample-count pass is in scope together with adaptive sampling only";
   else if (I(KD_FILM_PASS_FLAG) & ~((1 << CY_PASS_COMBINED) | (1 << CY_PASS_DEPTH) |
                                     (1 << CY_PASS_NORMAL) | (1 << CY_PASS_UV) |
-                                    (1 << CY_PASS_OBJECT_ID) | (1 << CY_PASS_MATERIAL_ID)))
+                                    (1 << CY_PASS_OBJECT_ID) | (1 << CY_PASS_MATERIAL_ID) |
+                                    (1 << CY_PASS_ADAPTIVE_AUX_BUFFER) |
+                                    (1 << CY_PASS_SAMPLE_COUNT)))
     why = "of the data passes depth, normal, UV, object id and material id are in scope "
           "(motion, AOV and render-time passes are not)";
   else if (I(KD_FILM_LIGHT_PASS_FLAG) &
@@ -2532,14 +2601,37 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
     return B200_OK;
   };
 
+  /* adaptive sampling (adaptive.cuh): Session's AdaptiveSampling (session.cpp:1077-1080)
+   * read from KernelData; a batch never crosses a filter point */
+  const int adaptive_aux = kd_host<int>(ctx, KD_FILM_PASS_ADAPTIVE_AUX_BUFFER);
+  const bool adaptive = adaptive_aux != 0 &&
+                        kd_host<int>(ctx, KD_INT_SAMPLING_PATTERN) == CY_SAMPLING_PATTERN_PMJ;
+  const int adaptive_step = std::max(1, kd_host<int>(ctx, KD_INT_ADAPTIVE_STEP));
+  const int adaptive_min = kd_host<int>(ctx, KD_INT_ADAPTIVE_MIN_SAMPLES);
+  AdaptiveTile atile;
+  atile.film = (float *)tile->buffer;
+  atile.x = tile->x, atile.y = tile->y, atile.w = tile->w, atile.h = tile->h;
+  atile.offset = tile->offset, atile.stride = tile->stride, atile.pass_stride = pass_stride;
+  atile.aux = adaptive_aux;
+  atile.sample_count = kd_host<int>(ctx, KD_FILM_PASS_SAMPLE_COUNT);
+  bool adaptive_done = false;
+
   /* bands of rows so that one sample of a band fits the pool */
   const int band_h = (int)std::max<size_t>(1, std::min<size_t>((size_t)tile->h,
                                                                pool->capacity / (size_t)tile->w));
+  if (adaptive && band_h < tile->h)
+    return fail(ctx, B200_ERR_UNSUPPORTED,
+                "adaptive sampling needs one sample of the whole tile to fit the path pool");
   for (int by = 0; by < tile->h; by += band_h) {
     const int bh = std::min(band_h, tile->h - by);
     const size_t npix = (size_t)tile->w * bh;
-    const int spb = (int)std::max<size_t>(1, pool->capacity / npix);
-    for (int s0 = 0; s0 < tile->num_samples; s0 += spb) {
+    int spb = (int)std::max<size_t>(1, pool->capacity / npix);
+    if (adaptive) { /* a divisor of the step, so that batches end where the filter runs */
+      spb = std::min(spb, adaptive_step);
+      while (adaptive_step % spb != 0)
+        spb--;
+    }
+    for (int s0 = 0; s0 < tile->num_samples && !adaptive_done; s0 += spb) {
       if ((cancel && *cancel) || (ctx->cancel_fn && ctx->cancel_fn(ctx->cancel_user)))
         return fail(ctx, B200_ERR_CANCELLED, "cancelled");
       BatchParams bp;
@@ -2553,6 +2645,9 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
       bp.stride = tile->stride;
       bp.num_keys = num_keys;
       bp.count_stats = count;
+      bp.adaptive_film = adaptive ? (const float *)tile->buffer : nullptr;
+      bp.pass_stride = pass_stride;
+      bp.adaptive_aux = adaptive_aux;
 
       for (int attempt = 0;; attempt++) {
         PathSoA soa = pool->soa;
@@ -2626,7 +2721,10 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
           ctx->force_svm_ext = true;
           continue;
         }
-        if (passes)
+        if (adaptive)
+          k_film_accumulate_adaptive<<<grid_wide, WF_BLOCK, 0, st>>>(
+              soa, bp, (float *)tile->buffer, pass_stride, adaptive_aux, atile.sample_count);
+        else if (passes)
           k_film_accumulate_passes<<<grid_wide, WF_BLOCK, 0, st>>>(soa, bp,
                                                                    (float *)tile->buffer,
                                                                    pass_stride);
@@ -2644,9 +2742,38 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
           if (rc)
             return rc;
         }
+        if (adaptive) {
+          /* AdaptiveSampling::need_filter (device_task.cpp:184-192) for the last sample of
+           * the batch: convergence test of every pixel, then the two dilation sweeps; the
+           * tile is finished when no pixel is left sampling */
+          const int last = bp.sample0 + bp.nsamples - 1;
+          if (last > adaptive_min && (last & (adaptive_step - 1)) == (adaptive_step - 1)) {
+            unsigned int *any = &soa.counters->adaptive_any;
+            CUDA_TRY(ctx, cudaMemsetAsync(any, 0, sizeof(unsigned int), st));
+            k_adaptive_stopping<<<grid_wide, WF_BLOCK, 0, st>>>(atile, last);
+            k_adaptive_filter_x<<<(tile->h + 63) / 64, 64, 0, st>>>(atile, any);
+            k_adaptive_filter_y<<<(tile->w + 63) / 64, 64, 0, st>>>(atile, any);
+            stats.kernel_launches += 3;
+            unsigned int h_any = 1;
+            CUDA_TRY(ctx, cudaMemcpyAsync(&pool->h_counters->adaptive_any, any, sizeof(unsigned int),
+                                          cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            stats.host_syncs += 1;
+            h_any = pool->h_counters->adaptive_any;
+            if (!h_any)
+              adaptive_done = true;
+          }
+        }
         break;
       } /* attempt */
     }
+  }
+  if (adaptive) {
+    /* adaptive_sampling_post (device_cpu.cpp:864-886): tile.sample is the end of the task
+     * whether the tile stopped early or not */
+    k_adaptive_scale_samples<<<grid_wide, WF_BLOCK, 0, st>>>(atile, tile->start_sample,
+                                                             tile->start_sample + tile->num_samples);
+    stats.kernel_launches += 1;
   }
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev6, st));
   rc = sum_batch_stats();

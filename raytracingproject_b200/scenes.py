@@ -56,7 +56,7 @@ PASS = {"depth": 2, "normal": 3, "uv": 4, "object_id": 5, "material_id": 6, "mis
         "emission": 33, "background": 34, "shadow": 36, "diffuse_direct": 38,
         "diffuse_indirect": 39, "diffuse_color": 40, "glossy_direct": 41, "glossy_indirect": 42,
         "glossy_color": 43, "transmission_direct": 44, "transmission_indirect": 45,
-        "transmission_color": 46}
+        "transmission_color": 46, "adaptive_aux_buffer": 13, "sample_count": 14}
 
 
 def _f(v):

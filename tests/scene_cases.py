@@ -125,6 +125,24 @@ def image_cases():
     }
 
 
+def adaptive_cases():
+    """Adaptive sampling (adaptive.cuh): PMJ pattern, the aux-buffer and sample-count passes,
+    a threshold loose enough that flat regions stop at the first filter point and tight
+    enough that edges sample on - the sample-count pass shows who stopped when."""
+    cases = {}
+    for name, d in (("adaptive_cornell", scenes.cornell(W, H, spp=32, materials="diffuse",
+                                                        pattern="pmj")),
+                    ("adaptive_cube", scenes.default_cube(W, H, spp=32, material="diffuse"))):
+        if "pmj" not in d.xml:
+            d = _replace(d, 'sampling_pattern="sobol"', 'sampling_pattern="pmj"')
+        d = _replace(d, 'filter_glossy="0"', 'filter_glossy="0" adaptive_threshold="0.02" '
+                     'adaptive_min_samples="8"')
+        d.passes = [scenes.PASS["adaptive_aux_buffer"], scenes.PASS["sample_count"]]
+        d.name += "_adaptive"
+        cases[name] = d
+    return cases
+
+
 def world_light_cases():
     """The world as a light (background MIS): an environment texture lights the startup
     scene and is importance-sampled through the luminance map the host builds from a

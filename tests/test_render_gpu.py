@@ -6,7 +6,7 @@ gates hold at any spp, not only at 1024."""
 import numpy as np
 import pytest
 
-from scene_cases import (ao_cases, camera_cases, closure_cases, image_cases, light_cases,
+from scene_cases import (adaptive_cases, ao_cases, camera_cases, closure_cases, image_cases, light_cases,
                          pass_cases, principled_cases, sampling_cases, small_cases,
                          texture_cases, world_light_cases)
 
@@ -303,6 +303,53 @@ def test_world_light_matches_reference(ref, device, name):
             shim, _ = rs.render(0, SPP, tile_size=64)
             assert host.error_message() == ""
             image_gates(ref_img[..., off:off + 4], shim[..., off:off + 4], SPP, name + " (shim)")
+        finally:
+            rs.close()
+    finally:
+        host.close()
+
+
+@pytest.mark.parametrize("name", ["adaptive_cornell", "adaptive_cube"])
+def test_adaptive_sampling_matches_reference(ref, device, name):
+    """Adaptive sampling (kernel_adaptive_sampling.h; device_cpu.cpp:838-945): pixels stop
+    at the filter points where the reference CPU device stops them - the sample-count pass
+    says which - and the film is rescaled to a uniform sample count at the end.  Through
+    the Python mirror and the C++ shim (whose KernelData says adaptive_stop_per_sample = 0:
+    the convergence test runs as a kernel at the filter points, like the CUDA device)."""
+    from raytracingproject_b200 import scenes
+    from raytracingproject_b200.device import B200HostDevice
+    desc = adaptive_cases()[name]
+    spp = desc.spp
+    rs = ref.build_scene(desc)
+    try:
+        device.upload_scene(rs.device_arrays(), rs.textures())
+        ref_img, _ = rs.render(0, spp, tile_size=0)
+        got = device.render(desc.width, desc.height, rs.pass_stride, 0, spp).copy()
+        c_off, _ = rs.pass_offset(scenes.PASS["sample_count"])
+        a_off, _ = rs.pass_offset(scenes.PASS["adaptive_aux_buffer"])
+    finally:
+        rs.close()
+
+    def check(img, label):
+        ref_cnt, cnt = ref_img[..., c_off], img[..., c_off]
+        same = float(np.mean(ref_cnt == cnt))
+        print(label, "sample count: ref mean %.2f got %.2f, identical pixels %.4f, histogram %s"
+              % (ref_cnt.mean(), cnt.mean(), same,
+                 dict(zip(*[a.tolist() for a in np.unique(cnt, return_counts=True)]))))
+        assert ref_cnt.min() < spp and ref_cnt.max() == spp   # the case does stop pixels
+        assert same >= 0.995
+        image_gates(ref_img[..., :4], img[..., :4], spp, label)
+        d = np.abs(ref_img[..., a_off:a_off + 3] - img[..., a_off:a_off + 3])[ref_cnt == cnt]
+        assert d.max() / spp < 2e-3
+
+    check(got, name)
+    host = B200HostDevice(0)
+    try:
+        rs = ref.build_scene(desc, external_device=host.ptr)
+        try:
+            shim, _ = rs.render(0, spp, tile_size=0)
+            assert host.error_message() == ""
+            check(shim, name + " (shim)")
         finally:
             rs.close()
     finally:
