@@ -1036,6 +1036,10 @@ int b200_set_option(b200_ctx *ctx, const char *name, int64_t value)
     ctx->opt_sync_iterations = value;
   else if (strcmp(name, "sort_tiles") == 0)
     ctx->opt_sort_tiles = value;
+  else if (strcmp(name, "shade_carveout") == 0) {
+    ctx->opt_shade_carveout = value;
+    ctx->shade_blocks_per_sm[0] = 0; /* set the kernels up again */
+  }
   else if (strcmp(name, "instance_detail_boxes") == 0) {
     ctx->opt_instance_detail_boxes = value;
     ctx->bvh_dirty = true;

@@ -80,6 +80,7 @@ struct b200_ctx {
   int64_t opt_trace_blocks_per_sm = 0;
   int64_t opt_instance_detail_boxes = 0; /* 0 = builder default */
   int64_t opt_loose_instances = 0; /* A/B: host's instance bounds, no tightening */
+  int64_t opt_shade_carveout = 0;  /* A/B: shared-memory carveout of the shade kernels, % */
   int64_t opt_sort_tiles = 0;      /* experiment: sort by shader inside 2048-entry tiles */
   int64_t opt_sync_iterations = 0; /* A/B: stop the stream for the counters every bounce */
 

@@ -32,7 +32,9 @@
 #define SH_INDIRECT_FLAG 0x40000000
 
 #define WF_MAX_KEYS 4096
-#define WF_BLOCK 256
+#ifndef WF_BLOCK
+#  define WF_BLOCK 256
+#endif
 
 #include "adaptive.cuh"
 /* sort keys below this are histogrammed / ranked in shared memory, the (rare) rest by
@@ -2376,6 +2378,10 @@ static int shade_kernel_setup(b200_ctx *ctx)
                                                                 smem));
     if (blocks < 1)
       return fail(ctx, B200_ERR_CUDA, "surface-shading kernel does not fit on an SM");
+    /* A/B: how much of the L1 / shared array is asked for as shared memory (percent) */
+    if (ctx->opt_shade_carveout > 0)
+      CUDA_TRY(ctx, cudaFuncSetAttribute(kernels[k], cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         (int)ctx->opt_shade_carveout));
     /* a few waves of blocks per SM even the tail out */
     ctx->shade_blocks_per_sm[k] = blocks * 2;
   }
