@@ -88,6 +88,7 @@ enum {
 /* Job of the batch hook: 32-byte ray records in (two 16-byte halves), 24-byte hit
  * records out. */
 struct BatchJob {
+  static constexpr bool QUEUE_RAYS = false; /* the caller's 32-byte ray records, interleaved */
   const b200_ray *rays;
   b200_hit *hits;
   __device__ __forceinline__ const float4 *ray_P(unsigned int qi) const
@@ -796,6 +797,8 @@ static int prepare_scene(b200_ctx *ctx, bool for_shader_task = false)
   ds.nodes = dev_nodes;
   ds.records = dev_records;
   ds.bvh_root = bvh_root;
+  ctx->dev_nodes = (const void *)dev_nodes;
+  ctx->dev_nodes_bytes = (size_t)ctx->bvh_info.node_bytes;
   auto ptr = [&](const char *name) -> uint64_t {
     const HostArray *h = find_global(ctx, name);
     return h ? h->dptr : 0;
@@ -884,6 +887,34 @@ static int check_trace_overflow(b200_ctx *ctx)
   CUDA_TRY(ctx, cudaMemcpyToSymbol(g_trace_overflow, &zero, sizeof(zero)));
   return fail(ctx, B200_ERR_UNSUPPORTED,
               "BVH8 traversal stack overflow: hits of this call are not reliable");
+}
+
+/* A/B (b200_set_option("l2_persist_nodes", 1)): an L2 access-policy window over the BVH8
+ * node array on the context's stream - hits stay, misses stream.  Measured on B200: see
+ * profiles/r02m_l2_window_ab.txt. */
+static int apply_l2_window(b200_ctx *ctx)
+{
+  cudaStreamAttrValue attr;
+  memset(&attr, 0, sizeof(attr));
+  if (ctx->opt_l2_persist_nodes && ctx->dev_nodes && ctx->dev_nodes_bytes) {
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->ordinal);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->ordinal);
+    const size_t bytes = std::min<size_t>(ctx->dev_nodes_bytes,
+                                          std::min<size_t>((size_t)max_persist, (size_t)max_window));
+    CUDA_TRY(ctx, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes));
+    attr.accessPolicyWindow.base_ptr = const_cast<void *>(ctx->dev_nodes);
+    attr.accessPolicyWindow.num_bytes = bytes;
+    attr.accessPolicyWindow.hitRatio = 1.0f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  }
+  else if (!ctx->l2_window_set) {
+    return B200_OK;
+  }
+  CUDA_TRY(ctx, cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+  ctx->l2_window_set = ctx->opt_l2_persist_nodes != 0;
+  return B200_OK;
 }
 
 #include "wavefront.cuh"
@@ -1036,6 +1067,8 @@ int b200_set_option(b200_ctx *ctx, const char *name, int64_t value)
     ctx->opt_sync_iterations = value;
   else if (strcmp(name, "sort_tiles") == 0)
     ctx->opt_sort_tiles = value;
+  else if (strcmp(name, "l2_persist_nodes") == 0)
+    ctx->opt_l2_persist_nodes = value;
   else if (strcmp(name, "shade_carveout") == 0) {
     ctx->opt_shade_carveout = value;
     ctx->shade_blocks_per_sm[0] = 0; /* set the kernels up again */

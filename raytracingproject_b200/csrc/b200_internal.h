@@ -81,6 +81,10 @@ struct b200_ctx {
   int64_t opt_instance_detail_boxes = 0; /* 0 = builder default */
   int64_t opt_loose_instances = 0; /* A/B: host's instance bounds, no tightening */
   int64_t opt_shade_carveout = 0;  /* A/B: shared-memory carveout of the shade kernels, % */
+  int64_t opt_l2_persist_nodes = 0; /* A/B: L2 persisting window over the BVH8 nodes */
+  bool l2_window_set = false;
+  const void *dev_nodes = nullptr;  /* what the traversal kernels read (prepare_scene) */
+  size_t dev_nodes_bytes = 0;
   int64_t opt_sort_tiles = 0;      /* experiment: sort by shader inside 2048-entry tiles */
   int64_t opt_sync_iterations = 0; /* A/B: stop the stream for the counters every bounce */
 

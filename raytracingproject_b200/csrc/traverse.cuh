@@ -411,6 +411,61 @@ template<int N> CY_DEV void cp_async_wait()
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+/* 1-D bulk asynchronous copy (the TMA unit, cp.async.bulk -> UBLKCP) with an mbarrier that
+ * counts the bytes: one elected lane moves a whole 512-byte tile of ray records per
+ * instruction where the LDGSTS path above spends one instruction per lane and record.
+ * Built, correct (hit-id tests green) and measured on B200 against the LDGSTS path
+ * (tools/r02_run19.sh, profiles/r02n_bulk_staging_ab.txt): closest-hit 4.92 vs 5.31 Grays/s
+ * on the terrain, 1.49 vs 1.58 on the instanced scene, 8.3 vs 9.1 on the Cornell box - 5-11 %
+ * SLOWER.  A warp's tile is 1 KB: too small for the bulk engine's fixed latency to pay, and
+ * the 32 lanes spin on the mbarrier where cp.async.wait_group parks the warp on a
+ * scoreboard.  Kept behind -DRAY_STAGE_BULK=1, not the default. */
+#ifndef RAY_STAGE_BULK
+#  define RAY_STAGE_BULK 0
+#endif
+CY_DEV void mbar_init(unsigned long long *bar, unsigned int count)
+{
+  const unsigned int a = (unsigned int)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+CY_DEV void mbar_expect_tx(unsigned long long *bar, unsigned int bytes)
+{
+  const unsigned int a = (unsigned int)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes)
+               : "memory");
+}
+CY_DEV void mbar_arrive(unsigned long long *bar)
+{
+  const unsigned int a = (unsigned int)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+CY_DEV void mbar_wait(unsigned long long *bar, unsigned int parity)
+{
+  const unsigned int a = (unsigned int)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(a),
+      "r"(parity)
+      : "memory");
+}
+CY_DEV void bulk_copy_g2s(void *smem_dst, const void *gmem_src, unsigned int bytes,
+                          unsigned long long *bar)
+{
+  const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  const unsigned int b = (unsigned int)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(d),
+      "l"(gmem_src), "r"(bytes), "r"(b)
+      : "memory");
+}
+
 /* Persistent-thread driver shared by every traversal kernel.
  *
  * Rays arrive in QUEUE ORDER as two 16-byte records (P.xyz,t | D.xyz,visibility) -
@@ -428,7 +483,11 @@ template<bool ANY_HIT, bool COUNT, class Job>
 __device__ __forceinline__ void trace_persistent(Job &job, unsigned int n, unsigned int *cursor,
                                                  int refill_threshold, TraceCounters &cnt)
 {
-  __shared__ float4 s_ray[TRACE_WARPS][2][2][32]; /* [warp][buffer][P|D][entry] : 8 KB */
+  __shared__ __align__(128) float4 s_ray[TRACE_WARPS][2][2][32]; /* [warp][buffer][P|D][entry] */
+  /* bulk staging: one mbarrier per warp and buffer, its phase parity kept per warp */
+  __shared__ __align__(8) unsigned long long s_bar[TRACE_WARPS][2];
+  constexpr bool BULK = RAY_STAGE_BULK && Job::QUEUE_RAYS;
+  unsigned int parity0 = 0u, parity1 = 0u;
   /* cooperative leaf phase: pooled (record, owner lane | bit << 8) work list */
   __shared__ uint2 s_list[TRACE_WARPS][224];
   const unsigned lane = threadIdx.x & 31u;
@@ -466,11 +525,26 @@ __device__ __forceinline__ void trace_persistent(Job &job, unsigned int n, unsig
     const unsigned int bs = chunk_next;
     chunk_next += 32u;
     const unsigned int av = (bs < n) ? min(32u, n - bs) : 0u;
-    if (lane < av) {
-      cp_async16(&s_ray[warp][b][0][lane], job.ray_P(bs + lane));
-      cp_async16(&s_ray[warp][b][1][lane], job.ray_D(bs + lane));
+    if (BULK) {
+      /* the queue is two arrays of 16-byte records: a tile is two contiguous runs */
+      if (lane == 0) {
+        if (av > 0) {
+          mbar_expect_tx(&s_bar[warp][b], av * 32u);
+          bulk_copy_g2s(&s_ray[warp][b][0][0], job.ray_P(bs), av * 16u, &s_bar[warp][b]);
+          bulk_copy_g2s(&s_ray[warp][b][1][0], job.ray_D(bs), av * 16u, &s_bar[warp][b]);
+        }
+        else {
+          mbar_arrive(&s_bar[warp][b]); /* nothing to move: the phase completes at once */
+        }
+      }
     }
-    cp_async_commit();
+    else {
+      if (lane < av) {
+        cp_async16(&s_ray[warp][b][0][lane], job.ray_P(bs + lane));
+        cp_async16(&s_ray[warp][b][1][lane], job.ray_D(bs + lane));
+      }
+      cp_async_commit();
+    }
     if (b == 0) {
       base0 = bs;
       avail0 = av;
@@ -481,9 +555,31 @@ __device__ __forceinline__ void trace_persistent(Job &job, unsigned int n, unsig
     }
   };
 
+  /* wait until the fill of buffer `b` queued last has landed */
+  auto landed = [&](unsigned int b) {
+    if (BULK) {
+      mbar_wait(&s_bar[warp][b], b ? parity1 : parity0);
+      if (b)
+        parity1 ^= 1u;
+      else
+        parity0 ^= 1u;
+    }
+    else {
+      cp_async_wait<1>(); /* all but the newest group: the older buffer */
+    }
+  };
+  if (BULK) {
+    if (lane == 0) {
+      mbar_init(&s_bar[warp][0], 1u);
+      mbar_init(&s_bar[warp][1], 1u);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+  }
+
   fill(0);
   fill(1);
-  cp_async_wait<1>(); /* buffer 0 has landed */
+  landed(0);
   __syncwarp();
   if (avail0 == 0)
     drained = true;
@@ -526,7 +622,7 @@ __device__ __forceinline__ void trace_persistent(Job &job, unsigned int n, unsig
         /* current half is used up: restage it, switch to the other half */
         __syncwarp();
         fill(cur);
-        cp_async_wait<1>();
+        landed(cur ^ 1u);
         __syncwarp();
         cur ^= 1u;
         consumed = 0;
@@ -673,7 +769,13 @@ __device__ __forceinline__ void trace_persistent(Job &job, unsigned int n, unsig
         break;
     }
   }
-  cp_async_wait<0>();
+  if (BULK) {
+    /* the fill queued last (never consumed) must have landed before the block may go */
+    landed(cur ^ 1u);
+  }
+  else {
+    cp_async_wait<0>();
+  }
 }
 
 #endif /* B200_TRAVERSE_CUH */

@@ -415,6 +415,7 @@ __global__ void __launch_bounds__(WF_BLOCK)
 /* ----------------------------------------------------- intersect_closest */
 
 struct ClosestJob {
+  static constexpr bool QUEUE_RAYS = true; /* two arrays of 16-byte records in queue order */
   PathSoA p;
   __device__ __forceinline__ const float4 *ray_P(unsigned int qi) const
   {
@@ -1255,6 +1256,7 @@ CY_DEV void shadow_light_arrives(const PathSoA &p, unsigned int sh, f3 shadow)
 }
 
 template<bool TRANSPARENT, bool AO = false, bool PASSES = false> struct ShadowJob {
+  static constexpr bool QUEUE_RAYS = true;
   PathSoA p;
   __device__ __forceinline__ const float4 *ray_P(unsigned int qi) const
   {
@@ -1325,6 +1327,7 @@ template<bool TRANSPARENT, bool AO = false, bool PASSES = false> struct ShadowJo
 
 /* closest-hit traversal of one stepping queue; hits land in the (idle) hit arrays */
 struct TransparentShadowJob {
+  static constexpr bool QUEUE_RAYS = true;
   PathSoA p;
   int cur;
   __device__ __forceinline__ const float4 *ray_P(unsigned int qi) const
@@ -2401,6 +2404,9 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
   if (rc)
     return rc;
   DeviceGuard guard(ctx->ordinal);
+  rc = apply_l2_window(ctx);
+  if (rc)
+    return rc;
 
   /* Paths per wavefront batch.  Every kernel of a bounce is one launch over the whole
    * batch and the persistent traversal kernels pay a drain phase per launch (warps
