@@ -228,6 +228,41 @@ CY_DEV uint32_t bvh8_node_intersect(const RaySpace &rs,
   return hitmask;
 }
 
+/* The (node group, leaf group) stack of one lane.  SMEM_STACK > 0 keeps the lowest
+ * SMEM_STACK entries in shared memory (a column per thread, entry k of thread t at
+ * s[k * TRACE_BLOCK + t]: conflict-free 64-bit accesses), deeper ones in local memory.
+ * A/B on B200: profiles/r02o_smem_stack_ab.txt. */
+#ifndef SMEM_STACK
+#  define SMEM_STACK 0
+#endif
+struct TraceStack {
+  uint2 *local;
+#if SMEM_STACK > 0
+  uint2 *shared; /* this thread's column */
+#endif
+  __device__ __forceinline__ uint2 get(int i) const
+  {
+#if SMEM_STACK > 0
+    if (i < SMEM_STACK)
+      return shared[i * 128];
+    return local[i - SMEM_STACK];
+#else
+    return local[i];
+#endif
+  }
+  __device__ __forceinline__ void set(int i, uint2 e) const
+  {
+#if SMEM_STACK > 0
+    if (i < SMEM_STACK)
+      shared[i * 128] = e;
+    else
+      local[i - SMEM_STACK] = e;
+#else
+    local[i] = e;
+#endif
+  }
+};
+
 /* Resumable traversal of one ray, cut into the three phases the persistent warp
  * driver below interleaves:
  *   node_phase()   one BVH8 node (or a leaf group popped earlier) -> pending leaf
@@ -274,15 +309,15 @@ template<bool ANY_HIT, bool COUNT> struct Traversal {
     Gt = make_uint2(0u, 0u);
   }
 
-  __device__ __forceinline__ void push(uint2 *stack, uint2 e)
+  __device__ __forceinline__ void push(const TraceStack &stack, uint2 e)
   {
     if (sp < BVH8_STACK_SIZE)
-      stack[sp++] = e;
+      stack.set(sp++, e);
     else
       g_trace_overflow = 1u;
   }
 
-  __device__ __forceinline__ void node_phase(uint2 *stack, TraceCounters &cnt)
+  __device__ __forceinline__ void node_phase(const TraceStack &stack, TraceCounters &cnt)
   {
     if (G.y & 0xff000000u) {
       const uint32_t hits_imask = G.y;
@@ -334,7 +369,8 @@ template<bool ANY_HIT, bool COUNT> struct Traversal {
    * instances.  Returns true when the traversal is complete. */
   template<class Job>
   __device__ __forceinline__ bool finish_step(
-      uint2 *stack, uint32_t inst_bits, TraceCounters &cnt, const Job &job, unsigned int qi)
+      const TraceStack &stack, uint32_t inst_bits, TraceCounters &cnt, const Job &job,
+      unsigned int qi)
   {
     if (inst_bits != 0u) {
       /* instance push - geom_object.h:427-443 */
@@ -371,10 +407,10 @@ template<bool ANY_HIT, bool COUNT> struct Traversal {
       while (true) {
         if (sp == 0)
           return true;
-        G = stack[--sp];
+        G = stack.get(--sp);
         if (G.x == BVH8_SENTINEL) {
           /* instance pop - geom_object.h:447-460 */
-          const uint2 saved = stack[--sp]; /* (world-space limit, direction scale) */
+          const uint2 saved = stack.get(--sp); /* (world-space limit, direction scale) */
           if (inst_hit)
             tmax = xdiv(tmax, __uint_as_float(saved.y));
           else
@@ -494,7 +530,13 @@ __device__ __forceinline__ void trace_persistent(Job &job, unsigned int n, unsig
   const unsigned warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  uint2 stack[BVH8_STACK_SIZE];
+  uint2 stack_local[BVH8_STACK_SIZE];
+  TraceStack stack;
+  stack.local = stack_local;
+#if SMEM_STACK > 0
+  __shared__ uint2 s_stack[SMEM_STACK * TRACE_BLOCK];
+  stack.shared = s_stack + threadIdx.x;
+#endif
   Traversal<ANY_HIT, COUNT> tr;
   bool active = false;
   unsigned int my_qi = 0;
