@@ -510,11 +510,20 @@ def run_b200(args):
     e2e_all = None
     host_film = None
     if not args.no_e2e:
+        # the step's input: an empty film in pinned host memory (never written, so it needs
+        # no clearing between steps); the step's result comes back into `host_film`
+        empty_film = torch.zeros(h * w * ps, dtype=torch.float32).pin_memory()
         host_film = torch.zeros(h * w * ps, dtype=torch.float32).pin_memory()
         mem = DeviceMemory("RenderBuffers", host_film.numpy())
         dev.mem_alloc(mem)
+        nbytes = int(host_film.numel() * 4)
         e2e_steps = max(1, min(args.steps, 3))
-        dev.mem_copy_to(mem)
+
+        def upload_empty_film():  # mem_copy_to with the input buffer as the source
+            dev._check(dev._L.b200_h2d(dev._ctx, mem.device_pointer, empty_film.data_ptr(), 0,
+                                       nbytes), "mem_copy_to(RenderBuffers)")
+
+        upload_empty_film()
         dev.render_tile(mem.device_pointer, 0, 0, w, h, start_sample, my_spp, 0, w)  # warm
         torch.cuda.synchronize()
         if world > 1:
@@ -522,14 +531,14 @@ def run_b200(args):
         t0 = time.perf_counter()
         e_rays = 0
         for _ in range(e2e_steps):
-            host_film.zero_()
-            dev.mem_copy_to(mem)          # H2D of the step's film (RenderBuffers)
+            upload_empty_film()           # H2D of the step's film (RenderBuffers), every rank
             dev.render_tile(mem.device_pointer, 0, 0, w, h, start_sample, my_spp, 0, w)
             s_ = dev.stats()
             e_rays += s_["primary_rays"] + s_["bounce_rays"] + s_["shadow_rays"]
-            if world > 1:
-                multigpu.reduce_film(mem_as_tensor(mem, film))
-            dev.mem_copy_from(mem)        # D2H of the result
+            if world > 1:                 # the sample split's one exchange: sum onto rank 0
+                multigpu.reduce_film(mem_as_tensor(mem, film), dst=0)
+            if rank == 0:
+                dev.mem_copy_from(mem)    # D2H of the result: the one film of the job
         torch.cuda.synchronize()
         e_sec = time.perf_counter() - t0
         dev.mem_free(mem)
@@ -539,11 +548,12 @@ def run_b200(args):
             e_sec = float(t.item())
         e_rays = all_sum([e_rays], world)[0]
         e2e_all = {"value": e_rays / e_sec / 1e6, "unit": "Mrays/s",
-                   "h2d_bytes_per_step": int(host_film.numel() * 4) * world,
-                   "d2h_bytes_per_step": int(host_film.numel() * 4) * world,
+                   "h2d_bytes_per_step": nbytes * world,
+                   "d2h_bytes_per_step": nbytes,
                    "ms_per_step": 1e3 * e_sec / e2e_steps, "steps": e2e_steps,
-                   "api": "B200Device.mem_copy_to / render_tile (DeviceTask::RENDER) / "
-                          "mem_copy_from over the C ABI, every rank"}
+                   "api": "B200Device.mem_copy_to (an empty film, every rank) / render_tile "
+                          "(DeviceTask::RENDER) / film sum onto rank 0 / mem_copy_from (rank 0) "
+                          "over the C ABI"}
 
     out = None
     if rank == 0:

@@ -5,7 +5,8 @@ cd "$(dirname "$0")/.."
 O=gpurun_out
 T=${1:-r02k}
 ( time python -m pytest tests -m gpu -q ) > $O/${T}_pytest.log 2>&1
-tail -3 $O/${T}_pytest.log | cut -c1-200
+grep -E "passed|failed" $O/${T}_pytest.log | tail -2
+python __graft_entry__.py smoke > $O/${T}_smoke.log 2>&1; tail -2 $O/${T}_smoke.log
 python bench.py --impl reference --steps 2 --warmup 1 > $O/${T}_bench_reference_arm.json 2> $O/${T}_ref.err
 python bench.py --steps 3 --warmup 3 > $O/${T}_bench_n1.json 2> $O/${T}_bench.err
 tail -c 300 $O/${T}_bench.err
