@@ -51,7 +51,8 @@ enum {
   PB_MATERIAL_ID = 51,
   PB_HAS_DATA = 52, /* != 0: the path wrote its data passes (PATH_RAY_SINGLE_PASS_DONE) */
   PB_UNTRACED = 53, /* != 0: no camera ray for this pixel sample, nothing is written */
-  PASS_WORDS = 56
+  PB_AO = 56,       /* the ambient-occlusion pass (path_radiance_accum_ao) */
+  PASS_WORDS = 60
 };
 
 CY_DEV f3 pb_get3(const float *pb, int off)
@@ -69,6 +70,14 @@ CY_DEV void pb_add3(float *pb, int off, f3 v)
   pb[off] += v.x;
   pb[off + 1] += v.y;
   pb[off + 2] += v.z;
+}
+
+/* the light ray and the AO ray of one path may arrive in the same launch */
+CY_DEV void pb_atomic_add3(float *pb, int off, f3 v)
+{
+  atomicAdd(pb + off, v.x);
+  atomicAdd(pb + off + 1, v.y);
+  atomicAdd(pb + off + 2, v.z);
 }
 
 CY_DEV bool light_pass_on(int pass_type) /* PassType 32..63 */

@@ -919,6 +919,22 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
           p.sh_D[slot] = make_float4(ao_D.x, ao_D.y, ao_D.z,
                                      __uint_as_float(CY_PATH_RAY_SHADOW_OPAQUE));
           p.sh_contrib[slot] = make_float4(contribution.x, contribution.y, contribution.z, 0.0f);
+          if (PASSES) {
+            /* path_radiance_accum_ao (kernel_accumulate.h:342-394): the AO pass gets
+             * alpha * throughput on a directly visible surface; the contribution goes to
+             * direct diffuse there, to the indirect light later.  .w of the second record:
+             * 2 / 3 = AO ray at / past the first surface */
+            const f3 transparency = (sd.flag & CY_SD_TRANSPARENT) ?
+                                        sd.closure_transparent_extinction :
+                                        zero3();
+            f3 alpha = mk3(1.0f, 1.0f, 1.0f) - transparency;
+            alpha = mk3(fminf(fmaxf(alpha.x, 0.0f), 1.0f), fminf(fmaxf(alpha.y, 0.0f), 1.0f),
+                        fminf(fmaxf(alpha.z, 0.0f), 1.0f));
+            const f3 ao_pass = alpha * throughput;
+            p.sh_pass[2 * (size_t)slot] = make_float4(ao_pass.x, ao_pass.y, ao_pass.z, 0.0f);
+            p.sh_pass[2 * (size_t)slot + 1] = make_float4(0.0f, 0.0f, 0.0f,
+                                                          st.bounce == 0 ? 2.0f : 3.0f);
+          }
         }
       }
 
@@ -1275,7 +1291,32 @@ template<bool TRANSPARENT, bool AO = false, bool PASSES = false> struct ShadowJo
       /* shade_shadow - path_radiance_accum_light, kernel_accumulate.h:402-459 */
       const int i = p.q_shadow[qi];
       const float4 cn = p.sh_contrib[qi];
-      if (PASSES && kd_int(KD_FILM_USE_LIGHT_PASS)) {
+      if (PASSES && AO) {
+        /* light and AO rays of a path share the launch: atomic adds.  Without light
+         * passes everything is one colour in L. */
+        float *pb = p.pass + (size_t)i * PASS_WORDS;
+        const float4 b = p.sh_pass[2 * (size_t)qi], cc = p.sh_pass[2 * (size_t)qi + 1];
+        if (!kd_int(KD_FILM_USE_LIGHT_PASS)) {
+          float *L = (float *)&p.L[i];
+          atomicAdd(L + 0, cn.x);
+          atomicAdd(L + 1, cn.y);
+          atomicAdd(L + 2, cn.z);
+        }
+        else if (cc.w == 1.0f) {
+          pb_atomic_add3(pb, PB_DIRECT_DIFFUSE, mk3(cn));
+          pb_atomic_add3(pb, PB_DIRECT_GLOSSY, mk3(b));
+          pb_atomic_add3(pb, PB_DIRECT_TRANSMISSION, mk3(cc));
+          pb_atomic_add3(pb, PB_SHADOW, mk3(b.w, b.w, b.w));
+        }
+        else if (cc.w == 2.0f) {
+          pb_atomic_add3(pb, PB_AO, mk3(b));
+          pb_atomic_add3(pb, PB_DIRECT_DIFFUSE, mk3(cn));
+        }
+        else {
+          pb_atomic_add3(pb, PB_INDIRECT, mk3(cn)); /* indirect light, or AO past bounce 0 */
+        }
+      }
+      else if (PASSES && kd_int(KD_FILM_USE_LIGHT_PASS)) {
         /* light passes: a directly visible surface adds per BSDF class (and counts the
          * lamp in the shadow pass), a later one adds to the indirect light */
         float *pb = p.pass + (size_t)i * PASS_WORDS;
@@ -1663,6 +1704,8 @@ __global__ void __launch_bounds__(WF_BLOCK)
           add3(buf + kd_int(KD_FILM_PASS_EMISSION), finite ? emission : zero3());
         if (lp(CY_PASS_BACKGROUND))
           add3(buf + kd_int(KD_FILM_PASS_BACKGROUND), pb_get3(pb, PB_BACKGROUND));
+        if (lp(CY_PASS_AO))
+          add3(buf + kd_int(KD_FILM_PASS_AO), pb_get3(pb, PB_AO));
         if (lp(CY_PASS_DIFFUSE_COLOR))
           add3(buf + kd_int(KD_FILM_PASS_DIFFUSE_COLOR), pb_get3(pb, PB_COLOR_DIFFUSE));
         if (lp(CY_PASS_GLOSSY_COLOR))
@@ -2332,11 +2375,8 @@ static int check_scope(b200_ctx *ctx)
     why = "of the data passes depth, normal, UV, object id and material id are in scope "
           "(motion, AOV and render-time passes are not)";
   else if (I(KD_FILM_LIGHT_PASS_FLAG) &
-           ((1 << (CY_PASS_AO % 32)) | (1 << (CY_PASS_VOLUME_DIRECT % 32)) |
-            (1 << (CY_PASS_VOLUME_INDIRECT % 32))))
-    why = "the AO and volume light passes are outside the hot-path scope";
-  else if (film_wants_passes(ctx) && I(KD_INT_USE_AMBIENT_OCCLUSION))
-    why = "render passes together with world ambient occlusion are outside the hot-path scope";
+           ((1 << (CY_PASS_VOLUME_DIRECT % 32)) | (1 << (CY_PASS_VOLUME_INDIRECT % 32))))
+    why = "the volume light passes are outside the hot-path scope";
   else if (!(I(KD_FILM_PASS_FLAG) & (1u << CY_PASS_COMBINED)))
     why = "the combined pass must be enabled";
   else if (I(KD_FILM_PASS_STRIDE) % 4 != 0)
@@ -2538,7 +2578,10 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
                                                                                       num_keys);
     }
     CUDA_TRY(ctx, cudaEventRecord(ev[2], st));
-    if (passes && transparent_shadows) /* passes never with AO (check_scope) */
+    if (passes && use_ao) /* AO never with transparent shadows (check_scope) */
+      k_intersect_shadow<false, false, true, true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa,
+                                                                                       refill);
+    else if (passes && transparent_shadows)
       k_intersect_shadow<false, true, false, true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa,
                                                                                        refill);
     else if (passes)

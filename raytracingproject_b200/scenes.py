@@ -53,7 +53,7 @@ class SceneDesc:
 
 # kernel_types.h PassType (checked against include/cycles_abi.h by tests/test_scenes_cpu.py)
 PASS = {"depth": 2, "normal": 3, "uv": 4, "object_id": 5, "material_id": 6, "mist": 32,
-        "emission": 33, "background": 34, "shadow": 36, "diffuse_direct": 38,
+        "emission": 33, "background": 34, "ao": 35, "shadow": 36, "diffuse_direct": 38,
         "diffuse_indirect": 39, "diffuse_color": 40, "glossy_direct": 41, "glossy_indirect": 42,
         "glossy_color": 43, "transmission_direct": 44, "transmission_indirect": 45,
         "transmission_color": 46, "adaptive_aux_buffer": 13, "sample_count": 14}

@@ -217,6 +217,19 @@ def pass_cases():
                  'sample_clamp_direct="0"', 'sample_clamp_direct="0.02"')
     d.name += "_clamped"
     cases["clamp_after_transparent_shadows"] = d
+    # world AO with passes (path_radiance_accum_ao): the AO pass itself, AO light in the
+    # direct diffuse pass at the first surface and in the indirect light afterwards; and
+    # with data passes alone, where it is one more colour in the combined pass
+    d = scenes.cornell(W, H, materials="principled", ao=(0.3, 5.0))
+    d.passes = [scenes.PASS[k] for k in ("ao", "diffuse_direct", "diffuse_indirect",
+                                         "glossy_direct", "glossy_indirect", "shadow",
+                                         "diffuse_color", "normal", "depth")]
+    d.name += "_passes"
+    cases["passes_ao"] = d
+    d = scenes.cornell(W, H, materials="diffuse", ao=(0.6, 0.8))
+    d.passes = [scenes.PASS[k] for k in ("normal", "depth", "object_id")]
+    d.name += "_data_passes"
+    cases["passes_ao_data_only"] = d
     return cases
 
 

@@ -190,6 +190,7 @@ def test_image_textures_match_reference(ref, device, name):
 @pytest.mark.parametrize("name", ["passes_cornell_principled", "passes_cornell_image",
                                   "passes_cube_env_transparent_film",
                                   "passes_cornell_mesh_light", "passes_data_only",
+                                  "passes_ao", "passes_ao_data_only",
                                   "light_invisible_to_glossy_rays",
                                   "passes_transparent_shadows",
                                   "clamp_after_transparent_shadows"])
@@ -227,6 +228,8 @@ def test_render_passes_match_reference(ref, device, name):
                 must_have.add("emission")       # lamps are not visible to the camera
             if "env" in name:
                 must_have.add("background")     # the Cornell box is closed, its world black
+            if name == "passes_ao":
+                must_have.add("ao")
             if name == "passes_cornell_principled":
                 must_have |= {"transmission_indirect", "transmission_color", "glossy_color",
                               "diffuse_color", "mist", "uv"}
