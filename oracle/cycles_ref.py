@@ -222,6 +222,13 @@ class RefScene:
         off = self._L.ref_scene_pass_offset(self._h, int(pass_type), C.byref(n))
         return None if off < 0 else (off, n.value)
 
+    def denoising_offset(self):
+        """(float offset of the denoising data passes, of the clean pass) in a film pixel,
+        0 = absent (KernelFilm::pass_denoising_data / pass_denoising_clean)."""
+        self._L.ref_scene_denoising_offset.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        clean = C.c_int()
+        return self._L.ref_scene_denoising_offset(self._h, C.byref(clean)), clean.value
+
     def textures(self):
         """[(slot, TextureInfo bytes, pixel bytes)] - the images the reference's
         ImageManager loaded into its device (CPUDevice::tex_alloc), for
@@ -346,6 +353,10 @@ def build_scene(desc, kernel=RefScene.GENERIC, external_device=None, threads=0, 
     for pass_type in getattr(desc, "passes", None) or []:
         rs._L.ref_scene_add_pass.argtypes = [C.c_void_p, C.c_int]
         rs._L.ref_scene_add_pass(rs._h, int(pass_type))
+    dn = getattr(desc, "denoising", None)  # (clean pass?, DenoiseFlag bits)
+    if dn is not None:
+        rs._L.ref_scene_set_denoising.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        rs._L.ref_scene_set_denoising(rs._h, 1, int(bool(dn[0])), int(dn[1]))
     handles = [rs.add_mesh(m.P, m.tris, m.shader, m.smooth) for m in desc.meshes]
     for mi, tfm in desc.objects:
         o = rs.add_object(handles[mi], tfm)

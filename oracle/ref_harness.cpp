@@ -325,7 +325,37 @@ int ref_scene_add_pass(ref_scene *rs, int pass_type)
   scene->film->tag_update(scene);
   BufferParams bp;
   bp.passes = scene->passes;
+  bp.denoising_data_pass = scene->film->denoising_data_pass;
+  bp.denoising_clean_pass = scene->film->denoising_clean_pass;
   return bp.get_passes_size();
+}
+
+/* Denoising data passes behind the regular ones (film.cpp:604-620; what
+ * BlenderSync::sync_view_layer sets from the view layer's denoising settings):
+ * normal / albedo / depth with their variances, the two shadowing buffers, the colour
+ * with variance, and - with `clean` - the components of `flags` (DenoiseFlag) kept out
+ * of the noisy colour in a clean pass of their own.  Returns the floats per pixel. */
+int ref_scene_set_denoising(ref_scene *rs, int data, int clean, int flags)
+{
+  Scene *scene = rs->scene;
+  scene->film->denoising_data_pass = data != 0;
+  scene->film->denoising_clean_pass = clean != 0;
+  scene->film->denoising_flags = flags;
+  scene->film->tag_update(scene);
+  BufferParams bp;
+  bp.passes = scene->passes;
+  bp.denoising_data_pass = scene->film->denoising_data_pass;
+  bp.denoising_clean_pass = scene->film->denoising_clean_pass;
+  return bp.get_passes_size();
+}
+
+/* After ref_scene_update: float offsets of the denoising data and clean passes inside a
+ * pixel (KernelFilm::pass_denoising_data / _clean, 0 = absent). */
+int ref_scene_denoising_offset(ref_scene *rs, int *clean)
+{
+  if (clean)
+    *clean = rs->scene->dscene.data.film.pass_denoising_clean;
+  return rs->scene->dscene.data.film.pass_denoising_data;
 }
 
 /* Float offset of a pass inside a pixel of the film (RenderBuffers layout: the passes in
@@ -553,6 +583,8 @@ int ref_render(ref_scene *rs,
   bp.full_width = width;
   bp.full_height = height;
   bp.passes = scene->passes;
+  bp.denoising_data_pass = scene->film->denoising_data_pass;
+  bp.denoising_clean_pass = scene->film->denoising_clean_pass;
 
   if (!rs->buffers || rs->buffers->params.modified(bp)) {
     delete rs->buffers;
@@ -657,6 +689,8 @@ int ref_render_tile_buffers(ref_scene *rs,
   full.full_width = width;
   full.full_height = height;
   full.passes = scene->passes;
+  full.denoising_data_pass = scene->film->denoising_data_pass;
+  full.denoising_clean_pass = scene->film->denoising_clean_pass;
   const int pass_stride = full.get_passes_size();
   memset(out, 0, sizeof(float) * (size_t)width * height * pass_stride);
 

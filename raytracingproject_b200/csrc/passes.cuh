@@ -52,8 +52,21 @@ enum {
   PB_HAS_DATA = 52, /* != 0: the path wrote its data passes (PATH_RAY_SINGLE_PASS_DONE) */
   PB_UNTRACED = 53, /* != 0: no camera ray for this pixel sample, nothing is written */
   PB_AO = 56,       /* the ambient-occlusion pass (path_radiance_accum_ao) */
-  PASS_WORDS = 60
+  /* denoising features (film.pass_denoising_data != 0), see denoising_update_features */
+  PB_DN_WEIGHT = 60,       /* PathState::denoising_feature_weight */
+  PB_DN_THROUGHPUT = 61,   /* PathState::denoising_feature_throughput */
+  PB_DN_NORMAL = 64,       /* PathRadiance::denoising_normal / _albedo / _depth */
+  PB_DN_ALBEDO = 67,
+  PB_DN_DEPTH = 70,
+  PB_PATH_TOTAL = 71,        /* light that could have arrived while the feature is open */
+  PB_PATH_TOTAL_SHADED = 74, /* light that did (the "shadowing" feature is their ratio) */
+  PASS_WORDS = 80
 };
+
+CY_DEV bool film_has_denoising()
+{
+  return kd_int(KD_FILM_PASS_DENOISING_DATA) != 0;
+}
 
 CY_DEV f3 pb_get3(const float *pb, int off)
 {
@@ -162,11 +175,14 @@ CY_DEV void shader_bsdf_multi_eval_split(ShaderDataG &sd, const LobeArena &arena
 /* shader_bsdf_eval towards a light sample, MIS-weighted */
 template<bool EXT, bool MS>
 CY_DEV void shader_bsdf_eval_split(ShaderDataG &sd, const LobeArena &arena, f3 omega_in,
-                                   float light_pdf, bool use_mis, EvalSplit &eval)
+                                   float light_pdf, bool use_mis, EvalSplit &eval,
+                                   f3 *sum_no_mis = nullptr)
 {
   eval_split_zero(eval);
   float pdf;
   shader_bsdf_multi_eval_split<EXT, MS>(sd, arena, omega_in, &pdf, -1, eval, 0.0f, 0.0f);
+  if (sum_no_mis)
+    *sum_no_mis = eval_split_sum(eval);
   if (use_mis)
     eval_split_mul(eval, power_heuristic(light_pdf, pdf));
 }
@@ -353,6 +369,94 @@ CY_DEV void pass_write_data(const ShaderDataG &sd, const LobeArena &arena, PathS
     else
       mist = powf(mist, falloff);
     pb[PB_MIST] += (1.0f - mist) * average(throughput * alpha);
+  }
+}
+
+CY_DEV float ensure_finite(float v)
+{
+  return isfinite_safe(v) ? v : 0.0f;
+}
+CY_DEV f3 ensure_finite3(f3 v)
+{
+  return mk3(ensure_finite(v.x), ensure_finite(v.y), ensure_finite(v.z));
+}
+
+/* kernel_update_denoising_features (kernel_passes.h:46-122): the denoiser's guide images
+ * are the normal, albedo and depth of the first surface that is not (mostly) specular -
+ * a path crossing glass or bouncing off a mirror keeps the feature open, weighted by the
+ * specular albedo so far.  Needs what the lobes know: the Fresnel tint a Principled-style
+ * lobe was weighted by (recomputed from its ior and cspec0, svm_closure.cuh
+ * lobe_weigh_by_fresnel), the sheen lobe's average value, the roughness pair. */
+CY_DEV void denoising_update_features(const ShaderDataG &sd, const LobeArena &arena, float *pb)
+{
+  const float fw = pb[PB_DN_WEIGHT];
+  if (fw == 0.0f)
+    return;
+  pb[PB_DN_DEPTH] += ensure_finite(fw * sd.ray_length);
+
+  f3 normal = zero3(), diffuse_albedo = zero3(), specular_albedo = zero3();
+  float sum_weight = 0.0f, sum_nonspecular_weight = 0.0f;
+  int at = 0;
+  for (int i = 0; i < arena.n; i++) {
+    const uint32_t kind = lobe_kind_at(arena, at);
+    if (lobe_is_sampled(kind)) {
+      const Lobe l = lobe_fetch(arena, at);
+      const int id = lobe_id(kind);
+      normal += l.N * l.sample_weight;
+      sum_weight += l.sample_weight;
+      f3 albedo = l.weight;
+      float roughness2 = 1.0f; /* bsdf_get_specular_roughness_squared, closure/bsdf.h:43-55 */
+      const bool fresnel = id == CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_FRESNEL_ID ||
+                           id == CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_GLASS_FRESNEL_ID ||
+                           id == CY_CLOSURE_BSDF_MICROFACET_GGX_FRESNEL_ID ||
+                           id == CY_CLOSURE_BSDF_MICROFACET_GGX_CLEARCOAT_ID;
+      if (fresnel) {
+        const float F0 = fresnel_dielectric_cos(1.0f, l.ior);
+        f3 tint = fresnel_tint(sd.I, l.N, l.ior, F0, l.cspec0);
+        if (id == CY_CLOSURE_BSDF_MICROFACET_GGX_CLEARCOAT_ID)
+          tint *= 0.25f * l.aux;
+        albedo *= tint;
+      }
+      else if (id == CY_CLOSURE_BSDF_PRINCIPLED_SHEEN_ID) {
+        const float NdotI = dot(l.N, sd.I);
+        albedo *= (NdotI < 0.0f) ? 0.0f : schlick_weight(NdotI) * NdotI;
+      }
+      if (id == CY_CLOSURE_BSDF_REFLECTION_ID || id == CY_CLOSURE_BSDF_REFRACTION_ID ||
+          id == CY_CLOSURE_BSDF_TRANSPARENT_ID)
+        roughness2 = 0.0f;
+      else if ((id >= CY_CLOSURE_BSDF_MICROFACET_GGX_ID &&
+                id <= CY_CLOSURE_BSDF_ASHIKHMIN_SHIRLEY_ID) ||
+               (id >= CY_CLOSURE_BSDF_MICROFACET_BECKMANN_REFRACTION_ID &&
+                id <= CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_GLASS_ID) ||
+               id == CY_CLOSURE_BSDF_MICROFACET_MULTI_GGX_GLASS_FRESNEL_ID)
+        roughness2 = l.ax * l.ay;
+      if (roughness2 > 0.075f * 0.075f) {
+        diffuse_albedo += albedo;
+        sum_nonspecular_weight += l.sample_weight;
+      }
+      else {
+        specular_albedo += albedo;
+      }
+    }
+    at += lobe_words(kind);
+  }
+
+  /* wait for the next bounce while 75 % or more of the sample weight is specular */
+  if (sum_weight == 0.0f || sum_nonspecular_weight * 4.0f > sum_weight) {
+    if (sum_weight != 0.0f)
+      normal = normal / sum_weight;
+    tfm34 w2c;
+    w2c.x = kd_float4(KD_CAM_WORLDTOCAMERA);
+    w2c.y = kd_float4(KD_CAM_WORLDTOCAMERA + 16);
+    w2c.z = kd_float4(KD_CAM_WORLDTOCAMERA + 32);
+    normal = transform_direction(w2c, normal);
+    pb_add3(pb, PB_DN_NORMAL, ensure_finite3(normal * fw));
+    pb_add3(pb, PB_DN_ALBEDO,
+            ensure_finite3(pb_get3(pb, PB_DN_THROUGHPUT) * fw * diffuse_albedo));
+    pb[PB_DN_WEIGHT] = 0.0f;
+  }
+  else {
+    pb_set3(pb, PB_DN_THROUGHPUT, pb_get3(pb, PB_DN_THROUGHPUT) * specular_albedo);
   }
 }
 

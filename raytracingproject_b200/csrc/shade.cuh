@@ -1032,11 +1032,13 @@ MULTI_EVAL_ATTR void shader_bsdf_multi_eval(ShaderDataG &sd, const LobeArena &ar
  * (shader_bsdf_eval, kernel_shader.h:612-636, non-branched) */
 template<bool EXT, bool MS = EXT>
 CY_DEV f3 shader_bsdf_eval(ShaderDataG &sd, const LobeArena &arena, f3 omega_in, float light_pdf,
-                           bool use_mis)
+                           bool use_mis, f3 *sum_no_mis = nullptr)
 {
   f3 eval = zero3();
   float pdf;
   shader_bsdf_multi_eval<EXT, MS>(sd, arena, omega_in, &pdf, -1, &eval, 0.0f, 0.0f);
+  if (sum_no_mis) /* BsdfEval::sum_no_mis, kernel_accumulate.h:62-69 */
+    *sum_no_mis = eval;
   if (use_mis)
     eval *= power_heuristic(light_pdf, pdf);
   return eval;

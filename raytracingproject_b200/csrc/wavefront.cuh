@@ -30,6 +30,8 @@
 /* bit 30 of a shadow-queue entry's transparent-bounce word: the path was past its first
  * bounce when it sampled the light (selects the indirect clamp in shadow_light_arrives) */
 #define SH_INDIRECT_FLAG 0x40000000
+/* float4 records per shadow-queue entry in PathSoA::sh_pass (render passes only) */
+#define SH_PASS_QUADS 3
 
 #define WF_MAX_KEYS 4096
 #ifndef WF_BLOCK
@@ -93,7 +95,8 @@ struct PathSoA {
   /* Render passes beyond the combined one (passes.cuh), null otherwise: the per-path
    * accumulator block, and two more colours per shadow-queue entry - a light sample on a
    * directly visible surface arrives split per BSDF class (sh_contrib = diffuse,
-   * sh_pass[2 qi] = glossy | shadow-pass weight, sh_pass[2 qi + 1] = transmission | 1) */
+   * sh_pass[3 qi] = glossy | shadow-pass weight, sh_pass[3 qi + 1] = transmission | kind),
+   * sh_pass[3 qi + 2] = the unweighted light of the denoiser's shadowing feature */
   float *pass;
   float4 *sh_pass;
   /* 1: q_sorted is ordered by key inside every tile of SORT_TILE queue entries
@@ -384,6 +387,8 @@ __global__ void __launch_bounds__(WF_BLOCK)
       /* path_state_init - kernel_path_state.h:19-70 */
       PathStateG st;
       st.flag = CY_PATH_RAY_CAMERA | CY_PATH_RAY_MIS_SKIP | CY_PATH_RAY_TRANSPARENT_BACKGROUND;
+      if (p.pass && film_has_denoising())
+        st.flag |= CY_PATH_RAY_STORE_SHADOW_INFO;
       st.rng_hash = rng_hash;
       st.rng_offset = CY_PRNG_BASE_NUM;
       st.sample = sample;
@@ -401,6 +406,11 @@ __global__ void __launch_bounds__(WF_BLOCK)
       p.L[i] = make_float4(0.0f, 0.0f, 0.0f, (t == 0.0f) ? 1.0f : 0.0f);
       if (p.pass && t == 0.0f) /* the block was cleared for the batch */
         p.pass[(size_t)i * PASS_WORDS + PB_UNTRACED] = 1.0f;
+      if (p.pass && film_has_denoising()) {
+        float *pb = p.pass + (size_t)i * PASS_WORDS;
+        pb[PB_DN_WEIGHT] = 1.0f;
+        pb_set3(pb, PB_DN_THROUGHPUT, mk3(1.0f, 1.0f, 1.0f));
+      }
     }
     unsigned int slot, unused;
     block_append2(&p.counters->n_active, t != 0.0f, &p.counters->n_active, false, &slot, &unused);
@@ -733,6 +743,14 @@ __global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(Pa
       f3 L_background = indirect_background<EXT>(esd, st, rayD);
       /* path_radiance_accum_background - kernel_accumulate.h:478-515 */
       f3 contribution = throughput * L_background;
+      if (PASSES && film_has_denoising()) {
+        if (st.flag & CY_PATH_RAY_STORE_SHADOW_INFO) {
+          pb_add3(pb, PB_PATH_TOTAL, contribution);
+          pb_add3(pb, PB_PATH_TOTAL_SHADED, contribution * 1.0f); /* shadow_transparency */
+        }
+        pb_add3(pb, PB_DN_ALBEDO,
+                pb_get3(pb, PB_DN_THROUGHPUT) * pb[PB_DN_WEIGHT] * L_background);
+      }
       path_radiance_clamp(&contribution, st.bounce - 1);
       if (!use_light_pass)
         L += contribution;
@@ -758,8 +776,8 @@ __global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(Pa
  * a column per thread: a warp touches one 128-byte row per word, no conflicts. */
 #define SHADE_STAGE_WORDS 12
 #define SHADE_SMEM_BYTES (SHADE_STAGE_WORDS * WF_BLOCK * sizeof(float))
-/* with render passes the record carries two more colours and two flags */
-#define SHADE_STAGE_WORDS_PASSES 20
+/* with render passes the record carries three more colours and two flags */
+#define SHADE_STAGE_WORDS_PASSES 24
 #define SHADE_SMEM_BYTES_PASSES (SHADE_STAGE_WORDS_PASSES * WF_BLOCK * sizeof(float))
 
 /* kernel_path_shader_apply .. kernel_path_surface_bounce (kernel_path.h:254-321, 540-640;
@@ -771,8 +789,17 @@ __global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(Pa
  * that follows does not carry them in registers; slots in the next-bounce and shadow
  * queues come from one block-wide reservation at the end of the round, after which the
  * staged record is copied out to its slot. */
-template<bool EXT, bool MS = EXT, bool PASSES = false>
-__global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_MIN_BLOCKS)
+/* DENSE: the same code under a tighter register budget - 3 blocks per SM (80 registers,
+ * some spills) instead of 2 (128 registers).  Measured on B200 (profiles/r02r_*): a scene
+ * where every hit runs the multiscatter random walk gains 20 % from the extra warps, one
+ * where most hits are plain diffuse loses 14 % to the spills; the host times both on the
+ * first batches of a scene and keeps the faster (b200_render, "shade_dense"). */
+#ifndef SHADE_DENSE_BLOCKS
+#  define SHADE_DENSE_BLOCKS 3
+#endif
+template<bool EXT, bool MS = EXT, bool PASSES = false, bool DENSE = false>
+__global__ void __launch_bounds__(WF_BLOCK, DENSE ? SHADE_DENSE_BLOCKS :
+                                                   (EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_MIN_BLOCKS))
     k_shade_surface(PathSoA p, int num_keys)
 {
   extern __shared__ float s_shade[];
@@ -881,6 +908,10 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
         }
       }
 
+      const bool denoising = PASSES && film_has_denoising();
+      if (denoising && alive) /* kernel_path.h:592-595 */
+        denoising_update_features(sd, arena, pb);
+
       if (EXT && alive && kd_int(KD_INT_USE_AMBIENT_OCCLUSION)) {
         /* kernel_path_ao (kernel_path.h:328-372): one cosine-weighted ray of length
          * ao_distance around the averaged diffuse normal; it joins the shadow queue as a
@@ -906,6 +937,9 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
         if (dot(sd.Ng, ao_D) > 0.0f && ao_pdf != 0.0f) {
           const f3 aP = ray_offset(sd.P, sd.Ng);
           const f3 contribution = throughput * ao_bsdf;
+          const bool store_shadow = denoising && (st.flag & CY_PATH_RAY_STORE_SHADOW_INFO);
+          if (store_shadow)
+            pb_add3(pb, PB_PATH_TOTAL, contribution);
           /* one returning atomic per warp */
           const unsigned int m = __activemask();
           const unsigned int lane = threadIdx.x & 31u;
@@ -931,9 +965,13 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
             alpha = mk3(fminf(fmaxf(alpha.x, 0.0f), 1.0f), fminf(fmaxf(alpha.y, 0.0f), 1.0f),
                         fminf(fmaxf(alpha.z, 0.0f), 1.0f));
             const f3 ao_pass = alpha * throughput;
-            p.sh_pass[2 * (size_t)slot] = make_float4(ao_pass.x, ao_pass.y, ao_pass.z, 0.0f);
-            p.sh_pass[2 * (size_t)slot + 1] = make_float4(0.0f, 0.0f, 0.0f,
-                                                          st.bounce == 0 ? 2.0f : 3.0f);
+            p.sh_pass[SH_PASS_QUADS * (size_t)slot] = make_float4(ao_pass.x, ao_pass.y, ao_pass.z,
+                                                                  0.0f);
+            p.sh_pass[SH_PASS_QUADS * (size_t)slot + 1] = make_float4(
+                0.0f, 0.0f, 0.0f, st.bounce == 0 ? 2.0f : 3.0f);
+            p.sh_pass[SH_PASS_QUADS * (size_t)slot + 2] =
+                store_shadow ? make_float4(contribution.x, contribution.y, contribution.z, 0.0f) :
+                               make_float4(0.0f, 0.0f, 0.0f, 0.0f);
           }
         }
       }
@@ -973,9 +1011,15 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
               f3 eval = zero3();
               EvalSplit ev;
               bool ok;
+              /* light that could arrive, before MIS: the denoiser's shadowing feature
+               * (BsdfEval::sum_no_mis, PATH_RAY_STORE_SHADOW_INFO) */
+              const bool store_shadow = denoising && (st.flag & CY_PATH_RAY_STORE_SHADOW_INFO);
+              f3 no_mis = zero3();
               if (use_light_pass) {
                 shader_bsdf_eval_split<EXT, MS>(sd, arena, ls.D, ls.pdf,
-                                                (ls.shader & CY_SHADER_USE_MIS) != 0, ev);
+                                                (ls.shader & CY_SHADER_USE_MIS) != 0, ev,
+                                                store_shadow ? &no_mis : nullptr);
+                no_mis *= light_eval / ls.pdf;
                 eval_split_mul3(ev, light_eval / ls.pdf);
                 if (ls.shader & CY_SHADER_EXCLUDE_ANY) {
                   if (ls.shader & CY_SHADER_EXCLUDE_DIFFUSE)
@@ -990,7 +1034,9 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
               }
               else {
                 eval = shader_bsdf_eval<EXT, MS>(sd, arena, ls.D, ls.pdf,
-                                                 (ls.shader & CY_SHADER_USE_MIS) != 0);
+                                                 (ls.shader & CY_SHADER_USE_MIS) != 0,
+                                                 store_shadow ? &no_mis : nullptr);
+                no_mis *= light_eval / ls.pdf;
                 eval *= light_eval / ls.pdf;
                 ok = !is_zero(eval);
               }
@@ -1002,6 +1048,7 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
                     ok = false;
                   else {
                     eval *= 1.0f / probability;
+                    no_mis *= 1.0f / probability;
                     if (use_light_pass)
                       eval_split_mul(ev, 1.0f / probability);
                   }
@@ -1015,6 +1062,9 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
                  * adds the total to the indirect light (A) */
                 f3 contribution, part_b = zero3(), part_c = zero3();
                 float shadow_add = 0.0f;
+                const f3 light_total = throughput * no_mis; /* zero unless store_shadow */
+                if (store_shadow)
+                  pb_add3(pb, PB_PATH_TOTAL, light_total);
                 /* with transparent shadows the clamp waits for the attenuation
                  * (shadow_light_arrives) */
                 const bool defer_clamp = kd_int(KD_INT_TRANSPARENT_SHADOWS) != 0 &&
@@ -1084,21 +1134,30 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
                     stage[17 * WF_BLOCK] = part_c.y;
                     stage[18 * WF_BLOCK] = part_c.z;
                     stage[19 * WF_BLOCK] = (use_light_pass && st.bounce == 0) ? 1.0f : 0.0f;
+                    stage[20 * WF_BLOCK] = light_total.x;
+                    stage[21 * WF_BLOCK] = light_total.y;
+                    stage[22 * WF_BLOCK] = light_total.z;
                   }
                   want_shadow = true;
                 }
                 else if (!use_light_pass) {
                   /* ray.t = 0: shadow_blocked returns false immediately */
                   L += contribution;
+                  if (store_shadow)
+                    pb_add3(pb, PB_PATH_TOTAL_SHADED, light_total);
                 }
                 else if (st.bounce == 0) {
                   pb_add3(pb, PB_DIRECT_DIFFUSE, contribution);
                   pb_add3(pb, PB_DIRECT_GLOSSY, part_b);
                   pb_add3(pb, PB_DIRECT_TRANSMISSION, part_c);
                   pb_add3(pb, PB_SHADOW, mk3(shadow_add, shadow_add, shadow_add));
+                  if (store_shadow)
+                    pb_add3(pb, PB_PATH_TOTAL_SHADED, light_total);
                 }
                 else {
                   pb_add3(pb, PB_INDIRECT, contribution);
+                  if (store_shadow)
+                    pb_add3(pb, PB_PATH_TOTAL_SHADED, light_total);
                 }
               }
             }
@@ -1152,6 +1211,11 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
               st.min_ray_pdf = fminf(bsdf_pdf, st.min_ray_pdf);
             }
             path_state_next(st, label);
+            /* kernel_path_state.h:164-168: once the feature is closed nothing more is
+             * counted for the shadowing ratio - decided at the end of path_state_next,
+             * which a transparent bounce leaves early (:84-99) */
+            if (denoising && !(label & CY_LABEL_TRANSPARENT) && pb[PB_DN_WEIGHT] == 0.0f)
+              st.flag &= ~CY_PATH_RAY_STORE_SHADOW_INFO;
             const f3 nP = ray_offset(sd.P, (label & CY_LABEL_TRANSMIT) ? -sd.Ng : sd.Ng);
             const f3 nD = normalize(omega_in);
             if (st.bounce == 0)
@@ -1207,10 +1271,13 @@ __global__ void __launch_bounds__(WF_BLOCK, EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_M
       p.sh_contrib[s_sh] = make_float4(stage[7 * WF_BLOCK], stage[8 * WF_BLOCK],
                                        stage[9 * WF_BLOCK], stage[10 * WF_BLOCK]);
       if (PASSES) {
-        p.sh_pass[2 * (size_t)s_sh] = make_float4(stage[12 * WF_BLOCK], stage[13 * WF_BLOCK],
-                                                  stage[14 * WF_BLOCK], stage[15 * WF_BLOCK]);
-        p.sh_pass[2 * (size_t)s_sh + 1] = make_float4(stage[16 * WF_BLOCK], stage[17 * WF_BLOCK],
-                                                      stage[18 * WF_BLOCK], stage[19 * WF_BLOCK]);
+        float4 *sp = p.sh_pass + SH_PASS_QUADS * (size_t)s_sh;
+        sp[0] = make_float4(stage[12 * WF_BLOCK], stage[13 * WF_BLOCK], stage[14 * WF_BLOCK],
+                            stage[15 * WF_BLOCK]);
+        sp[1] = make_float4(stage[16 * WF_BLOCK], stage[17 * WF_BLOCK], stage[18 * WF_BLOCK],
+                            stage[19 * WF_BLOCK]);
+        sp[2] = make_float4(stage[20 * WF_BLOCK], stage[21 * WF_BLOCK], stage[22 * WF_BLOCK],
+                            0.0f);
       }
     }
   }
@@ -1233,9 +1300,14 @@ CY_DEV void shadow_light_arrives(const PathSoA &p, unsigned int sh, f3 shadow)
   const float limit = (__float_as_int(cn.w) & SH_INDIRECT_FLAG) ?
                           kd_float(KD_INT_SAMPLE_CLAMP_INDIRECT) :
                           kd_float(KD_INT_SAMPLE_CLAMP_DIRECT);
+  if (PASSES && film_has_denoising()) {
+    /* path_total_shaded += shadow * light (kernel_accumulate.h:412-416) */
+    const f3 light = mk3(p.sh_pass[SH_PASS_QUADS * (size_t)sh + 2]);
+    pb_add3(p.pass + (size_t)i * PASS_WORDS, PB_PATH_TOTAL_SHADED, shadow * light);
+  }
   if (PASSES && kd_int(KD_FILM_USE_LIGHT_PASS)) {
     float *pb = p.pass + (size_t)i * PASS_WORDS;
-    const float4 b = p.sh_pass[2 * (size_t)sh], cc = p.sh_pass[2 * (size_t)sh + 1];
+    const float4 b = p.sh_pass[SH_PASS_QUADS * (size_t)sh], cc = p.sh_pass[SH_PASS_QUADS * (size_t)sh + 1];
     if (cc.w != 0.0f) {
       f3 A = mk3(cn) * shadow, B = mk3(b) * shadow, C = mk3(cc) * shadow;
       const float sum = reduce_add(fabs3(A + B + C));
@@ -1291,11 +1363,20 @@ template<bool TRANSPARENT, bool AO = false, bool PASSES = false> struct ShadowJo
       /* shade_shadow - path_radiance_accum_light, kernel_accumulate.h:402-459 */
       const int i = p.q_shadow[qi];
       const float4 cn = p.sh_contrib[qi];
+      if (PASSES && film_has_denoising()) {
+        /* the denoiser's shadowing feature: the light arrived (shadow = 1, or ao = 1) */
+        float *pb = p.pass + (size_t)i * PASS_WORDS;
+        const f3 light = mk3(p.sh_pass[SH_PASS_QUADS * (size_t)qi + 2]);
+        if (AO)
+          pb_atomic_add3(pb, PB_PATH_TOTAL_SHADED, light);
+        else
+          pb_add3(pb, PB_PATH_TOTAL_SHADED, light);
+      }
       if (PASSES && AO) {
         /* light and AO rays of a path share the launch: atomic adds.  Without light
          * passes everything is one colour in L. */
         float *pb = p.pass + (size_t)i * PASS_WORDS;
-        const float4 b = p.sh_pass[2 * (size_t)qi], cc = p.sh_pass[2 * (size_t)qi + 1];
+        const float4 b = p.sh_pass[SH_PASS_QUADS * (size_t)qi], cc = p.sh_pass[SH_PASS_QUADS * (size_t)qi + 1];
         if (!kd_int(KD_FILM_USE_LIGHT_PASS)) {
           float *L = (float *)&p.L[i];
           atomicAdd(L + 0, cn.x);
@@ -1320,7 +1401,7 @@ template<bool TRANSPARENT, bool AO = false, bool PASSES = false> struct ShadowJo
         /* light passes: a directly visible surface adds per BSDF class (and counts the
          * lamp in the shadow pass), a later one adds to the indirect light */
         float *pb = p.pass + (size_t)i * PASS_WORDS;
-        const float4 b = p.sh_pass[2 * (size_t)qi], cc = p.sh_pass[2 * (size_t)qi + 1];
+        const float4 b = p.sh_pass[SH_PASS_QUADS * (size_t)qi], cc = p.sh_pass[SH_PASS_QUADS * (size_t)qi + 1];
         if (cc.w != 0.0f) {
           pb_add3(pb, PB_DIRECT_DIFFUSE, mk3(cn));
           pb_add3(pb, PB_DIRECT_GLOSSY, mk3(b));
@@ -1720,6 +1801,50 @@ __global__ void __launch_bounds__(WF_BLOCK)
         if (lp(CY_PASS_MIST))
           buf[kd_int(KD_FILM_PASS_MIST)] += 1.0f - pb[PB_MIST];
       }
+      if (film_has_denoising()) {
+        /* kernel_write_result, kernel_passes.h:355-389 */
+        float *dn = buf + kd_int(KD_FILM_PASS_DENOISING_DATA);
+        {
+          /* kernel_write_denoising_shadow: even and odd samples in two buffers */
+          float *sh = dn + (sample_is_even(kd_int(KD_INT_SAMPLING_PATTERN), bp.sample0 + s) ?
+                                CY_DENOISING_PASS_SHADOW_B :
+                                CY_DENOISING_PASS_SHADOW_A);
+          const float path_total = ensure_finite(average(pb_get3(pb, PB_PATH_TOTAL)));
+          const float path_total_shaded = ensure_finite(
+              average(pb_get3(pb, PB_PATH_TOTAL_SHADED)));
+          sh[0] += path_total;
+          sh[1] += path_total_shaded;
+          const float value = path_total_shaded / fmaxf(path_total, 1e-7f);
+          sh[2] += value * value;
+        }
+        f3 noisy;
+        if (kd_int(KD_FILM_PASS_DENOISING_CLEAN)) {
+          /* path_radiance_split_denoising, kernel_accumulate.h:690-727 */
+          const int cf = kd_int(KD_FILM_DENOISING_FLAGS);
+          f3 clean = (finite ? emission : zero3()) + pb_get3(pb, PB_BACKGROUND);
+          noisy = zero3() + zero3();
+          if (cf & CY_DENOISING_CLEAN_DIFFUSE_DIR) clean += dd; else noisy += dd;
+          if (cf & CY_DENOISING_CLEAN_DIFFUSE_IND) clean += id; else noisy += id;
+          if (cf & CY_DENOISING_CLEAN_GLOSSY_DIR) clean += dg; else noisy += dg;
+          if (cf & CY_DENOISING_CLEAN_GLOSSY_IND) clean += ig; else noisy += ig;
+          if (cf & CY_DENOISING_CLEAN_TRANSMISSION_DIR) clean += dt; else noisy += dt;
+          if (cf & CY_DENOISING_CLEAN_TRANSMISSION_IND) clean += it; else noisy += it;
+          noisy = ensure_finite3(noisy);
+          add3(buf + kd_int(KD_FILM_PASS_DENOISING_CLEAN), ensure_finite3(clean));
+        }
+        else {
+          noisy = ensure_finite3(L_sum);
+        }
+        add3(dn + CY_DENOISING_PASS_COLOR, noisy);
+        add3(dn + CY_DENOISING_PASS_COLOR_VAR, noisy * noisy);
+        const f3 dnn = pb_get3(pb, PB_DN_NORMAL), dna = pb_get3(pb, PB_DN_ALBEDO);
+        add3(dn + CY_DENOISING_PASS_NORMAL, dnn);
+        add3(dn + CY_DENOISING_PASS_NORMAL_VAR, dnn * dnn);
+        add3(dn + CY_DENOISING_PASS_ALBEDO, dna);
+        add3(dn + CY_DENOISING_PASS_ALBEDO_VAR, dna * dna);
+        dn[CY_DENOISING_PASS_DEPTH] += pb[PB_DN_DEPTH];
+        dn[CY_DENOISING_PASS_DEPTH_VAR] += pb[PB_DN_DEPTH] * pb[PB_DN_DEPTH];
+      }
       if (pb[PB_HAS_DATA] != 0.0f) {
         if (bp.sample0 + s == 0) {
           if (flag & (1 << CY_PASS_DEPTH))
@@ -1932,7 +2057,7 @@ static int ensure_pool(b200_ctx *ctx, size_t capacity, bool transparent_shadows,
          o_tsT = carve(nts * 16);
   /* render passes: PASS_WORDS floats per path, two more colours per shadow entry */
   const size_t npass = passes ? n : 0;
-  size_t o_pass = carve(npass * PASS_WORDS * sizeof(float)), o_shpass = carve((passes ? nsh : 0) * 32);
+  size_t o_pass = carve(npass * PASS_WORDS * sizeof(float)), o_shpass = carve((passes ? nsh : 0) * SH_PASS_QUADS * 16);
   cudaError_t e = cudaMalloc(&pool->block, off);
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -2308,6 +2433,7 @@ static int bound_image_slots(const b200_ctx *ctx)
 static bool film_wants_passes(const b200_ctx *ctx)
 {
   return kd_host<int>(ctx, KD_FILM_USE_LIGHT_PASS) != 0 ||
+         kd_host<int>(ctx, KD_FILM_PASS_DENOISING_DATA) != 0 ||
          (kd_host<int>(ctx, KD_FILM_PASS_FLAG) &
           ~((1 << CY_PASS_COMBINED) | (1 << CY_PASS_ADAPTIVE_AUX_BUFFER) |
             (1 << CY_PASS_SAMPLE_COUNT))) != 0;
@@ -2359,8 +2485,11 @@ static int check_scope(b200_ctx *ctx)
             find_global(ctx, "__light_background_conditional_cdf")->bytes <
                 (size_t)(I(KD_BG_MAP_RES_X) + 1) * I(KD_BG_MAP_RES_Y) * 8))
     why = "background importance sampling needs the world map CDF arrays";
-  else if (I(KD_FILM_PASS_DENOISING_DATA) || I(KD_FILM_CRYPTOMATTE_PASSES))
-    why = "denoising data and cryptomatte passes are outside the hot-path scope";
+  else if (I(KD_FILM_CRYPTOMATTE_PASSES))
+    why = "cryptomatte passes are outside the hot-path scope";
+  else if (I(KD_FILM_PASS_DENOISING_CLEAN) &&
+           (!I(KD_FILM_PASS_DENOISING_DATA) || !I(KD_FILM_USE_LIGHT_PASS)))
+    why = "the denoising clean pass needs the denoising data passes and light passes";
   else if (I(KD_FILM_PASS_ADAPTIVE_AUX_BUFFER) &&
            (I(KD_INT_SAMPLING_PATTERN) != CY_SAMPLING_PATTERN_PMJ || film_wants_passes(ctx) ||
             I(KD_FILM_PASS_ADAPTIVE_AUX_BUFFER) % 4 != 0))
@@ -2408,11 +2537,12 @@ static int shade_kernel_setup(b200_ctx *ctx)
   if (ctx->shade_blocks_per_sm[0] > 0)
     return B200_OK;
   DeviceGuard guard(ctx->ordinal);
-  const void *kernels[4] = {(const void *)k_shade_surface<false, false>,
+  const void *kernels[5] = {(const void *)k_shade_surface<false, false>,
                             (const void *)k_shade_surface<false, true>,
                             (const void *)k_shade_surface<true, true>,
-                            (const void *)k_shade_surface<true, true, true>};
-  for (int k = 0; k < 4; k++) {
+                            (const void *)k_shade_surface<true, true, true>,
+                            (const void *)k_shade_surface<false, true, false, true>};
+  for (int k = 0; k < 5; k++) {
     const size_t smem = (k == 3) ? SHADE_SMEM_BYTES_PASSES : SHADE_SMEM_BYTES;
     CUDA_TRY(ctx, cudaFuncSetAttribute(kernels[k], cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
@@ -2464,7 +2594,7 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
       const size_t per_path = PATH_POOL_BYTES_PER_PATH +
                               (kd_host<int>(ctx, KD_INT_TRANSPARENT_SHADOWS) ? 88 : 0) +
                               (kd_host<int>(ctx, KD_INT_USE_AMBIENT_OCCLUSION) ? 52 : 0) +
-                              (film_wants_passes(ctx) ? PASS_WORDS * 4 + 32 : 0);
+                              (film_wants_passes(ctx) ? PASS_WORDS * 4 + SH_PASS_QUADS * 16 : 0);
       const size_t fit = (free_b + held) / 4 / per_path;
       capacity = std::max<size_t>(std::min(capacity, fit), (size_t)1 << 16);
     }
@@ -2538,10 +2668,14 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
 
   /* one bounce of the whole batch: 8 launches, the head of the counters into the
    * iteration's ring slot, events around the three phases */
+  /* which register budget of the lean multiscatter kernel this batch runs (see
+   * k_shade_surface, DENSE): forced, decided, or - while probing - alternating by batch */
+  bool shade_dense = false;
   auto enqueue_iteration = [&](const PathSoA &soa, int it) -> int {
     cudaEvent_t *ev = pool->ring_ev[it % WF_RING];
     const int grid_shade = ctx->num_sms *
-                           ctx->shade_blocks_per_sm[svm_ext ? 2 : (multiscatter ? 1 : 0)];
+                           ctx->shade_blocks_per_sm[svm_ext ? 2 :
+                                                    (multiscatter ? (shade_dense ? 4 : 1) : 0)];
     CUDA_TRY(ctx, cudaEventRecord(ev[0], st));
     if (count)
       k_intersect_closest<true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
@@ -2570,7 +2704,10 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
     }
     else {
       k_shade_background<false><<<grid_wide, WF_BLOCK, 0, st>>>(soa);
-      if (multiscatter)
+      if (multiscatter && shade_dense)
+        k_shade_surface<false, true, false, true>
+            <<<grid_shade, WF_BLOCK, SHADE_SMEM_BYTES, st>>>(soa, num_keys);
+      else if (multiscatter)
         k_shade_surface<false, true><<<grid_shade, WF_BLOCK, SHADE_SMEM_BYTES, st>>>(soa,
                                                                                      num_keys);
       else
@@ -2704,6 +2841,15 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
       bp.pass_stride = pass_stride;
       bp.adaptive_aux = adaptive_aux;
 
+      const bool probing = multiscatter && ctx->opt_shade_dense < 0 &&
+                           ctx->shade_dense_choice < 0;
+      if (ctx->opt_shade_dense >= 0)
+        shade_dense = ctx->opt_shade_dense != 0;
+      else if (ctx->shade_dense_choice >= 0)
+        shade_dense = ctx->shade_dense_choice != 0;
+      else
+        shade_dense = (ctx->shade_probe_batches++ & 1) != 0;
+      const float shade_ms_before = shade_ms;
       for (int attempt = 0;; attempt++) {
         PathSoA soa = pool->soa;
         soa.sort_tiles = (num_keys <= SORT_TILE_MAX_KEYS && ctx->opt_sort_tiles) ? 1 : 0;
@@ -2792,6 +2938,22 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
                                       st));
         CUDA_TRY(ctx, cudaGetLastError());
         stats.batches += 1;
+        if (probing && !svm_ext) {
+          /* every iteration with work has been harvested when the bounce loop ends: the
+           * batch's shading time is complete.  Decide once both budgets have shaded 4 Mi
+           * paths; until then (small tiles) keep alternating. */
+          const int v = shade_dense ? 1 : 0;
+          /* the first batch of each budget pays for loading its kernel: not counted */
+          if (ctx->shade_probe_batches > 2) {
+            ctx->shade_probe_ms[v] += (double)(shade_ms - shade_ms_before);
+            ctx->shade_probe_paths[v] += (double)npix * bp.nsamples;
+          }
+          const double enough = (double)(1 << 22);
+          if (ctx->shade_probe_paths[0] >= enough && ctx->shade_probe_paths[1] >= enough)
+            ctx->shade_dense_choice =
+                (ctx->shade_probe_ms[1] / ctx->shade_probe_paths[1] <
+                 ctx->shade_probe_ms[0] / ctx->shade_probe_paths[0]) ? 1 : 0;
+        }
         if (++batch_slot == WF_BATCH_SLOTS) {
           rc = sum_batch_stats();
           if (rc)
@@ -2843,6 +3005,10 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
     stats.shadow_ms = shadow_ms;
   }
   stats.svm_extended = svm_ext ? 1 : 0;
+  stats.shade_dense = (multiscatter && !svm_ext) ?
+                          (ctx->opt_shade_dense >= 0 ? (ctx->opt_shade_dense != 0) :
+                                                       ctx->shade_dense_choice) :
+                          0;
   ctx->stats = stats;
   return B200_OK;
 }

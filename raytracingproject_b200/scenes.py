@@ -41,6 +41,9 @@ class SceneDesc:
     passes: List[int] = field(default_factory=list)
     # UDIM tile numbers of Image Texture nodes: (shader name, node name, [tiles])
     image_tiles: List[Tuple[str, str, List[int]]] = field(default_factory=list)
+    # denoising data passes behind the others (film.cpp:604-620): None, or
+    # (clean pass?, DenoiseFlag bits of the components the clean pass takes)
+    denoising: Optional[Tuple[bool, int]] = None
 
     @property
     def num_triangles(self):

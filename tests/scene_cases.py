@@ -233,6 +233,38 @@ def pass_cases():
     return cases
 
 
+def denoising_cases():
+    """Denoising data passes (kernel_passes.h:21-122, 355-389): normal / albedo / depth
+    features of the first non-specular surface (through the glass box, off the metal one),
+    the shadowing buffers (light that arrived over light that could have), colour with
+    variance; alone, next to light passes with a clean pass that takes three components out
+    of the noisy colour, and with world AO (whose rays count for the shadowing too)."""
+    cases = {}
+    d = scenes.cornell(W, H, materials="principled")
+    d.denoising = (False, 0)
+    d.name += "_denoising"
+    cases["denoising_data"] = d
+    d = scenes.cornell(W, H, materials="principled")
+    d.passes = [scenes.PASS[k] for k in ("diffuse_direct", "diffuse_indirect", "glossy_indirect",
+                                         "normal")]
+    d.denoising = (True, 1 | 8 | 16)  # diffuse direct, glossy indirect, transmission direct
+    d.name += "_denoising_clean"
+    cases["denoising_clean"] = d
+    d = scenes.cornell(W, H, materials="principled", ao=(0.3, 5.0))
+    d.denoising = (False, 0)
+    d.name += "_denoising_ao"
+    cases["denoising_ao"] = d
+    d = scenes.cornell(W, H, materials="transparent", panes=3)
+    d.denoising = (False, 0)
+    d.name += "_denoising"
+    cases["denoising_transparent_shadows"] = d
+    d = scenes.default_cube(W, H, world="env_equirect")
+    d.denoising = (False, 0)
+    d.name += "_denoising"
+    cases["denoising_cube_env"] = d
+    return cases
+
+
 def _replace(desc, old, new):
     assert old in desc.xml, old
     desc.xml = desc.xml.replace(old, new)

@@ -6,7 +6,8 @@ gates hold at any spp, not only at 1024."""
 import numpy as np
 import pytest
 
-from scene_cases import (adaptive_cases, ao_cases, camera_cases, closure_cases, image_cases, light_cases,
+from scene_cases import (adaptive_cases, ao_cases, camera_cases, closure_cases, denoising_cases,
+                         image_cases, light_cases,
                          pass_cases, principled_cases, sampling_cases, small_cases,
                          texture_cases, world_light_cases)
 
@@ -537,4 +538,80 @@ def test_tiles_and_small_pool(ref, device):
         device.set_option("batch_paths", 0)
         assert np.array_equal(whole, film.host)
     finally:
+        rs.close()
+
+
+DENOISING_FEATURES = (("normal", 0, 3), ("normal_var", 3, 3), ("albedo", 6, 3),
+                      ("albedo_var", 9, 3), ("depth", 12, 1), ("depth_var", 13, 1),
+                      ("shadow_a", 14, 3), ("shadow_b", 17, 3), ("color", 20, 3),
+                      ("color_var", 23, 3))
+
+
+@pytest.mark.parametrize("name", ["denoising_data", "denoising_clean", "denoising_ao",
+                                  "denoising_transparent_shadows", "denoising_cube_env"])
+def test_denoising_data_passes_match_reference(ref, device, name):
+    """The denoising data passes behind the regular ones (kernel_passes.h:21-122, 355-389;
+    DENOISING_PASS_* offsets of kernel_types.h:414-437) against the reference CPU kernel,
+    feature by feature, plus the combined pass and the clean pass."""
+    desc = denoising_cases()[name]
+    rs = ref.build_scene(desc)
+    try:
+        device.upload_scene(rs.device_arrays(), rs.textures())
+        ref_img, _ = rs.render(0, SPP, tile_size=64)
+        got = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP)
+        assert got.shape == ref_img.shape
+        off, _ = rs.pass_offset(1)
+        image_gates(ref_img[..., off:off + 4], got[..., off:off + 4], SPP, name + " combined")
+        dn, clean = rs.denoising_offset()
+        assert dn > 0 and dn + 26 <= rs.pass_stride
+        features = list(DENOISING_FEATURES)
+        if desc.denoising[0]:
+            assert clean > 0
+            features.append(("clean", clean - dn, 3))
+        for label, o, n in features:
+            a = ref_img[..., dn + o:dn + o + n].astype(np.float64) / SPP
+            b = got[..., dn + o:dn + o + n].astype(np.float64) / SPP
+            rmse = float(np.sqrt(np.mean((a - b) ** 2)))
+            scale = max(float(np.abs(a).mean()), 1e-9)
+            rel = abs(float(a.mean()) - float(b.mean())) / scale
+            print("%s %-12s rmse=%.3e mean ref=%.6f got=%.6f rel=%.2e max|d|=%.2e" % (
+                name, label, rmse, a.mean(), b.mean(), rel, np.abs(a - b).max()))
+            assert np.abs(a).max() > 0.0, label + ": the reference feature is empty"
+            assert rmse <= 1e-3 * max(1.0, scale) and rel <= 1e-3, label
+        # nothing is written past the passes the film holds
+        used = dn + 26 + (3 if desc.denoising[0] else 0)
+        assert not got[..., used:].any() and not ref_img[..., used:].any()
+    finally:
+        rs.close()
+
+
+@pytest.mark.parametrize("name", ["cube_principled_multiscatter",
+                                  "cornell_principled_multiscatter"])
+def test_shading_register_budgets_render_the_same_film(ref, device, name):
+    """The lean multiscatter shading kernel exists at two register budgets (k_shade_surface
+    DENSE); the device times both on the first batches of a scene and keeps the faster.
+    Same code, same arithmetic: whichever runs, the film is bit-identical - forced either
+    way, and while the probe alternates between them batch by batch."""
+    from scene_cases import principled_cases
+    desc = principled_cases()[name]
+    rs = ref.build_scene(desc)
+    try:
+        device.upload_scene(rs.device_arrays())
+        films = {}
+        for mode in (0, 1, -1):
+            device.set_option("shade_dense", mode)
+            device.set_option("batch_paths", 0 if mode >= 0 else 1 << 16)
+            films[mode] = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP)
+            st = device.stats()
+            assert st["svm_extended"] == 0
+            assert st["shade_dense"] == (mode if mode >= 0 else st["shade_dense"])
+            if mode < 0:
+                assert st["batches"] >= 8   # the probe saw both budgets
+        assert np.array_equal(films[0], films[1])
+        assert np.array_equal(films[0], films[-1])
+        ref_img, _ = rs.render(0, SPP, tile_size=64)
+        image_gates(ref_img, films[1], SPP, name + " dense")
+    finally:
+        device.set_option("shade_dense", -1)
+        device.set_option("batch_paths", 0)
         rs.close()
