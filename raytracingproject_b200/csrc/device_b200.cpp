@@ -699,6 +699,22 @@ void device_b200_info(vector<DeviceInfo> &devices)
   }
 }
 
+/* In a patched tree Device::create calls the three functions above directly
+ * (INTEGRATION.md section 2).  The host library of this repo is built from the read-only
+ * reference with the same rows on a copy of device.cpp, reaching them through pointers
+ * registered here when this library is loaded (oracle/ref_host_hooks.cpp). */
+extern "C" void ref_host_register_b200_device(void *init, void *create, void *info);
+
+namespace {
+struct B200DeviceRegistration {
+  B200DeviceRegistration()
+  {
+    ref_host_register_b200_device((void *)&device_b200_init, (void *)&device_b200_create,
+                                  (void *)&device_b200_info);
+  }
+} g_b200_device_registration;
+}  // namespace
+
 CCL_NAMESPACE_END
 
 /* ---- C entry points for hosts that cannot name ccl:: types (ctypes harness) ---- */
@@ -815,6 +831,18 @@ int b200_host_device_stats(void *handle, b200_stats *out)
     return B200_ERR_INVALID;
   b200_host_device *h = (b200_host_device *)handle;
   *out = h->device ? h->device->last_stats : h->multi->last_stats;
+  return B200_OK;
+}
+
+/* For a ccl::Device* that came out of the reference's own registry (Device::create with
+ * the "B200" type): the last task's counters if it is one of ours, B200_ERR_INVALID if
+ * the registry handed out something else. */
+int b200_registered_device_stats(void *device_ptr, b200_stats *out)
+{
+  ccl::B200Device *dev = dynamic_cast<ccl::B200Device *>((ccl::Device *)device_ptr);
+  if (!dev || !out)
+    return B200_ERR_INVALID;
+  *out = dev->last_stats;
   return B200_OK;
 }
 

@@ -481,6 +481,73 @@ class B200Device:
 SHIM_PATH = os.path.join(_HERE, "libcycles_device_b200.so")
 
 
+class RegisteredDevice:
+    """A ccl::Device made by the REFERENCE's own registry - `Device::type_from_string`,
+    `Device::available_devices`, `Device::create` (device/device.cpp:367-550) - the way
+    `cycles --device B200` or Blender's preferences would make it, once the registration
+    patch of INTEGRATION.md section 2 is in.  `count` > 1 asks for
+    `Device::get_multi_device` of the first `count` devices of the type (the reference's
+    MultiDevice over B200 sub-devices).  `.ptr` is the ccl::Device*."""
+
+    def __init__(self, type_name="B200", index=0, count=1):
+        load_library()
+        if not os.path.exists(SHIM_PATH):
+            raise DeviceError("%s is missing" % SHIM_PATH)
+        S = C.CDLL(SHIM_PATH, mode=C.RTLD_GLOBAL)  # loading it registers the device type
+        S.ref_host_device_type_from_string.argtypes = [C.c_char_p]
+        S.ref_host_device_type_name.argtypes = [C.c_int, C.c_char_p, C.c_int]
+        S.ref_host_device_type_available.argtypes = [C.c_int]
+        S.ref_host_available_devices.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_int,
+                                                 C.c_char_p, C.c_int]
+        S.ref_host_device_create.restype = C.c_void_p
+        S.ref_host_device_create.argtypes = [C.c_int, C.c_int, C.c_int]
+        S.ref_host_device_free.argtypes = [C.c_void_p]
+        S.b200_registered_device_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        self._S = S
+        self.type = S.ref_host_device_type_from_string(type_name.encode())
+        if self.type == 0:
+            raise DeviceError("the reference's device registry does not know %r" % type_name)
+        self._ptr = None
+        if count > 0:
+            self._ptr = S.ref_host_device_create(self.type, int(index), int(count))
+            if not self._ptr:
+                raise DeviceError("Device::create(%s #%d) returned NULL" % (type_name, index))
+
+    def type_name(self):
+        buf = C.create_string_buffer(64)
+        self._S.ref_host_device_type_name(self.type, buf, len(buf))
+        return buf.value.decode()
+
+    def type_available(self):
+        """Device::available_types() lists the type."""
+        return bool(self._S.ref_host_device_type_available(self.type))
+
+    def available(self):
+        """[(id, description)] of Device::available_devices(mask of the type)."""
+        out = []
+        n = self._S.ref_host_available_devices(self.type, -1, None, 0, None, 0)
+        for i in range(n):
+            a, b = C.create_string_buffer(256), C.create_string_buffer(256)
+            self._S.ref_host_available_devices(self.type, i, a, len(a), b, len(b))
+            out.append((a.value.decode(), b.value.decode()))
+        return out
+
+    @property
+    def ptr(self):
+        return self._ptr
+
+    def stats(self):
+        s = Stats()
+        if self._S.b200_registered_device_stats(self._ptr, C.byref(s)) != 0:
+            raise DeviceError("the registry's device is not a B200Device")
+        return s.as_dict()
+
+    def close(self):
+        if getattr(self, "_ptr", None):
+            self._S.ref_host_device_free(self._ptr)
+            self._ptr = None
+
+
 class B200HostDevice:
     """The C++ `B200Device : ccl::Device` (csrc/device_b200.cpp) as a handle whose
     `.ptr` is a ccl::Device* that a reference Scene / DeviceTask can drive - the real

@@ -124,3 +124,24 @@ def test_bvh8_pack_refuses_what_the_device_cannot_traverse():
     from raytracingproject_b200 import device as D
     with pytest.raises(D.DeviceError, match="BVH2"):
         D.pack_bvh8({"__data": (np.zeros(4096, np.uint8), 1)})
+
+
+def test_reference_registry_knows_the_device_type():
+    """The registration patch applied to the host library's copy
+    of device/device.cpp: "B200" is a DeviceType of the reference's registry, named both
+    ways; without a GPU the plug-in reports no devices and Device::create gives NULL
+    instead of another backend."""
+    import os
+    from raytracingproject_b200 import device as D
+    if not os.path.exists(D.SHIM_PATH):
+        pytest.skip("libcycles_device_b200.so not built (needs /root/reference)")
+    reg = D.RegisteredDevice("B200", count=0)
+    assert reg.type == 7 and reg.type_name() == "B200"       # DEVICE_OPTIX + 1
+    assert D.RegisteredDevice("CPU", count=0).type == 1
+    with pytest.raises(D.DeviceError):
+        D.RegisteredDevice("B300", count=0)
+    import torch
+    if not torch.cuda.is_available():
+        assert not reg.type_available() and reg.available() == []
+        with pytest.raises(D.DeviceError):
+            D.RegisteredDevice("B200", index=0)

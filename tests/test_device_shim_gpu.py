@@ -67,6 +67,38 @@ def test_reference_scene_drives_b200_device(ref, device, name):
         del os.environ["B200_HOST_BVH"]
 
 
+def test_device_comes_out_of_the_reference_registry(ref, device):
+    """`cycles --device B200`, as far as it can be driven here: the reference's own
+    Device::type_from_string / available_types / available_devices / Device::create
+    (device/device.cpp:367-550, with the "B200" rows of the registration patch -
+    oracle/device_registry_hook.sed) hand out the B200Device; a reference Scene rendered on
+    it gives the film of the Python mirror."""
+    from raytracingproject_b200.device import RegisteredDevice
+    desc = small_cases()["cornell"]
+    spp = 8
+    cpu = ref.build_scene(desc)
+    device.upload_scene(cpu.device_arrays())
+    py_img = device.render(desc.width, desc.height, cpu.pass_stride, 0, spp).copy()
+    cpu.close()
+
+    reg = RegisteredDevice("B200", index=0)
+    try:
+        assert reg.type_name() == "B200" and reg.type_available()
+        listed = reg.available()
+        print("Device::available_devices(DEVICE_MASK_B200):", listed)
+        assert listed and listed[0][0].startswith("B200_") and "B200" in listed[0][1]
+        rs = ref.build_scene(desc, external_device=reg.ptr)
+        try:
+            img, _ = rs.render(0, spp, tile_size=64)
+            st = reg.stats()
+            assert st["kernel_launches"] > 0 and st["primary_rays"] > 0
+            assert np.array_equal(img, py_img)
+        finally:
+            rs.close()
+    finally:
+        reg.close()
+
+
 def test_multi_device_in_one_process(ref):
     """B200MultiDevice: the reference Scene + DeviceTask drive several contexts through
     ONE ccl::Device; every GPU renders its share of the samples, the films are summed on
