@@ -14,6 +14,17 @@ Device *b200_plugin_create(DeviceInfo &info, Stats &stats, Profiler &profiler, b
 void b200_plugin_info(vector<DeviceInfo> &devices);\
 static vector<DeviceInfo> b200_devices;
 
+/^    return device_multi_create(info, stats, profiler, background);$/i\
+    /* a B200-only list is ONE device that splits samples and sums films on the GPUs */\
+    {\
+      bool all_b200 = true;\
+      foreach (const DeviceInfo &sub, info.multi_devices)\
+        all_b200 &= (sub.type == DEVICE_B200);\
+      if (all_b200) {\
+        return b200_plugin_init() ? b200_plugin_create(info, stats, profiler, background) : NULL;\
+      }\
+    }
+
 /^    default:$/i\
     case DEVICE_B200:\
       if (b200_plugin_init())\

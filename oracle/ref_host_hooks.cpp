@@ -169,8 +169,8 @@ extern "C" int ref_host_available_devices(int type, int index, char *id, int id_
 }
 
 /* Device::create for device `index` of `type` - or, with count > 1, for the multi device
- * Device::get_multi_device makes of the first `count` of them (device.cpp:583-655); NULL
- * when there is none.  The Stats / Profiler the device reports into live as long as the
+ * Device::get_multi_device makes of `count` of them (device.cpp:583-655; the list wraps
+ * around when the box has fewer); NULL when there is none.  The Stats / Profiler the device reports into live as long as the
  * process (a Session owns them in the reference). */
 extern "C" void *ref_host_device_create(int type, int index, int count)
 {
@@ -180,9 +180,10 @@ extern "C" void *ref_host_device_create(int type, int index, int count)
   if (index < 0 || index >= (int)devices.size())
     return NULL;
   if (count > 1) {
-    if (index + count > (int)devices.size())
-      return NULL;
-    ccl::vector<ccl::DeviceInfo> sub(devices.begin() + index, devices.begin() + index + count);
+    /* fewer GPUs than asked for: the list wraps around (several contexts on one GPU) */
+    ccl::vector<ccl::DeviceInfo> sub;
+    for (int k = 0; k < count; k++)
+      sub.push_back(devices[(index + k) % devices.size()]);
     ccl::DeviceInfo multi = ccl::Device::get_multi_device(sub, 0, true);
     return ccl::Device::create(multi, stats, profiler, true);
   }

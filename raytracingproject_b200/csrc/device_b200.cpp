@@ -662,6 +662,14 @@ bool device_b200_init()
 
 Device *device_b200_create(DeviceInfo &info, Stats &stats, Profiler &profiler, bool background)
 {
+  /* Device::get_multi_device of a B200-only list (device.cpp:583-655): one device over
+   * the sub-devices' GPUs instead of the generic MultiDevice's tile fan-out */
+  if (!info.multi_devices.empty()) {
+    vector<int> ordinals;
+    foreach (const DeviceInfo &sub, info.multi_devices)
+      ordinals.push_back(sub.num);
+    return new B200MultiDevice(info, stats, profiler, background, ordinals);
+  }
   return new B200Device(info, stats, profiler, background);
 }
 
@@ -840,9 +848,10 @@ int b200_host_device_stats(void *handle, b200_stats *out)
 int b200_registered_device_stats(void *device_ptr, b200_stats *out)
 {
   ccl::B200Device *dev = dynamic_cast<ccl::B200Device *>((ccl::Device *)device_ptr);
-  if (!dev || !out)
+  ccl::B200MultiDevice *multi = dynamic_cast<ccl::B200MultiDevice *>((ccl::Device *)device_ptr);
+  if ((!dev && !multi) || !out)
     return B200_ERR_INVALID;
-  *out = dev->last_stats;
+  *out = dev ? dev->last_stats : multi->last_stats;
   return B200_OK;
 }
 

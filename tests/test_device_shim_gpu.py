@@ -99,6 +99,34 @@ def test_device_comes_out_of_the_reference_registry(ref, device):
         reg.close()
 
 
+def test_registry_makes_one_device_of_a_b200_list(ref, device):
+    """Device::get_multi_device of a B200-only list + Device::create (device.cpp:367-375,
+    583-655, patched rows): not the generic MultiDevice (tiles fanned out, films sliced
+    through the host) but ONE B200MultiDevice - samples split over the GPUs, films summed
+    on the device.  Two GPUs when the box has them, else two contexts on one."""
+    from raytracingproject_b200.device import RegisteredDevice
+    desc = small_cases()["cornell"]
+    spp = 8
+    cpu = ref.build_scene(desc)
+    device.upload_scene(cpu.device_arrays())
+    py_img = device.render(desc.width, desc.height, cpu.pass_stride, 0, spp).copy()
+    cpu.close()
+    reg = RegisteredDevice("B200", index=0, count=2)
+    try:
+        rs = ref.build_scene(desc, external_device=reg.ptr)
+        try:
+            img, _ = rs.render(0, spp, tile_size=0)
+            st = reg.stats()           # only a B200MultiDevice / B200Device answers
+            assert st["primary_rays"] == desc.width * desc.height * spp
+            # two partial films summed: equal up to the order of the float additions
+            a, b = img[..., :4] / spp, py_img[..., :4] / spp
+            assert np.abs(a - b).max() <= 1e-5 * max(1.0, np.abs(b).max())
+        finally:
+            rs.close()
+    finally:
+        reg.close()
+
+
 def test_multi_device_in_one_process(ref):
     """B200MultiDevice: the reference Scene + DeviceTask drive several contexts through
     ONE ccl::Device; every GPU renders its share of the samples, the films are summed on
