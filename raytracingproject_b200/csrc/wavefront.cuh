@@ -32,6 +32,9 @@
 #define SH_INDIRECT_FLAG 0x40000000
 /* float4 records per shadow-queue entry in PathSoA::sh_pass (render passes only) */
 #define SH_PASS_QUADS 3
+/* transparent shadows: up to this many stepping rounds are queued per iteration without
+ * reading the queue length back (wavefront loop) */
+#define WF_TS_BLIND_ROUNDS 16
 
 #define WF_MAX_KEYS 4096
 #ifndef WF_BLOCK
@@ -2644,8 +2647,14 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
    * host queues iteration `it`, and only then looks at the counters iteration it - 1
    * copied into its ring slot.  The price is one iteration over empty queues per batch
    * (8 launches that find nothing to do); the device never idles.  Transparent shadows
-   * size their stepping loop from a counter inside the iteration and stay in step. */
-  const int lag = (transparent_shadows || ctx->opt_sync_iterations) ? 0 : 1;
+   * queue a fixed number of stepping rounds (see ts_rounds) and are pipelined the same
+   * way. */
+  /* transparent shadows: rounds of the stepping loop queued per iteration without a
+   * counter read (0 = the host asks after every step) */
+  const int ts_max_bounce = kd_host<int>(ctx, KD_INT_TRANSPARENT_MAX_BOUNCE);
+  const int ts_rounds = (transparent_shadows && !ctx->opt_sync_iterations &&
+                         ts_max_bounce <= WF_TS_BLIND_ROUNDS) ? std::max(ts_max_bounce, 1) : 0;
+  const int lag = ((transparent_shadows && ts_rounds == 0) || ctx->opt_sync_iterations) ? 0 : 1;
   int batch_slot = 0;
   auto sum_batch_stats = [&]() -> int {
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
@@ -2733,8 +2742,28 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
     else
       k_intersect_shadow<false, false><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
     CUDA_TRY(ctx, cudaEventRecord(ev[3], st));
-    if (transparent_shadows) {
-      /* shadow rays stopped by a transparent surface walk on, one surface per step */
+    if (transparent_shadows && ts_rounds > 0) {
+      /* shadow rays stopped by a transparent surface walk on, one surface per step.  A ray
+       * crosses at most transparent_max_bounce surfaces, so that many rounds are queued
+       * without asking how many rays are left: a round over an empty queue is three launches
+       * that return at once, and the host stays out of the loop. */
+      int cur = 0;
+      for (int round = 0; round < ts_rounds; round++) {
+        k_intersect_shadow_step<<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, cur, refill);
+        if (passes)
+          k_shade_shadow_step<true, true><<<grid_wide, WF_BLOCK, 0, st>>>(soa, cur);
+        else if (svm_ext)
+          k_shade_shadow_step<true><<<grid_wide, WF_BLOCK, 0, st>>>(soa, cur);
+        else
+          k_shade_shadow_step<false><<<grid_wide, WF_BLOCK, 0, st>>>(soa, cur);
+        k_shadow_step_end<<<1, 1, 0, st>>>(soa, cur);
+        stats.kernel_launches += 3;
+        cur ^= 1;
+      }
+      CUDA_TRY(ctx, cudaGetLastError());
+    }
+    else if (transparent_shadows) {
+      /* more surfaces allowed than is worth queueing blind: ask after every step */
       CUDA_TRY(ctx, cudaMemcpyAsync(pool->h_counters, soa.counters, 64, cudaMemcpyDeviceToHost,
                                     st));
       CUDA_TRY(ctx, cudaStreamSynchronize(st));
