@@ -2490,6 +2490,12 @@ static int check_scope(b200_ctx *ctx)
     why = "background importance sampling needs the world map CDF arrays";
   else if (I(KD_FILM_CRYPTOMATTE_PASSES))
     why = "cryptomatte passes are outside the hot-path scope";
+  else if (I(KD_FILM_PASS_DENOISING_DATA) &&
+           (I(KD_FILM_PASS_DENOISING_DATA) + CY_DENOISING_PASS_SIZE_BASE > I(KD_FILM_PASS_STRIDE) ||
+            (I(KD_FILM_PASS_DENOISING_CLEAN) &&
+             I(KD_FILM_PASS_DENOISING_CLEAN) + CY_DENOISING_PASS_SIZE_CLEAN >
+                 I(KD_FILM_PASS_STRIDE))))
+    why = "the denoising data passes do not fit the film's pass stride";
   else if (I(KD_FILM_PASS_DENOISING_CLEAN) &&
            (!I(KD_FILM_PASS_DENOISING_DATA) || !I(KD_FILM_USE_LIGHT_PASS)))
     why = "the denoising clean pass needs the denoising data passes and light passes";

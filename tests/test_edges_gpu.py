@@ -77,7 +77,9 @@ def test_empty_work_leaves_the_film_alone(ref, device):
     ("KD_INT_USE_VOLUMES", 1, "volumes"),
     ("KD_INT_BRANCHED", 1, "branched"),
     ("KD_BVH_HAVE_CURVES", 1, "curves"),
-    ("KD_FILM_PASS_DENOISING_DATA", 4, "denoising data"),
+    ("KD_FILM_PASS_DENOISING_DATA", 4, "denoising data passes do not fit"),
+    ("KD_FILM_PASS_DENOISING_CLEAN", 4, "clean pass needs"),
+    ("KD_FILM_CRYPTOMATTE_PASSES", 1, "cryptomatte"),
     ("KD_BG_NUM_PORTALS", 1, "portals"),
     ("KD_INT_MAX_CLOSURES", 33, "closures per shader"),
 ])
