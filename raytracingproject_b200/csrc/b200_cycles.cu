@@ -462,10 +462,8 @@ int b200_bind_global(b200_ctx *ctx, const char *name, uint64_t dptr, const void 
   }
   if (strcmp(name, "__svm_nodes") == 0) {
     ctx->force_svm_ext = false;
-    ctx->shade_dense_choice = -1; /* new shader mix: probe the register budget again */
-    ctx->shade_probe_batches = 0;
-    ctx->shade_probe_ms[0] = ctx->shade_probe_ms[1] = 0.0;
-    ctx->shade_probe_paths[0] = ctx->shade_probe_paths[1] = 0.0;
+    /* new shader mix: probe the register budgets again */
+    ctx->shade_probe[0] = ctx->shade_probe[1] = b200_ctx::ShadeProbe();
     if (!bytes)
       ctx->svm_features = 0;
   }
@@ -1075,10 +1073,7 @@ int b200_set_option(b200_ctx *ctx, const char *name, int64_t value)
     ctx->opt_l2_persist_nodes = value;
   else if (strcmp(name, "shade_dense") == 0) {
     ctx->opt_shade_dense = value;
-    ctx->shade_dense_choice = -1;
-    ctx->shade_probe_batches = 0;
-    ctx->shade_probe_ms[0] = ctx->shade_probe_ms[1] = 0.0;
-    ctx->shade_probe_paths[0] = ctx->shade_probe_paths[1] = 0.0;
+    ctx->shade_probe[0] = ctx->shade_probe[1] = b200_ctx::ShadeProbe();
   }
   else if (strcmp(name, "shade_carveout") == 0) {
     ctx->opt_shade_carveout = value;

@@ -90,16 +90,19 @@ struct b200_ctx {
 
   /* k_shade_surface<lean / lean + multi-scatter / full / full + render passes>: grid size
    * per SM */
-  int shade_blocks_per_sm[5] = {0, 0, 0, 0, 0};
-  /* The lean multiscatter shading kernel exists at two register budgets (wavefront.cuh,
-   * SHADE_DENSE_BLOCKS).  Which one is faster depends on the shader mix of the scene, so
-   * the first batches of a scene alternate between them and the faster one is kept until
-   * the SVM programs change.  choice: -1 probing, 0 / 1 decided. */
+  int shade_blocks_per_sm[6] = {0, 0, 0, 0, 0, 0};
+  /* The lean multiscatter and the full shading kernels exist at two register budgets
+   * (wavefront.cuh, SHADE_DENSE_BLOCKS).  Which one is faster depends on the shader mix of
+   * the scene, so the first batches of a scene alternate between them and the faster one
+   * is kept until the SVM programs change.  One probe per kernel kind (0 = lean
+   * multiscatter, 1 = full).  choice: -1 probing, 0 / 1 decided. */
   int64_t opt_shade_dense = -1; /* -1 probe, 0 / 1 forced */
-  int shade_dense_choice = -1;
-  double shade_probe_ms[2] = {0.0, 0.0};
-  double shade_probe_paths[2] = {0.0, 0.0};
-  uint64_t shade_probe_batches = 0;
+  struct ShadeProbe {
+    int choice = -1;
+    double ms[2] = {0.0, 0.0};
+    double paths[2] = {0.0, 0.0};
+    uint64_t batches = 0;
+  } shade_probe[2];
 
   /* host cancel predicate (task.get_cancel()), polled between wavefront batches */
   b200_cancel_fn cancel_fn = nullptr;

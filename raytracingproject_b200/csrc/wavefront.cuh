@@ -795,8 +795,9 @@ __global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(Pa
 /* DENSE: the same code under a tighter register budget - 3 blocks per SM (80 registers,
  * some spills) instead of 2 (128 registers).  Measured on B200 (profiles/r02r_*): a scene
  * where every hit runs the multiscatter random walk gains 20 % from the extra warps, one
- * where most hits are plain diffuse loses 14 % to the spills; the host times both on the
- * first batches of a scene and keeps the faster (b200_render, "shade_dense"). */
+ * where most hits are plain diffuse loses 14 % to the spills - the lean multiscatter
+ * kernel and the full kernel alike; the host times both on the first batches of a scene
+ * and keeps the faster (b200_render, "shade_dense"). */
 #ifndef SHADE_DENSE_BLOCKS
 #  define SHADE_DENSE_BLOCKS 3
 #endif
@@ -2546,12 +2547,13 @@ static int shade_kernel_setup(b200_ctx *ctx)
   if (ctx->shade_blocks_per_sm[0] > 0)
     return B200_OK;
   DeviceGuard guard(ctx->ordinal);
-  const void *kernels[5] = {(const void *)k_shade_surface<false, false>,
+  const void *kernels[6] = {(const void *)k_shade_surface<false, false>,
                             (const void *)k_shade_surface<false, true>,
                             (const void *)k_shade_surface<true, true>,
                             (const void *)k_shade_surface<true, true, true>,
-                            (const void *)k_shade_surface<false, true, false, true>};
-  for (int k = 0; k < 5; k++) {
+                            (const void *)k_shade_surface<false, true, false, true>,
+                            (const void *)k_shade_surface<true, true, false, true>};
+  for (int k = 0; k < 6; k++) {
     const size_t smem = (k == 3) ? SHADE_SMEM_BYTES_PASSES : SHADE_SMEM_BYTES;
     CUDA_TRY(ctx, cudaFuncSetAttribute(kernels[k], cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
@@ -2684,12 +2686,13 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
   /* one bounce of the whole batch: 8 launches, the head of the counters into the
    * iteration's ring slot, events around the three phases */
   /* which register budget of the lean multiscatter kernel this batch runs (see
-   * k_shade_surface, DENSE): forced, decided, or - while probing - alternating by batch */
+   * and of the full kernel (see k_shade_surface, DENSE): forced, decided, or - while
+   * probing - alternating by batch */
   bool shade_dense = false;
   auto enqueue_iteration = [&](const PathSoA &soa, int it) -> int {
     cudaEvent_t *ev = pool->ring_ev[it % WF_RING];
     const int grid_shade = ctx->num_sms *
-                           ctx->shade_blocks_per_sm[svm_ext ? 2 :
+                           ctx->shade_blocks_per_sm[svm_ext ? (shade_dense ? 5 : 2) :
                                                     (multiscatter ? (shade_dense ? 4 : 1) : 0)];
     CUDA_TRY(ctx, cudaEventRecord(ev[0], st));
     if (count)
@@ -2715,7 +2718,12 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
     }
     else if (svm_ext) {
       k_shade_background<true><<<grid_wide, WF_BLOCK, 0, st>>>(soa);
-      k_shade_surface<true, true><<<grid_shade, WF_BLOCK, SHADE_SMEM_BYTES, st>>>(soa, num_keys);
+      if (shade_dense)
+        k_shade_surface<true, true, false, true>
+            <<<grid_shade, WF_BLOCK, SHADE_SMEM_BYTES, st>>>(soa, num_keys);
+      else
+        k_shade_surface<true, true><<<grid_shade, WF_BLOCK, SHADE_SMEM_BYTES, st>>>(soa,
+                                                                                    num_keys);
     }
     else {
       k_shade_background<false><<<grid_wide, WF_BLOCK, 0, st>>>(soa);
@@ -2876,14 +2884,21 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
       bp.pass_stride = pass_stride;
       bp.adaptive_aux = adaptive_aux;
 
-      const bool probing = multiscatter && ctx->opt_shade_dense < 0 &&
-                           ctx->shade_dense_choice < 0;
-      if (ctx->opt_shade_dense >= 0)
-        shade_dense = ctx->opt_shade_dense != 0;
-      else if (ctx->shade_dense_choice >= 0)
-        shade_dense = ctx->shade_dense_choice != 0;
-      else
-        shade_dense = (ctx->shade_probe_batches++ & 1) != 0;
+      /* kernels with a dense variant: the lean multiscatter one and the full one (not the
+       * lean GGX kernel - the cap lost on every scene measured - nor the passes kernel) */
+      auto probe_kind = [&]() { return passes ? -1 : (svm_ext ? 1 : (multiscatter ? 0 : -1)); };
+      auto pick_budget = [&]() {
+        const int kind = probe_kind();
+        if (kind < 0)
+          shade_dense = false;
+        else if (ctx->opt_shade_dense >= 0)
+          shade_dense = ctx->opt_shade_dense != 0;
+        else if (ctx->shade_probe[kind].choice >= 0)
+          shade_dense = ctx->shade_probe[kind].choice != 0;
+        else
+          shade_dense = (ctx->shade_probe[kind].batches++ & 1) != 0;
+      };
+      pick_budget();
       const float shade_ms_before = shade_ms;
       for (int attempt = 0;; attempt++) {
         PathSoA soa = pool->soa;
@@ -2955,6 +2970,7 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
             return fail(ctx, B200_ERR_UNSUPPORTED, "SVM scope miss in the full kernels");
           svm_ext = true;
           ctx->force_svm_ext = true;
+          pick_budget();
           continue;
         }
         if (adaptive)
@@ -2973,21 +2989,21 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
                                       st));
         CUDA_TRY(ctx, cudaGetLastError());
         stats.batches += 1;
-        if (probing && !svm_ext) {
+        if (probe_kind() >= 0 && ctx->opt_shade_dense < 0 &&
+            ctx->shade_probe[probe_kind()].choice < 0 && attempt == 0) {
           /* every iteration with work has been harvested when the bounce loop ends: the
            * batch's shading time is complete.  Decide once both budgets have shaded 4 Mi
            * paths; until then (small tiles) keep alternating. */
+          b200_ctx::ShadeProbe &pr = ctx->shade_probe[probe_kind()];
           const int v = shade_dense ? 1 : 0;
           /* the first batch of each budget pays for loading its kernel: not counted */
-          if (ctx->shade_probe_batches > 2) {
-            ctx->shade_probe_ms[v] += (double)(shade_ms - shade_ms_before);
-            ctx->shade_probe_paths[v] += (double)npix * bp.nsamples;
+          if (pr.batches > 2) {
+            pr.ms[v] += (double)(shade_ms - shade_ms_before);
+            pr.paths[v] += (double)npix * bp.nsamples;
           }
           const double enough = (double)(1 << 22);
-          if (ctx->shade_probe_paths[0] >= enough && ctx->shade_probe_paths[1] >= enough)
-            ctx->shade_dense_choice =
-                (ctx->shade_probe_ms[1] / ctx->shade_probe_paths[1] <
-                 ctx->shade_probe_ms[0] / ctx->shade_probe_paths[0]) ? 1 : 0;
+          if (pr.paths[0] >= enough && pr.paths[1] >= enough)
+            pr.choice = (pr.ms[1] / pr.paths[1] < pr.ms[0] / pr.paths[0]) ? 1 : 0;
         }
         if (++batch_slot == WF_BATCH_SLOTS) {
           rc = sum_batch_stats();
@@ -3040,10 +3056,12 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
     stats.shadow_ms = shadow_ms;
   }
   stats.svm_extended = svm_ext ? 1 : 0;
-  stats.shade_dense = (multiscatter && !svm_ext) ?
-                          (ctx->opt_shade_dense >= 0 ? (ctx->opt_shade_dense != 0) :
-                                                       ctx->shade_dense_choice) :
-                          0;
+  {
+    const int kind = passes ? -1 : (svm_ext ? 1 : (multiscatter ? 0 : -1));
+    stats.shade_dense = kind < 0 ? 0 :
+                        (ctx->opt_shade_dense >= 0 ? (ctx->opt_shade_dense != 0) :
+                                                     ctx->shade_probe[kind].choice);
+  }
   ctx->stats = stats;
   return B200_OK;
 }

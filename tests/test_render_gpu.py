@@ -628,3 +628,23 @@ def test_shading_register_budgets_render_the_same_film(ref, device, name):
         device.set_option("shade_dense", -1)
         device.set_option("batch_paths", 0)
         rs.close()
+
+
+def test_full_kernel_register_budgets_render_the_same_film(ref, device):
+    """The same for the full shading kernel (world AO routes the scene there)."""
+    desc = ao_cases()["cornell_ao_principled"]
+    rs = ref.build_scene(desc)
+    try:
+        device.upload_scene(rs.device_arrays())
+        films = {}
+        for mode in (0, 1):
+            device.set_option("shade_dense", mode)
+            films[mode] = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP)
+            st = device.stats()
+            assert st["svm_extended"] == 1 and st["shade_dense"] == mode
+        # the AO and the light ray of a path are added with atomics, in either order
+        a, b = films[0][..., :3] / SPP, films[1][..., :3] / SPP
+        assert np.abs(a - b).max() <= 1e-5 * max(1.0, np.abs(a).max())
+    finally:
+        device.set_option("shade_dense", -1)
+        rs.close()
