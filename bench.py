@@ -274,9 +274,9 @@ def control_of(agg, steps):
         "launches_per_step": agg["kernel_launches"] / steps,
         "stream_syncs_per_step": agg["host_syncs"] / steps,
         "lagged_counter_reads_per_step": agg["host_waits"] / steps,
-        # register budget of the lean multiscatter shading kernel the device settled on for
-        # this scene (-1 still probing, 0 = 128 registers, 1 = 80 registers / 3 blocks per SM)
-        "shade_dense": agg.get("shade_dense", 0),
+        # block shape of the lean multiscatter / full shading kernel the device settled on for
+        # this scene (-1 still probing, 0 = two blocks of 256 threads per SM, 1 = one of 512)
+        "shade_wide": agg.get("shade_wide", 0),
         "share": {"intersect_closest": agg["closest_ms"] / dev_ms,
                   "sort_and_shade": agg["shade_ms"] / dev_ms,
                   "intersect_shadow": agg["shadow_ms"] / dev_ms,
@@ -349,7 +349,7 @@ def timed_steps(arm, reducer, stream, steps, warmup, start_sample, my_spp, rank,
         st = step()
         for k in agg:
             agg[k] += st[k]
-    agg["shade_dense"] = st.get("shade_dense", 0)  # the last step's (decided in the warm-up)
+    agg["shade_wide"] = st.get("shade_wide", 0)  # the last step's (decided in the warm-up)
     reducer.finish()
     ev1.record(stream)
     torch.cuda.synchronize()

@@ -87,8 +87,9 @@ typedef struct b200_stats {
   uint64_t host_syncs;       /* stream synchronisations: the device drains, then waits for
                               * the host (one per call; one per step of a transparent shadow) */
   uint64_t host_waits;       /* waits on an iteration's counters while later work is queued */
-  int64_t shade_dense;       /* register budget of the lean multiscatter / full shading kernel after
-                                this call: -1 still probing, 0 = 2 blocks/SM, 1 = 3 blocks/SM */
+  int64_t shade_wide;        /* block shape of the lean multiscatter / full shading kernel after
+                                this call: -1 still probing, 0 = two blocks of 256 threads per
+                                SM, 1 = one block of 512 */
 } b200_stats;
 
 /* BVH8 build report (host builder). */
@@ -279,9 +280,9 @@ int b200_set_stream(b200_ctx *ctx, uint64_t cuda_stream);
 
 /* Tunables (0 keeps the default): "batch_paths" paths per wavefront batch,
  * "count_traversal" 1 = count BVH nodes / triangles per ray (slower),
- * "shade_dense" register budget of the lean multiscatter / the full shading kernel: -1 (default) =
- * time both on the first batches of a scene and keep the faster, 0 = 2 blocks per SM,
- * 1 = 3 blocks per SM (same arithmetic, same film either way). */
+ * "shade_wide" block shape of the lean multiscatter / the full shading kernel: -1 (default) =
+ * time both on the first batches of a scene and keep the faster, 0 = two blocks of 256
+ * threads per SM, 1 = one block of 512 (same arithmetic, same film either way). */
 int b200_set_option(b200_ctx *ctx, const char *name, int64_t value);
 
 #ifdef __cplusplus

@@ -462,7 +462,7 @@ int b200_bind_global(b200_ctx *ctx, const char *name, uint64_t dptr, const void 
   }
   if (strcmp(name, "__svm_nodes") == 0) {
     ctx->force_svm_ext = false;
-    /* new shader mix: probe the register budgets again */
+    /* new shader mix: probe the block shapes of the shading kernels again */
     ctx->shade_probe[0] = ctx->shade_probe[1] = b200_ctx::ShadeProbe();
     if (!bytes)
       ctx->svm_features = 0;
@@ -1071,8 +1071,8 @@ int b200_set_option(b200_ctx *ctx, const char *name, int64_t value)
     ctx->opt_sort_tiles = value;
   else if (strcmp(name, "l2_persist_nodes") == 0)
     ctx->opt_l2_persist_nodes = value;
-  else if (strcmp(name, "shade_dense") == 0) {
-    ctx->opt_shade_dense = value;
+  else if (strcmp(name, "shade_wide") == 0) {
+    ctx->opt_shade_wide = value;
     ctx->shade_probe[0] = ctx->shade_probe[1] = b200_ctx::ShadeProbe();
   }
   else if (strcmp(name, "shade_carveout") == 0) {

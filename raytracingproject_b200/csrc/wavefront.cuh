@@ -172,13 +172,14 @@ CY_DEV unsigned int warp_append(unsigned int *counter, bool pred)
 /* One atomic per BLOCK for up to two queues at once: the queue counters are single
  * addresses, and same-address atomics with a return value serialise in L2 at about
  * 2 ns each - per warp that was the whole cost of init_from_camera and a third of
- * shade_surface.  Must be reached by every thread of the block (WF_BLOCK threads).
+ * shade_surface.  Must be reached by every thread of the block (32 NW threads).
  * Lanes get consecutive slots in thread order, so what a block appends stays in the
  * (sorted, spatially coherent) order it was read in. */
+template<int NW = WF_BLOCK / 32>
 CY_DEV void block_append2(unsigned int *counter_a, bool pred_a, unsigned int *counter_b,
                           bool pred_b, unsigned int *slot_a, unsigned int *slot_b)
 {
-  constexpr int NW = WF_BLOCK / 32;
+  static_assert(NW <= 16, "the two scans share one warp: at most 16 warps per block");
   __shared__ unsigned int s_tab[2][NW];
   const unsigned int lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
   const unsigned int lt_mask = (1u << lane) - 1u;
@@ -778,7 +779,8 @@ __global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(Pa
  *   [SHADE_STAGE_WORDS][WF_BLOCK] floats   the staged shadow-ray record of each thread,
  * a column per thread: a warp touches one 128-byte row per word, no conflicts. */
 #define SHADE_STAGE_WORDS 12
-#define SHADE_SMEM_BYTES (SHADE_STAGE_WORDS * WF_BLOCK * sizeof(float))
+#define SHADE_SMEM_BYTES_OF(block) (SHADE_STAGE_WORDS * (block) * sizeof(float))
+#define SHADE_SMEM_BYTES SHADE_SMEM_BYTES_OF(WF_BLOCK)
 /* with render passes the record carries three more colours and two flags */
 #define SHADE_STAGE_WORDS_PASSES 24
 #define SHADE_SMEM_BYTES_PASSES (SHADE_STAGE_WORDS_PASSES * WF_BLOCK * sizeof(float))
@@ -792,20 +794,24 @@ __global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(Pa
  * that follows does not carry them in registers; slots in the next-bounce and shadow
  * queues come from one block-wide reservation at the end of the round, after which the
  * staged record is copied out to its slot. */
-/* DENSE: the same code under a tighter register budget - 3 blocks per SM (80 registers,
- * some spills) instead of 2 (128 registers).  Measured on B200 (profiles/r02r_*): a scene
- * where every hit runs the multiscatter random walk gains 20 % from the extra warps, one
- * where most hits are plain diffuse loses 14 % to the spills - the lean multiscatter
- * kernel and the full kernel alike; the host times both on the first batches of a scene
- * and keeps the faster (b200_render, "shade_dense"). */
-#ifndef SHADE_DENSE_BLOCKS
-#  define SHADE_DENSE_BLOCKS 3
-#endif
-template<bool EXT, bool MS = EXT, bool PASSES = false, bool DENSE = false>
-__global__ void __launch_bounds__(WF_BLOCK, DENSE ? SHADE_DENSE_BLOCKS :
-                                                   (EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_MIN_BLOCKS))
+/* WIDE: the same code as ONE block of 512 threads per SM instead of two of 256 (128
+ * registers either way).  Measured on B200 (profiles/r02r_shade_budget_ab.txt,
+ * r02s_block_size_ab.txt): where every hit runs the multiscatter random walk the kernel
+ * is bound by instruction fetch (684 KB - 1.1 MB of SASS against a 32 KB instruction
+ * cache per SM; no_instruction stalls 10 per issue) - the block-wide barrier of the queue
+ * append keeps the 16 warps of one block in the same stretch of code, two blocks run out
+ * of phase and fetch twice: +28 % (lean) / +40 % (full) on the startup scene.  Where most
+ * hits are plain diffuse the wider barrier costs 0-3 %.  The host times both on the first
+ * batches of a scene and keeps the faster (b200_render, "shade_wide").  A tighter register
+ * budget instead (3 blocks of 256 at 80 registers) gains as much on the startup scene on
+ * a good run, but with a large run-to-run spread, and loses 14-25 % on the Cornell box. */
+#define SHADE_WIDE_BLOCK 512
+template<bool EXT, bool MS = EXT, bool PASSES = false, bool WIDE = false>
+__global__ void __launch_bounds__(WIDE ? SHADE_WIDE_BLOCK : WF_BLOCK,
+                                  WIDE ? 1 : (EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_MIN_BLOCKS))
     k_shade_surface(PathSoA p, int num_keys)
 {
+  constexpr int BLOCK = WIDE ? SHADE_WIDE_BLOCK : WF_BLOCK;
   extern __shared__ float s_shade[];
   float *const stage = s_shade + threadIdx.x;
   float4 arena_words[ARENA_QUADS];
@@ -1117,30 +1123,30 @@ __global__ void __launch_bounds__(WF_BLOCK, DENSE ? SHADE_DENSE_BLOCKS :
                     sD = ray_offset(ls.P, ls.Ng) - sP;
                     sD = normalize_len(sD, &st_t);
                   }
-                  stage[0 * WF_BLOCK] = sP.x;
-                  stage[1 * WF_BLOCK] = sP.y;
-                  stage[2 * WF_BLOCK] = sP.z;
-                  stage[3 * WF_BLOCK] = st_t;
-                  stage[4 * WF_BLOCK] = sD.x;
-                  stage[5 * WF_BLOCK] = sD.y;
-                  stage[6 * WF_BLOCK] = sD.z;
-                  stage[7 * WF_BLOCK] = contribution.x;
-                  stage[8 * WF_BLOCK] = contribution.y;
-                  stage[9 * WF_BLOCK] = contribution.z;
-                  stage[10 * WF_BLOCK] = __int_as_float(
+                  stage[0 * BLOCK] = sP.x;
+                  stage[1 * BLOCK] = sP.y;
+                  stage[2 * BLOCK] = sP.z;
+                  stage[3 * BLOCK] = st_t;
+                  stage[4 * BLOCK] = sD.x;
+                  stage[5 * BLOCK] = sD.y;
+                  stage[6 * BLOCK] = sD.z;
+                  stage[7 * BLOCK] = contribution.x;
+                  stage[8 * BLOCK] = contribution.y;
+                  stage[9 * BLOCK] = contribution.z;
+                  stage[10 * BLOCK] = __int_as_float(
                       st.transparent_bounce | (st.bounce > 0 ? SH_INDIRECT_FLAG : 0));
                   if (PASSES) {
-                    stage[12 * WF_BLOCK] = part_b.x;
-                    stage[13 * WF_BLOCK] = part_b.y;
-                    stage[14 * WF_BLOCK] = part_b.z;
-                    stage[15 * WF_BLOCK] = shadow_add;
-                    stage[16 * WF_BLOCK] = part_c.x;
-                    stage[17 * WF_BLOCK] = part_c.y;
-                    stage[18 * WF_BLOCK] = part_c.z;
-                    stage[19 * WF_BLOCK] = (use_light_pass && st.bounce == 0) ? 1.0f : 0.0f;
-                    stage[20 * WF_BLOCK] = light_total.x;
-                    stage[21 * WF_BLOCK] = light_total.y;
-                    stage[22 * WF_BLOCK] = light_total.z;
+                    stage[12 * BLOCK] = part_b.x;
+                    stage[13 * BLOCK] = part_b.y;
+                    stage[14 * BLOCK] = part_b.z;
+                    stage[15 * BLOCK] = shadow_add;
+                    stage[16 * BLOCK] = part_c.x;
+                    stage[17 * BLOCK] = part_c.y;
+                    stage[18 * BLOCK] = part_c.z;
+                    stage[19 * BLOCK] = (use_light_pass && st.bounce == 0) ? 1.0f : 0.0f;
+                    stage[20 * BLOCK] = light_total.x;
+                    stage[21 * BLOCK] = light_total.y;
+                    stage[22 * BLOCK] = light_total.z;
                   }
                   want_shadow = true;
                 }
@@ -1260,7 +1266,7 @@ __global__ void __launch_bounds__(WF_BLOCK, DENSE ? SHADE_DENSE_BLOCKS :
       p.L[i] = make_float4(L.x, L.y, L.z, Lr.w);
     }
     unsigned int s_next, s_sh;
-    block_append2(&c->n_next, want_next, &c->n_shadow, want_shadow, &s_next, &s_sh);
+    block_append2<BLOCK / 32>(&c->n_next, want_next, &c->n_shadow, want_shadow, &s_next, &s_sh);
     if (want_next) {
       p.q_next[s_next] = i;
       p.nray_P_t[s_next] = out_ray_P;
@@ -1268,19 +1274,19 @@ __global__ void __launch_bounds__(WF_BLOCK, DENSE ? SHADE_DENSE_BLOCKS :
     }
     if (want_shadow) {
       p.q_shadow[s_sh] = i;
-      p.sh_P_t[s_sh] = make_float4(stage[0 * WF_BLOCK], stage[1 * WF_BLOCK], stage[2 * WF_BLOCK],
-                                   stage[3 * WF_BLOCK]);
-      p.sh_D[s_sh] = make_float4(stage[4 * WF_BLOCK], stage[5 * WF_BLOCK], stage[6 * WF_BLOCK],
+      p.sh_P_t[s_sh] = make_float4(stage[0 * BLOCK], stage[1 * BLOCK], stage[2 * BLOCK],
+                                   stage[3 * BLOCK]);
+      p.sh_D[s_sh] = make_float4(stage[4 * BLOCK], stage[5 * BLOCK], stage[6 * BLOCK],
                                  __uint_as_float(CY_PATH_RAY_SHADOW_OPAQUE));
-      p.sh_contrib[s_sh] = make_float4(stage[7 * WF_BLOCK], stage[8 * WF_BLOCK],
-                                       stage[9 * WF_BLOCK], stage[10 * WF_BLOCK]);
+      p.sh_contrib[s_sh] = make_float4(stage[7 * BLOCK], stage[8 * BLOCK],
+                                       stage[9 * BLOCK], stage[10 * BLOCK]);
       if (PASSES) {
         float4 *sp = p.sh_pass + SH_PASS_QUADS * (size_t)s_sh;
-        sp[0] = make_float4(stage[12 * WF_BLOCK], stage[13 * WF_BLOCK], stage[14 * WF_BLOCK],
-                            stage[15 * WF_BLOCK]);
-        sp[1] = make_float4(stage[16 * WF_BLOCK], stage[17 * WF_BLOCK], stage[18 * WF_BLOCK],
-                            stage[19 * WF_BLOCK]);
-        sp[2] = make_float4(stage[20 * WF_BLOCK], stage[21 * WF_BLOCK], stage[22 * WF_BLOCK],
+        sp[0] = make_float4(stage[12 * BLOCK], stage[13 * BLOCK], stage[14 * BLOCK],
+                            stage[15 * BLOCK]);
+        sp[1] = make_float4(stage[16 * BLOCK], stage[17 * BLOCK], stage[18 * BLOCK],
+                            stage[19 * BLOCK]);
+        sp[2] = make_float4(stage[20 * BLOCK], stage[21 * BLOCK], stage[22 * BLOCK],
                             0.0f);
       }
     }
@@ -2554,11 +2560,12 @@ static int shade_kernel_setup(b200_ctx *ctx)
                             (const void *)k_shade_surface<false, true, false, true>,
                             (const void *)k_shade_surface<true, true, false, true>};
   for (int k = 0; k < 6; k++) {
-    const size_t smem = (k == 3) ? SHADE_SMEM_BYTES_PASSES : SHADE_SMEM_BYTES;
+    const int block = (k >= 4) ? SHADE_WIDE_BLOCK : WF_BLOCK;
+    const size_t smem = (k == 3) ? SHADE_SMEM_BYTES_PASSES : SHADE_SMEM_BYTES_OF(block);
     CUDA_TRY(ctx, cudaFuncSetAttribute(kernels[k], cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
     int blocks = 0;
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernels[k], WF_BLOCK,
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernels[k], block,
                                                                 smem));
     if (blocks < 1)
       return fail(ctx, B200_ERR_CUDA, "surface-shading kernel does not fit on an SM");
@@ -2685,15 +2692,15 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
 
   /* one bounce of the whole batch: 8 launches, the head of the counters into the
    * iteration's ring slot, events around the three phases */
-  /* which register budget of the lean multiscatter kernel this batch runs (see
-   * and of the full kernel (see k_shade_surface, DENSE): forced, decided, or - while
-   * probing - alternating by batch */
-  bool shade_dense = false;
+  /* which block shape of the lean multiscatter kernel and of the full kernel this batch
+   * runs (see k_shade_surface, WIDE): forced, decided, or - while probing - alternating by
+   * batch */
+  bool shade_wide = false;
   auto enqueue_iteration = [&](const PathSoA &soa, int it) -> int {
     cudaEvent_t *ev = pool->ring_ev[it % WF_RING];
     const int grid_shade = ctx->num_sms *
-                           ctx->shade_blocks_per_sm[svm_ext ? (shade_dense ? 5 : 2) :
-                                                    (multiscatter ? (shade_dense ? 4 : 1) : 0)];
+                           ctx->shade_blocks_per_sm[svm_ext ? (shade_wide ? 5 : 2) :
+                                                    (multiscatter ? (shade_wide ? 4 : 1) : 0)];
     CUDA_TRY(ctx, cudaEventRecord(ev[0], st));
     if (count)
       k_intersect_closest<true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
@@ -2718,18 +2725,20 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
     }
     else if (svm_ext) {
       k_shade_background<true><<<grid_wide, WF_BLOCK, 0, st>>>(soa);
-      if (shade_dense)
+      if (shade_wide)
         k_shade_surface<true, true, false, true>
-            <<<grid_shade, WF_BLOCK, SHADE_SMEM_BYTES, st>>>(soa, num_keys);
+            <<<grid_shade, SHADE_WIDE_BLOCK, SHADE_SMEM_BYTES_OF(SHADE_WIDE_BLOCK), st>>>(
+                soa, num_keys);
       else
         k_shade_surface<true, true><<<grid_shade, WF_BLOCK, SHADE_SMEM_BYTES, st>>>(soa,
                                                                                     num_keys);
     }
     else {
       k_shade_background<false><<<grid_wide, WF_BLOCK, 0, st>>>(soa);
-      if (multiscatter && shade_dense)
+      if (multiscatter && shade_wide)
         k_shade_surface<false, true, false, true>
-            <<<grid_shade, WF_BLOCK, SHADE_SMEM_BYTES, st>>>(soa, num_keys);
+            <<<grid_shade, SHADE_WIDE_BLOCK, SHADE_SMEM_BYTES_OF(SHADE_WIDE_BLOCK), st>>>(
+                soa, num_keys);
       else if (multiscatter)
         k_shade_surface<false, true><<<grid_shade, WF_BLOCK, SHADE_SMEM_BYTES, st>>>(soa,
                                                                                      num_keys);
@@ -2884,21 +2893,21 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
       bp.pass_stride = pass_stride;
       bp.adaptive_aux = adaptive_aux;
 
-      /* kernels with a dense variant: the lean multiscatter one and the full one (not the
+      /* kernels with a wide variant: the lean multiscatter one and the full one (not the
        * lean GGX kernel - the cap lost on every scene measured - nor the passes kernel) */
       auto probe_kind = [&]() { return passes ? -1 : (svm_ext ? 1 : (multiscatter ? 0 : -1)); };
-      auto pick_budget = [&]() {
+      auto pick_shape = [&]() {
         const int kind = probe_kind();
         if (kind < 0)
-          shade_dense = false;
-        else if (ctx->opt_shade_dense >= 0)
-          shade_dense = ctx->opt_shade_dense != 0;
+          shade_wide = false;
+        else if (ctx->opt_shade_wide >= 0)
+          shade_wide = ctx->opt_shade_wide != 0;
         else if (ctx->shade_probe[kind].choice >= 0)
-          shade_dense = ctx->shade_probe[kind].choice != 0;
+          shade_wide = ctx->shade_probe[kind].choice != 0;
         else
-          shade_dense = (ctx->shade_probe[kind].batches++ & 1) != 0;
+          shade_wide = (ctx->shade_probe[kind].batches++ & 1) != 0;
       };
-      pick_budget();
+      pick_shape();
       const float shade_ms_before = shade_ms;
       for (int attempt = 0;; attempt++) {
         PathSoA soa = pool->soa;
@@ -2970,7 +2979,7 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
             return fail(ctx, B200_ERR_UNSUPPORTED, "SVM scope miss in the full kernels");
           svm_ext = true;
           ctx->force_svm_ext = true;
-          pick_budget();
+          pick_shape();
           continue;
         }
         if (adaptive)
@@ -2989,14 +2998,14 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
                                       st));
         CUDA_TRY(ctx, cudaGetLastError());
         stats.batches += 1;
-        if (probe_kind() >= 0 && ctx->opt_shade_dense < 0 &&
+        if (probe_kind() >= 0 && ctx->opt_shade_wide < 0 &&
             ctx->shade_probe[probe_kind()].choice < 0 && attempt == 0) {
           /* every iteration with work has been harvested when the bounce loop ends: the
-           * batch's shading time is complete.  Decide once both budgets have shaded 4 Mi
+           * batch's shading time is complete.  Decide once both shapes have shaded 4 Mi
            * paths; until then (small tiles) keep alternating. */
           b200_ctx::ShadeProbe &pr = ctx->shade_probe[probe_kind()];
-          const int v = shade_dense ? 1 : 0;
-          /* the first batch of each budget pays for loading its kernel: not counted */
+          const int v = shade_wide ? 1 : 0;
+          /* the first batch of each shape pays for loading its kernel: not counted */
           if (pr.batches > 2) {
             pr.ms[v] += (double)(shade_ms - shade_ms_before);
             pr.paths[v] += (double)npix * bp.nsamples;
@@ -3058,8 +3067,8 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
   stats.svm_extended = svm_ext ? 1 : 0;
   {
     const int kind = passes ? -1 : (svm_ext ? 1 : (multiscatter ? 0 : -1));
-    stats.shade_dense = kind < 0 ? 0 :
-                        (ctx->opt_shade_dense >= 0 ? (ctx->opt_shade_dense != 0) :
+    stats.shade_wide = kind < 0 ? 0 :
+                        (ctx->opt_shade_wide >= 0 ? (ctx->opt_shade_wide != 0) :
                                                      ctx->shade_probe[kind].choice);
   }
   ctx->stats = stats;

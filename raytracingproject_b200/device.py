@@ -64,7 +64,7 @@ class Stats(C.Structure):
                 ("svm_extended", C.c_uint64),
                 ("shade_ms", C.c_double), ("batches", C.c_uint64), ("iterations", C.c_uint64),
                 ("host_syncs", C.c_uint64), ("host_waits", C.c_uint64),
-                ("shade_dense", C.c_int64)]
+                ("shade_wide", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

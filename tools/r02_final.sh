@@ -23,7 +23,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_in
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_shade_surface --launch-count 2 \
   -o $R/${T}_shade_cornell -f python bench.py --workload cornell --spp 16 --steps 1 --warmup 0 $B > $O/${T}_ncu_a3.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_shade_surface --launch-count 2 \
-  -o $R/${T}_shade_cube_dense -f python bench.py --workload cube --spp 16 --steps 1 --warmup 0 --opt shade_dense=1 $B > $O/${T}_ncu_a4.log 2>&1
+  -o $R/${T}_shade_cube_dense -f python bench.py --workload cube --spp 16 --steps 1 --warmup 0 --opt shade_wide=1 $B > $O/${T}_ncu_a4.log 2>&1
 for n in closest_terrain closest_instanced shade_cornell shade_cube_dense; do
   python tools/ncu_summary.py $R/${T}_$n.ncu-rep > $O/${T}_prof_$n.txt 2>&1
   python tools/srclines.py $R/${T}_$n.ncu-rep 0 40 > $O/${T}_srclines_$n.txt 2>&1

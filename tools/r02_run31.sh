@@ -1,0 +1,9 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+for l in base wb384 wb512; do
+  lib=$PWD/raytracingproject_b200/_build/lib_$l.so
+  [ $l = base ] && lib=$PWD/raytracingproject_b200/libb200cycles.so
+  echo "== $l (shade_dense=0)"; SHADE_DENSE=0 B200_CYCLES_LIB=$lib timeout 300 python tools/shade_cap_ab.py 2>&1 | tail -5
+done
+echo "== terrain"
+BENCH_ARGS="--spp 64" tools/variants.sh run base wb384 wb512

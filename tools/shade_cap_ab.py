@@ -7,7 +7,7 @@ from raytracingproject_b200.device import B200Device
 from oracle import cycles_ref as ref
 
 W, H, SPP = 1920, 1080, 64
-MS = "Multiscatter GGX"
+MS = os.environ.get("DIST", "Multiscatter GGX")
 cases = {
     "cube_principled": scenes.default_cube(W, H, material="principled", distribution=MS),
     "cube_principled shallow (4 bounces)": scenes.default_cube(W, H, material="principled",
@@ -18,8 +18,8 @@ cases = {
     "cornell_glass(no metal)": scenes.cornell(W, H, materials="glass", distribution=MS),
 }
 dev = B200Device(0)
-if os.environ.get("SHADE_DENSE"):
-    dev.set_option("shade_dense", int(os.environ["SHADE_DENSE"]))
+if os.environ.get("SHADE_WIDE"):
+    dev.set_option("shade_wide", int(os.environ["SHADE_WIDE"]))
 for name, desc in cases.items():
     rs = ref.build_scene(desc)
     dev.upload_scene(rs.device_arrays(), rs.textures())
@@ -32,5 +32,5 @@ for name, desc in cases.items():
     rays = d["primary_rays"] + d["bounce_rays"] + d["shadow_rays"]
     print("%-34s device_ms %.1f  closest %.1f shade %.1f shadow %.1f  Mrays/s %.0f  ext=%d dense=%d" % (
         name, best, d["closest_ms"], d["shade_ms"], d["shadow_ms"], rays / best / 1e3,
-        d["svm_extended"], d.get("shade_dense", -9)))
+        d["svm_extended"], d.get("shade_wide", -9)))
     rs.close()

@@ -20,8 +20,8 @@ cases = {
     "cornell_textured": scenes.cornell(W, H, materials="textured3"),
 }
 dev = B200Device(0)
-if os.environ.get("SHADE_DENSE"):
-    dev.set_option("shade_dense", int(os.environ["SHADE_DENSE"]))
+if os.environ.get("SHADE_WIDE"):
+    dev.set_option("shade_wide", int(os.environ["SHADE_WIDE"]))
 for name, desc in cases.items():
     rs = ref.build_scene(desc)
     dev.upload_scene(rs.device_arrays(), rs.textures())
@@ -33,5 +33,5 @@ for name, desc in cases.items():
     rays = d["primary_rays"] + d["bounce_rays"] + d["shadow_rays"]
     print("%-28s device_ms %.1f  closest %.1f shade %.1f shadow %.1f  Mrays/s %.0f  ext=%d" % (
         name, best, d["closest_ms"], d["shade_ms"], d["shadow_ms"], rays / best / 1e3,
-        d["svm_extended"]) + " dense=%d" % d.get("shade_dense", -9))
+        d["svm_extended"]) + " dense=%d" % d.get("shade_wide", -9))
     rs.close()
