@@ -275,7 +275,8 @@ def control_of(agg, steps):
         "stream_syncs_per_step": agg["host_syncs"] / steps,
         "lagged_counter_reads_per_step": agg["host_waits"] / steps,
         # block shape of the lean multiscatter / full shading kernel the device settled on for
-        # this scene (-1 still probing, 0 = two blocks of 256 threads per SM, 1 = one of 512)
+        # this scene (-1 still probing, 0 = two blocks of 256 threads per SM, 1 = one of 512,
+        # 2 = one of 1024)
         "shade_wide": agg.get("shade_wide", 0),
         "share": {"intersect_closest": agg["closest_ms"] / dev_ms,
                   "sort_and_shade": agg["shade_ms"] / dev_ms,

@@ -89,7 +89,7 @@ typedef struct b200_stats {
   uint64_t host_waits;       /* waits on an iteration's counters while later work is queued */
   int64_t shade_wide;        /* block shape of the lean multiscatter / full shading kernel after
                                 this call: -1 still probing, 0 = two blocks of 256 threads per
-                                SM, 1 = one block of 512 */
+                                SM, 1 = one block of 512, 2 = one block of 1024 */
 } b200_stats;
 
 /* BVH8 build report (host builder). */
@@ -281,8 +281,9 @@ int b200_set_stream(b200_ctx *ctx, uint64_t cuda_stream);
 /* Tunables (0 keeps the default): "batch_paths" paths per wavefront batch,
  * "count_traversal" 1 = count BVH nodes / triangles per ray (slower),
  * "shade_wide" block shape of the lean multiscatter / the full shading kernel: -1 (default) =
- * time both on the first batches of a scene and keep the faster, 0 = two blocks of 256
- * threads per SM, 1 = one block of 512 (same arithmetic, same film either way). */
+ * time them on the first batches of a scene and keep the fastest, 0 = two blocks of 256
+ * threads per SM, 1 = one block of 512, 2 = one block of 1024 (same arithmetic, same film
+ * whichever runs). */
 int b200_set_option(b200_ctx *ctx, const char *name, int64_t value);
 
 #ifdef __cplusplus

@@ -90,18 +90,18 @@ struct b200_ctx {
 
   /* k_shade_surface<lean / lean + multi-scatter / full / full + render passes>: grid size
    * per SM */
-  int shade_blocks_per_sm[6] = {0, 0, 0, 0, 0, 0};
+  int shade_blocks_per_sm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   /* The lean multiscatter and the full shading kernels exist in two block shapes
-   * (wavefront.cuh, WIDE: one block of 512 threads per SM or two of 256).  Which one is
+   * (wavefront.cuh, WIDE: two blocks of 256 threads per SM, one of 512, one of 1024).  Which is
    * faster depends on the shader mix of the scene, so the first batches of a scene
    * alternate between them and the faster one is kept until the SVM programs change.  One
-   * probe per kernel kind (0 = lean multiscatter, 1 = full).  choice: -1 probing, 0 / 1
+   * probe per kernel kind (0 = lean multiscatter, 1 = full).  choice: -1 probing, 0 / 1 / 2
    * decided. */
-  int64_t opt_shade_wide = -1; /* -1 probe, 0 / 1 forced */
+  int64_t opt_shade_wide = -1; /* -1 probe, 0 / 1 / 2 forced */
   struct ShadeProbe {
     int choice = -1;
-    double ms[2] = {0.0, 0.0};
-    double paths[2] = {0.0, 0.0};
+    double ms[3] = {0.0, 0.0, 0.0};
+    double paths[3] = {0.0, 0.0, 0.0};
     uint64_t batches = 0;
   } shade_probe[2];
 

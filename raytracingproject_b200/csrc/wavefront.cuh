@@ -179,7 +179,7 @@ template<int NW = WF_BLOCK / 32>
 CY_DEV void block_append2(unsigned int *counter_a, bool pred_a, unsigned int *counter_b,
                           bool pred_b, unsigned int *slot_a, unsigned int *slot_b)
 {
-  static_assert(NW <= 16, "the two scans share one warp: at most 16 warps per block");
+  static_assert(NW <= 32, "one warp scans the per-warp counts of a queue");
   __shared__ unsigned int s_tab[2][NW];
   const unsigned int lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
   const unsigned int lt_mask = (1u << lane) - 1u;
@@ -190,21 +190,41 @@ CY_DEV void block_append2(unsigned int *counter_a, bool pred_a, unsigned int *co
     s_tab[1][w] = __popc(mb);
   }
   __syncthreads();
-  if (w == 0) {
-    /* lanes 0..NW-1 scan queue a, lanes 16..16+NW-1 queue b */
-    const unsigned int q = lane >> 4, j = lane & 15u;
+  if (NW <= 16) {
+    if (w == 0) {
+      /* lanes 0..NW-1 scan queue a, lanes 16..16+NW-1 queue b */
+      const unsigned int q = lane >> 4, j = lane & 15u;
+      const unsigned int v = (j < NW) ? s_tab[q][j] : 0u;
+      unsigned int inc = v;
+#pragma unroll
+      for (int o = 1; o < NW; o <<= 1) {
+        const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o, 16);
+        if (j >= (unsigned)o)
+          inc += u;
+      }
+      unsigned int base = 0;
+      if (j == NW - 1 && inc != 0u)
+        base = atomicAdd(q ? counter_b : counter_a, inc);
+      base = __shfl_sync(0xffffffffu, base, NW - 1, 16);
+      if (j < NW)
+        s_tab[q][j] = base + inc - v;
+    }
+  }
+  else if (w < 2) {
+    /* more than 16 warps: warp 0 scans queue a, warp 1 queue b */
+    const unsigned int q = w, j = lane;
     const unsigned int v = (j < NW) ? s_tab[q][j] : 0u;
     unsigned int inc = v;
 #pragma unroll
     for (int o = 1; o < NW; o <<= 1) {
-      const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o, 16);
+      const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o);
       if (j >= (unsigned)o)
         inc += u;
     }
     unsigned int base = 0;
     if (j == NW - 1 && inc != 0u)
       base = atomicAdd(q ? counter_b : counter_a, inc);
-    base = __shfl_sync(0xffffffffu, base, NW - 1, 16);
+    base = __shfl_sync(0xffffffffu, base, NW - 1);
     if (j < NW)
       s_tab[q][j] = base + inc - v;
   }
@@ -794,24 +814,26 @@ __global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(Pa
  * that follows does not carry them in registers; slots in the next-bounce and shadow
  * queues come from one block-wide reservation at the end of the round, after which the
  * staged record is copied out to its slot. */
-/* WIDE: the same code as ONE block of 512 threads per SM instead of two of 256 (128
- * registers either way).  Measured on B200 (profiles/r02r_shade_budget_ab.txt,
- * r02s_block_size_ab.txt): where every hit runs the multiscatter random walk the kernel
- * is bound by instruction fetch (684 KB - 1.1 MB of SASS against a 32 KB instruction
- * cache per SM; no_instruction stalls 10 per issue) - the block-wide barrier of the queue
- * append keeps the 16 warps of one block in the same stretch of code, two blocks run out
- * of phase and fetch twice: +28 % (lean) / +40 % (full) on the startup scene.  Where most
- * hits are plain diffuse the wider barrier costs 0-3 %.  The host times both on the first
- * batches of a scene and keeps the faster (b200_render, "shade_wide").  A tighter register
- * budget instead (3 blocks of 256 at 80 registers) gains as much on the startup scene on
- * a good run, but with a large run-to-run spread, and loses 14-25 % on the Cornell box. */
-#define SHADE_WIDE_BLOCK 512
-template<bool EXT, bool MS = EXT, bool PASSES = false, bool WIDE = false>
-__global__ void __launch_bounds__(WIDE ? SHADE_WIDE_BLOCK : WF_BLOCK,
+/* WIDE = 1 / 2: the same code as ONE block of 512 / 1024 threads per SM instead of two of
+ * 256.  Measured on B200 (profiles/r02r_shade_budget_ab.txt, r02s_block_size_ab.txt):
+ * where every hit runs the multiscatter random walk the kernel is bound by instruction
+ * fetch (684 KB - 1.1 MB of SASS against a 32 KB instruction cache per SM; no_instruction
+ * stalls 10 per issue) - the block-wide barrier of the queue append keeps the warps of one
+ * block in the same stretch of code, two blocks run out of phase and fetch twice.  512
+ * threads keep the 128 registers: +28 % (lean) / +32 % (full) on the startup scene, 0-3 %
+ * lost where most hits are plain diffuse.  1024 threads leave 64 registers: 32 warps share
+ * every fetch, another +10 % on the startup scene in spite of the spills, -15 % on the
+ * Cornell box.  The host times the shapes on the first batches of a scene and keeps the
+ * fastest (b200_render, "shade_wide").  A tighter register budget at 256 threads instead
+ * (3 blocks at 80 registers) gains as much on the startup scene on a good run, but with a
+ * large run-to-run spread, and loses 14-25 % on the Cornell box. */
+#define SHADE_BLOCK_OF(wide) ((wide) == 0 ? WF_BLOCK : ((wide) == 1 ? 512 : 1024))
+template<bool EXT, bool MS = EXT, bool PASSES = false, int WIDE = 0>
+__global__ void __launch_bounds__(SHADE_BLOCK_OF(WIDE),
                                   WIDE ? 1 : (EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_MIN_BLOCKS))
     k_shade_surface(PathSoA p, int num_keys)
 {
-  constexpr int BLOCK = WIDE ? SHADE_WIDE_BLOCK : WF_BLOCK;
+  constexpr int BLOCK = SHADE_BLOCK_OF(WIDE);
   extern __shared__ float s_shade[];
   float *const stage = s_shade + threadIdx.x;
   float4 arena_words[ARENA_QUADS];
@@ -2553,14 +2575,16 @@ static int shade_kernel_setup(b200_ctx *ctx)
   if (ctx->shade_blocks_per_sm[0] > 0)
     return B200_OK;
   DeviceGuard guard(ctx->ordinal);
-  const void *kernels[6] = {(const void *)k_shade_surface<false, false>,
+  const void *kernels[8] = {(const void *)k_shade_surface<false, false>,
                             (const void *)k_shade_surface<false, true>,
                             (const void *)k_shade_surface<true, true>,
                             (const void *)k_shade_surface<true, true, true>,
-                            (const void *)k_shade_surface<false, true, false, true>,
-                            (const void *)k_shade_surface<true, true, false, true>};
-  for (int k = 0; k < 6; k++) {
-    const int block = (k >= 4) ? SHADE_WIDE_BLOCK : WF_BLOCK;
+                            (const void *)k_shade_surface<false, true, false, 1>,
+                            (const void *)k_shade_surface<true, true, false, 1>,
+                            (const void *)k_shade_surface<false, true, false, 2>,
+                            (const void *)k_shade_surface<true, true, false, 2>};
+  for (int k = 0; k < 8; k++) {
+    const int block = (k < 4) ? WF_BLOCK : SHADE_BLOCK_OF(k < 6 ? 1 : 2);
     const size_t smem = (k == 3) ? SHADE_SMEM_BYTES_PASSES : SHADE_SMEM_BYTES_OF(block);
     CUDA_TRY(ctx, cudaFuncSetAttribute(kernels[k], cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
@@ -2695,12 +2719,14 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
   /* which block shape of the lean multiscatter kernel and of the full kernel this batch
    * runs (see k_shade_surface, WIDE): forced, decided, or - while probing - alternating by
    * batch */
-  bool shade_wide = false;
+  int shade_wide = 0;
   auto enqueue_iteration = [&](const PathSoA &soa, int it) -> int {
     cudaEvent_t *ev = pool->ring_ev[it % WF_RING];
     const int grid_shade = ctx->num_sms *
-                           ctx->shade_blocks_per_sm[svm_ext ? (shade_wide ? 5 : 2) :
-                                                    (multiscatter ? (shade_wide ? 4 : 1) : 0)];
+                           ctx->shade_blocks_per_sm[svm_ext ? (shade_wide ? 3 + 2 * shade_wide : 2) :
+                                                    (multiscatter ?
+                                                         (shade_wide ? 2 + 2 * shade_wide : 1) :
+                                                         0)];
     CUDA_TRY(ctx, cudaEventRecord(ev[0], st));
     if (count)
       k_intersect_closest<true><<<grid_trace, TRACE_BLOCK, 0, st>>>(soa, refill);
@@ -2725,9 +2751,13 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
     }
     else if (svm_ext) {
       k_shade_background<true><<<grid_wide, WF_BLOCK, 0, st>>>(soa);
-      if (shade_wide)
-        k_shade_surface<true, true, false, true>
-            <<<grid_shade, SHADE_WIDE_BLOCK, SHADE_SMEM_BYTES_OF(SHADE_WIDE_BLOCK), st>>>(
+      if (shade_wide == 2)
+        k_shade_surface<true, true, false, 2>
+            <<<grid_shade, SHADE_BLOCK_OF(2), SHADE_SMEM_BYTES_OF(SHADE_BLOCK_OF(2)), st>>>(
+                soa, num_keys);
+      else if (shade_wide == 1)
+        k_shade_surface<true, true, false, 1>
+            <<<grid_shade, SHADE_BLOCK_OF(1), SHADE_SMEM_BYTES_OF(SHADE_BLOCK_OF(1)), st>>>(
                 soa, num_keys);
       else
         k_shade_surface<true, true><<<grid_shade, WF_BLOCK, SHADE_SMEM_BYTES, st>>>(soa,
@@ -2735,9 +2765,13 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
     }
     else {
       k_shade_background<false><<<grid_wide, WF_BLOCK, 0, st>>>(soa);
-      if (multiscatter && shade_wide)
-        k_shade_surface<false, true, false, true>
-            <<<grid_shade, SHADE_WIDE_BLOCK, SHADE_SMEM_BYTES_OF(SHADE_WIDE_BLOCK), st>>>(
+      if (multiscatter && shade_wide == 2)
+        k_shade_surface<false, true, false, 2>
+            <<<grid_shade, SHADE_BLOCK_OF(2), SHADE_SMEM_BYTES_OF(SHADE_BLOCK_OF(2)), st>>>(
+                soa, num_keys);
+      else if (multiscatter && shade_wide == 1)
+        k_shade_surface<false, true, false, 1>
+            <<<grid_shade, SHADE_BLOCK_OF(1), SHADE_SMEM_BYTES_OF(SHADE_BLOCK_OF(1)), st>>>(
                 soa, num_keys);
       else if (multiscatter)
         k_shade_surface<false, true><<<grid_shade, WF_BLOCK, SHADE_SMEM_BYTES, st>>>(soa,
@@ -2899,13 +2933,13 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
       auto pick_shape = [&]() {
         const int kind = probe_kind();
         if (kind < 0)
-          shade_wide = false;
+          shade_wide = 0;
         else if (ctx->opt_shade_wide >= 0)
-          shade_wide = ctx->opt_shade_wide != 0;
+          shade_wide = (int)std::min<int64_t>(ctx->opt_shade_wide, 2);
         else if (ctx->shade_probe[kind].choice >= 0)
-          shade_wide = ctx->shade_probe[kind].choice != 0;
+          shade_wide = ctx->shade_probe[kind].choice;
         else
-          shade_wide = (ctx->shade_probe[kind].batches++ & 1) != 0;
+          shade_wide = (int)(ctx->shade_probe[kind].batches++ % 3);
       };
       pick_shape();
       const float shade_ms_before = shade_ms;
@@ -3004,15 +3038,20 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
            * batch's shading time is complete.  Decide once both shapes have shaded 4 Mi
            * paths; until then (small tiles) keep alternating. */
           b200_ctx::ShadeProbe &pr = ctx->shade_probe[probe_kind()];
-          const int v = shade_wide ? 1 : 0;
+          const int v = shade_wide;
           /* the first batch of each shape pays for loading its kernel: not counted */
-          if (pr.batches > 2) {
+          if (pr.batches > 3) {
             pr.ms[v] += (double)(shade_ms - shade_ms_before);
             pr.paths[v] += (double)npix * bp.nsamples;
           }
           const double enough = (double)(1 << 22);
-          if (pr.paths[0] >= enough && pr.paths[1] >= enough)
-            pr.choice = (pr.ms[1] / pr.paths[1] < pr.ms[0] / pr.paths[0]) ? 1 : 0;
+          if (pr.paths[0] >= enough && pr.paths[1] >= enough && pr.paths[2] >= enough) {
+            int best = 0;
+            for (int k = 1; k < 3; k++)
+              if (pr.ms[k] / pr.paths[k] < pr.ms[best] / pr.paths[best])
+                best = k;
+            pr.choice = best;
+          }
         }
         if (++batch_slot == WF_BATCH_SLOTS) {
           rc = sum_batch_stats();
@@ -3068,8 +3107,8 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
   {
     const int kind = passes ? -1 : (svm_ext ? 1 : (multiscatter ? 0 : -1));
     stats.shade_wide = kind < 0 ? 0 :
-                        (ctx->opt_shade_wide >= 0 ? (ctx->opt_shade_wide != 0) :
-                                                     ctx->shade_probe[kind].choice);
+                        (ctx->opt_shade_wide >= 0 ? std::min<int64_t>(ctx->opt_shade_wide, 2) :
+                                                     (int64_t)ctx->shade_probe[kind].choice);
   }
   ctx->stats = stats;
   return B200_OK;

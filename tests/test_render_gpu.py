@@ -601,9 +601,9 @@ def test_denoising_data_passes_match_reference(ref, device, name):
 @pytest.mark.parametrize("name", ["cube_principled_multiscatter",
                                   "cornell_principled_multiscatter"])
 def test_shading_block_shapes_render_the_same_film(ref, device, name):
-    """The lean multiscatter shading kernel exists in two block shapes (k_shade_surface
-    WIDE: one block of 512 threads per SM or two of 256); the device times both on the
-    first batches of a scene and keeps the faster.
+    """The lean multiscatter shading kernel exists in three block shapes (k_shade_surface
+    WIDE: two blocks of 256 threads per SM, one of 512, one of 1024); the device times them
+    on the first batches of a scene and keeps the fastest.
     Same code, same arithmetic: whichever runs, the film is bit-identical - forced either
     way, and while the probe alternates between them batch by batch."""
     from scene_cases import principled_cases
@@ -612,7 +612,7 @@ def test_shading_block_shapes_render_the_same_film(ref, device, name):
     try:
         device.upload_scene(rs.device_arrays())
         films = {}
-        for mode in (0, 1, -1):
+        for mode in (0, 1, 2, -1):
             device.set_option("shade_wide", mode)
             device.set_option("batch_paths", 0 if mode >= 0 else 1 << 16)
             films[mode] = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP)
@@ -620,8 +620,9 @@ def test_shading_block_shapes_render_the_same_film(ref, device, name):
             assert st["svm_extended"] == 0
             assert st["shade_wide"] == (mode if mode >= 0 else st["shade_wide"])
             if mode < 0:
-                assert st["batches"] >= 8   # the probe saw both shapes
+                assert st["batches"] >= 8   # the probe saw every shape
         assert np.array_equal(films[0], films[1])
+        assert np.array_equal(films[0], films[2])
         assert np.array_equal(films[0], films[-1])
         ref_img, _ = rs.render(0, SPP, tile_size=64)
         image_gates(ref_img, films[1], SPP, name + " wide")
@@ -638,14 +639,15 @@ def test_full_kernel_block_shapes_render_the_same_film(ref, device):
     try:
         device.upload_scene(rs.device_arrays())
         films = {}
-        for mode in (0, 1):
+        for mode in (0, 1, 2):
             device.set_option("shade_wide", mode)
             films[mode] = device.render(desc.width, desc.height, rs.pass_stride, 0, SPP)
             st = device.stats()
             assert st["svm_extended"] == 1 and st["shade_wide"] == mode
         # the AO and the light ray of a path are added with atomics, in either order
-        a, b = films[0][..., :3] / SPP, films[1][..., :3] / SPP
-        assert np.abs(a - b).max() <= 1e-5 * max(1.0, np.abs(a).max())
+        for mode in (1, 2):
+            a, b = films[0][..., :3] / SPP, films[mode][..., :3] / SPP
+            assert np.abs(a - b).max() <= 1e-5 * max(1.0, np.abs(a).max())
     finally:
         device.set_option("shade_wide", -1)
         rs.close()
