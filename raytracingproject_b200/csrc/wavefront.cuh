@@ -828,6 +828,11 @@ __global__ void __launch_bounds__(WF_BLOCK, BG_MIN_BLOCKS) k_shade_background(Pa
  * (3 blocks at 80 registers) gains as much on the startup scene on a good run, but with a
  * large run-to-run spread, and loses 14-25 % on the Cornell box. */
 #define SHADE_BLOCK_OF(wide) ((wide) == 0 ? WF_BLOCK : ((wide) == 1 ? 512 : 1024))
+/* the lean GGX kernel (368 KB) keeps two blocks of 256: a wide block lost 1-3 % on every
+ * scene measured (profiles/r02s_block_size_ab.txt); -DGGX_LEAN_SHAPE=1 / 2 for the A/B */
+#ifndef GGX_LEAN_SHAPE
+#  define GGX_LEAN_SHAPE 0
+#endif
 template<bool EXT, bool MS = EXT, bool PASSES = false, int WIDE = 0>
 __global__ void __launch_bounds__(SHADE_BLOCK_OF(WIDE),
                                   WIDE ? 1 : (EXT ? SHADE_MIN_BLOCKS_EXT : SHADE_MIN_BLOCKS))
@@ -2575,7 +2580,7 @@ static int shade_kernel_setup(b200_ctx *ctx)
   if (ctx->shade_blocks_per_sm[0] > 0)
     return B200_OK;
   DeviceGuard guard(ctx->ordinal);
-  const void *kernels[8] = {(const void *)k_shade_surface<false, false>,
+  const void *kernels[8] = {(const void *)k_shade_surface<false, false, false, GGX_LEAN_SHAPE>,
                             (const void *)k_shade_surface<false, true>,
                             (const void *)k_shade_surface<true, true>,
                             (const void *)k_shade_surface<true, true, true>,
@@ -2584,7 +2589,9 @@ static int shade_kernel_setup(b200_ctx *ctx)
                             (const void *)k_shade_surface<false, true, false, 2>,
                             (const void *)k_shade_surface<true, true, false, 2>};
   for (int k = 0; k < 8; k++) {
-    const int block = (k < 4) ? WF_BLOCK : SHADE_BLOCK_OF(k < 6 ? 1 : 2);
+    const int block = (k == 0) ? SHADE_BLOCK_OF(GGX_LEAN_SHAPE) :
+                      (k < 4)  ? WF_BLOCK :
+                                 SHADE_BLOCK_OF(k < 6 ? 1 : 2);
     const size_t smem = (k == 3) ? SHADE_SMEM_BYTES_PASSES : SHADE_SMEM_BYTES_OF(block);
     CUDA_TRY(ctx, cudaFuncSetAttribute(kernels[k], cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
@@ -2777,8 +2784,9 @@ int b200_render(b200_ctx *ctx, const b200_work_tile *tile, volatile const int *c
         k_shade_surface<false, true><<<grid_shade, WF_BLOCK, SHADE_SMEM_BYTES, st>>>(soa,
                                                                                      num_keys);
       else
-        k_shade_surface<false, false><<<grid_shade, WF_BLOCK, SHADE_SMEM_BYTES, st>>>(soa,
-                                                                                      num_keys);
+        k_shade_surface<false, false, false, GGX_LEAN_SHAPE>
+            <<<grid_shade, SHADE_BLOCK_OF(GGX_LEAN_SHAPE),
+               SHADE_SMEM_BYTES_OF(SHADE_BLOCK_OF(GGX_LEAN_SHAPE)), st>>>(soa, num_keys);
     }
     CUDA_TRY(ctx, cudaEventRecord(ev[2], st));
     if (passes && use_ao) /* AO never with transparent shadows (check_scope) */
